@@ -1,0 +1,255 @@
+/*
+ * b2rpc.h — C ABI of the B200-native brpc message-processing hot path.
+ *
+ * This is the drop-in boundary.  Every entry point names the
+ * reference interface it replaces (paths relative to the apache/brpc tree).
+ * Plain pointers and sizes only; no C++ / torch types cross this boundary.
+ * All compute runs in hand-written sm_100a CUDA kernels; there is no CPU
+ * fallback: every call fails with B2_E_NO_DEVICE when no CUDA device exists.
+ *
+ * Model.  The host messenger gathers, for each readable Socket, the bytes
+ * that are pending in its read buffer (reference: Socket::_read_buf filled by
+ * Socket::DoRead, src/brpc/socket.cpp:2042-2122) into one *batch*: a flat
+ * byte buffer plus one b2_run per socket.  One call cuts every run into
+ * messages exactly like InputMessenger::ProcessNewMessage
+ * (src/brpc/input_messenger.cpp:206-322) would, decodes the RpcMeta /
+ * StreamFrameMeta of each message, runs the registered device handler (echo)
+ * and packs the response frames (SendRpcResponse,
+ * src/brpc/policy/baidu_rpc_protocol.cpp:273-460).
+ */
+#ifndef B2RPC_H_
+#define B2RPC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes (never exceptions, never errno side channels) ---------- */
+#define B2_OK              0
+#define B2_E_INVAL        -1   /* bad argument */
+#define B2_E_NO_DEVICE    -2   /* CUDA device/driver missing: there is NO CPU path */
+#define B2_E_CUDA         -3   /* a CUDA call failed; see b2_last_error() */
+#define B2_E_CAPACITY     -4   /* batch exceeds a ctx capacity (bytes / msgs / resp) */
+#define B2_E_NOMEM        -5
+
+/* ---- ParseError, identical values to src/brpc/parse_result.h:25-32 ------- */
+#define B2_PARSE_OK                    0
+#define B2_PARSE_ERROR_TRY_OTHERS      1
+#define B2_PARSE_ERROR_NOT_ENOUGH_DATA 2
+#define B2_PARSE_ERROR_TOO_BIG_DATA    3
+#define B2_PARSE_ERROR_NO_RESOURCE     4
+#define B2_PARSE_ERROR_ABSOLUTELY_WRONG 5
+
+/* ---- ProtocolType subset, values of src/brpc/options.proto:38-67 --------- */
+#define B2_PROTOCOL_UNKNOWN       0
+#define B2_PROTOCOL_BAIDU_STD     1
+#define B2_PROTOCOL_STREAMING_RPC 2
+
+/* ---- CompressType / ChecksumType / ContentType, options.proto:69-88 ------ */
+#define B2_COMPRESS_TYPE_NONE   0
+#define B2_COMPRESS_TYPE_SNAPPY 1
+#define B2_COMPRESS_TYPE_GZIP   2
+#define B2_COMPRESS_TYPE_ZLIB   3
+#define B2_CHECKSUM_TYPE_NONE   0
+#define B2_CHECKSUM_TYPE_CRC32C 1
+#define B2_CONTENT_TYPE_PB      0
+
+/* ---- brpc error codes used in replies, src/brpc/errno.proto:25-49 -------- */
+#define B2_ENOSERVICE 1001
+#define B2_ENOMETHOD  1002
+#define B2_EREQUEST   1003
+
+/* ---- per-message disposition (b2_msg_desc.status) ------------------------ */
+#define B2_MSG_ECHOED        0  /* device handler ran, OK response packed            */
+#define B2_MSG_ERROR_REPLIED 1  /* error response packed on device (error_code != 0) */
+#define B2_MSG_HOST          2  /* valid request of a host-handled method; no reply  */
+#define B2_MSG_BAD_META      3  /* RpcMeta failed to parse: reference closes socket
+                                   with EREQUEST (baidu_rpc_protocol.cpp:577-582)   */
+#define B2_MSG_STREAM_FRAME  4  /* streaming_rpc frame, meta decoded, host routes it */
+#define B2_MSG_BAD_STREAM_META 5 /* StreamFrameMeta failed to parse: frame dropped
+                                   (streaming_rpc_protocol.cpp:97-100)              */
+#define B2_MSG_UNSUPPORTED   6  /* codec/content type outside this path (gzip, json) */
+
+/* ---- has_bits of b2_msg_desc --------------------------------------------- */
+#define B2_HAS_REQUEST          (1u << 0)
+#define B2_HAS_RESPONSE         (1u << 1)
+#define B2_HAS_COMPRESS_TYPE    (1u << 2)
+#define B2_HAS_CORRELATION_ID   (1u << 3)
+#define B2_HAS_ATTACHMENT_SIZE  (1u << 4)
+#define B2_HAS_CHUNK_INFO       (1u << 5)
+#define B2_HAS_AUTH_DATA        (1u << 6)
+#define B2_HAS_STREAM_SETTINGS  (1u << 7)
+#define B2_HAS_USER_FIELDS      (1u << 8)
+#define B2_HAS_CONTENT_TYPE     (1u << 9)
+#define B2_HAS_CHECKSUM_TYPE    (1u << 10)
+#define B2_HAS_CHECKSUM_VALUE   (1u << 11)
+#define B2_HAS_LOG_ID           (1u << 12)
+#define B2_HAS_TRACE_ID         (1u << 13)
+#define B2_HAS_REQUEST_ID       (1u << 14)
+#define B2_HAS_TIMEOUT_MS       (1u << 15)
+/* streaming_rpc frames reuse bits 0..4: */
+#define B2_SHAS_STREAM_ID        (1u << 0)
+#define B2_SHAS_SOURCE_STREAM_ID (1u << 1)
+#define B2_SHAS_FRAME_TYPE       (1u << 2)
+#define B2_SHAS_HAS_CONTINUATION (1u << 3)
+#define B2_SHAS_FEEDBACK         (1u << 4)
+#define B2_SVAL_HAS_CONTINUATION (1u << 8)  /* value of has_continuation */
+
+/*
+ * One socket's pending bytes inside the batch buffer.
+ * Reference: Socket::_read_buf + Socket::preferred_index()
+ * (src/brpc/socket.h:865-883).  `offset` must be a multiple of 16.
+ */
+typedef struct b2_run {
+    uint64_t socket_id;        /* opaque (SocketId); echoed back, never interpreted */
+    uint32_t offset;           /* byte offset of the run inside the batch buffer */
+    uint32_t length;           /* pending bytes of this socket */
+    int32_t  preferred_proto;  /* Socket::preferred_index(): B2_PROTOCOL_* or -1 */
+    uint32_t reserved;
+} b2_run;                      /* 24 bytes */
+
+/*
+ * Result of the cut loop for one run == what InputMessenger::ProcessNewMessage
+ * leaves behind on the Socket.
+ */
+typedef struct b2_run_status {
+    uint32_t consumed;         /* bytes cut off the front of the run (pop_front) */
+    uint32_t parse_error;      /* B2_PARSE_ERROR_* that ended the loop; anything
+                                  other than NOT_ENOUGH_DATA closes the socket
+                                  (input_messenger.cpp:227-239) */
+    uint32_t n_msgs;           /* messages cut (Socket::AddInputMessages) */
+    uint32_t first_msg;        /* index of this run's first b2_msg_desc */
+    int32_t  preferred_proto;  /* Socket::preferred_index() after the loop */
+    uint32_t reserved0;        /* (the _avg_msg_size read-size hint, input_messenger.cpp:242-261,
+                                  stays on the host: it is consumed / n_msgs smoothed) */
+    uint32_t resp_off;         /* first response byte of this run in the resp region */
+    uint32_t resp_bytes;       /* span (incl. alignment padding) of this run's responses */
+} b2_run_status;               /* 32 bytes */
+
+/*
+ * One cut message == MostCommonMessage (policy/most_common_message.h:33-49)
+ * + the decoded RpcMeta (policy/baidu_rpc_meta.proto:26-55)
+ * + where its response frame was packed.  Exactly 64 bytes, written once by
+ * the device.  For B2_PROTOCOL_STREAMING_RPC frames: correlation_id =
+ * StreamFrameMeta.stream_id, log_id = source_stream_id, compress_type =
+ * frame_type, attachment_size = low 32 bits of feedback.consumed_size,
+ * checksum_type = high 32 bits of it.
+ */
+typedef struct b2_msg_desc {
+    uint32_t run_idx;          /* index of the b2_run this message was cut from */
+    uint32_t frame_off;        /* offset of the 12-byte header in the batch buffer */
+    uint32_t body_size;        /* header: meta + payload (+attachment) bytes */
+    uint32_t meta_size;        /* header: RpcMeta bytes */
+    int64_t  correlation_id;
+    int64_t  log_id;
+    int32_t  attachment_size;
+    int32_t  compress_type;
+    int32_t  checksum_type;
+    int32_t  error_code;       /* brpc error code carried by the reply (0 = OK) */
+    uint16_t has_bits;         /* B2_HAS_* */
+    uint8_t  protocol;         /* B2_PROTOCOL_* */
+    uint8_t  content_type;
+    int16_t  method_idx;       /* registered method index, -1 = not found */
+    uint16_t status;           /* B2_MSG_* */
+    uint32_t resp_off;         /* offset of the reply frame in the resp region */
+    uint32_t resp_len;         /* bytes of the reply frame (0 = none) */
+} b2_msg_desc;                 /* 64 bytes */
+
+/* device handler kinds for b2_register_method */
+#define B2_HANDLER_HOST 0      /* descriptor only: user code runs on the host */
+#define B2_HANDLER_ECHO 1      /* example::EchoService::Echo, example/echo_c++/server.cpp:44-84 */
+
+typedef struct b2_method {
+    const char* service_full_name;  /* "example.EchoService" */
+    const char* service_name;       /* "EchoService" (jprotobuf short name,
+                                       baidu_rpc_protocol.cpp:738-748) */
+    const char* method_name;        /* "Echo" */
+    const char* request_type_name;  /* "example.EchoRequest" (used in EREQUEST text) */
+    int32_t handler;                /* B2_HANDLER_* */
+    int32_t echo_attachment;        /* -echo_attachment (server.cpp:31) */
+    int32_t response_checksum_type; /* -enable_checksum -> CRC32C (server.cpp:80-82) */
+    int32_t response_compress_type; /* cntl->set_response_compress_type() */
+} b2_method;
+
+typedef struct b2_options {
+    int32_t  device;           /* CUDA ordinal */
+    uint32_t max_batch_bytes;  /* capacity of the device batch buffer */
+    uint32_t max_msgs;         /* capacity of the descriptor array */
+    uint32_t max_runs;
+    uint32_t max_resp_bytes;   /* capacity of the response region (0 = derive) */
+    uint32_t tile_bytes;       /* speculative scan tile, power of two (0 = default) */
+    uint64_t max_body_size;    /* FLAGS_max_body_size (protocol.cpp:52), 0 = 64 MiB */
+} b2_options;
+
+/* Pointers into ctx-owned PINNED host memory, valid until the next batch call. */
+typedef struct b2_batch_result {
+    const b2_run_status* runs;     uint32_t n_runs;
+    const b2_msg_desc*   msgs;     uint32_t n_msgs;
+    const uint8_t*       resp;     uint32_t resp_bytes;   /* span of the resp region used */
+    float kernel_ms;               /* device time of the kernels (CUDA events) */
+    uint32_t n_launches;           /* kernels launched for this batch */
+} b2_batch_result;
+
+typedef struct b2_ctx b2_ctx;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+int  b2_ctx_create(const b2_options* opt, b2_ctx** out);
+void b2_ctx_destroy(b2_ctx* ctx);
+const char* b2_last_error(void);        /* thread-local text of the last failure */
+const char* b2_version(void);
+
+/* Replaces Server::AddService's method map used by ProcessRpcRequest
+ * (FindMethodPropertyByFullName, baidu_rpc_protocol.cpp:749-756).
+ * Returns the method index (>= 0) or a negative B2_E_*. */
+int  b2_register_method(b2_ctx* ctx, const b2_method* m);
+
+/* ---- block pool: assignable to butil::iobuf::blockmem_allocate/deallocate
+ * (src/butil/iobuf.cpp:168-169), same role as rdma::block_pool
+ * (src/brpc/rdma/rdma_helper.cpp:579-582).  Memory is cudaHostAlloc'ed. ------ */
+void* b2_block_alloc(size_t size);
+void  b2_block_free(void* p);
+
+/* ---- the hot path, host-facing (H2D + kernels + D2H inside) ---------------
+ * Replaces, for every run: InputMessenger::ProcessNewMessage
+ * (input_messenger.cpp:206-322) -> CutInputMessage (:84-179) ->
+ * ParseRpcMessage / ParseStreamingMessage -> ProcessRpcRequest
+ * (baidu_rpc_protocol.cpp:568-866) -> SendRpcResponse (:273-460).
+ * `bytes` may be any host memory (pinned memory from b2_block_alloc avoids a
+ * staging copy). */
+int  b2_process_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
+                      const b2_run* runs, uint32_t n_runs, b2_batch_result* out);
+
+/* ---- the same path split in three, for measurement with inputs resident in
+ * HBM (bench.py `value`): upload once, execute many times, download. -------- */
+int  b2_batch_upload(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
+                     const b2_run* runs, uint32_t n_runs);
+int  b2_batch_execute(b2_ctx* ctx, float* kernel_ms, uint32_t* n_launches);
+int  b2_batch_download(b2_ctx* ctx, b2_batch_result* out);
+
+/* Device time of each stage of the last execute, in launch order.  Writes up to
+ * `cap` entries of (name, ms); returns the number of stages. */
+int  b2_stage_times(b2_ctx* ctx, const char** names, float* ms, int cap);
+
+/* ---- leaf codecs on device-resident or host buffers ----------------------
+ * b2_crc32c_batch: one CRC-32C per (offset,length) slice == butil::crc32c::Value
+ * (src/butil/crc32c.h:30-33) on each slice; out[i] is the UNMASKED crc. */
+int  b2_crc32c_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
+                     const uint32_t* offs, const uint32_t* lens, uint32_t n,
+                     uint32_t* out);
+
+/* ---- counters (bvar::Adder-like): per-GPU totals accumulated by
+ * the kernels: [0] in_bytes [1] in_msgs [2] out_bytes [3] out_msgs [4] errors
+ * [5] batches [6..7] reserved.  The cross-GPU reduce is an NCCL all-reduce on
+ * this int64[8] done by the caller's communicator. -------------------------- */
+#define B2_N_COUNTERS 8
+int  b2_counters_read(b2_ctx* ctx, int64_t out[B2_N_COUNTERS]);
+/* device pointer of the int64[8] (for ncclAllReduce / torch.distributed) */
+void* b2_counters_device_ptr(b2_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* B2RPC_H_ */

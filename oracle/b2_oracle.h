@@ -1,0 +1,119 @@
+/*
+ * b2_oracle.h — CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C restatement of apache/brpc's message-processing hot path, written
+ * function by function from the reference sources (each function cites the
+ * file:line it follows).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library; the product
+ * (brpc_b200/libb2rpc.so) never links, imports or calls it.
+ *
+ * Parity pinning: CRC-32C is pinned by the RFC 3720 vectors of
+ * test/crc32c_unittest.cc:18-71 and against the reference's own crc32c.cc
+ * compiled into oracle/_ref; the protobuf wire codec (libprotobuf is a
+ * third-party dependency absent from /root/reference, pinned 27.3 in
+ * MODULE.bazel:11) is pinned by tests/golden/*.json generated with
+ * python-protobuf from the reference's .proto files (tests/golden/gen_golden.py).
+ * The reference's tests hold NO golden baidu_std wire bytes, so
+ * frame-level parity is pinned by those fixtures, not by reference test vectors.
+ */
+#ifndef B2_ORACLE_H_
+#define B2_ORACLE_H_
+#include <stddef.h>
+#include <stdint.h>
+#include "../include/b2rpc.h"   /* ABI structs only (b2_run, b2_msg_desc, ...) */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_span { uint32_t off; uint32_t len; } orc_span; /* relative to meta start */
+
+/* Decoded brpc.policy.RpcMeta (policy/baidu_rpc_meta.proto:26-55). */
+typedef struct orc_rpc_meta {
+    uint32_t has;                 /* B2_HAS_* */
+    /* RpcRequestMeta */
+    int      has_service_name, has_method_name;
+    orc_span service_name, method_name, request_id;
+    int64_t  log_id, trace_id, span_id, parent_span_id;
+    int      has_span_id, has_parent_span_id;
+    int32_t  timeout_ms;
+    /* RpcResponseMeta */
+    int      has_error_code, has_error_text;
+    int32_t  error_code;
+    orc_span error_text;
+    int32_t  compress_type;
+    int64_t  correlation_id;
+    int32_t  attachment_size;
+    int      chunk_has_stream_id, chunk_has_chunk_id;
+    orc_span authentication_data;
+    int      ss_has_stream_id;
+    int64_t  ss_stream_id;
+    int      ss_need_feedback, ss_writable;
+    uint32_t ss_n_extra;
+    uint32_t n_user_fields;       /* map entries seen on the wire */
+    int32_t  content_type;
+    int32_t  checksum_type;
+    orc_span checksum_value;
+} orc_rpc_meta;
+
+/* Decoded brpc.StreamFrameMeta (streaming_rpc_meta.proto:39-49). */
+typedef struct orc_stream_meta {
+    uint32_t has;                 /* B2_SHAS_* | B2_SVAL_HAS_CONTINUATION */
+    int64_t  stream_id, source_stream_id, consumed_size;
+    int32_t  frame_type;
+    int      feedback_has_consumed_size;
+} orc_stream_meta;
+
+typedef struct orc_config {
+    uint64_t max_body_size;       /* FLAGS_max_body_size, protocol.cpp:52 */
+    const char* server_identity;  /* "ip:port" of Controller::AppendServerIdentiy, or NULL */
+    const b2_method* methods; uint32_t n_methods;
+} orc_config;
+
+/* ---- leaf codecs ---------------------------------------------------------- */
+uint32_t orc_crc32c_extend(uint32_t init_crc, const void* data, size_t n); /* crc32c.cc:379-454 */
+uint32_t orc_crc32c_mask(uint32_t crc);                                      /* crc32c.h:38-41 */
+uint32_t orc_crc32c_unmask(uint32_t masked);                                 /* crc32c.h:44-47 */
+
+/* ---- protobuf wire decode of the path's messages --------------------------
+ * return 1 = ParsePbFromIOBuf succeeded (protocol.cpp:236-239), 0 = failed. */
+int orc_parse_rpc_meta(const uint8_t* p, size_t n, orc_rpc_meta* out);
+int orc_parse_stream_meta(const uint8_t* p, size_t n, orc_stream_meta* out);
+/* EchoRequest (example/echo_c++/echo.proto:23-25): span of `message` rel. to p */
+int orc_parse_echo_request(const uint8_t* p, size_t n, orc_span* message);
+
+/* ---- encoders (client mirror; used by tests to build traffic) -------------
+ * PackRpcRequest (baidu_rpc_protocol.cpp:1045-1133) for an EchoRequest;
+ * returns frame length written to out (cap must be large enough). */
+typedef struct orc_request_spec {
+    const char* service_name; const char* method_name;
+    int has_log_id; int64_t log_id;
+    int64_t correlation_id;
+    int32_t compress_type, checksum_type, content_type;
+    const uint8_t* message; uint32_t message_len;
+    const uint8_t* attachment; uint32_t attachment_len;
+    int has_trace; int64_t trace_id, span_id, parent_span_id;
+    const char* request_id;       /* NULL = unset */
+    int32_t timeout_ms;           /* 0 = unset */
+} orc_request_spec;
+size_t orc_pack_echo_request(const orc_request_spec* s, uint8_t* out, size_t cap);
+/* PackStreamMessage (streaming_rpc_protocol.cpp:42-58), DATA frame */
+size_t orc_pack_stream_frame(int64_t stream_id, int64_t source_stream_id, int frame_type,
+                             int has_continuation, int cont_value,
+                             const uint8_t* data, uint32_t data_len, uint8_t* out, size_t cap);
+
+/* ---- the whole path over one batch ----------------------------------------
+ * For every run: the ProcessNewMessage cut loop, ProcessRpcRequest, the echo
+ * service, SendRpcResponse.  Responses are packed back to back (no padding) in
+ * message order into resp; msgs[i].resp_off/resp_len index it.
+ * Returns 0, or -1 when a capacity is exceeded. */
+int orc_process_batch(const orc_config* cfg, const uint8_t* bytes, uint32_t nbytes,
+                      const b2_run* runs, uint32_t n_runs,
+                      b2_run_status* run_status,
+                      b2_msg_desc* msgs, uint32_t msg_cap, uint32_t* n_msgs,
+                      uint8_t* resp, uint32_t resp_cap, uint32_t* resp_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,169 @@
+"""ctypes binding of oracle/liboracle.so (CPU ORACLE — tests only)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+lib = C.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+
+
+class Span(C.Structure):
+    _fields_ = [("off", C.c_uint32), ("len", C.c_uint32)]
+
+
+class RpcMeta(C.Structure):
+    _fields_ = [("has", C.c_uint32),
+                ("has_service_name", C.c_int), ("has_method_name", C.c_int),
+                ("service_name", Span), ("method_name", Span), ("request_id", Span),
+                ("log_id", C.c_int64), ("trace_id", C.c_int64), ("span_id", C.c_int64), ("parent_span_id", C.c_int64),
+                ("has_span_id", C.c_int), ("has_parent_span_id", C.c_int),
+                ("timeout_ms", C.c_int32),
+                ("has_error_code", C.c_int), ("has_error_text", C.c_int),
+                ("error_code", C.c_int32), ("error_text", Span),
+                ("compress_type", C.c_int32), ("correlation_id", C.c_int64), ("attachment_size", C.c_int32),
+                ("chunk_has_stream_id", C.c_int), ("chunk_has_chunk_id", C.c_int),
+                ("authentication_data", Span),
+                ("ss_has_stream_id", C.c_int), ("ss_stream_id", C.c_int64),
+                ("ss_need_feedback", C.c_int), ("ss_writable", C.c_int),
+                ("ss_n_extra", C.c_uint32), ("n_user_fields", C.c_uint32),
+                ("content_type", C.c_int32), ("checksum_type", C.c_int32), ("checksum_value", Span)]
+
+
+class StreamMeta(C.Structure):
+    _fields_ = [("has", C.c_uint32), ("stream_id", C.c_int64), ("source_stream_id", C.c_int64),
+                ("consumed_size", C.c_int64), ("frame_type", C.c_int32), ("feedback_has_consumed_size", C.c_int)]
+
+
+class Method(C.Structure):
+    _fields_ = [("service_full_name", C.c_char_p), ("service_name", C.c_char_p), ("method_name", C.c_char_p),
+                ("request_type_name", C.c_char_p), ("handler", C.c_int32), ("echo_attachment", C.c_int32),
+                ("response_checksum_type", C.c_int32), ("response_compress_type", C.c_int32)]
+
+
+class Config(C.Structure):
+    _fields_ = [("max_body_size", C.c_uint64), ("server_identity", C.c_char_p),
+                ("methods", C.POINTER(Method)), ("n_methods", C.c_uint32)]
+
+
+class RequestSpec(C.Structure):
+    _fields_ = [("service_name", C.c_char_p), ("method_name", C.c_char_p),
+                ("has_log_id", C.c_int), ("log_id", C.c_int64), ("correlation_id", C.c_int64),
+                ("compress_type", C.c_int32), ("checksum_type", C.c_int32), ("content_type", C.c_int32),
+                ("message", C.c_char_p), ("message_len", C.c_uint32),
+                ("attachment", C.c_char_p), ("attachment_len", C.c_uint32),
+                ("has_trace", C.c_int), ("trace_id", C.c_int64), ("span_id", C.c_int64), ("parent_span_id", C.c_int64),
+                ("request_id", C.c_char_p), ("timeout_ms", C.c_int32)]
+
+
+RUN_DT = np.dtype([("socket_id", "<u8"), ("offset", "<u4"), ("length", "<u4"),
+                   ("preferred_proto", "<i4"), ("reserved", "<u4")])
+RUN_STATUS_DT = np.dtype([("consumed", "<u4"), ("parse_error", "<u4"), ("n_msgs", "<u4"), ("first_msg", "<u4"),
+                          ("preferred_proto", "<i4"), ("reserved0", "<u4"), ("resp_off", "<u4"), ("resp_bytes", "<u4")])
+MSG_DT = np.dtype([("run_idx", "<u4"), ("frame_off", "<u4"), ("body_size", "<u4"), ("meta_size", "<u4"),
+                   ("correlation_id", "<i8"), ("log_id", "<i8"),
+                   ("attachment_size", "<i4"), ("compress_type", "<i4"), ("checksum_type", "<i4"), ("error_code", "<i4"),
+                   ("has_bits", "<u2"), ("protocol", "u1"), ("content_type", "u1"),
+                   ("method_idx", "<i2"), ("status", "<u2"), ("resp_off", "<u4"), ("resp_len", "<u4")])
+assert RUN_DT.itemsize == 24 and RUN_STATUS_DT.itemsize == 32 and MSG_DT.itemsize == 64
+
+lib.orc_crc32c_extend.restype = C.c_uint32
+lib.orc_crc32c_extend.argtypes = [C.c_uint32, C.c_char_p, C.c_size_t]
+lib.orc_crc32c_mask.restype = C.c_uint32; lib.orc_crc32c_mask.argtypes = [C.c_uint32]
+lib.orc_crc32c_unmask.restype = C.c_uint32; lib.orc_crc32c_unmask.argtypes = [C.c_uint32]
+lib.orc_parse_rpc_meta.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(RpcMeta)]
+lib.orc_parse_stream_meta.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(StreamMeta)]
+lib.orc_parse_echo_request.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(Span)]
+lib.orc_pack_echo_request.restype = C.c_size_t
+lib.orc_pack_echo_request.argtypes = [C.POINTER(RequestSpec), C.c_void_p, C.c_size_t]
+lib.orc_pack_stream_frame.restype = C.c_size_t
+lib.orc_pack_stream_frame.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_uint32, C.c_void_p, C.c_size_t]
+lib.orc_process_batch.argtypes = [C.POINTER(Config), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                  C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+lib.orc_have_ref.restype = C.c_int
+
+
+def crc32c(b, init=0):
+    return lib.orc_crc32c_extend(init, bytes(b), len(b))
+
+
+def parse_rpc_meta(b):
+    m = RpcMeta()
+    ok = lib.orc_parse_rpc_meta(bytes(b), len(b), C.byref(m))
+    return bool(ok), m
+
+
+def parse_stream_meta(b):
+    m = StreamMeta()
+    ok = lib.orc_parse_stream_meta(bytes(b), len(b), C.byref(m))
+    return bool(ok), m
+
+
+def parse_echo_request(b):
+    s = Span()
+    ok = lib.orc_parse_echo_request(bytes(b), len(b), C.byref(s))
+    return bool(ok), (s.off, s.len)
+
+
+def pack_echo_request(service=b"example.EchoService", method=b"Echo", log_id=None, correlation_id=0,
+                      compress_type=0, checksum_type=0, content_type=0, message=b"", attachment=b"",
+                      trace=None, request_id=None, timeout_ms=0):
+    s = RequestSpec()
+    s.service_name, s.method_name = service, method
+    s.has_log_id, s.log_id = (0, 0) if log_id is None else (1, log_id)
+    s.correlation_id = correlation_id
+    s.compress_type, s.checksum_type, s.content_type = compress_type, checksum_type, content_type
+    s.message, s.message_len = message, len(message)
+    s.attachment, s.attachment_len = attachment, len(attachment)
+    if trace:
+        s.has_trace, s.trace_id, s.span_id, s.parent_span_id = 1, trace[0], trace[1], trace[2]
+    s.request_id = request_id
+    s.timeout_ms = timeout_ms
+    cap = 2048 + len(message) + len(message) // 5 + len(attachment)
+    buf = C.create_string_buffer(cap)
+    n = lib.orc_pack_echo_request(C.byref(s), buf, cap)
+    assert n > 0, "orc_pack_echo_request failed"
+    return buf.raw[:n]
+
+
+def pack_stream_frame(stream_id, source_stream_id=-1, frame_type=3, has_continuation=None, data=b""):
+    cap = 128 + len(data)
+    buf = C.create_string_buffer(cap)
+    n = lib.orc_pack_stream_frame(stream_id, source_stream_id, frame_type,
+                                  0 if has_continuation is None else 1, 1 if has_continuation else 0,
+                                  data, len(data), buf, cap)
+    assert n > 0
+    return buf.raw[:n]
+
+
+ECHO_METHOD = dict(service_full_name=b"example.EchoService", service_name=b"EchoService", method_name=b"Echo",
+                   request_type_name=b"example.EchoRequest", handler=1, echo_attachment=1,
+                   response_checksum_type=0, response_compress_type=0)
+
+
+def make_config(methods=None, max_body_size=0, server_identity=None):
+    methods = [ECHO_METHOD] if methods is None else methods
+    arr = (Method * max(1, len(methods)))()
+    for i, m in enumerate(methods):
+        for k, v in m.items():
+            setattr(arr[i], k, v)
+    cfg = Config(max_body_size, server_identity, arr, len(methods))
+    cfg._keep = arr
+    return cfg
+
+
+def process_batch(cfg, data, runs, msg_cap=None, resp_cap=None):
+    """data: bytes/np.uint8 array; runs: np array RUN_DT.  Returns (run_status, msgs, resp)."""
+    data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+    runs = np.ascontiguousarray(runs)
+    n_runs = len(runs)
+    msg_cap = msg_cap or (len(data) // 12 + 16)
+    resp_cap = resp_cap or (len(data) * 2 + 4096 * max(1, msg_cap // 8) + (1 << 16))
+    rs = np.zeros(n_runs, dtype=RUN_STATUS_DT)
+    msgs = np.zeros(msg_cap, dtype=MSG_DT)
+    resp = np.zeros(resp_cap, dtype=np.uint8)
+    nm, rb = C.c_uint32(0), C.c_uint32(0)
+    rc = lib.orc_process_batch(C.byref(cfg), data.ctypes.data, len(data), runs.ctypes.data, n_runs, rs.ctypes.data,
+                               msgs.ctypes.data, msg_cap, C.byref(nm), resp.ctypes.data, resp_cap, C.byref(rb))
+    assert rc == 0, "oracle capacity exceeded"
+    return rs, msgs[:nm.value], resp[:rb.value]
