@@ -1,0 +1,212 @@
+"""ctypes binding of include/b2rpc.h (brpc_b200/libb2rpc.so)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "libb2rpc.so")
+
+B2_OK, B2_E_INVAL, B2_E_NO_DEVICE, B2_E_CUDA, B2_E_CAPACITY, B2_E_NOMEM = 0, -1, -2, -3, -4, -5
+
+RUN_DT = np.dtype([("socket_id", "<u8"), ("offset", "<u4"), ("length", "<u4"),
+                   ("preferred_proto", "<i4"), ("reserved", "<u4")])
+RUN_STATUS_DT = np.dtype([("consumed", "<u4"), ("parse_error", "<u4"), ("n_msgs", "<u4"), ("first_msg", "<u4"),
+                          ("preferred_proto", "<i4"), ("reserved0", "<u4"), ("resp_off", "<u4"), ("resp_bytes", "<u4")])
+MSG_DT = np.dtype([("run_idx", "<u4"), ("frame_off", "<u4"), ("body_size", "<u4"), ("meta_size", "<u4"),
+                   ("correlation_id", "<i8"), ("log_id", "<i8"),
+                   ("attachment_size", "<i4"), ("compress_type", "<i4"), ("checksum_type", "<i4"), ("error_code", "<i4"),
+                   ("has_bits", "<u2"), ("protocol", "u1"), ("content_type", "u1"),
+                   ("method_idx", "<i2"), ("status", "<u2"), ("resp_off", "<u4"), ("resp_len", "<u4")])
+assert RUN_DT.itemsize == 24 and RUN_STATUS_DT.itemsize == 32 and MSG_DT.itemsize == 64
+
+
+class Method(C.Structure):
+    _fields_ = [("service_full_name", C.c_char_p), ("service_name", C.c_char_p), ("method_name", C.c_char_p),
+                ("request_type_name", C.c_char_p), ("handler", C.c_int32), ("echo_attachment", C.c_int32),
+                ("response_checksum_type", C.c_int32), ("response_compress_type", C.c_int32)]
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int32), ("max_batch_bytes", C.c_uint32), ("max_msgs", C.c_uint32),
+                ("max_runs", C.c_uint32), ("max_resp_bytes", C.c_uint32), ("tile_bytes", C.c_uint32),
+                ("max_body_size", C.c_uint64)]
+
+
+class BatchResult(C.Structure):
+    _fields_ = [("runs", C.c_void_p), ("n_runs", C.c_uint32),
+                ("msgs", C.c_void_p), ("n_msgs", C.c_uint32),
+                ("resp", C.c_void_p), ("resp_bytes", C.c_uint32),
+                ("kernel_ms", C.c_float), ("n_launches", C.c_uint32)]
+
+
+class B2Error(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("b2rpc error %d: %s" % (code, text))
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(lib_path):
+        raise ImportError("brpc_b200/libb2rpc.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a).  There is no CPU fallback.")
+    l = C.CDLL(lib_path)
+    l.b2_last_error.restype = C.c_char_p
+    l.b2_version.restype = C.c_char_p
+    l.b2_ctx_create.argtypes = [C.POINTER(Options), C.POINTER(C.c_void_p)]
+    l.b2_ctx_destroy.argtypes = [C.c_void_p]
+    l.b2_register_method.argtypes = [C.c_void_p, C.POINTER(Method)]
+    l.b2_set_server_identity.argtypes = [C.c_void_p, C.c_char_p]
+    l.b2_block_alloc.restype = C.c_void_p; l.b2_block_alloc.argtypes = [C.c_size_t]
+    l.b2_block_free.argtypes = [C.c_void_p]
+    l.b2_process_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(BatchResult)]
+    l.b2_batch_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    l.b2_batch_execute.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+    l.b2_batch_download.argtypes = [C.c_void_p, C.POINTER(BatchResult)]
+    l.b2_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    l.b2_crc32c_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    l.b2_counters_read.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    l.b2_counters_device_ptr.restype = C.c_void_p; l.b2_counters_device_ptr.argtypes = [C.c_void_p]
+    return l
+
+
+lib = _load()
+
+# every symbol include/b2rpc.h declares (tests check the library exports them)
+ABI_SYMBOLS = ["b2_ctx_create", "b2_ctx_destroy", "b2_last_error", "b2_version", "b2_register_method",
+               "b2_set_server_identity", "b2_block_alloc", "b2_block_free", "b2_process_batch", "b2_batch_upload",
+               "b2_batch_execute", "b2_batch_download", "b2_stage_times", "b2_crc32c_batch", "b2_counters_read",
+               "b2_counters_device_ptr"]
+
+ECHO_METHOD = dict(service_full_name=b"example.EchoService", service_name=b"EchoService", method_name=b"Echo",
+                   request_type_name=b"example.EchoRequest", handler=1, echo_attachment=1,
+                   response_checksum_type=0, response_compress_type=0)
+
+
+def _check(rc):
+    if rc < 0:
+        raise B2Error(rc, (lib.b2_last_error() or b"").decode("utf-8", "replace"))
+    return rc
+
+
+class PinnedBuffer:
+    """Host memory from b2_block_alloc (cudaHostAlloc), viewed as a numpy uint8 array."""
+
+    def __init__(self, nbytes):
+        self.ptr = lib.b2_block_alloc(nbytes)
+        if not self.ptr:
+            raise B2Error(B2_E_NOMEM, "b2_block_alloc failed")
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            lib.b2_block_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """b2_ctx: one per GPU."""
+
+    def __init__(self, device=0, max_batch_bytes=64 << 20, max_msgs=1 << 20, max_runs=4096, max_resp_bytes=0,
+                 tile_bytes=0, max_body_size=0, methods=(ECHO_METHOD,), server_identity=None):
+        opt = Options(device, max_batch_bytes, max_msgs, max_runs, max_resp_bytes, tile_bytes, max_body_size)
+        h = C.c_void_p()
+        _check(lib.b2_ctx_create(C.byref(opt), C.byref(h)))
+        self._h = h
+        self._keep = []
+        for m in methods:
+            self.register_method(**m)
+        if server_identity:
+            _check(lib.b2_set_server_identity(self._h, server_identity))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.b2_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def register_method(self, **kw):
+        m = Method(**kw)
+        self._keep.append(m)
+        return _check(lib.b2_register_method(self._h, C.byref(m)))
+
+    @staticmethod
+    def _views(res):
+        runs = np.ctypeslib.as_array((C.c_uint8 * (32 * res.n_runs)).from_address(res.runs)).view(RUN_STATUS_DT) \
+            if res.n_runs else np.zeros(0, RUN_STATUS_DT)
+        msgs = np.ctypeslib.as_array((C.c_uint8 * (64 * res.n_msgs)).from_address(res.msgs)).view(MSG_DT) \
+            if res.n_msgs else np.zeros(0, MSG_DT)
+        resp = np.ctypeslib.as_array((C.c_uint8 * res.resp_bytes).from_address(res.resp)) \
+            if res.resp_bytes else np.zeros(0, np.uint8)
+        return runs, msgs, resp
+
+    def process_batch(self, data, runs):
+        """Host buffers in, host (pinned) views out: (run_status, msgs, resp, info)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        runs = np.ascontiguousarray(runs, dtype=RUN_DT)
+        res = BatchResult()
+        _check(lib.b2_process_batch(self._h, data.ctypes.data, data.nbytes, runs.ctypes.data, len(runs), C.byref(res)))
+        rs, msgs, resp = self._views(res)
+        return rs, msgs, resp, {"kernel_ms": res.kernel_ms, "n_launches": res.n_launches}
+
+    def upload(self, data, runs):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        runs = np.ascontiguousarray(runs, dtype=RUN_DT)
+        _check(lib.b2_batch_upload(self._h, data.ctypes.data, data.nbytes, runs.ctypes.data, len(runs)))
+
+    def upload_ptr(self, ptr, nbytes, runs):
+        runs = np.ascontiguousarray(runs, dtype=RUN_DT)
+        _check(lib.b2_batch_upload(self._h, ptr, nbytes, runs.ctypes.data, len(runs)))
+
+    def execute(self):
+        ms, n = C.c_float(0), C.c_uint32(0)
+        _check(lib.b2_batch_execute(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def download(self):
+        res = BatchResult()
+        _check(lib.b2_batch_download(self._h, C.byref(res)))
+        rs, msgs, resp = self._views(res)
+        return rs, msgs, resp, {"kernel_ms": res.kernel_ms, "n_launches": res.n_launches}
+
+    def process_batch_ptr(self, ptr, nbytes, runs):
+        runs = np.ascontiguousarray(runs, dtype=RUN_DT)
+        res = BatchResult()
+        _check(lib.b2_process_batch(self._h, ptr, nbytes, runs.ctypes.data, len(runs), C.byref(res)))
+        rs, msgs, resp = self._views(res)
+        return rs, msgs, resp, {"kernel_ms": res.kernel_ms, "n_launches": res.n_launches}
+
+    def stage_times(self):
+        names = (C.c_char_p * 16)()
+        ms = (C.c_float * 16)()
+        n = lib.b2_stage_times(self._h, names, ms, 16)
+        return [(names[i].decode(), ms[i]) for i in range(max(0, min(n, 16)))]
+
+    def crc32c_batch(self, data, offs, lens):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint32)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        out = np.zeros(len(offs), dtype=np.uint32)
+        _check(lib.b2_crc32c_batch(self._h, data.ctypes.data, data.nbytes, offs.ctypes.data, lens.ctypes.data,
+                                   len(offs), out.ctypes.data))
+        return out
+
+    def counters(self):
+        out = (C.c_int64 * 8)()
+        _check(lib.b2_counters_read(self._h, out))
+        return list(out)
+
+    def counters_device_ptr(self):
+        return lib.b2_counters_device_ptr(self._h)

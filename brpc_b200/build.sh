@@ -1,0 +1,8 @@
+#!/bin/sh
+# Builds brpc_b200/libb2rpc.so (the C-ABI product library) for sm_100a, in-tree.
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+    -Xcompiler -fPIC,-Wall -Xptxas -v -shared \
+    -o "$HERE/libb2rpc.so" "$HERE/csrc/b2_api.cu" 2>&1

@@ -1,0 +1,339 @@
+// b2_api.cu — the C ABI (include/b2rpc.h) over the sm_100a kernels.
+// Host code is plain C++ + the CUDA runtime; nothing here computes on the CPU:
+// without a CUDA device every entry point fails with B2_E_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "b2_kernels.cuh"
+
+using namespace b2;
+
+static thread_local char g_err[512] = "";
+static void set_err(const char* fmt, const char* a = "", const char* b = "") { snprintf(g_err, sizeof g_err, fmt, a, b); }
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) { set_err("%s: %s", #call, cudaGetErrorString(e_)); return B2_E_CUDA; } \
+    } while (0)
+
+namespace {
+constexpr int kMaxStages = 16;
+struct Stage { const char* name; cudaEvent_t ev; };
+}
+
+struct b2_ctx {
+    b2_options opt;
+    DevConfig cfg;
+    std::vector<DevMethod> methods;
+    // device
+    uint8_t* d_bytes = nullptr; b2_run* d_runs = nullptr; uint32_t* d_run_tile_base = nullptr;
+    TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; b2_run_status* d_run_status = nullptr;
+    uint32_t* d_frame_off = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr;
+    uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr;
+    unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
+    uint32_t max_tiles = 0;
+    // pinned host mirrors
+    b2_run_status* h_run_status = nullptr; b2_msg_desc* h_msgs = nullptr; uint8_t* h_resp = nullptr;
+    uint32_t* h_totals = nullptr; uint32_t* h_run_tile_base = nullptr;
+    // current batch
+    uint32_t n_runs = 0, n_tiles = 0, nbytes = 0, max_run_tiles = 0;
+    bool uploaded = false, executed = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[kMaxStages + 1];
+    const char* stage_names[kMaxStages];
+    int n_stages = 0;
+    float last_kernel_ms = 0.f; uint32_t last_launches = 0;
+};
+
+static uint32_t g_crc_tab_host[256];
+static void crc_table_init() {
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0x82f63b78u : (c >> 1);
+        g_crc_tab_host[i] = c;
+    }
+}
+
+extern "C" const char* b2_last_error(void) { return g_err; }
+extern "C" const char* b2_version(void) { return "brpc_b200 0.1 (sm_100a)"; }
+
+extern "C" void* b2_block_alloc(size_t size) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, size, cudaHostAllocPortable) != cudaSuccess) { set_err("cudaHostAlloc failed"); return nullptr; }
+    return p;
+}
+extern "C" void b2_block_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" void b2_ctx_destroy(b2_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->opt.device);
+    cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base);
+    cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_slot);
+    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods);
+    cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
+    cudaFreeHost(c->h_run_tile_base);
+    for (int i = 0; i <= kMaxStages; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
+    if (!o || !out) { set_err("null argument"); return B2_E_INVAL; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_err("no CUDA device: brpc_b200 has no CPU path"); return B2_E_NO_DEVICE;
+    }
+    if (o->device < 0 || o->device >= ndev) { set_err("bad device ordinal"); return B2_E_INVAL; }
+    if (o->max_batch_bytes == 0 || o->max_batch_bytes >= (1u << 31) || o->max_msgs == 0 || o->max_runs == 0) {
+        set_err("capacities must be non-zero and max_batch_bytes < 2 GiB"); return B2_E_INVAL;
+    }
+    CU(cudaSetDevice(o->device));
+    b2_ctx* c = new b2_ctx();
+    for (int i = 0; i <= kMaxStages; i++) c->ev[i] = nullptr;
+    c->opt = *o;
+    uint32_t tile = o->tile_bytes ? o->tile_bytes : 8192;
+    if (tile < 512 || (tile & (tile - 1))) { delete c; set_err("tile_bytes must be a power of two >= 512"); return B2_E_INVAL; }
+    c->opt.tile_bytes = tile;
+    if (c->opt.max_resp_bytes == 0) {
+        uint64_t r = (uint64_t)o->max_batch_bytes + (uint64_t)o->max_msgs * 64 + (1u << 20);
+        c->opt.max_resp_bytes = r > 0xfffffff0ull ? 0xfffffff0u : (uint32_t)r;
+    }
+    memset(&c->cfg, 0, sizeof c->cfg);
+    c->cfg.max_body_size = o->max_body_size ? o->max_body_size : (64ull << 20);
+    c->cfg.tile_bytes = tile;
+    c->cfg.tile_shift = 0; while ((1u << c->cfg.tile_shift) < tile) c->cfg.tile_shift++;
+    c->max_tiles = o->max_batch_bytes / tile + o->max_runs + 1;
+    const uint32_t scan_blocks = o->max_msgs / (kScanBlock * kScanItems) + 2;
+#define ALLOC(ptr, bytes) do { if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) { set_err("cudaMalloc %s failed", #ptr); b2_ctx_destroy(c); return B2_E_NOMEM; } } while (0)
+#define HALLOC(ptr, bytes) do { if (cudaHostAlloc((void**)&(ptr), (bytes), cudaHostAllocDefault) != cudaSuccess) { set_err("cudaHostAlloc %s failed", #ptr); b2_ctx_destroy(c); return B2_E_NOMEM; } } while (0)
+    ALLOC(c->d_bytes, (size_t)o->max_batch_bytes + 1024);
+    ALLOC(c->d_runs, sizeof(b2_run) * (size_t)o->max_runs);
+    ALLOC(c->d_run_tile_base, 4 * ((size_t)o->max_runs + 1));
+    ALLOC(c->d_tiles, sizeof(TileRec) * (size_t)c->max_tiles);
+    ALLOC(c->d_tile_base, 4 * (size_t)c->max_tiles);
+    ALLOC(c->d_run_status, sizeof(b2_run_status) * (size_t)o->max_runs);
+    ALLOC(c->d_frame_off, 4 * (size_t)o->max_msgs);
+    ALLOC(c->d_msgs, sizeof(b2_msg_desc) * (size_t)o->max_msgs);
+    ALLOC(c->d_aux, sizeof(MsgAux) * (size_t)o->max_msgs);
+    ALLOC(c->d_slot, 4 * ((size_t)o->max_msgs + 1));
+    ALLOC(c->d_scan_tmp, 4 * (size_t)scan_blocks);
+    ALLOC(c->d_resp, (size_t)c->opt.max_resp_bytes + 1024);
+    ALLOC(c->d_counters, 8 * B2_N_COUNTERS);
+    ALLOC(c->d_totals, 16);
+    ALLOC(c->d_methods, sizeof(DevMethod) * 64);
+    HALLOC(c->h_run_status, sizeof(b2_run_status) * (size_t)o->max_runs);
+    HALLOC(c->h_msgs, sizeof(b2_msg_desc) * (size_t)o->max_msgs);
+    HALLOC(c->h_resp, (size_t)c->opt.max_resp_bytes);
+    HALLOC(c->h_totals, 16);
+    HALLOC(c->h_run_tile_base, 4 * ((size_t)o->max_runs + 1));
+    CU(cudaMemset(c->d_counters, 0, 8 * B2_N_COUNTERS));
+    CU(cudaMemset(c->d_bytes, 0, (size_t)o->max_batch_bytes + 1024));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i <= kMaxStages; i++) CU(cudaEventCreate(&c->ev[i]));
+    crc_table_init();
+    CU(cudaMemcpyToSymbol(c_crc_table, g_crc_tab_host, sizeof g_crc_tab_host));
+    CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    *out = c;
+    return B2_OK;
+}
+
+extern "C" int b2_set_server_identity(b2_ctx* c, const char* ip_port) {
+    if (!c) return B2_E_INVAL;
+    const size_t n = ip_port ? strlen(ip_port) : 0;
+    if (n >= sizeof c->cfg.identity) { set_err("identity too long"); return B2_E_INVAL; }
+    memset(c->cfg.identity, 0, sizeof c->cfg.identity);
+    if (n) memcpy(c->cfg.identity, ip_port, n);
+    c->cfg.identity_len = (uint32_t)n;
+    return B2_OK;
+}
+
+extern "C" int b2_register_method(b2_ctx* c, const b2_method* m) {
+    if (!c || !m || !m->service_full_name || !m->service_name || !m->method_name || !m->request_type_name) { set_err("null argument"); return B2_E_INVAL; }
+    if (c->methods.size() >= 64) { set_err("method table full"); return B2_E_CAPACITY; }
+    DevMethod d; memset(&d, 0, sizeof d);
+    std::string full = std::string(m->service_full_name) + "." + m->method_name;
+    if (full.size() >= sizeof d.full_method || strlen(m->service_name) >= sizeof d.service_short ||
+        strlen(m->service_full_name) >= sizeof d.service_full || strlen(m->request_type_name) >= sizeof d.request_type) {
+        set_err("method names too long"); return B2_E_INVAL;
+    }
+    memcpy(d.full_method, full.data(), full.size()); d.full_method_len = (uint32_t)full.size();
+    d.service_short_len = (uint32_t)strlen(m->service_name); memcpy(d.service_short, m->service_name, d.service_short_len);
+    d.service_full_len = (uint32_t)strlen(m->service_full_name); memcpy(d.service_full, m->service_full_name, d.service_full_len);
+    d.request_type_len = (uint32_t)strlen(m->request_type_name); memcpy(d.request_type, m->request_type_name, d.request_type_len);
+    d.handler = m->handler; d.echo_attachment = m->echo_attachment;
+    d.response_checksum_type = m->response_checksum_type; d.response_compress_type = m->response_compress_type;
+    c->methods.push_back(d);
+    c->cfg.n_methods = (uint32_t)c->methods.size();
+    CU(cudaSetDevice(c->opt.device));
+    CU(cudaMemcpy(c->d_methods, c->methods.data(), sizeof(DevMethod) * c->methods.size(), cudaMemcpyHostToDevice));
+    return (int)c->methods.size() - 1;
+}
+
+static BatchPtrs make_ptrs(b2_ctx* c) {
+    BatchPtrs B;
+    B.bytes = c->d_bytes; B.runs = c->d_runs; B.run_tile_base = c->d_run_tile_base; B.tiles = c->d_tiles;
+    B.tile_base = c->d_tile_base; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.msgs = c->d_msgs;
+    B.aux = c->d_aux; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.counters = c->d_counters;
+    B.totals = c->d_totals; B.methods = c->d_methods;
+    B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes;
+    return B;
+}
+
+extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs) {
+    if (!c || (!bytes && nbytes) || (!runs && n_runs)) { set_err("null argument"); return B2_E_INVAL; }
+    if (nbytes > c->opt.max_batch_bytes || n_runs > c->opt.max_runs) { set_err("batch exceeds ctx capacity"); return B2_E_CAPACITY; }
+    CU(cudaSetDevice(c->opt.device));
+    const uint32_t shift = c->cfg.tile_shift, tile = c->cfg.tile_bytes;
+    uint64_t nt = 0; uint32_t max_rt = 0;
+    for (uint32_t r = 0; r < n_runs; r++) {
+        if ((runs[r].offset & 15u) || (uint64_t)runs[r].offset + runs[r].length > nbytes) { set_err("run offset must be 16-aligned and inside the batch"); return B2_E_INVAL; }
+        c->h_run_tile_base[r] = (uint32_t)nt;
+        const uint32_t t = (uint32_t)(((uint64_t)runs[r].length + tile - 1) >> shift);
+        nt += t; if (t > max_rt) max_rt = t;
+    }
+    c->h_run_tile_base[n_runs] = (uint32_t)nt;
+    if (nt > c->max_tiles) { set_err("too many tiles"); return B2_E_CAPACITY; }
+    c->n_runs = n_runs; c->n_tiles = (uint32_t)nt; c->nbytes = nbytes; c->max_run_tiles = max_rt;
+    if (nbytes) CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
+    if (n_runs) {
+        CU(cudaMemcpyAsync(c->d_runs, runs, sizeof(b2_run) * n_runs, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaMemcpyAsync(c->d_run_tile_base, c->h_run_tile_base, 4 * ((size_t)n_runs + 1), cudaMemcpyHostToDevice, c->stream));
+    c->uploaded = true; c->executed = false;
+    return B2_OK;
+}
+
+static int launch_pipeline(b2_ctx* c) {
+    const BatchPtrs B = make_ptrs(c);
+    const DevConfig C = c->cfg;
+    cudaStream_t s = c->stream;
+    int st = 0; uint32_t launches = 0;
+    auto mark = [&](const char* name) { c->stage_names[st] = name; cudaEventRecord(c->ev[st + 1], s); st++; };
+    CU(cudaMemsetAsync(c->d_totals, 0, 16, s));
+    CU(cudaEventRecord(c->ev[0], s));
+    if (c->n_runs == 0) { c->n_stages = 0; c->last_launches = 0; return B2_OK; }
+    if (c->n_tiles) {
+        k_tile_search<<<(c->n_tiles * 32 + 255) / 256, 256, 0, s>>>(B, C); launches++; mark("tile_search");
+        k_tile_walk<<<(c->n_tiles + 127) / 128, 128, 0, s>>>(B, C); launches++; mark("tile_walk");
+    }
+    {
+        size_t smem = (size_t)c->max_run_tiles * 12;
+        if (smem > 200 * 1024) smem = 0;
+        k_resolve<<<c->n_runs, 256, smem, s>>>(B, C); launches++; mark("resolve");
+    }
+    k_run_prefix<<<1, 1024, 0, s>>>(B); launches++; mark("run_prefix");
+    if (c->n_tiles) { k_frame_table<<<(c->n_tiles + 127) / 128, 128, 0, s>>>(B, C); launches++; mark("frame_table"); }
+    // message-count dependent grids are sized for the capacity bound of this batch (nbytes / 12)
+    // and exit early on the device-side count
+    uint64_t bound = (uint64_t)c->nbytes / 12 + 1;
+    if (bound > c->opt.max_msgs) bound = c->opt.max_msgs;
+    const uint32_t mb = (uint32_t)bound;
+    k_decode<<<(mb + 127) / 128, 128, 0, s>>>(B, C); launches++; mark("decode");
+    k_scan_blocks<<<(mb + kScanBlock * kScanItems - 1) / (kScanBlock * kScanItems), kScanBlock, 0, s>>>(B); launches++;
+    k_scan_top<<<1, 1024, 0, s>>>(B); launches++; mark("scan");
+    k_pack<<<(uint32_t)(((uint64_t)mb * 32 + 255) / 256), 256, 0, s>>>(B, C); launches++; mark("pack");
+    k_finalize<<<(c->n_runs + 255) / 256, 256, 0, s>>>(B); launches++; mark("finalize");
+    c->n_stages = st; c->last_launches = launches;
+    CU(cudaGetLastError());
+    return B2_OK;
+}
+
+extern "C" int b2_batch_execute(b2_ctx* c, float* kernel_ms, uint32_t* n_launches) {
+    if (!c || !c->uploaded) { set_err("no batch uploaded"); return B2_E_INVAL; }
+    CU(cudaSetDevice(c->opt.device));
+    int rc = launch_pipeline(c);
+    if (rc != B2_OK) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    if (c->n_stages) CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[c->n_stages]));
+    c->last_kernel_ms = ms; c->executed = true;
+    if (kernel_ms) *kernel_ms = ms;
+    if (n_launches) *n_launches = c->last_launches;
+    return B2_OK;
+}
+
+extern "C" int b2_batch_download(b2_ctx* c, b2_batch_result* out) {
+    if (!c || !out || !c->executed) { set_err("no executed batch"); return B2_E_INVAL; }
+    CU(cudaSetDevice(c->opt.device));
+    memset(out, 0, sizeof *out);
+    CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->n_runs && (c->h_totals[2] & 3u)) {
+        set_err(c->h_totals[2] & 1u ? "more messages than max_msgs" : "responses exceed max_resp_bytes"); return B2_E_CAPACITY;
+    }
+    const uint32_t n_msgs = c->n_runs ? c->h_totals[0] : 0, resp_bytes = c->n_runs ? c->h_totals[1] : 0;
+    if (c->n_runs) CU(cudaMemcpyAsync(c->h_run_status, c->d_run_status, sizeof(b2_run_status) * c->n_runs, cudaMemcpyDeviceToHost, c->stream));
+    if (n_msgs) CU(cudaMemcpyAsync(c->h_msgs, c->d_msgs, sizeof(b2_msg_desc) * (size_t)n_msgs, cudaMemcpyDeviceToHost, c->stream));
+    if (resp_bytes) CU(cudaMemcpyAsync(c->h_resp, c->d_resp, resp_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    out->runs = c->h_run_status; out->n_runs = c->n_runs;
+    out->msgs = c->h_msgs; out->n_msgs = n_msgs;
+    out->resp = c->h_resp; out->resp_bytes = resp_bytes;
+    out->kernel_ms = c->last_kernel_ms; out->n_launches = c->last_launches;
+    return B2_OK;
+}
+
+extern "C" int b2_process_batch(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs,
+                                b2_batch_result* out) {
+    int rc = b2_batch_upload(c, bytes, nbytes, runs, n_runs);
+    if (rc != B2_OK) return rc;
+    CU(cudaSetDevice(c->opt.device));
+    rc = launch_pipeline(c);
+    if (rc != B2_OK) return rc;
+    c->executed = true;
+    rc = b2_batch_download(c, out);
+    if (rc != B2_OK) return rc;
+    float ms = 0.f;
+    if (c->n_stages) CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[c->n_stages]));
+    c->last_kernel_ms = ms; out->kernel_ms = ms;
+    return B2_OK;
+}
+
+extern "C" int b2_stage_times(b2_ctx* c, const char** names, float* ms, int cap) {
+    if (!c) return B2_E_INVAL;
+    int n = c->n_stages < cap ? c->n_stages : cap;
+    for (int i = 0; i < n; i++) {
+        names[i] = c->stage_names[i];
+        float t = 0.f;
+        cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1]);
+        ms[i] = t;
+    }
+    return c->n_stages;
+}
+
+extern "C" int b2_counters_read(b2_ctx* c, int64_t out[B2_N_COUNTERS]) {
+    if (!c || !out) return B2_E_INVAL;
+    CU(cudaSetDevice(c->opt.device));
+    CU(cudaMemcpy(out, c->d_counters, 8 * B2_N_COUNTERS, cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+extern "C" void* b2_counters_device_ptr(b2_ctx* c) { return c ? (void*)c->d_counters : nullptr; }
+
+// device pointers of the resident batch, for harnesses that time or inspect kernels directly
+extern "C" void* b2_debug_resp_device_ptr(b2_ctx* c) { return c ? (void*)c->d_resp : nullptr; }
+
+__global__ void k_crc32c_batch(const uint8_t* bytes, const uint32_t* offs, const uint32_t* lens, uint32_t n, uint32_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = crc32c_bytes_serial(0xffffffffu, bytes + offs[i], lens[i]) ^ 0xffffffffu;
+}
+
+extern "C" int b2_crc32c_batch(b2_ctx* c, const void* bytes, uint32_t nbytes, const uint32_t* offs, const uint32_t* lens,
+                               uint32_t n, uint32_t* out) {
+    if (!c || !bytes || !offs || !lens || !out) { set_err("null argument"); return B2_E_INVAL; }
+    if (nbytes > c->opt.max_batch_bytes || n > c->opt.max_msgs) { set_err("exceeds ctx capacity"); return B2_E_CAPACITY; }
+    for (uint32_t i = 0; i < n; i++) if ((uint64_t)offs[i] + lens[i] > nbytes) { set_err("slice outside buffer"); return B2_E_INVAL; }
+    CU(cudaSetDevice(c->opt.device));
+    CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_frame_off, offs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_slot, lens, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    if (n) k_crc32c_batch<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_bytes, c->d_frame_off, c->d_slot, n, c->d_scan_tmp ? (uint32_t*)c->d_aux : nullptr);
+    CU(cudaMemcpyAsync(out, c->d_aux, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->uploaded = false; c->executed = false;
+    return B2_OK;
+}

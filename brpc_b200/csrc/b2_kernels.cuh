@@ -1,0 +1,713 @@
+// b2_kernels.cuh — the sm_100a kernels of the brpc message-processing hot path.
+//
+// Data layout in HBM (all offsets < 4 GiB, one batch):
+//   bytes  : the batch buffer; run r occupies [runs[r].offset, +length), offset % 16 == 0
+//   tiles  : every run is split in TILE-byte tiles; tile t of the batch = (run, k)
+//   msgs   : b2_msg_desc[ ], 64 B each, per-run order, runs in order
+//   resp   : response region; message i owns the 16-byte aligned slot
+//            [slot_off[i], slot_off[i+1]) and its frame starts at slot_off[i] + pad
+//            so that the echoed payload keeps its (mod 16) alignment -> 16 B copies
+//
+// Pipeline (one launch each, same stream):
+//   k_tile_search  warp/tile   speculative first frame start of every tile (k >= 1)
+//   k_tile_walk    thread/tile header chain inside the tile -> (exit, count)
+//   k_resolve      CTA/run     verifies the speculation chain from tile 0 (exact),
+//                              falls back to a scalar walk where it fails, run status
+//   k_run_prefix   1 CTA       first_msg of every run
+//   k_frame_table  thread/tile frame offsets of live tiles
+//   k_decode       thread/msg  RpcMeta / StreamFrameMeta / EchoRequest decode -> desc, aux, slot
+//   k_scan_*       exclusive scan of the slot sizes
+//   k_pack         warp/msg    response header+meta, payload copy (+CRC32C)
+//   k_finalize     thread/run  per-run response span, counters
+#pragma once
+#include <cuda_runtime.h>
+#include "b2_core.cuh"
+
+namespace b2 {
+
+enum TileKind : uint8_t { kRanOff = 0, kStop = 1, kAmbig = 2 };
+
+struct __align__(16) TileRec {
+    uint32_t entry;      // first step position (run-relative), kNone = no candidate
+    uint32_t exit;       // position after the last step that started in this tile
+    uint32_t count;      // messages cut by those steps
+    uint8_t kind;        // TileKind
+    int8_t last_proto;   // protocol of the last message (0 = none)
+    uint8_t live;        // set by k_resolve: the true chain enters this tile at `entry`
+    int8_t pf_in;        // set by k_resolve: preferred index at the first step
+};
+
+struct __align__(16) MsgAux {     // device-internal side record of k_decode -> k_pack
+    uint32_t msg_off;    // echoed message: offset from the frame start
+    uint32_t msg_len;
+    uint32_t att_len;    // echoed attachment bytes (contiguous after body_wo_att)
+    uint32_t att_off;    // offset from the frame start
+    uint32_t cks_off;    // request checksum_value span (offset from frame start)
+    uint32_t cks_len;
+    uint32_t svc_off, svc_len;
+    uint32_t mth_off, mth_len;
+    uint32_t pad;        // bytes between slot start and frame start (0..15)
+    uint32_t err_kind;   // ErrKind for B2_MSG_ERROR_REPLIED
+};
+enum ErrKind : uint32_t { kErrNone = 0, kErrAttachment, kErrNoService, kErrNoMethod, kErrParseRequest };
+
+struct DevMethod {                // registered method table (global memory, tiny)
+    char full_method[200];        // "example.EchoService.Echo"
+    uint32_t full_method_len;
+    char service_short[64];  uint32_t service_short_len;
+    char service_full[120];  uint32_t service_full_len;
+    char request_type[96];   uint32_t request_type_len;
+    int32_t handler, echo_attachment, response_checksum_type, response_compress_type;
+};
+struct DevConfig {
+    uint64_t max_body_size;
+    uint32_t tile_bytes, tile_shift;
+    uint32_t n_methods;
+    uint32_t identity_len;
+    char identity[64];            // "ip:port" of Controller::AppendServerIdentiy
+};
+
+struct BatchPtrs {
+    const uint8_t* bytes;
+    const b2_run* runs;
+    const uint32_t* run_tile_base;   // [n_runs+1] first tile of each run
+    TileRec* tiles;
+    uint32_t* tile_base;             // [n_tiles] run-relative index of the tile's first message
+    b2_run_status* run_status;
+    uint32_t* frame_off;             // [max_msgs] frame offsets (batch-relative), bit31.. unused
+    b2_msg_desc* msgs;
+    MsgAux* aux;
+    uint32_t* slot;                  // [max_msgs+1] slot sizes -> exclusive offsets
+    uint32_t* scan_tmp;              // block sums
+    uint8_t* resp;
+    unsigned long long* counters;    // int64[B2_N_COUNTERS]
+    uint32_t* totals;                // [0]=n_msgs [1]=resp_bytes [2]=overflow flags
+    const DevMethod* methods;
+    uint32_t n_runs, n_tiles, max_msgs, max_resp;
+};
+
+// ---------------------------------------------------------------------------
+// tile walk: the CutInputMessage chain of the steps that START inside
+// [entry, tile_end).  kSpec: the preferred index at the first step is unknown
+// (speculation); a handler that pops bytes makes the outcome depend on it, so
+// the tile is handed to the resolver (kAmbig).
+template <bool kSpec, typename Emit>
+B2_HD void walk_tile(const uint8_t* run, uint32_t len, uint32_t entry, int pf_in, uint32_t tile_end,
+                     uint64_t max_body, TileRec& t, Emit emit) {
+    uint32_t pos = entry, count = 0;
+    int pf = kSpec ? -1 : pf_in, last = 0;
+    uint8_t kind = kRanOff;
+    while (pos < tile_end) {
+        const Step s = cut_input_message(run, len, pos, pf, max_body);
+        if (kSpec && count == 0 && s.popped) { kind = kAmbig; break; }
+        if (s.err != B2_PARSE_OK) { kind = kStop; break; }
+        emit(count, s);
+        count++; last = s.index; pf = s.index; pos = s.new_pos;
+    }
+    t.entry = entry; t.exit = pos; t.count = count; t.kind = kind; t.last_proto = (int8_t)last;
+}
+struct NoEmit { B2_HD void operator()(uint32_t, const Step&) const {} };
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ uint32_t find_run(const uint32_t* base, uint32_t n_runs, uint32_t tile) {
+    uint32_t lo = 0, hi = n_runs;          // largest r with base[r] <= tile
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(base + mid) <= tile) lo = mid; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ bool is_magic(uint32_t w) { return w == kMagicPRPC || w == kMagicSTRM; }
+
+// --- k_tile_search: one warp per tile ---------------------------------------
+// Finds the first position p in the tile where a frame of either protocol parses
+// completely (header sane, whole body inside the run) and is followed by another
+// magic or the run tail.  Pure speculation: k_resolve accepts it only if the true
+// chain arrives exactly there.
+__global__ void __launch_bounds__(256) k_tile_search(BatchPtrs B, DevConfig C) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B.n_tiles) return;
+    const uint32_t r = find_run(B.run_tile_base, B.n_runs, warp);
+    const uint32_t k = warp - __ldg(B.run_tile_base + r);
+    const b2_run run = B.runs[r];
+    const uint8_t* base = B.bytes + run.offset;
+    const uint32_t len = run.length;
+    uint32_t entry = kNone;
+    if (k == 0) {
+        entry = 0;
+    } else {
+        const uint32_t t0 = k << C.tile_shift;
+        const uint32_t t1 = min(t0 + C.tile_bytes, len);
+        for (uint32_t c0 = t0; c0 < t1 && entry == kNone; c0 += 512) {
+            // lane owns 16 positions [p0, p0+16); needs 3 more bytes for the last windows
+            const uint32_t p0 = c0 + lane * 16;
+            uint4 v = make_uint4(0, 0, 0, 0); uint32_t nx = 0;
+            if (p0 < t1) {
+                v = __ldg(reinterpret_cast<const uint4*>(base + p0));        // bytes buffer is padded: safe past len
+                nx = __ldg(reinterpret_cast<const uint32_t*>(base + p0 + 16));
+            }
+            const uint32_t w[5] = { v.x, v.y, v.z, v.w, nx };
+            uint32_t mask = 0;
+            #pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t word = __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], (j & 3) * 8);
+                if (is_magic(word) && p0 + j + 4 <= len && p0 + j < t1) mask |= 1u << j;
+            }
+            // candidates in position order: lanes ascending, bits ascending
+            uint32_t any = __ballot_sync(0xffffffffu, mask != 0);
+            while (any && entry == kNone) {
+                const int src = __ffs(any) - 1;
+                uint32_t m = __shfl_sync(0xffffffffu, mask, src);
+                while (m && entry == kNone) {
+                    const uint32_t p = c0 + src * 16 + (__ffs(m) - 1);
+                    m &= m - 1;
+                    const Step s = cut_input_message(base, len, p, -1, C.max_body_size);   // uniform across lanes
+                    if (s.err == B2_PARSE_OK && !s.popped) {
+                        const uint32_t q = s.new_pos;
+                        if (q + 4 > len || is_magic(load_le32(base + q))) entry = p;
+                    }
+                }
+                any &= any - 1;
+            }
+        }
+    }
+    if (lane == 0) B.tiles[warp].entry = entry;
+}
+
+// --- k_tile_walk: one thread per tile ---------------------------------------
+__global__ void __launch_bounds__(128) k_tile_walk(BatchPtrs B, DevConfig C) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B.n_tiles) return;
+    const uint32_t r = find_run(B.run_tile_base, B.n_runs, t);
+    const uint32_t k = t - __ldg(B.run_tile_base + r);
+    const b2_run run = B.runs[r];
+    TileRec rec;
+    rec.entry = B.tiles[t].entry; rec.exit = 0; rec.count = 0; rec.kind = kStop; rec.last_proto = 0; rec.live = 0; rec.pf_in = -1;
+    if (rec.entry != kNone)
+        walk_tile<true>(B.bytes + run.offset, run.length, rec.entry, -1, (k + 1) << C.tile_shift, C.max_body_size, rec, NoEmit());
+    B.tiles[t] = rec;
+}
+
+// --- k_resolve: one CTA per run ---------------------------------------------
+// Walks the tile chain from position 0 with the true preferred index.  A tile's
+// summary is used only when the chain arrives exactly at its speculated entry
+// (by induction every used summary is what a sequential walk would have
+// produced); otherwise the tile is re-walked here, scalar, from the true entry.
+__global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C) {
+    extern __shared__ uint32_t sm[];
+    const uint32_t r = blockIdx.x;
+    const b2_run run = B.runs[r];
+    const uint8_t* base = B.bytes + run.offset;
+    const uint32_t len = run.length;
+    const uint32_t tb = B.run_tile_base[r], nt = B.run_tile_base[r + 1] - tb;
+    TileRec* tiles = B.tiles + tb;
+    __shared__ uint32_t s_use_smem;
+    // smem mirror: [0,nt) entry, [nt,2nt) exit, [2nt,3nt) count<<8 | kind<<6 | (last_proto & 3)
+    const bool fits = nt * 12u <= 200u * 1024u;
+    if (threadIdx.x == 0) s_use_smem = fits;
+    if (fits) {
+        for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) {
+            const TileRec t = tiles[i];
+            sm[i] = t.entry; sm[nt + i] = t.exit; sm[2 * nt + i] = (t.count << 8) | ((uint32_t)t.kind << 6) | ((uint32_t)t.last_proto & 3u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t pos = 0, nmsg = 0;
+        int pf = run.preferred_proto;
+        int err = B2_PARSE_ERROR_NOT_ENOUGH_DATA;
+        for (;;) {
+            const uint32_t k = pos >> C.tile_shift;
+            if (k >= nt) break;                       // chain left the run's tiles: final step below
+            uint32_t entry, exit_, packed;
+            if (fits) { entry = sm[k]; exit_ = sm[nt + k]; packed = sm[2 * nt + k]; }
+            else { const TileRec t = tiles[k]; entry = t.entry; exit_ = t.exit; packed = (t.count << 8) | ((uint32_t)t.kind << 6) | ((uint32_t)t.last_proto & 3u); }
+            uint32_t count = packed >> 8, kind = (packed >> 6) & 3u; int last = (int)(packed & 3u);
+            if (entry != pos || kind == kAmbig) {
+                // mis-speculation (or pf-sensitive step): authoritative scalar walk of this tile
+                TileRec t; t.live = 0; t.pf_in = 0;
+                walk_tile<false>(base, len, pos, pf, (k + 1) << C.tile_shift, C.max_body_size, t, NoEmit());
+                entry = pos; exit_ = t.exit; count = t.count; kind = t.kind; last = t.last_proto;
+                tiles[k].entry = entry; tiles[k].exit = exit_; tiles[k].count = count; tiles[k].kind = (uint8_t)kind; tiles[k].last_proto = (int8_t)last;
+            }
+            tiles[k].live = 1; tiles[k].pf_in = (int8_t)pf;
+            B.tile_base[tb + k] = nmsg;
+            nmsg += count;
+            if (count) pf = last;
+            pos = exit_;
+            if (kind != kRanOff) break;
+        }
+        // the step that ends ProcessNewMessage's loop, with the true preferred index
+        const Step s = cut_input_message(base, len, pos, pf, C.max_body_size);
+        // (an OK step here is impossible: every tile walk stops only on a non-OK step
+        //  or past the last tile, where no bytes remain)
+        err = s.err; pf = s.pf; pos = s.new_pos;
+        b2_run_status st;
+        st.consumed = pos; st.parse_error = (uint32_t)err; st.n_msgs = nmsg; st.first_msg = 0;
+        st.preferred_proto = pf; st.reserved0 = 0; st.resp_off = 0; st.resp_bytes = 0;
+        B.run_status[r] = st;
+    }
+}
+
+// --- k_run_prefix: exclusive scan of n_msgs over runs (single CTA) ----------
+__global__ void __launch_bounds__(1024) k_run_prefix(BatchPtrs B) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < B.n_runs; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t v = i < B.n_runs ? B.run_status[i].n_msgs : 0, x = v;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = s_warp[threadIdx.x], ws = w;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, ws, d); if (threadIdx.x >= d) ws += y; }
+            s_warp[threadIdx.x] = ws - w;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + s_warp[threadIdx.x >> 5] + x - v;
+        if (i < B.n_runs) B.run_status[i].first_msg = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { B.totals[0] = s_carry; if (s_carry > B.max_msgs) B.totals[2] |= 1u; }
+}
+
+// --- k_frame_table: one thread per tile --------------------------------------
+struct EmitFrame {
+    uint32_t* out; uint32_t run_off; uint32_t cap_left;
+    __device__ __forceinline__ void operator()(uint32_t i, const Step& s) const {
+        if (i < cap_left) out[i] = (run_off + s.frame_pos) | ((uint32_t)(s.index - 1) << 31);
+    }
+};
+__global__ void __launch_bounds__(128) k_frame_table(BatchPtrs B, DevConfig C) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B.n_tiles) return;
+    const TileRec rec = B.tiles[t];
+    if (!rec.live || rec.count == 0) return;
+    if (B.totals[2] & 1u) return;
+    const uint32_t r = find_run(B.run_tile_base, B.n_runs, t);
+    const uint32_t k = t - __ldg(B.run_tile_base + r);
+    const b2_run run = B.runs[r];
+    const uint32_t first = B.run_status[r].first_msg + B.tile_base[t];
+    TileRec tmp;
+    EmitFrame e; e.out = B.frame_off + first; e.run_off = run.offset; e.cap_left = B.max_msgs - first;
+    walk_tile<false>(B.bytes + run.offset, run.length, rec.entry, rec.pf_in, (k + 1) << C.tile_shift, C.max_body_size, tmp, e);
+}
+
+// --- k_decode: one thread per message ----------------------------------------
+__device__ __forceinline__ bool bytes_eq(const uint8_t* a, const char* b, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) if (a[i] != (uint8_t)b[i]) return false;
+    return true;
+}
+// Server::FindMethodPropertyByFullName(service, method): key = service + '.' + method (server.cpp:1970-1988)
+__device__ __forceinline__ int find_method(const DevMethod* ms, uint32_t n, const uint8_t* svc, uint32_t svc_len,
+                                           const uint8_t* mth, uint32_t mth_len, bool& no_service) {
+    no_service = false;
+    bool has_dot = false;
+    for (uint32_t i = 0; i < svc_len; i++) if (svc[i] == '.') { has_dot = true; break; }
+    const char* full = nullptr; uint32_t full_len = 0;
+    if (!has_dot) {                                   // jprotobuf short service name (baidu_rpc_protocol.cpp:738-748)
+        int sp = -1;
+        for (uint32_t m = 0; m < n; m++)
+            if (ms[m].service_short_len == svc_len && bytes_eq(svc, ms[m].service_short, svc_len)) { sp = (int)m; break; }
+        if (sp < 0) { no_service = true; return -1; }
+        full = ms[sp].service_full; full_len = ms[sp].service_full_len;
+    }
+    for (uint32_t m = 0; m < n; m++) {
+        const DevMethod& d = ms[m];
+        const uint32_t sl = has_dot ? svc_len : full_len;
+        if (d.full_method_len != sl + 1 + mth_len) continue;
+        bool eq = has_dot ? bytes_eq(svc, d.full_method, sl) : bytes_eq((const uint8_t*)full, d.full_method, sl);
+        eq = eq && d.full_method[sl] == '.' && bytes_eq(mth, d.full_method + sl + 1, mth_len);
+        if (eq) return (int)m;
+    }
+    return -1;
+}
+__device__ __forceinline__ uint32_t strnlen_dev(const uint8_t* s, uint32_t n) { uint32_t i = 0; while (i < n && s[i]) i++; return i; }
+
+__device__ __forceinline__ uint32_t cstr_len_compress(int32_t t) { return t == 0 ? 4 : t == 1 ? 6 : (t == 2 || t == 3) ? 4 : 7; }   // none snappy gzip zlib unknown
+__device__ __forceinline__ uint32_t cstr_len_checksum(int32_t t) { return t == 0 ? 4 : t == 1 ? 6 : 7; }                          // none crc32c unknown
+
+// bytes of "[identity][E<code>]" + reason
+__device__ __forceinline__ uint32_t error_text_len(const DevConfig& C, const DevMethod* ms, const b2_msg_desc& d, const MsgAux& a,
+                                                   const uint8_t* frame) {
+    uint32_t n = (C.identity_len ? C.identity_len + 2 : 0) + 3 + dec_len((uint32_t)d.error_code);
+    const uint32_t req_size = d.body_size - d.meta_size;
+    switch (a.err_kind) {
+    case kErrAttachment:   // "attachment_size=%d is larger than request_size=%d"
+        n += 16 + dec_len_i32(d.attachment_size) + 29 + dec_len(req_size); break;
+    case kErrNoService:    // "Fail to find service=%s"
+        n += 21 + strnlen_dev(frame + a.svc_off, a.svc_len); break;
+    case kErrNoMethod:     // "Fail to find method=%s/%s"
+        n += 20 + strnlen_dev(frame + a.svc_off, a.svc_len) + 1 + strnlen_dev(frame + a.mth_off, a.mth_len); break;
+    case kErrParseRequest: // "Fail to parse request=%s, ContentType=%s, CompressType=%s, ChecksumType=%s, request_size=%d"
+        n += 22 + ms[d.method_idx].request_type_len + 14 + 2 /*pb*/ + 15 + cstr_len_compress(d.compress_type) + 15 +
+             cstr_len_checksum(d.checksum_type) + 15 + dec_len(req_size); break;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(128) k_decode(BatchPtrs B, DevConfig C) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_msgs = B.totals[0];
+    if (i >= n_msgs || (B.totals[2] & 1u)) return;
+    const uint32_t fo_raw = B.frame_off[i];
+    const uint32_t fo = fo_raw & 0x7fffffffu;
+    const int proto = (int)(fo_raw >> 31) + 1;
+    const uint8_t* frame = B.bytes + fo;
+    b2_msg_desc d;
+    d.frame_off = fo; d.body_size = load_be32(frame + 4); d.meta_size = load_be32(frame + 8);
+    d.correlation_id = 0; d.log_id = 0; d.attachment_size = 0; d.compress_type = 0; d.checksum_type = 0; d.error_code = 0;
+    d.has_bits = 0; d.protocol = (uint8_t)proto; d.content_type = 0; d.method_idx = -1; d.status = 0; d.resp_off = 0; d.resp_len = 0;
+    // run index: binary search over first_msg (runs without messages are skipped by the <= rule)
+    {
+        uint32_t lo = 0, hi = B.n_runs;
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (B.run_status[mid].first_msg <= i) lo = mid; else hi = mid; }
+        d.run_idx = lo;
+    }
+    MsgAux a; a.msg_off = a.msg_len = a.att_len = a.att_off = a.cks_off = a.cks_len = 0;
+    a.svc_off = a.svc_len = a.mth_off = a.mth_len = 0; a.pad = 0; a.err_kind = kErrNone;
+    uint32_t resp_len = 0;
+    const uint8_t* meta_p = frame + 12;
+    const uint32_t req_size = d.body_size - d.meta_size;
+    if (proto == B2_PROTOCOL_STREAMING_RPC) {
+        StreamMetaOut sm;
+        if (!decode_stream_meta(meta_p, d.meta_size, sm)) d.status = B2_MSG_BAD_STREAM_META;
+        else {
+            d.status = B2_MSG_STREAM_FRAME; d.correlation_id = sm.stream_id; d.log_id = sm.source_stream_id;
+            d.compress_type = sm.frame_type; d.has_bits = (uint16_t)sm.has;
+            d.attachment_size = (int32_t)(uint32_t)((uint64_t)sm.consumed_size & 0xffffffffu);
+            d.checksum_type = (int32_t)(uint32_t)((uint64_t)sm.consumed_size >> 32);
+        }
+    } else {
+        RpcMetaOut m;
+        if (!decode_rpc_meta(meta_p, d.meta_size, m)) d.status = B2_MSG_BAD_META;
+        else {
+            d.correlation_id = m.correlation_id; d.log_id = m.log_id; d.attachment_size = m.attachment_size;
+            d.compress_type = m.compress_type; d.checksum_type = m.checksum_type; d.content_type = (uint8_t)m.content_type;
+            d.has_bits = (uint16_t)m.has;
+            if (m.has & B2_HAS_CHECKSUM_VALUE) { a.cks_off = 12 + m.checksum_value.off; a.cks_len = m.checksum_value.len; }
+            if (m.has & B2_HAS_REQUEST) {
+                a.svc_off = 12 + m.service_name.off; a.svc_len = m.service_name.len;
+                a.mth_off = 12 + m.method_name.off; a.mth_len = m.method_name.len;
+            }
+            const int64_t att = m.attachment_size;
+            const DevMethod* mp = nullptr;
+            if ((m.has & B2_HAS_ATTACHMENT_SIZE) && (int64_t)req_size < att) {
+                a.err_kind = kErrAttachment; d.error_code = B2_EREQUEST;
+            } else {
+                bool no_service;
+                const int mi = find_method(B.methods, C.n_methods, frame + a.svc_off, a.svc_len, frame + a.mth_off, a.mth_len, no_service);
+                if (no_service) { a.err_kind = kErrNoService; d.error_code = B2_ENOSERVICE; }
+                else if (mi < 0) { a.err_kind = kErrNoMethod; d.error_code = B2_ENOMETHOD; }
+                else { d.method_idx = (int16_t)mi; mp = B.methods + mi; }
+            }
+            if (mp && mp->handler == B2_HANDLER_HOST) d.status = B2_MSG_HOST;
+            else if (mp) {
+                int64_t bwo = (int64_t)req_size - att;
+                if (bwo > (int64_t)req_size) bwo = req_size;
+                const uint32_t body_wo_att = (uint32_t)bwo;
+                const uint32_t in_att_len = att > 0 ? (uint32_t)att : 0;
+                if (m.content_type != B2_CONTENT_TYPE_PB) d.status = B2_MSG_UNSUPPORTED;
+                else if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) d.status = B2_MSG_UNSUPPORTED;
+                else if (m.compress_type == B2_COMPRESS_TYPE_SNAPPY) d.status = B2_MSG_UNSUPPORTED;   // TODO(snappy kernels)
+                else if (mp->response_compress_type != B2_COMPRESS_TYPE_NONE) d.status = B2_MSG_UNSUPPORTED;
+                else if (m.compress_type != B2_COMPRESS_TYPE_NONE) { a.err_kind = kErrParseRequest; d.error_code = B2_EREQUEST; }
+                else {
+                    Span msg;
+                    const uint8_t* body = meta_p + d.meta_size;
+                    bool ok = true;
+                    if (m.checksum_type == B2_CHECKSUM_TYPE_CRC32C && a.cks_len != 4) ok = false;   // reference CHECK-aborts; see DESIGN.md
+                    if (ok) ok = decode_echo_request(body, body_wo_att, msg);
+                    if (!ok) { a.err_kind = kErrParseRequest; d.error_code = B2_EREQUEST; }
+                    else {
+                        d.status = B2_MSG_ECHOED;
+                        a.msg_off = 12 + d.meta_size + msg.off; a.msg_len = msg.len;
+                        if (mp->echo_attachment) { a.att_len = in_att_len; a.att_off = 12 + d.meta_size + body_wo_att; }
+                        const uint32_t cks_len = mp->response_checksum_type == B2_CHECKSUM_TYPE_CRC32C ? 4u : a.cks_len;
+                        const uint32_t ml = response_meta_len(0, 0, mp->response_compress_type, m.correlation_id, a.att_len,
+                                                              mp->response_checksum_type, cks_len);
+                        const uint32_t prefix = 12 + ml + 1 + varint_len(msg.len);
+                        resp_len = prefix + msg.len + a.att_len;
+                        a.pad = (fo + a.msg_off - prefix) & 15u;       // payload keeps its (mod 16) alignment
+                    }
+                }
+            }
+            if (a.err_kind != kErrNone) {
+                d.status = B2_MSG_ERROR_REPLIED;
+                const uint32_t tl = error_text_len(C, B.methods, d, a, frame);
+                resp_len = 12 + response_meta_len(d.error_code, tl, 0, m.correlation_id, 0, 0, a.cks_len);
+            }
+            // a CRC-verified request can still turn into an EREQUEST reply in k_pack: reserve for both
+            if (d.status == B2_MSG_ECHOED && m.checksum_type == B2_CHECKSUM_TYPE_CRC32C) {
+                b2_msg_desc e = d; MsgAux ea = a; e.error_code = B2_EREQUEST; ea.err_kind = kErrParseRequest;
+                const uint32_t tl = error_text_len(C, B.methods, e, ea, frame);
+                const uint32_t el = 12 + response_meta_len(B2_EREQUEST, tl, 0, m.correlation_id, 0, 0, a.cks_len);
+                if (a.pad + resp_len < el) resp_len = el - a.pad;   // slot must hold either reply (error reply is packed at pad 0)
+            }
+        }
+    }
+    d.resp_len = resp_len;
+    B.msgs[i] = d;
+    B.aux[i] = a;
+    B.slot[i] = resp_len ? ((a.pad + resp_len + 15u) & ~15u) : 0u;
+}
+
+// --- exclusive scan of slot sizes: 2 kernels ---------------------------------
+constexpr int kScanBlock = 1024, kScanItems = 4;
+__global__ void __launch_bounds__(kScanBlock) k_scan_blocks(BatchPtrs B) {
+    __shared__ uint32_t s_warp[32];
+    const uint32_t n = B.totals[0];
+    const uint32_t base = blockIdx.x * kScanBlock * kScanItems + threadIdx.x * kScanItems;
+    if (blockIdx.x * kScanBlock * kScanItems >= n) return;
+    uint32_t v[kScanItems], sum = 0;
+    #pragma unroll
+    for (int j = 0; j < kScanItems; j++) { v[j] = base + j < n ? B.slot[base + j] : 0; sum += v[j]; }
+    uint32_t x = sum;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = s_warp[threadIdx.x], ws = w;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, ws, d); if (threadIdx.x >= d) ws += y; }
+        s_warp[threadIdx.x] = ws - w;
+        if (threadIdx.x == 31) B.scan_tmp[blockIdx.x] = ws;
+    }
+    __syncthreads();
+    uint32_t excl = s_warp[threadIdx.x >> 5] + x - sum;
+    #pragma unroll
+    for (int j = 0; j < kScanItems; j++) { if (base + j < n) B.slot[base + j] = excl; excl += v[j]; }
+}
+__global__ void __launch_bounds__(1024) k_scan_top(BatchPtrs B) {
+    // serial-by-chunks exclusive scan of the block sums (<= a few thousand entries)
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t n = B.totals[0];
+    const uint32_t nb = (n + kScanBlock * kScanItems - 1) / (kScanBlock * kScanItems);
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t v = i < nb ? B.scan_tmp[i] : 0, x = v;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = s_warp[threadIdx.x], ws = w;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, ws, d); if (threadIdx.x >= d) ws += y; }
+            s_warp[threadIdx.x] = ws - w;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + s_warp[threadIdx.x >> 5] + x - v;
+        if (i < nb) B.scan_tmp[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { B.totals[1] = s_carry; if (s_carry > B.max_resp) B.totals[2] |= 2u; }
+}
+
+// --- k_pack: one warp per message --------------------------------------------
+__device__ __constant__ uint32_t c_crc_table[256];   // CRC-32C byte table (poly 0x82f63b78 reflected)
+
+__device__ __forceinline__ uint32_t crc32c_bytes_serial(uint32_t l, const uint8_t* p, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) l = c_crc_table[(l ^ p[i]) & 0xff] ^ (l >> 8);
+    return l;
+}
+
+// byte j of the base-128 varint of v (n bytes long)
+__device__ __forceinline__ uint8_t varint_byte(uint64_t v, uint32_t j, uint32_t n) {
+    return (uint8_t)(((v >> (7 * j)) & 0x7f) | (j + 1 < n ? 0x80 : 0));
+}
+
+// serial emitters used by the (rare) error-reply path
+__device__ __forceinline__ uint8_t* put_str(uint8_t* p, const char* s, uint32_t n) { for (uint32_t i = 0; i < n; i++) p[i] = (uint8_t)s[i]; return p + n; }
+__device__ __forceinline__ uint8_t* put_bytes(uint8_t* p, const uint8_t* s, uint32_t n) { for (uint32_t i = 0; i < n; i++) p[i] = s[i]; return p + n; }
+
+__device__ __noinline__ uint32_t pack_error_reply(uint8_t* out, const DevConfig& C, const DevMethod* ms, const b2_msg_desc& d,
+                                                  const MsgAux& a, const uint8_t* frame) {
+    const uint32_t tl = error_text_len(C, ms, d, a, frame);
+    const uint32_t req_size = d.body_size - d.meta_size;
+    const uint32_t ml = response_meta_len(d.error_code, tl, 0, d.correlation_id, 0, 0, a.cks_len);
+    uint8_t* p = out;
+    p = put_str(p, "PRPC", 4); p = put_be32(p, ml); p = put_be32(p, ml);
+    const uint32_t rm = 1 + varint_len((uint64_t)(int64_t)d.error_code) + 1 + varint_len(tl) + tl;
+    *p++ = 0x12; p = put_varint(p, rm);
+    *p++ = 0x08; p = put_varint(p, (uint64_t)(int64_t)d.error_code);
+    *p++ = 0x12; p = put_varint(p, tl);
+    if (C.identity_len) { *p++ = '['; p = put_str(p, C.identity, C.identity_len); *p++ = ']'; }
+    *p++ = '['; *p++ = 'E'; p = put_dec(p, (uint32_t)d.error_code); *p++ = ']';
+    switch (a.err_kind) {
+    case kErrAttachment:
+        p = put_str(p, "attachment_size=", 16); p = put_dec_i32(p, d.attachment_size);
+        p = put_str(p, " is larger than request_size=", 29); p = put_dec(p, req_size); break;
+    case kErrNoService:
+        p = put_str(p, "Fail to find service=", 21); p = put_bytes(p, frame + a.svc_off, strnlen_dev(frame + a.svc_off, a.svc_len)); break;
+    case kErrNoMethod:
+        p = put_str(p, "Fail to find method=", 20); p = put_bytes(p, frame + a.svc_off, strnlen_dev(frame + a.svc_off, a.svc_len));
+        *p++ = '/'; p = put_bytes(p, frame + a.mth_off, strnlen_dev(frame + a.mth_off, a.mth_len)); break;
+    case kErrParseRequest: {
+        const DevMethod& m = ms[d.method_idx];
+        p = put_str(p, "Fail to parse request=", 22); p = put_str(p, m.request_type, m.request_type_len);
+        p = put_str(p, ", ContentType=", 14); p = put_str(p, "pb", 2);
+        p = put_str(p, ", CompressType=", 15);
+        { const int32_t t = d.compress_type; p = put_str(p, t == 0 ? "none" : t == 1 ? "snappy" : t == 2 ? "gzip" : t == 3 ? "zlib" : "unknown", cstr_len_compress(t)); }
+        p = put_str(p, ", ChecksumType=", 15);
+        { const int32_t t = d.checksum_type; p = put_str(p, t == 0 ? "none" : t == 1 ? "crc32c" : "unknown", cstr_len_checksum(t)); }
+        p = put_str(p, ", request_size=", 15); p = put_dec(p, req_size); break; }
+    }
+    *p++ = 0x18; *p++ = 0x00;                                  // compress_type = 0
+    *p++ = 0x20; p = put_varint(p, (uint64_t)d.correlation_id);
+    *p++ = 0x50; *p++ = 0x00;                                  // content_type = PB
+    *p++ = 0x58; *p++ = 0x00;                                  // checksum_type = 0
+    *p++ = 0x62; p = put_varint(p, a.cks_len); p = put_bytes(p, frame + a.cks_off, a.cks_len);   // request's checksum_value travels back
+    return (uint32_t)(p - out);
+}
+
+// copy n bytes src -> dst with the whole warp; fast path when both share (mod 16) alignment
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane) {
+    if ((((uintptr_t)dst ^ (uintptr_t)src) & 15u) == 0) {
+        const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u));
+        if (lane < head) dst[lane] = src[lane];
+        const uint32_t nv = (n - head) >> 4;
+        const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+        uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+        uint32_t i = lane;
+        for (; i + 96 < nv; i += 128) {                        // 4 independent 16 B loads in flight per lane
+            const uint4 a = __ldg(s4 + i), b = __ldg(s4 + i + 32), c = __ldg(s4 + i + 64), d = __ldg(s4 + i + 96);
+            d4[i] = a; d4[i + 32] = b; d4[i + 64] = c; d4[i + 96] = d;
+        }
+        for (; i < nv; i += 32) d4[i] = __ldg(s4 + i);
+        const uint32_t done = head + (nv << 4);
+        if (lane < n - done) dst[done + lane] = src[done + lane];
+    } else {
+        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pack(BatchPtrs B, DevConfig C) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_msgs = B.totals[0];
+    if (i >= n_msgs || (B.totals[2] & 3u)) return;
+    const uint32_t bi = i / (kScanBlock * kScanItems);
+    const uint32_t slot_off = B.slot[i] + B.scan_tmp[bi];
+    const b2_msg_desc d = B.msgs[i];
+    if (d.resp_len == 0) { if (lane == 0) B.msgs[i].resp_off = slot_off; return; }
+    const MsgAux a = B.aux[i];
+    const uint8_t* frame = B.bytes + d.frame_off;
+    const DevMethod* mp = d.method_idx >= 0 ? B.methods + d.method_idx : nullptr;
+    uint16_t status = d.status;
+    if (status == B2_MSG_ECHOED && d.checksum_type == B2_CHECKSUM_TYPE_CRC32C) {
+        // Crc32cVerify (policy/crc32c_checksum.cpp:44-61) over body_wo_att
+        const uint32_t req_size = d.body_size - d.meta_size;
+        int64_t bwo = (int64_t)req_size - (int64_t)d.attachment_size; if (bwo > (int64_t)req_size) bwo = req_size;
+        uint32_t ok = 1;
+        if (lane == 0) {
+            const uint32_t crc = crc32c_bytes_serial(0xffffffffu, frame + 12 + d.meta_size, (uint32_t)bwo) ^ 0xffffffffu;
+            const uint32_t expected = crc32c_unmask(load_be32(frame + a.cks_off));
+            ok = crc == expected;
+        }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) status = B2_MSG_ERROR_REPLIED;
+    }
+    if (status == B2_MSG_ERROR_REPLIED) {
+        uint32_t n = 0;
+        if (lane == 0) {
+            b2_msg_desc e = d; MsgAux ea = a;
+            if (d.status == B2_MSG_ECHOED) { e.error_code = B2_EREQUEST; ea.err_kind = kErrParseRequest; }
+            n = pack_error_reply(B.resp + slot_off, C, B.methods, e, ea, frame);
+            B.msgs[i].resp_off = slot_off; B.msgs[i].resp_len = n;
+            if (d.status == B2_MSG_ECHOED) { B.msgs[i].status = B2_MSG_ERROR_REPLIED; B.msgs[i].error_code = B2_EREQUEST; }
+        }
+        return;
+    }
+    // ---- OK echo reply: SendRpcResponse with append_body -----------------------------------
+    const int32_t r_cks_type = mp->response_checksum_type;
+    const uint32_t cks_len = r_cks_type == B2_CHECKSUM_TYPE_CRC32C ? 4u : a.cks_len;
+    const uint32_t ml = response_meta_len(0, 0, 0, d.correlation_id, a.att_len, r_cks_type, cks_len);
+    const uint32_t vl = varint_len(a.msg_len);
+    const uint32_t prefix = 12 + ml + 1 + vl;
+    const uint32_t body_len = 1 + vl + a.msg_len;
+    const uint32_t resp_len = prefix + a.msg_len + a.att_len;
+    uint8_t* out = B.resp + slot_off + a.pad;
+    uint32_t crc_be = 0;
+    if (r_cks_type == B2_CHECKSUM_TYPE_CRC32C) {
+        // Crc32cCompute (policy/crc32c_checksum.cpp:28-42) over the serialized EchoResponse
+        if (lane == 0) {
+            uint32_t l = 0xffffffffu;
+            uint8_t hdr[6]; hdr[0] = 0x0a; uint8_t* e = put_varint(hdr + 1, a.msg_len);
+            l = crc32c_bytes_serial(l, hdr, (uint32_t)(e - hdr));
+            l = crc32c_bytes_serial(l, frame + a.msg_off, a.msg_len);
+            crc_be = crc32c_mask(l ^ 0xffffffffu);
+        }
+        crc_be = __shfl_sync(0xffffffffu, crc_be, 0);
+    }
+    // lane-parallel prefix: lane j produces byte j (+32, +64 ...) of
+    //   "PRPC" be32(body) be32(meta) | 12 02 08 00 | 18 00 | 20 cid | [28 att] | 50 00 | 58 ck | 62 len cks | 0a len
+    const uint32_t cid_n = varint_len((uint64_t)d.correlation_id);
+    const uint32_t att_n = a.att_len ? 1 + varint_len(a.att_len) : 0;
+    const uint32_t o_cid = 12 + 6;                 // after 12 02 08 00 18 00
+    const uint32_t o_att = o_cid + 1 + cid_n;
+    const uint32_t o_ct = o_att + att_n;           // 50 00 58 xx 62
+    const uint32_t o_ckl = o_ct + 5;               // varint(cks_len)
+    const uint32_t ckl_n = varint_len(cks_len);
+    const uint32_t o_ckv = o_ckl + ckl_n;
+    const uint32_t o_pb = o_ckv + cks_len;         // == 12 + ml
+    const uint32_t total_body = ml + body_len + a.att_len;
+    for (uint32_t j = lane; j < prefix; j += 32) {
+        uint8_t b;
+        if (j < 4) b = (uint8_t)(kMagicPRPC >> (8 * j));
+        else if (j < 8) b = (uint8_t)(total_body >> (8 * (7 - j)));
+        else if (j < 12) b = (uint8_t)(ml >> (8 * (11 - j)));
+        else if (j < o_cid) { const uint32_t k = j - 12; b = (k == 0) ? 0x12 : (k == 1) ? 0x02 : (k == 2) ? 0x08 : (k == 4) ? 0x18 : 0x00; }
+        else if (j == o_cid) b = 0x20;
+        else if (j < o_att) b = varint_byte((uint64_t)d.correlation_id, j - o_cid - 1, cid_n);
+        else if (j < o_ct) b = (j == o_att) ? 0x28 : varint_byte(a.att_len, j - o_att - 1, att_n - 1);
+        else if (j < o_ckl) { const uint32_t k = j - o_ct; b = (k == 0) ? 0x50 : (k == 2) ? 0x58 : (k == 3) ? (uint8_t)r_cks_type : (k == 4) ? 0x62 : 0x00; }
+        else if (j < o_ckv) b = varint_byte(cks_len, j - o_ckl, ckl_n);
+        else if (j < o_pb) b = (r_cks_type == B2_CHECKSUM_TYPE_CRC32C) ? (uint8_t)(crc_be >> (8 * (3 - (j - o_ckv)))) : frame[a.cks_off + (j - o_ckv)];
+        else if (j == o_pb) b = 0x0a;
+        else b = varint_byte(a.msg_len, j - o_pb - 1, vl);
+        out[j] = b;
+    }
+    // payload: message bytes (+ attachment when it directly follows them, the normal layout)
+    if (a.att_len && a.att_off == a.msg_off + a.msg_len) {
+        warp_copy(out + prefix, frame + a.msg_off, a.msg_len + a.att_len, lane);
+    } else {
+        warp_copy(out + prefix, frame + a.msg_off, a.msg_len, lane);
+        if (a.att_len) warp_copy(out + prefix + a.msg_len, frame + a.att_off, a.att_len, lane);
+    }
+    if (lane == 0) { B.msgs[i].resp_off = slot_off + a.pad; B.msgs[i].resp_len = resp_len; }
+}
+
+// --- k_finalize: per-run response span + counters ----------------------------
+__global__ void __launch_bounds__(256) k_finalize(BatchPtrs B) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B.n_runs) return;
+    if (B.totals[2] & 3u) return;
+    b2_run_status st = B.run_status[r];
+    const uint32_t n_msgs = B.totals[0];
+    auto off_of = [&](uint32_t i) -> uint32_t {
+        if (i >= n_msgs) return B.totals[1];
+        return B.slot[i] + B.scan_tmp[i / (kScanBlock * kScanItems)];
+    };
+    st.resp_off = off_of(st.first_msg);
+    st.resp_bytes = off_of(st.first_msg + st.n_msgs) - st.resp_off;
+    B.run_status[r] = st;
+    atomicAdd(B.counters + 0, (unsigned long long)st.consumed);
+    atomicAdd(B.counters + 1, (unsigned long long)st.n_msgs);
+    atomicAdd(B.counters + 2, (unsigned long long)st.resp_bytes);
+    if (st.parse_error != B2_PARSE_ERROR_NOT_ENOUGH_DATA) atomicAdd(B.counters + 4, 1ull);
+    if (r == 0) atomicAdd(B.counters + 5, 1ull);
+}
+
+#endif  // __CUDACC__
+}  // namespace b2

@@ -206,6 +206,10 @@ const char* b2_version(void);
  * Returns the method index (>= 0) or a negative B2_E_*. */
 int  b2_register_method(b2_ctx* ctx, const b2_method* m);
 
+/* "ip:port" that Controller::AppendServerIdentiy (src/brpc/controller.cpp:407-428)
+ * prepends to every error text as "[ip:port]"; NULL/"" = no server identity. */
+int  b2_set_server_identity(b2_ctx* ctx, const char* ip_port);
+
 /* ---- block pool: assignable to butil::iobuf::blockmem_allocate/deallocate
  * (src/butil/iobuf.cpp:168-169), same role as rdma::block_pool
  * (src/brpc/rdma/rdma_helper.cpp:579-582).  Memory is cudaHostAlloc'ed. ------ */

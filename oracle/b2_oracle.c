@@ -621,6 +621,9 @@ static int process_rpc_request(const orc_config* cfg, const uint8_t* frame, b2_m
         /* DeserializeRpcMessage :498-566 */
         int ok = 1;
         if (m.content_type != B2_CONTENT_TYPE_PB) { d->status = B2_MSG_UNSUPPORTED; return 0; }
+        /* scope decision: DEFLATE codecs and non-pb content types are outside
+         * this path; such requests are surfaced untouched, before any checksum work */
+        if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) { d->status = B2_MSG_UNSUPPORTED; return 0; }
         if (m.checksum_type == B2_CHECKSUM_TYPE_CRC32C) {                  /* Crc32cVerify, crc32c_checksum.cpp:44-61 */
             if (req_cks_len != 4) ok = 0;   /* reference CHECK_EQ-aborts here; treated as a failed verify */
             else {
@@ -642,8 +645,6 @@ static int process_rpc_request(const orc_config* cfg, const uint8_t* frame, b2_m
                     if (!g_sn_u((const char*)req_buf, req_buf_len, (char*)unz, ulen, &got)) ok = 0;
                     pb = unz; pb_len = got;
                 }
-            } else if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) {
-                d->status = B2_MSG_UNSUPPORTED; return 0;                    /* DEFLATE: out of scope */
             } else ok = 0;                                                   /* FindCompressHandler == NULL */
         }
         if (ok) ok = orc_parse_echo_request(pb, pb_len, &msg);
