@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — echo QPS of the B200 brpc hot path (BASELINE.json metric).
+
+Workload (config.workload): BASELINE configs[1] — example/multi_threaded_echo_c++ shape:
+64 client connections per GPU, baidu_std, 1 KB 'r' payload (client.cpp:116), every
+connection's read buffer holding RUN_MIB MiB of pipelined requests whose last frame
+is cut mid-way.  One *step* = one pass of the whole hot path over one such batch
+(cut loop -> RpcMeta decode -> echo -> response pack), 256 MiB in / ~249 MiB out at
+N=1, i.e. larger than the 126 MB L2, so no L2 flush is needed between iterations.
+
+  value    : messages/s with the batch resident in HBM (kernel pipeline only)
+  e2e      : messages/s through b2_process_batch with PINNED HOST buffers, H2D of the
+             request bytes and D2H of descriptors + response bytes inside the timed region
+  roofline : dominant kernel (k_pack) algorithmic bytes / CUDA-event time vs measured HBM peak
+  cpu_baseline : the oracle port (oracle/liboracle.so) on the host cores, bounded sample
+
+`--impl reference` times the CPU implementation of the same path on all host threads
+(the reference itself cannot be built: SURVEY §0 — protoc/libprotobuf/gflags absent).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+PAYLOAD = 1024
+N_SOCKETS = 64
+DESC_BYTES = 64
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill(); out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_batch(run_mib, rank, pinned=True):
+    from brpc_b200 import press
+    from brpc_b200.abi import PinnedBuffer
+    run_bytes = (run_mib << 20) - 16 * 7          # not a multiple of the frame: every run ends mid-frame
+    stride = (run_bytes + 15) // 16 * 16
+    nbytes = N_SOCKETS * stride
+    buf = PinnedBuffer(nbytes) if pinned else None
+    data = buf.array if pinned else np.zeros(nbytes, np.uint8)
+    sp = press.spec(payload_bytes=PAYLOAD, payload_kind=0)
+    # sockets are sharded over GPUs by socket id: rank r serves ids r*64 .. r*64+63
+    runs, n_full = press.fill_batch(sp, data, N_SOCKETS, run_bytes, start_index=rank * 1000003)
+    runs["socket_id"] += rank * N_SOCKETS
+    return buf, data, runs, n_full, nbytes
+
+
+def cpu_arm(data, runs, threads, min_seconds):
+    """Time the oracle port over `runs` with `threads` host threads (ctypes drops the GIL)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as O
+    cfg = O.make_config()
+    parts = [p for p in np.array_split(np.arange(len(runs)), threads) if len(p)]
+    bufs = []
+    for p in parts:
+        sub = np.ascontiguousarray(runs[p])
+        nb = int(sub["length"].sum())
+        bufs.append((sub, np.zeros(len(p), O.RUN_STATUS_DT), np.zeros(nb // 1000 + 64, O.MSG_DT),
+                     np.zeros(nb + (1 << 16), np.uint8), C.c_uint32(), C.c_uint32()))
+    total = {"msgs": 0}
+
+    def work(b):
+        sub, rs, msgs, resp, nm, rb = b
+        rc = O.lib.orc_process_batch(C.byref(cfg), data.ctypes.data, data.nbytes, sub.ctypes.data, len(sub), rs.ctypes.data,
+                                     msgs.ctypes.data, len(msgs), C.byref(nm), resp.ctypes.data, len(resp), C.byref(rb))
+        assert rc == 0
+
+    def one_pass():
+        ts = [threading.Thread(target=work, args=(b,)) for b in bufs]
+        t0 = time.perf_counter()
+        for t in ts: t.start()
+        for t in ts: t.join()
+        dt = time.perf_counter() - t0
+        return dt, sum(b[4].value for b in bufs)
+
+    one_pass()                                    # warm-up: page faults, tables
+    best, n, spent = None, 0, 0.0
+    while spent < min_seconds or n < 3:
+        dt, msgs = one_pass()
+        spent += dt; n += 1
+        if best is None or dt < best[0]:
+            best = (dt, msgs)
+    return best[1] / best[0], best[1], n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--run-mib", type=int, default=4, help="MiB pending per connection per batch")
+    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    hbm_peak, peak_src = read_peaks()
+    ncores = os.cpu_count() or 1
+    workload = ("multi_threaded_echo_c++ baidu_std 1 KB: %d connections/GPU x %d MiB pending, 'r' payload, "
+                "runs cut mid-frame; batch %d MiB > L2 (no flush needed)" % (N_SOCKETS, args.run_mib, N_SOCKETS * args.run_mib))
+    config = {"workload": workload, "payload_bytes": PAYLOAD, "connections_per_gpu": N_SOCKETS,
+              "run_mib": args.run_mib, "l2": "inputs larger than L2", "sharding": "socket_id %% %d" % max(1, world)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        _, data, runs, n_full, nbytes = build_batch(min(args.run_mib, 2), 0, pinned=False)
+        t0 = time.perf_counter()
+        qps, msgs, passes = cpu_arm(data, runs, ncores, min_seconds=min(20.0, 1.0 * steps))
+        line = {"impl": "reference", "metric": "echo QPS, 1 KB baidu_std", "value": qps, "unit": "msgs/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * msgs / qps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": qps, "unit": "msgs/s", "cores": ncores, "kind": "port",
+                                 "sample": "%d connections x %d MiB (%d msgs/pass), best of %d passes, %d threads; "
+                                           "oracle port of the reference path (brpc itself cannot be built here)"
+                                           % (N_SOCKETS, min(args.run_mib, 2), msgs, passes, ncores)},
+                "e2e": {"value": qps, "unit": "msgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "wall_s": time.perf_counter() - t0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import brpc_b200
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank if use_dist else 0
+    torch.cuda.set_device(dev)
+
+    buf, data, runs, n_full, nbytes = build_batch(args.run_mib, rank)
+    ctx = brpc_b200.Context(device=dev, max_batch_bytes=nbytes + (1 << 20), max_msgs=n_full + 4096,
+                            max_runs=N_SOCKETS, tile_bytes=args.tile)
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness gate before timing: every message echoed, lengths obey the frame law -------
+    rs, msgs, resp, info = ctx.process_batch_ptr(buf.ptr, nbytes, runs)
+    assert len(msgs) == n_full and np.all(msgs["status"] == 0), "bench batch did not echo cleanly"
+    launches_per_step = info["n_launches"]
+    req_bytes = int(rs["consumed"].sum())
+    resp_frame_bytes = int(msgs["resp_len"].sum())
+    d2h_bytes = int(len(msgs) * 64 + len(rs) * 32 + int(rs["resp_bytes"].sum()))
+    h2d_bytes = int(nbytes + runs.nbytes + 4 * (len(runs) + 1))
+
+    # ---- value: resident batch, kernel pipeline only -------------------------------------------
+    ctx.upload_ptr(buf.ptr, nbytes, runs)
+    ctx.execute_many(warmup)
+    sampler = ClockSampler(dev); sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, n_launch = ctx.execute_many(steps)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    # per-stage device times (CUDA events between the launches of one pass), averaged
+    stage_acc = {}
+    for _ in range(5):
+        ctx.execute()
+        for name, ms in ctx.stage_times():
+            stage_acc.setdefault(name, []).append(ms)
+    stages = {k: statistics.mean(v) for k, v in stage_acc.items()}
+
+    # ---- e2e: host buffers, copies inside the timed region --------------------------------------
+    e2e_steps = max(3, min(steps, 10))
+    for _ in range(2):
+        ctx.process_batch_ptr(buf.ptr, nbytes, runs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.process_batch_ptr(buf.ptr, nbytes, runs)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
+    # ---- reduce over ranks: max time, summed messages; NCCL all-reduce of the bvar-like counters --
+    t_dev = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n_full)], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        counters = torch.tensor(ctx.counters(), dtype=torch.int64, device="cuda")
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)      # Adder semantics (bvar/reducer.h:335)
+        counters = counters.tolist()
+    else:
+        counters = ctx.counters()
+    dev_ms_max, e2e_ms_max, wall_ms_max = t_dev.tolist()
+    total_msgs = tot.item()
+    ms_per_step = dev_ms_max / steps
+    value = total_msgs / (ms_per_step * 1e-3)
+    e2e_value = total_msgs / (e2e_ms_max * 1e-3)
+
+    if rank == 0:
+        # roofline of the dominant kernel, from THIS rank's stage times
+        dom = max(stages, key=stages.get)
+        pack_alg = float(int(msgs["resp_len"].sum()) + len(msgs) * (PAYLOAD + DESC_BYTES))   # resp written + payload & desc read
+        alg = {"pack": pack_alg}
+        dom_alg = alg.get(dom, float(req_bytes + resp_frame_bytes + DESC_BYTES * len(msgs)))
+        achieved = dom_alg / (stages[dom] * 1e-3) / 1e9
+        pipe_alg = float(req_bytes + resp_frame_bytes + DESC_BYTES * len(msgs))               # req + resp + 64 B desc
+        pipe_ms = sum(stages.values())
+        line = {"metric": "echo QPS, 1 KB baidu_std", "value": value, "unit": "msgs/s", "n_gpus": world if use_dist else 1,
+                "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+                "e2e": {"value": e2e_value, "unit": "msgs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "ms_per_step": e2e_ms_max, "note": "b2_process_batch, pinned host buffers, copies serial with kernels"},
+                "gpu_launches": int(n_launch),
+                "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": dom_alg, "kernel_ms": stages[dom]},
+                "roofline_pipeline": {"achieved": pipe_alg / (pipe_ms * 1e-3) / 1e9, "frac": pipe_alg / (pipe_ms * 1e-3) / 1e9 / hbm_peak,
+                                      "algorithmic_bytes_per_msg": pipe_alg / len(msgs), "stage_ms": stages},
+                "clocks": clocks, "wall_ms_per_step": wall_ms_max / steps, "msgs_per_step": total_msgs,
+                "counters_allreduced": counters}
+        if not args.no_cpu_baseline:
+            # bounded sample: the first 8 connections of the same batch, 1 thread, ~10 s
+            sub = runs[:8].copy()
+            q1, m1, p1 = cpu_arm(data, sub, 1, min_seconds=8.0)
+            line["cpu_baseline"] = {"value": q1, "unit": "msgs/s", "cores": 1, "kind": "port",
+                                    "sample": "8 of the %d connections (%d msgs/pass), best of %d passes, single thread" % (N_SOCKETS, m1, p1)}
+        print(json.dumps(line))
+    if use_dist:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -62,6 +62,7 @@ def _load():
     l.b2_process_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(BatchResult)]
     l.b2_batch_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
     l.b2_batch_execute.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+    l.b2_batch_execute_many.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
     l.b2_batch_download.argtypes = [C.c_void_p, C.POINTER(BatchResult)]
     l.b2_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     l.b2_crc32c_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
@@ -75,7 +76,7 @@ lib = _load()
 # every symbol include/b2rpc.h declares (tests check the library exports them)
 ABI_SYMBOLS = ["b2_ctx_create", "b2_ctx_destroy", "b2_last_error", "b2_version", "b2_register_method",
                "b2_set_server_identity", "b2_block_alloc", "b2_block_free", "b2_process_batch", "b2_batch_upload",
-               "b2_batch_execute", "b2_batch_download", "b2_stage_times", "b2_crc32c_batch", "b2_counters_read",
+               "b2_batch_execute", "b2_batch_execute_many", "b2_batch_download", "b2_stage_times", "b2_crc32c_batch", "b2_counters_read",
                "b2_counters_device_ptr"]
 
 ECHO_METHOD = dict(service_full_name=b"example.EchoService", service_name=b"EchoService", method_name=b"Echo",
@@ -173,6 +174,11 @@ class Context:
     def execute(self):
         ms, n = C.c_float(0), C.c_uint32(0)
         _check(lib.b2_batch_execute(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def execute_many(self, steps):
+        ms, n = C.c_float(0), C.c_uint32(0)
+        _check(lib.b2_batch_execute_many(self._h, steps, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
     def download(self):

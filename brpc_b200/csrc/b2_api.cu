@@ -31,11 +31,11 @@ struct b2_ctx {
     std::vector<DevMethod> methods;
     // device
     uint8_t* d_bytes = nullptr; b2_run* d_runs = nullptr; uint32_t* d_run_tile_base = nullptr;
-    TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; b2_run_status* d_run_status = nullptr;
+    TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; uint32_t* d_tile_scratch = nullptr; b2_run_status* d_run_status = nullptr;
     uint32_t* d_frame_off = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr;
     uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr;
     unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
-    uint32_t max_tiles = 0;
+    uint32_t max_tiles = 0; uint32_t n_sms = 148;
     // pinned host mirrors
     b2_run_status* h_run_status = nullptr; b2_msg_desc* h_msgs = nullptr; uint8_t* h_resp = nullptr;
     uint32_t* h_totals = nullptr; uint32_t* h_run_tile_base = nullptr;
@@ -71,7 +71,7 @@ extern "C" void b2_block_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" void b2_ctx_destroy(b2_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->opt.device);
-    cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base);
+    cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch);
     cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_slot);
     cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods);
     cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
@@ -93,6 +93,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     }
     CU(cudaSetDevice(o->device));
     b2_ctx* c = new b2_ctx();
+    { int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, o->device); c->n_sms = (uint32_t)v; }
     for (int i = 0; i <= kMaxStages; i++) c->ev[i] = nullptr;
     c->opt = *o;
     uint32_t tile = o->tile_bytes ? o->tile_bytes : 8192;
@@ -115,6 +116,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     ALLOC(c->d_run_tile_base, 4 * ((size_t)o->max_runs + 1));
     ALLOC(c->d_tiles, sizeof(TileRec) * (size_t)c->max_tiles);
     ALLOC(c->d_tile_base, 4 * (size_t)c->max_tiles);
+    ALLOC(c->d_tile_scratch, 12 * (size_t)c->max_tiles);
     ALLOC(c->d_run_status, sizeof(b2_run_status) * (size_t)o->max_runs);
     ALLOC(c->d_frame_off, 4 * (size_t)o->max_msgs);
     ALLOC(c->d_msgs, sizeof(b2_msg_desc) * (size_t)o->max_msgs);
@@ -176,7 +178,7 @@ extern "C" int b2_register_method(b2_ctx* c, const b2_method* m) {
 static BatchPtrs make_ptrs(b2_ctx* c) {
     BatchPtrs B;
     B.bytes = c->d_bytes; B.runs = c->d_runs; B.run_tile_base = c->d_run_tile_base; B.tiles = c->d_tiles;
-    B.tile_base = c->d_tile_base; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.msgs = c->d_msgs;
+    B.tile_base = c->d_tile_base; B.tile_scratch = c->d_tile_scratch; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.msgs = c->d_msgs;
     B.aux = c->d_aux; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.counters = c->d_counters;
     B.totals = c->d_totals; B.methods = c->d_methods;
     B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes;
@@ -227,15 +229,13 @@ static int launch_pipeline(b2_ctx* c) {
     }
     k_run_prefix<<<1, 1024, 0, s>>>(B); launches++; mark("run_prefix");
     if (c->n_tiles) { k_frame_table<<<(c->n_tiles + 127) / 128, 128, 0, s>>>(B, C); launches++; mark("frame_table"); }
-    // message-count dependent grids are sized for the capacity bound of this batch (nbytes / 12)
-    // and exit early on the device-side count
-    uint64_t bound = (uint64_t)c->nbytes / 12 + 1;
-    if (bound > c->opt.max_msgs) bound = c->opt.max_msgs;
-    const uint32_t mb = (uint32_t)bound;
-    k_decode<<<(mb + 127) / 128, 128, 0, s>>>(B, C); launches++; mark("decode");
-    k_scan_blocks<<<(mb + kScanBlock * kScanItems - 1) / (kScanBlock * kScanItems), kScanBlock, 0, s>>>(B); launches++;
+    // message-count dependent kernels are persistent: fixed grids (multiples of the SM count)
+    // stride over the device-side message count, so no host round trip sizes a launch
+    const uint32_t sms = c->n_sms;
+    k_decode<<<sms * 8, 128, 0, s>>>(B, C); launches++; mark("decode");
+    k_scan_blocks<<<sms, kScanBlock, 0, s>>>(B); launches++;
     k_scan_top<<<1, 1024, 0, s>>>(B); launches++; mark("scan");
-    k_pack<<<(uint32_t)(((uint64_t)mb * 32 + 255) / 256), 256, 0, s>>>(B, C); launches++; mark("pack");
+    k_pack<<<sms * B2_PACK_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack");
     k_finalize<<<(c->n_runs + 255) / 256, 256, 0, s>>>(B); launches++; mark("finalize");
     c->n_stages = st; c->last_launches = launches;
     CU(cudaGetLastError());
@@ -253,6 +253,30 @@ extern "C" int b2_batch_execute(b2_ctx* c, float* kernel_ms, uint32_t* n_launche
     c->last_kernel_ms = ms; c->executed = true;
     if (kernel_ms) *kernel_ms = ms;
     if (n_launches) *n_launches = c->last_launches;
+    return B2_OK;
+}
+
+extern "C" int b2_batch_execute_many(b2_ctx* c, uint32_t steps, float* total_ms, uint32_t* n_launches) {
+    if (!c || !c->uploaded || steps == 0) { set_err("no batch uploaded"); return B2_E_INVAL; }
+    CU(cudaSetDevice(c->opt.device));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, c->stream));
+    uint32_t launches = 0;
+    for (uint32_t i = 0; i < steps; i++) {
+        int rc = launch_pipeline(c);
+        if (rc != B2_OK) return rc;
+        launches += c->last_launches;
+    }
+    CU(cudaEventRecord(e1, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c->executed = true;
+    if (c->n_stages) { float t = 0.f; cudaEventElapsedTime(&t, c->ev[0], c->ev[c->n_stages]); c->last_kernel_ms = t; }
+    if (total_ms) *total_ms = ms;
+    if (n_launches) *n_launches = launches;
     return B2_OK;
 }
 

@@ -73,6 +73,7 @@ struct BatchPtrs {
     const uint32_t* run_tile_base;   // [n_runs+1] first tile of each run
     TileRec* tiles;
     uint32_t* tile_base;             // [n_tiles] run-relative index of the tile's first message
+    uint32_t* tile_scratch;          // [3 * n_tiles] k_resolve spill when a run's tiles exceed shared memory
     b2_run_status* run_status;
     uint32_t* frame_off;             // [max_msgs] frame offsets (batch-relative), bit31.. unused
     b2_msg_desc* msgs;
@@ -187,10 +188,28 @@ __global__ void __launch_bounds__(128) k_tile_walk(BatchPtrs B, DevConfig C) {
 }
 
 // --- k_resolve: one CTA per run ---------------------------------------------
-// Walks the tile chain from position 0 with the true preferred index.  A tile's
-// summary is used only when the chain arrives exactly at its speculated entry
-// (by induction every used summary is what a sequential walk would have
+// Verifies the speculation chain from position 0 with the true preferred index.
+// A tile's summary is used only when the chain arrives exactly at its speculated
+// entry (by induction every used summary is what a sequential walk would have
 // produced); otherwise the tile is re-walked here, scalar, from the true entry.
+//   phase 1 (all threads): per tile, the link to the next tile on the chain
+//   phase 2 (thread 0)   : hop along the links, one shared-memory load per hop;
+//                          broken links / pf-sensitive tiles take the scalar path
+//   phase 3 (all threads): message-index base and preferred index of every live tile
+constexpr uint32_t kLinkOk = 0x80000000u;      // | next tile index
+constexpr uint32_t kLinkStop = 0x40000000u;    // chain ends inside this tile (non-OK step)
+constexpr uint32_t kLinkEnd = 0x20000000u;     // chain leaves the run's tiles (pos == len)
+constexpr uint32_t kLinkBroken = 0x10000000u;  // | next tile index: its entry is not where we arrive
+constexpr uint32_t kLinkRewalk = 0x08000000u;  // this tile itself must be re-walked (no entry / ambiguous)
+
+__device__ __forceinline__ uint32_t make_link(const TileRec& t, const TileRec* tiles, uint32_t nt, uint32_t shift) {
+    if (t.entry == kNone || t.kind == kAmbig) return kLinkRewalk;
+    if (t.kind == kStop) return kLinkStop;
+    const uint32_t j = t.exit >> shift;
+    if (j >= nt) return kLinkEnd;
+    return (tiles[j].entry == t.exit ? kLinkOk : kLinkBroken) | j;
+}
+
 __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C) {
     extern __shared__ uint32_t sm[];
     const uint32_t r = blockIdx.x;
@@ -199,50 +218,93 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C) {
     const uint32_t len = run.length;
     const uint32_t tb = B.run_tile_base[r], nt = B.run_tile_base[r + 1] - tb;
     TileRec* tiles = B.tiles + tb;
-    __shared__ uint32_t s_use_smem;
-    // smem mirror: [0,nt) entry, [nt,2nt) exit, [2nt,3nt) count<<8 | kind<<6 | (last_proto & 3)
     const bool fits = nt * 12u <= 200u * 1024u;
-    if (threadIdx.x == 0) s_use_smem = fits;
-    if (fits) {
-        for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) {
-            const TileRec t = tiles[i];
-            sm[i] = t.entry; sm[nt + i] = t.exit; sm[2 * nt + i] = (t.count << 8) | ((uint32_t)t.kind << 6) | ((uint32_t)t.last_proto & 3u);
-        }
+    uint32_t* link = fits ? sm : B.tile_scratch + 3ull * tb;     // [nt]
+    uint32_t* cp = link + nt;                                     // [nt] count << 2 | last_proto
+    uint32_t* live = cp + nt;                                     // [nt]
+    __shared__ uint32_t s_final_pos, s_warp_sum[8], s_warp_pf[8], s_carry_sum, s_carry_pf;
+    for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) {
+        const TileRec t = tiles[k];
+        link[k] = (k == 0 && t.entry != 0) ? kLinkRewalk : make_link(t, tiles, nt, C.tile_shift);
+        cp[k] = (t.count << 2) | ((uint32_t)t.last_proto & 3u);
+        live[k] = 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t pos = 0, nmsg = 0;
-        int pf = run.preferred_proto;
-        int err = B2_PARSE_ERROR_NOT_ENOUGH_DATA;
-        for (;;) {
-            const uint32_t k = pos >> C.tile_shift;
-            if (k >= nt) break;                       // chain left the run's tiles: final step below
-            uint32_t entry, exit_, packed;
-            if (fits) { entry = sm[k]; exit_ = sm[nt + k]; packed = sm[2 * nt + k]; }
-            else { const TileRec t = tiles[k]; entry = t.entry; exit_ = t.exit; packed = (t.count << 8) | ((uint32_t)t.kind << 6) | ((uint32_t)t.last_proto & 3u); }
-            uint32_t count = packed >> 8, kind = (packed >> 6) & 3u; int last = (int)(packed & 3u);
-            if (entry != pos || kind == kAmbig) {
-                // mis-speculation (or pf-sensitive step): authoritative scalar walk of this tile
+        uint32_t k = 0, pos = 0;
+        bool via_ok = false;                         // arrived through a verified link: pos == tiles[k].entry
+        while (k < nt) {
+            uint32_t v = link[k];
+            if (v & kLinkRewalk) {
+                if (via_ok) pos = tiles[k].entry;
+                // the true chain enters tile k at `pos` but the speculation has nothing usable there
+                int pf = run.preferred_proto;
+                for (uint32_t j = k; j-- > 0;) if (live[j] && (cp[j] >> 2)) { pf = (int)(cp[j] & 3u); break; }
                 TileRec t; t.live = 0; t.pf_in = 0;
                 walk_tile<false>(base, len, pos, pf, (k + 1) << C.tile_shift, C.max_body_size, t, NoEmit());
-                entry = pos; exit_ = t.exit; count = t.count; kind = t.kind; last = t.last_proto;
-                tiles[k].entry = entry; tiles[k].exit = exit_; tiles[k].count = count; tiles[k].kind = (uint8_t)kind; tiles[k].last_proto = (int8_t)last;
+                tiles[k].entry = t.entry; tiles[k].exit = t.exit; tiles[k].count = t.count; tiles[k].kind = t.kind; tiles[k].last_proto = t.last_proto;
+                cp[k] = (t.count << 2) | ((uint32_t)t.last_proto & 3u);
+                v = make_link(t, tiles, nt, C.tile_shift);
+                link[k] = v;
             }
-            tiles[k].live = 1; tiles[k].pf_in = (int8_t)pf;
-            B.tile_base[tb + k] = nmsg;
-            nmsg += count;
-            if (count) pf = last;
-            pos = exit_;
-            if (kind != kRanOff) break;
+            live[k] = 1;
+            if (v & kLinkOk) { k = v & 0x07ffffffu; via_ok = true; continue; }
+            if (v & kLinkBroken) {
+                const uint32_t j = v & 0x07ffffffu;
+                pos = tiles[k].exit; k = j; link[j] = kLinkRewalk; via_ok = false;
+                continue;
+            }
+            pos = tiles[k].exit;                     // kLinkStop / kLinkEnd
+            break;
         }
-        // the step that ends ProcessNewMessage's loop, with the true preferred index
-        const Step s = cut_input_message(base, len, pos, pf, C.max_body_size);
-        // (an OK step here is impossible: every tile walk stops only on a non-OK step
-        //  or past the last tile, where no bytes remain)
-        err = s.err; pf = s.pf; pos = s.new_pos;
+        // tiles reached through kLinkOk never set `pos`; recover it from the last live tile
+        s_final_pos = pos;
+        if (k < nt) s_final_pos = tiles[k].exit;
+        if (nt == 0) s_final_pos = 0;
+    }
+    __syncthreads();
+    // phase 3: exclusive sum of live counts; pf_in = protocol of the last message before the tile
+    if (threadIdx.x == 0) { s_carry_sum = 0; s_carry_pf = 0; }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t k0 = 0; k0 < nt; k0 += blockDim.x) {
+        const uint32_t k = k0 + threadIdx.x;
+        const uint32_t lv = k < nt ? live[k] : 0;
+        const uint32_t c = lv ? (cp[k] >> 2) : 0;
+        const uint32_t pr = (lv && c) ? (cp[k] & 3u) : 0;
+        uint32_t x = c, y = pr;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t xs = __shfl_up_sync(0xffffffffu, x, d), ys = __shfl_up_sync(0xffffffffu, y, d);
+            if (lane >= d) { x += xs; if (!y) y = ys; }
+        }
+        if (lane == 31) { s_warp_sum[wid] = x; s_warp_pf[wid] = y; }
+        __syncthreads();
+        uint32_t wsum = 0, wpf = 0;
+        for (uint32_t w = 0; w < wid; w++) { wsum += s_warp_sum[w]; if (s_warp_pf[w]) wpf = s_warp_pf[w]; }
+        const uint32_t carry_sum = s_carry_sum, carry_pf = s_carry_pf;
+        // exclusive values for this tile
+        const uint32_t incl_pf = y ? y : (wpf ? wpf : carry_pf);
+        uint32_t excl_pf = __shfl_up_sync(0xffffffffu, incl_pf, 1);
+        if (lane == 0) excl_pf = wpf ? wpf : carry_pf;
+        if (k < nt && lv) {
+            B.tile_base[tb + k] = carry_sum + wsum + x - c;
+            tiles[k].live = 1;
+            tiles[k].pf_in = (int8_t)(excl_pf ? (int)excl_pf : run.preferred_proto);
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) { s_carry_sum = carry_sum + wsum + x; s_carry_pf = incl_pf; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t pos = s_final_pos;
+        const int pf_true = s_carry_pf ? (int)s_carry_pf : run.preferred_proto;
+        // the step that ends ProcessNewMessage's loop, with the true preferred index (never OK:
+        // every tile walk stops only on a non-OK step or past the last tile, where no bytes remain)
+        const Step s = cut_input_message(base, len, pos, pf_true, C.max_body_size);
         b2_run_status st;
-        st.consumed = pos; st.parse_error = (uint32_t)err; st.n_msgs = nmsg; st.first_msg = 0;
-        st.preferred_proto = pf; st.reserved0 = 0; st.resp_off = 0; st.resp_bytes = 0;
+        st.consumed = s.new_pos; st.parse_error = (uint32_t)s.err; st.n_msgs = s_carry_sum; st.first_msg = 0;
+        st.preferred_proto = s.pf; st.reserved0 = 0; st.resp_off = 0; st.resp_bytes = 0;
         B.run_status[r] = st;
     }
 }
@@ -351,10 +413,16 @@ __device__ __forceinline__ uint32_t error_text_len(const DevConfig& C, const Dev
     return n;
 }
 
+__device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i);
+
+// persistent: a fixed grid (multiple of the SM count) strides over the device-side message count
 __global__ void __launch_bounds__(128) k_decode(BatchPtrs B, DevConfig C) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_msgs = B.totals[0];
-    if (i >= n_msgs || (B.totals[2] & 1u)) return;
+    if (B.totals[2] & 1u) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_msgs; i += gridDim.x * blockDim.x) decode_one(B, C, i);
+}
+
+__device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i) {
     const uint32_t fo_raw = B.frame_off[i];
     const uint32_t fo = fo_raw & 0x7fffffffu;
     const int proto = (int)(fo_raw >> 31) + 1;
@@ -462,8 +530,8 @@ constexpr int kScanBlock = 1024, kScanItems = 4;
 __global__ void __launch_bounds__(kScanBlock) k_scan_blocks(BatchPtrs B) {
     __shared__ uint32_t s_warp[32];
     const uint32_t n = B.totals[0];
-    const uint32_t base = blockIdx.x * kScanBlock * kScanItems + threadIdx.x * kScanItems;
-    if (blockIdx.x * kScanBlock * kScanItems >= n) return;
+    for (uint32_t blk = blockIdx.x; blk * kScanBlock * kScanItems < n; blk += gridDim.x) {
+    const uint32_t base = blk * kScanBlock * kScanItems + threadIdx.x * kScanItems;
     uint32_t v[kScanItems], sum = 0;
     #pragma unroll
     for (int j = 0; j < kScanItems; j++) { v[j] = base + j < n ? B.slot[base + j] : 0; sum += v[j]; }
@@ -477,12 +545,14 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_blocks(BatchPtrs B) {
         #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, ws, d); if (threadIdx.x >= d) ws += y; }
         s_warp[threadIdx.x] = ws - w;
-        if (threadIdx.x == 31) B.scan_tmp[blockIdx.x] = ws;
+        if (threadIdx.x == 31) B.scan_tmp[blk] = ws;
     }
     __syncthreads();
     uint32_t excl = s_warp[threadIdx.x >> 5] + x - sum;
     #pragma unroll
     for (int j = 0; j < kScanItems; j++) { if (base + j < n) B.slot[base + j] = excl; excl += v[j]; }
+    __syncthreads();
+    }
 }
 __global__ void __launch_bounds__(1024) k_scan_top(BatchPtrs B) {
     // serial-by-chunks exclusive scan of the block sums (<= a few thousand entries)
@@ -515,6 +585,9 @@ __global__ void __launch_bounds__(1024) k_scan_top(BatchPtrs B) {
     if (threadIdx.x == 0) { B.totals[1] = s_carry; if (s_carry > B.max_resp) B.totals[2] |= 2u; }
 }
 
+#ifndef B2_PACK_MIN_BLOCKS
+#define B2_PACK_MIN_BLOCKS 6
+#endif
 // --- k_pack: one warp per message --------------------------------------------
 __device__ __constant__ uint32_t c_crc_table[256];   // CRC-32C byte table (poly 0x82f63b78 reflected)
 
@@ -585,6 +658,10 @@ __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint
             const uint4 a = __ldg(s4 + i), b = __ldg(s4 + i + 32), c = __ldg(s4 + i + 64), d = __ldg(s4 + i + 96);
             d4[i] = a; d4[i + 32] = b; d4[i + 64] = c; d4[i + 96] = d;
         }
+        for (; i + 32 < nv; i += 64) {                        // 2 loads in flight per lane (1 KB payloads)
+            const uint4 a = __ldg(s4 + i), b = __ldg(s4 + i + 32);
+            d4[i] = a; d4[i + 32] = b;
+        }
         for (; i < nv; i += 32) d4[i] = __ldg(s4 + i);
         const uint32_t done = head + (nv << 4);
         if (lane < n - done) dst[done + lane] = src[done + lane];
@@ -593,10 +670,18 @@ __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint
     }
 }
 
-__global__ void __launch_bounds__(256) k_pack(BatchPtrs B, DevConfig C) {
-    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t lane);
+
+// persistent: a fixed grid (multiple of the SM count); every warp strides over the messages
+__global__ void __launch_bounds__(256, B2_PACK_MIN_BLOCKS) k_pack(BatchPtrs B, DevConfig C) {
+    const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_msgs = B.totals[0];
-    if (i >= n_msgs || (B.totals[2] & 3u)) return;
+    if (B.totals[2] & 3u) return;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_msgs; i += n_warps) pack_one(B, C, i, lane);
+}
+
+__device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t lane) {
     const uint32_t bi = i / (kScanBlock * kScanItems);
     const uint32_t slot_off = B.slot[i] + B.scan_tmp[bi];
     const b2_msg_desc d = B.msgs[i];

@@ -232,6 +232,9 @@ int  b2_batch_upload(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
                      const b2_run* runs, uint32_t n_runs);
 int  b2_batch_execute(b2_ctx* ctx, float* kernel_ms, uint32_t* n_launches);
 int  b2_batch_download(b2_ctx* ctx, b2_batch_result* out);
+/* `steps` back-to-back passes of the whole kernel pipeline over the resident batch,
+ * one CUDA-event pair around all of them on the launching stream. */
+int  b2_batch_execute_many(b2_ctx* ctx, uint32_t steps, float* total_ms, uint32_t* n_launches);
 
 /* Device time of each stage of the last execute, in launch order.  Writes up to
  * `cap` entries of (name, ms); returns the number of stages. */
