@@ -49,6 +49,17 @@ struct __align__(16) MsgAux {     // device-internal side record of k_decode -> 
     uint32_t pad;        // bytes between slot start and frame start (0..15)
     uint32_t err_kind;   // ErrKind for B2_MSG_ERROR_REPLIED
 };
+// k_decode -> k_pack_tma: everything the bandwidth path needs for one OK echo reply
+struct __align__(16) PackJob {
+    uint32_t src_off;    // batch offset of the first payload byte that TMA moves (16-byte aligned)
+    uint32_t bulk_len;   // payload bytes moved by TMA, rounded up to 16 (0 = payload fits in the head)
+    uint16_t head_len;   // bytes of the head record: pad + prefix + payload bytes up to the 16-byte boundary
+    uint8_t pad;         // slot start -> frame start
+    uint8_t fast;        // 1 = take the TMA path
+    uint32_t slot_len;   // roundup16(pad + resp_len)
+};
+constexpr uint32_t kHeadBytes = 96;               // head record stride; prefix <= 64 on the TMA path
+
 enum ErrKind : uint32_t { kErrNone = 0, kErrAttachment, kErrNoService, kErrNoMethod, kErrParseRequest };
 
 struct DevMethod {                // registered method table (global memory, tiny)
@@ -78,6 +89,8 @@ struct BatchPtrs {
     uint32_t* frame_off;             // [max_msgs] frame offsets (batch-relative), bit31.. unused
     b2_msg_desc* msgs;
     MsgAux* aux;
+    PackJob* jobs;                   // [max_msgs]
+    uint8_t* heads;                  // [max_msgs * kHeadBytes] reply prefixes pre-shifted to their slot alignment
     uint32_t* slot;                  // [max_msgs+1] slot sizes -> exclusive offsets
     uint32_t* scan_tmp;              // block sums
     uint8_t* resp;
@@ -413,20 +426,59 @@ __device__ __forceinline__ uint32_t error_text_len(const DevConfig& C, const Dev
     return n;
 }
 
-__device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i);
+// k_decode stages the first kRowBytes of every frame (header + RpcMeta + first body bytes) in
+// shared memory with coalesced 4-byte loads (one row per lane) and decodes from there; the head
+// records are assembled in shared memory and leave with coalesced 16-byte stores.
+constexpr uint32_t kRowBytes = 176, kRowWords = kRowBytes / 4;
+constexpr uint32_t kDecodeWarps = 4;
+struct DecodeWarpSmem {
+    alignas(16) uint8_t head[32][kHeadBytes];
+    alignas(16) uint32_t row[32][kRowWords];
+};
+
+__device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
+                                           const uint8_t* srow, uint8_t* shead);
 
 // persistent: a fixed grid (multiple of the SM count) strides over the device-side message count
-__global__ void __launch_bounds__(128) k_decode(BatchPtrs B, DevConfig C) {
+__global__ void __launch_bounds__(kDecodeWarps * 32) k_decode(BatchPtrs B, DevConfig C) {
+    __shared__ DecodeWarpSmem smem[kDecodeWarps];
     const uint32_t n_msgs = B.totals[0];
     if (B.totals[2] & 1u) return;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_msgs; i += gridDim.x * blockDim.x) decode_one(B, C, i);
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    DecodeWarpSmem& S = smem[wid];
+    for (uint32_t i0 = (blockIdx.x * kDecodeWarps + wid) * 32; i0 < n_msgs; i0 += gridDim.x * kDecodeWarps * 32) {
+        const uint32_t i = i0 + lane;
+        const uint32_t fo_raw = i < n_msgs ? B.frame_off[i] : 0;
+        const uint32_t nm = min(32u, n_msgs - i0);
+        // stage: row m <- the aligned words covering frame m's first bytes
+        for (uint32_t m = 0; m < nm; m++) {
+            const uint32_t f = __shfl_sync(0xffffffffu, fo_raw, m) & 0x7fffffffu;
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(B.bytes + (f & ~3u));
+            S.row[m][lane] = __ldg(src + lane);                                  // (batch buffer is padded past its end)
+            if (lane + 32 < kRowWords) S.row[m][lane + 32] = __ldg(src + lane + 32);
+        }
+        __syncwarp();
+        if (i < n_msgs) decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 3u), S.head[lane]);
+        __syncwarp();
+        // heads of 32 consecutive messages are contiguous: coalesced 16-byte stores
+        {
+            const uint4* hs = reinterpret_cast<const uint4*>(&S.head[0][0]);
+            uint4* hd = reinterpret_cast<uint4*>(B.heads + (size_t)i0 * kHeadBytes);
+            for (uint32_t k = lane; k < nm * (kHeadBytes / 16); k += 32) hd[k] = hs[k];
+        }
+        __syncwarp();
+    }
 }
 
-__device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i) {
-    const uint32_t fo_raw = B.frame_off[i];
+__device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
+                                           const uint8_t* srow, uint8_t* shead) {
     const uint32_t fo = fo_raw & 0x7fffffffu;
     const int proto = (int)(fo_raw >> 31) + 1;
-    const uint8_t* frame = B.bytes + fo;
+    const uint8_t* gframe = B.bytes + fo;
+    // decode from the staged copy when header + meta + the first body bytes are inside it
+    const uint32_t meta_size_peek = load_be32(srow + 8);
+    const bool staged = (uint64_t)(fo_raw & 3u) + 12ull + meta_size_peek + 40ull <= kRowBytes;
+    const uint8_t* frame = staged ? srow : gframe;
     b2_msg_desc d;
     d.frame_off = fo; d.body_size = load_be32(frame + 4); d.meta_size = load_be32(frame + 8);
     d.correlation_id = 0; d.log_id = 0; d.attachment_size = 0; d.compress_type = 0; d.checksum_type = 0; d.error_code = 0;
@@ -486,11 +538,22 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                 else if (mp->response_compress_type != B2_COMPRESS_TYPE_NONE) d.status = B2_MSG_UNSUPPORTED;
                 else if (m.compress_type != B2_COMPRESS_TYPE_NONE) { a.err_kind = kErrParseRequest; d.error_code = B2_EREQUEST; }
                 else {
-                    Span msg;
-                    const uint8_t* body = meta_p + d.meta_size;
+                    Span msg; msg.off = 0; msg.len = 0;
                     bool ok = true;
                     if (m.checksum_type == B2_CHECKSUM_TYPE_CRC32C && a.cks_len != 4) ok = false;   // reference CHECK-aborts; see DESIGN.md
-                    if (ok) ok = decode_echo_request(body, body_wo_att, msg);
+                    if (ok) {
+                        // canonical body "0a <len> <message>": recognised from the staged bytes without walking
+                        const uint8_t* sb = meta_p + d.meta_size;
+                        bool canon = false;
+                        if (staged && body_wo_att >= 2 && sb[0] == 0x0a) {
+                            Reader r; r.p = sb + 1; r.end = sb + (body_wo_att < 6 ? body_wo_att : 6);
+                            uint64_t l;
+                            if (rd_varint(r, l) && l <= 0x7fffffefull && (uint64_t)(r.p - sb) + l == body_wo_att) {
+                                canon = true; msg.off = (uint32_t)(r.p - sb); msg.len = (uint32_t)l;
+                            }
+                        }
+                        if (!canon) ok = decode_echo_request(gframe + 12 + d.meta_size, body_wo_att, msg);
+                    }
                     if (!ok) { a.err_kind = kErrParseRequest; d.error_code = B2_EREQUEST; }
                     else {
                         d.status = B2_MSG_ECHOED;
@@ -522,7 +585,39 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
     d.resp_len = resp_len;
     B.msgs[i] = d;
     B.aux[i] = a;
-    B.slot[i] = resp_len ? ((a.pad + resp_len + 15u) & ~15u) : 0u;
+    const uint32_t slot_len = resp_len ? ((a.pad + resp_len + 15u) & ~15u) : 0u;
+    B.slot[i] = slot_len;
+    // ---- bandwidth path: pre-build the reply prefix, shifted to the slot alignment -------------
+    PackJob job; job.src_off = 0; job.bulk_len = 0; job.head_len = 0; job.pad = (uint8_t)a.pad; job.fast = 0; job.slot_len = slot_len;
+    if (d.status == B2_MSG_ECHOED && d.checksum_type != B2_CHECKSUM_TYPE_CRC32C &&
+        B.methods[d.method_idx].response_checksum_type == B2_CHECKSUM_TYPE_NONE &&
+        (a.att_len == 0 || a.att_off == a.msg_off + a.msg_len)) {
+        const uint32_t ml = response_meta_len(0, 0, 0, d.correlation_id, a.att_len, 0, a.cks_len);
+        const uint32_t vl = varint_len(a.msg_len);
+        const uint32_t prefix = 12 + ml + 1 + vl;
+        if (prefix <= 64) {
+            const uint32_t n = a.msg_len + a.att_len;
+            const uint32_t gs = fo + a.msg_off;
+            const uint32_t lead = min(n, (16u - (gs & 15u)) & 15u);
+            const uint32_t hl = (a.pad + prefix + lead + 15u) & ~15u;
+            uint8_t* h = shead;
+            uint8_t* p = h;
+            for (uint32_t k = 0; k < a.pad; k++) *p++ = 0;
+            p[0] = 'P'; p[1] = 'R'; p[2] = 'P'; p[3] = 'C';
+            put_be32(p + 4, ml + 1 + vl + n); put_be32(p + 8, ml); p += 12;
+            *p++ = 0x12; *p++ = 0x02; *p++ = 0x08; *p++ = 0x00; *p++ = 0x18; *p++ = 0x00;
+            *p++ = 0x20; p = put_varint(p, (uint64_t)d.correlation_id);
+            if (a.att_len) { *p++ = 0x28; p = put_varint(p, a.att_len); }
+            *p++ = 0x50; *p++ = 0x00; *p++ = 0x58; *p++ = 0x00;
+            *p++ = 0x62; p = put_varint(p, a.cks_len);
+            for (uint32_t k = 0; k < a.cks_len; k++) *p++ = frame[a.cks_off + k];
+            *p++ = 0x0a; p = put_varint(p, a.msg_len);
+            for (uint32_t k = 0; k < lead; k++) *p++ = frame[a.msg_off + k];
+            while (p < h + hl) *p++ = 0;
+            job.src_off = gs + lead; job.bulk_len = (n - lead + 15u) & ~15u; job.head_len = (uint16_t)hl; job.fast = 1;
+        }
+    }
+    B.jobs[i] = job;
 }
 
 // --- exclusive scan of slot sizes: 2 kernels ---------------------------------
@@ -670,6 +765,41 @@ __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint
     }
 }
 
+// Lane-parallel reply prefix: lane j produces byte j (+32, +64 ...) of
+//   "PRPC" be32(body) be32(meta) | 12 02 08 00 | 18 00 | 20 cid | [28 att] | 50 00 | 58 ck | 62 len cks | 0a len
+// == PackRpcHeader + the RpcMeta of SendRpcResponse (baidu_rpc_protocol.cpp:75-81,339-349) + the
+// EchoResponse field header.  `out` may point to shared or global memory.
+__device__ __forceinline__ void write_echo_prefix(uint8_t* out, uint32_t lane, int64_t correlation_id, uint32_t att_len,
+                                                  int32_t r_cks_type, uint32_t cks_len, uint32_t crc_be, const uint8_t* req_cks,
+                                                  uint32_t msg_len, uint32_t ml, uint32_t vl, uint32_t prefix) {
+    const uint32_t cid_n = varint_len((uint64_t)correlation_id);
+    const uint32_t att_n = att_len ? 1 + varint_len(att_len) : 0;
+    const uint32_t o_cid = 12 + 6;                 // after 12 02 08 00 18 00
+    const uint32_t o_att = o_cid + 1 + cid_n;
+    const uint32_t o_ct = o_att + att_n;           // 50 00 58 xx 62
+    const uint32_t o_ckl = o_ct + 5;               // varint(cks_len)
+    const uint32_t ckl_n = varint_len(cks_len);
+    const uint32_t o_ckv = o_ckl + ckl_n;
+    const uint32_t o_pb = o_ckv + cks_len;         // == 12 + ml
+    const uint32_t total_body = ml + 1 + vl + msg_len + att_len;
+    for (uint32_t j = lane; j < prefix; j += 32) {
+        uint8_t b;
+        if (j < 4) b = (uint8_t)(kMagicPRPC >> (8 * j));
+        else if (j < 8) b = (uint8_t)(total_body >> (8 * (7 - j)));
+        else if (j < 12) b = (uint8_t)(ml >> (8 * (11 - j)));
+        else if (j < o_cid) { const uint32_t k = j - 12; b = (k == 0) ? 0x12 : (k == 1) ? 0x02 : (k == 2) ? 0x08 : (k == 4) ? 0x18 : 0x00; }
+        else if (j == o_cid) b = 0x20;
+        else if (j < o_att) b = varint_byte((uint64_t)correlation_id, j - o_cid - 1, cid_n);
+        else if (j < o_ct) b = (j == o_att) ? 0x28 : varint_byte(att_len, j - o_att - 1, att_n - 1);
+        else if (j < o_ckl) { const uint32_t k = j - o_ct; b = (k == 0) ? 0x50 : (k == 2) ? 0x58 : (k == 3) ? (uint8_t)r_cks_type : (k == 4) ? 0x62 : 0x00; }
+        else if (j < o_ckv) b = varint_byte(cks_len, j - o_ckl, ckl_n);
+        else if (j < o_pb) b = (r_cks_type == B2_CHECKSUM_TYPE_CRC32C) ? (uint8_t)(crc_be >> (8 * (3 - (j - o_ckv)))) : req_cks[j - o_ckv];
+        else if (j == o_pb) b = 0x0a;
+        else b = varint_byte(msg_len, j - o_pb - 1, vl);
+        out[j] = b;
+    }
+}
+
 __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t lane);
 
 // persistent: a fixed grid (multiple of the SM count); every warp strides over the messages
@@ -720,7 +850,6 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
     const uint32_t ml = response_meta_len(0, 0, 0, d.correlation_id, a.att_len, r_cks_type, cks_len);
     const uint32_t vl = varint_len(a.msg_len);
     const uint32_t prefix = 12 + ml + 1 + vl;
-    const uint32_t body_len = 1 + vl + a.msg_len;
     const uint32_t resp_len = prefix + a.msg_len + a.att_len;
     uint8_t* out = B.resp + slot_off + a.pad;
     uint32_t crc_be = 0;
@@ -735,34 +864,7 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
         }
         crc_be = __shfl_sync(0xffffffffu, crc_be, 0);
     }
-    // lane-parallel prefix: lane j produces byte j (+32, +64 ...) of
-    //   "PRPC" be32(body) be32(meta) | 12 02 08 00 | 18 00 | 20 cid | [28 att] | 50 00 | 58 ck | 62 len cks | 0a len
-    const uint32_t cid_n = varint_len((uint64_t)d.correlation_id);
-    const uint32_t att_n = a.att_len ? 1 + varint_len(a.att_len) : 0;
-    const uint32_t o_cid = 12 + 6;                 // after 12 02 08 00 18 00
-    const uint32_t o_att = o_cid + 1 + cid_n;
-    const uint32_t o_ct = o_att + att_n;           // 50 00 58 xx 62
-    const uint32_t o_ckl = o_ct + 5;               // varint(cks_len)
-    const uint32_t ckl_n = varint_len(cks_len);
-    const uint32_t o_ckv = o_ckl + ckl_n;
-    const uint32_t o_pb = o_ckv + cks_len;         // == 12 + ml
-    const uint32_t total_body = ml + body_len + a.att_len;
-    for (uint32_t j = lane; j < prefix; j += 32) {
-        uint8_t b;
-        if (j < 4) b = (uint8_t)(kMagicPRPC >> (8 * j));
-        else if (j < 8) b = (uint8_t)(total_body >> (8 * (7 - j)));
-        else if (j < 12) b = (uint8_t)(ml >> (8 * (11 - j)));
-        else if (j < o_cid) { const uint32_t k = j - 12; b = (k == 0) ? 0x12 : (k == 1) ? 0x02 : (k == 2) ? 0x08 : (k == 4) ? 0x18 : 0x00; }
-        else if (j == o_cid) b = 0x20;
-        else if (j < o_att) b = varint_byte((uint64_t)d.correlation_id, j - o_cid - 1, cid_n);
-        else if (j < o_ct) b = (j == o_att) ? 0x28 : varint_byte(a.att_len, j - o_att - 1, att_n - 1);
-        else if (j < o_ckl) { const uint32_t k = j - o_ct; b = (k == 0) ? 0x50 : (k == 2) ? 0x58 : (k == 3) ? (uint8_t)r_cks_type : (k == 4) ? 0x62 : 0x00; }
-        else if (j < o_ckv) b = varint_byte(cks_len, j - o_ckl, ckl_n);
-        else if (j < o_pb) b = (r_cks_type == B2_CHECKSUM_TYPE_CRC32C) ? (uint8_t)(crc_be >> (8 * (3 - (j - o_ckv)))) : frame[a.cks_off + (j - o_ckv)];
-        else if (j == o_pb) b = 0x0a;
-        else b = varint_byte(a.msg_len, j - o_pb - 1, vl);
-        out[j] = b;
-    }
+    write_echo_prefix(out, lane, d.correlation_id, a.att_len, r_cks_type, cks_len, crc_be, frame + a.cks_off, a.msg_len, ml, vl, prefix);
     // payload: message bytes (+ attachment when it directly follows them, the normal layout)
     if (a.att_len && a.att_off == a.msg_off + a.msg_len) {
         warp_copy(out + prefix, frame + a.msg_off, a.msg_len + a.att_len, lane);
@@ -771,6 +873,122 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
         if (a.att_len) warp_copy(out + prefix + a.msg_len, frame + a.att_off, a.att_len, lane);
     }
     if (lane == 0) { B.msgs[i].resp_off = slot_off + a.pad; B.msgs[i].resp_len = resp_len; }
+}
+
+
+// --- k_pack_tma: the bandwidth path -------------------------------------------
+// OK echo replies without CRC work are staged through shared memory with the bulk
+// async-copy engine (TMA, cp.async.bulk): every warp owns two staging buffers; per
+// round it takes kPackGroup consecutive messages, pulls their metadata with one
+// coalesced load, issues one bulk load per payload (all in flight together, completion
+// on an mbarrier), writes the reply prefixes into the same staging image while the
+// payloads fly, then pushes every reply frame out with one bulk store.  Because the slot
+// layout keeps (dst mod 16) == (src mod 16), the 16-byte aligned interior of payload and
+// frame moves with TMA and only <= 15 head/tail bytes per side move with byte accesses.
+// Everything else (error replies, CRC32C, replies larger than a staging buffer, split
+// attachments) goes through pack_one.
+constexpr uint32_t kPackWarps = 11;
+constexpr uint32_t kPackGroup = 8;               // messages per warp round (one lane each)
+constexpr uint32_t kStageBytes = 9216;           // per buffer, two buffers per warp
+struct PackWarpSmem {
+    alignas(128) uint8_t stage[2][kStageBytes];
+    alignas(8) unsigned long long mbar[2];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Pure data movement: per message two TMA bulk loads (the pre-built head record and the
+// 16-byte aligned remainder of the payload) into one staging slot and one TMA bulk store of
+// the whole slot.  Lane l of a warp owns message base+l of the round; two staging buffers per
+// warp keep one round's stores draining while the next round's loads are in flight.
+__global__ void __launch_bounds__(kPackWarps * 32, 1) k_pack_tma(BatchPtrs B, DevConfig C) {
+    extern __shared__ __align__(128) uint8_t pack_smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    PackWarpSmem& S = reinterpret_cast<PackWarpSmem*>(pack_smem_raw)[wid];
+    const uint32_t n_msgs = B.totals[0];
+    if (B.totals[2] & 3u) return;
+    if (lane == 0) {
+        mbar_init(&S.mbar[0], 1); mbar_init(&S.mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const uint32_t stride = gridDim.x * kPackWarps * kPackGroup;
+    uint32_t it = 0, phase0 = 0, phase1 = 0;        // mbarrier phases advance only in rounds that arm them
+    PackJob job; job.fast = 0; job.slot_len = 0; job.head_len = 0; job.bulk_len = 0; job.src_off = 0; job.pad = 0;
+    uint32_t slot_off = 0;
+    uint32_t base = (blockIdx.x * kPackWarps + wid) * kPackGroup;
+    auto fetch = [&](uint32_t bse, PackJob& j, uint32_t& so) {
+        const uint32_t i = bse + lane;
+        j.fast = 0; j.slot_len = 0;
+        if (lane < kPackGroup && i < n_msgs) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(B.jobs + i));
+            j = *reinterpret_cast<const PackJob*>(&v);
+            so = B.slot[i] + B.scan_tmp[i / (kScanBlock * kScanItems)];
+        }
+    };
+    if (base < n_msgs) fetch(base, job, slot_off);
+    for (; base < n_msgs; base += stride, it++) {
+        const uint32_t nm = min(kPackGroup, n_msgs - base);
+        const uint32_t b = it & 1;
+        uint8_t* stage = S.stage[b];
+        // software pipeline: request the next round's jobs now, use them next iteration
+        PackJob njob; uint32_t nslot = 0;
+        njob.fast = 0; njob.slot_len = 0; njob.head_len = 0; njob.bulk_len = 0; njob.src_off = 0; njob.pad = 0;
+        if (base + stride < n_msgs) fetch(base + stride, njob, nslot);
+        // staging layout: inclusive scan of the slot lengths of this round's TMA messages
+        uint32_t need = job.fast ? job.slot_len : 0, incl = need;
+        #pragma unroll
+        for (int d = 1; d < (int)kPackGroup; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += y; }
+        const bool take = job.fast && incl <= kStageBytes;
+        const uint32_t soff = incl - need;
+        uint32_t tx = take ? (uint32_t)job.head_len + job.bulk_len : 0;
+        #pragma unroll
+        for (int d = 1; d < (int)kPackGroup; d <<= 1) tx += __shfl_xor_sync(0xffffffffu, tx, d);
+        tx = __shfl_sync(0xffffffffu, tx, 0);
+        // the bulk stores that last read this staging buffer (two rounds ago) must have drained it
+        bulk_wait_read<1>();
+        __syncwarp();
+        if (lane == 0 && tx) mbar_arrive_expect_tx(&S.mbar[b], tx);
+        __syncwarp();
+        if (take) {
+            bulk_g2s(stage + soff, B.heads + (size_t)(base + lane) * kHeadBytes, job.head_len, &S.mbar[b]);
+            if (job.bulk_len) bulk_g2s(stage + soff + job.head_len, B.bytes + job.src_off, job.bulk_len, &S.mbar[b]);
+        }
+        if (tx) { mbar_wait(&S.mbar[b], (b ? phase1 : phase0) & 1u); if (b) phase1++; else phase0++; }
+        if (take) {
+            bulk_s2g(B.resp + slot_off, stage + soff, job.slot_len);
+            B.msgs[base + lane].resp_off = slot_off + job.pad;
+        }
+        bulk_commit();
+        // everything that is not a plain OK echo (or did not fit the staging buffer): register path
+        const uint32_t slow = __ballot_sync(0xffffffffu, lane < nm && !take);
+        for (uint32_t m = slow; m; m &= m - 1) pack_one(B, C, base + (__ffs(m) - 1), lane);
+        job = njob; slot_off = nslot;
+    }
+    bulk_wait<0>();
 }
 
 // --- k_finalize: per-run response span + counters ----------------------------
