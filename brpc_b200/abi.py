@@ -60,9 +60,14 @@ def _load():
     l.b2_block_alloc.restype = C.c_void_p; l.b2_block_alloc.argtypes = [C.c_size_t]
     l.b2_block_free.argtypes = [C.c_void_p]
     l.b2_process_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(BatchResult)]
+    l.b2_batch_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    l.b2_batch_collect.argtypes = [C.c_void_p, C.POINTER(BatchResult)]
     l.b2_batch_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
     l.b2_batch_execute.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
     l.b2_batch_execute_many.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+    l.b2_batch_launch.argtypes = [C.c_void_p]
+    l.b2_batch_wait.argtypes = [C.c_void_p]
+    l.b2_elapsed_ms.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     l.b2_batch_download.argtypes = [C.c_void_p, C.POINTER(BatchResult)]
     l.b2_stage_times.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     l.b2_crc32c_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
@@ -75,8 +80,9 @@ lib = _load()
 
 # every symbol include/b2rpc.h declares (tests check the library exports them)
 ABI_SYMBOLS = ["b2_ctx_create", "b2_ctx_destroy", "b2_last_error", "b2_version", "b2_register_method",
-               "b2_set_server_identity", "b2_block_alloc", "b2_block_free", "b2_process_batch", "b2_batch_upload",
-               "b2_batch_execute", "b2_batch_execute_many", "b2_batch_download", "b2_stage_times", "b2_crc32c_batch", "b2_counters_read",
+               "b2_set_server_identity", "b2_block_alloc", "b2_block_free", "b2_process_batch", "b2_batch_submit", "b2_batch_collect", "b2_batch_upload",
+               "b2_batch_execute", "b2_batch_execute_many", "b2_batch_download", "b2_batch_launch", "b2_batch_wait",
+               "b2_elapsed_ms", "b2_stage_times", "b2_crc32c_batch", "b2_counters_read",
                "b2_counters_device_ptr"]
 
 ECHO_METHOD = dict(service_full_name=b"example.EchoService", service_name=b"EchoService", method_name=b"Echo",
@@ -181,6 +187,17 @@ class Context:
         _check(lib.b2_batch_execute_many(self._h, steps, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def launch(self):
+        _check(lib.b2_batch_launch(self._h))
+
+    def wait(self):
+        _check(lib.b2_batch_wait(self._h))
+
+    def elapsed_ms_to(self, other):
+        ms = C.c_float(0)
+        _check(lib.b2_elapsed_ms(self._h, other._h, C.byref(ms)))
+        return ms.value
+
     def download(self):
         res = BatchResult()
         _check(lib.b2_batch_download(self._h, C.byref(res)))
@@ -191,6 +208,17 @@ class Context:
         runs = np.ascontiguousarray(runs, dtype=RUN_DT)
         res = BatchResult()
         _check(lib.b2_process_batch(self._h, ptr, nbytes, runs.ctypes.data, len(runs), C.byref(res)))
+        rs, msgs, resp = self._views(res)
+        return rs, msgs, resp, {"kernel_ms": res.kernel_ms, "n_launches": res.n_launches}
+
+    def submit_ptr(self, ptr, nbytes, runs):
+        runs = np.ascontiguousarray(runs, dtype=RUN_DT)
+        self._submitted_runs = runs           # keep alive until collect
+        _check(lib.b2_batch_submit(self._h, ptr, nbytes, runs.ctypes.data, len(runs)))
+
+    def collect(self):
+        res = BatchResult()
+        _check(lib.b2_batch_collect(self._h, C.byref(res)))
         rs, msgs, resp = self._views(res)
         return rs, msgs, resp, {"kernel_ms": res.kernel_ms, "n_launches": res.n_launches}
 

@@ -47,6 +47,7 @@ struct b2_ctx {
     const char* stage_names[kMaxStages];
     int n_stages = 0;
     float last_kernel_ms = 0.f; uint32_t last_launches = 0;
+    cudaEvent_t ev_first = nullptr, ev_last = nullptr; bool first_pending = true;
 };
 
 static uint32_t g_crc_tab_host[256];
@@ -138,6 +139,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     CU(cudaMemset(c->d_bytes, 0, (size_t)o->max_batch_bytes + 1024));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i <= kMaxStages; i++) CU(cudaEventCreate(&c->ev[i]));
+    CU(cudaEventCreate(&c->ev_first)); CU(cudaEventCreate(&c->ev_last));
     crc_table_init();
     CU(cudaMemcpyToSymbol(c_crc_table, g_crc_tab_host, sizeof g_crc_tab_host));
     CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -286,6 +288,30 @@ extern "C" int b2_batch_execute_many(b2_ctx* c, uint32_t steps, float* total_ms,
     return B2_OK;
 }
 
+extern "C" int b2_batch_launch(b2_ctx* c) {
+    if (!c || !c->uploaded) { set_err("no batch uploaded"); return B2_E_INVAL; }
+    CU(cudaSetDevice(c->opt.device));
+    if (c->first_pending) { CU(cudaEventRecord(c->ev_first, c->stream)); c->first_pending = false; }
+    int rc = launch_pipeline(c);
+    if (rc != B2_OK) return rc;
+    CU(cudaEventRecord(c->ev_last, c->stream));
+    c->executed = true;
+    return B2_OK;
+}
+extern "C" int b2_batch_wait(b2_ctx* c) {
+    if (!c) return B2_E_INVAL;
+    CU(cudaSetDevice(c->opt.device));
+    CU(cudaStreamSynchronize(c->stream));
+    c->first_pending = true;
+    return B2_OK;
+}
+extern "C" int b2_elapsed_ms(b2_ctx* a, b2_ctx* b, float* ms) {
+    if (!a || !b || !ms) return B2_E_INVAL;
+    CU(cudaSetDevice(a->opt.device));
+    CU(cudaEventElapsedTime(ms, a->ev_first, b->ev_last));
+    return B2_OK;
+}
+
 extern "C" int b2_batch_download(b2_ctx* c, b2_batch_result* out) {
     if (!c || !out || !c->executed) { set_err("no executed batch"); return B2_E_INVAL; }
     CU(cudaSetDevice(c->opt.device));
@@ -307,20 +333,30 @@ extern "C" int b2_batch_download(b2_ctx* c, b2_batch_result* out) {
     return B2_OK;
 }
 
-extern "C" int b2_process_batch(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs,
-                                b2_batch_result* out) {
+extern "C" int b2_batch_submit(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs) {
     int rc = b2_batch_upload(c, bytes, nbytes, runs, n_runs);
     if (rc != B2_OK) return rc;
-    CU(cudaSetDevice(c->opt.device));
     rc = launch_pipeline(c);
     if (rc != B2_OK) return rc;
     c->executed = true;
-    rc = b2_batch_download(c, out);
+    CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 16, cudaMemcpyDeviceToHost, c->stream));
+    return B2_OK;
+}
+
+extern "C" int b2_batch_collect(b2_ctx* c, b2_batch_result* out) {
+    int rc = b2_batch_download(c, out);
     if (rc != B2_OK) return rc;
     float ms = 0.f;
     if (c->n_stages) CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[c->n_stages]));
     c->last_kernel_ms = ms; out->kernel_ms = ms;
     return B2_OK;
+}
+
+extern "C" int b2_process_batch(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs,
+                                b2_batch_result* out) {
+    int rc = b2_batch_submit(c, bytes, nbytes, runs, n_runs);
+    if (rc != B2_OK) return rc;
+    return b2_batch_collect(c, out);
 }
 
 extern "C" int b2_stage_times(b2_ctx* c, const char** names, float* ms, int cap) {

@@ -242,10 +242,24 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C) {
         cp[k] = (t.count << 2) | ((uint32_t)t.last_proto & 3u);
         live[k] = 0;
     }
+    // dense shortcut: the leading stretch of tiles whose verified link goes to the next tile is
+    // live without hopping (the common case: frames smaller than a tile, speculation all correct)
+    __shared__ uint32_t s_first_bad;
+    if (threadIdx.x == 0) s_first_bad = nt ? nt - 1 : 0;
+    __syncthreads();
+    {
+        uint32_t mine = nt;
+        for (uint32_t k = threadIdx.x; k + 1 < nt; k += blockDim.x)
+            if (link[k] != (kLinkOk | (k + 1))) { mine = k; break; }
+        if (mine < nt) atomicMin(&s_first_bad, mine);
+    }
+    __syncthreads();
+    const uint32_t first_bad = s_first_bad;
+    for (uint32_t k = threadIdx.x; k < first_bad; k += blockDim.x) live[k] = 1;
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t k = 0, pos = 0;
-        bool via_ok = false;                         // arrived through a verified link: pos == tiles[k].entry
+        uint32_t k = first_bad, pos = 0;
+        bool via_ok = first_bad > 0;                 // arrived through a verified link: pos == tiles[k].entry
         while (k < nt) {
             uint32_t v = link[k];
             if (v & kLinkRewalk) {
@@ -887,7 +901,10 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
 // frame moves with TMA and only <= 15 head/tail bytes per side move with byte accesses.
 // Everything else (error replies, CRC32C, replies larger than a staging buffer, split
 // attachments) goes through pack_one.
-constexpr uint32_t kPackWarps = 11;
+#ifndef B2_PACK_WARPS
+#define B2_PACK_WARPS 8
+#endif
+constexpr uint32_t kPackWarps = B2_PACK_WARPS;
 constexpr uint32_t kPackGroup = 8;               // messages per warp round (one lane each)
 constexpr uint32_t kStageBytes = 9216;           // per buffer, two buffers per warp
 struct PackWarpSmem {

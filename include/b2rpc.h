@@ -226,6 +226,13 @@ void  b2_block_free(void* p);
 int  b2_process_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
                       const b2_run* runs, uint32_t n_runs, b2_batch_result* out);
 
+/* b2_process_batch split in two so that several batches (one ctx each) can be in flight on
+ * one GPU: submit enqueues H2D + kernels on the ctx's stream and returns; collect waits and
+ * brings descriptors + responses back.  With >= 3 contexts the H2D copy of one batch, the
+ * kernels of another and the D2H copy of a third overlap (full-duplex PCIe). */
+int  b2_batch_submit(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs);
+int  b2_batch_collect(b2_ctx* ctx, b2_batch_result* out);
+
 /* ---- the same path split in three, for measurement with inputs resident in
  * HBM (bench.py `value`): upload once, execute many times, download. -------- */
 int  b2_batch_upload(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
@@ -235,6 +242,14 @@ int  b2_batch_download(b2_ctx* ctx, b2_batch_result* out);
 /* `steps` back-to-back passes of the whole kernel pipeline over the resident batch,
  * one CUDA-event pair around all of them on the launching stream. */
 int  b2_batch_execute_many(b2_ctx* ctx, uint32_t steps, float* total_ms, uint32_t* n_launches);
+
+/* Asynchronous form for pipelining several resident batches (one ctx each) on one GPU:
+ * b2_batch_launch enqueues one pass on the ctx's stream and returns; b2_batch_wait blocks
+ * until it is done.  b2_elapsed_ms(a, b) = device time from a's FIRST launch since its last
+ * wait to b's LAST launch end (CUDA events; a and b may be the same ctx). */
+int  b2_batch_launch(b2_ctx* ctx);
+int  b2_batch_wait(b2_ctx* ctx);
+int  b2_elapsed_ms(b2_ctx* a, b2_ctx* b, float* ms);
 
 /* Device time of each stage of the last execute, in launch order.  Writes up to
  * `cap` entries of (name, ms); returns the number of stages. */
