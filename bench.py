@@ -186,6 +186,7 @@ def main():
     import brpc_b200
     use_dist = world > 1
     if use_dist:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
