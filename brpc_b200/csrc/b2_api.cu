@@ -34,7 +34,7 @@ struct b2_ctx {
     TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; uint32_t* d_tile_scratch = nullptr; b2_run_status* d_run_status = nullptr;
     uint32_t* d_frame_off = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr; PackJob* d_jobs = nullptr; uint8_t* d_heads = nullptr;
     uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr;
-    unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
+    uint32_t* d_crc_adv = nullptr; unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
     uint32_t max_tiles = 0; uint32_t n_sms = 148; bool use_tma_pack = true;
     // pinned host mirrors
     b2_run_status* h_run_status = nullptr; b2_msg_desc* h_msgs = nullptr; uint8_t* h_resp = nullptr;
@@ -74,7 +74,7 @@ extern "C" void b2_ctx_destroy(b2_ctx* c) {
     cudaSetDevice(c->opt.device);
     cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch);
     cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_heads); cudaFree(c->d_slot);
-    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods);
+    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv);
     cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
     cudaFreeHost(c->h_run_tile_base);
     for (int i = 0; i <= kMaxStages; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -130,6 +130,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     ALLOC(c->d_counters, 8 * B2_N_COUNTERS);
     ALLOC(c->d_totals, 16);
     ALLOC(c->d_methods, sizeof(DevMethod) * 64);
+    ALLOC(c->d_crc_adv, 6 * 4 * 256 * 4);
     HALLOC(c->h_run_status, sizeof(b2_run_status) * (size_t)o->max_runs);
     HALLOC(c->h_msgs, sizeof(b2_msg_desc) * (size_t)o->max_msgs);
     HALLOC(c->h_resp, (size_t)c->opt.max_resp_bytes);
@@ -142,6 +143,17 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     CU(cudaEventCreate(&c->ev_first)); CU(cudaEventCreate(&c->ev_last));
     crc_table_init();
     CU(cudaMemcpyToSymbol(c_crc_table, g_crc_tab_host, sizeof g_crc_tab_host));
+    {   // ADV_{4<<t}: the register advanced over 4, 8, ..., 128 zero bytes, as 4x256 byte-sliced tables
+        std::vector<uint32_t> adv(6 * 4 * 256);
+        for (int t = 0; t < 6; t++)
+            for (int j = 0; j < 4; j++)
+                for (uint32_t b = 0; b < 256; b++) {
+                    uint32_t x = b << (8 * j);
+                    for (int k = 0; k < (4 << t); k++) x = g_crc_tab_host[x & 0xff] ^ (x >> 8);
+                    adv[(t * 4 + j) * 256 + b] = x;
+                }
+        CU(cudaMemcpy(c->d_crc_adv, adv.data(), adv.size() * 4, cudaMemcpyHostToDevice));
+    }
     CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k_pack_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PackWarpSmem) * kPackWarps)));
     if (const char* e = getenv("B2_PACK")) c->use_tma_pack = strcmp(e, "reg") != 0;
@@ -186,7 +198,7 @@ static BatchPtrs make_ptrs(b2_ctx* c) {
     B.bytes = c->d_bytes; B.runs = c->d_runs; B.run_tile_base = c->d_run_tile_base; B.tiles = c->d_tiles;
     B.tile_base = c->d_tile_base; B.tile_scratch = c->d_tile_scratch; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.msgs = c->d_msgs;
     B.aux = c->d_aux; B.jobs = c->d_jobs; B.heads = c->d_heads; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.counters = c->d_counters;
-    B.totals = c->d_totals; B.methods = c->d_methods;
+    B.totals = c->d_totals; B.methods = c->d_methods; B.crc_adv = c->d_crc_adv;
     B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes;
     return B;
 }
@@ -382,10 +394,13 @@ extern "C" void* b2_counters_device_ptr(b2_ctx* c) { return c ? (void*)c->d_coun
 // device pointers of the resident batch, for harnesses that time or inspect kernels directly
 extern "C" void* b2_debug_resp_device_ptr(b2_ctx* c) { return c ? (void*)c->d_resp : nullptr; }
 
-__global__ void k_crc32c_batch(const uint8_t* bytes, const uint32_t* offs, const uint32_t* lens, uint32_t n, uint32_t* out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    out[i] = crc32c_bytes_serial(0xffffffffu, bytes + offs[i], lens[i]) ^ 0xffffffffu;
+__global__ void k_crc32c_batch(const uint8_t* bytes, const uint32_t* offs, const uint32_t* lens, uint32_t n, uint32_t* out,
+                               const uint32_t* adv) {
+    const uint32_t lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += n_warps) {
+        const uint32_t c = warp_crc32c_update(0xffffffffu, bytes + offs[i], lens[i], lane, adv) ^ 0xffffffffu;
+        if (lane == 0) out[i] = c;
+    }
 }
 
 extern "C" int b2_crc32c_batch(b2_ctx* c, const void* bytes, uint32_t nbytes, const uint32_t* offs, const uint32_t* lens,
@@ -397,7 +412,7 @@ extern "C" int b2_crc32c_batch(b2_ctx* c, const void* bytes, uint32_t nbytes, co
     CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_frame_off, offs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_slot, lens, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    if (n) k_crc32c_batch<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_bytes, c->d_frame_off, c->d_slot, n, c->d_scan_tmp ? (uint32_t*)c->d_aux : nullptr);
+    if (n) k_crc32c_batch<<<c->n_sms * 8, 256, 0, c->stream>>>(c->d_bytes, c->d_frame_off, c->d_slot, n, (uint32_t*)c->d_aux, c->d_crc_adv);
     CU(cudaMemcpyAsync(out, c->d_aux, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->uploaded = false; c->executed = false;

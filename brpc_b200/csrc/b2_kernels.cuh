@@ -97,6 +97,7 @@ struct BatchPtrs {
     unsigned long long* counters;    // int64[B2_N_COUNTERS]
     uint32_t* totals;                // [0]=n_msgs [1]=resp_bytes [2]=overflow flags
     const DevMethod* methods;
+    const uint32_t* crc_adv;         // [6][4][256] ADV_{4<<t} tables of the warp CRC
     uint32_t n_runs, n_tiles, max_msgs, max_resp;
 };
 
@@ -705,6 +706,46 @@ __device__ __forceinline__ uint32_t crc32c_bytes_serial(uint32_t l, const uint8_
     return l;
 }
 
+// CRC-32C as a warp-level primitive (butil::crc32c::Extend, src/butil/crc32c.cc:379-454, without
+// the 0xffffffff pre/post inversion: this works on the raw register `l`).
+// The CRC register is linear over GF(2): update(l, A||B) = ADV_|B|(update(l, A)) ^ update(0, B),
+// where ADV_k advances the register over k zero bytes.  adv[t] are 4x256 lookup tables of
+// ADV_{4<<t}, t = 0..5 (4, 8, 16, 32, 64, 128 bytes).  Lane i takes every 32nd aligned 4-byte
+// word (coalesced 128 B rows): R_i = ADV_128(R_i) ^ ADV_4(word); the words are front-padded with
+// virtual zero words (no-ops on a zero register) so that the last word sits in lane 31, the
+// incoming register value is XORed into the first four message bytes, a 5-level shuffle tree
+// with ADV_4..ADV_64 folds the 32 lanes, and the <= 3 trailing bytes finish serially.
+__device__ __forceinline__ uint32_t crc_adv(const uint32_t* __restrict__ T, uint32_t x) {
+    return __ldg(T + (x & 0xff)) ^ __ldg(T + 256 + ((x >> 8) & 0xff)) ^ __ldg(T + 512 + ((x >> 16) & 0xff)) ^ __ldg(T + 768 + (x >> 24));
+}
+__device__ __forceinline__ uint32_t warp_crc32c_update(uint32_t l, const uint8_t* p, uint32_t n, uint32_t lane,
+                                                       const uint32_t* __restrict__ adv) {
+    if (n < 8) return crc32c_bytes_serial(l, p, n);                 // (uniform across the warp)
+    const uint32_t lead = (uint32_t)((uintptr_t)p & 3u);
+    const uint32_t* a0 = reinterpret_cast<const uint32_t*>(p - lead);
+    const uint32_t W = (lead + n) >> 2, tailn = (lead + n) & 3u;
+    const uint32_t off = (32u - (W & 31u)) & 31u, rows = (W + off) >> 5;
+    uint32_t R = 0;
+    for (uint32_t r = 0; r < rows; r++) {
+        const int32_t v = (int32_t)(r * 32 + lane) - (int32_t)off;
+        uint32_t w = 0;
+        if (v >= 0) {
+            w = __ldg(a0 + v);
+            if (v == 0) { w &= 0xffffffffu << (8 * lead); w ^= l << (8 * lead); }
+            else if (v == 1 && lead) w ^= l >> (32 - 8 * lead);
+        }
+        R = crc_adv(adv + 5 * 1024, R) ^ crc_adv(adv, w);
+    }
+    #pragma unroll
+    for (int t = 0; t < 5; t++) {
+        const uint32_t d = 1u << t;
+        const uint32_t left = __shfl_up_sync(0xffffffffu, R, d);
+        if ((lane & (2 * d - 1)) == 2 * d - 1) R = crc_adv(adv + t * 1024, left) ^ R;
+    }
+    R = __shfl_sync(0xffffffffu, R, 31);
+    return crc32c_bytes_serial(R, reinterpret_cast<const uint8_t*>(a0 + W), tailn);
+}
+
 // byte j of the base-128 varint of v (n bytes long)
 __device__ __forceinline__ uint8_t varint_byte(uint64_t v, uint32_t j, uint32_t n) {
     return (uint8_t)(((v >> (7 * j)) & 0x7f) | (j + 1 < n ? 0x80 : 0));
@@ -838,14 +879,8 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
         // Crc32cVerify (policy/crc32c_checksum.cpp:44-61) over body_wo_att
         const uint32_t req_size = d.body_size - d.meta_size;
         int64_t bwo = (int64_t)req_size - (int64_t)d.attachment_size; if (bwo > (int64_t)req_size) bwo = req_size;
-        uint32_t ok = 1;
-        if (lane == 0) {
-            const uint32_t crc = crc32c_bytes_serial(0xffffffffu, frame + 12 + d.meta_size, (uint32_t)bwo) ^ 0xffffffffu;
-            const uint32_t expected = crc32c_unmask(load_be32(frame + a.cks_off));
-            ok = crc == expected;
-        }
-        ok = __shfl_sync(0xffffffffu, ok, 0);
-        if (!ok) status = B2_MSG_ERROR_REPLIED;
+        const uint32_t crc = warp_crc32c_update(0xffffffffu, frame + 12 + d.meta_size, (uint32_t)bwo, lane, B.crc_adv) ^ 0xffffffffu;
+        if (crc != crc32c_unmask(load_be32(frame + a.cks_off))) status = B2_MSG_ERROR_REPLIED;
     }
     if (status == B2_MSG_ERROR_REPLIED) {
         uint32_t n = 0;
@@ -869,14 +904,11 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
     uint32_t crc_be = 0;
     if (r_cks_type == B2_CHECKSUM_TYPE_CRC32C) {
         // Crc32cCompute (policy/crc32c_checksum.cpp:28-42) over the serialized EchoResponse
-        if (lane == 0) {
-            uint32_t l = 0xffffffffu;
-            uint8_t hdr[6]; hdr[0] = 0x0a; uint8_t* e = put_varint(hdr + 1, a.msg_len);
-            l = crc32c_bytes_serial(l, hdr, (uint32_t)(e - hdr));
-            l = crc32c_bytes_serial(l, frame + a.msg_off, a.msg_len);
-            crc_be = crc32c_mask(l ^ 0xffffffffu);
-        }
-        crc_be = __shfl_sync(0xffffffffu, crc_be, 0);
+        uint32_t l = 0xffffffffu;
+        uint8_t hdr[6]; hdr[0] = 0x0a; uint8_t* e = put_varint(hdr + 1, a.msg_len);
+        l = crc32c_bytes_serial(l, hdr, (uint32_t)(e - hdr));
+        l = warp_crc32c_update(l, frame + a.msg_off, a.msg_len, lane, B.crc_adv);
+        crc_be = crc32c_mask(l ^ 0xffffffffu);
     }
     write_echo_prefix(out, lane, d.correlation_id, a.att_len, r_cks_type, cks_len, crc_be, frame + a.cks_off, a.msg_len, ml, vl, prefix);
     // payload: message bytes (+ attachment when it directly follows them, the normal layout)
