@@ -32,7 +32,7 @@ struct b2_ctx {
     // device
     uint8_t* d_bytes = nullptr; b2_run* d_runs = nullptr; uint32_t* d_run_tile_base = nullptr;
     TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; uint32_t* d_tile_scratch = nullptr; b2_run_status* d_run_status = nullptr;
-    uint32_t* d_frame_off = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr; PackJob* d_jobs = nullptr; uint8_t* d_heads = nullptr;
+    uint32_t* d_frame_off = nullptr; uint32_t* d_frame_run = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr; PackJob* d_jobs = nullptr; uint8_t* d_heads = nullptr;
     uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr;
     uint32_t* d_crc_adv = nullptr; unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
     uint32_t max_tiles = 0; uint32_t n_sms = 148; bool use_tma_pack = true;
@@ -73,7 +73,7 @@ extern "C" void b2_ctx_destroy(b2_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->opt.device);
     cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch);
-    cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_heads); cudaFree(c->d_slot);
+    cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_frame_run); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_heads); cudaFree(c->d_slot);
     cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv);
     cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
     cudaFreeHost(c->h_run_tile_base);
@@ -120,6 +120,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     ALLOC(c->d_tile_scratch, 12 * (size_t)c->max_tiles);
     ALLOC(c->d_run_status, sizeof(b2_run_status) * (size_t)o->max_runs);
     ALLOC(c->d_frame_off, 4 * (size_t)o->max_msgs);
+    ALLOC(c->d_frame_run, 4 * (size_t)o->max_msgs);
     ALLOC(c->d_msgs, sizeof(b2_msg_desc) * (size_t)o->max_msgs);
     ALLOC(c->d_aux, sizeof(MsgAux) * (size_t)o->max_msgs);
     ALLOC(c->d_jobs, sizeof(PackJob) * (size_t)o->max_msgs);
@@ -196,7 +197,7 @@ extern "C" int b2_register_method(b2_ctx* c, const b2_method* m) {
 static BatchPtrs make_ptrs(b2_ctx* c) {
     BatchPtrs B;
     B.bytes = c->d_bytes; B.runs = c->d_runs; B.run_tile_base = c->d_run_tile_base; B.tiles = c->d_tiles;
-    B.tile_base = c->d_tile_base; B.tile_scratch = c->d_tile_scratch; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.msgs = c->d_msgs;
+    B.tile_base = c->d_tile_base; B.tile_scratch = c->d_tile_scratch; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.frame_run = c->d_frame_run; B.msgs = c->d_msgs;
     B.aux = c->d_aux; B.jobs = c->d_jobs; B.heads = c->d_heads; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.counters = c->d_counters;
     B.totals = c->d_totals; B.methods = c->d_methods; B.crc_adv = c->d_crc_adv;
     B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes;
@@ -250,7 +251,7 @@ static int launch_pipeline(b2_ctx* c) {
     // message-count dependent kernels are persistent: fixed grids (multiples of the SM count)
     // stride over the device-side message count, so no host round trip sizes a launch
     const uint32_t sms = c->n_sms;
-    k_decode<<<sms * 6, kDecodeWarps * 32, 0, s>>>(B, C); launches++; mark("decode");
+    k_decode<<<sms * B2_DECODE_MIN_BLOCKS, kDecodeWarps * 32, 0, s>>>(B, C); launches++; mark("decode");
     k_scan_blocks<<<sms, kScanBlock, 0, s>>>(B); launches++;
     k_scan_top<<<1, 1024, 0, s>>>(B); launches++; mark("scan");
     if (c->use_tma_pack) k_pack_tma<<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C);

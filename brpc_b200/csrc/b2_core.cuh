@@ -113,6 +113,7 @@ B2_HD Step cut_input_message(const uint8_t* run, uint32_t len, uint32_t pos, int
 struct Reader { const uint8_t* p; const uint8_t* end; };
 
 B2_HD bool rd_varint(Reader& r, uint64_t& out) {       // VarintParse<uint64_t>: <= 10 bytes
+    if (r.p < r.end && *r.p < 0x80) { out = *r.p++; return true; }
     uint64_t v = 0;
     #pragma unroll 1
     for (int i = 0; i < 10; i++) {
@@ -124,6 +125,7 @@ B2_HD bool rd_varint(Reader& r, uint64_t& out) {       // VarintParse<uint64_t>:
     return false;
 }
 B2_HD bool rd_tag(Reader& r, uint32_t& tag) {           // ReadTag: <= 5 bytes
+    if (r.p < r.end && *r.p < 0x80) { tag = *r.p++; return true; }
     uint32_t v = 0;
     #pragma unroll 1
     for (int i = 0; i < 5; i++) {
@@ -135,6 +137,11 @@ B2_HD bool rd_tag(Reader& r, uint32_t& tag) {           // ReadTag: <= 5 bytes
     return false;
 }
 B2_HD bool rd_size(Reader& r, uint32_t& n) {            // ReadSize: <= 5 bytes, < 2 GiB - 16, inside parent
+    if (r.p < r.end && *r.p < 0x80) {
+        const uint32_t v1 = *r.p++;
+        if ((uint64_t)v1 > (uint64_t)(r.end - r.p)) return false;
+        n = v1; return true;
+    }
     uint32_t v = 0;
     #pragma unroll 1
     for (int i = 0; i < 5; i++) {

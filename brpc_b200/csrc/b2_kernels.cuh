@@ -86,7 +86,8 @@ struct BatchPtrs {
     uint32_t* tile_base;             // [n_tiles] run-relative index of the tile's first message
     uint32_t* tile_scratch;          // [3 * n_tiles] k_resolve spill when a run's tiles exceed shared memory
     b2_run_status* run_status;
-    uint32_t* frame_off;             // [max_msgs] frame offsets (batch-relative), bit31.. unused
+    uint32_t* frame_off;             // [max_msgs] frame offsets (batch-relative), bit 31 = protocol - 1
+    uint32_t* frame_run;             // [max_msgs] run index of every message
     b2_msg_desc* msgs;
     MsgAux* aux;
     PackJob* jobs;                   // [max_msgs]
@@ -368,9 +369,9 @@ __global__ void __launch_bounds__(1024) k_run_prefix(BatchPtrs B) {
 
 // --- k_frame_table: one thread per tile --------------------------------------
 struct EmitFrame {
-    uint32_t* out; uint32_t run_off; uint32_t cap_left;
+    uint32_t* out; uint32_t* out_run; uint32_t run_off; uint32_t run_idx; uint32_t cap_left;
     __device__ __forceinline__ void operator()(uint32_t i, const Step& s) const {
-        if (i < cap_left) out[i] = (run_off + s.frame_pos) | ((uint32_t)(s.index - 1) << 31);
+        if (i < cap_left) { out[i] = (run_off + s.frame_pos) | ((uint32_t)(s.index - 1) << 31); out_run[i] = run_idx; }
     }
 };
 __global__ void __launch_bounds__(128) k_frame_table(BatchPtrs B, DevConfig C) {
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(128) k_frame_table(BatchPtrs B, DevConfig C) {
     const b2_run run = B.runs[r];
     const uint32_t first = B.run_status[r].first_msg + B.tile_base[t];
     TileRec tmp;
-    EmitFrame e; e.out = B.frame_off + first; e.run_off = run.offset; e.cap_left = B.max_msgs - first;
+    EmitFrame e; e.out = B.frame_off + first; e.out_run = B.frame_run + first; e.run_off = run.offset; e.run_idx = r; e.cap_left = B.max_msgs - first;
     walk_tile<false>(B.bytes + run.offset, run.length, rec.entry, rec.pf_in, (k + 1) << C.tile_shift, C.max_body_size, tmp, e);
 }
 
@@ -444,18 +445,21 @@ __device__ __forceinline__ uint32_t error_text_len(const DevConfig& C, const Dev
 // k_decode stages the first kRowBytes of every frame (header + RpcMeta + first body bytes) in
 // shared memory with coalesced 4-byte loads (one row per lane) and decodes from there; the head
 // records are assembled in shared memory and leave with coalesced 16-byte stores.
-constexpr uint32_t kRowBytes = 176, kRowWords = kRowBytes / 4;
+constexpr uint32_t kRowBytes = 160, kRowVecs = kRowBytes / 16;
 constexpr uint32_t kDecodeWarps = 4;
+#ifndef B2_DECODE_MIN_BLOCKS
+#define B2_DECODE_MIN_BLOCKS 6
+#endif
 struct DecodeWarpSmem {
     alignas(16) uint8_t head[32][kHeadBytes];
-    alignas(16) uint32_t row[32][kRowWords];
+    alignas(16) uint4 row[32][kRowVecs + 1];       // +1: odd 16-byte stride spreads the rows over the banks
 };
 
 __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
                                            const uint8_t* srow, uint8_t* shead);
 
 // persistent: a fixed grid (multiple of the SM count) strides over the device-side message count
-__global__ void __launch_bounds__(kDecodeWarps * 32) k_decode(BatchPtrs B, DevConfig C) {
+__global__ void __launch_bounds__(kDecodeWarps * 32, B2_DECODE_MIN_BLOCKS) k_decode(BatchPtrs B, DevConfig C) {
     __shared__ DecodeWarpSmem smem[kDecodeWarps];
     const uint32_t n_msgs = B.totals[0];
     if (B.totals[2] & 1u) return;
@@ -465,15 +469,16 @@ __global__ void __launch_bounds__(kDecodeWarps * 32) k_decode(BatchPtrs B, DevCo
         const uint32_t i = i0 + lane;
         const uint32_t fo_raw = i < n_msgs ? B.frame_off[i] : 0;
         const uint32_t nm = min(32u, n_msgs - i0);
-        // stage: row m <- the aligned words covering frame m's first bytes
-        for (uint32_t m = 0; m < nm; m++) {
-            const uint32_t f = __shfl_sync(0xffffffffu, fo_raw, m) & 0x7fffffffu;
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(B.bytes + (f & ~3u));
-            S.row[m][lane] = __ldg(src + lane);                                  // (batch buffer is padded past its end)
-            if (lane + 32 < kRowWords) S.row[m][lane + 32] = __ldg(src + lane + 32);
+        // stage: row m <- the 16-byte aligned vectors covering frame m's first bytes; half a warp per row
+        const uint32_t sub = lane & 15, half = lane >> 4;
+        for (uint32_t m2 = 0; m2 < nm; m2 += 2) {
+            const uint32_t m = m2 + half;
+            const uint32_t f = __shfl_sync(0xffffffffu, fo_raw, m & 31) & 0x7fffffffu;
+            if (m < nm && sub < kRowVecs)
+                S.row[m][sub] = __ldg(reinterpret_cast<const uint4*>(B.bytes + (f & ~15u)) + sub);   // (buffer is padded past its end)
         }
         __syncwarp();
-        if (i < n_msgs) decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 3u), S.head[lane]);
+        if (i < n_msgs) decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 15u), S.head[lane]);
         __syncwarp();
         // heads of 32 consecutive messages are contiguous: coalesced 16-byte stores
         {
@@ -492,18 +497,13 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
     const uint8_t* gframe = B.bytes + fo;
     // decode from the staged copy when header + meta + the first body bytes are inside it
     const uint32_t meta_size_peek = load_be32(srow + 8);
-    const bool staged = (uint64_t)(fo_raw & 3u) + 12ull + meta_size_peek + 40ull <= kRowBytes;
+    const bool staged = (uint64_t)(fo_raw & 15u) + 12ull + meta_size_peek + 40ull <= kRowBytes;
     const uint8_t* frame = staged ? srow : gframe;
     b2_msg_desc d;
     d.frame_off = fo; d.body_size = load_be32(frame + 4); d.meta_size = load_be32(frame + 8);
     d.correlation_id = 0; d.log_id = 0; d.attachment_size = 0; d.compress_type = 0; d.checksum_type = 0; d.error_code = 0;
     d.has_bits = 0; d.protocol = (uint8_t)proto; d.content_type = 0; d.method_idx = -1; d.status = 0; d.resp_off = 0; d.resp_len = 0;
-    // run index: binary search over first_msg (runs without messages are skipped by the <= rule)
-    {
-        uint32_t lo = 0, hi = B.n_runs;
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (B.run_status[mid].first_msg <= i) lo = mid; else hi = mid; }
-        d.run_idx = lo;
-    }
+    d.run_idx = B.frame_run[i];
     MsgAux a; a.msg_off = a.msg_len = a.att_len = a.att_off = a.cks_off = a.cks_len = 0;
     a.svc_off = a.svc_len = a.mth_off = a.mth_len = 0; a.pad = 0; a.err_kind = kErrNone;
     uint32_t resp_len = 0;
