@@ -274,6 +274,34 @@ def main():
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     assert e2e_ok, "e2e batches returned wrong results"
 
+    # ---- latency: one small batch at a time through the same ABI call (p99 of the metric) --------
+    # 64 connections x 1 complete 1 KB request each = what 64 synchronous client threads
+    # (multi_threaded_echo_c++ -thread_num=64) have in flight; host buffers, blocking call.
+    from brpc_b200 import press as _press
+    from brpc_b200.abi import PinnedBuffer as _Pinned
+    lat_ctx = brpc_b200.Context(device=dev, max_batch_bytes=1 << 20, max_msgs=4096, max_runs=N_SOCKETS, tile_bytes=args.tile)
+    _sp = _press.spec(payload_bytes=PAYLOAD)
+    _f = _press.frame(_sp, 12345)
+    _stride = (len(_f) + 15) // 16 * 16
+    lbuf = _Pinned(N_SOCKETS * _stride)
+    lruns = np.zeros(N_SOCKETS, dtype=brpc_b200.RUN_DT)
+    for s_ in range(N_SOCKETS):
+        fr = _press.frame(_sp, (s_ << 32) + 7)
+        lbuf.array[s_ * _stride:s_ * _stride + len(fr)] = np.frombuffer(fr, np.uint8)
+        lruns[s_] = (s_, s_ * _stride, len(fr), 1, 0)
+    for _ in range(50):
+        lat_ctx.process_batch_ptr(lbuf.ptr, N_SOCKETS * _stride, lruns)
+    lat = []
+    for _ in range(2000):
+        t1 = time.perf_counter()
+        lrs, lm, lresp, _i = lat_ctx.process_batch_ptr(lbuf.ptr, N_SOCKETS * _stride, lruns)
+        lat.append((time.perf_counter() - t1) * 1e6)
+    assert len(lm) == N_SOCKETS and np.all(lm["status"] == 0)
+    lat.sort()
+    latency = {"batch": "%d connections x 1 request (1 KB), blocking b2_process_batch, host buffers" % N_SOCKETS,
+               "p50_us": lat[len(lat) // 2], "p99_us": lat[int(len(lat) * 0.99)], "mean_us": sum(lat) / len(lat),
+               "iters": len(lat), "kernel_launches_per_batch": int(_i["n_launches"])}
+
     # ---- reduce over ranks: max time, summed messages; NCCL all-reduce of the bvar-like counters --
     t_dev = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(n_full)], dtype=torch.float64, device="cuda")
@@ -314,7 +342,7 @@ def main():
                                       "frac": pipe_alg / (step_ms_rank0 * 1e-3) / 1e9 / hbm_peak,
                                       "algorithmic_bytes_per_msg": pipe_alg / len(msgs), "single_pass_ms": pipe_ms,
                                       "stage_ms": stages, "note": "whole hot path: (req + resp + 64 B desc) x msgs / measured step time"},
-                "clocks": clocks, "wall_ms_per_step": wall_ms_max / steps, "msgs_per_step": total_msgs,
+                "latency": latency, "clocks": clocks, "wall_ms_per_step": wall_ms_max / steps, "msgs_per_step": total_msgs,
                 "counters_allreduced": counters}
         if not args.no_cpu_baseline:
             # bounded sample: the first 8 connections of the same batch, 1 thread, ~10 s

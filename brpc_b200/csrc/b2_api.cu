@@ -22,6 +22,9 @@ static void set_err(const char* fmt, const char* a = "", const char* b = "") { s
 
 namespace {
 constexpr int kMaxStages = 16;
+constexpr uint32_t kSmallBytes = 128 << 10;        // batches up to this size take the latency path
+constexpr uint32_t kSmallRuns = 512, kSmallMsgs = 1024;
+constexpr size_t kSmallBlock = 64 + kSmallRuns * 32 + kSmallMsgs * 64 + (kSmallBytes + kSmallMsgs * 80 + 4096);
 struct Stage { const char* name; cudaEvent_t ev; };
 }
 
@@ -48,6 +51,11 @@ struct b2_ctx {
     int n_stages = 0;
     float last_kernel_ms = 0.f; uint32_t last_launches = 0;
     cudaEvent_t ev_first = nullptr, ev_last = nullptr; bool first_pending = true;
+    bool profile_stages = false; bool allow_small = true;      // per-stage events only when a harness asks for stage times
+    // small-batch (latency) mode: one compact H2D block, one compact output block, one D2H, one sync
+    uint8_t* d_meta = nullptr; uint8_t* h_meta = nullptr;       // [runs | run_tile_base]
+    uint8_t* d_small = nullptr; uint8_t* h_small = nullptr;     // [totals | run_status | msgs | resp]
+    bool small = false, small_copy_queued = false; uint32_t small_msgs = 0, small_resp = 0, small_off_rs = 0, small_off_msgs = 0, small_off_resp = 0, small_total = 0;
 };
 
 static uint32_t g_crc_tab_host[256];
@@ -74,7 +82,7 @@ extern "C" void b2_ctx_destroy(b2_ctx* c) {
     cudaSetDevice(c->opt.device);
     cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch);
     cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_frame_run); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_heads); cudaFree(c->d_slot);
-    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv);
+    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
     cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
     cudaFreeHost(c->h_run_tile_base);
     for (int i = 0; i <= kMaxStages; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -132,6 +140,10 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     ALLOC(c->d_totals, 16);
     ALLOC(c->d_methods, sizeof(DevMethod) * 64);
     ALLOC(c->d_crc_adv, 6 * 4 * 256 * 4);
+    ALLOC(c->d_meta, (size_t)o->max_runs * 28 + 64);
+    ALLOC(c->d_small, kSmallBlock);
+    HALLOC(c->h_meta, (size_t)o->max_runs * 28 + 64);
+    HALLOC(c->h_small, kSmallBlock);
     HALLOC(c->h_run_status, sizeof(b2_run_status) * (size_t)o->max_runs);
     HALLOC(c->h_msgs, sizeof(b2_msg_desc) * (size_t)o->max_msgs);
     HALLOC(c->h_resp, (size_t)c->opt.max_resp_bytes);
@@ -201,6 +213,15 @@ static BatchPtrs make_ptrs(b2_ctx* c) {
     B.aux = c->d_aux; B.jobs = c->d_jobs; B.heads = c->d_heads; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.counters = c->d_counters;
     B.totals = c->d_totals; B.methods = c->d_methods; B.crc_adv = c->d_crc_adv;
     B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes;
+    B.runs = reinterpret_cast<const b2_run*>(c->d_meta);
+    B.run_tile_base = reinterpret_cast<const uint32_t*>(c->d_meta + (size_t)c->n_runs * sizeof(b2_run));
+    if (c->small) {
+        B.totals = reinterpret_cast<uint32_t*>(c->d_small);
+        B.run_status = reinterpret_cast<b2_run_status*>(c->d_small + c->small_off_rs);
+        B.msgs = reinterpret_cast<b2_msg_desc*>(c->d_small + c->small_off_msgs);
+        B.resp = c->d_small + c->small_off_resp;
+        B.max_msgs = c->small_msgs; B.max_resp = c->small_resp;
+    }
     return B;
 }
 
@@ -219,11 +240,20 @@ extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, co
     c->h_run_tile_base[n_runs] = (uint32_t)nt;
     if (nt > c->max_tiles) { set_err("too many tiles"); return B2_E_CAPACITY; }
     c->n_runs = n_runs; c->n_tiles = (uint32_t)nt; c->nbytes = nbytes; c->max_run_tiles = max_rt;
+    // runs + tile bases travel as one compact block (24 B * n is 4-byte aligned)
+    const size_t meta_bytes = (size_t)n_runs * sizeof(b2_run) + 4 * ((size_t)n_runs + 1);
+    if (n_runs) memcpy(c->h_meta, runs, (size_t)n_runs * sizeof(b2_run));
+    memcpy(c->h_meta + (size_t)n_runs * sizeof(b2_run), c->h_run_tile_base, 4 * ((size_t)n_runs + 1));
     if (nbytes) CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
-    if (n_runs) {
-        CU(cudaMemcpyAsync(c->d_runs, runs, sizeof(b2_run) * n_runs, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_meta, c->h_meta, meta_bytes, cudaMemcpyHostToDevice, c->stream));
+    // latency path: outputs of a small batch live in one compact block -> one D2H copy, one sync
+    c->small = c->allow_small && nbytes <= kSmallBytes && n_runs <= kSmallRuns && n_runs > 0;
+    if (c->small) {
+        uint32_t mb = nbytes / 12 + 1; if (mb > kSmallMsgs) mb = kSmallMsgs;
+        c->small_msgs = mb; c->small_resp = nbytes + mb * 80 + 2048;
+        c->small_off_rs = 64; c->small_off_msgs = 64 + n_runs * 32; c->small_off_resp = (c->small_off_msgs + mb * 64 + 255u) & ~255u;
+        c->small_total = c->small_off_resp + c->small_resp;
     }
-    CU(cudaMemcpyAsync(c->d_run_tile_base, c->h_run_tile_base, 4 * ((size_t)n_runs + 1), cudaMemcpyHostToDevice, c->stream));
     c->uploaded = true; c->executed = false;
     return B2_OK;
 }
@@ -233,8 +263,9 @@ static int launch_pipeline(b2_ctx* c) {
     const DevConfig C = c->cfg;
     cudaStream_t s = c->stream;
     int st = 0; uint32_t launches = 0;
-    auto mark = [&](const char* name) { c->stage_names[st] = name; cudaEventRecord(c->ev[st + 1], s); st++; };
-    CU(cudaMemsetAsync(c->d_totals, 0, 16, s));
+    const bool prof = c->profile_stages;
+    auto mark = [&](const char* name) { if (prof) { c->stage_names[st] = name; cudaEventRecord(c->ev[st + 1], s); st++; } };
+    CU(cudaMemsetAsync(B.totals, 0, 16, s));
     CU(cudaEventRecord(c->ev[0], s));
     if (c->n_runs == 0) { c->n_stages = 0; c->last_launches = 0; return B2_OK; }
     if (c->n_tiles) {
@@ -258,6 +289,7 @@ static int launch_pipeline(b2_ctx* c) {
     else k_pack<<<sms * B2_PACK_MIN_BLOCKS, 256, 0, s>>>(B, C);
     launches++; mark("pack");
     k_finalize<<<(c->n_runs + 255) / 256, 256, 0, s>>>(B); launches++; mark("finalize");
+    if (!prof) { c->stage_names[0] = "pipeline"; cudaEventRecord(c->ev[1], s); st = 1; }
     c->n_stages = st; c->last_launches = launches;
     CU(cudaGetLastError());
     return B2_OK;
@@ -266,7 +298,9 @@ static int launch_pipeline(b2_ctx* c) {
 extern "C" int b2_batch_execute(b2_ctx* c, float* kernel_ms, uint32_t* n_launches) {
     if (!c || !c->uploaded) { set_err("no batch uploaded"); return B2_E_INVAL; }
     CU(cudaSetDevice(c->opt.device));
+    c->profile_stages = true;
     int rc = launch_pipeline(c);
+    c->profile_stages = false;
     if (rc != B2_OK) return rc;
     CU(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
@@ -325,10 +359,7 @@ extern "C" int b2_elapsed_ms(b2_ctx* a, b2_ctx* b, float* ms) {
     return B2_OK;
 }
 
-extern "C" int b2_batch_download(b2_ctx* c, b2_batch_result* out) {
-    if (!c || !out || !c->executed) { set_err("no executed batch"); return B2_E_INVAL; }
-    CU(cudaSetDevice(c->opt.device));
-    memset(out, 0, sizeof *out);
+static int download_normal(b2_ctx* c, b2_batch_result* out) {
     CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 16, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (c->n_runs && (c->h_totals[2] & 3u)) {
@@ -342,6 +373,34 @@ extern "C" int b2_batch_download(b2_ctx* c, b2_batch_result* out) {
     out->runs = c->h_run_status; out->n_runs = c->n_runs;
     out->msgs = c->h_msgs; out->n_msgs = n_msgs;
     out->resp = c->h_resp; out->resp_bytes = resp_bytes;
+    return B2_OK;
+}
+
+extern "C" int b2_batch_download(b2_ctx* c, b2_batch_result* out) {
+    if (!c || !out || !c->executed) { set_err("no executed batch"); return B2_E_INVAL; }
+    CU(cudaSetDevice(c->opt.device));
+    memset(out, 0, sizeof *out);
+    if (c->small) {
+        if (!c->small_copy_queued) CU(cudaMemcpyAsync(c->h_small, c->d_small, c->small_total, cudaMemcpyDeviceToHost, c->stream));
+        c->small_copy_queued = false;
+        CU(cudaStreamSynchronize(c->stream));
+        const uint32_t* tot = reinterpret_cast<const uint32_t*>(c->h_small);
+        if (tot[2] & 3u) {
+            // more messages / response bytes than the compact block holds: redo on the normal path
+            c->small = false;
+            int rc = launch_pipeline(c);
+            if (rc != B2_OK) return rc;
+            rc = download_normal(c, out);
+            if (rc != B2_OK) return rc;
+        } else {
+            out->runs = reinterpret_cast<const b2_run_status*>(c->h_small + c->small_off_rs); out->n_runs = c->n_runs;
+            out->msgs = reinterpret_cast<const b2_msg_desc*>(c->h_small + c->small_off_msgs); out->n_msgs = tot[0];
+            out->resp = c->h_small + c->small_off_resp; out->resp_bytes = tot[1];
+        }
+    } else {
+        int rc = download_normal(c, out);
+        if (rc != B2_OK) return rc;
+    }
     out->kernel_ms = c->last_kernel_ms; out->n_launches = c->last_launches;
     return B2_OK;
 }
@@ -352,7 +411,7 @@ extern "C" int b2_batch_submit(b2_ctx* c, const void* bytes, uint32_t nbytes, co
     rc = launch_pipeline(c);
     if (rc != B2_OK) return rc;
     c->executed = true;
-    CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 16, cudaMemcpyDeviceToHost, c->stream));
+    if (c->small) { CU(cudaMemcpyAsync(c->h_small, c->d_small, c->small_total, cudaMemcpyDeviceToHost, c->stream)); c->small_copy_queued = true; }
     return B2_OK;
 }
 

@@ -275,3 +275,17 @@ def test_messenger_carries_partial_frames(b2):
             continue      # a corrupted frame closes the socket; how much was cut before depends on the read pattern
         exp = [(int(x["status"]), int(x["correlation_id"]), bytes(o_resp[int(x["resp_off"]):int(x["resp_off"]) + int(x["resp_len"])])) for x in o_msgs]
         assert got[s] == exp
+
+
+def test_small_batch_overflow_redo(b2):
+    """> 1024 tiny messages in < 128 KB: the compact latency block overflows and the batch is
+    transparently redone on the normal path; results identical to the oracle."""
+    ctx = make_ctx(b2)
+    rng = random.Random(12)
+    frames = [echo_frame(rng, i, b"") for i in range(1500)]
+    assert sum(map(len, frames)) < 128 << 10
+    dev, _ = run_both(b2, ctx, [b"".join(frames[:700]), b"".join(frames[700:])])
+    assert len(dev[1]) == 1500
+    # and right at the edge
+    run_both(b2, ctx, [b"".join(frames[:1024])])
+    run_both(b2, ctx, [b"".join(frames[:1025])])
