@@ -95,6 +95,7 @@ struct BatchPtrs {
     uint32_t* slot;                  // [max_msgs+1] slot sizes -> exclusive offsets
     uint32_t* scan_tmp;              // block sums
     uint8_t* resp;
+    uint8_t* unz;                    // [max_resp] scratch: decompressed request bodies, at the message's slot offset
     unsigned long long* counters;    // int64[B2_N_COUNTERS]
     uint32_t* totals;                // [0]=n_msgs [1]=resp_bytes [2]=overflow flags
     const DevMethod* methods;
@@ -442,6 +443,7 @@ __device__ __forceinline__ uint32_t error_text_len(const DevConfig& C, const Dev
     return n;
 }
 
+__device__ __forceinline__ bool snappy_preamble(const uint8_t* in, uint32_t n, uint32_t& ulen, uint32_t& used);
 // k_decode stages the first kRowBytes of every frame (header + RpcMeta + first body bytes) in
 // shared memory with coalesced 4-byte loads (one row per lane) and decodes from there; the head
 // records are assembled in shared memory and leave with coalesced 16-byte stores.
@@ -549,8 +551,26 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                 const uint32_t in_att_len = att > 0 ? (uint32_t)att : 0;
                 if (m.content_type != B2_CONTENT_TYPE_PB) d.status = B2_MSG_UNSUPPORTED;
                 else if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) d.status = B2_MSG_UNSUPPORTED;
-                else if (m.compress_type == B2_COMPRESS_TYPE_SNAPPY) d.status = B2_MSG_UNSUPPORTED;   // TODO(snappy kernels)
                 else if (mp->response_compress_type != B2_COMPRESS_TYPE_NONE) d.status = B2_MSG_UNSUPPORTED;
+                else if (m.compress_type == B2_COMPRESS_TYPE_SNAPPY) {
+                    // SnappyDecompress (policy/snappy_compress.cpp:51-70) happens in the pack stage; here only the
+                    // announced length is read to reserve the reply slot.  A stream cannot expand more than ~22x
+                    // (a 3-byte copy yields <= 64 bytes), so an announced length beyond 32x + 64 must fail.
+                    uint32_t ulen = 0, used = 0;
+                    bool ok = !(m.checksum_type == B2_CHECKSUM_TYPE_CRC32C && a.cks_len != 4);
+                    if (ok) ok = snappy_preamble(gframe + 12 + d.meta_size, body_wo_att, ulen, used);
+                    if (ok && (uint64_t)ulen > 32ull * body_wo_att + 64ull) ok = false;
+                    if (!ok) { a.err_kind = kErrParseRequest; d.error_code = B2_EREQUEST; }
+                    else {
+                        d.status = B2_MSG_ECHOED;
+                        a.msg_off = kNone; a.msg_len = ulen;        // resolved after decompression
+                        if (mp->echo_attachment) { a.att_len = in_att_len; a.att_off = 12 + d.meta_size + body_wo_att; }
+                        const uint32_t cks_len = mp->response_checksum_type == B2_CHECKSUM_TYPE_CRC32C ? 4u : a.cks_len;
+                        const uint32_t ml = response_meta_len(0, 0, 0, m.correlation_id, a.att_len, mp->response_checksum_type, cks_len);
+                        resp_len = 12 + ml + 8 + ulen + a.att_len;   // upper bound; the pack stage writes the real length
+                        a.pad = 0;
+                    }
+                }
                 else if (m.compress_type != B2_COMPRESS_TYPE_NONE) { a.err_kind = kErrParseRequest; d.error_code = B2_EREQUEST; }
                 else {
                     Span msg; msg.off = 0; msg.len = 0;
@@ -589,7 +609,7 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                 resp_len = 12 + response_meta_len(d.error_code, tl, 0, m.correlation_id, 0, 0, a.cks_len);
             }
             // a CRC-verified request can still turn into an EREQUEST reply in k_pack: reserve for both
-            if (d.status == B2_MSG_ECHOED && m.checksum_type == B2_CHECKSUM_TYPE_CRC32C) {
+            if (d.status == B2_MSG_ECHOED && (m.checksum_type == B2_CHECKSUM_TYPE_CRC32C || m.compress_type == B2_COMPRESS_TYPE_SNAPPY)) {
                 b2_msg_desc e = d; MsgAux ea = a; e.error_code = B2_EREQUEST; ea.err_kind = kErrParseRequest;
                 const uint32_t tl = error_text_len(C, B.methods, e, ea, frame);
                 const uint32_t el = 12 + response_meta_len(B2_EREQUEST, tl, 0, m.correlation_id, 0, 0, a.cks_len);
@@ -604,7 +624,7 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
     B.slot[i] = slot_len;
     // ---- bandwidth path: pre-build the reply prefix, shifted to the slot alignment -------------
     PackJob job; job.src_off = 0; job.bulk_len = 0; job.head_len = 0; job.pad = (uint8_t)a.pad; job.fast = 0; job.slot_len = slot_len;
-    if (d.status == B2_MSG_ECHOED && d.checksum_type != B2_CHECKSUM_TYPE_CRC32C &&
+    if (d.status == B2_MSG_ECHOED && d.checksum_type != B2_CHECKSUM_TYPE_CRC32C && d.compress_type == B2_COMPRESS_TYPE_NONE &&
         B.methods[d.method_idx].response_checksum_type == B2_CHECKSUM_TYPE_NONE &&
         (a.att_len == 0 || a.att_off == a.msg_off + a.msg_len)) {
         const uint32_t ml = response_meta_len(0, 0, 0, d.correlation_id, a.att_len, 0, a.cks_len);
@@ -693,6 +713,75 @@ __global__ void __launch_bounds__(1024) k_scan_top(BatchPtrs B) {
         __syncthreads();
     }
     if (threadIdx.x == 0) { B.totals[1] = s_carry; if (s_carry > B.max_resp) B.totals[2] |= 2u; }
+}
+
+// Snappy raw-format decoder as a warp-level primitive: butil::snappy::RawUncompress
+// (src/butil/third_party/snappy/snappy.cc:716-787 DecompressAllTags, :1145-1215 SnappyArrayWriter,
+// format_description.txt).  The tag stream is inherently serial; every lane follows it (the tag
+// bytes are broadcast loads) and the bytes of each element are moved by the whole warp.  A copy may
+// overlap its own output (offset < length, RLE): byte i comes from out[op - offset + i % offset],
+// which was written by an earlier element, so the lanes are independent.  Returns true iff the
+// stream is well formed, consumed exactly, and produced exactly the announced length.
+__device__ __forceinline__ bool snappy_preamble(const uint8_t* in, uint32_t n, uint32_t& ulen, uint32_t& used) {
+    uint32_t v = 0, shift = 0, ip = 0;              // SnappyDecompressor::ReadUncompressedLength, snappy.cc:690-711
+    for (;;) {
+        if (shift >= 32) return false;
+        if (ip >= n) return false;
+        const uint32_t c = in[ip++];
+        v |= (c & 0x7f) << shift;
+        if (c < 128) break;
+        shift += 7;
+    }
+    ulen = v; used = ip;
+    return true;
+}
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane);
+__device__ __noinline__ bool warp_snappy_decode(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, uint32_t lane,
+                                                uint32_t& produced) {
+    uint32_t ulen, ip;
+    produced = 0;
+    if (!snappy_preamble(in, n, ulen, ip)) return false;
+    if (ulen > cap) return false;
+    uint32_t op = 0;
+    while (ip < n) {
+        const uint32_t c = in[ip++];
+        if ((c & 3u) == 0) {                                         // literal
+            uint32_t len = (c >> 2) + 1;
+            if (len >= 61) {
+                const uint32_t ll = len - 60;
+                if (n - ip < ll) return false;
+                uint32_t v = 0;
+                for (uint32_t k = 0; k < ll; k++) v |= (uint32_t)in[ip + k] << (8 * k);
+                len = v + 1; ip += ll;
+                if (len == 0) return false;                          // 2^32 wrap: cannot fit
+            }
+            if (len > n - ip) return false;                          // premature end of input
+            if (len > ulen - op) return false;                       // SnappyArrayWriter::Append: no room
+            warp_copy(out + op, in + ip, len, lane);
+            ip += len; op += len;
+        } else {                                                     // copy
+            uint32_t len, offset;
+            if ((c & 3u) == 1) {
+                if (n - ip < 1) return false;
+                len = ((c >> 2) & 7u) + 4; offset = ((c >> 5) << 8) | in[ip]; ip += 1;
+            } else if ((c & 3u) == 2) {
+                if (n - ip < 2) return false;
+                len = (c >> 2) + 1; offset = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8); ip += 2;
+            } else {
+                if (n - ip < 4) return false;
+                len = (c >> 2) + 1;
+                offset = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8) | ((uint32_t)in[ip + 2] << 16) | ((uint32_t)in[ip + 3] << 24); ip += 4;
+            }
+            if (offset == 0 || offset > op) return false;            // AppendFromSelf: op - base <= offset - 1
+            if (len > ulen - op) return false;
+            const uint8_t* from = out + op - offset;
+            for (uint32_t i = lane; i < len; i += 32) out[op + i] = from[offset >= len ? i : i % offset];
+            op += len;
+        }
+        __syncwarp();                                                // later elements read what this one wrote
+    }
+    produced = op;
+    return op == ulen;
 }
 
 #ifndef B2_PACK_MIN_BLOCKS
@@ -882,6 +971,20 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
         const uint32_t crc = warp_crc32c_update(0xffffffffu, frame + 12 + d.meta_size, (uint32_t)bwo, lane, B.crc_adv) ^ 0xffffffffu;
         if (crc != crc32c_unmask(load_be32(frame + a.cks_off))) status = B2_MSG_ERROR_REPLIED;
     }
+    const uint8_t* msg_src = frame + a.msg_off;
+    uint32_t msg_len = a.msg_len;
+    if (status == B2_MSG_ECHOED && d.compress_type == B2_COMPRESS_TYPE_SNAPPY) {
+        // SnappyDecompress (policy/snappy_compress.cpp:51-70) into the scratch slot, then ParseFromZeroCopyStream
+        const uint32_t req_size = d.body_size - d.meta_size;
+        int64_t bwo = (int64_t)req_size - (int64_t)d.attachment_size; if (bwo > (int64_t)req_size) bwo = req_size;
+        uint8_t* scratch = B.unz + slot_off;
+        uint32_t produced = 0;
+        bool ok = warp_snappy_decode(frame + 12 + d.meta_size, (uint32_t)bwo, scratch, a.msg_len, lane, produced);
+        Span msg; msg.off = 0; msg.len = 0;
+        if (ok) ok = decode_echo_request(scratch, produced, msg);
+        if (!ok) status = B2_MSG_ERROR_REPLIED;
+        else { msg_src = scratch + msg.off; msg_len = msg.len; }
+    }
     if (status == B2_MSG_ERROR_REPLIED) {
         uint32_t n = 0;
         if (lane == 0) {
@@ -897,26 +1000,26 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
     const int32_t r_cks_type = mp->response_checksum_type;
     const uint32_t cks_len = r_cks_type == B2_CHECKSUM_TYPE_CRC32C ? 4u : a.cks_len;
     const uint32_t ml = response_meta_len(0, 0, 0, d.correlation_id, a.att_len, r_cks_type, cks_len);
-    const uint32_t vl = varint_len(a.msg_len);
+    const uint32_t vl = varint_len(msg_len);
     const uint32_t prefix = 12 + ml + 1 + vl;
-    const uint32_t resp_len = prefix + a.msg_len + a.att_len;
+    const uint32_t resp_len = prefix + msg_len + a.att_len;
     uint8_t* out = B.resp + slot_off + a.pad;
     uint32_t crc_be = 0;
     if (r_cks_type == B2_CHECKSUM_TYPE_CRC32C) {
         // Crc32cCompute (policy/crc32c_checksum.cpp:28-42) over the serialized EchoResponse
         uint32_t l = 0xffffffffu;
-        uint8_t hdr[6]; hdr[0] = 0x0a; uint8_t* e = put_varint(hdr + 1, a.msg_len);
+        uint8_t hdr[6]; hdr[0] = 0x0a; uint8_t* e = put_varint(hdr + 1, msg_len);
         l = crc32c_bytes_serial(l, hdr, (uint32_t)(e - hdr));
-        l = warp_crc32c_update(l, frame + a.msg_off, a.msg_len, lane, B.crc_adv);
+        l = warp_crc32c_update(l, msg_src, msg_len, lane, B.crc_adv);
         crc_be = crc32c_mask(l ^ 0xffffffffu);
     }
-    write_echo_prefix(out, lane, d.correlation_id, a.att_len, r_cks_type, cks_len, crc_be, frame + a.cks_off, a.msg_len, ml, vl, prefix);
+    write_echo_prefix(out, lane, d.correlation_id, a.att_len, r_cks_type, cks_len, crc_be, frame + a.cks_off, msg_len, ml, vl, prefix);
     // payload: message bytes (+ attachment when it directly follows them, the normal layout)
-    if (a.att_len && a.att_off == a.msg_off + a.msg_len) {
-        warp_copy(out + prefix, frame + a.msg_off, a.msg_len + a.att_len, lane);
+    if (a.att_len && d.compress_type == B2_COMPRESS_TYPE_NONE && a.att_off == a.msg_off + a.msg_len) {
+        warp_copy(out + prefix, msg_src, msg_len + a.att_len, lane);
     } else {
-        warp_copy(out + prefix, frame + a.msg_off, a.msg_len, lane);
-        if (a.att_len) warp_copy(out + prefix + a.msg_len, frame + a.att_off, a.att_len, lane);
+        warp_copy(out + prefix, msg_src, msg_len, lane);
+        if (a.att_len) warp_copy(out + prefix + msg_len, frame + a.att_off, a.att_len, lane);
     }
     if (lane == 0) { B.msgs[i].resp_off = slot_off + a.pad; B.msgs[i].resp_len = resp_len; }
 }

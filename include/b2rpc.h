@@ -262,6 +262,14 @@ int  b2_crc32c_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
                      const uint32_t* offs, const uint32_t* lens, uint32_t n,
                      uint32_t* out);
 
+/* b2_snappy_uncompress_batch: butil::snappy::Uncompress (src/butil/third_party/snappy/snappy.cc:1526-1552)
+ * on each (offset,length) slice of raw-format snappy.  Output i is written to out + out_offs[i]
+ * (out_offs is filled by the call, 16-byte aligned, in slice order) and out_lens[i] is its length,
+ * or -1 when the reference would return false (malformed stream / length mismatch). */
+int  b2_snappy_uncompress_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
+                                const uint32_t* offs, const uint32_t* lens, uint32_t n,
+                                void* out, uint32_t out_cap, uint32_t* out_offs, int32_t* out_lens);
+
 /* ---- counters (bvar::Adder-like): per-GPU totals accumulated by
  * the kernels: [0] in_bytes [1] in_msgs [2] out_bytes [3] out_msgs [4] errors
  * [5] batches [6..7] reserved.  The cross-GPU reduce is an NCCL all-reduce on
