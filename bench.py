@@ -89,7 +89,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_batch(run_mib, rank, pinned=True):
+def build_batch(run_mib, rank, pinned=True, payload=PAYLOAD, checksum=0, kind=0):
     from brpc_b200 import press
     from brpc_b200.abi import PinnedBuffer
     run_bytes = (run_mib << 20) - 16 * 7          # not a multiple of the frame: every run ends mid-frame
@@ -97,7 +97,7 @@ def build_batch(run_mib, rank, pinned=True):
     nbytes = N_SOCKETS * stride
     buf = PinnedBuffer(nbytes) if pinned else None
     data = buf.array if pinned else np.zeros(nbytes, np.uint8)
-    sp = press.spec(payload_bytes=PAYLOAD, payload_kind=0)
+    sp = press.spec(payload_bytes=payload, payload_kind=kind, checksum_type=checksum)
     # sockets are sharded over GPUs by socket id: rank r serves ids r*64 .. r*64+63
     runs, n_full = press.fill_batch(sp, data, N_SOCKETS, run_bytes, start_index=rank * 1000003)
     runs["socket_id"] += rank * N_SOCKETS
@@ -151,6 +151,10 @@ def main():
     ap.add_argument("--run-mib", type=int, default=4, help="MiB pending per connection per batch")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--payload", type=int, default=1024, help="EchoRequest.message bytes (rpc_press sweep: 64..65536)")
+    ap.add_argument("--checksum", type=int, default=0, help="1 = CRC32C on requests (-enable_checksum)")
+    ap.add_argument("--payload-kind", type=int, default=0, help="0 = 'r' fill, 1 = random over 62 symbols")
+    ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--pipeline", type=int, default=2, help="resident batches in flight per GPU (one ctx + stream each)")
     args = ap.parse_args()
     steps, warmup = max(1, args.steps), max(3, args.warmup)
@@ -158,9 +162,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     hbm_peak, peak_src = read_peaks()
     ncores = os.cpu_count() or 1
-    workload = ("multi_threaded_echo_c++ baidu_std 1 KB: %d connections/GPU x %d MiB pending, 'r' payload, "
-                "runs cut mid-frame; batch %d MiB > L2 (no flush needed)" % (N_SOCKETS, args.run_mib, N_SOCKETS * args.run_mib))
-    config = {"workload": workload, "payload_bytes": PAYLOAD, "connections_per_gpu": N_SOCKETS,
+    workload = ("multi_threaded_echo_c++ baidu_std %d B payload: %d connections/GPU x %d MiB pending, "
+                "runs cut mid-frame; batch %d MiB > L2 (no flush needed)" % (args.payload, N_SOCKETS, args.run_mib, N_SOCKETS * args.run_mib))
+    config = {"workload": workload, "payload_bytes": args.payload, "request_checksum": args.checksum, "connections_per_gpu": N_SOCKETS,
               "run_mib": args.run_mib, "l2": "inputs larger than L2", "pipeline_depth": args.pipeline, "sharding": "socket_id %% %d" % max(1, world)}
 
     if args.impl == "reference":
@@ -193,9 +197,9 @@ def main():
     dev = local_rank if use_dist else 0
     torch.cuda.set_device(dev)
 
-    buf, data, runs, n_full, nbytes = build_batch(args.run_mib, rank)
+    buf, data, runs, n_full, nbytes = build_batch(args.run_mib, rank, payload=args.payload, checksum=args.checksum, kind=args.payload_kind)
     ctx = brpc_b200.Context(device=dev, max_batch_bytes=nbytes + (1 << 20), max_msgs=n_full + 4096,
-                            max_runs=N_SOCKETS, tile_bytes=args.tile)
+                            max_runs=N_SOCKETS, tile_bytes=args.tile, max_resp_bytes=nbytes + 96 * n_full + (4 << 20))
 
     def barrier():
         if use_dist:
@@ -216,7 +220,8 @@ def main():
     # them so the latency-bound scan/decode stages of one step overlap the TMA pack of another.
     depth = max(1, args.pipeline)
     ctxs = [ctx] + [brpc_b200.Context(device=dev, max_batch_bytes=nbytes + (1 << 20), max_msgs=n_full + 4096,
-                                      max_runs=N_SOCKETS, tile_bytes=args.tile) for _ in range(depth - 1)]
+                                      max_runs=N_SOCKETS, tile_bytes=args.tile, max_resp_bytes=nbytes + 96 * n_full + (4 << 20))
+                    for _ in range(depth - 1)]
     for cx in ctxs:
         cx.upload_ptr(buf.ptr, nbytes, runs)
     for s_ in range(warmup * depth):
@@ -253,7 +258,7 @@ def main():
     e2e_depth = 3
     while len(ctxs) < e2e_depth:
         ctxs.append(brpc_b200.Context(device=dev, max_batch_bytes=nbytes + (1 << 20), max_msgs=n_full + 4096,
-                                      max_runs=N_SOCKETS, tile_bytes=args.tile))
+                                      max_runs=N_SOCKETS, tile_bytes=args.tile, max_resp_bytes=nbytes + 96 * n_full + (4 << 20)))
     e2e_steps = max(6, min(steps, 30))
     for cx in ctxs[:e2e_depth]:
         cx.submit_ptr(buf.ptr, nbytes, runs)
@@ -281,6 +286,8 @@ def main():
     from brpc_b200.abi import PinnedBuffer as _Pinned
     lat_ctx = brpc_b200.Context(device=dev, max_batch_bytes=1 << 20, max_msgs=4096, max_runs=N_SOCKETS, tile_bytes=args.tile)
     _sp = _press.spec(payload_bytes=PAYLOAD)
+    if args.no_latency:
+        pass
     _f = _press.frame(_sp, 12345)
     _stride = (len(_f) + 15) // 16 * 16
     lbuf = _Pinned(N_SOCKETS * _stride)
@@ -322,7 +329,7 @@ def main():
     if rank == 0:
         # roofline of the dominant kernel, from THIS rank's stage times
         dom = max(stages, key=stages.get)
-        pack_alg = float(int(msgs["resp_len"].sum()) + len(msgs) * (PAYLOAD + DESC_BYTES))   # resp written + payload & desc read
+        pack_alg = float(int(msgs["resp_len"].sum()) + len(msgs) * (args.payload + DESC_BYTES))   # resp written + payload & desc read
         alg = {"pack": pack_alg}
         dom_alg = alg.get(dom, float(req_bytes + resp_frame_bytes + DESC_BYTES * len(msgs)))
         achieved = dom_alg / (stages[dom] * 1e-3) / 1e9

@@ -51,7 +51,8 @@ struct b2_ctx {
     int n_stages = 0;
     float last_kernel_ms = 0.f; uint32_t last_launches = 0;
     cudaEvent_t ev_first = nullptr, ev_last = nullptr; bool first_pending = true;
-    bool profile_stages = false; bool allow_small = true;      // per-stage events only when a harness asks for stage times
+    bool profile_stages = false; bool allow_small = true;
+    bool adaptive_tile = false; uint32_t avg_frame = 0;   // tile size follows the message size of the previous batch      // per-stage events only when a harness asks for stage times
     // small-batch (latency) mode: one compact H2D block, one compact output block, one D2H, one sync
     uint8_t* d_meta = nullptr; uint8_t* h_meta = nullptr;       // [runs | run_tile_base]
     uint8_t* d_small = nullptr; uint8_t* h_small = nullptr;     // [totals | run_status | msgs | resp]
@@ -105,6 +106,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     { int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, o->device); c->n_sms = (uint32_t)v; }
     for (int i = 0; i <= kMaxStages; i++) c->ev[i] = nullptr;
     c->opt = *o;
+    c->adaptive_tile = o->tile_bytes == 0;
     uint32_t tile = o->tile_bytes ? o->tile_bytes : 8192;
     if (tile < 512 || (tile & (tile - 1))) { delete c; set_err("tile_bytes must be a power of two >= 512"); return B2_E_INVAL; }
     c->opt.tile_bytes = tile;
@@ -230,6 +232,13 @@ extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, co
     if (!c || (!bytes && nbytes) || (!runs && n_runs)) { set_err("null argument"); return B2_E_INVAL; }
     if (nbytes > c->opt.max_batch_bytes || n_runs > c->opt.max_runs) { set_err("batch exceeds ctx capacity"); return B2_E_CAPACITY; }
     CU(cudaSetDevice(c->opt.device));
+    if (c->adaptive_tile) {
+        // like Socket::_avg_msg_size steering the read size (input_messenger.cpp:348-353): a tile should hold
+        // ~8 messages so the speculative entry search reads a small fraction of it
+        uint32_t t = 8192;
+        while (t < (1u << 20) && t < 8u * c->avg_frame) t <<= 1;
+        c->cfg.tile_bytes = t; c->cfg.tile_shift = 0; while ((1u << c->cfg.tile_shift) < t) c->cfg.tile_shift++;
+    }
     const uint32_t shift = c->cfg.tile_shift, tile = c->cfg.tile_bytes;
     uint64_t nt = 0; uint32_t max_rt = 0;
     for (uint32_t r = 0; r < n_runs; r++) {
@@ -286,9 +295,10 @@ static int launch_pipeline(b2_ctx* c) {
     k_decode<<<sms * B2_DECODE_MIN_BLOCKS, kDecodeWarps * 32, 0, s>>>(B, C); launches++; mark("decode");
     k_scan_blocks<<<sms, kScanBlock, 0, s>>>(B); launches++;
     k_scan_top<<<1, 1024, 0, s>>>(B); launches++; mark("scan");
-    if (c->use_tma_pack) k_pack_tma<<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C);
-    else k_pack<<<sms * B2_PACK_MIN_BLOCKS, 256, 0, s>>>(B, C);
-    launches++; mark("pack");
+    if (c->use_tma_pack) {
+        k_pack_tma<<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C); launches++; mark("pack");
+        k_pack_slow<<<sms * B2_PACK_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack_slow");
+    } else { k_pack<<<sms * B2_PACK_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack"); }
     k_finalize<<<(c->n_runs + 255) / 256, 256, 0, s>>>(B); launches++; mark("finalize");
     if (!prof) { c->stage_names[0] = "pipeline"; cudaEventRecord(c->ev[1], s); st = 1; }
     c->n_stages = st; c->last_launches = launches;
@@ -402,6 +412,7 @@ extern "C" int b2_batch_download(b2_ctx* c, b2_batch_result* out) {
         int rc = download_normal(c, out);
         if (rc != B2_OK) return rc;
     }
+    if (out->n_msgs) c->avg_frame = (uint32_t)(((uint64_t)c->avg_frame * 3 + c->nbytes / out->n_msgs) / 4);
     out->kernel_ms = c->last_kernel_ms; out->n_launches = c->last_launches;
     return B2_OK;
 }

@@ -153,36 +153,46 @@ __global__ void __launch_bounds__(256) k_tile_search(BatchPtrs B, DevConfig C) {
     } else {
         const uint32_t t0 = k << C.tile_shift;
         const uint32_t t1 = min(t0 + C.tile_bytes, len);
-        for (uint32_t c0 = t0; c0 < t1 && entry == kNone; c0 += 512) {
-            // lane owns 16 positions [p0, p0+16); needs 3 more bytes for the last windows
-            const uint32_t p0 = c0 + lane * 16;
-            uint4 v = make_uint4(0, 0, 0, 0); uint32_t nx = 0;
-            if (p0 < t1) {
-                v = __ldg(reinterpret_cast<const uint4*>(base + p0));        // bytes buffer is padded: safe past len
-                nx = __ldg(reinterpret_cast<const uint32_t*>(base + p0 + 16));
-            }
-            const uint32_t w[5] = { v.x, v.y, v.z, v.w, nx };
-            uint32_t mask = 0;
+        // four 512-byte windows per trip: all eight loads of a lane are issued before the first use
+        for (uint32_t c0 = t0; c0 < t1 && entry == kNone; c0 += 2048) {
+            uint4 v[4]; uint32_t nx[4];
             #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const uint32_t word = __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], (j & 3) * 8);
-                if (is_magic(word) && p0 + j + 4 <= len && p0 + j < t1) mask |= 1u << j;
-            }
-            // candidates in position order: lanes ascending, bits ascending
-            uint32_t any = __ballot_sync(0xffffffffu, mask != 0);
-            while (any && entry == kNone) {
-                const int src = __ffs(any) - 1;
-                uint32_t m = __shfl_sync(0xffffffffu, mask, src);
-                while (m && entry == kNone) {
-                    const uint32_t p = c0 + src * 16 + (__ffs(m) - 1);
-                    m &= m - 1;
-                    const Step s = cut_input_message(base, len, p, -1, C.max_body_size);   // uniform across lanes
-                    if (s.err == B2_PARSE_OK && !s.popped) {
-                        const uint32_t q = s.new_pos;
-                        if (q + 4 > len || is_magic(load_le32(base + q))) entry = p;
-                    }
+            for (int u = 0; u < 4; u++) {
+                const uint32_t p0 = c0 + u * 512 + lane * 16;
+                v[u] = make_uint4(0, 0, 0, 0); nx[u] = 0;
+                if (p0 < t1) {
+                    v[u] = __ldg(reinterpret_cast<const uint4*>(base + p0));        // bytes buffer is padded: safe past len
+                    nx[u] = __ldg(reinterpret_cast<const uint32_t*>(base + p0 + 16));
                 }
-                any &= any - 1;
+            }
+            #pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (entry != kNone) break;
+                // lane owns 16 positions [p0, p0+16); needs 3 more bytes for the last windows
+                const uint32_t w0 = c0 + u * 512, p0 = w0 + lane * 16;
+                const uint32_t w[5] = { v[u].x, v[u].y, v[u].z, v[u].w, nx[u] };
+                uint32_t mask = 0;
+                #pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const uint32_t word = __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], (j & 3) * 8);
+                    if (is_magic(word) && p0 + j + 4 <= len && p0 + j < t1) mask |= 1u << j;
+                }
+                // candidates in position order: lanes ascending, bits ascending
+                uint32_t any = __ballot_sync(0xffffffffu, mask != 0);
+                while (any && entry == kNone) {
+                    const int src = __ffs(any) - 1;
+                    uint32_t m = __shfl_sync(0xffffffffu, mask, src);
+                    while (m && entry == kNone) {
+                        const uint32_t p = w0 + src * 16 + (__ffs(m) - 1);
+                        m &= m - 1;
+                        const Step s = cut_input_message(base, len, p, -1, C.max_body_size);   // uniform across lanes
+                        if (s.err == B2_PARSE_OK && !s.popped) {
+                            const uint32_t q = s.new_pos;
+                            if (q + 4 > len || is_magic(load_le32(base + q))) entry = p;
+                        }
+                    }
+                    any &= any - 1;
+                }
             }
         }
     }
@@ -480,7 +490,10 @@ __global__ void __launch_bounds__(kDecodeWarps * 32, B2_DECODE_MIN_BLOCKS) k_dec
                 S.row[m][sub] = __ldg(reinterpret_cast<const uint4*>(B.bytes + (f & ~15u)) + sub);   // (buffer is padded past its end)
         }
         __syncwarp();
-        if (i < n_msgs) decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 15u), S.head[lane]);
+        bool is_slow = false;
+        if (i < n_msgs) { decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 15u), S.head[lane]); is_slow = B.jobs[i].fast == 0; }
+        const uint32_t n_slow = __popc(__ballot_sync(0xffffffffu, is_slow));
+        if (lane == 0 && n_slow) atomicAdd(B.totals + 3, n_slow);          // k_pack_slow returns at once when this stays 0
         __syncwarp();
         // heads of 32 consecutive messages are contiguous: coalesced 16-byte stores
         {
@@ -1101,46 +1114,95 @@ __global__ void __launch_bounds__(kPackWarps * 32, 1) k_pack_tma(BatchPtrs B, De
             so = B.slot[i] + B.scan_tmp[i / (kScanBlock * kScanItems)];
         }
     };
+    // one staging round: arm the buffer's mbarrier, run `issue` (bulk loads), wait for the bytes
+    auto begin_round = [&](uint32_t b) { bulk_wait_read<1>(); __syncwarp(); };   // stores that last read buffer b drained
+    auto wait_round = [&](uint32_t b) { mbar_wait(&S.mbar[b], (b ? phase1 : phase0) & 1u); if (b) phase1++; else phase0++; };
     if (base < n_msgs) fetch(base, job, slot_off);
-    for (; base < n_msgs; base += stride, it++) {
-        const uint32_t nm = min(kPackGroup, n_msgs - base);
-        const uint32_t b = it & 1;
-        uint8_t* stage = S.stage[b];
-        // software pipeline: request the next round's jobs now, use them next iteration
+    for (; base < n_msgs; base += stride) {
+        // software pipeline: request the next group's jobs now, use them next iteration
         PackJob njob; uint32_t nslot = 0;
         njob.fast = 0; njob.slot_len = 0; njob.head_len = 0; njob.bulk_len = 0; njob.src_off = 0; njob.pad = 0;
         if (base + stride < n_msgs) fetch(base + stride, njob, nslot);
-        // staging layout: inclusive scan of the slot lengths of this round's TMA messages
-        uint32_t need = job.fast ? job.slot_len : 0, incl = need;
-        #pragma unroll
-        for (int d = 1; d < (int)kPackGroup; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += y; }
-        const bool take = job.fast && incl <= kStageBytes;
-        const uint32_t soff = incl - need;
-        uint32_t tx = take ? (uint32_t)job.head_len + job.bulk_len : 0;
-        #pragma unroll
-        for (int d = 1; d < (int)kPackGroup; d <<= 1) tx += __shfl_xor_sync(0xffffffffu, tx, d);
-        tx = __shfl_sync(0xffffffffu, tx, 0);
-        // the bulk stores that last read this staging buffer (two rounds ago) must have drained it
-        bulk_wait_read<1>();
-        __syncwarp();
-        if (lane == 0 && tx) mbar_arrive_expect_tx(&S.mbar[b], tx);
-        __syncwarp();
-        if (take) {
-            bulk_g2s(stage + soff, B.heads + (size_t)(base + lane) * kHeadBytes, job.head_len, &S.mbar[b]);
-            if (job.bulk_len) bulk_g2s(stage + soff + job.head_len, B.bytes + job.src_off, job.bulk_len, &S.mbar[b]);
+        uint32_t pending = __ballot_sync(0xffffffffu, job.fast != 0);      // (jobs that are not fast belong to k_pack_slow)
+        while (pending) {
+            const uint32_t b = it & 1; it++;
+            uint8_t* stage = S.stage[b];
+            const uint32_t first = __ffs(pending) - 1;
+            const uint32_t first_len = __shfl_sync(0xffffffffu, job.slot_len, first);
+            if (first_len > kStageBytes) {
+                // ---- a reply larger than a staging buffer: the warp streams it in chunks.  The slot image is
+                // [head record | payload bulk]; chunk boundaries are multiples of 16, so every piece is a legal
+                // bulk copy.  Lane 0 drives; two buffers alternate so a chunk's store overlaps the next load.
+                const uint32_t hl = __shfl_sync(0xffffffffu, (uint32_t)job.head_len, first);
+                const uint32_t so = __shfl_sync(0xffffffffu, slot_off, first);
+                const uint32_t src = __shfl_sync(0xffffffffu, job.src_off, first);
+                const uint32_t pad = __shfl_sync(0xffffffffu, (uint32_t)job.pad, first);
+                const uint8_t* head = B.heads + (size_t)(base + first) * kHeadBytes;
+                uint32_t bb = b;
+                for (uint32_t c0 = 0; c0 < first_len; c0 += kStageBytes) {
+                    const uint32_t c1 = min(c0 + kStageBytes, first_len);
+                    if (c0) { bb = it & 1; it++; }
+                    uint8_t* st = S.stage[bb];
+                    begin_round(bb);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&S.mbar[bb], c1 - c0);
+                        uint32_t at = c0;
+                        if (at < hl) { const uint32_t e = min(hl, c1); bulk_g2s(st, head + at, e - at, &S.mbar[bb]); at = e; }
+                        if (at < c1) bulk_g2s(st + (at - c0), B.bytes + src + (at - hl), c1 - at, &S.mbar[bb]);
+                    }
+                    wait_round(bb);
+                    if (lane == 0) bulk_s2g(B.resp + so + c0, st, c1 - c0);
+                    bulk_commit();
+                }
+                if (lane == 0) B.msgs[base + first].resp_off = so + pad;
+                pending &= ~(1u << first);
+                continue;
+            }
+            // ---- staging layout: the pending jobs, in lane order, as long as they fit the buffer
+            const bool mine = (pending >> lane) & 1u;
+            uint32_t need = mine ? job.slot_len : 0, incl = need;
+            #pragma unroll
+            for (int d = 1; d < (int)kPackGroup; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += y; }
+            const bool take = mine && incl <= kStageBytes;
+            const uint32_t soff = incl - need;
+            uint32_t tx = take ? (uint32_t)job.head_len + job.bulk_len : 0;
+            #pragma unroll
+            for (int d = 1; d < (int)kPackGroup; d <<= 1) tx += __shfl_xor_sync(0xffffffffu, tx, d);
+            tx = __shfl_sync(0xffffffffu, tx, 0);
+            begin_round(b);
+            if (lane == 0) mbar_arrive_expect_tx(&S.mbar[b], tx);
+            __syncwarp();
+            if (take) {
+                bulk_g2s(stage + soff, B.heads + (size_t)(base + lane) * kHeadBytes, job.head_len, &S.mbar[b]);
+                if (job.bulk_len) bulk_g2s(stage + soff + job.head_len, B.bytes + job.src_off, job.bulk_len, &S.mbar[b]);
+            }
+            wait_round(b);
+            if (take) {
+                bulk_s2g(B.resp + slot_off, stage + soff, job.slot_len);
+                B.msgs[base + lane].resp_off = slot_off + job.pad;
+            }
+            bulk_commit();
+            pending &= ~__ballot_sync(0xffffffffu, take);
         }
-        if (tx) { mbar_wait(&S.mbar[b], (b ? phase1 : phase0) & 1u); if (b) phase1++; else phase0++; }
-        if (take) {
-            bulk_s2g(B.resp + slot_off, stage + soff, job.slot_len);
-            B.msgs[base + lane].resp_off = slot_off + job.pad;
-        }
-        bulk_commit();
-        // everything that is not a plain OK echo (or did not fit the staging buffer): register path
-        const uint32_t slow = __ballot_sync(0xffffffffu, lane < nm && !take);
-        for (uint32_t m = slow; m; m &= m - 1) pack_one(B, C, base + (__ffs(m) - 1), lane);
         job = njob; slot_off = nslot;
     }
     bulk_wait<0>();
+}
+
+// --- k_pack_slow: everything that is not a plain OK echo ----------------------
+// error replies, CRC32C verify/compute, snappy requests, split attachments: warp per message,
+// high occupancy (these are latency-bound), skipping the messages k_pack_tma moves.
+__global__ void __launch_bounds__(256, B2_PACK_MIN_BLOCKS) k_pack_slow(BatchPtrs B, DevConfig C) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n_msgs = B.totals[0];
+    if ((B.totals[2] & 3u) || B.totals[3] == 0) return;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; i0 < n_msgs; i0 += n_warps * 32) {
+        // one coalesced look at 32 job flags, then the warp serves the slow ones in turn
+        const uint32_t i = i0 + lane;
+        const bool slow = i < n_msgs && reinterpret_cast<const uint8_t*>(B.jobs + i)[11] == 0;   // PackJob::fast
+        for (uint32_t m = __ballot_sync(0xffffffffu, slow); m; m &= m - 1) pack_one(B, C, i0 + (__ffs(m) - 1), lane);
+    }
 }
 
 // --- k_finalize: per-run response span + counters ----------------------------
