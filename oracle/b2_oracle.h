@@ -11,7 +11,7 @@
  * test/crc32c_unittest.cc:18-71 and against the reference's own crc32c.cc
  * compiled into oracle/_ref; the protobuf wire codec (libprotobuf is a
  * third-party dependency absent from /root/reference, pinned 27.3 in
- * MODULE.bazel:11) is pinned by tests/golden/*.json generated with
+ * MODULE.bazel:11) is pinned by tests/golden/ (json) generated with
  * python-protobuf from the reference's .proto files (tests/golden/gen_golden.py).
  * The reference's tests hold NO golden baidu_std wire bytes, so
  * frame-level parity is pinned by those fixtures, not by reference test vectors.

@@ -1,0 +1,150 @@
+// C++ tests of the host side (brpc_b200/host).  `host_test cpu` needs no GPU: b2::IOBuf behaves like
+// the slice of butil::IOBuf the path uses (cases modelled on test/iobuf_unittest.cpp: block geometry
+// :60-61, append/cut/pop, zero-copy sharing, user data :1593-1723, the counting allocator installed
+// through blockmem_allocate/deallocate :40-100).  `host_test gpu` drives GpuInputMessenger end to end
+// and checks every response byte against the oracle (tests may link the oracle).
+#include <assert.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../brpc_b200/host/input_messenger.h"
+#include "../../oracle/b2_oracle.h"
+
+#define CHECK(c) do { if (!(c)) { fprintf(stderr, "CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #c); exit(1); } } while (0)
+
+extern "C" {
+typedef struct b2press_spec { const char* service; const char* method; uint32_t payload_bytes, attachment_bytes; int32_t payload_kind, checksum_type; uint64_t seed; } b2press_spec;
+size_t b2press_frame(const b2press_spec* s, uint64_t index, uint8_t* out, size_t cap);
+}
+
+static int g_live_blocks = 0, g_total_allocs = 0;
+static void* counting_alloc(size_t n) { g_live_blocks++; g_total_allocs++; return malloc(n); }
+static void counting_free(void* p) { g_live_blocks--; free(p); }
+
+static void test_iobuf() {
+    using b2::IOBuf;
+    b2::iobuf::blockmem_allocate = counting_alloc; b2::iobuf::blockmem_deallocate = counting_free;
+    {
+        IOBuf b;
+        CHECK(b.empty() && b.length() == 0 && b.backing_block_num() == 0);
+        std::string s(20000, 'x'); for (size_t i = 0; i < s.size(); i++) s[i] = (char)('a' + i % 26);
+        CHECK(b.append(s) == 0);
+        CHECK(b.length() == 20000 && b.backing_block_num() == 3);               // 8160 + 8160 + 3680
+        CHECK(b.backing_block(0).second == IOBuf::DEFAULT_PAYLOAD && IOBuf::DEFAULT_PAYLOAD == 8192 - 32);
+        CHECK(b.backing_block(2).second == 20000 - 2 * 8160 && b.backing_block(3).first == nullptr);
+        CHECK(b.to_string() == s);
+        char hdr[12]; CHECK(b.copy_to(hdr, 12) == 12 && memcmp(hdr, s.data(), 12) == 0);
+        CHECK(b.copy_to(hdr, 12, 8155) == 12 && memcmp(hdr, s.data() + 8155, 12) == 0);   // spans two blocks
+        CHECK(b.copy_to(hdr, 12, 19995) == 5 && b.copy_to(hdr, 1, 20000) == 0);
+        char aux[16]; CHECK(b.fetch(aux, 8) == b.backing_block(0).first);          // contiguous: no copy
+        IOBuf head; CHECK(b.cutn(&head, 8150) == 8150);
+        CHECK(b.fetch(aux, 16) == aux && memcmp(aux, s.data() + 8150, 16) == 0);   // straddles: copied
+        IOBuf meta, payload;                                                        // ParseRpcMessage's two cutn
+        CHECK(b.cutn(&meta, 46) == 46 && b.cutn(&payload, 1027) == 1027);
+        CHECK(meta.to_string() == s.substr(8150, 46) && payload.to_string() == s.substr(8196, 1027));
+        CHECK(meta.backing_block_num() == 2 && payload.backing_block_num() == 1);
+        CHECK(payload.block_nshared(0) >= 3);                                       // shared, not copied
+        CHECK(b.length() == 20000 - 8150 - 46 - 1027);
+        CHECK(b.pop_front(100) == 100 && b.pop_back(50) == 50 && b.to_string() == s.substr(8150 + 46 + 1027 + 100, b.length()));
+        CHECK(b.pop_front(1 << 30) == 20000 - 8150 - 46 - 1027 - 150 && b.empty());
+        IOBuf all; all.append(head); all.append(meta.movable()); all.append(payload);
+        CHECK(meta.empty() && all.length() == 8150 + 46 + 1027 && all.to_string() == s.substr(0, all.length()));
+        CHECK(all.backing_block_num() == 2);                                        // adjacent refs of one block merge
+        IOBuf copy(all); std::string t; CHECK(copy.cutn(&t, 5) == 5 && t == s.substr(0, 5) && all.length() == 9223);
+        char c; CHECK(copy.cut1(&c) && c == s[5]);
+        IOBuf mv(all.movable()); CHECK(all.empty() && mv.length() == 9223);
+        swap(all, mv); CHECK(mv.empty() && all.length() == 9223);
+        // user data: referenced, not copied; deleter runs when the last reference goes away
+        static int deleted = 0; static char user[64] = "user-owned-bytes";
+        { IOBuf u; CHECK(u.append_user_data(user, 16, [](void* p) { deleted += (p == user); }) == 0);
+          IOBuf u2(u); CHECK(u.backing_block(0).first == user && u2.to_string() == "user-owned-bytes");
+          u.clear(); CHECK(deleted == 0); }
+        CHECK(deleted == 1);
+        // appending small pieces fills the tail block instead of allocating
+        IOBuf small; const int before = g_total_allocs;
+        for (int i = 0; i < 1000; i++) small.append("12345678", 8);
+        CHECK(small.length() == 8000 && g_total_allocs == before + 1 && small.backing_block_num() == 1);
+    }
+    CHECK(g_live_blocks == 0);                                                      // every block went back (iobuf_unittest.cpp:94-100)
+    b2::iobuf::blockmem_allocate = b2::iobuf::default_alloc; b2::iobuf::blockmem_deallocate = b2::iobuf::default_free;
+    printf("iobuf ok (%d blocks allocated and freed)\n", g_total_allocs);
+}
+
+static int g_host_msgs = 0;
+static void HostProcess(b2::InputMessageBase* base) {
+    b2::MostCommonMessage* m = static_cast<b2::MostCommonMessage*>(base);
+    CHECK(m->meta.length() == m->desc.meta_size && m->payload.length() == m->desc.body_size - m->desc.meta_size);
+    g_host_msgs++;
+    delete m;
+}
+
+static void test_messenger_gpu() {
+    // pinned IOBuf blocks, as a brpc integration would install them
+    b2::iobuf::blockmem_allocate = b2_block_alloc; b2::iobuf::blockmem_deallocate = b2_block_free;
+    b2_options opt; memset(&opt, 0, sizeof opt);
+    opt.device = 0; opt.max_batch_bytes = 8 << 20; opt.max_msgs = 1 << 16; opt.max_runs = 256;
+    b2::GpuInputMessenger messenger(opt);
+    b2_method echo = { "example.EchoService", "EchoService", "Echo", "example.EchoRequest", B2_HANDLER_ECHO, 1, 0, 0 };
+    b2_method other = { "example.Other", "Other", "Call", "example.OtherRequest", B2_HANDLER_HOST, 0, 0, 0 };
+    CHECK(messenger.AddMethod(echo) == 0 && messenger.AddMethod(other) == 1);
+    messenger.SetHostProcess(HostProcess);
+
+    const int kSockets = 16, kFrames = 40;
+    std::vector<std::string> streams(kSockets);
+    std::vector<uint8_t> f(1 << 17);
+    for (int s = 0; s < kSockets; s++)
+        for (int i = 0; i < kFrames; i++) {
+            b2press_spec sp = { (s == 3 && i % 5 == 0) ? "example.Other" : "example.EchoService", (s == 3 && i % 5 == 0) ? "Call" : "Echo",
+                                (uint32_t)(16 << (i % 9)), (uint32_t)(i % 3 == 0 ? 21 : 0), i % 2, i % 4 == 1, 20260921 };
+            const size_t n = b2press_frame(&sp, ((uint64_t)s << 32) + i, f.data(), f.size());
+            CHECK(n > 0);
+            streams[s].append((const char*)f.data(), n);
+        }
+    streams[7][5000] ^= 0x40;   // corruption somewhere in socket 7's stream
+    // feed in uneven chunks over several rounds, like reads that stop mid-frame
+    std::vector<b2::Socket*> socks; std::vector<size_t> pos(kSockets, 0);
+    for (int s = 0; s < kSockets; s++) socks.push_back(messenger.AddSocket(1000 + s));
+    unsigned seed = 12345; int rounds = 0, total_msgs = 0;
+    for (bool more = true; more; rounds++) {
+        more = false;
+        for (int s = 0; s < kSockets; s++) {
+            seed = seed * 1103515245u + 12345u;
+            const size_t n = std::min(streams[s].size() - pos[s], (size_t)(seed >> 16) % 9000);
+            socks[s]->_read_buf.append(streams[s].data() + pos[s], n); pos[s] += n;
+            if (pos[s] < streams[s].size()) more = true;
+        }
+        const int n = messenger.ProcessNewMessages(socks);
+        CHECK(n >= 0); total_msgs += n;
+    }
+    // expectation: the oracle over each whole stream
+    orc_config cfg; memset(&cfg, 0, sizeof cfg);
+    b2_method ms[2] = { echo, other }; cfg.methods = ms; cfg.n_methods = 2;
+    int checked = 0;
+    for (int s = 0; s < kSockets; s++) {
+        b2_run run = { 0, 0, (uint32_t)streams[s].size(), -1, 0 };
+        b2_run_status rs; std::vector<b2_msg_desc> msgs(4096); std::vector<uint8_t> resp(streams[s].size() * 2 + (1 << 16));
+        uint32_t nm = 0, rb = 0;
+        CHECK(orc_process_batch(&cfg, (const uint8_t*)streams[s].data(), run.length, &run, 1, &rs, msgs.data(), 4096, &nm,
+                                resp.data(), (uint32_t)resp.size(), &rb) == 0);
+        if (rs.parse_error != B2_PARSE_ERROR_NOT_ENOUGH_DATA) {         // corrupted stream: the socket must be closed
+            CHECK(socks[s]->Failed());
+            continue;
+        }
+        CHECK(!socks[s]->Failed() && socks[s]->in_msgs() == nm && socks[s]->_read_buf.length() == streams[s].size() - rs.consumed);
+        CHECK(socks[s]->_write_buf.length() == rb);
+        CHECK(socks[s]->_write_buf.to_string() == std::string((const char*)resp.data(), rb));
+        checked++;
+    }
+    CHECK(checked >= kSockets - 2 && g_host_msgs == 8);
+    printf("messenger ok: %d sockets, %d messages in %d rounds, %d streams byte-identical to the oracle, %d host-handled\n",
+           kSockets, total_msgs, rounds, checked, g_host_msgs);
+}
+
+int main(int argc, char** argv) {
+    const std::string mode = argc > 1 ? argv[1] : "cpu";
+    test_iobuf();
+    if (mode == "gpu") test_messenger_gpu();
+    return 0;
+}

@@ -1,0 +1,41 @@
+"""The C++ host side (brpc_b200/host: b2::IOBuf, b2::GpuInputMessenger) — builds tests/cpp/host_test
+with g++ and runs it: `cpu` (IOBuf contract, allocator hook; no GPU) and `gpu` (messenger end to end,
+responses byte-identical to the oracle)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "host_test")
+
+
+def _build():
+    src = os.path.join(ROOT, "tests", "cpp", "host_test.cc")
+    deps = [src, os.path.join(ROOT, "brpc_b200", "host", "iobuf.h"), os.path.join(ROOT, "brpc_b200", "host", "input_messenger.h")]
+    if os.path.exists(BIN) and all(os.path.getmtime(BIN) >= os.path.getmtime(d) for d in deps):
+        return
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-Wall", "-o", BIN, src,
+                           "-L" + os.path.join(ROOT, "brpc_b200"), "-lb2rpc",
+                           "-L" + os.path.join(ROOT, "brpc_b200", "tools"), "-lb2press",
+                           "-L" + os.path.join(ROOT, "oracle"), "-loracle",
+                           "-Wl,-rpath," + os.path.join(ROOT, "brpc_b200"),
+                           "-Wl,-rpath," + os.path.join(ROOT, "brpc_b200", "tools"),
+                           "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
+
+
+def test_iobuf_contract_cpp():
+    import brpc_b200.press  # noqa: F401  (builds libb2press.so if missing)
+    _build()
+    out = subprocess.run([BIN, "cpu"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "iobuf ok" in out.stdout
+
+
+@pytest.mark.gpu
+def test_gpu_input_messenger_cpp():
+    import brpc_b200.press  # noqa: F401
+    _build()
+    out = subprocess.run([BIN, "gpu"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "messenger ok" in out.stdout
