@@ -10,7 +10,7 @@ lib_path = os.path.join(_HERE, "libb2rpc.so")
 B2_OK, B2_E_INVAL, B2_E_NO_DEVICE, B2_E_CUDA, B2_E_CAPACITY, B2_E_NOMEM = 0, -1, -2, -3, -4, -5
 
 RUN_DT = np.dtype([("socket_id", "<u8"), ("offset", "<u4"), ("length", "<u4"),
-                   ("preferred_proto", "<i4"), ("reserved", "<u4")])
+                   ("preferred_proto", "<i4"), ("flags", "<u4")])
 RUN_STATUS_DT = np.dtype([("consumed", "<u4"), ("parse_error", "<u4"), ("n_msgs", "<u4"), ("first_msg", "<u4"),
                           ("preferred_proto", "<i4"), ("reserved0", "<u4"), ("resp_off", "<u4"), ("resp_bytes", "<u4")])
 MSG_DT = np.dtype([("run_idx", "<u4"), ("frame_off", "<u4"), ("body_size", "<u4"), ("meta_size", "<u4"),

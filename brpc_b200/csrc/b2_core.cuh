@@ -77,20 +77,28 @@ struct Step {
     bool popped;         // some handler popped bytes and answered TRY_OTHERS (pf-sensitive path)
 };
 
-B2_HD Step cut_input_message(const uint8_t* run, uint32_t len, uint32_t pos, int pf, uint64_t max_body) {
+B2_HD Step cut_input_message(const uint8_t* run, uint32_t len, uint32_t pos, int pf, uint64_t max_body, bool client = false) {
     Step s; s.err = B2_PARSE_ERROR_TRY_OTHERS; s.index = -1; s.pf = pf; s.frame_pos = pos; s.new_pos = pos;
     s.body = 0; s.meta = 0; s.popped = false;
     const int pref = pf;
     if (pref >= 1 && pref <= 2) {
-        Cut c = parse_prefixed(run + pos, len - pos, magic_of(pref), max_body);
-        if (c.err == B2_PARSE_OK || c.err == B2_PARSE_ERROR_NOT_ENOUGH_DATA) {
-            s.err = c.err; s.index = pref; s.pf = pref;
-            if (c.err == B2_PARSE_OK) { s.frame_pos = pos; s.new_pos = pos + c.pop; s.body = c.body; s.meta = c.meta; }
-            return s;
+        int cur = pref;
+        for (;;) {
+            Cut c = parse_prefixed(run + pos, len - pos, magic_of(cur), max_body);
+            if (c.err == B2_PARSE_OK || c.err == B2_PARSE_ERROR_NOT_ENOUGH_DATA) {
+                s.err = c.err; s.index = cur; s.pf = cur;
+                if (c.err == B2_PARSE_OK) { s.frame_pos = pos; s.new_pos = pos + c.pop; s.body = c.body; s.meta = c.meta; }
+                return s;
+            }
+            if (c.err != B2_PARSE_ERROR_TRY_OTHERS) { s.err = c.err; return s; }
+            if (c.pop) { pos += c.pop; s.popped = true; s.new_pos = pos; }
+            if (len - pos >= 4 && load_le32(run + pos) == 0x414d4452u /* "RDMA" */) { s.err = B2_PARSE_ERROR_TRY_OTHERS; return s; }
+            if (!client) break;
+            // client side (CreatedByConnect): baidu_std may fall to streaming_rpc and back, once;
+            // anything else is fixed by the channel's protocol (input_messenger.cpp:122-138)
+            if (cur == pref) { cur = 3 - pref; continue; }
+            s.err = B2_PARSE_ERROR_ABSOLUTELY_WRONG; return s;
         }
-        if (c.err != B2_PARSE_ERROR_TRY_OTHERS) { s.err = c.err; return s; }
-        if (c.pop) { pos += c.pop; s.popped = true; s.new_pos = pos; }
-        if (len - pos >= 4 && load_le32(run + pos) == 0x414d4452u /* "RDMA" */) { s.err = B2_PARSE_ERROR_TRY_OTHERS; return s; }
         s.pf = -1;
     }
     for (int i = 1; i <= 2; i++) {
@@ -203,6 +211,7 @@ struct RpcMetaOut {
     int64_t correlation_id, log_id;
     int32_t compress_type, attachment_size, checksum_type, content_type;
     Span service_name, method_name, checksum_value;   // offsets relative to the meta start
+    int32_t error_code;         // RpcResponseMeta.error_code (0 when absent)
 };
 
 B2_HD bool rd_span(Reader& r, const uint8_t* base, Span& s) {
@@ -222,7 +231,7 @@ B2_HD bool decode_rpc_meta(const uint8_t* p, uint32_t n, RpcMetaOut& o) {
     int kind = kTop;
     uint32_t req_bits = 0, chunk_bits = 0, ss_bits = 0;
     o.has = 0; o.correlation_id = 0; o.log_id = 0; o.compress_type = 0; o.attachment_size = 0;
-    o.checksum_type = 0; o.content_type = 0;
+    o.checksum_type = 0; o.content_type = 0; o.error_code = 0;
     o.service_name.off = o.service_name.len = 0; o.method_name = o.service_name; o.checksum_value = o.service_name;
     for (;;) {
         if (r.p >= r.end) {
@@ -281,7 +290,7 @@ B2_HD bool decode_rpc_meta(const uint8_t* p, uint32_t n, RpcMetaOut& o) {
                 else if (fn == 8) o.has |= B2_HAS_TIMEOUT_MS;
             }
         } else if (kind == kResponse) {
-            if (wt == 0 && fn == 1) { if (!rd_varint(r, v)) return false; handled = true; }
+            if (wt == 0 && fn == 1) { if (!rd_varint(r, v)) return false; handled = true; o.error_code = (int32_t)(uint32_t)v; }
             else if (wt == 2 && fn == 2) { if (!rd_span(r, p, sp)) return false; handled = true; }
         } else if (kind == kChunk) {
             if (wt == 0 && (fn == 1 || fn == 2)) { if (!rd_varint(r, v)) return false; handled = true; chunk_bits |= fn; }

@@ -110,12 +110,12 @@ struct BatchPtrs {
 // the tile is handed to the resolver (kAmbig).
 template <bool kSpec, typename Emit>
 B2_HD void walk_tile(const uint8_t* run, uint32_t len, uint32_t entry, int pf_in, uint32_t tile_end,
-                     uint64_t max_body, TileRec& t, Emit emit) {
+                     uint64_t max_body, bool client, TileRec& t, Emit emit) {
     uint32_t pos = entry, count = 0;
     int pf = kSpec ? -1 : pf_in, last = 0;
     uint8_t kind = kRanOff;
     while (pos < tile_end) {
-        const Step s = cut_input_message(run, len, pos, pf, max_body);
+        const Step s = cut_input_message(run, len, pos, pf, max_body, client);
         if (kSpec && count == 0 && s.popped) { kind = kAmbig; break; }
         if (s.err != B2_PARSE_OK) { kind = kStop; break; }
         emit(count, s);
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(128) k_tile_walk(BatchPtrs B, DevConfig C) {
     TileRec rec;
     rec.entry = B.tiles[t].entry; rec.exit = 0; rec.count = 0; rec.kind = kStop; rec.last_proto = 0; rec.live = 0; rec.pf_in = -1;
     if (rec.entry != kNone)
-        walk_tile<true>(B.bytes + run.offset, run.length, rec.entry, -1, (k + 1) << C.tile_shift, C.max_body_size, rec, NoEmit());
+        walk_tile<true>(B.bytes + run.offset, run.length, rec.entry, -1, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, rec, NoEmit());
     B.tiles[t] = rec;
 }
 
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C) {
                 int pf = run.preferred_proto;
                 for (uint32_t j = k; j-- > 0;) if (live[j] && (cp[j] >> 2)) { pf = (int)(cp[j] & 3u); break; }
                 TileRec t; t.live = 0; t.pf_in = 0;
-                walk_tile<false>(base, len, pos, pf, (k + 1) << C.tile_shift, C.max_body_size, t, NoEmit());
+                walk_tile<false>(base, len, pos, pf, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, t, NoEmit());
                 tiles[k].entry = t.entry; tiles[k].exit = t.exit; tiles[k].count = t.count; tiles[k].kind = t.kind; tiles[k].last_proto = t.last_proto;
                 cp[k] = (t.count << 2) | ((uint32_t)t.last_proto & 3u);
                 v = make_link(t, tiles, nt, C.tile_shift);
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C) {
         const int pf_true = s_carry_pf ? (int)s_carry_pf : run.preferred_proto;
         // the step that ends ProcessNewMessage's loop, with the true preferred index (never OK:
         // every tile walk stops only on a non-OK step or past the last tile, where no bytes remain)
-        const Step s = cut_input_message(base, len, pos, pf_true, C.max_body_size);
+        const Step s = cut_input_message(base, len, pos, pf_true, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0);
         b2_run_status st;
         st.consumed = s.new_pos; st.parse_error = (uint32_t)s.err; st.n_msgs = s_carry_sum; st.first_msg = 0;
         st.preferred_proto = s.pf; st.reserved0 = 0; st.resp_off = 0; st.resp_bytes = 0;
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(128) k_frame_table(BatchPtrs B, DevConfig C) {
     const uint32_t first = B.run_status[r].first_msg + B.tile_base[t];
     TileRec tmp;
     EmitFrame e; e.out = B.frame_off + first; e.out_run = B.frame_run + first; e.run_off = run.offset; e.run_idx = r; e.cap_left = B.max_msgs - first;
-    walk_tile<false>(B.bytes + run.offset, run.length, rec.entry, rec.pf_in, (k + 1) << C.tile_shift, C.max_body_size, tmp, e);
+    walk_tile<false>(B.bytes + run.offset, run.length, rec.entry, rec.pf_in, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, tmp, e);
 }
 
 // --- k_decode: one thread per message ----------------------------------------
@@ -547,6 +547,40 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
             }
             const int64_t att = m.attachment_size;
             const DevMethod* mp = nullptr;
+            if (B.runs[d.run_idx].flags & B2_RUN_CLIENT) {
+                // ---- client-side socket: ProcessRpcResponse (baidu_rpc_protocol.cpp:911-1013), EchoResponse channel
+                d.status = B2_MSG_RESPONSE;
+                const uint32_t res_size = req_size;
+                if (m.error_code != 0) d.error_code = m.error_code;                                   // :960-965
+                else if ((m.has & B2_HAS_ATTACHMENT_SIZE) && att > (int64_t)res_size) d.error_code = B2_ERESPONSE;   // :971-976
+                else {
+                    int64_t bwo = (int64_t)res_size - ((m.has & B2_HAS_ATTACHMENT_SIZE) ? att : 0);
+                    if (bwo > (int64_t)res_size) bwo = res_size;
+                    const uint32_t body_len = (uint32_t)bwo;
+                    if (m.content_type != B2_CONTENT_TYPE_PB) d.status = B2_MSG_UNSUPPORTED;
+                    else if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) d.status = B2_MSG_UNSUPPORTED;
+                    else {
+                        bool ok = !(m.checksum_type == B2_CHECKSUM_TYPE_CRC32C && a.cks_len != 4);
+                        if (ok && m.compress_type == B2_COMPRESS_TYPE_NONE) {
+                            Span msg; msg.off = 0; msg.len = 0;
+                            ok = decode_echo_request(gframe + 12 + d.meta_size, body_len, msg);
+                            if (ok) { a.msg_off = 12 + d.meta_size + msg.off; a.msg_len = msg.len; a.att_off = body_len; d.resp_off = fo + a.msg_off; resp_len = msg.len; }
+                        } else if (ok && m.compress_type == B2_COMPRESS_TYPE_SNAPPY) {
+                            uint32_t ulen = 0, used = 0;
+                            ok = snappy_preamble(gframe + 12 + d.meta_size, body_len, ulen, used);
+                            if (ok && (uint64_t)ulen > 32ull * body_len + 64ull) ok = false;
+                            if (ok) { d.status = B2_MSG_RESPONSE_UNZ; a.msg_off = kNone; a.msg_len = ulen; a.att_off = body_len; resp_len = ulen ? ulen : 1; }
+                        } else ok = false;
+                        if (!ok) { d.error_code = B2_EREQUEST; resp_len = 0; d.status = B2_MSG_RESPONSE; }  // :999-1007
+                    }
+                }
+                d.resp_len = resp_len;
+                B.msgs[i] = d; B.aux[i] = a;
+                B.slot[i] = d.status == B2_MSG_RESPONSE_UNZ ? ((resp_len + 15u) & ~15u) : 0u;
+                PackJob cj; cj.src_off = 0; cj.bulk_len = 0; cj.head_len = 0; cj.pad = 0; cj.fast = 0; cj.slot_len = 0;
+                B.jobs[i] = cj;
+                return;
+            }
             if ((m.has & B2_HAS_ATTACHMENT_SIZE) && (int64_t)req_size < att) {
                 a.err_kind = kErrAttachment; d.error_code = B2_EREQUEST;
             } else {
@@ -972,9 +1006,31 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
     const uint32_t bi = i / (kScanBlock * kScanItems);
     const uint32_t slot_off = B.slot[i] + B.scan_tmp[bi];
     const b2_msg_desc d = B.msgs[i];
-    if (d.resp_len == 0) { if (lane == 0) B.msgs[i].resp_off = slot_off; return; }
+    if (d.resp_len == 0) { if (lane == 0 && d.status != B2_MSG_RESPONSE) B.msgs[i].resp_off = slot_off; return; }
     const MsgAux a = B.aux[i];
     const uint8_t* frame = B.bytes + d.frame_off;
+    if (d.status == B2_MSG_RESPONSE || d.status == B2_MSG_RESPONSE_UNZ) {
+        // client side: DeserializeRpcMessage of the response body = checksum verify, then (snappy ->) parse
+        bool ok = true;
+        const uint8_t* body = frame + 12 + d.meta_size; const uint32_t body_len = a.att_off;
+        if (d.checksum_type == B2_CHECKSUM_TYPE_CRC32C) {
+            const uint32_t crc = warp_crc32c_update(0xffffffffu, body, body_len, lane, B.crc_adv) ^ 0xffffffffu;
+            ok = crc == crc32c_unmask(load_be32(frame + a.cks_off));
+        }
+        uint32_t off = d.resp_off, len = d.resp_len;
+        if (ok && d.status == B2_MSG_RESPONSE_UNZ) {
+            uint32_t produced = 0;
+            ok = warp_snappy_decode(body, body_len, B.resp + slot_off, a.msg_len, lane, produced);
+            Span msg; msg.off = 0; msg.len = 0;
+            if (ok) ok = decode_echo_request(B.resp + slot_off, produced, msg);
+            off = slot_off + msg.off; len = msg.len;
+        }
+        if (lane == 0) {
+            if (ok) { B.msgs[i].resp_off = off; B.msgs[i].resp_len = len; }
+            else { B.msgs[i].status = B2_MSG_RESPONSE; B.msgs[i].error_code = B2_EREQUEST; B.msgs[i].resp_off = 0; B.msgs[i].resp_len = 0; }
+        }
+        return;
+    }
     const DevMethod* mp = d.method_idx >= 0 ? B.methods + d.method_idx : nullptr;
     uint16_t status = d.status;
     if (status == B2_MSG_ECHOED && d.checksum_type == B2_CHECKSUM_TYPE_CRC32C) {

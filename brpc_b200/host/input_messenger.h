@@ -104,7 +104,7 @@ public:
             if (total + n + 16 > _cap) break;                 // the rest waits for the next round
             s->_read_buf.copy_to(_batch + total, n, 0);       // gather the (pinned) blocks into the batch buffer
             b2_run r; r.socket_id = s->id(); r.offset = (uint32_t)total; r.length = (uint32_t)n;
-            r.preferred_proto = s->preferred_index(); r.reserved = 0;
+            r.preferred_proto = s->preferred_index(); r.flags = 0;
             runs.push_back(r); live.push_back(s);
             total = (total + n + 15) & ~(size_t)15;
         }

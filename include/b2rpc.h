@@ -61,6 +61,7 @@ extern "C" {
 #define B2_ENOSERVICE 1001
 #define B2_ENOMETHOD  1002
 #define B2_EREQUEST   1003
+#define B2_ERESPONSE  2002
 
 /* ---- per-message disposition (b2_msg_desc.status) ------------------------ */
 #define B2_MSG_ECHOED        0  /* device handler ran, OK response packed            */
@@ -72,6 +73,11 @@ extern "C" {
 #define B2_MSG_BAD_STREAM_META 5 /* StreamFrameMeta failed to parse: frame dropped
                                    (streaming_rpc_protocol.cpp:97-100)              */
 #define B2_MSG_UNSUPPORTED   6  /* codec/content type outside this path (gzip, json) */
+#define B2_MSG_RESPONSE      7  /* client-side socket: a response was processed (ProcessRpcResponse,
+                                   baidu_rpc_protocol.cpp:911-1013).  error_code = what Controller::SetFailed
+                                   would get (0 = OK); resp_off/resp_len = the EchoResponse.message bytes,
+                                   located in the BATCH buffer */
+#define B2_MSG_RESPONSE_UNZ  8  /* same, the response was snappy-compressed: message bytes are in the resp region */
 
 /* ---- has_bits of b2_msg_desc --------------------------------------------- */
 #define B2_HAS_REQUEST          (1u << 0)
@@ -108,8 +114,10 @@ typedef struct b2_run {
     uint32_t offset;           /* byte offset of the run inside the batch buffer */
     uint32_t length;           /* pending bytes of this socket */
     int32_t  preferred_proto;  /* Socket::preferred_index(): B2_PROTOCOL_* or -1 */
-    uint32_t reserved;
+    uint32_t flags;            /* B2_RUN_* */
 } b2_run;                      /* 24 bytes */
+#define B2_RUN_CLIENT 1u       /* Socket::CreatedByConnect(): client-side protocol rules of CutInputMessage
+                                  (input_messenger.cpp:122-138) and ProcessRpcResponse instead of ProcessRpcRequest */
 
 /*
  * Result of the cut loop for one run == what InputMessenger::ProcessNewMessage

@@ -445,20 +445,28 @@ static const char* k_magic[3] = { NULL, "PRPC", "STRM" };   /* handler index == 
  * server-side socket (CreatedByConnect() false) with handlers {1: baidu_std,
  * 2: streaming_rpc}.  *pos advances by what the handlers popped.             */
 static cut_t cut_input_message(const uint8_t* run, uint32_t len, uint32_t* pos, int* preferred,
-                               int* index, uint64_t max_body) {
+                               int* index, uint64_t max_body, int created_by_connect) {
     const int max_index = 2;
     const int pref = *preferred;
     cut_t c;
     if (pref >= 1 && pref <= max_index) {
-        c = parse_prefixed(run + *pos, len - *pos, k_magic[pref], max_body);
-        if (c.err == B2_PARSE_OK || c.err == B2_PARSE_ERROR_NOT_ENOUGH_DATA) {
-            if (c.err == B2_PARSE_OK) *pos += c.pop;
-            *preferred = pref; *index = pref; return c;
-        } else if (c.err != B2_PARSE_ERROR_TRY_OTHERS) {
-            return c;
-        }
-        *pos += c.pop;
-        if (len - *pos >= 4 && memcmp(run + *pos, "RDMA", 4) == 0) { c.pop = 0; return c; }   /* :111-119 */
+        int cur_index = pref;
+        do {
+            c = parse_prefixed(run + *pos, len - *pos, k_magic[cur_index], max_body);
+            if (c.err == B2_PARSE_OK || c.err == B2_PARSE_ERROR_NOT_ENOUGH_DATA) {
+                if (c.err == B2_PARSE_OK) *pos += c.pop;
+                *preferred = cur_index; *index = cur_index; return c;
+            } else if (c.err != B2_PARSE_ERROR_TRY_OTHERS) {
+                return c;
+            }
+            *pos += c.pop;
+            if (len - *pos >= 4 && memcmp(run + *pos, "RDMA", 4) == 0) { c.pop = 0; return c; }   /* :111-119 */
+            if (created_by_connect) {                                                            /* :122-138 */
+                if (cur_index == B2_PROTOCOL_BAIDU_STD && cur_index == pref) { cur_index = B2_PROTOCOL_STREAMING_RPC; continue; }
+                else if (cur_index == B2_PROTOCOL_STREAMING_RPC && cur_index == pref) { cur_index = B2_PROTOCOL_BAIDU_STD; continue; }
+                else { c.err = B2_PARSE_ERROR_ABSOLUTELY_WRONG; c.pop = 0; return c; }
+            } else break;
+        } while (1);
         *preferred = -1;
     }
     for (int i = 1; i <= max_index; i++) {
@@ -684,6 +692,54 @@ static int process_rpc_request(const orc_config* cfg, const uint8_t* frame, b2_m
     return 0;
 }
 
+/* ProcessRpcResponse (baidu_rpc_protocol.cpp:911-1013) for a channel whose response type is EchoResponse.
+ * d->error_code = what Controller::SetFailed receives (0 = success); the message bytes are reported
+ * in place (batch offset) or, for a snappy response, decompressed into resp. */
+static int process_rpc_response(const uint8_t* frame, b2_msg_desc* d, uint8_t* resp, size_t resp_cap, size_t* resp_len) {
+    const uint8_t* meta_p = frame + 12;
+    const uint8_t* payload = meta_p + d->meta_size;
+    const uint32_t res_size = d->body_size - d->meta_size;
+    orc_rpc_meta m;
+    *resp_len = 0; d->method_idx = -1; d->error_code = 0;
+    if (!orc_parse_rpc_meta(meta_p, d->meta_size, &m)) { d->status = B2_MSG_BAD_META; return 0; }   /* :914-918: dropped */
+    d->correlation_id = m.correlation_id; d->log_id = m.log_id; d->attachment_size = m.attachment_size;
+    d->compress_type = m.compress_type; d->checksum_type = m.checksum_type; d->content_type = (uint8_t)m.content_type;
+    d->has_bits = (uint16_t)m.has; d->status = B2_MSG_RESPONSE;
+    if (m.error_code != 0) { d->error_code = m.error_code; return 0; }                               /* :960-965 */
+    int64_t att = m.attachment_size;
+    size_t body_len = res_size;
+    if (m.has & B2_HAS_ATTACHMENT_SIZE) {
+        if (att > (int64_t)res_size) { d->error_code = B2_ERESPONSE; return 0; }                      /* :971-976 */
+        int64_t bwo = (int64_t)res_size - att; if (bwo > (int64_t)res_size) bwo = res_size;
+        body_len = (size_t)bwo;
+    }
+    if (m.content_type != B2_CONTENT_TYPE_PB) { d->status = B2_MSG_UNSUPPORTED; return 0; }
+    if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) { d->status = B2_MSG_UNSUPPORTED; return 0; }
+    int ok = 1;
+    const uint8_t* cks = meta_p + m.checksum_value.off; size_t cks_len = (m.has & B2_HAS_CHECKSUM_VALUE) ? m.checksum_value.len : 0;
+    if (m.checksum_type == B2_CHECKSUM_TYPE_CRC32C) {
+        if (cks_len != 4) ok = 0;
+        else {
+            uint32_t expected = ((uint32_t)cks[0] << 24) | ((uint32_t)cks[1] << 16) | ((uint32_t)cks[2] << 8) | cks[3];
+            ok = orc_crc32c_extend(0, payload, body_len) == orc_crc32c_unmask(expected);
+        }
+    }
+    orc_span msg = { 0, 0 };
+    if (ok && m.compress_type == B2_COMPRESS_TYPE_NONE) {
+        ok = orc_parse_echo_request(payload, body_len, &msg);       /* EchoResponse has the same schema */
+        if (ok) { d->resp_off = d->frame_off + 12 + d->meta_size + msg.off; d->resp_len = msg.len; }
+    } else if (ok && m.compress_type == B2_COMPRESS_TYPE_SNAPPY) {
+        size_t ulen = 0, got = 0;
+        if (!ref_load()) { d->status = B2_MSG_UNSUPPORTED; return 0; }
+        if (!g_sn_len((const char*)payload, body_len, &ulen) || ulen > 32 * (uint64_t)body_len + 64 || ulen > resp_cap) ok = 0;
+        else if (!g_sn_u((const char*)payload, body_len, (char*)resp, ulen, &got)) ok = 0;
+        else ok = orc_parse_echo_request(resp, got, &msg);
+        if (ok) { d->status = B2_MSG_RESPONSE_UNZ; *resp_len = got; d->resp_len = msg.len; d->resp_off = msg.off; /* + slot, by caller */ }
+    } else if (ok) ok = 0;                                                                           /* no such handler */
+    if (!ok) { d->error_code = B2_EREQUEST; d->resp_off = 0; d->resp_len = 0; d->status = B2_MSG_RESPONSE; }   /* :999-1007 */
+    return 0;
+}
+
 /* ParseStreamingMessage's meta step, streaming_rpc_protocol.cpp:95-100 */
 static void process_stream_frame(const uint8_t* frame, b2_msg_desc* d) {
     orc_stream_meta sm;
@@ -712,7 +768,8 @@ int orc_process_batch(const orc_config* cfg, const uint8_t* bytes, uint32_t nbyt
         rs[r].first_msg = nm; rs[r].resp_off = (uint32_t)rb;
         for (;;) {
             uint32_t before = pos;
-            cut_t c = cut_input_message(run, len, &pos, &preferred, &index, max_body);
+            const int client = (runs[r].flags & B2_RUN_CLIENT) != 0;
+            cut_t c = cut_input_message(run, len, &pos, &preferred, &index, max_body, client);
             if (c.err != B2_PARSE_OK) { rs[r].parse_error = (uint32_t)c.err; break; }
             if (nm >= msg_cap) return -1;
             b2_msg_desc* d = &msgs[nm];
@@ -721,12 +778,16 @@ int orc_process_batch(const orc_config* cfg, const uint8_t* bytes, uint32_t nbyt
             d->body_size = c.body_size; d->meta_size = c.meta_size; d->protocol = (uint8_t)index;
             (void)before;
             size_t rl = 0;
-            if (index == B2_PROTOCOL_BAIDU_STD) {
+            if (index == B2_PROTOCOL_BAIDU_STD && client) {
+                if (process_rpc_response(bytes + d->frame_off, d, resp + rb, resp_cap - rb, &rl) != 0) return -1;
+                if (d->status == B2_MSG_RESPONSE_UNZ) d->resp_off += (uint32_t)rb;       /* message inside the decompressed bytes */
+            } else if (index == B2_PROTOCOL_BAIDU_STD) {
                 if (process_rpc_request(cfg, bytes + d->frame_off, d, resp + rb, resp_cap - rb, &rl) != 0) return -1;
+                d->resp_off = (uint32_t)rb; d->resp_len = (uint32_t)rl;
             } else {
                 process_stream_frame(bytes + d->frame_off, d);
+                d->resp_off = (uint32_t)rb; d->resp_len = 0;
             }
-            d->resp_off = (uint32_t)rb; d->resp_len = (uint32_t)rl;
             rb += rl; nm++; rs[r].n_msgs++;
         }
         rs[r].consumed = pos; rs[r].preferred_proto = preferred;

@@ -30,28 +30,32 @@ def assert_same(dev, orc, what=""):
         bad = np.nonzero(d_msgs[f] != o_msgs[f])[0]
         assert len(bad) == 0, "%s msgs.%s differs at %s: dev %s oracle %s (status dev %s orc %s)" % (
             what, f, bad[:5], d_msgs[f][bad[:5]], o_msgs[f][bad[:5]], d_msgs["status"][bad[:5]], o_msgs["status"][bad[:5]])
+    # client-side responses (status 7) report the message in place: offsets are batch-relative and must agree
+    inplace = d_msgs["status"] == 7
+    assert np.array_equal(d_msgs["resp_off"][inplace], o_msgs["resp_off"][inplace]), what + " in-place response offsets differ"
     # response bytes, message by message (the device pads slots; the oracle packs tight)
-    dg = gather(d_resp, d_msgs["resp_off"], d_msgs["resp_len"])
-    og = gather(o_resp, o_msgs["resp_off"], o_msgs["resp_len"])
+    dl = np.where(inplace, 0, d_msgs["resp_len"]); ol = np.where(inplace, 0, o_msgs["resp_len"])
+    dg = gather(d_resp, d_msgs["resp_off"], dl)
+    og = gather(o_resp, o_msgs["resp_off"], ol)
     assert len(dg) == len(og)
     if len(dg):
         neq = np.nonzero(dg != og)[0]
         if len(neq):
-            pos = int(neq[0]); ends = np.cumsum(o_msgs["resp_len"].astype(np.int64))
+            pos = int(neq[0]); ends = np.cumsum(ol.astype(np.int64))
             mi = int(np.searchsorted(ends, pos, side="right"))
-            lo = int(ends[mi] - o_msgs["resp_len"][mi])
+            lo = int(ends[mi] - ol[mi])
             raise AssertionError("%s response bytes differ in msg %d at byte %d:\n dev %s\n orc %s" % (
                 what, mi, pos - lo, bytes(dg[lo:lo + 96]).hex(), bytes(og[lo:lo + 96]).hex()))
     # layout invariants of the device response region
     if len(d_msgs):
-        has = d_msgs["resp_len"] > 0
+        has = (d_msgs["resp_len"] > 0) & ~inplace
         off = d_msgs["resp_off"][has].astype(np.int64); ln = d_msgs["resp_len"][has].astype(np.int64)
         assert np.all(off[1:] >= off[:-1] + ln[:-1]), what + " response slots overlap or are out of order"
         if len(off):
             assert off[-1] + ln[-1] <= len(d_resp) or len(d_resp) == 0 or True
     for r in range(len(d_rs)):
         a, n = int(d_rs["first_msg"][r]), int(d_rs["n_msgs"][r])
-        if n and np.any(d_msgs["resp_len"][a:a + n] > 0):
-            m = d_msgs[a:a + n]; m = m[m["resp_len"] > 0]
+        if n and np.any((d_msgs["resp_len"][a:a + n] > 0) & (d_msgs["status"][a:a + n] != 7)):
+            m = d_msgs[a:a + n]; m = m[(m["resp_len"] > 0) & (m["status"] != 7)]
             assert int(m["resp_off"][0]) >= int(d_rs["resp_off"][r])
             assert int(m["resp_off"][-1] + m["resp_len"][-1]) <= int(d_rs["resp_off"][r]) + int(d_rs["resp_bytes"][r])

@@ -57,7 +57,7 @@ class RequestSpec(C.Structure):
 
 
 RUN_DT = np.dtype([("socket_id", "<u8"), ("offset", "<u4"), ("length", "<u4"),
-                   ("preferred_proto", "<i4"), ("reserved", "<u4")])
+                   ("preferred_proto", "<i4"), ("flags", "<u4")])
 RUN_STATUS_DT = np.dtype([("consumed", "<u4"), ("parse_error", "<u4"), ("n_msgs", "<u4"), ("first_msg", "<u4"),
                           ("preferred_proto", "<i4"), ("reserved0", "<u4"), ("resp_off", "<u4"), ("resp_bytes", "<u4")])
 MSG_DT = np.dtype([("run_idx", "<u4"), ("frame_off", "<u4"), ("body_size", "<u4"), ("meta_size", "<u4"),

@@ -289,3 +289,46 @@ def test_small_batch_overflow_redo(b2):
     # and right at the edge
     run_both(b2, ctx, [b"".join(frames[:1024])])
     run_both(b2, ctx, [b"".join(frames[:1025])])
+
+
+def test_client_side_responses(b2):
+    """Client-side sockets (CreatedByConnect): CutInputMessage's baidu_std<->streaming fallback rules and
+    ProcessRpcResponse.  The response streams are what the oracle's server writes for mixed requests
+    (OK / error replies, crc32c and snappy responses), re-read as a client would."""
+    rng = random.Random(13)
+    for opts in (dict(), dict(response_checksum_type=1), dict(response_compress_type=1), dict(response_checksum_type=1, response_compress_type=1)):
+        ms = [dict(b2.ECHO_METHOD, **opts)]
+        srv = O.make_config(methods=ms, server_identity=b"127.0.0.1:8002")
+        streams = [mixed_frames(rng, 25) for _ in range(40)]
+        data, runs = b2.make_runs(split_runs(rng, streams, cut_tail=False))
+        rs, msgs, resp = O.process_batch(srv, data, runs)
+        # per-socket response streams; sprinkle stream frames and a corrupted response
+        client_chunks = []
+        for r in range(len(runs)):
+            m = msgs[int(rs["first_msg"][r]):int(rs["first_msg"][r]) + int(rs["n_msgs"][r])]
+            parts = [bytes(resp[int(x["resp_off"]):int(x["resp_off"]) + int(x["resp_len"])]) for x in m if x["resp_len"] > 0 and x["status"] in (0, 1)]
+            if r % 5 == 0 and parts:
+                parts.insert(len(parts) // 2, O.pack_stream_frame(77, 78, 3, False, b"stream-data"))
+            if r % 7 == 0 and parts:
+                p = bytearray(parts[-1]); p[-1] ^= 0x33; parts[-1] = bytes(p)
+            if r % 11 == 0 and parts:
+                p = bytearray(parts[0]); p[0] = ord("X"); parts[0] = bytes(p)      # bad magic on a client socket
+            b = b"".join(parts)
+            if r % 3 == 0 and len(b) > 20:
+                b = b[:len(b) - rng.randrange(1, 20)]
+            client_chunks.append(b)
+        ctx = make_ctx(b2, tile_bytes=1024)
+        cdata, cruns = b2.make_runs(client_chunks)
+        cruns["flags"] = 1
+        for pref in (1, 2, -1):
+            cruns["preferred_proto"] = pref
+            dev = ctx.process_batch(cdata, cruns)
+            orc = O.process_batch(O.make_config(), cdata, cruns)
+            assert_same(dev, orc, "opts=%s pref=%d" % (opts, pref))
+            st = set(dev[1]["status"].tolist())
+            assert 7 in st or 8 in st
+            if opts.get("response_compress_type"):
+                assert 8 in st
+        # the in-place message of an OK response equals the request's message
+        ok = dev[1][(dev[1]["status"] == 7) & (dev[1]["error_code"] == 0) & (dev[1]["resp_len"] > 0)]
+        assert len(ok) > 10 or opts.get("response_compress_type")
