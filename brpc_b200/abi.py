@@ -73,6 +73,8 @@ def _load():
     l.b2_crc32c_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     l.b2_snappy_uncompress_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                              C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    l.b2_snappy_compress_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                           C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     l.b2_counters_read.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     l.b2_counters_device_ptr.restype = C.c_void_p; l.b2_counters_device_ptr.argtypes = [C.c_void_p]
     return l
@@ -84,7 +86,7 @@ lib = _load()
 ABI_SYMBOLS = ["b2_ctx_create", "b2_ctx_destroy", "b2_last_error", "b2_version", "b2_register_method",
                "b2_set_server_identity", "b2_block_alloc", "b2_block_free", "b2_process_batch", "b2_batch_submit", "b2_batch_collect", "b2_batch_upload",
                "b2_batch_execute", "b2_batch_execute_many", "b2_batch_download", "b2_batch_launch", "b2_batch_wait",
-               "b2_elapsed_ms", "b2_stage_times", "b2_crc32c_batch", "b2_snappy_uncompress_batch", "b2_counters_read",
+               "b2_elapsed_ms", "b2_stage_times", "b2_crc32c_batch", "b2_snappy_uncompress_batch", "b2_snappy_compress_batch", "b2_counters_read",
                "b2_counters_device_ptr"]
 
 ECHO_METHOD = dict(service_full_name=b"example.EchoService", service_name=b"EchoService", method_name=b"Echo",
@@ -248,6 +250,15 @@ class Context:
         _check(lib.b2_snappy_uncompress_batch(self._h, data.ctypes.data, data.nbytes, offs.ctypes.data, lens.ctypes.data, n,
                                               out.ctypes.data, out_cap, ooffs.ctypes.data, olens.ctypes.data))
         return [None if olens[i] < 0 else out[ooffs[i]:ooffs[i] + olens[i]].tobytes() for i in range(n)]
+
+    def snappy_compress_batch(self, data, offs, lens, out_cap):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint32); lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        n = len(offs)
+        out = np.zeros(out_cap, dtype=np.uint8); ooffs = np.zeros(n, dtype=np.uint32); olens = np.zeros(n, dtype=np.uint32)
+        _check(lib.b2_snappy_compress_batch(self._h, data.ctypes.data, data.nbytes, offs.ctypes.data, lens.ctypes.data, n,
+                                            out.ctypes.data, out_cap, ooffs.ctypes.data, olens.ctypes.data))
+        return [out[ooffs[i]:ooffs[i] + olens[i]].tobytes() for i in range(n)]
 
     def counters(self):
         out = (C.c_int64 * 8)()

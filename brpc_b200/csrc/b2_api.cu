@@ -36,7 +36,7 @@ struct b2_ctx {
     uint8_t* d_bytes = nullptr; b2_run* d_runs = nullptr; uint32_t* d_run_tile_base = nullptr;
     TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; uint32_t* d_tile_scratch = nullptr; b2_run_status* d_run_status = nullptr;
     uint32_t* d_frame_off = nullptr; uint32_t* d_frame_run = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr; PackJob* d_jobs = nullptr; uint8_t* d_heads = nullptr;
-    uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr; uint8_t* d_unz = nullptr;
+    uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr; uint8_t* d_unz = nullptr; uint16_t* d_snappy_tab = nullptr;
     uint32_t* d_crc_adv = nullptr; unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
     uint32_t max_tiles = 0; uint32_t n_sms = 148; bool use_tma_pack = true;
     // pinned host mirrors
@@ -83,7 +83,7 @@ extern "C" void b2_ctx_destroy(b2_ctx* c) {
     cudaSetDevice(c->opt.device);
     cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch);
     cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_frame_run); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_heads); cudaFree(c->d_slot);
-    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
+    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
     cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
     cudaFreeHost(c->h_run_tile_base);
     for (int i = 0; i <= kMaxStages; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -138,7 +138,8 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     ALLOC(c->d_slot, 4 * ((size_t)o->max_msgs + 1));
     ALLOC(c->d_scan_tmp, 4 * (size_t)scan_blocks);
     ALLOC(c->d_resp, (size_t)c->opt.max_resp_bytes + 1024);
-    ALLOC(c->d_unz, (size_t)c->opt.max_resp_bytes + 1024);
+    ALLOC(c->d_unz, 2 * (size_t)c->opt.max_resp_bytes + 1024);
+    ALLOC(c->d_snappy_tab, (size_t)kSnappyWarps * kSnappyMaxTable * 2);
     ALLOC(c->d_counters, 8 * B2_N_COUNTERS);
     ALLOC(c->d_totals, 16);
     ALLOC(c->d_methods, sizeof(DevMethod) * 64);
@@ -213,7 +214,7 @@ static BatchPtrs make_ptrs(b2_ctx* c) {
     BatchPtrs B;
     B.bytes = c->d_bytes; B.runs = c->d_runs; B.run_tile_base = c->d_run_tile_base; B.tiles = c->d_tiles;
     B.tile_base = c->d_tile_base; B.tile_scratch = c->d_tile_scratch; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.frame_run = c->d_frame_run; B.msgs = c->d_msgs;
-    B.aux = c->d_aux; B.jobs = c->d_jobs; B.heads = c->d_heads; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.unz = c->d_unz; B.counters = c->d_counters;
+    B.aux = c->d_aux; B.jobs = c->d_jobs; B.heads = c->d_heads; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.unz = c->d_unz; B.snappy_tab = c->d_snappy_tab; B.counters = c->d_counters;
     B.totals = c->d_totals; B.methods = c->d_methods; B.crc_adv = c->d_crc_adv;
     B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes;
     B.runs = reinterpret_cast<const b2_run*>(c->d_meta);
@@ -529,6 +530,41 @@ extern "C" int b2_snappy_uncompress_batch(b2_ctx* c, const void* bytes, uint32_t
     CU(cudaMemcpyAsync(d_ooffs, out_offs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_caps, caps.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     if (n) k_snappy_batch<<<c->n_sms * 4, 256, 0, c->stream>>>(c->d_bytes, d_offs, d_lens, n, c->d_unz, d_ooffs, d_caps, d_olens);
+    CU(cudaMemcpyAsync(out_lens, d_olens, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (total) CU(cudaMemcpyAsync(out, c->d_unz, total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->uploaded = false; c->executed = false;
+    return B2_OK;
+}
+
+__global__ void __launch_bounds__(256) k_snappy_compress_batch(const uint8_t* bytes, const uint32_t* offs, const uint32_t* lens, uint32_t n,
+                                                               uint8_t* out, const uint32_t* out_offs, uint32_t* out_lens, uint16_t* tabs) {
+    const uint32_t lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint16_t* table = tabs + (size_t)(warp % kSnappyWarps) * kSnappyMaxTable;
+    for (uint32_t i = warp; i < n; i += n_warps) {
+        const uint32_t c = warp_snappy_compress(bytes + offs[i], lens[i], out + out_offs[i], table, lane);
+        if (lane == 0) out_lens[i] = c;
+    }
+}
+
+extern "C" int b2_snappy_compress_batch(b2_ctx* c, const void* bytes, uint32_t nbytes, const uint32_t* offs, const uint32_t* lens,
+                                        uint32_t n, void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens) {
+    if (!c || !bytes || !offs || !lens || !out || !out_offs || !out_lens) { set_err("null argument"); return B2_E_INVAL; }
+    if (nbytes > c->opt.max_batch_bytes || n > c->opt.max_msgs || out_cap > c->opt.max_resp_bytes) { set_err("exceeds ctx capacity"); return B2_E_CAPACITY; }
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if ((uint64_t)offs[i] + lens[i] > nbytes) { set_err("slice outside buffer"); return B2_E_INVAL; }
+        out_offs[i] = (uint32_t)total;
+        total += ((uint64_t)snappy_max_compressed_length(lens[i]) + 15) & ~15ull;
+        if (total > out_cap) { set_err("output exceeds out_cap"); return B2_E_CAPACITY; }
+    }
+    CU(cudaSetDevice(c->opt.device));
+    uint32_t* d_offs = c->d_frame_off; uint32_t* d_lens = c->d_slot; uint32_t* d_ooffs = c->d_frame_run; uint32_t* d_olens = (uint32_t*)c->d_aux;
+    CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_offs, offs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_lens, lens, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_ooffs, out_offs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    if (n) k_snappy_compress_batch<<<c->n_sms * 4, 256, 0, c->stream>>>(c->d_bytes, d_offs, d_lens, n, c->d_unz, d_ooffs, d_olens, c->d_snappy_tab);
     CU(cudaMemcpyAsync(out_lens, d_olens, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     if (total) CU(cudaMemcpyAsync(out, c->d_unz, total, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -95,7 +95,9 @@ struct BatchPtrs {
     uint32_t* slot;                  // [max_msgs+1] slot sizes -> exclusive offsets
     uint32_t* scan_tmp;              // block sums
     uint8_t* resp;
-    uint8_t* unz;                    // [max_resp] scratch: decompressed request bodies, at the message's slot offset
+    uint8_t* unz;                    // [2 * max_resp] scratch at the message's slot offset: decompressed request bodies (first half),
+                                     // serialized replies awaiting compression (second half)
+    uint16_t* snappy_tab;            // [kSnappyWarps][16384] hash tables of the snappy encoder, one per warp
     unsigned long long* counters;    // int64[B2_N_COUNTERS]
     uint32_t* totals;                // [0]=n_msgs [1]=resp_bytes [2]=overflow flags
     const DevMethod* methods;
@@ -454,6 +456,7 @@ __device__ __forceinline__ uint32_t error_text_len(const DevConfig& C, const Dev
 }
 
 __device__ __forceinline__ bool snappy_preamble(const uint8_t* in, uint32_t n, uint32_t& ulen, uint32_t& used);
+__host__ __device__ __forceinline__ uint32_t snappy_max_compressed_length(uint32_t n) { return 32 + n + n / 6; }   // snappy.cc:55-77
 // k_decode stages the first kRowBytes of every frame (header + RpcMeta + first body bytes) in
 // shared memory with coalesced 4-byte loads (one row per lane) and decodes from there; the head
 // records are assembled in shared memory and leave with coalesced 16-byte stores.
@@ -598,7 +601,7 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                 const uint32_t in_att_len = att > 0 ? (uint32_t)att : 0;
                 if (m.content_type != B2_CONTENT_TYPE_PB) d.status = B2_MSG_UNSUPPORTED;
                 else if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) d.status = B2_MSG_UNSUPPORTED;
-                else if (mp->response_compress_type != B2_COMPRESS_TYPE_NONE) d.status = B2_MSG_UNSUPPORTED;
+                else if (mp->response_compress_type != B2_COMPRESS_TYPE_NONE && mp->response_compress_type != B2_COMPRESS_TYPE_SNAPPY) d.status = B2_MSG_UNSUPPORTED;
                 else if (m.compress_type == B2_COMPRESS_TYPE_SNAPPY) {
                     // SnappyDecompress (policy/snappy_compress.cpp:51-70) happens in the pack stage; here only the
                     // announced length is read to reserve the reply slot.  A stream cannot expand more than ~22x
@@ -613,8 +616,9 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                         a.msg_off = kNone; a.msg_len = ulen;        // resolved after decompression
                         if (mp->echo_attachment) { a.att_len = in_att_len; a.att_off = 12 + d.meta_size + body_wo_att; }
                         const uint32_t cks_len = mp->response_checksum_type == B2_CHECKSUM_TYPE_CRC32C ? 4u : a.cks_len;
-                        const uint32_t ml = response_meta_len(0, 0, 0, m.correlation_id, a.att_len, mp->response_checksum_type, cks_len);
+                        const uint32_t ml = response_meta_len(0, 0, mp->response_compress_type, m.correlation_id, a.att_len, mp->response_checksum_type, cks_len);
                         resp_len = 12 + ml + 8 + ulen + a.att_len;   // upper bound; the pack stage writes the real length
+                        if (mp->response_compress_type == B2_COMPRESS_TYPE_SNAPPY) resp_len = 12 + ml + snappy_max_compressed_length(ulen + 8) + a.att_len;
                         a.pad = 0;
                     }
                 }
@@ -647,6 +651,9 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                         const uint32_t prefix = 12 + ml + 1 + varint_len(msg.len);
                         resp_len = prefix + msg.len + a.att_len;
                         a.pad = (fo + a.msg_off - prefix) & 15u;       // payload keeps its (mod 16) alignment
+                        if (mp->response_compress_type == B2_COMPRESS_TYPE_SNAPPY) {
+                            resp_len = 12 + ml + snappy_max_compressed_length(1 + varint_len(msg.len) + msg.len) + a.att_len; a.pad = 0;
+                        }
                     }
                 }
             }
@@ -673,6 +680,7 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
     PackJob job; job.src_off = 0; job.bulk_len = 0; job.head_len = 0; job.pad = (uint8_t)a.pad; job.fast = 0; job.slot_len = slot_len;
     if (d.status == B2_MSG_ECHOED && d.checksum_type != B2_CHECKSUM_TYPE_CRC32C && d.compress_type == B2_COMPRESS_TYPE_NONE &&
         B.methods[d.method_idx].response_checksum_type == B2_CHECKSUM_TYPE_NONE &&
+        B.methods[d.method_idx].response_compress_type == B2_COMPRESS_TYPE_NONE &&
         (a.att_len == 0 || a.att_off == a.msg_off + a.msg_len)) {
         const uint32_t ml = response_meta_len(0, 0, 0, d.correlation_id, a.att_len, 0, a.cks_len);
         const uint32_t vl = varint_len(a.msg_len);
@@ -831,6 +839,149 @@ __device__ __noinline__ bool warp_snappy_decode(const uint8_t* in, uint32_t n, u
     return op == ulen;
 }
 
+// Snappy raw-format ENCODER, bit-exact with butil::snappy::RawCompress (snappy.cc:875-956 Compress,
+// :329-468 CompressFragment, :156-233 EmitLiteral/EmitCopy, snappy-internal.h:86-120 FindMatchLength):
+// same hash (load32 * 0x1e35a7bd >> shift), same table size rule (256..16384 entries, >= fragment
+// size), same skip heuristic (skip++ >> 5), same 15-byte input margin, same emit rules, 64 KiB
+// fragments with a zeroed table each.  The probe chain is serial by construction (every table write
+// feeds later probes): lane 0 walks it; match extension and literal/tag emission use the warp.
+constexpr uint32_t kSnappyWarps = 8192;
+constexpr uint32_t kSnappyBlock = 65536, kSnappyMaxTable = 16384;
+
+__device__ __forceinline__ uint32_t ld32u(const uint8_t* p) {      // UNALIGNED_LOAD32
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+// number of leading bytes in which s1[] and s2[] agree, s2 bounded by s2_limit (FindMatchLength)
+__device__ __forceinline__ uint32_t warp_find_match_length(const uint8_t* s1, const uint8_t* s2, const uint8_t* s2_limit, uint32_t lane) {
+    const uint32_t maxn = (uint32_t)(s2_limit - s2);
+    for (uint32_t base = 0; base < maxn; base += 32) {
+        const uint32_t i = base + lane;
+        const bool diff = i >= maxn || s1[i] != s2[i];
+        const uint32_t m = __ballot_sync(0xffffffffu, diff);
+        if (m) return base + (__ffs(m) - 1);
+    }
+    return maxn;
+}
+// tag bytes of a literal of `len` (EmitLiteral); returns their count
+__device__ __forceinline__ uint32_t snappy_literal_tag(uint8_t* op, uint32_t len, bool write) {
+    uint32_t n = len - 1;
+    if (n < 60) { if (write) op[0] = (uint8_t)(n << 2); return 1; }
+    uint32_t count = 0, v = n;
+    while (v > 0) { if (write) op[1 + count] = (uint8_t)(v & 0xff); v >>= 8; count++; }
+    if (write) op[0] = (uint8_t)((59 + count) << 2);
+    return 1 + count;
+}
+// EmitCopy: tags for a copy of `len` at `offset`; returns their byte count
+__device__ __forceinline__ uint32_t snappy_copy_tags(uint8_t* op, uint32_t offset, uint32_t len, bool write) {
+    uint32_t w = 0;
+    auto less64 = [&](uint32_t l) {
+        if (l < 12 && offset < 2048) {
+            if (write) { op[w] = (uint8_t)(1 + ((l - 4) << 2) + ((offset >> 8) << 5)); op[w + 1] = (uint8_t)(offset & 0xff); }
+            w += 2;
+        } else {
+            if (write) { op[w] = (uint8_t)(2 + ((l - 1) << 2)); op[w + 1] = (uint8_t)(offset & 0xff); op[w + 2] = (uint8_t)(offset >> 8); }
+            w += 3;
+        }
+    };
+    while (len >= 68) { less64(64); len -= 64; }
+    if (len > 64) { less64(60); len -= 60; }
+    less64(len);
+    return w;
+}
+__device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane);
+
+// one fragment (<= 64 KiB); returns the compressed size.  `table` is this warp's hash table.
+__device__ __noinline__ uint32_t warp_snappy_compress_fragment(const uint8_t* input, uint32_t input_size, uint8_t* out,
+                                                               uint16_t* table, uint32_t lane) {
+    uint32_t table_size = 256;
+    while (table_size < kSnappyMaxTable && table_size < input_size) table_size <<= 1;
+    for (uint32_t i = lane; i < table_size / 2; i += 32) reinterpret_cast<uint32_t*>(table)[i] = 0;
+    __syncwarp();
+    const int shift = 32 - (31 - __clz(table_size));
+    uint32_t op = 0, ip = 0, next_emit = 0;
+    const uint32_t ip_end = input_size;
+    if (input_size >= 15) {
+        const uint32_t ip_limit = input_size - 15;
+        uint32_t next_hash = 0;
+        ip = 1;
+        if (lane == 0) next_hash = (ld32u(input + ip) * 0x1e35a7bdu) >> shift;
+        for (;;) {
+            // Step 1 (lane 0): scan forward for a 4-byte match
+            uint32_t found = 0, candidate = 0;
+            if (lane == 0) {
+                uint32_t skip = 32, next_ip = ip;
+                for (;;) {
+                    ip = next_ip;
+                    const uint32_t hash = next_hash;
+                    const uint32_t step = skip++ >> 5;
+                    next_ip = ip + step;
+                    if (next_ip > ip_limit) { found = 0; break; }
+                    next_hash = (ld32u(input + next_ip) * 0x1e35a7bdu) >> shift;
+                    candidate = table[hash];
+                    table[hash] = (uint16_t)ip;
+                    if (ld32u(input + ip) == ld32u(input + candidate)) { found = 1; break; }
+                }
+            }
+            found = __shfl_sync(0xffffffffu, found, 0);
+            if (!found) break;                                   // goto emit_remainder
+            ip = __shfl_sync(0xffffffffu, ip, 0); candidate = __shfl_sync(0xffffffffu, candidate, 0);
+            // Step 2: the literal [next_emit, ip)
+            {
+                const uint32_t len = ip - next_emit;
+                const uint32_t tl = snappy_literal_tag(out + op, len, lane == 0);
+                warp_copy(out + op + tl, input + next_emit, len, lane);
+                op += tl + len;
+            }
+            // Step 3: copies, as long as the position right after a copy matches again
+            bool remainder = false;
+            for (;;) {
+                const uint32_t base_ip = ip;
+                const uint32_t matched = 4 + warp_find_match_length(input + candidate + 4, input + ip + 4, input + ip_end, lane);
+                ip += matched;
+                op += snappy_copy_tags(out + op, base_ip - candidate, matched, lane == 0);
+                next_emit = ip;
+                if (ip >= ip_limit) { remainder = true; break; }
+                uint32_t again = 0;
+                if (lane == 0) {
+                    const uint32_t prev_hash = (ld32u(input + ip - 1) * 0x1e35a7bdu) >> shift;
+                    table[prev_hash] = (uint16_t)(ip - 1);
+                    const uint32_t cur = ld32u(input + ip);
+                    const uint32_t cur_hash = (cur * 0x1e35a7bdu) >> shift;
+                    candidate = table[cur_hash];
+                    const uint32_t cand_bytes = ld32u(input + candidate);
+                    table[cur_hash] = (uint16_t)ip;
+                    again = cur == cand_bytes;
+                }
+                again = __shfl_sync(0xffffffffu, again, 0);
+                candidate = __shfl_sync(0xffffffffu, candidate, 0);
+                if (!again) break;
+            }
+            if (remainder) break;
+            if (lane == 0) next_hash = (ld32u(input + ip + 1) * 0x1e35a7bdu) >> shift;
+            ++ip;
+        }
+    }
+    // emit_remainder
+    if (next_emit < ip_end) {
+        const uint32_t len = ip_end - next_emit;
+        const uint32_t tl = snappy_literal_tag(out + op, len, lane == 0);
+        warp_copy(out + op + tl, input + next_emit, len, lane);
+        op += tl + len;
+    }
+    __syncwarp();
+    return op;
+}
+// whole buffer: varint32 length + fragments; returns the compressed size
+__device__ __forceinline__ uint32_t warp_snappy_compress(const uint8_t* in, uint32_t n, uint8_t* out, uint16_t* table, uint32_t lane) {
+    uint32_t op = 0;
+    { uint32_t v = n; while (v >= 0x80) { if (lane == 0) out[op] = (uint8_t)(v | 0x80); v >>= 7; op++; } if (lane == 0) out[op] = (uint8_t)v; op++; }
+    for (uint32_t pos = 0; pos < n; pos += kSnappyBlock) {
+        const uint32_t len = min(kSnappyBlock, n - pos);
+        op += warp_snappy_compress_fragment(in + pos, len, out + op, table, lane);
+    }
+    return op;
+}
+
 #ifndef B2_PACK_MIN_BLOCKS
 #define B2_PACK_MIN_BLOCKS 6
 #endif
@@ -962,7 +1113,8 @@ __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint
 // EchoResponse field header.  `out` may point to shared or global memory.
 __device__ __forceinline__ void write_echo_prefix(uint8_t* out, uint32_t lane, int64_t correlation_id, uint32_t att_len,
                                                   int32_t r_cks_type, uint32_t cks_len, uint32_t crc_be, const uint8_t* req_cks,
-                                                  uint32_t msg_len, uint32_t ml, uint32_t vl, uint32_t prefix) {
+                                                  uint32_t msg_len, uint32_t ml, uint32_t vl, uint32_t prefix,
+                                                  int32_t compress_type = 0, uint32_t compressed_body = 0) {
     const uint32_t cid_n = varint_len((uint64_t)correlation_id);
     const uint32_t att_n = att_len ? 1 + varint_len(att_len) : 0;
     const uint32_t o_cid = 12 + 6;                 // after 12 02 08 00 18 00
@@ -972,13 +1124,14 @@ __device__ __forceinline__ void write_echo_prefix(uint8_t* out, uint32_t lane, i
     const uint32_t ckl_n = varint_len(cks_len);
     const uint32_t o_ckv = o_ckl + ckl_n;
     const uint32_t o_pb = o_ckv + cks_len;         // == 12 + ml
-    const uint32_t total_body = ml + 1 + vl + msg_len + att_len;
+    // compressed reply: the body is the compressed EchoResponse (no pb field header here, prefix == 12 + ml)
+    const uint32_t total_body = compress_type ? ml + compressed_body + att_len : ml + 1 + vl + msg_len + att_len;
     for (uint32_t j = lane; j < prefix; j += 32) {
         uint8_t b;
         if (j < 4) b = (uint8_t)(kMagicPRPC >> (8 * j));
         else if (j < 8) b = (uint8_t)(total_body >> (8 * (7 - j)));
         else if (j < 12) b = (uint8_t)(ml >> (8 * (11 - j)));
-        else if (j < o_cid) { const uint32_t k = j - 12; b = (k == 0) ? 0x12 : (k == 1) ? 0x02 : (k == 2) ? 0x08 : (k == 4) ? 0x18 : 0x00; }
+        else if (j < o_cid) { const uint32_t k = j - 12; b = (k == 0) ? 0x12 : (k == 1) ? 0x02 : (k == 2) ? 0x08 : (k == 4) ? 0x18 : (k == 5) ? (uint8_t)compress_type : 0x00; }
         else if (j == o_cid) b = 0x20;
         else if (j < o_att) b = varint_byte((uint64_t)correlation_id, j - o_cid - 1, cid_n);
         else if (j < o_ct) b = (j == o_att) ? 0x28 : varint_byte(att_len, j - o_att - 1, att_n - 1);
@@ -1067,12 +1220,34 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
     }
     // ---- OK echo reply: SendRpcResponse with append_body -----------------------------------
     const int32_t r_cks_type = mp->response_checksum_type;
+    const int32_t r_compress = mp->response_compress_type;
     const uint32_t cks_len = r_cks_type == B2_CHECKSUM_TYPE_CRC32C ? 4u : a.cks_len;
-    const uint32_t ml = response_meta_len(0, 0, 0, d.correlation_id, a.att_len, r_cks_type, cks_len);
+    const uint32_t ml = response_meta_len(0, 0, r_compress, d.correlation_id, a.att_len, r_cks_type, cks_len);
     const uint32_t vl = varint_len(msg_len);
+    uint8_t* out = B.resp + slot_off + a.pad;
+    if (r_compress == B2_COMPRESS_TYPE_SNAPPY) {
+        // SnappyCompress (policy/snappy_compress.cpp:28-49): serialize the EchoResponse, then compress it
+        uint8_t* pb = B.unz + (size_t)B.max_resp + slot_off;
+        const uint32_t pb_len = 1 + vl + msg_len;
+        if (lane == 0) { pb[0] = 0x0a; put_varint(pb + 1, msg_len); }
+        warp_copy(pb + 1 + vl, msg_src, msg_len, lane);
+        __syncwarp();
+        const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        uint16_t* table = B.snappy_tab + (size_t)(warp_id % kSnappyWarps) * kSnappyMaxTable;
+        const uint32_t prefix = 12 + ml;
+        const uint32_t clen = warp_snappy_compress(pb, pb_len, out + prefix, table, lane);
+        __syncwarp();
+        uint32_t crc_be = 0;
+        if (r_cks_type == B2_CHECKSUM_TYPE_CRC32C)
+            crc_be = crc32c_mask(warp_crc32c_update(0xffffffffu, out + prefix, clen, lane, B.crc_adv) ^ 0xffffffffu);
+        write_echo_prefix(out, lane, d.correlation_id, a.att_len, r_cks_type, cks_len, crc_be, frame + a.cks_off, msg_len, ml, vl, prefix,
+                          r_compress, clen);
+        if (a.att_len) warp_copy(out + prefix + clen, frame + a.att_off, a.att_len, lane);
+        if (lane == 0) { B.msgs[i].resp_off = slot_off + a.pad; B.msgs[i].resp_len = prefix + clen + a.att_len; }
+        return;
+    }
     const uint32_t prefix = 12 + ml + 1 + vl;
     const uint32_t resp_len = prefix + msg_len + a.att_len;
-    uint8_t* out = B.resp + slot_off + a.pad;
     uint32_t crc_be = 0;
     if (r_cks_type == B2_CHECKSUM_TYPE_CRC32C) {
         // Crc32cCompute (policy/crc32c_checksum.cpp:28-42) over the serialized EchoResponse

@@ -278,6 +278,13 @@ int  b2_snappy_uncompress_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
                                 const uint32_t* offs, const uint32_t* lens, uint32_t n,
                                 void* out, uint32_t out_cap, uint32_t* out_offs, int32_t* out_lens);
 
+/* b2_snappy_compress_batch: butil::snappy::Compress (snappy.cc:875-956), BIT-EXACT with the vendored
+ * 1.1.3 encoder, on each (offset,length) slice.  Output i goes to out + out_offs[i] (filled by the
+ * call: slots of MaxCompressedLength, 16-byte aligned), out_lens[i] = compressed size. */
+int  b2_snappy_compress_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
+                              const uint32_t* offs, const uint32_t* lens, uint32_t n,
+                              void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens);
+
 /* ---- counters (bvar::Adder-like): per-GPU totals accumulated by
  * the kernels: [0] in_bytes [1] in_msgs [2] out_bytes [3] out_msgs [4] errors
  * [5] batches [6..7] reserved.  The cross-GPU reduce is an NCCL all-reduce on
