@@ -13,6 +13,8 @@ RUN_DT = np.dtype([("socket_id", "<u8"), ("offset", "<u4"), ("length", "<u4"),
                    ("preferred_proto", "<i4"), ("flags", "<u4")])
 RUN_STATUS_DT = np.dtype([("consumed", "<u4"), ("parse_error", "<u4"), ("n_msgs", "<u4"), ("first_msg", "<u4"),
                           ("preferred_proto", "<i4"), ("reserved0", "<u4"), ("resp_off", "<u4"), ("resp_bytes", "<u4")])
+H2_FRAME_DT = np.dtype([("type", "u1"), ("flags", "u1"), ("pad", "<u2"), ("stream_id", "<u4"), ("payload_off", "<u4"), ("payload_len", "<u4")])
+HPACK_BLOCK_DT = np.dtype([("conn", "<u4"), ("offset", "<u4"), ("length", "<u4"), ("reserved", "<u4")])
 MSG_DT = np.dtype([("run_idx", "<u4"), ("frame_off", "<u4"), ("body_size", "<u4"), ("meta_size", "<u4"),
                    ("correlation_id", "<i8"), ("log_id", "<i8"),
                    ("attachment_size", "<i4"), ("compress_type", "<i4"), ("checksum_type", "<i4"), ("error_code", "<i4"),
@@ -75,6 +77,11 @@ def _load():
                                              C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     l.b2_snappy_compress_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                            C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    l.b2_hpack_reset.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    l.b2_hpack_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
+    l.b2_h2_scan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
     l.b2_counters_read.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     l.b2_counters_device_ptr.restype = C.c_void_p; l.b2_counters_device_ptr.argtypes = [C.c_void_p]
     return l
@@ -86,7 +93,7 @@ lib = _load()
 ABI_SYMBOLS = ["b2_ctx_create", "b2_ctx_destroy", "b2_last_error", "b2_version", "b2_register_method",
                "b2_set_server_identity", "b2_block_alloc", "b2_block_free", "b2_process_batch", "b2_batch_submit", "b2_batch_collect", "b2_batch_upload",
                "b2_batch_execute", "b2_batch_execute_many", "b2_batch_download", "b2_batch_launch", "b2_batch_wait",
-               "b2_elapsed_ms", "b2_stage_times", "b2_crc32c_batch", "b2_snappy_uncompress_batch", "b2_snappy_compress_batch", "b2_counters_read",
+               "b2_elapsed_ms", "b2_stage_times", "b2_crc32c_batch", "b2_snappy_uncompress_batch", "b2_snappy_compress_batch", "b2_hpack_reset", "b2_hpack_decode_batch", "b2_h2_scan_batch", "b2_counters_read",
                "b2_counters_device_ptr"]
 
 ECHO_METHOD = dict(service_full_name=b"example.EchoService", service_name=b"EchoService", method_name=b"Echo",
@@ -259,6 +266,37 @@ class Context:
         _check(lib.b2_snappy_compress_batch(self._h, data.ctypes.data, data.nbytes, offs.ctypes.data, lens.ctypes.data, n,
                                             out.ctypes.data, out_cap, ooffs.ctypes.data, olens.ctypes.data))
         return [out[ooffs[i]:ooffs[i] + olens[i]].tobytes() for i in range(n)]
+
+    def hpack_reset(self, conn, max_table_size=4096):
+        _check(lib.b2_hpack_reset(self._h, conn, max_table_size))
+
+    def hpack_decode_batch(self, data, blocks, per_block_cap=4096):
+        """blocks: list of (conn, offset, length).  Returns [(status, [(name, value), ...]), ...]."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        b = np.zeros(len(blocks), HPACK_BLOCK_DT)
+        for i, (c, o, n) in enumerate(blocks):
+            b[i] = (c, o, n, 0)
+        n = len(blocks)
+        out = np.zeros(max(1, n * per_block_cap), np.uint8); ol = np.zeros(n, np.uint32); st = np.zeros(n, np.int32); nh = np.zeros(n, np.uint32)
+        _check(lib.b2_hpack_decode_batch(self._h, data.ctypes.data, data.nbytes, b.ctypes.data, n, out.ctypes.data, per_block_cap,
+                                         ol.ctypes.data, st.ctypes.data, nh.ctypes.data))
+        res = []
+        for i in range(n):
+            buf = out[i * per_block_cap:i * per_block_cap + ol[i]]; o = 0; hs = []
+            while o < len(buf):
+                nl = int(buf[o]) | (int(buf[o + 1]) << 8); vl = int(buf[o + 2]) | (int(buf[o + 3]) << 8)
+                hs.append((buf[o + 4:o + 4 + nl].tobytes(), buf[o + 4 + nl:o + 4 + nl + vl].tobytes())); o += 4 + nl + vl
+            assert len(hs) == nh[i]
+            res.append((int(st[i]), hs))
+        return res
+
+    def h2_scan_batch(self, data, runs, max_frame_size=16384, cap_per_run=256):
+        data = np.ascontiguousarray(data, dtype=np.uint8); runs = np.ascontiguousarray(runs, dtype=RUN_DT)
+        n = len(runs)
+        frames = np.zeros(max(1, n * cap_per_run), H2_FRAME_DT); nf = np.zeros(n, np.uint32); cons = np.zeros(n, np.uint32); err = np.zeros(n, np.uint32)
+        _check(lib.b2_h2_scan_batch(self._h, data.ctypes.data, data.nbytes, runs.ctypes.data, n, max_frame_size, frames.ctypes.data, cap_per_run,
+                                    nf.ctypes.data, cons.ctypes.data, err.ctypes.data))
+        return [frames[i * cap_per_run:i * cap_per_run + min(int(nf[i]), cap_per_run)] for i in range(n)], nf, cons, err
 
     def counters(self):
         out = (C.c_int64 * 8)()

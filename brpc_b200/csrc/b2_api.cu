@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include "b2_kernels.cuh"
+#include "b2_h2.cuh"
 
 using namespace b2;
 
@@ -36,7 +37,7 @@ struct b2_ctx {
     uint8_t* d_bytes = nullptr; b2_run* d_runs = nullptr; uint32_t* d_run_tile_base = nullptr;
     TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; uint32_t* d_tile_scratch = nullptr; b2_run_status* d_run_status = nullptr;
     uint32_t* d_frame_off = nullptr; uint32_t* d_frame_run = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr; PackJob* d_jobs = nullptr; uint8_t* d_heads = nullptr;
-    uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr; uint8_t* d_unz = nullptr; uint16_t* d_snappy_tab = nullptr;
+    uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr; uint8_t* d_unz = nullptr; uint16_t* d_snappy_tab = nullptr; HpackState* d_hpack = nullptr;
     uint32_t* d_crc_adv = nullptr; unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
     uint32_t max_tiles = 0; uint32_t n_sms = 148; bool use_tma_pack = true;
     // pinned host mirrors
@@ -83,7 +84,7 @@ extern "C" void b2_ctx_destroy(b2_ctx* c) {
     cudaSetDevice(c->opt.device);
     cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch);
     cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_frame_run); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_heads); cudaFree(c->d_slot);
-    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
+    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_hpack); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
     cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
     cudaFreeHost(c->h_run_tile_base);
     for (int i = 0; i <= kMaxStages; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -140,6 +141,8 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     ALLOC(c->d_resp, (size_t)c->opt.max_resp_bytes + 1024);
     ALLOC(c->d_unz, 2 * (size_t)c->opt.max_resp_bytes + 1024);
     ALLOC(c->d_snappy_tab, (size_t)kSnappyWarps * kSnappyMaxTable * 2);
+    ALLOC(c->d_hpack, sizeof(HpackState) * (size_t)B2_HPACK_MAX_CONNS);
+    CU(cudaMemset(c->d_hpack, 0, sizeof(HpackState) * (size_t)B2_HPACK_MAX_CONNS));
     ALLOC(c->d_counters, 8 * B2_N_COUNTERS);
     ALLOC(c->d_totals, 16);
     ALLOC(c->d_methods, sizeof(DevMethod) * 64);
@@ -567,6 +570,66 @@ extern "C" int b2_snappy_compress_batch(b2_ctx* c, const void* bytes, uint32_t n
     if (n) k_snappy_compress_batch<<<c->n_sms * 4, 256, 0, c->stream>>>(c->d_bytes, d_offs, d_lens, n, c->d_unz, d_ooffs, d_olens, c->d_snappy_tab);
     CU(cudaMemcpyAsync(out_lens, d_olens, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     if (total) CU(cudaMemcpyAsync(out, c->d_unz, total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->uploaded = false; c->executed = false;
+    return B2_OK;
+}
+
+extern "C" int b2_hpack_reset(b2_ctx* c, uint32_t conn, uint32_t max_table_size) {
+    if (!c || conn >= B2_HPACK_MAX_CONNS || max_table_size > 4096) { set_err("bad connection / table size"); return B2_E_INVAL; }
+    CU(cudaSetDevice(c->opt.device));
+    k_hpack_reset<<<1, 1, 0, c->stream>>>(c->d_hpack, conn, max_table_size);
+    CU(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
+extern "C" int b2_hpack_decode_batch(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_hpack_block* blocks, uint32_t n,
+                                     void* out, uint32_t per_block_cap, uint32_t* out_lens, int32_t* status, uint32_t* n_headers) {
+    if (!c || !bytes || !blocks || !out || !out_lens || !status || !n_headers) { set_err("null argument"); return B2_E_INVAL; }
+    if (nbytes > c->opt.max_batch_bytes || n > c->opt.max_msgs / 4 || (uint64_t)n * per_block_cap > c->opt.max_resp_bytes) { set_err("exceeds ctx capacity"); return B2_E_CAPACITY; }
+    std::vector<uint32_t> conn(n), off(n), len(n), first;
+    for (uint32_t i = 0; i < n; i++) {
+        if (blocks[i].conn >= B2_HPACK_MAX_CONNS || (uint64_t)blocks[i].offset + blocks[i].length > nbytes) { set_err("bad block"); return B2_E_INVAL; }
+        conn[i] = blocks[i].conn; off[i] = blocks[i].offset; len[i] = blocks[i].length;
+        if (i == 0 || conn[i] != conn[i - 1]) first.push_back(i);
+    }
+    const uint32_t n_groups = (uint32_t)first.size();
+    first.push_back(n);
+    for (uint32_t g = 0; g < n_groups; g++)                       // a connection may appear in one group only
+        for (uint32_t g2 = g + 1; g2 < n_groups; g2++) if (conn[first[g]] == conn[first[g2]]) { set_err("blocks of one connection must be adjacent"); return B2_E_INVAL; }
+    CU(cudaSetDevice(c->opt.device));
+    uint32_t* d_conn = c->d_frame_off; uint32_t* d_off = c->d_frame_run; uint32_t* d_len = c->d_slot;
+    uint32_t* d_first = (uint32_t*)c->d_jobs; uint32_t* d_olens = (uint32_t*)c->d_aux; int32_t* d_st = (int32_t*)c->d_aux + n; uint32_t* d_nh = (uint32_t*)c->d_aux + 2 * (size_t)n;
+    CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_conn, conn.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_off, off.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_len, len.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_first, first.data(), 4 * first.size(), cudaMemcpyHostToDevice, c->stream));
+    if (n_groups) k_hpack_decode<<<(n_groups + 63) / 64, 64, 0, c->stream>>>(c->d_bytes, d_conn, d_off, d_len, d_first, n_groups, c->d_hpack, c->d_unz, per_block_cap, d_olens, d_st, d_nh);
+    CU(cudaMemcpyAsync(out_lens, d_olens, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(status, d_st, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(n_headers, d_nh, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (n) CU(cudaMemcpyAsync(out, c->d_unz, (size_t)n * per_block_cap, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->uploaded = false; c->executed = false;
+    return B2_OK;
+}
+
+extern "C" int b2_h2_scan_batch(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs, uint32_t max_frame_size,
+                                b2_h2_frame* frames, uint32_t cap_per_run, uint32_t* n_frames, uint32_t* consumed, uint32_t* err) {
+    if (!c || !bytes || !runs || !frames || !n_frames || !consumed || !err) { set_err("null argument"); return B2_E_INVAL; }
+    if (nbytes > c->opt.max_batch_bytes || n_runs > c->opt.max_runs || (uint64_t)n_runs * cap_per_run * sizeof(b2_h2_frame) > c->opt.max_resp_bytes) { set_err("exceeds ctx capacity"); return B2_E_CAPACITY; }
+    for (uint32_t r = 0; r < n_runs; r++) if ((uint64_t)runs[r].offset + runs[r].length > nbytes) { set_err("run outside buffer"); return B2_E_INVAL; }
+    CU(cudaSetDevice(c->opt.device));
+    static_assert(sizeof(b2_h2_frame) == sizeof(H2Frame), "frame layout");
+    uint32_t* d_n = c->d_frame_off; uint32_t* d_cons = c->d_frame_run; uint32_t* d_err = c->d_slot;
+    CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_meta, runs, sizeof(b2_run) * (size_t)n_runs, cudaMemcpyHostToDevice, c->stream));
+    if (n_runs) k_h2_scan<<<(n_runs + 63) / 64, 64, 0, c->stream>>>(c->d_bytes, (const b2_run*)c->d_meta, n_runs, max_frame_size, (H2Frame*)c->d_unz, cap_per_run, d_n, d_cons, d_err);
+    CU(cudaMemcpyAsync(n_frames, d_n, 4 * (size_t)n_runs, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(consumed, d_cons, 4 * (size_t)n_runs, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(err, d_err, 4 * (size_t)n_runs, cudaMemcpyDeviceToHost, c->stream));
+    if (n_runs) CU(cudaMemcpyAsync(frames, c->d_unz, (size_t)n_runs * cap_per_run * sizeof(b2_h2_frame), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->uploaded = false; c->executed = false;
     return B2_OK;

@@ -285,6 +285,28 @@ int  b2_snappy_compress_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
                               const uint32_t* offs, const uint32_t* lens, uint32_t n,
                               void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens);
 
+/* ---- h2 / gRPC building blocks (the stream state machine stays on the host) -----
+ * b2_h2_scan_batch: H2Context::ConsumeFrameHead (src/brpc/policy/http2_rpc_protocol.cpp:438-465)
+ * chained over every connection run.  runs[i].flags & B2_RUN_H2_PREFACE: the run starts a server-side
+ * connection, the 24-byte client preface (:119-120, :469-479) is checked and skipped first.
+ * frames of run i land at frames[i * cap_per_run ...]; err[i] is a B2_PARSE_ERROR_*. */
+#define B2_RUN_H2_PREFACE 2u
+typedef struct b2_h2_frame { uint8_t type, flags; uint16_t pad; uint32_t stream_id, payload_off, payload_len; } b2_h2_frame;
+int  b2_h2_scan_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs,
+                      uint32_t max_frame_size, b2_h2_frame* frames, uint32_t cap_per_run,
+                      uint32_t* n_frames, uint32_t* consumed, uint32_t* err);
+/* b2_hpack_decode_batch: HPacker::Decode (src/brpc/details/hpack.cpp:765-843) looped over header
+ * blocks like H2StreamContext::ConsumeHeaders (http2_rpc_protocol.cpp:1221-1232).  Blocks of one
+ * connection must be adjacent and in wire order; every connection (0 .. B2_HPACK_MAX_CONNS-1) owns a
+ * dynamic table that persists across calls (b2_hpack_reset starts a new connection).  Block i's
+ * records (u16 name_len, u16 value_len, name, value) land at out + i * per_block_cap.
+ * status[i]: 0 consumed, 1 ran out of bytes inside a field, -1 malformed, -2 per_block_cap exceeded. */
+#define B2_HPACK_MAX_CONNS 4096
+typedef struct b2_hpack_block { uint32_t conn, offset, length, reserved; } b2_hpack_block;
+int  b2_hpack_reset(b2_ctx* ctx, uint32_t conn, uint32_t max_table_size);
+int  b2_hpack_decode_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_hpack_block* blocks, uint32_t n_blocks,
+                           void* out, uint32_t per_block_cap, uint32_t* out_lens, int32_t* status, uint32_t* n_headers);
+
 /* ---- counters (bvar::Adder-like): per-GPU totals accumulated by
  * the kernels: [0] in_bytes [1] in_msgs [2] out_bytes [3] out_msgs [4] errors
  * [5] batches [6..7] reserved.  The cross-GPU reduce is an NCCL all-reduce on

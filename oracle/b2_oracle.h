@@ -117,3 +117,28 @@ int orc_process_batch(const orc_config* cfg, const uint8_t* bytes, uint32_t nbyt
 }
 #endif
 #endif
+
+/* ---- HPACK (h2 header compression), a15 ------------------------------------------------------
+ * Restates HPacker::Decode (src/brpc/details/hpack.cpp:765-843), DecodeWithKnownPrefix (:733-763),
+ * DecodeInteger (:531-565), DecodeString + HuffmanDecoder (:606-635, :403-473) and the decoder's
+ * IndexTable (:72-229).  One orc_hpack holds a connection's dynamic table. */
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct orc_hpack orc_hpack;
+orc_hpack* orc_hpack_new(uint32_t max_table_size);
+void orc_hpack_free(orc_hpack*);
+/* Decode a whole header block the way H2StreamContext::ConsumeHeaders loops HPacker::Decode
+ * (policy/http2_rpc_protocol.cpp:1221-1232).  Output records: u16 name_len, u16 value_len, name, value.
+ * Returns 0 = block consumed, 1 = ran out of bytes inside a field (rc == 0), -1 = error. */
+int orc_hpack_decode_block(orc_hpack* h, const uint8_t* in, uint32_t n, uint8_t* out, uint32_t out_cap,
+                           uint32_t* out_len, uint32_t* n_headers);
+/* H2Context::ConsumeFrameHead (policy/http2_rpc_protocol.cpp:438-465) chained over a byte run:
+ * fills frames[i] = {type, flags, stream_id, payload_off, payload_len}; returns the count, sets
+ * *consumed and *err (B2_PARSE_ERROR_NOT_ENOUGH_DATA normally, ABSOLUTELY_WRONG on a bad head). */
+typedef struct orc_h2_frame { uint8_t type, flags; uint16_t pad; uint32_t stream_id, payload_off, payload_len; } orc_h2_frame;
+uint32_t orc_h2_scan(const uint8_t* in, uint32_t n, uint32_t max_frame_size, orc_h2_frame* frames, uint32_t cap,
+                     uint32_t* consumed, uint32_t* err);
+#ifdef __cplusplus
+}
+#endif

@@ -167,3 +167,41 @@ def process_batch(cfg, data, runs, msg_cap=None, resp_cap=None):
                                msgs.ctypes.data, msg_cap, C.byref(nm), resp.ctypes.data, resp_cap, C.byref(rb))
     assert rc == 0, "oracle capacity exceeded"
     return rs, msgs[:nm.value], resp[:rb.value]
+
+
+# ---- HPACK / h2 (a15) ----
+H2_FRAME_DT = np.dtype([("type", "u1"), ("flags", "u1"), ("pad", "<u2"), ("stream_id", "<u4"), ("payload_off", "<u4"), ("payload_len", "<u4")])
+lib.orc_hpack_new.restype = C.c_void_p; lib.orc_hpack_new.argtypes = [C.c_uint32]
+lib.orc_hpack_free.argtypes = [C.c_void_p]
+lib.orc_hpack_decode_block.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+lib.orc_h2_scan.restype = C.c_uint32
+lib.orc_h2_scan.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+
+
+def parse_header_records(buf):
+    out, o = [], 0
+    while o < len(buf):
+        nl = buf[o] | (buf[o + 1] << 8); vl = buf[o + 2] | (buf[o + 3] << 8)
+        out.append((bytes(buf[o + 4:o + 4 + nl]), bytes(buf[o + 4 + nl:o + 4 + nl + vl]))); o += 4 + nl + vl
+    return out
+
+
+class HPack:
+    def __init__(self, max_table_size=4096):
+        self.h = lib.orc_hpack_new(max_table_size)
+
+    def decode_block(self, b):
+        cap = 1 << 20
+        out = C.create_string_buffer(cap); ol, nh = C.c_uint32(), C.c_uint32()
+        st = lib.orc_hpack_decode_block(self.h, bytes(b), len(b), out, cap, C.byref(ol), C.byref(nh))
+        return st, parse_header_records(out.raw[:ol.value])
+
+    def __del__(self):
+        lib.orc_hpack_free(self.h)
+
+
+def h2_scan(b, max_frame_size=16384):
+    cap = len(b) // 9 + 2
+    fr = np.zeros(cap, H2_FRAME_DT); consumed, err = C.c_uint32(), C.c_uint32()
+    n = lib.orc_h2_scan(bytes(b), len(b), max_frame_size, fr.ctypes.data, cap, C.byref(consumed), C.byref(err))
+    return fr[:n], consumed.value, err.value
