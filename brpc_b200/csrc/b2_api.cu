@@ -146,7 +146,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     ALLOC(c->d_counters, 8 * B2_N_COUNTERS);
     ALLOC(c->d_totals, 16);
     ALLOC(c->d_methods, sizeof(DevMethod) * 64);
-    ALLOC(c->d_crc_adv, 6 * 4 * 256 * 4);
+    ALLOC(c->d_crc_adv, (kCrcHotWords + kCrcTreeWords) * 4);
     ALLOC(c->d_meta, (size_t)o->max_runs * 28 + 64);
     ALLOC(c->d_small, kSmallBlock);
     HALLOC(c->h_meta, (size_t)o->max_runs * 28 + 64);
@@ -163,16 +163,15 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     CU(cudaEventCreate(&c->ev_first)); CU(cudaEventCreate(&c->ev_last));
     crc_table_init();
     CU(cudaMemcpyToSymbol(c_crc_table, g_crc_tab_host, sizeof g_crc_tab_host));
-    {   // ADV_{4<<t}: the register advanced over 4, 8, ..., 128 zero bytes, as 4x256 byte-sliced tables
-        std::vector<uint32_t> adv(6 * 4 * 256);
-        for (int t = 0; t < 6; t++)
-            for (int j = 0; j < 4; j++)
-                for (uint32_t b = 0; b < 256; b++) {
-                    uint32_t x = b << (8 * j);
-                    for (int k = 0; k < (4 << t); k++) x = g_crc_tab_host[x & 0xff] ^ (x >> 8);
-                    adv[(t * 4 + j) * 256 + b] = x;
-                }
-        CU(cudaMemcpy(c->d_crc_adv, adv.data(), adv.size() * 4, cudaMemcpyHostToDevice));
+    {   // warp-CRC tables: T[k][b] = byte b followed by k zero bytes (k = 0..15), A512 = advance by 512 zero bytes,
+        // tree t = advance by 16 << t zero bytes; the advance operators are stored byte-sliced (4 x 256)
+        std::vector<uint32_t> tab(kCrcHotWords + kCrcTreeWords);
+        auto adv = [&](uint32_t x, int bytes) { for (int k = 0; k < bytes; k++) x = g_crc_tab_host[x & 0xff] ^ (x >> 8); return x; };
+        for (int k = 0; k < 16; k++) for (uint32_t b = 0; b < 256; b++) tab[k * 256 + b] = adv(g_crc_tab_host[b], k);
+        for (int j = 0; j < 4; j++) for (uint32_t b = 0; b < 256; b++) tab[(16 + j) * 256 + b] = adv(b << (8 * j), 512);
+        for (int t = 0; t < 5; t++) for (int j = 0; j < 4; j++) for (uint32_t b = 0; b < 256; b++)
+            tab[kCrcHotWords + (t * 4 + j) * 256 + b] = adv(b << (8 * j), 16 << t);
+        CU(cudaMemcpy(c->d_crc_adv, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
     }
     CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k_pack_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PackWarpSmem) * kPackWarps)));
@@ -301,7 +300,7 @@ static int launch_pipeline(b2_ctx* c) {
     k_scan_top<<<1, 1024, 0, s>>>(B); launches++; mark("scan");
     if (c->use_tma_pack) {
         k_pack_tma<<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C); launches++; mark("pack");
-        k_pack_slow<<<sms * B2_PACK_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack_slow");
+        k_pack_slow<<<sms * B2_SLOW_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack_slow");
     } else { k_pack<<<sms * B2_PACK_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack"); }
     k_finalize<<<(c->n_runs + 255) / 256, 256, 0, s>>>(B); launches++; mark("finalize");
     if (!prof) { c->stage_names[0] = "pipeline"; cudaEventRecord(c->ev[1], s); st = 1; }
@@ -472,9 +471,12 @@ extern "C" void* b2_debug_resp_device_ptr(b2_ctx* c) { return c ? (void*)c->d_re
 
 __global__ void k_crc32c_batch(const uint8_t* bytes, const uint32_t* offs, const uint32_t* lens, uint32_t n, uint32_t* out,
                                const uint32_t* adv) {
+    __shared__ uint32_t s_hot[kCrcHotWords];
+    crc_tabs_to_smem(s_hot, adv);
+    CrcTabs ct; ct.hot = s_hot; ct.tree = adv + kCrcHotWords;
     const uint32_t lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += n_warps) {
-        const uint32_t c = warp_crc32c_update(0xffffffffu, bytes + offs[i], lens[i], lane, adv) ^ 0xffffffffu;
+        const uint32_t c = warp_crc32c_update(0xffffffffu, bytes + offs[i], lens[i], lane, ct) ^ 0xffffffffu;
         if (lane == 0) out[i] = c;
     }
 }

@@ -101,7 +101,7 @@ struct BatchPtrs {
     unsigned long long* counters;    // int64[B2_N_COUNTERS]
     uint32_t* totals;                // [0]=n_msgs [1]=resp_bytes [2]=overflow flags
     const DevMethod* methods;
-    const uint32_t* crc_adv;         // [6][4][256] ADV_{4<<t} tables of the warp CRC
+    const uint32_t* crc_adv;         // warp CRC tables: hot [20][256] then tree [5][4][256]
     uint32_t n_runs, n_tiles, max_msgs, max_resp;
 };
 
@@ -996,41 +996,73 @@ __device__ __forceinline__ uint32_t crc32c_bytes_serial(uint32_t l, const uint8_
 // CRC-32C as a warp-level primitive (butil::crc32c::Extend, src/butil/crc32c.cc:379-454, without
 // the 0xffffffff pre/post inversion: this works on the raw register `l`).
 // The CRC register is linear over GF(2): update(l, A||B) = ADV_|B|(update(l, A)) ^ update(0, B),
-// where ADV_k advances the register over k zero bytes.  adv[t] are 4x256 lookup tables of
-// ADV_{4<<t}, t = 0..5 (4, 8, 16, 32, 64, 128 bytes).  Lane i takes every 32nd aligned 4-byte
-// word (coalesced 128 B rows): R_i = ADV_128(R_i) ^ ADV_4(word); the words are front-padded with
-// virtual zero words (no-ops on a zero register) so that the last word sits in lane 31, the
-// incoming register value is XORed into the first four message bytes, a 5-level shuffle tree
-// with ADV_4..ADV_64 folds the 32 lanes, and the <= 3 trailing bytes finish serially.
-__device__ __forceinline__ uint32_t crc_adv(const uint32_t* __restrict__ T, uint32_t x) {
-    return __ldg(T + (x & 0xff)) ^ __ldg(T + 256 + ((x >> 8) & 0xff)) ^ __ldg(T + 512 + ((x >> 16) & 0xff)) ^ __ldg(T + 768 + (x >> 24));
+// where ADV_k advances the register over k zero bytes.  Lane i takes every 32nd aligned 16-byte
+// block (one coalesced 512-byte row per warp load): R_i = ADV_512(R_i) ^ S16(block), S16 = the
+// slice-by-16 table sum of the block's bytes.  The blocks are front-padded with virtual zero
+// blocks (no-ops on a zero register) so that the last block sits in lane 31, the incoming
+// register is XORed into the first four message bytes, a 5-level shuffle tree with
+// ADV_16..ADV_256 folds the 32 lanes, and the <= 15 trailing bytes finish serially.
+// Tables (built on the host): hot = T[16][256] (T[k][b] = byte b followed by k zero bytes) then
+// A512[4][256]; tree = ADV_{16<<t}[4][256], t = 0..4.  `hot` may live in shared memory.
+constexpr uint32_t kCrcHotWords = 20 * 256, kCrcTreeWords = 5 * 4 * 256;
+struct CrcTabs { const uint32_t* hot; const uint32_t* tree; };
+__device__ __forceinline__ uint32_t crc_adv4(const uint32_t* T, uint32_t x) {      // 4x256 byte-sliced operator
+    return T[x & 0xff] ^ T[256 + ((x >> 8) & 0xff)] ^ T[512 + ((x >> 16) & 0xff)] ^ T[768 + (x >> 24)];
 }
-__device__ __forceinline__ uint32_t warp_crc32c_update(uint32_t l, const uint8_t* p, uint32_t n, uint32_t lane,
-                                                       const uint32_t* __restrict__ adv) {
-    if (n < 8) return crc32c_bytes_serial(l, p, n);                 // (uniform across the warp)
-    const uint32_t lead = (uint32_t)((uintptr_t)p & 3u);
-    const uint32_t* a0 = reinterpret_cast<const uint32_t*>(p - lead);
-    const uint32_t W = (lead + n) >> 2, tailn = (lead + n) & 3u;
+__device__ __forceinline__ uint32_t crc_s16(const uint32_t* T, const uint4& v) {
+    uint32_t r = 0;
+    #pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t w = j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w;
+        r ^= T[(15 - 4 * j) * 256 + (w & 0xff)] ^ T[(14 - 4 * j) * 256 + ((w >> 8) & 0xff)] ^
+             T[(13 - 4 * j) * 256 + ((w >> 16) & 0xff)] ^ T[(12 - 4 * j) * 256 + (w >> 24)];
+    }
+    return r;
+}
+__device__ __forceinline__ uint32_t warp_crc32c_update(uint32_t l, const uint8_t* p, uint32_t n, uint32_t lane, const CrcTabs& ct) {
+    const uint32_t lead = (uint32_t)((uintptr_t)p & 15u);
+    if (lead + n < 48) return crc32c_bytes_serial(l, p, n);          // (uniform across the warp)
+    const uint4* a0 = reinterpret_cast<const uint4*>(p - lead);
+    const uint32_t W = (lead + n) >> 4, tailn = (lead + n) & 15u;    // whole 16-byte blocks from a0
     const uint32_t off = (32u - (W & 31u)) & 31u, rows = (W + off) >> 5;
     uint32_t R = 0;
     for (uint32_t r = 0; r < rows; r++) {
         const int32_t v = (int32_t)(r * 32 + lane) - (int32_t)off;
-        uint32_t w = 0;
+        uint4 blk = make_uint4(0, 0, 0, 0);
         if (v >= 0) {
-            w = __ldg(a0 + v);
-            if (v == 0) { w &= 0xffffffffu << (8 * lead); w ^= l << (8 * lead); }
-            else if (v == 1 && lead) w ^= l >> (32 - 8 * lead);
+            blk = __ldg(a0 + v);
+            if (v <= 1) {
+                // the incoming register lands on message bytes 0..3 = virtual bytes lead..lead+3 (blocks 0 and 1);
+                // the bytes in front of the message are zeroed
+                uint32_t w[4] = { blk.x, blk.y, blk.z, blk.w };
+                #pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int byte0 = v * 16 + k * 4;
+                    #pragma unroll
+                    for (int bb = 0; bb < 4; bb++) {
+                        const int vi = byte0 + bb;
+                        if (vi < (int)lead) w[k] &= ~(0xffu << (8 * bb));
+                        else if (vi < (int)lead + 4) w[k] ^= ((l >> (8 * (vi - (int)lead))) & 0xffu) << (8 * bb);
+                    }
+                }
+                blk = make_uint4(w[0], w[1], w[2], w[3]);
+            }
         }
-        R = crc_adv(adv + 5 * 1024, R) ^ crc_adv(adv, w);
+        R = crc_adv4(ct.hot + 16 * 256, R) ^ crc_s16(ct.hot, blk);
     }
     #pragma unroll
     for (int t = 0; t < 5; t++) {
         const uint32_t d = 1u << t;
         const uint32_t left = __shfl_up_sync(0xffffffffu, R, d);
-        if ((lane & (2 * d - 1)) == 2 * d - 1) R = crc_adv(adv + t * 1024, left) ^ R;
+        if ((lane & (2 * d - 1)) == 2 * d - 1) R = crc_adv4(ct.tree + t * 1024, left) ^ R;
     }
     R = __shfl_sync(0xffffffffu, R, 31);
     return crc32c_bytes_serial(R, reinterpret_cast<const uint8_t*>(a0 + W), tailn);
+}
+// stage the hot tables into shared memory (all threads of the block cooperate)
+__device__ __forceinline__ void crc_tabs_to_smem(uint32_t* s_hot, const uint32_t* g_hot) {
+    for (uint32_t i = threadIdx.x; i < kCrcHotWords; i += blockDim.x) s_hot[i] = g_hot[i];
+    __syncthreads();
 }
 
 // byte j of the base-128 varint of v (n bytes long)
@@ -1144,18 +1176,22 @@ __device__ __forceinline__ void write_echo_prefix(uint8_t* out, uint32_t lane, i
     }
 }
 
-__device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t lane);
+struct CrcTabs;
+__device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t lane, const CrcTabs& ct);
 
 // persistent: a fixed grid (multiple of the SM count); every warp strides over the messages
 __global__ void __launch_bounds__(256, B2_PACK_MIN_BLOCKS) k_pack(BatchPtrs B, DevConfig C) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_msgs = B.totals[0];
     if (B.totals[2] & 3u) return;
+    __shared__ uint32_t s_hot[kCrcHotWords];
+    crc_tabs_to_smem(s_hot, B.crc_adv);
+    CrcTabs ct; ct.hot = s_hot; ct.tree = B.crc_adv + kCrcHotWords;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_msgs; i += n_warps) pack_one(B, C, i, lane);
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_msgs; i += n_warps) pack_one(B, C, i, lane, ct);
 }
 
-__device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t lane) {
+__device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t lane, const CrcTabs& ct) {
     const uint32_t bi = i / (kScanBlock * kScanItems);
     const uint32_t slot_off = B.slot[i] + B.scan_tmp[bi];
     const b2_msg_desc d = B.msgs[i];
@@ -1167,7 +1203,7 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
         bool ok = true;
         const uint8_t* body = frame + 12 + d.meta_size; const uint32_t body_len = a.att_off;
         if (d.checksum_type == B2_CHECKSUM_TYPE_CRC32C) {
-            const uint32_t crc = warp_crc32c_update(0xffffffffu, body, body_len, lane, B.crc_adv) ^ 0xffffffffu;
+            const uint32_t crc = warp_crc32c_update(0xffffffffu, body, body_len, lane, ct) ^ 0xffffffffu;
             ok = crc == crc32c_unmask(load_be32(frame + a.cks_off));
         }
         uint32_t off = d.resp_off, len = d.resp_len;
@@ -1190,7 +1226,7 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
         // Crc32cVerify (policy/crc32c_checksum.cpp:44-61) over body_wo_att
         const uint32_t req_size = d.body_size - d.meta_size;
         int64_t bwo = (int64_t)req_size - (int64_t)d.attachment_size; if (bwo > (int64_t)req_size) bwo = req_size;
-        const uint32_t crc = warp_crc32c_update(0xffffffffu, frame + 12 + d.meta_size, (uint32_t)bwo, lane, B.crc_adv) ^ 0xffffffffu;
+        const uint32_t crc = warp_crc32c_update(0xffffffffu, frame + 12 + d.meta_size, (uint32_t)bwo, lane, ct) ^ 0xffffffffu;
         if (crc != crc32c_unmask(load_be32(frame + a.cks_off))) status = B2_MSG_ERROR_REPLIED;
     }
     const uint8_t* msg_src = frame + a.msg_off;
@@ -1239,7 +1275,7 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
         __syncwarp();
         uint32_t crc_be = 0;
         if (r_cks_type == B2_CHECKSUM_TYPE_CRC32C)
-            crc_be = crc32c_mask(warp_crc32c_update(0xffffffffu, out + prefix, clen, lane, B.crc_adv) ^ 0xffffffffu);
+            crc_be = crc32c_mask(warp_crc32c_update(0xffffffffu, out + prefix, clen, lane, ct) ^ 0xffffffffu);
         write_echo_prefix(out, lane, d.correlation_id, a.att_len, r_cks_type, cks_len, crc_be, frame + a.cks_off, msg_len, ml, vl, prefix,
                           r_compress, clen);
         if (a.att_len) warp_copy(out + prefix + clen, frame + a.att_off, a.att_len, lane);
@@ -1254,7 +1290,7 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
         uint32_t l = 0xffffffffu;
         uint8_t hdr[6]; hdr[0] = 0x0a; uint8_t* e = put_varint(hdr + 1, msg_len);
         l = crc32c_bytes_serial(l, hdr, (uint32_t)(e - hdr));
-        l = warp_crc32c_update(l, msg_src, msg_len, lane, B.crc_adv);
+        l = warp_crc32c_update(l, msg_src, msg_len, lane, ct);
         crc_be = crc32c_mask(l ^ 0xffffffffu);
     }
     write_echo_prefix(out, lane, d.correlation_id, a.att_len, r_cks_type, cks_len, crc_be, frame + a.cks_off, msg_len, ml, vl, prefix);
@@ -1423,16 +1459,22 @@ __global__ void __launch_bounds__(kPackWarps * 32, 1) k_pack_tma(BatchPtrs B, De
 // --- k_pack_slow: everything that is not a plain OK echo ----------------------
 // error replies, CRC32C verify/compute, snappy requests, split attachments: warp per message,
 // high occupancy (these are latency-bound), skipping the messages k_pack_tma moves.
-__global__ void __launch_bounds__(256, B2_PACK_MIN_BLOCKS) k_pack_slow(BatchPtrs B, DevConfig C) {
+#ifndef B2_SLOW_MIN_BLOCKS
+#define B2_SLOW_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs B, DevConfig C) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_msgs = B.totals[0];
     if ((B.totals[2] & 3u) || B.totals[3] == 0) return;
+    __shared__ uint32_t s_hot[kCrcHotWords];
+    crc_tabs_to_smem(s_hot, B.crc_adv);
+    CrcTabs ct; ct.hot = s_hot; ct.tree = B.crc_adv + kCrcHotWords;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t i0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; i0 < n_msgs; i0 += n_warps * 32) {
         // one coalesced look at 32 job flags, then the warp serves the slow ones in turn
         const uint32_t i = i0 + lane;
         const bool slow = i < n_msgs && reinterpret_cast<const uint8_t*>(B.jobs + i)[11] == 0;   // PackJob::fast
-        for (uint32_t m = __ballot_sync(0xffffffffu, slow); m; m &= m - 1) pack_one(B, C, i0 + (__ffs(m) - 1), lane);
+        for (uint32_t m = __ballot_sync(0xffffffffu, slow); m; m &= m - 1) pack_one(B, C, i0 + (__ffs(m) - 1), lane, ct);
     }
 }
 
