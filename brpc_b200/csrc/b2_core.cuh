@@ -315,6 +315,45 @@ B2_HD bool decode_rpc_meta(const uint8_t* p, uint32_t n, RpcMetaOut& o) {
     return true;
 }
 
+// Fast path for the exact shape PackRpcRequest emits (baidu_rpc_protocol.cpp:1045-1133): known fields in
+// ascending order, each at most once, one-byte tags and lengths:
+//   0a L { 0a sl <service> 12 ml <method> [18 log_id] }  [18 compress] [20 cid] [28 att] [50 content] [58 cktype] [62 len <bytes>]
+// Returns false on ANY deviation — the caller then runs decode_rpc_meta, which alone defines the semantics;
+// for inputs it accepts, the result is identical field by field (same varint / int32 truncation rules).
+B2_HD bool decode_rpc_meta_fast(const uint8_t* p, uint32_t n, RpcMetaOut& o) {
+    o.has = 0; o.correlation_id = 0; o.log_id = 0; o.compress_type = 0; o.attachment_size = 0;
+    o.checksum_type = 0; o.content_type = 0; o.error_code = 0;
+    o.service_name.off = o.service_name.len = 0; o.method_name = o.service_name; o.checksum_value = o.service_name;
+    if (n < 6 || p[0] != 0x0a) return false;
+    const uint32_t L = p[1];
+    if (L >= 128 || 2 + L > n) return false;
+    const uint8_t* q = p + 2; const uint8_t* e = q + L;
+    if (e - q < 2 || q[0] != 0x0a || q[1] >= 128 || (uint32_t)(e - q - 2) < q[1]) return false;
+    o.service_name.off = (uint32_t)(q + 2 - p); o.service_name.len = q[1]; q += 2 + q[1];
+    if (e - q < 2 || q[0] != 0x12 || q[1] >= 128 || (uint32_t)(e - q - 2) < q[1]) return false;
+    o.method_name.off = (uint32_t)(q + 2 - p); o.method_name.len = q[1]; q += 2 + q[1];
+    o.has = B2_HAS_REQUEST;
+    Reader r; uint64_t v;
+    if (q < e && *q == 0x18) { r.p = q + 1; r.end = e; if (!rd_varint(r, v)) return false; o.log_id = (int64_t)v; o.has |= B2_HAS_LOG_ID; q = r.p; }
+    if (q != e) return false;
+    r.p = e; r.end = p + n;
+    if (r.p < r.end && *r.p == 0x18) { r.p++; if (!rd_varint(r, v)) return false; o.compress_type = (int32_t)(uint32_t)v; o.has |= B2_HAS_COMPRESS_TYPE; }
+    if (r.p < r.end && *r.p == 0x20) { r.p++; if (!rd_varint(r, v)) return false; o.correlation_id = (int64_t)v; o.has |= B2_HAS_CORRELATION_ID; }
+    if (r.p < r.end && *r.p == 0x28) { r.p++; if (!rd_varint(r, v)) return false; o.attachment_size = (int32_t)(uint32_t)v; o.has |= B2_HAS_ATTACHMENT_SIZE; }
+    if (r.p < r.end && *r.p == 0x50) {
+        r.p++; if (!rd_varint(r, v)) return false;
+        const int32_t ct = (int32_t)(uint32_t)v;
+        if (ct < 0 || ct > 3) return false;                  // closed-enum corner: leave it to the generic decoder
+        o.content_type = ct; o.has |= B2_HAS_CONTENT_TYPE;
+    }
+    if (r.p < r.end && *r.p == 0x58) { r.p++; if (!rd_varint(r, v)) return false; o.checksum_type = (int32_t)(uint32_t)v; o.has |= B2_HAS_CHECKSUM_TYPE; }
+    if (r.p < r.end && *r.p == 0x62) {
+        if (r.end - r.p < 2 || r.p[1] >= 128 || (uint32_t)(r.end - r.p - 2) < r.p[1]) return false;
+        o.checksum_value.off = (uint32_t)(r.p + 2 - p); o.checksum_value.len = r.p[1]; o.has |= B2_HAS_CHECKSUM_VALUE; r.p += 2 + r.p[1];
+    }
+    return r.p == r.end;
+}
+
 struct StreamMetaOut { uint32_t has; int64_t stream_id, source_stream_id, consumed_size; int32_t frame_type; };
 
 B2_HD bool decode_stream_meta(const uint8_t* p, uint32_t n, StreamMetaOut& o) {

@@ -156,20 +156,21 @@ __global__ void __launch_bounds__(256) k_tile_search(BatchPtrs B, DevConfig C) {
         const uint32_t t0 = k << C.tile_shift;
         const uint32_t t1 = min(t0 + C.tile_bytes, len);
         // four 512-byte windows per trip: all eight loads of a lane are issued before the first use
-        for (uint32_t c0 = t0; c0 < t1 && entry == kNone; c0 += 2048) {
+        for (uint32_t c0 = t0; c0 < t1 && entry == kNone; c0 += (c0 == t0 ? 512u : 2048u)) {
+            const int nwin = c0 == t0 ? 1 : 4;      // the first 512-byte window usually holds the entry; later trips go 4 wide
             uint4 v[4]; uint32_t nx[4];
             #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const uint32_t p0 = c0 + u * 512 + lane * 16;
                 v[u] = make_uint4(0, 0, 0, 0); nx[u] = 0;
-                if (p0 < t1) {
+                if (u < nwin && p0 < t1) {
                     v[u] = __ldg(reinterpret_cast<const uint4*>(base + p0));        // bytes buffer is padded: safe past len
                     nx[u] = __ldg(reinterpret_cast<const uint32_t*>(base + p0 + 16));
                 }
             }
             #pragma unroll
             for (int u = 0; u < 4; u++) {
-                if (entry != kNone) break;
+                if (entry != kNone || u >= nwin) break;
                 // lane owns 16 positions [p0, p0+16); needs 3 more bytes for the last windows
                 const uint32_t w0 = c0 + u * 512, p0 = w0 + lane * 16;
                 const uint32_t w[5] = { v[u].x, v[u].y, v[u].z, v[u].w, nx[u] };
@@ -489,9 +490,15 @@ __global__ void __launch_bounds__(kDecodeWarps * 32, B2_DECODE_MIN_BLOCKS) k_dec
         for (uint32_t m2 = 0; m2 < nm; m2 += 2) {
             const uint32_t m = m2 + half;
             const uint32_t f = __shfl_sync(0xffffffffu, fo_raw, m & 31) & 0x7fffffffu;
-            if (m < nm && sub < kRowVecs)
-                S.row[m][sub] = __ldg(reinterpret_cast<const uint4*>(B.bytes + (f & ~15u)) + sub);   // (buffer is padded past its end)
+            if (m < nm && sub < kRowVecs) {
+                // cp.async (LDGSTS): global -> shared without a register round trip, so all 16 trips are in flight together
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.row[m][sub]);
+                const uint4* src = reinterpret_cast<const uint4*>(B.bytes + (f & ~15u)) + sub;       // (buffer is padded past its end)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         bool is_slow = false;
         if (i < n_msgs) { decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 15u), S.head[lane]); is_slow = B.jobs[i].fast == 0; }
@@ -538,7 +545,7 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
         }
     } else {
         RpcMetaOut m;
-        if (!decode_rpc_meta(meta_p, d.meta_size, m)) d.status = B2_MSG_BAD_META;
+        if (!decode_rpc_meta_fast(meta_p, d.meta_size, m) && !decode_rpc_meta(meta_p, d.meta_size, m)) d.status = B2_MSG_BAD_META;
         else {
             d.correlation_id = m.correlation_id; d.log_id = m.log_id; d.attachment_size = m.attachment_size;
             d.compress_type = m.compress_type; d.checksum_type = m.checksum_type; d.content_type = (uint8_t)m.content_type;

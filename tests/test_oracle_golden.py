@@ -145,3 +145,40 @@ def test_pb_fuzz_vectors(oracle):
         if ok:
             check_stream(m, rec["fields"])
     assert not bad, bad[:10]
+
+
+def test_meta_fast_path_agrees_with_generic_on_golden_vectors():
+    """decode_rpc_meta_fast (product, csrc/b2_core.cuh) is a host+device function: compiled here for the host,
+    it must either decline or agree with the generic decoder on every golden / fuzz vector."""
+    import subprocess, tempfile, struct
+    root = os.path.dirname(HERE)
+    src = r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "brpc_b200/csrc/b2_core.cuh"
+int main(int argc, char** argv) {
+    FILE* f = fopen(argv[1], "rb"); unsigned n_fast = 0, n_tot = 0, bad = 0;
+    for (;;) {
+        unsigned len; if (fread(&len, 4, 1, f) != 1) break;
+        unsigned char* b = (unsigned char*)malloc(len + 1); if (len && fread(b, 1, len, f) != len) return 2;
+        b2::RpcMetaOut a, g; memset(&a, 0, sizeof a); memset(&g, 0, sizeof g);
+        const bool fa = b2::decode_rpc_meta_fast(b, len, a), ge = b2::decode_rpc_meta(b, len, g);
+        n_tot++;
+        if (fa) { n_fast++; if (!ge || memcmp(&a, &g, sizeof a) != 0) { bad++; fprintf(stderr, "mismatch at vector %u\n", n_tot - 1); } }
+        free(b);
+    }
+    printf("%u %u %u\n", n_tot, n_fast, bad);
+    return bad ? 1 : 0;
+}'''
+    blobs = [bytes.fromhex(r["hex"]) for r in load("rpc_meta_vectors.json")["rpc_meta"]] + [bytes.fromhex(r["hex"]) for r in load("pb_fuzz_vectors.json")["rpc_meta"]]
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "t.cc"), "w").write(src)
+        with open(os.path.join(td, "v.bin"), "wb") as f:
+            for b in blobs:
+                f.write(struct.pack("<I", len(b))); f.write(b)
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", root, "-o", os.path.join(td, "t"), os.path.join(td, "t.cc")])
+        out = subprocess.run([os.path.join(td, "t"), os.path.join(td, "v.bin")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    tot, fast, bad = map(int, out.stdout.split())
+    assert tot == len(blobs) and bad == 0 and fast > 50
