@@ -24,7 +24,7 @@ static void set_err(const char* fmt, const char* a = "", const char* b = "") { s
 namespace {
 constexpr int kMaxStages = 16;
 constexpr uint32_t kSmallBytes = 128 << 10;        // batches up to this size take the latency path
-constexpr uint32_t kSmallRuns = 512, kSmallMsgs = 1024;
+constexpr uint32_t kSmallRuns = 512, kSmallMsgs = 1024;   // == kSmallThreads, 2 * kSmallThreads of k_small
 constexpr size_t kSmallBlock = 64 + kSmallRuns * 32 + kSmallMsgs * 64 + (kSmallBytes + kSmallMsgs * 80 + 4096);
 struct Stage { const char* name; cudaEvent_t ev; };
 }
@@ -57,7 +57,7 @@ struct b2_ctx {
     // small-batch (latency) mode: one compact H2D block, one compact output block, one D2H, one sync
     uint8_t* d_meta = nullptr; uint8_t* h_meta = nullptr;       // [runs | run_tile_base]
     uint8_t* d_small = nullptr; uint8_t* h_small = nullptr;     // [totals | run_status | msgs | resp]
-    bool small = false, small_copy_queued = false; uint32_t small_msgs = 0, small_resp = 0, small_off_rs = 0, small_off_msgs = 0, small_off_resp = 0, small_total = 0;
+    bool small = false, small_copy_queued = false, use_fused_small = true; uint32_t small_msgs = 0, small_resp = 0, small_off_rs = 0, small_off_msgs = 0, small_off_resp = 0, small_total = 0;
 };
 
 static uint32_t g_crc_tab_host[256];
@@ -176,6 +176,8 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k_pack_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PackWarpSmem) * kPackWarps)));
     if (const char* e = getenv("B2_PACK")) c->use_tma_pack = strcmp(e, "reg") != 0;
+    if (const char* e = getenv("B2_SMALL")) c->use_fused_small = strcmp(e, "off") != 0;
+    CU(cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
     *out = c;
     return B2_OK;
 }
@@ -281,6 +283,14 @@ static int launch_pipeline(b2_ctx* c) {
     CU(cudaMemsetAsync(B.totals, 0, 16, s));
     CU(cudaEventRecord(c->ev[0], s));
     if (c->n_runs == 0) { c->n_stages = 0; c->last_launches = 0; return B2_OK; }
+    if (c->small && c->use_fused_small && !prof) {
+        // latency path: the whole pipeline in one launch, one CTA
+        k_small<<<1, kSmallThreads, sizeof(SmallSmem), s>>>(B, C);
+        c->stage_names[0] = "fused_small"; cudaEventRecord(c->ev[1], s);
+        c->n_stages = 1; c->last_launches = 1;
+        CU(cudaGetLastError());
+        return B2_OK;
+    }
     if (c->n_tiles) {
         k_tile_search<<<(c->n_tiles * 32 + 255) / 256, 256, 0, s>>>(B, C); launches++; mark("tile_search");
         k_tile_walk<<<(c->n_tiles + 127) / 128, 128, 0, s>>>(B, C); launches++; mark("tile_walk");

@@ -474,45 +474,48 @@ struct DecodeWarpSmem {
 __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
                                            const uint8_t* srow, uint8_t* shead);
 
+// one warp round: 32 consecutive messages starting at i0 (staging, decode, head write-out)
+__device__ __forceinline__ void decode_round(const BatchPtrs& B, const DevConfig& C, DecodeWarpSmem& S, uint32_t i0, uint32_t n_msgs, uint32_t lane) {
+    const uint32_t i = i0 + lane;
+    const uint32_t fo_raw = i < n_msgs ? B.frame_off[i] : 0;
+    const uint32_t nm = min(32u, n_msgs - i0);
+    // stage: row m <- the 16-byte aligned vectors covering frame m's first bytes; half a warp per row
+    const uint32_t sub = lane & 15, half = lane >> 4;
+    for (uint32_t m2 = 0; m2 < nm; m2 += 2) {
+        const uint32_t m = m2 + half;
+        const uint32_t f = __shfl_sync(0xffffffffu, fo_raw, m & 31) & 0x7fffffffu;
+        if (m < nm && sub < kRowVecs) {
+            // cp.async (LDGSTS): global -> shared without a register round trip, so all 16 trips are in flight together
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.row[m][sub]);
+            const uint4* src = reinterpret_cast<const uint4*>(B.bytes + (f & ~15u)) + sub;       // (buffer is padded past its end)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    bool is_slow = false;
+    if (i < n_msgs) { decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 15u), S.head[lane]); is_slow = B.jobs[i].fast == 0; }
+    const uint32_t n_slow = __popc(__ballot_sync(0xffffffffu, is_slow));
+    if (lane == 0 && n_slow) atomicAdd(B.totals + 3, n_slow);          // k_pack_slow returns at once when this stays 0
+    __syncwarp();
+    // heads of 32 consecutive messages are contiguous: coalesced 16-byte stores
+    {
+        const uint4* hs = reinterpret_cast<const uint4*>(&S.head[0][0]);
+        uint4* hd = reinterpret_cast<uint4*>(B.heads + (size_t)i0 * kHeadBytes);
+        for (uint32_t k = lane; k < nm * (kHeadBytes / 16); k += 32) hd[k] = hs[k];
+    }
+    __syncwarp();
+}
+
 // persistent: a fixed grid (multiple of the SM count) strides over the device-side message count
 __global__ void __launch_bounds__(kDecodeWarps * 32, B2_DECODE_MIN_BLOCKS) k_decode(BatchPtrs B, DevConfig C) {
     __shared__ DecodeWarpSmem smem[kDecodeWarps];
     const uint32_t n_msgs = B.totals[0];
     if (B.totals[2] & 1u) return;
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    DecodeWarpSmem& S = smem[wid];
-    for (uint32_t i0 = (blockIdx.x * kDecodeWarps + wid) * 32; i0 < n_msgs; i0 += gridDim.x * kDecodeWarps * 32) {
-        const uint32_t i = i0 + lane;
-        const uint32_t fo_raw = i < n_msgs ? B.frame_off[i] : 0;
-        const uint32_t nm = min(32u, n_msgs - i0);
-        // stage: row m <- the 16-byte aligned vectors covering frame m's first bytes; half a warp per row
-        const uint32_t sub = lane & 15, half = lane >> 4;
-        for (uint32_t m2 = 0; m2 < nm; m2 += 2) {
-            const uint32_t m = m2 + half;
-            const uint32_t f = __shfl_sync(0xffffffffu, fo_raw, m & 31) & 0x7fffffffu;
-            if (m < nm && sub < kRowVecs) {
-                // cp.async (LDGSTS): global -> shared without a register round trip, so all 16 trips are in flight together
-                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.row[m][sub]);
-                const uint4* src = reinterpret_cast<const uint4*>(B.bytes + (f & ~15u)) + sub;       // (buffer is padded past its end)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        bool is_slow = false;
-        if (i < n_msgs) { decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 15u), S.head[lane]); is_slow = B.jobs[i].fast == 0; }
-        const uint32_t n_slow = __popc(__ballot_sync(0xffffffffu, is_slow));
-        if (lane == 0 && n_slow) atomicAdd(B.totals + 3, n_slow);          // k_pack_slow returns at once when this stays 0
-        __syncwarp();
-        // heads of 32 consecutive messages are contiguous: coalesced 16-byte stores
-        {
-            const uint4* hs = reinterpret_cast<const uint4*>(&S.head[0][0]);
-            uint4* hd = reinterpret_cast<uint4*>(B.heads + (size_t)i0 * kHeadBytes);
-            for (uint32_t k = lane; k < nm * (kHeadBytes / 16); k += 32) hd[k] = hs[k];
-        }
-        __syncwarp();
-    }
+    for (uint32_t i0 = (blockIdx.x * kDecodeWarps + wid) * 32; i0 < n_msgs; i0 += gridDim.x * kDecodeWarps * 32)
+        decode_round(B, C, smem[wid], i0, n_msgs, lane);
 }
 
 __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
@@ -1504,6 +1507,118 @@ __global__ void __launch_bounds__(256) k_finalize(BatchPtrs B) {
     atomicAdd(B.counters + 2, (unsigned long long)st.resp_bytes);
     if (st.parse_error != B2_PARSE_ERROR_NOT_ENOUGH_DATA) atomicAdd(B.counters + 4, 1ull);
     if (r == 0) atomicAdd(B.counters + 5, 1ull);
+}
+
+// --- k_small: the whole path in ONE launch for latency-sized batches ------------------------------
+// A batch of <= 128 KB / 512 runs / 1024 messages (what a set of synchronous clients has in flight)
+// does not need the tile machinery: one CTA walks every run's frame chain (thread per run, true
+// preferred index, no speculation), scans, decodes (same decode_round as k_decode), scans the reply
+// slots and packs (register copies), with __syncthreads() where the big pipeline has kernel
+// boundaries.  Ten launches become one; results are identical by construction (same device functions).
+constexpr uint32_t kSmallThreads = 512, kSmallWarps = kSmallThreads / 32;
+struct SmallSmem {
+    DecodeWarpSmem dec[kSmallWarps];
+    uint32_t run_count[kSmallThreads];
+    uint32_t scan[1024 + 1];
+    uint32_t s_hot[kCrcHotWords];
+    uint32_t warp_tot[kSmallWarps];
+    uint32_t n_msgs, resp_total;
+};
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_tot, uint32_t& total) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += y; }
+    __syncthreads();
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+    for (uint32_t w = 0; w < kSmallWarps; w++) { const uint32_t t = warp_tot[w]; if (w < wid) base += t; tot += t; }
+    total = tot;
+    return base + x - v;
+}
+__global__ void __launch_bounds__(kSmallThreads, 1) k_small(BatchPtrs B, DevConfig C) {
+    extern __shared__ __align__(128) uint8_t small_raw[];
+    SmallSmem& S = *reinterpret_cast<SmallSmem*>(small_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    crc_tabs_to_smem(S.s_hot, B.crc_adv);
+    CrcTabs ct; ct.hot = S.s_hot; ct.tree = B.crc_adv + kCrcHotWords;
+    // ---- cut loop: thread per run (ProcessNewMessage over the whole run)
+    uint32_t my_count = 0; b2_run_status st; st.consumed = 0; st.parse_error = B2_PARSE_ERROR_NOT_ENOUGH_DATA; st.n_msgs = 0;
+    st.first_msg = 0; st.preferred_proto = -1; st.reserved0 = 0; st.resp_off = 0; st.resp_bytes = 0;
+    b2_run run; run.offset = 0; run.length = 0; run.preferred_proto = -1; run.flags = 0; run.socket_id = 0;
+    if (tid < B.n_runs) {
+        run = B.runs[tid];
+        uint32_t pos = 0; int pf = run.preferred_proto;
+        for (;;) {
+            const Step sp = cut_input_message(B.bytes + run.offset, run.length, pos, pf, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0);
+            pos = sp.new_pos; pf = sp.pf;
+            if (sp.err != B2_PARSE_OK) { st.parse_error = (uint32_t)sp.err; break; }
+            my_count++;
+        }
+        st.consumed = pos; st.preferred_proto = pf; st.n_msgs = my_count;
+    }
+    uint32_t total = 0;
+    const uint32_t first = block_excl_scan(my_count, S.warp_tot, total);
+    if (tid == 0) { S.n_msgs = total; B.totals[0] = total; if (total > B.max_msgs) B.totals[2] |= 1u; }
+    __syncthreads();
+    if (total > B.max_msgs) return;
+    // ---- frame table: the same walk again, now writing offsets
+    if (tid < B.n_runs) {
+        st.first_msg = first;
+        uint32_t pos = 0, k = 0; int pf = run.preferred_proto;
+        for (;;) {
+            const Step sp = cut_input_message(B.bytes + run.offset, run.length, pos, pf, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0);
+            if (sp.err != B2_PARSE_OK) break;
+            B.frame_off[first + k] = (run.offset + sp.frame_pos) | ((uint32_t)(sp.index - 1) << 31);
+            B.frame_run[first + k] = tid; k++;
+            pos = sp.new_pos; pf = sp.pf;
+        }
+        B.run_status[tid] = st;
+    }
+    __syncthreads();
+    // ---- decode
+    for (uint32_t i0 = wid * 32; i0 < total; i0 += kSmallWarps * 32) decode_round(B, C, S.dec[wid], i0, total, lane);
+    __syncthreads();
+    // ---- reply slots: exclusive scan (<= 1024 messages: two per thread)
+    {
+        const uint32_t a0 = 2 * tid, a1 = 2 * tid + 1;
+        const uint32_t v0 = a0 < total ? B.slot[a0] : 0, v1 = a1 < total ? B.slot[a1] : 0;
+        uint32_t tot = 0;
+        const uint32_t ex = block_excl_scan(v0 + v1, S.warp_tot, tot);
+        if (a0 < total) B.slot[a0] = ex;
+        if (a1 < total) B.slot[a1] = ex + v0;
+        if (tid == 0) { B.scan_tmp[0] = 0; B.totals[1] = tot; S.resp_total = tot; if (tot > B.max_resp) B.totals[2] |= 2u; }
+    }
+    __syncthreads();
+    if (S.resp_total > B.max_resp) return;
+    // ---- pack: warp per message
+    for (uint32_t i = wid; i < total; i += kSmallWarps) {
+        const PackJob job = B.jobs[i];
+        if (!job.fast) { pack_one(B, C, i, lane, ct); continue; }
+        const uint32_t so = B.slot[i];
+        // slot image = head record + 16-byte aligned rest of the payload (see k_pack_tma); plain 16 B copies here
+        const uint4* hs = reinterpret_cast<const uint4*>(B.heads + (size_t)i * kHeadBytes);
+        uint4* dst = reinterpret_cast<uint4*>(B.resp + so);
+        for (uint32_t k = lane; k < job.head_len / 16u; k += 32) dst[k] = hs[k];
+        const uint4* ps = reinterpret_cast<const uint4*>(B.bytes + job.src_off);
+        uint4* pd = reinterpret_cast<uint4*>(B.resp + so + job.head_len);
+        for (uint32_t k = lane; k < job.bulk_len / 16u; k += 32) pd[k] = __ldg(ps + k);
+        if (lane == 0) B.msgs[i].resp_off = so + job.pad;
+    }
+    __syncthreads();
+    // ---- per-run reply span + counters
+    if (tid < B.n_runs) {
+        auto off_of = [&](uint32_t i) -> uint32_t { return i >= total ? S.resp_total : B.slot[i]; };
+        st.resp_off = off_of(st.first_msg);
+        st.resp_bytes = off_of(st.first_msg + st.n_msgs) - st.resp_off;
+        B.run_status[tid] = st;
+        atomicAdd(B.counters + 0, (unsigned long long)st.consumed);
+        atomicAdd(B.counters + 1, (unsigned long long)st.n_msgs);
+        atomicAdd(B.counters + 2, (unsigned long long)st.resp_bytes);
+        if (st.parse_error != B2_PARSE_ERROR_NOT_ENOUGH_DATA) atomicAdd(B.counters + 4, 1ull);
+        if (tid == 0) atomicAdd(B.counters + 5, 1ull);
+    }
 }
 
 #endif  // __CUDACC__

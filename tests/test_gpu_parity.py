@@ -48,7 +48,7 @@ def test_single_socket_whole_frames(b2):
     dev, _ = run_both(b2, ctx, [b"".join(frames)])
     rs, msgs, resp, info = dev
     assert rs["n_msgs"][0] == 10 and rs["consumed"][0] == sum(map(len, frames)) and rs["parse_error"][0] == 2
-    assert np.all(msgs["status"] == 0) and info["n_launches"] >= 5
+    assert np.all(msgs["status"] == 0) and info["n_launches"] >= 1
 
 
 def test_empty_inputs(b2):
@@ -71,7 +71,8 @@ def test_truncated_header_every_length(b2):
         run_both(b2, ctx, chunks, preferred=pref, what="pref=%d" % pref)
 
 
-def test_split_at_every_offset(b2):
+def test_split_at_every_offset(b2, monkeypatch):
+    monkeypatch.setenv("B2_SMALL", "off")
     """One frame stream cut at every byte offset (brpc_input_messenger_unittest.cpp chunking discipline)."""
     ctx = make_ctx(b2, tile_bytes=512)
     rng = random.Random(3)
@@ -80,8 +81,11 @@ def test_split_at_every_offset(b2):
     run_both(b2, ctx, chunks)
 
 
-def test_mixed_matrix_many_sockets(b2):
+def test_mixed_matrix_many_sockets(b2, monkeypatch):
     for tile in (512, 2048, 8192):
+        # small batches normally take the one-launch k_small path; B2_SMALL=off sends them through the
+        # tile pipeline instead, so both implementations face the same traffic
+        monkeypatch.setenv("B2_SMALL", "off" if tile == 2048 else "on")
         ctx = make_ctx(b2, tile_bytes=tile, identity=b"10.1.2.3:8000")
         rng = random.Random(SEED + tile)
         streams = [mixed_frames(rng, rng.randrange(1, 40)) for _ in range(200)]
@@ -118,7 +122,8 @@ def test_large_frames_span_tiles(b2):
     run_both(b2, ctx, split_runs(rng, streams))
 
 
-def test_payload_full_of_fake_frames(b2):
+def test_payload_full_of_fake_frames(b2, monkeypatch):
+    monkeypatch.setenv("B2_SMALL", "off")
     """Payloads that contain valid-looking baidu_std frames: the speculative tile scan must never
     change the result (SURVEY §7 'hard parts')."""
     rng = random.Random(7)
@@ -135,7 +140,8 @@ def test_payload_full_of_fake_frames(b2):
         run_both(b2, ctx, split_runs(rng, streams), what="tile=%d" % tile)
 
 
-def test_corrupted_streams(b2):
+def test_corrupted_streams(b2, monkeypatch):
+    monkeypatch.setenv("B2_SMALL", "off")           # exercise the speculative tile pipeline on these small batches
     ctx = make_ctx(b2, tile_bytes=512, max_body_size=1 << 20)
     cfg = O.make_config(max_body_size=1 << 20)
     rng = random.Random(8)
