@@ -141,8 +141,10 @@ def test_payload_full_of_fake_frames(b2, monkeypatch):
 
 
 def test_corrupted_streams(b2, monkeypatch):
-    monkeypatch.setenv("B2_SMALL", "off")           # exercise the speculative tile pipeline on these small batches
+    monkeypatch.setenv("B2_SMALL", "off")           # the speculative tile pipeline ...
     ctx = make_ctx(b2, tile_bytes=512, max_body_size=1 << 20)
+    monkeypatch.setenv("B2_SMALL", "on")            # ... and the one-launch k_small path, same streams
+    ctx_small = make_ctx(b2, tile_bytes=512, max_body_size=1 << 20)
     cfg = O.make_config(max_body_size=1 << 20)
     rng = random.Random(8)
     chunks = []
@@ -161,6 +163,8 @@ def test_corrupted_streams(b2, monkeypatch):
         chunks.append(b"".join(fr))
     for pref in (-1, 1, 2):
         run_both(b2, ctx, chunks, cfg=cfg, preferred=pref, what="pref=%d" % pref)
+        for k in range(0, len(chunks), 40):         # k_small takes batches of <= 128 KB
+            run_both(b2, ctx_small, chunks[k:k + 40], cfg=cfg, preferred=pref, what="small pref=%d k=%d" % (pref, k))
 
 
 def test_meta_edge_encodings(b2):
