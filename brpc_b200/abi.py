@@ -59,6 +59,7 @@ def _load():
     l.b2_ctx_destroy.argtypes = [C.c_void_p]
     l.b2_register_method.argtypes = [C.c_void_p, C.POINTER(Method)]
     l.b2_set_server_identity.argtypes = [C.c_void_p, C.c_char_p]
+    l.b2_set_stream_handler.argtypes = [C.c_void_p, C.c_int]
     l.b2_block_alloc.restype = C.c_void_p; l.b2_block_alloc.argtypes = [C.c_size_t]
     l.b2_block_free.argtypes = [C.c_void_p]
     l.b2_process_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(BatchResult)]
@@ -91,7 +92,7 @@ lib = _load()
 
 # every symbol include/b2rpc.h declares (tests check the library exports them)
 ABI_SYMBOLS = ["b2_ctx_create", "b2_ctx_destroy", "b2_last_error", "b2_version", "b2_register_method",
-               "b2_set_server_identity", "b2_block_alloc", "b2_block_free", "b2_process_batch", "b2_batch_submit", "b2_batch_collect", "b2_batch_upload",
+               "b2_set_server_identity", "b2_set_stream_handler", "b2_block_alloc", "b2_block_free", "b2_process_batch", "b2_batch_submit", "b2_batch_collect", "b2_batch_upload",
                "b2_batch_execute", "b2_batch_execute_many", "b2_batch_download", "b2_batch_launch", "b2_batch_wait",
                "b2_elapsed_ms", "b2_stage_times", "b2_crc32c_batch", "b2_snappy_uncompress_batch", "b2_snappy_compress_batch", "b2_hpack_reset", "b2_hpack_decode_batch", "b2_h2_scan_batch", "b2_counters_read",
                "b2_counters_device_ptr"]
@@ -133,7 +134,7 @@ class Context:
     """b2_ctx: one per GPU."""
 
     def __init__(self, device=0, max_batch_bytes=64 << 20, max_msgs=1 << 20, max_runs=4096, max_resp_bytes=0,
-                 tile_bytes=0, max_body_size=0, methods=(ECHO_METHOD,), server_identity=None):
+                 tile_bytes=0, max_body_size=0, methods=(ECHO_METHOD,), server_identity=None, stream_handler=0):
         opt = Options(device, max_batch_bytes, max_msgs, max_runs, max_resp_bytes, tile_bytes, max_body_size)
         h = C.c_void_p()
         _check(lib.b2_ctx_create(C.byref(opt), C.byref(h)))
@@ -143,6 +144,8 @@ class Context:
             self.register_method(**m)
         if server_identity:
             _check(lib.b2_set_server_identity(self._h, server_identity))
+        if stream_handler:
+            _check(lib.b2_set_stream_handler(self._h, stream_handler))
 
     def close(self):
         if getattr(self, "_h", None):

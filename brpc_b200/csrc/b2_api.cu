@@ -192,6 +192,12 @@ extern "C" int b2_set_server_identity(b2_ctx* c, const char* ip_port) {
     return B2_OK;
 }
 
+extern "C" int b2_set_stream_handler(b2_ctx* c, int kind) {
+    if (!c || (kind != B2_STREAM_DESC_ONLY && kind != B2_STREAM_SNAPPY_UNCOMPRESS)) { set_err("bad stream handler"); return B2_E_INVAL; }
+    c->cfg.stream_handler = (uint32_t)kind;
+    return B2_OK;
+}
+
 extern "C" int b2_register_method(b2_ctx* c, const b2_method* m) {
     if (!c || !m || !m->service_full_name || !m->service_name || !m->method_name || !m->request_type_name) { set_err("null argument"); return B2_E_INVAL; }
     if (c->methods.size() >= 64) { set_err("method table full"); return B2_E_CAPACITY; }

@@ -75,6 +75,7 @@ struct DevConfig {
     uint32_t tile_bytes, tile_shift;
     uint32_t n_methods;
     uint32_t identity_len;
+    uint32_t stream_handler;      // B2_STREAM_*
     char identity[64];            // "ip:port" of Controller::AppendServerIdentiy
 };
 
@@ -545,6 +546,13 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
             d.compress_type = sm.frame_type; d.has_bits = (uint16_t)sm.has;
             d.attachment_size = (int32_t)(uint32_t)((uint64_t)sm.consumed_size & 0xffffffffu);
             d.checksum_type = (int32_t)(uint32_t)((uint64_t)sm.consumed_size >> 32);
+            if (C.stream_handler == B2_STREAM_SNAPPY_UNCOMPRESS && (sm.has & B2_SHAS_FRAME_TYPE) && sm.frame_type == 3 /*FRAME_TYPE_DATA*/) {
+                uint32_t ulen = 0, used = 0;
+                bool ok = snappy_preamble(gframe + 12 + d.meta_size, req_size, ulen, used);
+                if (ok && (uint64_t)ulen > 32ull * req_size + 64ull) ok = false;
+                if (!ok) d.error_code = B2_EREQUEST;
+                else { a.msg_off = kNone; a.msg_len = ulen; a.att_off = req_size; resp_len = ulen ? ulen : 1; }
+            }
         }
     } else {
         RpcMetaOut m;
@@ -1208,6 +1216,16 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
     if (d.resp_len == 0) { if (lane == 0 && d.status != B2_MSG_RESPONSE) B.msgs[i].resp_off = slot_off; return; }
     const MsgAux a = B.aux[i];
     const uint8_t* frame = B.bytes + d.frame_off;
+    if (d.status == B2_MSG_STREAM_FRAME) {
+        // the application-level SnappyDecompress of a streaming DATA frame's payload
+        uint32_t produced = 0;
+        const bool ok = warp_snappy_decode(frame + 12 + d.meta_size, a.att_off, B.resp + slot_off, a.msg_len, lane, produced);
+        if (lane == 0) {
+            if (ok) { B.msgs[i].resp_off = slot_off; B.msgs[i].resp_len = produced; }
+            else { B.msgs[i].resp_off = slot_off; B.msgs[i].resp_len = 0; B.msgs[i].error_code = B2_EREQUEST; }
+        }
+        return;
+    }
     if (d.status == B2_MSG_RESPONSE || d.status == B2_MSG_RESPONSE_UNZ) {
         // client side: DeserializeRpcMessage of the response body = checksum verify, then (snappy ->) parse
         bool ok = true;

@@ -214,6 +214,15 @@ const char* b2_version(void);
  * Returns the method index (>= 0) or a negative B2_E_*. */
 int  b2_register_method(b2_ctx* ctx, const b2_method* m);
 
+/* What the device does with streaming_rpc DATA frames beyond cutting them and decoding StreamFrameMeta:
+ * B2_STREAM_DESC_ONLY (default) or B2_STREAM_SNAPPY_UNCOMPRESS — the frame payload is a snappy stream
+ * (policy::SnappyDecompress(IOBuf, IOBuf), src/brpc/policy/snappy_compress.cpp:77-82, as an application of
+ * example/streaming_echo_c++ would call on each received message) and is decompressed into the resp
+ * region: resp_off/resp_len = the plain bytes, error_code = B2_EREQUEST when the stream is malformed. */
+#define B2_STREAM_DESC_ONLY         0
+#define B2_STREAM_SNAPPY_UNCOMPRESS 1
+int  b2_set_stream_handler(b2_ctx* ctx, int kind);
+
 /* "ip:port" that Controller::AppendServerIdentiy (src/brpc/controller.cpp:407-428)
  * prepends to every error text as "[ip:port]"; NULL/"" = no server identity. */
 int  b2_set_server_identity(b2_ctx* ctx, const char* ip_port);

@@ -741,15 +741,23 @@ static int process_rpc_response(const uint8_t* frame, b2_msg_desc* d, uint8_t* r
 }
 
 /* ParseStreamingMessage's meta step, streaming_rpc_protocol.cpp:95-100 */
-static void process_stream_frame(const uint8_t* frame, b2_msg_desc* d) {
+static void process_stream_frame(const orc_config* cfg, const uint8_t* frame, b2_msg_desc* d, uint8_t* resp, size_t resp_cap, size_t* resp_len) {
     orc_stream_meta sm;
-    d->method_idx = -1; d->error_code = 0;
+    d->method_idx = -1; d->error_code = 0; *resp_len = 0;
     if (!orc_parse_stream_meta(frame + 12, d->meta_size, &sm)) { d->status = B2_MSG_BAD_STREAM_META; return; }
     d->status = B2_MSG_STREAM_FRAME;
     d->correlation_id = sm.stream_id; d->log_id = sm.source_stream_id;
     d->compress_type = sm.frame_type; d->has_bits = (uint16_t)sm.has;
     d->attachment_size = (int32_t)(uint32_t)((uint64_t)sm.consumed_size & 0xffffffffu);
     d->checksum_type = (int32_t)(uint32_t)((uint64_t)sm.consumed_size >> 32);
+    if (cfg->stream_handler == B2_STREAM_SNAPPY_UNCOMPRESS && (sm.has & B2_SHAS_FRAME_TYPE) && sm.frame_type == 3) {
+        /* policy::SnappyDecompress(IOBuf, IOBuf), snappy_compress.cpp:77-82, on the frame payload */
+        const uint8_t* data = frame + 12 + d->meta_size; const size_t n = d->body_size - d->meta_size;
+        size_t ulen = 0, got = 0;
+        if (!ref_load() || !g_sn_len((const char*)data, n, &ulen) || ulen > 32 * (uint64_t)n + 64 || ulen > resp_cap ||
+            !g_sn_u((const char*)data, n, (char*)resp, ulen, &got)) { d->error_code = B2_EREQUEST; return; }
+        *resp_len = got;
+    }
 }
 
 /* InputMessenger::ProcessNewMessage, input_messenger.cpp:206-322, per run. */
@@ -785,8 +793,8 @@ int orc_process_batch(const orc_config* cfg, const uint8_t* bytes, uint32_t nbyt
                 if (process_rpc_request(cfg, bytes + d->frame_off, d, resp + rb, resp_cap - rb, &rl) != 0) return -1;
                 d->resp_off = (uint32_t)rb; d->resp_len = (uint32_t)rl;
             } else {
-                process_stream_frame(bytes + d->frame_off, d);
-                d->resp_off = (uint32_t)rb; d->resp_len = 0;
+                process_stream_frame(cfg, bytes + d->frame_off, d, resp + rb, resp_cap - rb, &rl);
+                d->resp_off = (uint32_t)rb; d->resp_len = (uint32_t)rl;
             }
             rb += rl; nm++; rs[r].n_msgs++;
         }

@@ -68,6 +68,7 @@ typedef struct orc_config {
     uint64_t max_body_size;       /* FLAGS_max_body_size, protocol.cpp:52 */
     const char* server_identity;  /* "ip:port" of Controller::AppendServerIdentiy, or NULL */
     const b2_method* methods; uint32_t n_methods;
+    int stream_handler;           /* B2_STREAM_* */
 } orc_config;
 
 /* ---- leaf codecs ---------------------------------------------------------- */

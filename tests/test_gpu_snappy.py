@@ -150,3 +150,40 @@ def test_snappy_replies_through_the_path():
         orc = O.process_batch(cfg, data, runs)
         assert_same(dev, orc, "cks=%d" % cks)
         assert (dev[1]["status"] == 0).sum() > 50
+
+
+def _ref_compress(ref, raw):
+    ref.ref_snappy_max_compressed_length.restype = C.c_size_t; ref.ref_snappy_max_compressed_length.argtypes = [C.c_size_t]
+    ref.ref_snappy_compress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.POINTER(C.c_size_t)]
+    cap = ref.ref_snappy_max_compressed_length(len(raw)); out = C.create_string_buffer(cap); n = C.c_size_t(cap)
+    ref.ref_snappy_compress(raw, len(raw), out, C.byref(n))
+    return out.raw[:n.value]
+
+
+def test_streaming_frames_with_snappy_payloads():
+    """BASELINE configs[4] shape: streaming_rpc DATA frames whose payloads the application snappy-compressed
+    (policy::SnappyCompress), cut + meta-decoded + decompressed on the device, interleaved with baidu_std calls."""
+    import brpc_b200
+    ref = _ref()
+    rng = random.Random(SEED + 3)
+    ctx = brpc_b200.Context(device=0, max_batch_bytes=64 << 20, max_msgs=1 << 16, max_runs=256, stream_handler=1)
+    cfg = O.make_config(stream_handler=1)
+    streams = []
+    for s in range(48):
+        fr = []
+        for i in range(rng.randrange(1, 8)):
+            n = rng.choice([0, 10, 1000, 70000, 262144])
+            raw = rng.choice([_pattern(n), rnd62(rng, min(n, 30000)), (rnd62(rng, 64) * (n // 64 + 1))[:n]])
+            comp = _ref_compress(ref, raw)
+            if rng.random() < 0.15 and len(comp) > 4:
+                comp = bytearray(comp); comp[rng.randrange(len(comp))] ^= 0x10; comp = bytes(comp)
+            fr.append(O.pack_stream_frame(1000 + s, 2000 + s, rng.choice([3, 3, 3, 4, 1]), rng.choice([None, False]), comp))
+            if rng.random() < 0.3:
+                fr.append(echo_frame(rng, i, rnd62(rng, 100)))
+        streams.append(b"".join(fr))
+    data, runs = brpc_b200.make_runs(streams)
+    dev = ctx.process_batch(data, runs)
+    orc = O.process_batch(cfg, data, runs)
+    assert_same(dev, orc, "streaming")
+    m = dev[1]
+    assert ((m["status"] == 4) & (m["resp_len"] > 100000)).sum() > 3 and ((m["status"] == 4) & (m["error_code"] == 1003)).sum() > 0
