@@ -144,12 +144,12 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     ALLOC(c->d_hpack, sizeof(HpackState) * (size_t)B2_HPACK_MAX_CONNS);
     CU(cudaMemset(c->d_hpack, 0, sizeof(HpackState) * (size_t)B2_HPACK_MAX_CONNS));
     ALLOC(c->d_counters, 8 * B2_N_COUNTERS);
-    ALLOC(c->d_totals, 16);
+    ALLOC(c->d_totals, 64);
     ALLOC(c->d_methods, sizeof(DevMethod) * 64);
     ALLOC(c->d_crc_adv, (kCrcHotWords + kCrcTreeWords) * 4);
-    ALLOC(c->d_meta, (size_t)o->max_runs * 28 + 64);
+    ALLOC(c->d_meta, (size_t)o->max_runs * 28 + 4 * (size_t)c->max_tiles + 64);
     ALLOC(c->d_small, kSmallBlock);
-    HALLOC(c->h_meta, (size_t)o->max_runs * 28 + 64);
+    HALLOC(c->h_meta, (size_t)o->max_runs * 28 + 4 * (size_t)c->max_tiles + 64);
     HALLOC(c->h_small, kSmallBlock);
     HALLOC(c->h_run_status, sizeof(b2_run_status) * (size_t)o->max_runs);
     HALLOC(c->h_msgs, sizeof(b2_msg_desc) * (size_t)o->max_msgs);
@@ -229,6 +229,7 @@ static BatchPtrs make_ptrs(b2_ctx* c) {
     B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes;
     B.runs = reinterpret_cast<const b2_run*>(c->d_meta);
     B.run_tile_base = reinterpret_cast<const uint32_t*>(c->d_meta + (size_t)c->n_runs * sizeof(b2_run));
+    B.tile_run = B.run_tile_base + c->n_runs + 1;
     if (c->small) {
         B.totals = reinterpret_cast<uint32_t*>(c->d_small);
         B.run_status = reinterpret_cast<b2_run_status*>(c->d_small + c->small_off_rs);
@@ -262,9 +263,14 @@ extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, co
     if (nt > c->max_tiles) { set_err("too many tiles"); return B2_E_CAPACITY; }
     c->n_runs = n_runs; c->n_tiles = (uint32_t)nt; c->nbytes = nbytes; c->max_run_tiles = max_rt;
     // runs + tile bases travel as one compact block (24 B * n is 4-byte aligned)
-    const size_t meta_bytes = (size_t)n_runs * sizeof(b2_run) + 4 * ((size_t)n_runs + 1);
+    const size_t meta_bytes = (size_t)n_runs * sizeof(b2_run) + 4 * ((size_t)n_runs + 1) + 4 * (size_t)nt;
     if (n_runs) memcpy(c->h_meta, runs, (size_t)n_runs * sizeof(b2_run));
     memcpy(c->h_meta + (size_t)n_runs * sizeof(b2_run), c->h_run_tile_base, 4 * ((size_t)n_runs + 1));
+    {   // tile -> run map (replaces three binary searches per tile on the device)
+        uint32_t* tr = reinterpret_cast<uint32_t*>(c->h_meta + (size_t)n_runs * sizeof(b2_run) + 4 * ((size_t)n_runs + 1));
+        for (uint32_t r = 0; r < n_runs; r++)
+            for (uint32_t t = c->h_run_tile_base[r]; t < c->h_run_tile_base[r + 1]; t++) tr[t] = r;
+    }
     if (nbytes) CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_meta, c->h_meta, meta_bytes, cudaMemcpyHostToDevice, c->stream));
     // latency path: outputs of a small batch live in one compact block -> one D2H copy, one sync
@@ -286,7 +292,7 @@ static int launch_pipeline(b2_ctx* c) {
     int st = 0; uint32_t launches = 0;
     const bool prof = c->profile_stages;
     auto mark = [&](const char* name) { if (prof) { c->stage_names[st] = name; cudaEventRecord(c->ev[st + 1], s); st++; } };
-    CU(cudaMemsetAsync(B.totals, 0, 16, s));
+    CU(cudaMemsetAsync(B.totals, 0, 32, s));
     CU(cudaEventRecord(c->ev[0], s));
     if (c->n_runs == 0) { c->n_stages = 0; c->last_launches = 0; return B2_OK; }
     if (c->small && c->use_fused_small && !prof) {
@@ -306,19 +312,17 @@ static int launch_pipeline(b2_ctx* c) {
         if (smem > 200 * 1024) smem = 0;
         k_resolve<<<c->n_runs, 256, smem, s>>>(B, C); launches++; mark("resolve");
     }
-    k_run_prefix<<<1, 1024, 0, s>>>(B); launches++; mark("run_prefix");
     if (c->n_tiles) { k_frame_table<<<(c->n_tiles + 127) / 128, 128, 0, s>>>(B, C); launches++; mark("frame_table"); }
     // message-count dependent kernels are persistent: fixed grids (multiples of the SM count)
     // stride over the device-side message count, so no host round trip sizes a launch
     const uint32_t sms = c->n_sms;
     k_decode<<<sms * B2_DECODE_MIN_BLOCKS, kDecodeWarps * 32, 0, s>>>(B, C); launches++; mark("decode");
     k_scan_blocks<<<sms, kScanBlock, 0, s>>>(B); launches++;
-    k_scan_top<<<1, 1024, 0, s>>>(B); launches++; mark("scan");
+    mark("scan");
     if (c->use_tma_pack) {
         k_pack_tma<<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C); launches++; mark("pack");
         k_pack_slow<<<sms * B2_SLOW_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack_slow");
     } else { k_pack<<<sms * B2_PACK_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack"); }
-    k_finalize<<<(c->n_runs + 255) / 256, 256, 0, s>>>(B); launches++; mark("finalize");
     if (!prof) { c->stage_names[0] = "pipeline"; cudaEventRecord(c->ev[1], s); st = 1; }
     c->n_stages = st; c->last_launches = launches;
     CU(cudaGetLastError());

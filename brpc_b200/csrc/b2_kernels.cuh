@@ -13,12 +13,12 @@
 //   k_tile_walk    thread/tile header chain inside the tile -> (exit, count)
 //   k_resolve      CTA/run     verifies the speculation chain from tile 0 (exact),
 //                              falls back to a scalar walk where it fails, run status
-//   k_run_prefix   1 CTA       first_msg of every run
+//   (run prefix)   first_msg of every run: the last CTA of k_resolve
 //   k_frame_table  thread/tile frame offsets of live tiles
 //   k_decode       thread/msg  RpcMeta / StreamFrameMeta / EchoRequest decode -> desc, aux, slot
 //   k_scan_*       exclusive scan of the slot sizes
 //   k_pack         warp/msg    response header+meta, payload copy (+CRC32C)
-//   k_finalize     thread/run  per-run response span, counters
+//   (finalize)     per-run response span + counters: prologue of k_pack_slow
 #pragma once
 #include <cuda_runtime.h>
 #include "b2_core.cuh"
@@ -83,6 +83,7 @@ struct BatchPtrs {
     const uint8_t* bytes;
     const b2_run* runs;
     const uint32_t* run_tile_base;   // [n_runs+1] first tile of each run
+    const uint32_t* tile_run;        // [n_tiles] run of every tile (host-built with the batch)
     TileRec* tiles;
     uint32_t* tile_base;             // [n_tiles] run-relative index of the tile's first message
     uint32_t* tile_scratch;          // [3 * n_tiles] k_resolve spill when a run's tiles exceed shared memory
@@ -145,7 +146,7 @@ __device__ __forceinline__ bool is_magic(uint32_t w) { return w == kMagicPRPC ||
 __global__ void __launch_bounds__(256) k_tile_search(BatchPtrs B, DevConfig C) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B.n_tiles) return;
-    const uint32_t r = find_run(B.run_tile_base, B.n_runs, warp);
+    const uint32_t r = __ldg(B.tile_run + warp);
     const uint32_t k = warp - __ldg(B.run_tile_base + r);
     const b2_run run = B.runs[r];
     const uint8_t* base = B.bytes + run.offset;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) k_tile_search(BatchPtrs B, DevConfig C) {
 __global__ void __launch_bounds__(128) k_tile_walk(BatchPtrs B, DevConfig C) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B.n_tiles) return;
-    const uint32_t r = find_run(B.run_tile_base, B.n_runs, t);
+    const uint32_t r = __ldg(B.tile_run + t);
     const uint32_t k = t - __ldg(B.run_tile_base + r);
     const b2_run run = B.runs[r];
     TileRec rec;
@@ -215,6 +216,29 @@ __global__ void __launch_bounds__(128) k_tile_walk(BatchPtrs B, DevConfig C) {
     if (rec.entry != kNone)
         walk_tile<true>(B.bytes + run.offset, run.length, rec.entry, -1, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, rec, NoEmit());
     B.tiles[t] = rec;
+}
+
+// --- run prefix: exclusive scan of n_msgs over runs, done by the LAST CTA of k_resolve to finish -------
+__device__ __forceinline__ void run_prefix_body(const BatchPtrs& B, uint32_t* s_warp, uint32_t* s_carry) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) *s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < B.n_runs; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t v = i < B.n_runs ? __ldcg(&B.run_status[i].n_msgs) : 0, x = v;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += y; }
+        if (lane == 31) s_warp[wid] = x;
+        __syncthreads();
+        uint32_t wbase = 0, wtot = 0;
+        for (uint32_t w = 0; w < nw; w++) { const uint32_t t = s_warp[w]; if (w < wid) wbase += t; wtot += t; }
+        const uint32_t carry = *s_carry;
+        if (i < B.n_runs) B.run_status[i].first_msg = carry + wbase + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) *s_carry = carry + wtot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { B.totals[0] = *s_carry; if (*s_carry > B.max_msgs) B.totals[2] |= 1u; }
 }
 
 // --- k_resolve: one CTA per run ---------------------------------------------
@@ -351,35 +375,13 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C) {
         st.preferred_proto = s.pf; st.reserved0 = 0; st.resp_off = 0; st.resp_bytes = 0;
         B.run_status[r] = st;
     }
-}
-
-// --- k_run_prefix: exclusive scan of n_msgs over runs (single CTA) ----------
-__global__ void __launch_bounds__(1024) k_run_prefix(BatchPtrs B) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+    // the last CTA to get here turns the per-run counts into first_msg (was a separate launch)
+    __shared__ uint32_t s_ticket, s_pw[8], s_pc;
+    __threadfence();
     __syncthreads();
-    for (uint32_t base = 0; base < B.n_runs; base += blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        uint32_t v = i < B.n_runs ? B.run_status[i].n_msgs : 0, x = v;
-        #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
-        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t w = s_warp[threadIdx.x], ws = w;
-            #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, ws, d); if (threadIdx.x >= d) ws += y; }
-            s_warp[threadIdx.x] = ws - w;
-        }
-        __syncthreads();
-        const uint32_t excl = s_carry + s_warp[threadIdx.x >> 5] + x - v;
-        if (i < B.n_runs) B.run_status[i].first_msg = excl;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { B.totals[0] = s_carry; if (s_carry > B.max_msgs) B.totals[2] |= 1u; }
+    if (threadIdx.x == 0) s_ticket = atomicAdd(B.totals + 4, 1u);
+    __syncthreads();
+    if (s_ticket == gridDim.x - 1) { __threadfence(); run_prefix_body(B, s_pw, &s_pc); }
 }
 
 // --- k_frame_table: one thread per tile --------------------------------------
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(128) k_frame_table(BatchPtrs B, DevConfig C) {
     const TileRec rec = B.tiles[t];
     if (!rec.live || rec.count == 0) return;
     if (B.totals[2] & 1u) return;
-    const uint32_t r = find_run(B.run_tile_base, B.n_runs, t);
+    const uint32_t r = __ldg(B.tile_run + t);
     const uint32_t k = t - __ldg(B.run_tile_base + r);
     const b2_run run = B.runs[r];
     const uint32_t first = B.run_status[r].first_msg + B.tile_base[t];
@@ -730,6 +732,34 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
 
 // --- exclusive scan of slot sizes: 2 kernels ---------------------------------
 constexpr int kScanBlock = 1024, kScanItems = 4;
+__device__ __forceinline__ void scan_top_body(const BatchPtrs& B, uint32_t* s_warp, uint32_t* s_carry_p) {
+    // serial-by-chunks exclusive scan of the block sums (<= a few thousand entries)
+    const uint32_t n = B.totals[0];
+    const uint32_t nb = (n + kScanBlock * kScanItems - 1) / (kScanBlock * kScanItems);
+    if (threadIdx.x == 0) *s_carry_p = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t v = i < nb ? __ldcg(B.scan_tmp + i) : 0, x = v;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = s_warp[threadIdx.x], ws = w;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, ws, d); if (threadIdx.x >= d) ws += y; }
+            s_warp[threadIdx.x] = ws - w;
+        }
+        __syncthreads();
+        const uint32_t excl = *s_carry_p + s_warp[threadIdx.x >> 5] + x - v;
+        if (i < nb) B.scan_tmp[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) *s_carry_p = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { B.totals[1] = *s_carry_p; if (*s_carry_p > B.max_resp) B.totals[2] |= 2u; }
+}
 __global__ void __launch_bounds__(kScanBlock) k_scan_blocks(BatchPtrs B) {
     __shared__ uint32_t s_warp[32];
     const uint32_t n = B.totals[0];
@@ -756,36 +786,32 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_blocks(BatchPtrs B) {
     for (int j = 0; j < kScanItems; j++) { if (base + j < n) B.slot[base + j] = excl; excl += v[j]; }
     __syncthreads();
     }
-}
-__global__ void __launch_bounds__(1024) k_scan_top(BatchPtrs B) {
-    // serial-by-chunks exclusive scan of the block sums (<= a few thousand entries)
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
-    const uint32_t n = B.totals[0];
-    const uint32_t nb = (n + kScanBlock * kScanItems - 1) / (kScanBlock * kScanItems);
-    if (threadIdx.x == 0) s_carry = 0;
+    // the last CTA to finish scans the block sums (was a separate launch)
+    __shared__ uint32_t s_ticket, s_carry;
+    __threadfence();
     __syncthreads();
-    for (uint32_t base = 0; base < nb; base += blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        uint32_t v = i < nb ? B.scan_tmp[i] : 0, x = v;
-        #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((threadIdx.x & 31) >= d) x += y; }
-        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t w = s_warp[threadIdx.x], ws = w;
-            #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, ws, d); if (threadIdx.x >= d) ws += y; }
-            s_warp[threadIdx.x] = ws - w;
-        }
-        __syncthreads();
-        const uint32_t excl = s_carry + s_warp[threadIdx.x >> 5] + x - v;
-        if (i < nb) B.scan_tmp[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = excl + v;
-        __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(B.totals + 5, 1u);
+    __syncthreads();
+    if (s_ticket == gridDim.x - 1) { __threadfence(); scan_top_body(B, s_warp, &s_carry); }
+}
+// --- finalize: per-run response span + counters (prologue of the last pack kernel) ----------------
+__device__ __forceinline__ void finalize_runs(const BatchPtrs& B) {
+    const uint32_t n_msgs = B.totals[0];
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < B.n_runs; r += gridDim.x * blockDim.x) {
+        b2_run_status st = B.run_status[r];
+        auto off_of = [&](uint32_t i) -> uint32_t {
+            if (i >= n_msgs) return B.totals[1];
+            return B.slot[i] + B.scan_tmp[i / (kScanBlock * kScanItems)];
+        };
+        st.resp_off = off_of(st.first_msg);
+        st.resp_bytes = off_of(st.first_msg + st.n_msgs) - st.resp_off;
+        B.run_status[r] = st;
+        atomicAdd(B.counters + 0, (unsigned long long)st.consumed);
+        atomicAdd(B.counters + 1, (unsigned long long)st.n_msgs);
+        atomicAdd(B.counters + 2, (unsigned long long)st.resp_bytes);
+        if (st.parse_error != B2_PARSE_ERROR_NOT_ENOUGH_DATA) atomicAdd(B.counters + 4, 1ull);
+        if (r == 0) atomicAdd(B.counters + 5, 1ull);
     }
-    if (threadIdx.x == 0) { B.totals[1] = s_carry; if (s_carry > B.max_resp) B.totals[2] |= 2u; }
 }
 
 // Snappy raw-format decoder as a warp-level primitive: butil::snappy::RawUncompress
@@ -1202,6 +1228,7 @@ __global__ void __launch_bounds__(256, B2_PACK_MIN_BLOCKS) k_pack(BatchPtrs B, D
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_msgs = B.totals[0];
     if (B.totals[2] & 3u) return;
+    finalize_runs(B);
     __shared__ uint32_t s_hot[kCrcHotWords];
     crc_tabs_to_smem(s_hot, B.crc_adv);
     CrcTabs ct; ct.hot = s_hot; ct.tree = B.crc_adv + kCrcHotWords;
@@ -1493,7 +1520,9 @@ __global__ void __launch_bounds__(kPackWarps * 32, 1) k_pack_tma(BatchPtrs B, De
 __global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs B, DevConfig C) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_msgs = B.totals[0];
-    if ((B.totals[2] & 3u) || B.totals[3] == 0) return;
+    if (B.totals[2] & 3u) return;
+    finalize_runs(B);                                  // (was a separate launch)
+    if (B.totals[3] == 0) return;
     __shared__ uint32_t s_hot[kCrcHotWords];
     crc_tabs_to_smem(s_hot, B.crc_adv);
     CrcTabs ct; ct.hot = s_hot; ct.tree = B.crc_adv + kCrcHotWords;
@@ -1504,27 +1533,6 @@ __global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs
         const bool slow = i < n_msgs && reinterpret_cast<const uint8_t*>(B.jobs + i)[11] == 0;   // PackJob::fast
         for (uint32_t m = __ballot_sync(0xffffffffu, slow); m; m &= m - 1) pack_one(B, C, i0 + (__ffs(m) - 1), lane, ct);
     }
-}
-
-// --- k_finalize: per-run response span + counters ----------------------------
-__global__ void __launch_bounds__(256) k_finalize(BatchPtrs B) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= B.n_runs) return;
-    if (B.totals[2] & 3u) return;
-    b2_run_status st = B.run_status[r];
-    const uint32_t n_msgs = B.totals[0];
-    auto off_of = [&](uint32_t i) -> uint32_t {
-        if (i >= n_msgs) return B.totals[1];
-        return B.slot[i] + B.scan_tmp[i / (kScanBlock * kScanItems)];
-    };
-    st.resp_off = off_of(st.first_msg);
-    st.resp_bytes = off_of(st.first_msg + st.n_msgs) - st.resp_off;
-    B.run_status[r] = st;
-    atomicAdd(B.counters + 0, (unsigned long long)st.consumed);
-    atomicAdd(B.counters + 1, (unsigned long long)st.n_msgs);
-    atomicAdd(B.counters + 2, (unsigned long long)st.resp_bytes);
-    if (st.parse_error != B2_PARSE_ERROR_NOT_ENOUGH_DATA) atomicAdd(B.counters + 4, 1ull);
-    if (r == 0) atomicAdd(B.counters + 5, 1ull);
 }
 
 // --- k_small: the whole path in ONE launch for latency-sized batches ------------------------------
