@@ -158,6 +158,152 @@ def cpu_arm(data, runs, threads, min_seconds):
     return best[1] / best[0], best[1], n
 
 
+def stream_snappy_main(args):
+    """BASELINE configs[4]: streaming_rpc DATA frames carrying 256 KiB snappy-compressed messages, 64 streams per GPU;
+    the device cuts the frames, decodes StreamFrameMeta and decompresses every payload (b2_set_stream_handler).
+    Same JSON shape as the headline line; the unit of work is one frame."""
+    import torch
+    import brpc_b200
+    from brpc_b200 import press
+    from brpc_b200.abi import PinnedBuffer
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    use_dist = world > 1
+    if use_dist:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank if use_dist else 0
+    torch.cuda.set_device(dev)
+    hbm_peak, peak_src = read_peaks()
+    steps, warmup = max(1, min(args.steps, 100)), max(3, args.warmup)
+    RAW = 256 << 10
+    rng = np.random.default_rng(20260921 + rank)
+    table = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ", np.uint8)
+    pattern = np.resize(table[:36], RAW)                                   # brpc_snappy_compress_unittest.cpp text: a-z0-9 repeating
+    if args.payload_kind == 0:
+        raws = [pattern]
+    else:
+        raws = [table[rng.integers(0, 62, RAW)] for _ in range(4)]         # uniform random over the 62-symbol table
+    K = args.frames_per_stream
+    n_frames = N_SOCKETS * K
+    gen = brpc_b200.Context(device=dev, max_batch_bytes=8 << 20, max_msgs=64, max_runs=8)
+    flat = np.concatenate(raws)
+    comps = gen.snappy_compress_batch(flat, np.arange(len(raws), dtype=np.uint32) * RAW, np.full(len(raws), RAW, np.uint32),
+                                      len(raws) * (RAW + RAW // 6 + 64))  # the device encoder (bit-exact with the vendored snappy)
+    del gen
+    streams = []
+    for s_ in range(N_SOCKETS):
+        sid = rank * N_SOCKETS + s_
+        streams.append(b"".join(press.stream_frame(1000 + sid, 5000 + sid, comps[(s_ + i) % len(comps)]) for i in range(K)))
+    stride = (max(len(x) for x in streams) + 15) // 16 * 16
+    nbytes = N_SOCKETS * stride
+    buf = PinnedBuffer(nbytes)
+    runs = np.zeros(N_SOCKETS, dtype=brpc_b200.RUN_DT)
+    for s_, x in enumerate(streams):
+        buf.array[s_ * stride:s_ * stride + len(x)] = np.frombuffer(x, np.uint8)
+        runs[s_] = (rank * N_SOCKETS + s_, s_ * stride, len(x), -1, 0)
+    out_bytes = n_frames * (RAW + 64) + (4 << 20)
+    mk = lambda: brpc_b200.Context(device=dev, max_batch_bytes=nbytes + (1 << 20), max_msgs=n_frames + 1024, max_runs=N_SOCKETS,
+                                   max_resp_bytes=out_bytes, stream_handler=1)
+    ctxs = [mk() for _ in range(2)]
+    rs, msgs, resp, info = ctxs[0].process_batch_ptr(buf.ptr, nbytes, runs)
+    assert len(msgs) == n_frames and np.all(msgs["status"] == 4) and np.all(msgs["resp_len"] == RAW) and np.all(msgs["error_code"] == 0)
+    for i in range(0, n_frames, max(1, n_frames // 16)):                  # decompressed bytes == what was compressed
+        s_, k = divmod(i, K)
+        o = int(msgs["resp_off"][i])
+        assert np.array_equal(resp[o:o + RAW], raws[(s_ + k) % len(raws)]), "stream frame %d decompressed wrong" % i
+    req_bytes = int(rs["consumed"].sum())
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for cx in ctxs:
+        cx.upload_ptr(buf.ptr, nbytes, runs)
+    for s_ in range(warmup * 2):
+        ctxs[s_ % 2].launch()
+    for cx in ctxs:
+        cx.wait()
+    sampler = ClockSampler(dev); sampler.start()
+    barrier()
+    for s_ in range(steps):
+        ctxs[s_ % 2].launch()
+    for cx in ctxs:
+        cx.wait()
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = max(ctxs[0].elapsed_ms_to(cx) for cx in ctxs[:min(2, steps)])
+    stage_acc = {}
+    for _ in range(3):
+        ctxs[0].execute()
+        for name, ms in ctxs[0].stage_times():
+            stage_acc.setdefault(name, []).append(ms)
+    stages = {k: statistics.mean(v) for k, v in stage_acc.items()}
+    e2e_steps = max(4, min(steps, 12))
+    for cx in ctxs:
+        cx.submit_ptr(buf.ptr, nbytes, runs)
+    for cx in ctxs:
+        cx.collect()
+    barrier()
+    t0 = time.perf_counter()
+    for s_ in range(min(2, e2e_steps)):
+        ctxs[s_].submit_ptr(buf.ptr, nbytes, runs)
+    for s_ in range(e2e_steps):
+        cx = ctxs[s_ % 2]
+        r3, m3, p3, _ = cx.collect()
+        assert len(m3) == n_frames
+        if s_ + 2 < e2e_steps:
+            cx.submit_ptr(buf.ptr, nbytes, runs)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t_dev = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n_frames)], dtype=torch.float64, device="cuda")
+    counters = ctxs[0].counters()
+    if use_dist:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        cnt = torch.tensor(counters, dtype=torch.int64, device="cuda")
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)                        # the NCCL counter reduce of configs[4]
+        counters = cnt.tolist()
+    dev_ms_max, e2e_ms_max = t_dev.tolist()
+    ms_per_step = dev_ms_max / steps
+    if rank == 0:
+        alg = float(req_bytes + n_frames * (RAW + DESC_BYTES))            # SURVEY §8d: 12+meta+C read, U written, 64 B desc
+        dom = max(stages, key=stages.get)
+        line = {"metric": "streaming_rpc snappy frames (256 KiB) decompressed", "value": tot.item() / (ms_per_step * 1e-3), "unit": "frames/s",
+                "n_gpus": world if use_dist else 1, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "streaming_echo_c++-style STRM DATA frames, %d streams/GPU x %d frames, 256 KiB %s messages, snappy"
+                                       % (N_SOCKETS, K, "a-z0-9 pattern" if args.payload_kind == 0 else "random-62"),
+                           "compressed_bytes_per_frame": len(comps[0]), "l2": "outputs larger than L2"},
+                "decompressed_GBps": tot.item() * RAW / (ms_per_step * 1e-3) / 1e9,
+                "e2e": {"value": tot.item() / (e2e_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(nbytes + runs.nbytes),
+                        "d2h_bytes_per_step": int(n_frames * (RAW + 64) + len(rs) * 32), "ms_per_step": e2e_ms_max},
+                "gpu_launches": int(steps * info["n_launches"]),
+                "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": alg / (stages[dom] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": alg / (stages[dom] * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg, "kernel_ms": stages[dom], "stage_ms": stages},
+                "clocks": clocks, "counters_allreduced": counters}
+        if not args.no_cpu_baseline:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import _oracle as O
+            cfg = O.make_config(stream_handler=1)
+            sub = runs[:4].copy()
+            t0 = time.perf_counter(); n = 0; best = None
+            while time.perf_counter() - t0 < 8.0 or n < 2:
+                t1 = time.perf_counter()
+                ors, om, _ = O.process_batch(cfg, buf.array, sub, msg_cap=4 * K + 16, resp_cap=4 * K * (RAW + 64) + (1 << 20))
+                dt = time.perf_counter() - t1; n += 1
+                best = dt if best is None or dt < best else best
+            line["cpu_baseline"] = {"value": len(om) / best, "unit": "frames/s", "cores": 1, "kind": "port",
+                                    "sample": "4 of the %d streams (%d frames/pass), best of %d passes, single thread" % (N_SOCKETS, len(om), n)}
+        print(json.dumps(line))
+    if use_dist:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,7 +318,12 @@ def main():
     ap.add_argument("--payload-kind", type=int, default=0, help="0 = 'r' fill, 1 = random over 62 symbols")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--pipeline", type=int, default=2, help="resident batches in flight per GPU (one ctx + stream each)")
+    ap.add_argument("--workload", default="echo", choices=["echo", "stream_snappy"],
+                    help="echo = the headline metric; stream_snappy = BASELINE configs[4] (256 KiB snappy streaming frames), a side measurement")
+    ap.add_argument("--frames-per-stream", type=int, default=8)
     args = ap.parse_args()
+    if args.workload == "stream_snappy":
+        return stream_snappy_main(args)
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

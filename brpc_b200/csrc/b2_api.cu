@@ -36,10 +36,10 @@ struct b2_ctx {
     // device
     uint8_t* d_bytes = nullptr; b2_run* d_runs = nullptr; uint32_t* d_run_tile_base = nullptr;
     TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; uint32_t* d_tile_scratch = nullptr; b2_run_status* d_run_status = nullptr;
-    uint32_t* d_frame_off = nullptr; uint32_t* d_frame_run = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr; PackJob* d_jobs = nullptr; uint8_t* d_heads = nullptr;
+    uint32_t* d_frame_off = nullptr; uint32_t* d_frame_run = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr; PackJob* d_jobs = nullptr; uint32_t* d_slow_idx = nullptr; uint8_t* d_heads = nullptr;
     uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr; uint8_t* d_unz = nullptr; uint16_t* d_snappy_tab = nullptr; HpackState* d_hpack = nullptr;
     uint32_t* d_crc_adv = nullptr; unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
-    uint32_t max_tiles = 0; uint32_t n_sms = 148; bool use_tma_pack = true;
+    uint32_t max_tiles = 0; uint32_t n_sms = 148; bool use_tma_pack = true; uint32_t stage_mask = 7;  // debug: 1 front stages, 2 k_pack_tma, 4 k_pack_slow
     // pinned host mirrors
     b2_run_status* h_run_status = nullptr; b2_msg_desc* h_msgs = nullptr; uint8_t* h_resp = nullptr;
     uint32_t* h_totals = nullptr; uint32_t* h_run_tile_base = nullptr;
@@ -83,7 +83,7 @@ extern "C" void b2_ctx_destroy(b2_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->opt.device);
     cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch);
-    cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_frame_run); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_heads); cudaFree(c->d_slot);
+    cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_frame_run); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_slow_idx); cudaFree(c->d_heads); cudaFree(c->d_slot);
     cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_hpack); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
     cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
     cudaFreeHost(c->h_run_tile_base);
@@ -135,6 +135,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     ALLOC(c->d_msgs, sizeof(b2_msg_desc) * (size_t)o->max_msgs);
     ALLOC(c->d_aux, sizeof(MsgAux) * (size_t)o->max_msgs);
     ALLOC(c->d_jobs, sizeof(PackJob) * (size_t)o->max_msgs);
+    ALLOC(c->d_slow_idx, sizeof(uint32_t) * (size_t)o->max_msgs);
     ALLOC(c->d_heads, (size_t)kHeadBytes * (size_t)o->max_msgs);
     ALLOC(c->d_slot, 4 * ((size_t)o->max_msgs + 1));
     ALLOC(c->d_scan_tmp, 4 * (size_t)scan_blocks);
@@ -174,6 +175,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
         CU(cudaMemcpy(c->d_crc_adv, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
     }
     CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CU(cudaFuncSetAttribute(k_pack_slow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * kSnapRing)));
     CU(cudaFuncSetAttribute(k_pack_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PackWarpSmem) * kPackWarps)));
     if (const char* e = getenv("B2_PACK")) c->use_tma_pack = strcmp(e, "reg") != 0;
     if (const char* e = getenv("B2_SMALL")) c->use_fused_small = strcmp(e, "off") != 0;
@@ -224,7 +226,7 @@ static BatchPtrs make_ptrs(b2_ctx* c) {
     BatchPtrs B;
     B.bytes = c->d_bytes; B.runs = c->d_runs; B.run_tile_base = c->d_run_tile_base; B.tiles = c->d_tiles;
     B.tile_base = c->d_tile_base; B.tile_scratch = c->d_tile_scratch; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.frame_run = c->d_frame_run; B.msgs = c->d_msgs;
-    B.aux = c->d_aux; B.jobs = c->d_jobs; B.heads = c->d_heads; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.unz = c->d_unz; B.snappy_tab = c->d_snappy_tab; B.counters = c->d_counters;
+    B.aux = c->d_aux; B.jobs = c->d_jobs; B.slow_idx = c->d_slow_idx; B.heads = c->d_heads; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.unz = c->d_unz; B.snappy_tab = c->d_snappy_tab; B.counters = c->d_counters;
     B.totals = c->d_totals; B.methods = c->d_methods; B.crc_adv = c->d_crc_adv;
     B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes;
     B.runs = reinterpret_cast<const b2_run*>(c->d_meta);
@@ -281,6 +283,7 @@ extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, co
         c->small_off_rs = 64; c->small_off_msgs = 64 + n_runs * 32; c->small_off_resp = (c->small_off_msgs + mb * 64 + 255u) & ~255u;
         c->small_total = c->small_off_resp + c->small_resp;
     }
+    if (const char* e = getenv("B2_STAGE_MASK")) c->stage_mask = (uint32_t)atoi(e);   // timing experiments only (tools/overlap_probe.py)
     c->uploaded = true; c->executed = false;
     return B2_OK;
 }
@@ -292,7 +295,8 @@ static int launch_pipeline(b2_ctx* c) {
     int st = 0; uint32_t launches = 0;
     const bool prof = c->profile_stages;
     auto mark = [&](const char* name) { if (prof) { c->stage_names[st] = name; cudaEventRecord(c->ev[st + 1], s); st++; } };
-    CU(cudaMemsetAsync(B.totals, 0, 32, s));
+    const uint32_t mask = c->stage_mask;
+    if (mask & 1) CU(cudaMemsetAsync(B.totals, 0, 32, s));
     CU(cudaEventRecord(c->ev[0], s));
     if (c->n_runs == 0) { c->n_stages = 0; c->last_launches = 0; return B2_OK; }
     if (c->small && c->use_fused_small && !prof) {
@@ -303,6 +307,8 @@ static int launch_pipeline(b2_ctx* c) {
         CU(cudaGetLastError());
         return B2_OK;
     }
+    const uint32_t sms = c->n_sms;
+    if (mask & 1) {
     if (c->n_tiles) {
         k_tile_search<<<(c->n_tiles * 32 + 255) / 256, 256, 0, s>>>(B, C); launches++; mark("tile_search");
         k_tile_walk<<<(c->n_tiles + 127) / 128, 128, 0, s>>>(B, C); launches++; mark("tile_walk");
@@ -315,13 +321,13 @@ static int launch_pipeline(b2_ctx* c) {
     if (c->n_tiles) { k_frame_table<<<(c->n_tiles + 127) / 128, 128, 0, s>>>(B, C); launches++; mark("frame_table"); }
     // message-count dependent kernels are persistent: fixed grids (multiples of the SM count)
     // stride over the device-side message count, so no host round trip sizes a launch
-    const uint32_t sms = c->n_sms;
     k_decode<<<sms * B2_DECODE_MIN_BLOCKS, kDecodeWarps * 32, 0, s>>>(B, C); launches++; mark("decode");
     k_scan_blocks<<<sms, kScanBlock, 0, s>>>(B); launches++;
     mark("scan");
+    }
     if (c->use_tma_pack) {
-        k_pack_tma<<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C); launches++; mark("pack");
-        k_pack_slow<<<sms * B2_SLOW_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack_slow");
+        if (mask & 2) { k_pack_tma<<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C); launches++; mark("pack"); }
+        if (mask & 4) { k_pack_slow<<<sms * B2_SLOW_MIN_BLOCKS, 256, 8 * kSnapRing, s>>>(B, C); launches++; mark("pack_slow"); }
     } else { k_pack<<<sms * B2_PACK_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack"); }
     if (!prof) { c->stage_names[0] = "pipeline"; cudaEventRecord(c->ev[1], s); st = 1; }
     c->n_stages = st; c->last_launches = launches;
@@ -520,10 +526,11 @@ extern "C" int b2_crc32c_batch(b2_ctx* c, const void* bytes, uint32_t nbytes, co
 __global__ void k_snappy_batch(const uint8_t* bytes, const uint32_t* offs, const uint32_t* lens, uint32_t n, uint8_t* out,
                                const uint32_t* out_offs, const uint32_t* out_caps, int32_t* out_lens) {
     const uint32_t lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
+    __shared__ __align__(16) uint8_t s_rings[8 * kSnapRing];
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += n_warps) {
         uint32_t produced = 0;
         const bool ok = out_caps[i] != 0xffffffffu &&
-                        warp_snappy_decode(bytes + offs[i], lens[i], out + out_offs[i], out_caps[i], lane, produced);
+                        warp_snappy_decode(bytes + offs[i], lens[i], out + out_offs[i], out_caps[i], lane, produced, s_rings + (threadIdx.x >> 5) * kSnapRing);
         if (lane == 0) out_lens[i] = ok ? (int32_t)produced : -1;
     }
 }

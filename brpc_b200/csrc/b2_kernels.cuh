@@ -93,6 +93,7 @@ struct BatchPtrs {
     b2_msg_desc* msgs;
     MsgAux* aux;
     PackJob* jobs;                   // [max_msgs]
+    uint32_t* slow_idx;              // [max_msgs] messages k_pack_slow has to serve (unordered), count in totals[3]
     uint8_t* heads;                  // [max_msgs * kHeadBytes] reply prefixes pre-shifted to their slot alignment
     uint32_t* slot;                  // [max_msgs+1] slot sizes -> exclusive offsets
     uint32_t* scan_tmp;              // block sums
@@ -499,8 +500,13 @@ __device__ __forceinline__ void decode_round(const BatchPtrs& B, const DevConfig
     __syncwarp();
     bool is_slow = false;
     if (i < n_msgs) { decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 15u), S.head[lane]); is_slow = B.jobs[i].fast == 0; }
-    const uint32_t n_slow = __popc(__ballot_sync(0xffffffffu, is_slow));
-    if (lane == 0 && n_slow) atomicAdd(B.totals + 3, n_slow);          // k_pack_slow returns at once when this stays 0
+    const uint32_t slow_mask = __ballot_sync(0xffffffffu, is_slow);
+    if (slow_mask) {                                                    // k_pack_slow returns at once when totals[3] stays 0
+        uint32_t sbase = 0;
+        if (lane == 0) sbase = atomicAdd(B.totals + 3, (uint32_t)__popc(slow_mask));
+        sbase = __shfl_sync(0xffffffffu, sbase, 0);
+        if (is_slow) B.slow_idx[sbase + __popc(slow_mask & ((1u << lane) - 1u))] = i;
+    }
     __syncwarp();
     // heads of 32 consecutive messages are contiguous: coalesced 16-byte stores
     {
@@ -835,46 +841,101 @@ __device__ __forceinline__ bool snappy_preamble(const uint8_t* in, uint32_t n, u
     return true;
 }
 __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t lane);
+// `ring` (optional): kSnapRing bytes of shared memory owned by this warp, mirroring the most recent output
+// (ring[p & (kSnapRing-1)] == out[p] for p in [op - kSnapRing, op)).  A copy whose offset fits in it reads its
+// source from shared memory (a back-reference to bytes the warp has just stored would otherwise pay an L2 round
+// trip per element: stores do not allocate in L1).  The tag stream itself is read 32 bytes at a time, one byte
+// per lane, and walked with shuffles, so a run of short elements costs one global load.
+constexpr uint32_t kSnapRing = 4096;
+__device__ __forceinline__ uint32_t ring_ld(uint32_t ring_s, uint32_t p) {
+    uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(ring_s + (p & (kSnapRing - 1))) : "memory"); return v;
+}
+__device__ __forceinline__ void ring_st(uint32_t ring_s, uint32_t p, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(ring_s + (p & (kSnapRing - 1))), "r"(v) : "memory");
+}
 __device__ __noinline__ bool warp_snappy_decode(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, uint32_t lane,
-                                                uint32_t& produced) {
+                                                uint32_t& produced, uint8_t* ring = nullptr) {
     uint32_t ulen, ip;
     produced = 0;
     if (!snappy_preamble(in, n, ulen, ip)) return false;
     if (ulen > cap) return false;
+    const bool use_ring = ring != nullptr;
+    const uint32_t ring_s = use_ring ? (uint32_t)__cvta_generic_to_shared(ring) : 0u;
     uint32_t op = 0;
+    // look-ahead window [wbase, wbase + 32): lane L holds bytes wbase+L .. wbase+L+4 (w_lo = first four, w_b4 = the fifth)
+    uint32_t wbase = 0, wbyte = 0, w_lo = 0, w_b4 = 0;
+    auto refill = [&](uint32_t at) {
+        wbase = at;
+        wbyte = (wbase + lane < n) ? in[wbase + lane] : 0u;
+        const uint32_t b1 = __shfl_down_sync(0xffffffffu, wbyte, 1), b2 = __shfl_down_sync(0xffffffffu, wbyte, 2);
+        const uint32_t b3 = __shfl_down_sync(0xffffffffu, wbyte, 3);
+        w_b4 = __shfl_down_sync(0xffffffffu, wbyte, 4);
+        w_lo = wbyte | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    };
+    refill(ip);
     while (ip < n) {
-        const uint32_t c = in[ip++];
+        if (ip + 5 > wbase + 32) refill(ip);                          // a whole tag (<= 5 bytes) is inside, on lanes <= 27
+        const uint32_t t = __shfl_sync(0xffffffffu, w_lo, ip - wbase);            // tag + three operand bytes
+        const uint32_t c = t & 0xffu;
+        ip++;
         if ((c & 3u) == 0) {                                         // literal
             uint32_t len = (c >> 2) + 1;
             if (len >= 61) {
                 const uint32_t ll = len - 60;
                 if (n - ip < ll) return false;
-                uint32_t v = 0;
-                for (uint32_t k = 0; k < ll; k++) v |= (uint32_t)in[ip + k] << (8 * k);
-                len = v + 1; ip += ll;
+                const uint32_t v = (t >> 8) | (__shfl_sync(0xffffffffu, w_b4, ip - 1 - wbase) << 24);
+                len = (ll == 4 ? v : (v & ((1u << (8 * ll)) - 1u))) + 1; ip += ll;
                 if (len == 0) return false;                          // 2^32 wrap: cannot fit
             }
             if (len > n - ip) return false;                          // premature end of input
             if (len > ulen - op) return false;                       // SnappyArrayWriter::Append: no room
-            warp_copy(out + op, in + ip, len, lane);
+            if (ip + len <= wbase + 32) {                            // the literal's bytes are already in the window
+                const uint32_t b = __shfl_sync(0xffffffffu, wbyte, (ip - wbase + lane) & 31);
+                if (lane < len) { out[op + lane] = (uint8_t)b; if (use_ring) ring_st(ring_s, op + lane, b); }
+            } else {
+                warp_copy(out + op, in + ip, len, lane);
+                if (use_ring) {                                      // keep the mirror: the last min(len, ring) bytes
+                    const uint32_t keep = min(len, kSnapRing), skip = len - keep;
+                    for (uint32_t i = lane; i < keep; i += 32) ring_st(ring_s, op + skip + i, in[ip + skip + i]);
+                }
+            }
             ip += len; op += len;
         } else {                                                     // copy
             uint32_t len, offset;
             if ((c & 3u) == 1) {
                 if (n - ip < 1) return false;
-                len = ((c >> 2) & 7u) + 4; offset = ((c >> 5) << 8) | in[ip]; ip += 1;
+                len = ((c >> 2) & 7u) + 4; offset = ((c >> 5) << 8) | ((t >> 8) & 0xffu); ip += 1;
             } else if ((c & 3u) == 2) {
                 if (n - ip < 2) return false;
-                len = (c >> 2) + 1; offset = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8); ip += 2;
+                len = (c >> 2) + 1; offset = (t >> 8) & 0xffffu; ip += 2;
             } else {
                 if (n - ip < 4) return false;
                 len = (c >> 2) + 1;
-                offset = (uint32_t)in[ip] | ((uint32_t)in[ip + 1] << 8) | ((uint32_t)in[ip + 2] << 16) | ((uint32_t)in[ip + 3] << 24); ip += 4;
+                offset = (t >> 8) | (__shfl_sync(0xffffffffu, w_b4, ip - 1 - wbase) << 24); ip += 4;
             }
             if (offset == 0 || offset > op) return false;            // AppendFromSelf: op - base <= offset - 1
             if (len > ulen - op) return false;
-            const uint8_t* from = out + op - offset;
-            for (uint32_t i = lane; i < len; i += 32) out[op + i] = from[offset >= len ? i : i % offset];
+            // byte i of the element comes from source byte i mod offset (an overlapping copy repeats its period)
+            const uint32_t sp = op - offset;
+            uint32_t i0 = lane, i1 = lane + 32;                      // len <= 64: at most two bytes per lane
+            uint32_t s0, s1;
+            if (offset >= len) { s0 = i0; s1 = i1; }
+            else if (offset >= 32) { s0 = i0 >= offset ? i0 - offset : i0; s1 = i1 >= offset ? i1 - offset : i1; }   // i < 64 <= 2 * offset
+            else { s0 = i0 % offset; s1 = i1 % offset; }
+            if (use_ring && offset <= kSnapRing - 64) {              // sources [op-offset, op) stay mirrored through this element's writes
+                uint32_t b0 = 0, b1 = 0;
+                if (i0 < len) b0 = ring_ld(ring_s, sp + s0);
+                if (i1 < len) b1 = ring_ld(ring_s, sp + s1);
+                if (i0 < len) { out[op + i0] = (uint8_t)b0; ring_st(ring_s, op + i0, b0); }
+                if (i1 < len) { out[op + i1] = (uint8_t)b1; ring_st(ring_s, op + i1, b1); }
+            } else {
+                const uint8_t* from = out + sp;
+                uint32_t b0 = 0, b1 = 0;
+                if (i0 < len) b0 = from[s0];
+                if (i1 < len) b1 = from[s1];
+                if (i0 < len) { out[op + i0] = (uint8_t)b0; if (use_ring) ring_st(ring_s, op + i0, b0); }
+                if (i1 < len) { out[op + i1] = (uint8_t)b1; if (use_ring) ring_st(ring_s, op + i1, b1); }
+            }
             op += len;
         }
         __syncwarp();                                                // later elements read what this one wrote
@@ -1049,7 +1110,7 @@ __device__ __forceinline__ uint32_t crc32c_bytes_serial(uint32_t l, const uint8_
 // Tables (built on the host): hot = T[16][256] (T[k][b] = byte b followed by k zero bytes) then
 // A512[4][256]; tree = ADV_{16<<t}[4][256], t = 0..4.  `hot` may live in shared memory.
 constexpr uint32_t kCrcHotWords = 20 * 256, kCrcTreeWords = 5 * 4 * 256;
-struct CrcTabs { const uint32_t* hot; const uint32_t* tree; };
+struct CrcTabs { const uint32_t* hot; const uint32_t* tree; uint8_t* ring = nullptr; };   // + this warp's snappy ring (or null)
 __device__ __forceinline__ uint32_t crc_adv4(const uint32_t* T, uint32_t x) {      // 4x256 byte-sliced operator
     return T[x & 0xff] ^ T[256 + ((x >> 8) & 0xff)] ^ T[512 + ((x >> 16) & 0xff)] ^ T[768 + (x >> 24)];
 }
@@ -1179,7 +1240,15 @@ __device__ __forceinline__ void warp_copy(uint8_t* dst, const uint8_t* src, uint
         const uint32_t done = head + (nv << 4);
         if (lane < n - done) dst[done + lane] = src[done + lane];
     } else {
-        for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+        uint32_t i = lane;
+        for (; i + 224 < n; i += 256) {                        // 8 independent byte loads in flight per lane
+            uint8_t v[8];
+            #pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = src[i + 32 * k];
+            #pragma unroll
+            for (int k = 0; k < 8; k++) dst[i + 32 * k] = v[k];
+        }
+        for (; i < n; i += 32) dst[i] = src[i];
     }
 }
 
@@ -1246,7 +1315,7 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
     if (d.status == B2_MSG_STREAM_FRAME) {
         // the application-level SnappyDecompress of a streaming DATA frame's payload
         uint32_t produced = 0;
-        const bool ok = warp_snappy_decode(frame + 12 + d.meta_size, a.att_off, B.resp + slot_off, a.msg_len, lane, produced);
+        const bool ok = warp_snappy_decode(frame + 12 + d.meta_size, a.att_off, B.resp + slot_off, a.msg_len, lane, produced, ct.ring);
         if (lane == 0) {
             if (ok) { B.msgs[i].resp_off = slot_off; B.msgs[i].resp_len = produced; }
             else { B.msgs[i].resp_off = slot_off; B.msgs[i].resp_len = 0; B.msgs[i].error_code = B2_EREQUEST; }
@@ -1264,7 +1333,7 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
         uint32_t off = d.resp_off, len = d.resp_len;
         if (ok && d.status == B2_MSG_RESPONSE_UNZ) {
             uint32_t produced = 0;
-            ok = warp_snappy_decode(body, body_len, B.resp + slot_off, a.msg_len, lane, produced);
+            ok = warp_snappy_decode(body, body_len, B.resp + slot_off, a.msg_len, lane, produced, ct.ring);
             Span msg; msg.off = 0; msg.len = 0;
             if (ok) ok = decode_echo_request(B.resp + slot_off, produced, msg);
             off = slot_off + msg.off; len = msg.len;
@@ -1292,7 +1361,7 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
         int64_t bwo = (int64_t)req_size - (int64_t)d.attachment_size; if (bwo > (int64_t)req_size) bwo = req_size;
         uint8_t* scratch = B.unz + slot_off;
         uint32_t produced = 0;
-        bool ok = warp_snappy_decode(frame + 12 + d.meta_size, (uint32_t)bwo, scratch, a.msg_len, lane, produced);
+        bool ok = warp_snappy_decode(frame + 12 + d.meta_size, (uint32_t)bwo, scratch, a.msg_len, lane, produced, ct.ring);
         Span msg; msg.off = 0; msg.len = 0;
         if (ok) ok = decode_echo_request(scratch, produced, msg);
         if (!ok) status = B2_MSG_ERROR_REPLIED;
@@ -1375,8 +1444,14 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
 #define B2_PACK_WARPS 8
 #endif
 constexpr uint32_t kPackWarps = B2_PACK_WARPS;
-constexpr uint32_t kPackGroup = 8;               // messages per warp round (one lane each)
-constexpr uint32_t kStageBytes = 9216;           // per buffer, two buffers per warp
+#ifndef B2_PACK_GROUP
+#define B2_PACK_GROUP 8
+#endif
+#ifndef B2_STAGE_BYTES
+#define B2_STAGE_BYTES 9216
+#endif
+constexpr uint32_t kPackGroup = B2_PACK_GROUP;    // messages per warp round (one lane each), power of two
+constexpr uint32_t kStageBytes = B2_STAGE_BYTES;  // per buffer, two buffers per warp
 struct PackWarpSmem {
     alignas(128) uint8_t stage[2][kStageBytes];
     alignas(8) unsigned long long mbar[2];
@@ -1524,14 +1599,18 @@ __global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs
     finalize_runs(B);                                  // (was a separate launch)
     if (B.totals[3] == 0) return;
     __shared__ uint32_t s_hot[kCrcHotWords];
+    extern __shared__ __align__(16) uint8_t s_rings[];           // kSnapRing bytes per warp
     crc_tabs_to_smem(s_hot, B.crc_adv);
-    CrcTabs ct; ct.hot = s_hot; ct.tree = B.crc_adv + kCrcHotWords;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; i0 < n_msgs; i0 += n_warps * 32) {
-        // one coalesced look at 32 job flags, then the warp serves the slow ones in turn
-        const uint32_t i = i0 + lane;
-        const bool slow = i < n_msgs && reinterpret_cast<const uint8_t*>(B.jobs + i)[11] == 0;   // PackJob::fast
-        for (uint32_t m = __ballot_sync(0xffffffffu, slow); m; m &= m - 1) pack_one(B, C, i0 + (__ffs(m) - 1), lane, ct);
+    CrcTabs ct; ct.hot = s_hot; ct.tree = B.crc_adv + kCrcHotWords; ct.ring = s_rings + (threadIdx.x >> 5) * kSnapRing;
+    // the slow messages were listed by k_decode; warps pull them one at a time (sizes vary from an error
+    // text to a 256 KiB snappy stream, so the queue is dynamic: totals[6] is the ticket)
+    const uint32_t n_slow = B.totals[3];
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(B.totals + 6, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_slow) break;
+        pack_one(B, C, B.slow_idx[k], lane, ct);
     }
 }
 

@@ -57,3 +57,22 @@ def fill_batch(sp, out, n_sockets, run_bytes, start_index=0):
         total += lib.b2press_fill_run(C.byref(sp), C.byref(idx), base + s * stride, run_bytes)
         runs[s] = (s, s * stride, run_bytes, -1, 0)
     return runs, total
+
+
+def _varint(v):
+    v &= (1 << 64) - 1
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80); v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def stream_frame(stream_id, source_stream_id, data=b"", frame_type=3, has_continuation=None):
+    """Client mirror of PackStreamMessage (policy/streaming_rpc_protocol.cpp:42-58) with the StreamFrameMeta
+    fields Stream::AppendIfNotFull/Write sets on DATA frames (stream.cpp:181-186,199-204):
+    "STRM" + BE32(meta+data) + BE32(meta) + StreamFrameMeta + data."""
+    meta = b"\x08" + _varint(stream_id) + b"\x10" + _varint(source_stream_id) + b"\x18" + _varint(frame_type)
+    if has_continuation is not None:
+        meta += b"\x20" + (b"\x01" if has_continuation else b"\x00")
+    return b"STRM" + (len(meta) + len(data)).to_bytes(4, "big") + len(meta).to_bytes(4, "big") + meta + bytes(data)
