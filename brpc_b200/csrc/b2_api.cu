@@ -296,7 +296,7 @@ static int launch_pipeline(b2_ctx* c) {
     const bool prof = c->profile_stages;
     auto mark = [&](const char* name) { if (prof) { c->stage_names[st] = name; cudaEventRecord(c->ev[st + 1], s); st++; } };
     const uint32_t mask = c->stage_mask;
-    if (mask & 1) CU(cudaMemsetAsync(B.totals, 0, 32, s));
+    if (mask & 1) CU(cudaMemsetAsync(B.totals, 0, 48, s));
     CU(cudaEventRecord(c->ev[0], s));
     if (c->n_runs == 0) { c->n_stages = 0; c->last_launches = 0; return B2_OK; }
     if (c->small && c->use_fused_small && !prof) {
@@ -326,8 +326,9 @@ static int launch_pipeline(b2_ctx* c) {
     mark("scan");
     }
     if (c->use_tma_pack) {
-        if (mask & 2) { k_pack_tma<<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C); launches++; mark("pack"); }
+        // k_pack_slow first: its verify pass decides which CRC-carrying echoes k_pack_tma may move
         if (mask & 4) { k_pack_slow<<<sms * B2_SLOW_MIN_BLOCKS, 256, 8 * kSnapRing, s>>>(B, C); launches++; mark("pack_slow"); }
+        if (mask & 2) { k_pack_tma<<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C); launches++; mark("pack"); }
     } else { k_pack<<<sms * B2_PACK_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack"); }
     if (!prof) { c->stage_names[0] = "pipeline"; cudaEventRecord(c->ev[1], s); st = 1; }
     c->n_stages = st; c->last_launches = launches;

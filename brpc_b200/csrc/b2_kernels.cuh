@@ -102,7 +102,8 @@ struct BatchPtrs {
                                      // serialized replies awaiting compression (second half)
     uint16_t* snappy_tab;            // [kSnappyWarps][16384] hash tables of the snappy encoder, one per warp
     unsigned long long* counters;    // int64[B2_N_COUNTERS]
-    uint32_t* totals;                // [0]=n_msgs [1]=resp_bytes [2]=overflow flags
+    uint32_t* totals;                // [0]=n_msgs [1]=resp_bytes [2]=overflow flags [3]=slow count [4],[5]=last-CTA tickets
+                                     // [6]=slow queue ticket [7]=verify count [8]=verify queue ticket
     const DevMethod* methods;
     const uint32_t* crc_adv;         // warp CRC tables: hot [20][256] then tree [5][4][256]
     uint32_t n_runs, n_tiles, max_msgs, max_resp;
@@ -498,14 +499,24 @@ __device__ __forceinline__ void decode_round(const BatchPtrs& B, const DevConfig
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
-    bool is_slow = false;
-    if (i < n_msgs) { decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 15u), S.head[lane]); is_slow = B.jobs[i].fast == 0; }
+    bool is_slow = false, is_verify = false;
+    if (i < n_msgs) {
+        decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 15u), S.head[lane]);
+        const uint32_t f = B.jobs[i].fast; is_slow = f == 0; is_verify = f == 2;
+    }
     const uint32_t slow_mask = __ballot_sync(0xffffffffu, is_slow);
     if (slow_mask) {                                                    // k_pack_slow returns at once when totals[3] stays 0
         uint32_t sbase = 0;
         if (lane == 0) sbase = atomicAdd(B.totals + 3, (uint32_t)__popc(slow_mask));
         sbase = __shfl_sync(0xffffffffu, sbase, 0);
         if (is_slow) B.slow_idx[sbase + __popc(slow_mask & ((1u << lane) - 1u))] = i;
+    }
+    const uint32_t ver_mask = __ballot_sync(0xffffffffu, is_verify);
+    if (ver_mask) {                                                     // verify list: same array, filled from the top
+        uint32_t vbase = 0;
+        if (lane == 0) vbase = atomicAdd(B.totals + 7, (uint32_t)__popc(ver_mask));
+        vbase = __shfl_sync(0xffffffffu, vbase, 0);
+        if (is_verify) B.slow_idx[B.max_msgs - 1 - (vbase + __popc(ver_mask & ((1u << lane) - 1u)))] = i;
     }
     __syncwarp();
     // heads of 32 consecutive messages are contiguous: coalesced 16-byte stores
@@ -543,7 +554,7 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
     d.run_idx = B.frame_run[i];
     MsgAux a; a.msg_off = a.msg_len = a.att_len = a.att_off = a.cks_off = a.cks_len = 0;
     a.svc_off = a.svc_len = a.mth_off = a.mth_len = 0; a.pad = 0; a.err_kind = kErrNone;
-    uint32_t resp_len = 0;
+    uint32_t resp_len = 0, reserve = 0;               // reserve: slot bytes beyond resp_len a second outcome may need
     const uint8_t* meta_p = frame + 12;
     const uint32_t req_size = d.body_size - d.meta_size;
     if (proto == B2_PROTOCOL_STREAMING_RPC) {
@@ -693,18 +704,18 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                 b2_msg_desc e = d; MsgAux ea = a; e.error_code = B2_EREQUEST; ea.err_kind = kErrParseRequest;
                 const uint32_t tl = error_text_len(C, B.methods, e, ea, frame);
                 const uint32_t el = 12 + response_meta_len(B2_EREQUEST, tl, 0, m.correlation_id, 0, 0, a.cks_len);
-                if (a.pad + resp_len < el) resp_len = el - a.pad;   // slot must hold either reply (error reply is packed at pad 0)
+                if (a.pad + resp_len < el) reserve = el - a.pad;    // slot must hold either reply (error reply is packed at pad 0)
             }
         }
     }
     d.resp_len = resp_len;
     B.msgs[i] = d;
     B.aux[i] = a;
-    const uint32_t slot_len = resp_len ? ((a.pad + resp_len + 15u) & ~15u) : 0u;
+    const uint32_t slot_len = resp_len ? ((a.pad + max(resp_len, reserve) + 15u) & ~15u) : 0u;
     B.slot[i] = slot_len;
     // ---- bandwidth path: pre-build the reply prefix, shifted to the slot alignment -------------
     PackJob job; job.src_off = 0; job.bulk_len = 0; job.head_len = 0; job.pad = (uint8_t)a.pad; job.fast = 0; job.slot_len = slot_len;
-    if (d.status == B2_MSG_ECHOED && d.checksum_type != B2_CHECKSUM_TYPE_CRC32C && d.compress_type == B2_COMPRESS_TYPE_NONE &&
+    if (d.status == B2_MSG_ECHOED && d.compress_type == B2_COMPRESS_TYPE_NONE &&
         B.methods[d.method_idx].response_checksum_type == B2_CHECKSUM_TYPE_NONE &&
         B.methods[d.method_idx].response_compress_type == B2_COMPRESS_TYPE_NONE &&
         (a.att_len == 0 || a.att_off == a.msg_off + a.msg_len)) {
@@ -730,7 +741,9 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
             *p++ = 0x0a; p = put_varint(p, a.msg_len);
             for (uint32_t k = 0; k < lead; k++) *p++ = frame[a.msg_off + k];
             while (p < h + hl) *p++ = 0;
-            job.src_off = gs + lead; job.bulk_len = (n - lead + 15u) & ~15u; job.head_len = (uint16_t)hl; job.fast = 1;
+            job.src_off = gs + lead; job.bulk_len = (n - lead + 15u) & ~15u; job.head_len = (uint16_t)hl;
+            // a CRC32C-carrying request takes the bandwidth path once k_pack_slow's verify pass has checked it (fast 2 -> 1)
+            job.fast = d.checksum_type == B2_CHECKSUM_TYPE_CRC32C ? 2 : 1;
         }
     }
     B.jobs[i] = job;
@@ -1130,25 +1143,23 @@ __device__ __forceinline__ uint32_t warp_crc32c_update(uint32_t l, const uint8_t
     const uint4* a0 = reinterpret_cast<const uint4*>(p - lead);
     const uint32_t W = (lead + n) >> 4, tailn = (lead + n) & 15u;    // whole 16-byte blocks from a0
     const uint32_t off = (32u - (W & 31u)) & 31u, rows = (W + off) >> 5;
+    // the incoming register lands on message bytes 0..3 = virtual bytes lead..lead+3, i.e. words k0, k0+1 of blocks 0/1
+    const uint32_t k0 = lead >> 2, sh = 8 * (lead & 3u);
+    const uint32_t x_lo = l << sh, x_hi = sh ? l >> (32 - sh) : 0u;
     uint32_t R = 0;
     for (uint32_t r = 0; r < rows; r++) {
         const int32_t v = (int32_t)(r * 32 + lane) - (int32_t)off;
         uint4 blk = make_uint4(0, 0, 0, 0);
         if (v >= 0) {
             blk = __ldg(a0 + v);
-            if (v <= 1) {
-                // the incoming register lands on message bytes 0..3 = virtual bytes lead..lead+3 (blocks 0 and 1);
-                // the bytes in front of the message are zeroed
+            if (v <= 1) {                                            // zero the bytes in front of the message, fold the register in
                 uint32_t w[4] = { blk.x, blk.y, blk.z, blk.w };
                 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    const int byte0 = v * 16 + k * 4;
-                    #pragma unroll
-                    for (int bb = 0; bb < 4; bb++) {
-                        const int vi = byte0 + bb;
-                        if (vi < (int)lead) w[k] &= ~(0xffu << (8 * bb));
-                        else if (vi < (int)lead + 4) w[k] ^= ((l >> (8 * (vi - (int)lead))) & 0xffu) << (8 * bb);
-                    }
+                    const uint32_t gw = 4u * (uint32_t)v + k;        // word index over blocks 0 and 1
+                    if (gw < k0) w[k] = 0;
+                    else if (gw == k0) w[k] = (w[k] & (0xffffffffu << sh)) ^ x_lo;
+                    else if (gw == k0 + 1) w[k] ^= x_hi;
                 }
                 blk = make_uint4(w[0], w[1], w[2], w[3]);
             }
@@ -1162,7 +1173,20 @@ __device__ __forceinline__ uint32_t warp_crc32c_update(uint32_t l, const uint8_t
         if ((lane & (2 * d - 1)) == 2 * d - 1) R = crc_adv4(ct.tree + t * 1024, left) ^ R;
     }
     R = __shfl_sync(0xffffffffu, R, 31);
-    return crc32c_bytes_serial(R, reinterpret_cast<const uint8_t*>(a0 + W), tailn);
+    if (tailn == 0) return R;
+    // the <= 15 trailing bytes, in parallel: update(R, tail) = update(R, tailn zero bytes) ^ update(0, tail);
+    // a byte followed by k zero bytes is one lookup in T[k] (the slice tables), the register's byte j acts as data byte j
+    const uint8_t* tp = reinterpret_cast<const uint8_t*>(a0 + W);
+    uint32_t c = 0;
+    if (lane < tailn) c = ct.hot[(tailn - 1 - lane) * 256 + tp[lane]];
+    else if (lane >= 16 && lane < 20) {
+        const uint32_t j = lane - 16, rb = (R >> (8 * j)) & 0xffu;
+        if (j < tailn) c = ct.hot[(tailn - 1 - j) * 256 + rb];
+    }
+    if (lane == 20 && tailn < 4) c = R >> (8 * tailn);               // register bytes the short tail did not consume
+    #pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, d);
+    return c;
 }
 // stage the hot tables into shared memory (all threads of the block cooperate)
 __device__ __forceinline__ void crc_tabs_to_smem(uint32_t* s_hot, const uint32_t* g_hot) {
@@ -1597,13 +1621,31 @@ __global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs
     const uint32_t n_msgs = B.totals[0];
     if (B.totals[2] & 3u) return;
     finalize_runs(B);                                  // (was a separate launch)
-    if (B.totals[3] == 0) return;
+    const uint32_t n_verify = B.totals[7];
+    if (B.totals[3] == 0 && n_verify == 0) return;
     __shared__ uint32_t s_hot[kCrcHotWords];
     extern __shared__ __align__(16) uint8_t s_rings[];           // kSnapRing bytes per warp
     crc_tabs_to_smem(s_hot, B.crc_adv);
     CrcTabs ct; ct.hot = s_hot; ct.tree = B.crc_adv + kCrcHotWords; ct.ring = s_rings + (threadIdx.x >> 5) * kSnapRing;
     // the slow messages were listed by k_decode; warps pull them one at a time (sizes vary from an error
     // text to a 256 KiB snappy stream, so the queue is dynamic: totals[6] is the ticket)
+    // verify pass: Crc32cVerify (policy/crc32c_checksum.cpp:44-61) of the plain echoes whose reply k_pack_tma moves;
+    // a request that fails is answered here (EREQUEST) and taken off the bandwidth path
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(B.totals + 8, 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_verify) break;
+        const uint32_t i = B.slow_idx[B.max_msgs - 1 - k];
+        const uint32_t fo = B.msgs[i].frame_off, meta_size = B.msgs[i].meta_size;
+        const uint32_t req_size = B.msgs[i].body_size - meta_size;
+        int64_t bwo = (int64_t)req_size - (int64_t)B.msgs[i].attachment_size; if (bwo > (int64_t)req_size) bwo = req_size;
+        const uint8_t* frame = B.bytes + fo;
+        const uint32_t crc = warp_crc32c_update(0xffffffffu, frame + 12 + meta_size, (uint32_t)bwo, lane, ct) ^ 0xffffffffu;
+        const bool good = crc == crc32c_unmask(load_be32(frame + B.aux[i].cks_off));
+        if (good) { if (lane == 0) B.jobs[i].fast = 1; }
+        else { if (lane == 0) B.jobs[i].fast = 0; __syncwarp(); pack_one(B, C, i, lane, ct); }
+    }
     const uint32_t n_slow = B.totals[3];
     for (;;) {
         uint32_t k = 0;
@@ -1700,7 +1742,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(BatchPtrs B, DevConf
     // ---- pack: warp per message
     for (uint32_t i = wid; i < total; i += kSmallWarps) {
         const PackJob job = B.jobs[i];
-        if (!job.fast) { pack_one(B, C, i, lane, ct); continue; }
+        if (job.fast != 1) { pack_one(B, C, i, lane, ct); continue; }   // (2 = CRC to verify: pack_one does it)
         const uint32_t so = B.slot[i];
         // slot image = head record + 16-byte aligned rest of the payload (see k_pack_tma); plain 16 B copies here
         const uint4* hs = reinterpret_cast<const uint4*>(B.heads + (size_t)i * kHeadBytes);
