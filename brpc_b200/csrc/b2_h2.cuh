@@ -108,6 +108,54 @@ __device__ __forceinline__ bool hp_copy_indexed(const HpackState& h, uint32_t in
     }
     return false;
 }
+// HPacker::Decode (hpack.cpp:765-843): ONE field at p[0..left).  The record bytes (name then value) land in rec.
+// rc > 0: a field was produced, `adv` bytes consumed; rc == 0: ran out of bytes inside an indexed field / size update
+// (the iterator is then at the end: the bytes are swallowed, as in the reference); -1 malformed; -2 rec too small.
+__device__ __forceinline__ int hpack_decode_field(HpackState& h, const uint8_t* p, uint32_t left, uint8_t* rec, uint32_t cap,
+                                                  uint32_t& nl, uint32_t& vl, uint32_t& adv) {
+    const uint8_t* p0 = p;
+    nl = vl = 0; adv = 0;
+    // (001x) dynamic table size updates precede the field they travel with
+    while (left && (p[0] >> 5) == 1) {
+        uint32_t max_size = 0;
+        const int ib = hp_int(p, left, 5, max_size);
+        if (ib <= 0) return ib;
+        if (max_size > 4096) return -1;
+        if (max_size > h.max_size) h.max_size = max_size;
+        else if (max_size < h.max_size) { h.max_size = max_size; while (h.size > h.max_size) hp_pop(h); }
+        p += ib; left -= (uint32_t)ib;
+    }
+    if (!left) return 0;
+    const uint8_t fb = p[0];
+    uint32_t index = 0;
+    bool ovf = false;
+    if (fb & 0x80) {                                     // indexed field
+        const int ib = hp_int(p, left, 7, index);
+        if (ib <= 0) return ib;
+        if (!hp_copy_indexed(h, index, true, rec, cap, nl, vl, ovf)) return ovf ? -2 : -1;
+        p += ib;
+    } else {
+        const bool incremental = (fb >> 6) == 1;
+        const int ib = hp_int(p, left, incremental ? 6 : 4, index);
+        if (ib <= 0) return -1;
+        uint32_t used = (uint32_t)ib;
+        if (index != 0) {
+            if (!hp_copy_indexed(h, index, false, rec, cap, nl, vl, ovf)) return ovf ? -2 : -1;
+        } else {
+            const int nb = hp_str(p + used, left - used, rec, cap, nl);
+            if (nb <= 0) return nb == -2 ? -2 : -1;
+            used += (uint32_t)nb;
+            for (uint32_t i = 0; i < nl; i++) if (rec[i] >= 'A' && rec[i] <= 'Z') rec[i] = (uint8_t)(rec[i] + 32);
+        }
+        const int vb = hp_str(p + used, left - used, rec + nl, cap - nl, vl);
+        if (vb <= 0) return vb == -2 ? -2 : -1;
+        used += (uint32_t)vb;
+        if (incremental && hp_add(h, rec, nl, vl) != 0) return -1;
+        p += used;
+    }
+    adv = (uint32_t)(p - p0);
+    return 1;
+}
 // One header block, the way ConsumeHeaders loops HPacker::Decode.  Records: u16 name_len, u16 value_len, name, value.
 // status: 0 consumed, 1 ran out of bytes inside a field, -1 malformed, -2 output capacity exceeded
 __device__ __noinline__ int hpack_decode_block(HpackState& h, const uint8_t* in, uint32_t n, uint8_t* out, uint32_t out_cap,
@@ -116,52 +164,12 @@ __device__ __noinline__ int hpack_decode_block(HpackState& h, const uint8_t* in,
     int status = 0;
     while (pos < n) {
         if (o + 4 > out_cap) { status = -2; break; }
-        uint8_t* rec = out + o + 4; const uint32_t cap = out_cap - o - 4;
-        uint32_t nl = 0, vl = 0, index = 0;
-        const uint8_t* p = in + pos; uint32_t left = n - pos;
-        // (001x) dynamic table size updates precede the field they travel with
-        int rc = 1; bool size_update_only = false;
-        while (left && (p[0] >> 5) == 1) {
-            uint32_t max_size = 0;
-            const int ib = hp_int(p, left, 5, max_size);
-            if (ib <= 0) { rc = ib; break; }
-            if (max_size > 4096) { rc = -1; break; }
-            if (max_size > h.max_size) h.max_size = max_size;
-            else if (max_size < h.max_size) { h.max_size = max_size; while (h.size > h.max_size) hp_pop(h); }
-            p += ib; left -= (uint32_t)ib;
-            if (!left) { rc = 0; size_update_only = true; }
-        }
-        (void)size_update_only;
-        if (rc <= 0) { status = rc < 0 ? -1 : 1; break; }
-        const uint8_t fb = p[0];
-        bool ovf = false;
-        if (fb & 0x80) {                                     // indexed field
-            const int ib = hp_int(p, left, 7, index);
-            if (ib <= 0) { status = ib < 0 ? -1 : 1; break; }
-            if (!hp_copy_indexed(h, index, true, rec, cap, nl, vl, ovf)) { status = ovf ? -2 : -1; break; }
-            p += ib;
-        } else {
-            const bool incremental = (fb >> 6) == 1;
-            const int ib = hp_int(p, left, incremental ? 6 : 4, index);
-            if (ib <= 0) { status = -1; break; }
-            uint32_t used = (uint32_t)ib;
-            if (index != 0) {
-                if (!hp_copy_indexed(h, index, false, rec, cap, nl, vl, ovf)) { status = ovf ? -2 : -1; break; }
-            } else {
-                const int nb = hp_str(p + used, left - used, rec, cap, nl);
-                if (nb <= 0) { status = nb == -2 ? -2 : -1; break; }
-                used += (uint32_t)nb;
-                for (uint32_t i = 0; i < nl; i++) if (rec[i] >= 'A' && rec[i] <= 'Z') rec[i] = (uint8_t)(rec[i] + 32);
-            }
-            const int vb = hp_str(p + used, left - used, rec + nl, cap - nl, vl);
-            if (vb <= 0) { status = vb == -2 ? -2 : -1; break; }
-            used += (uint32_t)vb;
-            if (incremental && hp_add(h, rec, nl, vl) != 0) { status = -1; break; }
-            p += used;
-        }
+        uint32_t nl = 0, vl = 0, adv = 0;
+        const int rc = hpack_decode_field(h, in + pos, n - pos, out + o + 4, out_cap - o - 4, nl, vl, adv);
+        if (rc <= 0) { status = rc == 0 ? 1 : rc; break; }
         out[o] = (uint8_t)nl; out[o + 1] = (uint8_t)(nl >> 8); out[o + 2] = (uint8_t)vl; out[o + 3] = (uint8_t)(vl >> 8);
         o += 4 + nl + vl; cnt++;
-        pos = (uint32_t)(p - in);
+        pos += adv;
     }
     out_len = o; n_headers = cnt;
     return status;
@@ -218,6 +226,445 @@ __global__ void k_h2_scan(const uint8_t* bytes, const b2_run* runs, uint32_t n_r
         cnt++; pos += 9 + length;
     }
     n_frames[r] = cnt; consumed[r] = pos; err[r] = e;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The server side of ParseH2Message: one thread per connection run walks H2Context::Consume
+// (policy/http2_rpc_protocol.cpp:467-543) frame by frame.  A connection is a serial state machine (HPACK table,
+// settings, windows, pending streams), so connections are the unit of parallelism, exactly like the reference
+// runs one input bthread per socket.  Every quirk of the reference that shapes the byte stream is kept: handlers
+// that fail (or PING acks) leave the rest of their payload unread and the next "frame head" is parsed from there.
+constexpr uint32_t kH2Pending = B2_H2_MAX_PENDING, kH2StreamBytes = B2_H2_STREAM_BYTES, kH2HdrBytes = B2_H2_HEADER_BYTES;
+constexpr long long kH2MaxWindow = 2147483647ll;                 // H2Settings::MAX_WINDOW_SIZE
+struct H2Stream {
+    int32_t id; uint32_t hdr_len, n_headers, body_len;
+    uint32_t stream_ended, pad;
+    long long remote_window_left, deferred_wu;
+};
+struct H2Conn {
+    uint32_t conn_state; int32_t last_received_stream_id; uint32_t remote_settings_received, n_pending;
+    uint32_t r_header_table_size, r_enable_push, r_max_concurrent_streams, r_stream_window_size, r_max_frame_size, r_max_header_list_size;
+    uint32_t l_stream_window_size, l_max_frame_size;
+    long long remote_window_left, deferred_window_update;
+    H2Stream streams[kH2Pending];
+    uint8_t slots[kH2Pending][kH2StreamBytes];                   // [0, kH2HdrBytes) header records, then the body
+};
+struct H2Out {                      // this run's slice of the output buffer
+    uint8_t* base; uint32_t ctrl_cap, ctrl_len, blob_off, blob_end; bool overflow;
+};
+__device__ __forceinline__ void h2_conn_init(H2Conn& c) {
+    c.conn_state = 0; c.last_received_stream_id = -1; c.remote_settings_received = 0; c.n_pending = 0;
+    // _remote_settings: H2Settings() with the windows maximised (H2Context ctor, :323-345)
+    c.r_header_table_size = 4096; c.r_enable_push = 0; c.r_max_concurrent_streams = 0xffffffffu;
+    c.r_stream_window_size = (uint32_t)kH2MaxWindow; c.r_max_frame_size = 16384; c.r_max_header_list_size = 0xffffffffu;
+    c.l_stream_window_size = 256 * 1024; c.l_max_frame_size = 16384;     // H2Settings() defaults, http2.cpp:26-34
+    c.remote_window_left = kH2MaxWindow; c.deferred_window_update = 0;
+    for (uint32_t i = 0; i < kH2Pending; i++) c.streams[i].id = -1;
+}
+__device__ __forceinline__ void h2_put_head(uint8_t* p, uint32_t payload, uint8_t type, uint8_t flags, uint32_t sid) {   // SerializeFrameHead :123-136
+    p[0] = (uint8_t)(payload >> 16); p[1] = (uint8_t)(payload >> 8); p[2] = (uint8_t)payload; p[3] = type; p[4] = flags;
+    p[5] = (uint8_t)(sid >> 24); p[6] = (uint8_t)(sid >> 16); p[7] = (uint8_t)(sid >> 8); p[8] = (uint8_t)sid;
+}
+__device__ __forceinline__ uint8_t* h2_ack_room(H2Out& o, uint32_t n) {                  // WriteAck :144-150
+    if (o.ctrl_len + n > o.ctrl_cap) { o.overflow = true; return nullptr; }
+    uint8_t* p = o.base + o.ctrl_len; o.ctrl_len += n; return p;
+}
+__device__ __forceinline__ void h2_write_wu(H2Out& o, uint32_t sid, long long inc) {
+    uint8_t* p = h2_ack_room(o, 13); if (!p) return;
+    h2_put_head(p, 4, 8, 0, sid); put_be32(p + 9, (uint32_t)inc);
+}
+// AddWindowSize (:261-281), literally: the sum is stored even when the check fails
+__device__ __forceinline__ bool h2_add_window(long long& w, long long diff) {
+    const long long before = w; w = before + diff;
+    const long long mask = (long long)(int)0x80000000;            // `(1 << 31)` promoted to int64
+    if ((((before | diff) >> 31) & 1) == 0) { if ((before + diff) & mask) return false; }
+    if ((((before & diff) >> 31) & 1) == 1) { if (((before + diff) & mask) == 0) return false; }
+    return true;
+}
+__device__ __forceinline__ void h2_defer_wu(H2Conn& c, H2Out& o, long long size) {         // H2Context::DeferWindowUpdate :1078-1094
+    if (size <= 0) return;
+    c.deferred_window_update += size;
+    if (c.deferred_window_update >= (long long)(c.l_stream_window_size / 2)) {
+        const long long conn_wu = c.deferred_window_update; c.deferred_window_update = 0;
+        if (conn_wu > 0) h2_write_wu(o, 0, conn_wu);
+    }
+}
+__device__ __forceinline__ int h2_find(const H2Conn& c, int32_t id) {
+    for (uint32_t i = 0; i < kH2Pending; i++) if (c.streams[i].id == id) return (int)i;
+    return -1;
+}
+// RemoveStreamAndDeferWU (:378-392); returns the slot (the caller still reads the stream's data) or -1
+__device__ __forceinline__ int h2_remove_stream(H2Conn& c, H2Out& o, int32_t id) {
+    const int k = h2_find(c, id);
+    if (k < 0) return -1;
+    c.streams[k].id = -1; c.n_pending--;
+    const long long d = c.streams[k].deferred_wu; c.streams[k].deferred_wu = 0;
+    h2_defer_wu(c, o, d);
+    return k;
+}
+__device__ __forceinline__ bool ci_eq(const uint8_t* a, uint32_t n, const char* lit) {    // strcasecmp(a (c_str of n bytes), lit) == 0
+    uint32_t i = 0;
+    for (; lit[i]; i++) {
+        if (i >= n) return false;
+        uint8_t x = a[i]; if (x >= 'a' && x <= 'z') x = (uint8_t)(x - 32);
+        if (x != (uint8_t)lit[i]) return false;
+    }
+    return i == n;
+}
+__device__ __forceinline__ uint32_t cstr_len(const uint8_t* p, uint32_t n) { uint32_t i = 0; while (i < n && p[i]) i++; return i; }
+__device__ __forceinline__ bool lit_eq(const uint8_t* a, uint32_t n, const char* lit) {   // strcmp(c_str, lit) == 0
+    uint32_t i = 0;
+    for (; lit[i]; i++) if (i >= n || a[i] != (uint8_t)lit[i]) return false;
+    return i == n;
+}
+__device__ __forceinline__ bool has_prefix(const uint8_t* a, uint32_t n, const char* lit, uint32_t& l) {
+    l = 0; while (lit[l]) { if (l >= n || a[l] != (uint8_t)lit[l]) return false; l++; }
+    return true;
+}
+// Str2HttpMethod (http_method.cpp:104-140): case-insensitive exact match of the c_str against the 27 names
+__device__ __forceinline__ int h2_http_method(const uint8_t* v, uint32_t vl) {
+    const uint32_t n = cstr_len(v, vl);
+    const char* const names[27] = { "DELETE", "GET", "HEAD", "POST", "PUT", "CONNECT", "OPTIONS", "TRACE", "COPY", "LOCK", "MKCOL", "MOVE",
+        "PROPFIND", "PROPPATCH", "SEARCH", "UNLOCK", "REPORT", "MKACTIVITY", "CHECKOUT", "MERGE", "M-SEARCH", "NOTIFY", "SUBSCRIBE",
+        "UNSUBSCRIBE", "PATCH", "PURGE", "MKCALENDAR" };
+    for (int m = 0; m < 27; m++) if (ci_eq(v, n, names[m])) return m;
+    return -1;
+}
+// ParseContentType (policy/http_rpc_protocol.cpp:176-230)
+__device__ __forceinline__ uint32_t h2_content_type(const uint8_t* ct, uint32_t n, bool& is_grpc) {
+    is_grpc = false;
+    uint32_t l;
+    if (!has_prefix(ct, n, "application/", l)) return 0;
+    ct += l; n -= l;
+    if (has_prefix(ct, n, "grpc", l)) {
+        if (n == 4 || ct[4] == ';') { is_grpc = true; return 2; }
+        else if (ct[4] == '+') { ct += 5; n -= 5; is_grpc = true; }
+    }
+    uint32_t type;
+    if (has_prefix(ct, n, "json", l)) type = 1;
+    else if (has_prefix(ct, n, "proto-json", l)) type = 4;
+    else if (has_prefix(ct, n, "proto-text", l)) type = 3;
+    else if (has_prefix(ct, n, "proto", l)) type = 2;
+    else if (has_prefix(ct, n, "x-protobuf", l)) type = 2;
+    else return 0;
+    ct += l; n -= l;
+    return (n == 0 || ct[0] == ';') ? type : 0;
+}
+// one header of ConsumeHeaders (:1232-1287): false = the reference returns -1
+__device__ __forceinline__ bool h2_check_header(const uint8_t* name, uint32_t nl, const uint8_t* value, uint32_t vl) {
+    const uint32_t n = cstr_len(name, nl);
+    if (n == 0 || name[0] != ':') return true;
+    const uint8_t c1 = n > 1 ? name[1] : 0;
+    const uint8_t* rest = name + 2; const uint32_t rn = n > 2 ? n - 2 : 0;
+    switch (c1) {
+    case 'a': return lit_eq(rest, rn, "uthority");
+    case 'm': return lit_eq(rest, rn, "ethod") && h2_http_method(value, vl) >= 0;
+    case 'p': return lit_eq(rest, rn, "ath");
+    case 's':
+        if (lit_eq(rest, rn, "cheme")) return true;
+        if (lit_eq(rest, rn, "tatus")) {                 // strtol(value, &end, 10) must stop at the terminating NUL
+            const uint32_t m = cstr_len(value, vl);
+            uint32_t i = 0;
+            while (i < m && (value[i] == ' ' || (value[i] >= 9 && value[i] <= 13))) i++;
+            uint32_t j = i;
+            if (j < m && (value[j] == '+' || value[j] == '-')) j++;
+            uint32_t d = j; while (d < m && value[d] >= '0' && value[d] <= '9') d++;
+            const uint32_t end = d > j ? d : 0;          // no digits: endptr = nptr
+            return end == m;
+        }
+        return false;
+    default: return false;
+    }
+}
+struct H2Res { int kind; uint32_t err; int32_t err_stream; int slot; };   // kind 0 ok, 1 ok + message in `slot`, 2 error
+__device__ __forceinline__ H2Res h2_ok() { H2Res r; r.kind = 0; r.err = 0; r.err_stream = 0; r.slot = -1; return r; }
+__device__ __forceinline__ H2Res h2_err(uint32_t e, int32_t sid = 0) { H2Res r; r.kind = 2; r.err = e; r.err_stream = sid; r.slot = -1; return r; }
+
+// H2StreamContext::ConsumeHeaders over one fragment, records appended to the stream's slot
+__device__ __forceinline__ int h2_consume_headers(H2Conn& c, HpackState& hp, H2Stream& st, uint8_t* slot, const uint8_t* frag, uint32_t n, bool& no_room) {
+    uint32_t pos = 0;
+    while (pos < n) {
+        if (st.hdr_len + 4 > kH2HdrBytes) { no_room = true; return -1; }
+        uint8_t* rec = slot + st.hdr_len;
+        uint32_t nl = 0, vl = 0, adv = 0;
+        const int rc = hpack_decode_field(hp, frag + pos, n - pos, rec + 4, kH2HdrBytes - st.hdr_len - 4, nl, vl, adv);
+        if (rc == -2) { no_room = true; return -1; }
+        if (rc < 0) return -1;
+        if (rc == 0) break;
+        if (!h2_check_header(rec + 4, nl, rec + 4 + nl, vl)) return -1;
+        rec[0] = (uint8_t)nl; rec[1] = (uint8_t)(nl >> 8); rec[2] = (uint8_t)vl; rec[3] = (uint8_t)(vl >> 8);
+        st.hdr_len += 4 + nl + vl; st.n_headers++;
+        pos += adv;
+    }
+    return 0;
+}
+// OnEndStream (:823-846): the stream leaves the pending map; the caller emits the message from its slot
+__device__ __forceinline__ H2Res h2_end_stream(H2Conn& c, H2Out& o, int32_t id) {
+    const int k = h2_remove_stream(c, o, id);
+    if (k < 0) return h2_ok();
+    H2Res r = h2_ok(); r.kind = 1; r.slot = k; r.err_stream = id; return r;
+}
+
+__global__ void k_h2_conn_reset(H2Conn* conns, HpackState* hps, uint32_t conn) {
+    h2_conn_init(conns[conn]);
+    HpackState& h = hps[conn]; h.max_size = 4096; h.size = 0; h.count = 0; h.head = 0; h.byte_head = 0;
+}
+
+__global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t n_runs, H2Conn* conns, HpackState* hps,
+                             const DevMethod* methods, uint32_t n_methods, b2_h2_run_status* rs, b2_h2_msg* msgs, uint32_t msg_cap_per_run,
+                             uint8_t* out, uint32_t region) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    const uint8_t* in = bytes + runs[r].offset; const uint32_t n = runs[r].length;
+    H2Conn& c = conns[(uint32_t)runs[r].socket_id];
+    HpackState& hp = hps[(uint32_t)runs[r].socket_id];
+    H2Out o; o.base = out + (size_t)r * region; o.ctrl_cap = region / 4; o.ctrl_len = 0; o.blob_off = region / 4; o.blob_end = region; o.overflow = false;
+    b2_h2_msg* mout = msgs + (size_t)r * msg_cap_per_run;
+    uint32_t n_msgs = 0, pos = 0, last_ok = 0, perr = B2_PARSE_ERROR_NOT_ENOUGH_DATA;
+    bool no_room = false;
+    for (;;) {
+        if (o.overflow || no_room) { perr = B2_PARSE_ERROR_NO_RESOURCE; break; }
+        if (c.conn_state == 0) {                                     // H2_CONNECTION_UNINITIALIZED, server side (:469-489)
+            const char* pre = "PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n";
+            const uint32_t k = (n - pos) < 24 ? (n - pos) : 24;
+            bool match = true;
+            for (uint32_t i = 0; i < k; i++) if (in[pos + i] != (uint8_t)pre[i]) { match = false; break; }
+            if (!match) { perr = B2_PARSE_ERROR_TRY_OTHERS; break; }
+            if (k < 24) break;
+            c.conn_state = 1; pos += 24;
+            // SerializeH2SettingsFrameAndWU of the default server settings (:230-259): ENABLE_PUSH=0, INITIAL_WINDOW_SIZE=256K, WU 1M-65535
+            uint8_t* p = h2_ack_room(o, 9 + 12 + 13);
+            if (p) {
+                h2_put_head(p, 12, 4, 0, 0);
+                p[9] = 0; p[10] = 2; put_be32(p + 11, 0);
+                p[15] = 0; p[16] = 4; put_be32(p + 17, c.l_stream_window_size);
+                h2_put_head(p + 21, 4, 8, 0, 0); put_be32(p + 30, 1024 * 1024 - 65535);
+            }
+            last_ok = pos;
+            continue;
+        }
+        // ---- ConsumeFrameHead (:438-465)
+        const uint32_t left = n - pos;
+        if (left < 3) break;
+        const uint32_t length = ((uint32_t)in[pos] << 16) | ((uint32_t)in[pos + 1] << 8) | in[pos + 2];
+        if (length > c.l_max_frame_size) { perr = B2_PARSE_ERROR_ABSOLUTELY_WRONG; break; }
+        if ((unsigned long long)(left - 3) < 6ull + length) break;
+        const uint32_t type = in[pos + 3], flags = in[pos + 4], sid_raw = load_be32(in + pos + 5);
+        if (sid_raw & 0x80000000u) { perr = B2_PARSE_ERROR_ABSOLUTELY_WRONG; break; }
+        const int32_t sid = (int32_t)sid_raw;
+        pos += 9;
+        if (type > 9) { perr = B2_PARSE_ERROR_ABSOLUTELY_WRONG; break; }          // FindFrameHandler == NULL (:498-502)
+        const uint8_t* pl = in + pos;                                // payload; handlers advance `used`
+        uint32_t used = 0;
+        H2Res res = h2_ok();
+        switch (type) {
+        case 0: {                                                    // ---- OnData (:700-723) + H2StreamContext::OnData (:725-779)
+            uint32_t frag = length, padl = 0;
+            if (flags & 0x8) { frag--; padl = pl[used++]; }          // (a zero-length padded frame underflows like the reference's uint32)
+            if (frag < padl) { res = h2_err(6); break; }
+            frag -= padl;
+            const int k = h2_find(c, sid);
+            if (k < 0) {
+                // stream unknown: the bytes are still counted against the connection window, then STREAM_CLOSED
+                used += frag + padl;
+                const long long acc = (long long)frag;
+                const long long quota = (long long)(c.l_stream_window_size / (c.n_pending + 1));
+                long long tmp_deferred = (long long)frag;
+                if (acc >= quota) {
+                    if (acc > (long long)c.l_stream_window_size) { h2_defer_wu(c, o, tmp_deferred); res = h2_err(5, sid); break; }   // (inner FLOW_CONTROL result is discarded)
+                    const long long swu = tmp_deferred; tmp_deferred = 0;
+                    if (swu > 0) { h2_write_wu(o, (uint32_t)sid, swu); const long long cw = swu + c.deferred_window_update; c.deferred_window_update = 0; h2_write_wu(o, 0, cw); }
+                }
+                h2_defer_wu(c, o, tmp_deferred);
+                res = h2_err(5, sid);
+                break;
+            }
+            H2Stream& st = c.streams[k];
+            if (kH2HdrBytes + st.body_len + frag > kH2StreamBytes) { no_room = true; break; }
+            for (uint32_t i = 0; i < frag; i++) c.slots[k][kH2HdrBytes + st.body_len + i] = pl[used + i];
+            st.body_len += frag; used += frag + padl;
+            const long long acc = (long long)frag + st.deferred_wu; st.deferred_wu += frag;
+            const long long quota = (long long)(c.l_stream_window_size / (c.n_pending + 1));
+            if (acc >= quota) {
+                if (acc > (long long)c.l_stream_window_size) { res = h2_err(3, sid); break; }
+                const long long swu = st.deferred_wu; st.deferred_wu = 0;
+                if (swu > 0) { h2_write_wu(o, (uint32_t)sid, swu); const long long cw = swu + c.deferred_window_update; c.deferred_window_update = 0; h2_write_wu(o, 0, cw); }
+            }
+            if (flags & 0x1) res = h2_end_stream(c, o, sid);
+            break; }
+        case 1: {                                                    // ---- OnHeaders (:545-613) + H2StreamContext::OnHeaders (:615-655)
+            if (sid == 0) { res = h2_err(1); break; }
+            const bool has_padding = flags & 0x8, has_priority = flags & 0x20;
+            if (length < (has_priority ? 5u : 0u) + (has_padding ? 1u : 0u)) { res = h2_err(6); break; }
+            uint32_t frag = length, padl = 0;
+            if (has_padding) { padl = pl[used++]; frag--; }
+            if (has_priority) { used += 5; frag -= 5; }
+            if (frag < padl) { res = h2_err(6); break; }
+            frag -= padl;
+            int k;
+            if (sid > c.last_received_stream_id) {                   // new stream
+                if ((sid & 1) == 0) { res = h2_err(1); break; }
+                c.last_received_stream_id = sid;
+                k = h2_find(c, -1);
+                if (k < 0) { no_room = true; break; }                // (device limit: B2_H2_MAX_PENDING)
+                H2Stream& st = c.streams[k];
+                st.id = sid; st.hdr_len = 0; st.n_headers = 0; st.body_len = 0; st.stream_ended = 0; st.deferred_wu = 0;
+                st.remote_window_left = (long long)c.r_stream_window_size;
+                c.n_pending++;
+            } else {
+                k = h2_find(c, sid);
+                if (k < 0) { res = h2_err(1); break; }
+            }
+            H2Stream& st = c.streams[k];
+            if (h2_consume_headers(c, hp, st, c.slots[k], pl + used, frag, no_room) < 0) { if (!no_room) res = h2_err(1); break; }
+            used += frag + padl;
+            if (flags & 0x4) { if (flags & 0x1) res = h2_end_stream(c, o, sid); }
+            else if (flags & 0x1) st.stream_ended = 1;
+            break; }
+        case 2: res = h2_err(1); break;                              // OnPriority (:917-921)
+        case 3: {                                                    // ---- OnResetStream (:781-821)
+            if (length != 4) { res = h2_err(6); break; }
+            used += 4;
+            (void)h2_remove_stream(c, o, sid);                       // server side: the stream is dropped, no message
+            break; }
+        case 4: {                                                    // ---- OnSettings (:848-915)
+            if (sid != 0) { res = h2_err(1); break; }
+            if (flags & 0x1) { if (length != 0) res = h2_err(1); break; }
+            const long long old_sw = (long long)c.r_stream_window_size;
+            uint32_t t_hts, t_push, t_mcs, t_sws, t_mfs, t_mhl;
+            if (!c.remote_settings_received) { t_hts = 4096; t_push = 0; t_mcs = 0xffffffffu; t_sws = 256 * 1024; t_mfs = 16384; t_mhl = 0xffffffffu; }
+            else { t_hts = c.r_header_table_size; t_push = c.r_enable_push; t_mcs = c.r_max_concurrent_streams; t_sws = c.r_stream_window_size; t_mfs = c.r_max_frame_size; t_mhl = c.r_max_header_list_size; }
+            bool okp = (length / 6) * 6 == length;                   // ParseH2Settings (:166-211)
+            if (okp) for (uint32_t i = 0; i < length / 6; i++) {
+                const uint32_t id = ((uint32_t)pl[used] << 8) | pl[used + 1], value = load_be32(pl + used + 2);
+                used += 6;
+                if (id == 1) t_hts = value;
+                else if (id == 2) { if (value > 1) { okp = false; break; } t_push = value; }
+                else if (id == 3) t_mcs = value;
+                else if (id == 4) { if (value > (uint32_t)kH2MaxWindow) { okp = false; break; } t_sws = value; }
+                else if (id == 5) { if (value > 16777215u || value < 16384u) { okp = false; break; } t_mfs = value; }
+                else if (id == 6) t_mhl = value;
+            }
+            if (!c.remote_settings_received) {
+                if (!okp) { res = h2_err(1); break; }                // parsed into a temporary: nothing is kept
+                c.remote_window_left -= (kH2MaxWindow - 65535);
+                c.remote_settings_received = 1;
+            }
+            // (after the first frame the reference parses in place: fields set before a bad pair stay)
+            c.r_header_table_size = t_hts; c.r_enable_push = t_push; c.r_max_concurrent_streams = t_mcs;
+            c.r_stream_window_size = t_sws; c.r_max_frame_size = t_mfs; c.r_max_header_list_size = t_mhl;
+            if (!okp) { res = h2_err(1); break; }
+            const long long diff = (long long)c.r_stream_window_size - old_sw;
+            bool flow_ok = true;
+            if (diff) for (uint32_t i = 0; i < kH2Pending; i++) if (c.streams[i].id >= 0) { if (!h2_add_window(c.streams[i].remote_window_left, diff)) { flow_ok = false; break; } }
+            if (!flow_ok) { res = h2_err(3); break; }
+            uint8_t* p = h2_ack_room(o, 9); if (p) h2_put_head(p, 0, 4, 1, 0);
+            break; }
+        case 5: res = h2_err(1); break;                              // OnPushPromise (:923-927)
+        case 6: {                                                    // ---- OnPing (:929-951)
+            if (length != 8) { res = h2_err(6); break; }
+            if (sid != 0) { res = h2_err(1); break; }
+            if (flags & 0x1) break;                                  // (an ack's payload is left unread, as in the reference)
+            uint8_t* p = h2_ack_room(o, 17);
+            if (p) { h2_put_head(p, 8, 6, 1, 0); for (uint32_t i = 0; i < 8; i++) p[9 + i] = pl[i]; }
+            used += 8;
+            break; }
+        case 7: {                                                    // ---- OnGoAway (:958-1004), server side: ignored
+            if (length < 8) { res = h2_err(6); break; }
+            if (sid != 0) { res = h2_err(1); break; }
+            if (flags) { res = h2_err(1); break; }
+            used += length;
+            break; }
+        case 8: {                                                    // ---- OnWindowUpdate (:1006-1041)
+            if (length != 4) { res = h2_err(6); break; }
+            const uint32_t inc = load_be32(pl); used += 4;
+            if ((inc & 0x80000000u) || inc == 0) { res = h2_err(1); break; }
+            if (sid == 0) { if (!h2_add_window(c.remote_window_left, (long long)inc)) res = h2_err(3); break; }
+            const int k = h2_find(c, sid);
+            if (k < 0) break;
+            if (!h2_add_window(c.streams[k].remote_window_left, (long long)inc)) res = h2_err(3);
+            break; }
+        case 9: {                                                    // ---- OnContinuation (:657-698)
+            const int k = h2_find(c, sid);
+            if (k < 0) { res = h2_err(1); break; }
+            H2Stream& st = c.streams[k];
+            used += length;                                          // the payload moves into _remaining_header_fragment first
+            if (h2_consume_headers(c, hp, st, c.slots[k], pl, length, no_room) < 0) { if (!no_room) res = h2_err(1); break; }
+            if ((flags & 0x4) && st.stream_ended) res = h2_end_stream(c, o, sid);
+            break; }
+        }
+        if (no_room) continue;
+        pos += used;
+        if (res.kind == 2) {
+            if (res.err_stream) {                                    // RST_STREAM, then the stream is forgotten (:507-527)
+                uint8_t* p = h2_ack_room(o, 13);
+                if (p) { h2_put_head(p, 4, 3, 0, (uint32_t)res.err_stream); put_be32(p + 9, res.err); }
+                (void)h2_remove_stream(c, o, res.err_stream);
+            } else {                                                 // GOAWAY (:528-538); parsing goes on
+                uint8_t* p = h2_ack_room(o, 17);
+                if (p) { h2_put_head(p, 8, 7, 0, 0); put_be32(p + 9, (uint32_t)c.last_received_stream_id); put_be32(p + 13, res.err); }
+            }
+            last_ok = pos;
+            continue;
+        }
+        last_ok = pos;
+        if (res.kind == 1) {
+            // ---- the completed request, as ProcessHttpRequest first sees it
+            const H2Stream& st = c.streams[res.slot];
+            const uint8_t* slot = c.slots[res.slot];
+            const uint32_t need = ((st.hdr_len + 15u) & ~15u) + ((st.body_len + 15u) & ~15u);
+            if (n_msgs >= msg_cap_per_run || o.blob_off + need > o.blob_end) { no_room = true; continue; }
+            b2_h2_msg m;
+            m.run_idx = r; m.stream_id = (uint32_t)res.err_stream; m.reserved = 0;
+            const uint32_t ho = o.blob_off, bo = ho + ((st.hdr_len + 15u) & ~15u);
+            for (uint32_t i = 0; i < st.hdr_len; i++) o.base[ho + i] = slot[i];
+            for (uint32_t i = 0; i < st.body_len; i++) o.base[bo + i] = slot[kH2HdrBytes + i];
+            o.blob_off += need;
+            const uint32_t gbase = r * region;
+            m.headers_off = gbase + ho; m.headers_len = st.hdr_len; m.n_headers = st.n_headers;
+            m.body_off = gbase + bo; m.body_len = st.body_len;
+            m.http_method = B2_H2_NO_METHOD; m.content_type = 0; m.flags = 0; m.method_idx = -1;
+            m.msg_off = 0; m.msg_len = 0; m.path_off = 0; m.path_len = 0;
+            bool is_grpc = false;
+            const uint8_t* path = nullptr; uint32_t path_len = 0;
+            for (uint32_t q = 0; q < st.hdr_len;) {
+                const uint32_t nl = slot[q] | ((uint32_t)slot[q + 1] << 8), vl = slot[q + 2] | ((uint32_t)slot[q + 3] << 8);
+                const uint8_t* nm = slot + q + 4; const uint8_t* v = nm + nl;
+                const uint32_t cn = cstr_len(nm, nl);
+                if (lit_eq(nm, cn, ":method")) m.http_method = (uint32_t)h2_http_method(v, vl);
+                else if (lit_eq(nm, cn, ":path")) {                  // URI::SetH2Path (uri.cpp:403-425): up to '?' / '#'
+                    uint32_t e = 0; while (e < vl && v[e] && v[e] != '?' && v[e] != '#') e++;
+                    path = v; path_len = e; m.path_off = gbase + ho + (uint32_t)(v - slot); m.path_len = e; m.flags |= B2_H2_FLAG_HAS_PATH;
+                } else if (lit_eq(nm, cn, "content-type")) m.content_type = h2_content_type(v, vl, is_grpc);
+                q += 4 + nl + vl;
+            }
+            if (is_grpc) {
+                m.flags |= B2_H2_FLAG_GRPC;
+                // RemoveGrpcPrefix (policy/http_rpc_protocol.cpp:264-277)
+                if (st.body_len == 0) { m.flags |= B2_H2_FLAG_GRPC_PREFIX_OK; m.msg_off = m.body_off; }
+                else if (st.body_len >= 5) {
+                    const uint8_t* b = slot + kH2HdrBytes;
+                    if (b[0]) m.flags |= B2_H2_FLAG_GRPC_COMPRESSED;
+                    if ((unsigned long long)load_be32(b + 1) + 5ull == st.body_len) { m.flags |= B2_H2_FLAG_GRPC_PREFIX_OK; m.msg_off = m.body_off + 5; m.msg_len = st.body_len - 5; }
+                }
+            }
+            if (path) {
+                // FindMethodPropertyByURIImpl (:1088-1138), "[service]/[method]" form: '/'-separated, empty fields skipped
+                uint32_t f0 = 0; while (f0 < path_len && path[f0] == '/') f0++;
+                uint32_t e0 = f0; while (e0 < path_len && path[e0] != '/') e0++;
+                uint32_t f1 = e0; while (f1 < path_len && path[f1] == '/') f1++;
+                uint32_t e1 = f1; while (e1 < path_len && path[e1] != '/') e1++;
+                if (e0 > f0 && e1 > f1) {
+                    bool no_service = false;
+                    m.method_idx = find_method(methods, n_methods, path + f0, e0 - f0, path + f1, e1 - f1, no_service);
+                }
+            }
+            mout[n_msgs++] = m;
+        }
+    }
+    b2_h2_run_status st; st.consumed = last_ok; st.parse_error = perr; st.n_msgs = n_msgs; st.first_msg = r * msg_cap_per_run;
+    st.ctrl_off = r * region; st.ctrl_len = o.ctrl_len; st.remote_max_frame_size = c.r_max_frame_size; st.remote_stream_window_size = c.r_stream_window_size;
+    rs[r] = st;
 }
 #endif
 }  // namespace b2

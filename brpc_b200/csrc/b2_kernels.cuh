@@ -409,9 +409,21 @@ __global__ void __launch_bounds__(128) k_frame_table(BatchPtrs B, DevConfig C) {
 }
 
 // --- k_decode: one thread per message ----------------------------------------
+// four bytes at any alignment from two aligned words (reads up to 3 bytes past p + 3: every buffer compared here
+// has that much slack — staged rows, the padded batch buffer, the char arrays inside DevMethod)
+__device__ __forceinline__ uint32_t ld32_any(const uint8_t* p) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>((uintptr_t)p & ~(uintptr_t)3);
+    const uint32_t sh = 8u * (uint32_t)((uintptr_t)p & 3u);
+    return sh ? __funnelshift_r(q[0], q[1], sh) : q[0];
+}
 __device__ __forceinline__ bool bytes_eq(const uint8_t* a, const char* b, uint32_t n) {
-    for (uint32_t i = 0; i < n; i++) if (a[i] != (uint8_t)b[i]) return false;
-    return true;
+    const uint8_t* bb = reinterpret_cast<const uint8_t*>(b);
+    uint32_t i = 0;
+    for (; i + 4 <= n; i += 4) if (ld32_any(a + i) != ld32_any(bb + i)) return false;
+    const uint32_t rem = n - i;
+    if (rem == 0) return true;
+    const uint32_t mask = (1u << (8 * rem)) - 1u;
+    return ((ld32_any(a + i) ^ ld32_any(bb + i)) & mask) == 0;
 }
 // Server::FindMethodPropertyByFullName(service, method): key = service + '.' + method (server.cpp:1970-1988)
 __device__ __forceinline__ int find_method(const DevMethod* ms, uint32_t n, const uint8_t* svc, uint32_t svc_len,

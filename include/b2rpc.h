@@ -316,6 +316,54 @@ int  b2_hpack_reset(b2_ctx* ctx, uint32_t conn, uint32_t max_table_size);
 int  b2_hpack_decode_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_hpack_block* blocks, uint32_t n_blocks,
                            void* out, uint32_t per_block_cap, uint32_t* out_lens, int32_t* status, uint32_t* n_headers);
 
+/* b2_h2_process_batch: the server side of ParseH2Message (src/brpc/policy/http2_rpc_protocol.cpp:1103-1138) =
+ * H2Context::Consume (:467-543) looped over every connection run: client preface, frame heads, the frame handlers
+ * OnData/OnHeaders/OnContinuation/OnResetStream/OnSettings/OnPing/OnGoAway/OnWindowUpdate (:545-1041) with their
+ * flow-control bookkeeping, H2StreamContext::ConsumeHeaders (:1221-1306) over the connection's HPACK table, and — for
+ * every stream that reaches OnEndStream — what ProcessHttpRequest reads first: ParseContentType and RemoveGrpcPrefix
+ * (policy/http_rpc_protocol.cpp:176-230, :264-277) and the "/service/method" lookup of FindMethodPropertyByURIImpl
+ * (:1088-1138, plain service/method form only).
+ *   runs[i].socket_id = connection index (0 .. B2_H2_MAX_CONNS-1); state (settings, windows, pending streams, HPACK
+ *   table) persists across calls; b2_h2_conn_reset starts a new server-side connection (H2Context ctor + Init).
+ *   rs[i].ctrl_off/len  : the bytes the reference WriteAck()s while parsing (SETTINGS + WINDOW_UPDATE after the
+ *                         preface, SETTINGS acks, PING acks, RST_STREAM, GOAWAY, WINDOW_UPDATEs), in order, inside out.
+ *   msgs                : one per completed request, in parse order per run; header records (u16 name_len,
+ *                         u16 value_len, name, value — every decoded field in order) and the concatenated DATA
+ *                         payloads live in out.
+ * Device limits (the reference has none): B2_H2_MAX_PENDING concurrent streams per connection and
+ * B2_H2_STREAM_BYTES (4 KiB header records + 12 KiB body) per unfinished stream; beyond them the run ends with
+ * B2_PARSE_ERROR_NO_RESOURCE (the host takes the connection over or closes it, input_messenger.cpp:227-239). */
+#define B2_H2_MAX_CONNS 1024
+#define B2_H2_MAX_PENDING 8
+#define B2_H2_STREAM_BYTES 16384
+#define B2_H2_HEADER_BYTES 4096
+#define B2_H2_FLAG_GRPC            1u   /* content-type is application/grpc[+...] (is_grpc_ct) */
+#define B2_H2_FLAG_GRPC_PREFIX_OK  2u   /* RemoveGrpcPrefix succeeded: msg_off/msg_len are valid */
+#define B2_H2_FLAG_GRPC_COMPRESSED 4u   /* compressed flag of the 5-byte prefix */
+#define B2_H2_FLAG_HAS_PATH        8u
+#define B2_H2_NO_METHOD 255u            /* no :method header (HttpHeader defaults to GET) */
+typedef struct b2_h2_run_status {
+    uint32_t consumed, parse_error, n_msgs, first_msg;
+    uint32_t ctrl_off, ctrl_len;
+    uint32_t remote_max_frame_size, remote_stream_window_size;   /* what PackH2Message needs next */
+} b2_h2_run_status;                                              /* 32 bytes */
+typedef struct b2_h2_msg {
+    uint32_t run_idx, stream_id;
+    uint32_t headers_off, headers_len, n_headers;
+    uint32_t body_off, body_len;
+    uint32_t http_method;        /* brpc::HttpMethod of the last :method, B2_H2_NO_METHOD if none */
+    uint32_t content_type;       /* brpc::HttpContentType of the last content-type header (0 = others / none) */
+    uint32_t flags;              /* B2_H2_FLAG_* */
+    int32_t  method_idx;         /* registered method named by :path, -1 if none */
+    uint32_t msg_off, msg_len;   /* gRPC message (body without the 5-byte prefix) */
+    uint32_t path_off, path_len; /* the path part of :path inside out */
+    uint32_t reserved;
+} b2_h2_msg;                     /* 64 bytes */
+int  b2_h2_conn_reset(b2_ctx* ctx, uint32_t conn);
+int  b2_h2_process_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs,
+                         b2_h2_run_status* rs, b2_h2_msg* msgs, uint32_t msg_cap, uint32_t* n_msgs,
+                         void* out, uint32_t out_cap);
+
 /* ---- counters (bvar::Adder-like): per-GPU totals accumulated by
  * the kernels: [0] in_bytes [1] in_msgs [2] out_bytes [3] out_msgs [4] errors
  * [5] batches [6..7] reserved.  The cross-GPU reduce is an NCCL all-reduce on

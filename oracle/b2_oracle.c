@@ -804,3 +804,10 @@ int orc_process_batch(const orc_config* cfg, const uint8_t* bytes, uint32_t nbyt
     *n_msgs = nm; *resp_bytes = (uint32_t)rb;
     return 0;
 }
+
+/* index of the method FindMethodPropertyByFullName(service, method) resolves, -1 if none (used by the h2 oracle) */
+int orc_find_method_idx(const orc_config* cfg, const uint8_t* svc, uint32_t svc_len, const uint8_t* mth, uint32_t mth_len) {
+    int idx = -1, no_service = 0;
+    find_method(cfg, svc, svc_len, mth, mth_len, &idx, &no_service);
+    return idx;
+}

@@ -138,6 +138,20 @@ int orc_hpack_decode_block(orc_hpack* h, const uint8_t* in, uint32_t n, uint8_t*
  * fills frames[i] = {type, flags, stream_id, payload_off, payload_len}; returns the count, sets
  * *consumed and *err (B2_PARSE_ERROR_NOT_ENOUGH_DATA normally, ABSOLUTELY_WRONG on a bad head). */
 typedef struct orc_h2_frame { uint8_t type, flags; uint16_t pad; uint32_t stream_id, payload_off, payload_len; } orc_h2_frame;
+/* HPacker::Decode, one field (name/value buffers of 64 KiB).  >0 field bytes, 0 out of data, -1 error; *adv = iterator advance */
+int orc_hpack_field(orc_hpack* h, const uint8_t* p, uint32_t n, uint8_t* name, uint32_t* nl, uint8_t* value, uint32_t* vl, uint32_t* adv);
+/* The server side of ParseH2Message (policy/http2_rpc_protocol.cpp:1103-1138) over one connection's read buffer:
+ * H2Context::Consume (:467-543) until it stops, with the reference's unbounded stream map.  Completed requests are
+ * appended to msgs (b2_h2_msg, offsets into blob), the WriteAck()ed bytes to ctrl.  Returns the ParseError that ended
+ * the loop (B2_PARSE_ERROR_*), *consumed = bytes popped from the buffer. */
+typedef struct orc_h2_conn orc_h2_conn;
+orc_h2_conn* orc_h2_conn_new(void);
+void orc_h2_conn_free(orc_h2_conn*);
+uint32_t orc_h2_consume(orc_h2_conn* c, const orc_config* cfg, const uint8_t* in, uint32_t n, uint32_t* consumed,
+                        b2_h2_msg* msgs, uint32_t msg_cap, uint32_t* n_msgs,
+                        uint8_t* ctrl, uint32_t ctrl_cap, uint32_t* ctrl_len,
+                        uint8_t* blob, uint32_t blob_cap, uint32_t* blob_len,
+                        uint32_t* remote_max_frame_size, uint32_t* remote_stream_window_size);
 uint32_t orc_h2_scan(const uint8_t* in, uint32_t n, uint32_t max_frame_size, orc_h2_frame* frames, uint32_t cap,
                      uint32_t* consumed, uint32_t* err);
 #ifdef __cplusplus

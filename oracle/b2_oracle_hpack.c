@@ -96,7 +96,7 @@ static int hp_str(const uint8_t* p, uint32_t n, uint8_t* out, uint32_t cap, uint
 #define HP_STR_CAP (1u << 16)
 /* HPacker::Decode :765-843: one field.  Returns bytes consumed by the field (>0), 0, or -1; *adv is how
  * far the iterator moved (a table size update moves it without producing a field). */
-static int hp_field(orc_hpack* h, const uint8_t* p, uint32_t n, uint8_t* name, uint32_t* nl, uint8_t* value, uint32_t* vl, uint32_t* adv) {
+int orc_hpack_field(orc_hpack* h, const uint8_t* p, uint32_t n, uint8_t* name, uint32_t* nl, uint8_t* value, uint32_t* vl, uint32_t* adv) {
     *adv = 0;
     if (n == 0) return 0;
     const uint8_t fb = p[0];
@@ -117,7 +117,7 @@ static int hp_field(orc_hpack* h, const uint8_t* p, uint32_t n, uint8_t* name, u
         if (max_size > h->max_size) h->max_size = max_size;
         else if (max_size < h->max_size) { h->max_size = max_size; while (h->size > h->max_size) hp_pop(h); }
         uint32_t a2 = 0;
-        int rc = hp_field(h, p + ib, n - (uint32_t)ib, name, nl, value, vl, &a2);
+        int rc = orc_hpack_field(h, p + ib, n - (uint32_t)ib, name, nl, value, vl, &a2);
         *adv = (uint32_t)ib + a2;
         return rc;
     }
@@ -148,7 +148,7 @@ int orc_hpack_decode_block(orc_hpack* h, const uint8_t* in, uint32_t n, uint8_t*
     uint32_t pos = 0, o = 0, cnt = 0; int status = 0;
     while (pos < n) {
         uint32_t nl = 0, vl = 0, adv = 0;
-        int rc = hp_field(h, in + pos, n - pos, name, &nl, value, &vl, &adv);
+        int rc = orc_hpack_field(h, in + pos, n - pos, name, &nl, value, &vl, &adv);
         if (rc < 0) { status = -1; break; }
         if (rc == 0) { status = 1; break; }
         if (o + 4 + nl + vl > out_cap) { status = -1; break; }

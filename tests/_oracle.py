@@ -205,3 +205,35 @@ def h2_scan(b, max_frame_size=16384):
     fr = np.zeros(cap, H2_FRAME_DT); consumed, err = C.c_uint32(), C.c_uint32()
     n = lib.orc_h2_scan(bytes(b), len(b), max_frame_size, fr.ctypes.data, cap, C.byref(consumed), C.byref(err))
     return fr[:n], consumed.value, err.value
+
+
+# ---- h2 server-side parser (a15) ----
+H2_MSG_DT = np.dtype([("run_idx", "<u4"), ("stream_id", "<u4"), ("headers_off", "<u4"), ("headers_len", "<u4"), ("n_headers", "<u4"),
+                      ("body_off", "<u4"), ("body_len", "<u4"), ("http_method", "<u4"), ("content_type", "<u4"), ("flags", "<u4"),
+                      ("method_idx", "<i4"), ("msg_off", "<u4"), ("msg_len", "<u4"), ("path_off", "<u4"), ("path_len", "<u4"), ("reserved", "<u4")])
+lib.orc_h2_conn_new.restype = C.c_void_p
+lib.orc_h2_conn_free.argtypes = [C.c_void_p]
+lib.orc_h2_consume.restype = C.c_uint32
+lib.orc_h2_consume.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
+                               C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
+                               C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+
+
+class H2Conn:
+    """One server-side H2Context of the oracle."""
+    def __init__(self, cfg=None):
+        self._h = lib.orc_h2_conn_new(); self.cfg = cfg or make_config()
+
+    def consume(self, b):
+        """Returns (parse_error, consumed, msgs, ctrl bytes, blob, remote_max_frame_size, remote_stream_window_size)."""
+        b = bytes(b)
+        msgs = np.zeros(256, H2_MSG_DT); ctrl = np.zeros(len(b) * 3 + 4096, np.uint8); blob = np.zeros(len(b) * 8 + (1 << 18), np.uint8)
+        cons, nm, cl, bl, mfs, sws = (C.c_uint32() for _ in range(6))
+        err = lib.orc_h2_consume(self._h, C.byref(self.cfg), b, len(b), C.byref(cons), msgs.ctypes.data, len(msgs), C.byref(nm),
+                                 ctrl.ctypes.data, len(ctrl), C.byref(cl), blob.ctypes.data, len(blob), C.byref(bl), C.byref(mfs), C.byref(sws))
+        assert nm.value <= len(msgs)
+        return err, cons.value, msgs[:nm.value], ctrl[:cl.value].tobytes(), blob[:bl.value], mfs.value, sws.value
+
+    def __del__(self):
+        if self._h:
+            lib.orc_h2_conn_free(self._h); self._h = None
