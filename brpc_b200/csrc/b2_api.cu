@@ -717,3 +717,42 @@ extern "C" int b2_h2_process_batch(b2_ctx* c, const void* bytes, uint32_t nbytes
     c->uploaded = false; c->executed = false;
     return B2_OK;
 }
+
+extern "C" int b2_h2_pack_responses(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_h2_response* resps, uint32_t n,
+                                    void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens) {
+    if (!c || !bytes || !resps || !out || !out_offs || !out_lens) { set_err("null argument"); return B2_E_INVAL; }
+    static_assert(sizeof(b2_h2_response) == 48, "h2 response ABI layout");
+    if (nbytes > c->opt.max_batch_bytes || n > c->opt.max_msgs || out_cap > 2ull * c->opt.max_resp_bytes) { set_err("exceeds ctx capacity"); return B2_E_CAPACITY; }
+    if (n == 0) return B2_OK;
+    std::vector<uint32_t> first;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const b2_h2_response& r = resps[i];
+        if (r.conn >= B2_H2_MAX_CONNS || (uint64_t)r.body_off + r.body_len > nbytes || (uint64_t)r.content_type_off + r.content_type_len > nbytes ||
+            (uint64_t)r.grpc_message_off + r.grpc_message_len > nbytes || r.content_type_len > 256 || r.grpc_message_len > 512) { set_err("bad response descriptor"); return B2_E_INVAL; }
+        if (i == 0 || r.conn != resps[i - 1].conn) first.push_back(i);
+        const uint64_t data = (uint64_t)r.body_len + 5;
+        const uint64_t need = data + 9 * (data / 16384 + 4) + 2ull * (r.content_type_len + r.grpc_message_len + 64) + 13 + 16;
+        out_offs[i] = (uint32_t)total;
+        total = (total + need + 15) & ~15ull;
+        if (total > out_cap) { set_err("out_cap too small"); return B2_E_CAPACITY; }
+    }
+    const uint32_t n_groups = (uint32_t)first.size();
+    first.push_back(n);
+    for (uint32_t g = 0; g < n_groups; g++)
+        for (uint32_t g2 = g + 1; g2 < n_groups; g2++) if (resps[first[g]].conn == resps[first[g2]].conn) { set_err("responses of one connection must be adjacent"); return B2_E_INVAL; }
+    int rc = h2_ensure(c); if (rc != B2_OK) return rc;
+    CU(cudaSetDevice(c->opt.device));
+    b2_h2_response* d_resps = reinterpret_cast<b2_h2_response*>(c->d_msgs);       // 48 B <= 64 B per entry
+    uint32_t* d_first = c->d_frame_off; uint32_t* d_offs = c->d_frame_run; uint32_t* d_lens = c->d_slot;
+    CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_resps, resps, sizeof(b2_h2_response) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_first, first.data(), 4 * first.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_offs, out_offs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    k_h2_pack<<<(n_groups + 31) / 32, 32, 0, c->stream>>>(c->d_bytes, d_resps, d_first, n_groups, c->d_h2, c->d_unz, d_offs, d_lens);
+    CU(cudaMemcpyAsync(out_lens, d_lens, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out, c->d_unz, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->uploaded = false; c->executed = false;
+    return B2_OK;
+}

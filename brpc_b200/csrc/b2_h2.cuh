@@ -247,6 +247,7 @@ struct H2Conn {
     uint32_t l_stream_window_size, l_max_frame_size;
     long long remote_window_left, deferred_window_update;
     H2Stream streams[kH2Pending];
+    HpackState enc;                                              // HPacker::_encode_table (responses)
     uint8_t slots[kH2Pending][kH2StreamBytes];                   // [0, kH2HdrBytes) header records, then the body
 };
 struct H2Out {                      // this run's slice of the output buffer
@@ -260,6 +261,7 @@ __device__ __forceinline__ void h2_conn_init(H2Conn& c) {
     c.l_stream_window_size = 256 * 1024; c.l_max_frame_size = 16384;     // H2Settings() defaults, http2.cpp:26-34
     c.remote_window_left = kH2MaxWindow; c.deferred_window_update = 0;
     for (uint32_t i = 0; i < kH2Pending; i++) c.streams[i].id = -1;
+    c.enc.max_size = 4096; c.enc.size = 0; c.enc.count = 0; c.enc.head = 0; c.enc.byte_head = 0;   // _hpacker.Init(header_table_size), :367
 }
 __device__ __forceinline__ void h2_put_head(uint8_t* p, uint32_t payload, uint8_t type, uint8_t flags, uint32_t sid) {   // SerializeFrameHead :123-136
     p[0] = (uint8_t)(payload >> 16); p[1] = (uint8_t)(payload >> 8); p[2] = (uint8_t)payload; p[3] = type; p[4] = flags;
@@ -665,6 +667,122 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
     b2_h2_run_status st; st.consumed = last_ok; st.parse_error = perr; st.n_msgs = n_msgs; st.first_msg = r * msg_cap_per_run;
     st.ctrl_off = r * region; st.ctrl_len = o.ctrl_len; st.remote_max_frame_size = c.r_max_frame_size; st.remote_stream_window_size = c.r_stream_window_size;
     rs[r] = st;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Response side: H2UnsentResponse::AppendAndDestroySelf (:1688-1750) + PackH2Message (:1310-1380), one thread per connection.
+__device__ __forceinline__ uint8_t lc(uint8_t c) { return (c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c; }
+__device__ __forceinline__ uint8_t* hp_put_int(uint8_t* p, uint8_t msb, uint32_t prefix, uint32_t value) {       // EncodeInteger :479-496
+    const uint32_t lim = (1u << prefix) - 1;
+    if (value < lim) { *p++ = (uint8_t)(msb | value); return p; }
+    value -= lim; *p++ = (uint8_t)(msb | lim);
+    for (; value >= 128;) { *p++ = (uint8_t)((value & 0x7f) | 0x80); value >>= 7; }
+    *p++ = (uint8_t)value;
+    return p;
+}
+// the encoder's view of "is this header / this name in a table": static first, then the connection's encode table;
+// names compare case-insensitively, entries with an empty value are never full matches (IndexTable::AddHeader :165-171)
+__device__ __forceinline__ uint32_t hp_enc_find(const HpackState& t, const uint8_t* n, uint32_t nl, const uint8_t* v, uint32_t vl, bool want_value) {
+    for (uint32_t i = 0; i < 61; i++) {                          // reverse insertion => the smallest index wins for names
+        if (kHpackStaticName[i][1] != nl) continue;
+        if (want_value && (vl == 0 || kHpackStaticValue[i][1] != vl)) continue;
+        bool eq = true;
+        for (uint32_t k = 0; k < nl && eq; k++) eq = lc(n[k]) == lc(kHpackStaticBlob[kHpackStaticName[i][0] + k]);
+        for (uint32_t k = 0; want_value && k < vl && eq; k++) eq = v[k] == kHpackStaticBlob[kHpackStaticValue[i][0] + k];
+        if (eq) return i + 1;
+    }
+    for (uint32_t i = 0; i < t.count; i++) {                     // newest first == the latest id of a duplicated header
+        const uint32_t e = (t.head + i) & 127u;
+        if (t.meta[e].nl != nl) continue;
+        if (want_value && (vl == 0 || t.meta[e].vl != vl)) continue;
+        bool eq = true;
+        for (uint32_t k = 0; k < nl && eq; k++) eq = lc(n[k]) == lc(t.bytes[(t.meta[e].off + k) & 4095u]);
+        for (uint32_t k = 0; want_value && k < vl && eq; k++) eq = v[k] == t.bytes[(t.meta[e].off + nl + k) & 4095u];
+        if (eq) return 62 + i;
+    }
+    return 0;
+}
+// HPacker::Encode (:696-726); hp_add wants name||value contiguous: `tmp` (>= nl + vl bytes) is scratch
+__device__ __forceinline__ uint8_t* hp_encode(HpackState& t, uint8_t* p, const uint8_t* n, uint32_t nl, const uint8_t* v, uint32_t vl, bool never_index, uint8_t* tmp) {
+    if (!never_index) {
+        const uint32_t idx = hp_enc_find(t, n, nl, v, vl, true);
+        if (idx) return hp_put_int(p, 0x80, 7, idx);
+    }
+    const uint32_t name_index = hp_enc_find(t, n, nl, nullptr, 0, false);
+    if (!never_index) {
+        for (uint32_t k = 0; k < nl; k++) tmp[k] = n[k];
+        for (uint32_t k = 0; k < vl; k++) tmp[nl + k] = v[k];
+        (void)hp_add(t, tmp, nl, vl);
+        p = hp_put_int(p, 0x40, 6, name_index);
+    } else p = hp_put_int(p, 0x10, 4, name_index);
+    if (name_index == 0) { p = hp_put_int(p, 0x00, 7, nl); for (uint32_t k = 0; k < nl; k++) *p++ = lc(n[k]); }
+    p = hp_put_int(p, 0x00, 7, vl); for (uint32_t k = 0; k < vl; k++) *p++ = v[k];
+    return p;
+}
+__device__ __forceinline__ uint32_t put_dec_i32_h2(uint8_t* p, int32_t v) {     // "%d"
+    uint8_t tmp[12]; uint32_t n = 0; uint32_t u = v < 0 ? (uint32_t)(-(long long)v) : (uint32_t)v;
+    do { tmp[n++] = (uint8_t)('0' + u % 10); u /= 10; } while (u);
+    uint32_t o = 0; if (v < 0) p[o++] = '-';
+    while (n) p[o++] = tmp[--n];
+    return o;
+}
+constexpr uint32_t kH2FragCap = 1024;      // encoded header block of one response (":status", "content-type", trailers)
+__global__ void k_h2_pack(const uint8_t* bytes, const b2_h2_response* resps, const uint32_t* group_first, uint32_t n_groups, H2Conn* conns,
+                          uint8_t* out, const uint32_t* out_offs, uint32_t* out_lens) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    uint8_t frag[kH2FragCap], trailer[kH2FragCap], tmp[kH2FragCap];
+    for (uint32_t i = group_first[g]; i < group_first[g + 1]; i++) {
+        const b2_h2_response R = resps[i];
+        H2Conn& c = conns[R.conn];
+        uint8_t* o0 = out + out_offs[i]; uint8_t* o = o0;
+        const bool grpc = R.flags & B2_H2_RESP_GRPC;
+        const uint32_t data_size = R.body_len + (grpc ? 5u : 0u);
+        // MinusWindowSize(&_remote_window_left, _data.size()) (:283-296)
+        if (c.remote_window_left < (long long)data_size) {
+            h2_put_head(o, 4, 3, 0, R.stream_id); put_be32(o + 9, 3); out_lens[i] = 13; continue;
+        }
+        c.remote_window_left -= (long long)data_size;
+        const bool never = c.r_header_table_size == 0;
+        uint8_t num[16];
+        uint8_t* f = frag;
+        { const uint32_t nn = put_dec_i32_h2(num, R.status_code); f = hp_encode(c.enc, f, (const uint8_t*)":status", 7, num, nn, never, tmp); }
+        if (R.content_type_len) f = hp_encode(c.enc, f, (const uint8_t*)"content-type", 12, bytes + R.content_type_off, R.content_type_len, never, tmp);
+        uint8_t* t = trailer;
+        if (grpc) {
+            const uint32_t nn = put_dec_i32_h2(num, R.grpc_status);
+            t = hp_encode(c.enc, t, (const uint8_t*)"grpc-status", 11, num, nn, never, tmp);
+            if (R.grpc_message_len) t = hp_encode(c.enc, t, (const uint8_t*)"grpc-message", 12, bytes + R.grpc_message_off, R.grpc_message_len, never, tmp);
+        }
+        const uint32_t fl = (uint32_t)(f - frag), tl = (uint32_t)(t - trailer), mfs = c.r_max_frame_size;
+        // ---- PackH2Message
+        uint8_t hflags = (data_size == 0 && tl == 0) ? 0x1 : 0;
+        if (fl <= mfs) { h2_put_head(o, fl, 1, hflags | 0x4, R.stream_id); o += 9; for (uint32_t k = 0; k < fl; k++) *o++ = frag[k]; }
+        else {                                                    // (cannot happen with kH2FragCap < 16384 <= max_frame_size; kept for the shape)
+            h2_put_head(o, mfs, 1, hflags, R.stream_id); o += 9; for (uint32_t k = 0; k < mfs; k++) *o++ = frag[k];
+            for (uint32_t at = mfs; at < fl;) { const uint32_t nn = min(fl - at, mfs); h2_put_head(o, nn, 9, at + nn == fl ? 0x4 : 0, R.stream_id); o += 9; for (uint32_t k = 0; k < nn; k++) *o++ = frag[at + k]; at += nn; }
+        }
+        const uint8_t* body = bytes + R.body_off;
+        for (uint32_t at = 0; at < data_size;) {
+            const uint32_t nn = min(data_size - at, mfs);
+            const uint8_t dflags = (at + nn == data_size && tl == 0) ? 0x1 : 0;
+            h2_put_head(o, nn, 0, dflags, R.stream_id); o += 9;
+            for (uint32_t k = 0; k < nn; k++) {
+                const uint32_t q = at + k;
+                uint8_t b;
+                if (grpc) { if (q == 0) b = 0; else if (q < 5) b = (uint8_t)(R.body_len >> (8 * (4 - q))); else b = body[q - 5]; }   // AddGrpcPrefix: flag 0 + BE32 length
+                else b = body[q];
+                *o++ = b;
+            }
+            at += nn;
+        }
+        if (tl) { h2_put_head(o, tl, 1, 0x5, R.stream_id); o += 9; for (uint32_t k = 0; k < tl; k++) *o++ = trailer[k]; }
+        if (c.deferred_window_update > 0) {                       // ReleaseDeferredWindowUpdate
+            const long long cw = c.deferred_window_update; c.deferred_window_update = 0;
+            h2_put_head(o, 4, 8, 0, 0); put_be32(o + 9, (uint32_t)cw); o += 13;
+        }
+        out_lens[i] = (uint32_t)(o - o0);
+    }
 }
 #endif
 }  // namespace b2

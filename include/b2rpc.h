@@ -364,6 +364,30 @@ int  b2_h2_process_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const 
                          b2_h2_run_status* rs, b2_h2_msg* msgs, uint32_t msg_cap, uint32_t* n_msgs,
                          void* out, uint32_t out_cap);
 
+/* b2_h2_pack_responses: H2UnsentResponse::AppendAndDestroySelf (src/brpc/policy/http2_rpc_protocol.cpp:1688-1750) +
+ * PackH2Message (:1310-1380) + AddGrpcPrefix (policy/http_rpc_protocol.cpp:254-262) for a list of responses:
+ * connection flow control (MinusWindowSize, else RST_STREAM(FLOW_CONTROL_ERROR)), HPacker::Encode (details/hpack.cpp:696-726)
+ * of ":status" and "content-type" — and of the "grpc-status" / "grpc-message" trailers of a gRPC response — against
+ * the connection's ENCODER table (indexed if present, else literal with incremental indexing and a name index when one
+ * exists, no Huffman: the reference's defaults; never-indexed when the peer announced header_table_size 0), HEADERS
+ * (+CONTINUATION), DATA frames split at the peer's max_frame_size, trailers, and the deferred connection WINDOW_UPDATE.
+ * Responses of one connection must be adjacent and in write order; the state is the connection's (b2_h2_process_batch).
+ * Response i's bytes land at out + out_offs[i] (filled by the call), out_lens[i] long.  User-defined response headers
+ * are not covered. */
+#define B2_H2_RESP_GRPC 1u
+typedef struct b2_h2_response {
+    uint32_t conn, stream_id;
+    int32_t  status_code;                            /* :status */
+    uint32_t flags;                                  /* B2_H2_RESP_GRPC */
+    uint32_t content_type_off, content_type_len;     /* inside bytes; length 0 = no content-type header */
+    uint32_t body_off, body_len;                     /* the body; for gRPC the serialized message (the prefix is added here) */
+    int32_t  grpc_status;
+    uint32_t grpc_message_off, grpc_message_len;     /* already percent-encoded; length 0 = none */
+    uint32_t reserved;
+} b2_h2_response;                                    /* 48 bytes */
+int  b2_h2_pack_responses(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_h2_response* resps, uint32_t n,
+                          void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens);
+
 /* ---- counters (bvar::Adder-like): per-GPU totals accumulated by
  * the kernels: [0] in_bytes [1] in_msgs [2] out_bytes [3] out_msgs [4] errors
  * [5] batches [6..7] reserved.  The cross-GPU reduce is an NCCL all-reduce on

@@ -152,6 +152,9 @@ uint32_t orc_h2_consume(orc_h2_conn* c, const orc_config* cfg, const uint8_t* in
                         uint8_t* ctrl, uint32_t ctrl_cap, uint32_t* ctrl_len,
                         uint8_t* blob, uint32_t blob_cap, uint32_t* blob_len,
                         uint32_t* remote_max_frame_size, uint32_t* remote_stream_window_size);
+/* one response through H2UnsentResponse::AppendAndDestroySelf + PackH2Message on this connection; returns the byte count
+ * (out must hold body_len + 9 * (body_len / 16384 + 8) + 1 KiB) */
+uint32_t orc_h2_pack_response(orc_h2_conn* c, const b2_h2_response* r, const uint8_t* bytes, uint8_t* out);
 uint32_t orc_h2_scan(const uint8_t* in, uint32_t n, uint32_t max_frame_size, orc_h2_frame* frames, uint32_t cap,
                      uint32_t* consumed, uint32_t* err);
 #ifdef __cplusplus

@@ -7,6 +7,7 @@
  * brpc itself cannot be built here and its tests hold no byte-level h2 server transcripts (test/brpc_h2_unittest*
  * drives client and server together), so this part is "parity unpinned" beyond the RFC 7541 HPACK vectors. */
 #include "b2_oracle.h"
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -26,6 +27,8 @@ struct orc_h2_conn {
     int64_t remote_window_left, deferred_window_update;
     h2_stream* streams; uint32_t n_pending, cap;      /* _pending_streams */
     orc_hpack* hp;
+    /* HPacker::_encode_table: newest first */
+    struct enc_entry { uint8_t* name; uint32_t nl; uint8_t* value; uint32_t vl; }* enc; uint32_t enc_count, enc_cap, enc_size, enc_max;
 };
 orc_h2_conn* orc_h2_conn_new(void) {                 /* H2Context::H2Context (:323-353) + Init (:363-371), server side */
     orc_h2_conn* c = (orc_h2_conn*)calloc(1, sizeof *c);
@@ -35,12 +38,15 @@ orc_h2_conn* orc_h2_conn_new(void) {                 /* H2Context::H2Context (:3
     c->l_stream_window_size = 256 * 1024; c->l_max_frame_size = 16384;
     c->remote_window_left = MAX_WINDOW;
     c->hp = orc_hpack_new(4096);
+    c->enc_max = 4096;
     return c;
 }
 static void stream_free(h2_stream* s) { free(s->hdr); free(s->body); }
 void orc_h2_conn_free(orc_h2_conn* c) {
     if (!c) return;
     for (uint32_t i = 0; i < c->n_pending; i++) stream_free(&c->streams[i]);
+    for (uint32_t i = 0; i < c->enc_count; i++) { free(c->enc[i].name); free(c->enc[i].value); }
+    free(c->enc);
     free(c->streams); orc_hpack_free(c->hp); free(c);
 }
 typedef struct { uint8_t* p; uint32_t cap, len; int ovf; } wbuf;
@@ -392,4 +398,99 @@ uint32_t orc_h2_consume(orc_h2_conn* c, const orc_config* cfg, const uint8_t* in
     *consumed = last_ok; *n_msgs = nm; *ctrl_len = w.len; *blob_len = blob.len;
     *remote_max_frame_size = c->r_max_frame_size; *remote_stream_window_size = c->r_stream_window_size;
     return perr;
+}
+
+/* ---- response side: H2UnsentResponse::AppendAndDestroySelf (:1688-1750) + PackH2Message (:1310-1380) -------------------- */
+#include "hpack_tables.h"
+static uint8_t lc(uint8_t c) { return (c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c; }
+static int ci_same(const uint8_t* a, const uint8_t* b, uint32_t n) { for (uint32_t i = 0; i < n; i++) if (lc(a[i]) != lc(b[i])) return 0; return 1; }
+/* FindHeaderFromIndexTable / FindNameFromIndexTable (hpack.cpp:676-694): static table first (names resolve to their
+ * smallest index: the table is filled in reverse, :250-258), then the latest matching entry of the encode table */
+static uint32_t enc_find(const orc_h2_conn* c, const uint8_t* n, uint32_t nl, const uint8_t* v, uint32_t vl, int want_value) {
+    for (uint32_t i = 0; i < 61; i++) {
+        if (orc_hpack_static_name[i][1] != nl || !ci_same(n, orc_hpack_static_blob + orc_hpack_static_name[i][0], nl)) continue;
+        if (want_value && (vl == 0 || orc_hpack_static_value[i][1] != vl || memcmp(v, orc_hpack_static_blob + orc_hpack_static_value[i][0], vl) != 0)) continue;
+        return i + 1;
+    }
+    for (uint32_t i = 0; i < c->enc_count; i++) {
+        if (c->enc[i].nl != nl || !ci_same(n, c->enc[i].name, nl)) continue;
+        if (want_value && (vl == 0 || c->enc[i].vl != vl || memcmp(v, c->enc[i].value, vl) != 0)) continue;
+        return 62 + i;
+    }
+    return 0;
+}
+static void enc_add(orc_h2_conn* c, const uint8_t* n, uint32_t nl, const uint8_t* v, uint32_t vl) {       /* IndexTable::AddHeader :146-173 */
+    const uint32_t es = nl + vl + 32;
+    while (c->enc_count && c->enc_size + es > c->enc_max) {
+        struct enc_entry* e = &c->enc[c->enc_count - 1];
+        c->enc_size -= e->nl + e->vl + 32; free(e->name); free(e->value); c->enc_count--;
+    }
+    if (es > c->enc_max) return;
+    if (c->enc_count == c->enc_cap) { c->enc_cap = c->enc_cap ? c->enc_cap * 2 : 16; c->enc = (struct enc_entry*)realloc(c->enc, sizeof(struct enc_entry) * c->enc_cap); }
+    memmove(&c->enc[1], &c->enc[0], sizeof(struct enc_entry) * c->enc_count);
+    c->enc[0].name = (uint8_t*)malloc(nl ? nl : 1); memcpy(c->enc[0].name, n, nl); c->enc[0].nl = nl;
+    c->enc[0].value = (uint8_t*)malloc(vl ? vl : 1); memcpy(c->enc[0].value, v, vl); c->enc[0].vl = vl;
+    c->enc_count++; c->enc_size += es;
+}
+static uint8_t* put_int(uint8_t* p, uint8_t msb, uint32_t prefix, uint32_t value) {                      /* EncodeInteger :479-496 */
+    const uint32_t lim = (1u << prefix) - 1;
+    if (value < lim) { *p++ = (uint8_t)(msb | value); return p; }
+    value -= lim; *p++ = (uint8_t)(msb | lim);
+    for (; value >= 128;) { *p++ = (uint8_t)((value & 0x7f) | 0x80); value >>= 7; }
+    *p++ = (uint8_t)value;
+    return p;
+}
+static uint8_t* encode(orc_h2_conn* c, uint8_t* p, const char* name, const uint8_t* v, uint32_t vl, int never_index) {   /* HPacker::Encode :696-726 */
+    const uint8_t* n = (const uint8_t*)name; const uint32_t nl = (uint32_t)strlen(name);
+    if (!never_index) {
+        const uint32_t idx = enc_find(c, n, nl, v, vl, 1);
+        if (idx) return put_int(p, 0x80, 7, idx);
+    }
+    const uint32_t name_index = enc_find(c, n, nl, NULL, 0, 0);
+    if (!never_index) { enc_add(c, n, nl, v, vl); p = put_int(p, 0x40, 6, name_index); }
+    else p = put_int(p, 0x10, 4, name_index);
+    if (name_index == 0) { p = put_int(p, 0x00, 7, nl); for (uint32_t k = 0; k < nl; k++) *p++ = lc(n[k]); }
+    p = put_int(p, 0x00, 7, vl); memcpy(p, v, vl); p += vl;
+    return p;
+}
+uint32_t orc_h2_pack_response(orc_h2_conn* c, const b2_h2_response* R, const uint8_t* bytes, uint8_t* out) {
+    uint8_t* o = out;
+    const int grpc = R->flags & B2_H2_RESP_GRPC;
+    const uint32_t data_size = R->body_len + (grpc ? 5u : 0u);
+    if (c->remote_window_left < (int64_t)data_size) {                       /* MinusWindowSize :283-296 -> RST_STREAM(FLOW_CONTROL_ERROR) */
+        put_head(o, 4, 3, 0, R->stream_id); put32(o + 9, 3); return 13;
+    }
+    c->remote_window_left -= (int64_t)data_size;
+    const int never = c->r_header_table_size == 0;
+    uint8_t* frag = (uint8_t*)malloc(4096); uint8_t* trailer = (uint8_t*)malloc(4096);
+    char num[16];
+    uint8_t* f = frag;
+    snprintf(num, sizeof num, "%d", R->status_code);
+    f = encode(c, f, ":status", (const uint8_t*)num, (uint32_t)strlen(num), never);
+    if (R->content_type_len) f = encode(c, f, "content-type", bytes + R->content_type_off, R->content_type_len, never);
+    uint8_t* t = trailer;
+    if (grpc) {
+        snprintf(num, sizeof num, "%d", R->grpc_status);
+        t = encode(c, t, "grpc-status", (const uint8_t*)num, (uint32_t)strlen(num), never);
+        if (R->grpc_message_len) t = encode(c, t, "grpc-message", bytes + R->grpc_message_off, R->grpc_message_len, never);
+    }
+    const uint32_t fl = (uint32_t)(f - frag), tl = (uint32_t)(t - trailer), mfs = c->r_max_frame_size;
+    uint8_t* data = (uint8_t*)malloc(data_size ? data_size : 1);
+    if (grpc) { data[0] = 0; put32(data + 1, R->body_len); memcpy(data + 5, bytes + R->body_off, R->body_len); }   /* AddGrpcPrefix */
+    else memcpy(data, bytes + R->body_off, R->body_len);
+    uint8_t hflags = (data_size == 0 && tl == 0) ? 0x1 : 0;
+    if (fl <= mfs) { put_head(o, fl, 1, hflags | 0x4, R->stream_id); o += 9; memcpy(o, frag, fl); o += fl; }
+    else {
+        put_head(o, mfs, 1, hflags, R->stream_id); o += 9; memcpy(o, frag, mfs); o += mfs;
+        for (uint32_t at = mfs; at < fl;) { const uint32_t nn = fl - at < mfs ? fl - at : mfs; put_head(o, nn, 9, at + nn == fl ? 0x4 : 0, R->stream_id); o += 9; memcpy(o, frag + at, nn); o += nn; at += nn; }
+    }
+    for (uint32_t at = 0; at < data_size;) {
+        const uint32_t nn = data_size - at < mfs ? data_size - at : mfs;
+        put_head(o, nn, 0, (at + nn == data_size && tl == 0) ? 0x1 : 0, R->stream_id); o += 9;
+        memcpy(o, data + at, nn); o += nn; at += nn;
+    }
+    if (tl) { put_head(o, tl, 1, 0x5, R->stream_id); o += 9; memcpy(o, trailer, tl); o += tl; }
+    if (c->deferred_window_update > 0) { const int64_t cw = c->deferred_window_update; c->deferred_window_update = 0; put_head(o, 4, 8, 0, 0); put32(o + 9, (uint32_t)cw); o += 13; }
+    free(frag); free(trailer); free(data);
+    return (uint32_t)(o - out);
 }

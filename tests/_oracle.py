@@ -211,6 +211,11 @@ def h2_scan(b, max_frame_size=16384):
 H2_MSG_DT = np.dtype([("run_idx", "<u4"), ("stream_id", "<u4"), ("headers_off", "<u4"), ("headers_len", "<u4"), ("n_headers", "<u4"),
                       ("body_off", "<u4"), ("body_len", "<u4"), ("http_method", "<u4"), ("content_type", "<u4"), ("flags", "<u4"),
                       ("method_idx", "<i4"), ("msg_off", "<u4"), ("msg_len", "<u4"), ("path_off", "<u4"), ("path_len", "<u4"), ("reserved", "<u4")])
+H2_RESPONSE_DT = np.dtype([("conn", "<u4"), ("stream_id", "<u4"), ("status_code", "<i4"), ("flags", "<u4"), ("content_type_off", "<u4"),
+                           ("content_type_len", "<u4"), ("body_off", "<u4"), ("body_len", "<u4"), ("grpc_status", "<i4"),
+                           ("grpc_message_off", "<u4"), ("grpc_message_len", "<u4"), ("reserved", "<u4")])
+lib.orc_h2_pack_response.restype = C.c_uint32
+lib.orc_h2_pack_response.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]
 lib.orc_h2_conn_new.restype = C.c_void_p
 lib.orc_h2_conn_free.argtypes = [C.c_void_p]
 lib.orc_h2_consume.restype = C.c_uint32
@@ -233,6 +238,15 @@ class H2Conn:
                                  ctrl.ctypes.data, len(ctrl), C.byref(cl), blob.ctypes.data, len(blob), C.byref(bl), C.byref(mfs), C.byref(sws))
         assert nm.value <= len(msgs)
         return err, cons.value, msgs[:nm.value], ctrl[:cl.value].tobytes(), blob[:bl.value], mfs.value, sws.value
+
+    def pack_response(self, stream_id, body=b"", status=200, content_type=b"application/grpc", grpc=True, grpc_status=0, grpc_message=b""):
+        blob = bytes(content_type) + bytes(body) + bytes(grpc_message)
+        r = np.zeros(1, H2_RESPONSE_DT)
+        r[0] = (0, stream_id, status, 1 if grpc else 0, 0, len(content_type), len(content_type), len(body), grpc_status,
+                len(content_type) + len(body), len(grpc_message), 0)
+        out = np.zeros(len(body) * 2 + 4096, np.uint8)
+        n = lib.orc_h2_pack_response(self._h, r.ctypes.data, blob, out.ctypes.data)
+        return out[:n].tobytes()
 
     def __del__(self):
         if self._h:

@@ -79,3 +79,27 @@ def test_every_split_point_gives_the_same_transcript():
             if e not in (2,):
                 break
         assert (ctrl2, got) == ref, step
+
+
+def test_grpc_response_bytes_first_and_later_calls():
+    """H2UnsentResponse::AppendAndDestroySelf + PackH2Message: the first response on a connection carries literal
+    (incrementally indexed) content-type / grpc-status fields, later ones are fully indexed (hpack.cpp:696-726)."""
+    c = O.H2Conn()
+    c.consume(T.PREFACE + T.settings())
+    r1 = c.pack_response(1, b"\x0a\x05hello")
+    assert r1 == (bytes.fromhex("000013010400000001") + b"\x88\x5f\x10application/grpc" +
+                  bytes.fromhex("00000c000000000001") + b"\x00\x00\x00\x00\x07\x0a\x05hello" +
+                  bytes.fromhex("00000f010500000001") + b"\x40\x0bgrpc-status\x010")
+    r2 = c.pack_response(3, b"\x0a\x05hello")
+    assert r2 == bytes.fromhex("000002010400000003" "88bf" "00000c000000000003") + b"\x00\x00\x00\x00\x07\x0a\x05hello" + bytes.fromhex("000001010500000003" "be")
+    r3 = c.pack_response(5, b"", grpc_status=12, grpc_message=b"no%20method")
+    assert r3.endswith(b"\x7e\x0212\x40\x0cgrpc-message\x0bno%20method") and bytes.fromhex("000005000000000005" "0000000000") in r3
+    # a body longer than the peer's max_frame_size is cut into DATA frames; the last one does not end the stream (trailers do)
+    big = c.pack_response(7, b"z" * 40000)
+    assert big.count(bytes.fromhex("004000000000000007")) == 2 and bytes.fromhex("001c45000000000007") in big
+    # peer announced header_table_size 0: never-indexed literals (index_policy, :1718-1720)
+    c2 = O.H2Conn(); c2.consume(T.PREFACE + T.settings([(1, 0)]))
+    assert c2.pack_response(1, b"", grpc=False, content_type=b"text/plain") == bytes.fromhex("000012010500000001") + b"\x18\x03200\x1f\x10\x0atext/plain"
+    # connection window exhausted: RST_STREAM(FLOW_CONTROL_ERROR) instead of the response (:1706-1712)
+    c3 = O.H2Conn(); c3.consume(T.PREFACE + T.settings())
+    assert c3.pack_response(1, b"y" * 70000) == bytes.fromhex("000004030000000001" "00000003")
