@@ -158,6 +158,109 @@ def cpu_arm(data, runs, threads, min_seconds):
     return best[1] / best[0], best[1], n
 
 
+def grpc_h2_main(args):
+    """BASELINE configs[3]: h2/gRPC unary calls with 4 KB messages, 256 connections per GPU, through the h2 entry points
+    of the C ABI (b2_h2_process_batch + b2_h2_pack_responses, host buffers, synchronous): parse + echo + reply framing.
+    A side measurement (the h2 path is one thread per connection; it is latency-, not bandwidth-bound)."""
+    import torch
+    import brpc_b200
+    from brpc_b200.abi import H2_RESPONSE_DT
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _h2traffic as T
+    import random
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    hbm_peak, peak_src = read_peaks()
+    n_conns, K, msg_len = 256, args.frames_per_stream, args.payload if args.payload != 1024 else 4096
+    steps, warmup = max(1, min(args.steps, 200)), max(3, args.warmup)
+    rng = random.Random(20260921 + rank)
+    ctx = brpc_b200.Context(device=dev, max_batch_bytes=64 << 20, max_msgs=1 << 16, max_runs=1024, max_resp_bytes=128 << 20)
+    message = bytes(rng.choice(b"abcdefghijklmnopqrstuvwxyz0123456789") for _ in range(msg_len))
+    # one batch = K complete calls per connection; the same bytes are replayed every step with fresh (growing) stream ids
+    first_batch, batch, sid_pos = [], [], []
+    for cidx in range(n_conns):
+        ctx.h2_conn_reset(cidx)
+        enc = T.HpackEncoder(rng); enc.fixed_mode = "auto"              # indexed when present, else literal + incremental indexing
+        warm = b"".join(T.request_frames(rng, enc, 1, message=message, chunk=16384))       # fills the HPACK tables: later calls are all table hits
+        first_batch.append(T.PREFACE + T.settings() + warm)
+        calls = [T.request_frames(rng, enc, 3 + 2 * k, message=message, chunk=16384) for k in range(K)]
+        # the client returns the connection-level credit the replies of the previous round used (WINDOW_UPDATE on stream 0)
+        batch.append(T.frame(8, 0, 0, (K * (msg_len + 16)).to_bytes(4, "big")) + b"".join(b"".join(c) for c in calls))
+    data0, runs0 = brpc_b200.make_runs(first_batch)
+    rs, msgs, out = ctx.h2_process_batch(data0, runs0)
+    assert int(rs["n_msgs"].sum()) == n_conns
+    data, runs = brpc_b200.make_runs(batch)
+    data = np.array(data, dtype=np.uint8)
+    pos = []                                                   # offsets of every frame's stream-id field
+    for r_ in runs:
+        p_ = int(r_["offset"]); end = p_ + int(r_["length"])
+        while p_ < end:
+            ln = (int(data[p_]) << 16) | (int(data[p_ + 1]) << 8) | int(data[p_ + 2])
+            pos.append(p_ + 5); p_ += 9 + ln
+    pos = np.array(pos, dtype=np.int64)
+    pos = pos[(data[pos] | data[pos + 1] | data[pos + 2] | data[pos + 3]) != 0]        # stream 0 (connection) frames keep their id
+    base_sid = ((data[pos].astype(np.int64) << 24) | (data[pos + 1].astype(np.int64) << 16) | (data[pos + 2].astype(np.int64) << 8) | data[pos + 3])
+
+    def set_round(t):
+        sid = base_sid + 2 * K * t
+        data[pos] = (sid >> 24) & 255; data[pos + 1] = (sid >> 16) & 255; data[pos + 2] = (sid >> 8) & 255; data[pos + 3] = sid & 255
+
+    ct = b"application/grpc"
+    # where the content-type value sits inside a request's header records (same for every steady-state call)
+    hb0 = bytes(out[msgs[0]["headers_off"]:msgs[0]["headers_off"] + msgs[0]["headers_len"]]); ct_rel = hb0.index(ct)
+    def one_step(t, check=False):
+        set_round(t)
+        rs, msgs, out = ctx.h2_process_batch(data, runs, msg_cap=n_conns * (K + 2), out_cap=n_conns * (K * 1024 + 8192))
+        n = len(msgs)
+        assert n == n_conns * K, (n, rs["parse_error"][:4])
+        # echo: the reply message is the request message, still on the device (input buffer when one DATA frame carried it,
+        # else the out buffer); the reply's content-type is the request's own value inside out — nothing is uploaded again
+        resps = np.zeros(n, dtype=H2_RESPONSE_DT)
+        resps["conn"] = runs["socket_id"][msgs["run_idx"]]; resps["stream_id"] = msgs["stream_id"]; resps["status_code"] = 200
+        resps["flags"] = 1 | 8 | np.where(msgs["flags"] & 16, 2, 4)
+        resps["content_type_off"] = msgs["headers_off"] + ct_rel; resps["content_type_len"] = len(ct)
+        resps["body_off"] = msgs["msg_off"]; resps["body_len"] = msgs["msg_len"]
+        pout, poffs, plens = ctx.h2_pack_responses(None, resps, out_cap=n * (msg_len + 256) + 4096, raw=True)
+        if check:
+            assert np.all(plens > msg_len) and bytes(pout[poffs[0] + 9:poffs[0] + 10]) == b"\x88"       # HEADERS begin with :status 200 (static index 8)
+        return n
+    for t in range(warmup):
+        one_step(t, check=True)
+    sampler = ClockSampler(dev); sampler.start()
+    torch.cuda.synchronize(); t0 = time.perf_counter(); total = 0
+    for t in range(steps):
+        total += one_step(warmup + t)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    ms = wall * 1e3 / steps
+    if rank == 0:
+        line = {"metric": "h2/gRPC echo QPS, %d B messages" % msg_len, "value": total / wall, "unit": "msgs/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "grpc_c++-style unary calls over h2: %d connections/GPU x %d calls per batch, %d B messages, HPACK dynamic-table hits" % (n_conns, K, msg_len),
+                           "note": "timed through the synchronous C ABI with host buffers (copies and the Python glue that builds the response list included)"},
+                "e2e": {"value": total / wall, "unit": "msgs/s", "h2d_bytes_per_step": int(data.nbytes + runs.nbytes + n_conns * K * 48),
+                        "d2h_bytes_per_step": int(n_conns * K * (64 + 320 + msg_len + 64) + n_conns * 32)},
+                "gpu_launches": int(2 * steps), "clocks": clocks}
+        if not args.no_cpu_baseline:
+            import _oracle as O
+            conns = [O.H2Conn() for _ in range(8)]
+            for i_, c_ in enumerate(conns): c_.consume(first_batch[i_])
+            t1 = time.perf_counter(); n = 0; rounds = 0
+            while time.perf_counter() - t1 < 5.0:
+                set_round(1000 + rounds); rounds += 1
+                for i_, c_ in enumerate(conns):
+                    o_, l_ = int(runs["offset"][i_]), int(runs["length"][i_])
+                    e_, cons_, om, _, ob, _, _ = c_.consume(data[o_:o_ + l_].tobytes())
+                    for m_ in om:
+                        c_.pack_response(int(m_["stream_id"]), bytes(ob[m_["msg_off"]:m_["msg_off"] + m_["msg_len"]])); n += 1
+            line["cpu_baseline"] = {"value": n / (time.perf_counter() - t1), "unit": "msgs/s", "cores": 1, "kind": "port",
+                                    "sample": "8 of the %d connections, parse + pack through the oracle (Python glue included), ~5 s" % n_conns}
+        print(json.dumps(line))
+    return 0
+
+
 def stream_snappy_main(args):
     """BASELINE configs[4]: streaming_rpc DATA frames carrying 256 KiB snappy-compressed messages, 64 streams per GPU;
     the device cuts the frames, decodes StreamFrameMeta and decompresses every payload (b2_set_stream_handler).
@@ -318,12 +421,14 @@ def main():
     ap.add_argument("--payload-kind", type=int, default=0, help="0 = 'r' fill, 1 = random over 62 symbols")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--pipeline", type=int, default=2, help="resident batches in flight per GPU (one ctx + stream each)")
-    ap.add_argument("--workload", default="echo", choices=["echo", "stream_snappy"],
+    ap.add_argument("--workload", default="echo", choices=["echo", "stream_snappy", "grpc_h2"],
                     help="echo = the headline metric; stream_snappy = BASELINE configs[4] (256 KiB snappy streaming frames), a side measurement")
     ap.add_argument("--frames-per-stream", type=int, default=8)
     args = ap.parse_args()
     if args.workload == "stream_snappy":
         return stream_snappy_main(args)
+    if args.workload == "grpc_h2":
+        return grpc_h2_main(args)
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

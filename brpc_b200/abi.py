@@ -322,18 +322,24 @@ class Context:
         n = len(runs)
         msg_cap = msg_cap or max(64, 64 * n)
         out_cap = out_cap or max(1 << 16, n * (1 << 17))
-        rs = np.zeros(n, H2_RUN_STATUS_DT); msgs = np.zeros(msg_cap, H2_MSG_DT); out = np.zeros(out_cap, np.uint8); nm = C.c_uint32(0)
+        rs = np.zeros(n, H2_RUN_STATUS_DT); msgs = np.zeros(msg_cap, H2_MSG_DT); out = np.empty(out_cap, np.uint8); nm = C.c_uint32(0)
         _check(lib.b2_h2_process_batch(self._h, data.ctypes.data, data.nbytes, runs.ctypes.data, n, rs.ctypes.data, msgs.ctypes.data, msg_cap,
                                        C.byref(nm), out.ctypes.data, out_cap))
         return rs, msgs[:nm.value], out
 
-    def h2_pack_responses(self, data, resps, out_cap=None):
+    def h2_pack_responses(self, data, resps, out_cap=None, raw=False):
         """resps: H2_RESPONSE_DT array (offsets into data).  Returns the packed bytes of every response."""
-        data = np.ascontiguousarray(data, dtype=np.uint8); resps = np.ascontiguousarray(resps, dtype=H2_RESPONSE_DT)
+        resps = np.ascontiguousarray(resps, dtype=H2_RESPONSE_DT)
         n = len(resps)
         out_cap = out_cap or int(resps["body_len"].astype(np.int64).sum() * 2 + n * 2048 + 4096)
-        out = np.zeros(out_cap, np.uint8); offs = np.zeros(n, np.uint32); lens = np.zeros(n, np.uint32)
-        _check(lib.b2_h2_pack_responses(self._h, data.ctypes.data, data.nbytes, resps.ctypes.data, n, out.ctypes.data, out_cap, offs.ctypes.data, lens.ctypes.data))
+        out = np.empty(out_cap, np.uint8); offs = np.zeros(n, np.uint32); lens = np.zeros(n, np.uint32)
+        if data is None:                 # every field uses a zero-copy source (B2_H2_RESP_*_IN_INPUT / _IN_OUT)
+            ptr, nb = None, 0
+        else:
+            data = np.ascontiguousarray(data, dtype=np.uint8); ptr, nb = data.ctypes.data, data.nbytes
+        _check(lib.b2_h2_pack_responses(self._h, ptr, nb, resps.ctypes.data, n, out.ctypes.data, out_cap, offs.ctypes.data, lens.ctypes.data))
+        if raw:
+            return out, offs, lens
         return [out[offs[i]:offs[i] + lens[i]].tobytes() for i in range(n)]
 
     def counters(self):

@@ -37,7 +37,7 @@ struct b2_ctx {
     uint8_t* d_bytes = nullptr; b2_run* d_runs = nullptr; uint32_t* d_run_tile_base = nullptr;
     TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; uint32_t* d_tile_scratch = nullptr; b2_run_status* d_run_status = nullptr;
     uint32_t* d_frame_off = nullptr; uint32_t* d_frame_run = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr; PackJob* d_jobs = nullptr; uint32_t* d_slow_idx = nullptr; uint8_t* d_heads = nullptr;
-    uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr; uint8_t* d_unz = nullptr; uint16_t* d_snappy_tab = nullptr; HpackState* d_hpack = nullptr; H2Conn* d_h2 = nullptr;
+    uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr; uint8_t* d_unz = nullptr; uint16_t* d_snappy_tab = nullptr; HpackState* d_hpack = nullptr; H2Conn* d_h2 = nullptr; uint64_t h2_last_in = 0, h2_last_out = 0;   // sizes of the last h2 batch still on the device
     uint32_t* d_crc_adv = nullptr; unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
     uint32_t max_tiles = 0; uint32_t n_sms = 148; bool use_tma_pack = true; uint32_t stage_mask = 7;  // debug: 1 front stages, 2 k_pack_tma, 4 k_pack_slow
     // pinned host mirrors
@@ -705,14 +705,27 @@ extern "C" int b2_h2_process_batch(b2_ctx* c, const void* bytes, uint32_t nbytes
                                                             d_rs, d_msgs, per_run_msgs, c->d_unz, region);
     CU(cudaMemcpyAsync(rs, d_rs, sizeof(b2_h2_run_status) * (size_t)n_runs, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    // compact the per-run message arrays into one list (run order) and fetch what they reference
-    uint32_t total = 0;
+    // fetch only what was produced: every run owns `region` bytes (acks from its start, records/bodies from region/4) and
+    // per_run_msgs descriptors — three strided copies, then the descriptors are compacted into one list (run order)
+    uint32_t total = 0, max_msgs = 0, max_ctrl = 0, max_blob = 0;
     for (uint32_t r = 0; r < n_runs; r++) {
-        if (rs[r].n_msgs) CU(cudaMemcpyAsync(msgs + total, d_msgs + (size_t)r * per_run_msgs, sizeof(b2_h2_msg) * (size_t)rs[r].n_msgs, cudaMemcpyDeviceToHost, c->stream));
+        total += rs[r].n_msgs; if (rs[r].n_msgs > max_msgs) max_msgs = rs[r].n_msgs;
+        if (rs[r].ctrl_len > max_ctrl) max_ctrl = rs[r].ctrl_len;
+        if (rs[r].first_msg > max_blob) max_blob = rs[r].first_msg;             // (the kernel reports the blob bytes it used here)
+    }
+    if (total > msg_cap) { set_err("msg_cap too small"); return B2_E_CAPACITY; }
+    std::vector<b2_h2_msg> tmp((size_t)n_runs * (max_msgs ? max_msgs : 1));
+    if (max_msgs) CU(cudaMemcpy2DAsync(tmp.data(), sizeof(b2_h2_msg) * (size_t)max_msgs, d_msgs, sizeof(b2_h2_msg) * (size_t)per_run_msgs,
+                                       sizeof(b2_h2_msg) * (size_t)max_msgs, n_runs, cudaMemcpyDeviceToHost, c->stream));
+    if (max_ctrl) CU(cudaMemcpy2DAsync(out, region, c->d_unz, region, max_ctrl, n_runs, cudaMemcpyDeviceToHost, c->stream));
+    if (max_blob) CU(cudaMemcpy2DAsync((uint8_t*)out + region / 4, region, c->d_unz + region / 4, region, max_blob, n_runs, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    total = 0;
+    for (uint32_t r = 0; r < n_runs; r++) {
+        if (rs[r].n_msgs) memcpy(msgs + total, tmp.data() + (size_t)r * max_msgs, sizeof(b2_h2_msg) * (size_t)rs[r].n_msgs);
         rs[r].first_msg = total; total += rs[r].n_msgs;
     }
-    CU(cudaMemcpyAsync(out, c->d_unz, (size_t)region * n_runs, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    c->h2_last_in = nbytes; c->h2_last_out = (uint64_t)region * n_runs;
     *n_msgs = total;
     c->uploaded = false; c->executed = false;
     return B2_OK;
@@ -720,16 +733,19 @@ extern "C" int b2_h2_process_batch(b2_ctx* c, const void* bytes, uint32_t nbytes
 
 extern "C" int b2_h2_pack_responses(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_h2_response* resps, uint32_t n,
                                     void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens) {
-    if (!c || !bytes || !resps || !out || !out_offs || !out_lens) { set_err("null argument"); return B2_E_INVAL; }
+    if (!c || (!bytes && nbytes) || !resps || !out || !out_offs || !out_lens) { set_err("null argument"); return B2_E_INVAL; }
     static_assert(sizeof(b2_h2_response) == 48, "h2 response ABI layout");
-    if (nbytes > c->opt.max_batch_bytes || n > c->opt.max_msgs || out_cap > 2ull * c->opt.max_resp_bytes) { set_err("exceeds ctx capacity"); return B2_E_CAPACITY; }
+    if (nbytes > c->opt.max_resp_bytes || n > c->opt.max_msgs || out_cap > c->opt.max_resp_bytes) { set_err("exceeds ctx capacity"); return B2_E_CAPACITY; }
     if (n == 0) return B2_OK;
     std::vector<uint32_t> first;
     uint64_t total = 0;
     for (uint32_t i = 0; i < n; i++) {
         const b2_h2_response& r = resps[i];
-        if (r.conn >= B2_H2_MAX_CONNS || (uint64_t)r.body_off + r.body_len > nbytes || (uint64_t)r.content_type_off + r.content_type_len > nbytes ||
+        const uint64_t body_lim = (r.flags & B2_H2_RESP_BODY_IN_INPUT) ? c->h2_last_in : (r.flags & B2_H2_RESP_BODY_IN_OUT) ? c->h2_last_out : nbytes;
+        const uint64_t ct_lim = (r.flags & B2_H2_RESP_CT_IN_OUT) ? c->h2_last_out : nbytes;
+        if (r.conn >= B2_H2_MAX_CONNS || (uint64_t)r.body_off + r.body_len > body_lim || (uint64_t)r.content_type_off + r.content_type_len > ct_lim ||
             (uint64_t)r.grpc_message_off + r.grpc_message_len > nbytes || r.content_type_len > 256 || r.grpc_message_len > 512) { set_err("bad response descriptor"); return B2_E_INVAL; }
+        if ((r.flags & (B2_H2_RESP_BODY_IN_OUT | B2_H2_RESP_CT_IN_OUT)) && c->h2_last_out > c->opt.max_resp_bytes) { set_err("last h2 out buffer too large to stay resident"); return B2_E_CAPACITY; }
         if (i == 0 || r.conn != resps[i - 1].conn) first.push_back(i);
         const uint64_t data = (uint64_t)r.body_len + 5;
         const uint64_t need = data + 9 * (data / 16384 + 4) + 2ull * (r.content_type_len + r.grpc_message_len + 64) + 13 + 16;
@@ -745,13 +761,14 @@ extern "C" int b2_h2_pack_responses(b2_ctx* c, const void* bytes, uint32_t nbyte
     CU(cudaSetDevice(c->opt.device));
     b2_h2_response* d_resps = reinterpret_cast<b2_h2_response*>(c->d_msgs);       // 48 B <= 64 B per entry
     uint32_t* d_first = c->d_frame_off; uint32_t* d_offs = c->d_frame_run; uint32_t* d_lens = c->d_slot;
-    CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
+    uint8_t* d_aux = c->d_unz + c->opt.max_resp_bytes;            // second half of the scratch: the first half may hold the last h2 out buffer
+    if (nbytes) CU(cudaMemcpyAsync(d_aux, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_resps, resps, sizeof(b2_h2_response) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_first, first.data(), 4 * first.size(), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_offs, out_offs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    k_h2_pack<<<(n_groups + 31) / 32, 32, 0, c->stream>>>(c->d_bytes, d_resps, d_first, n_groups, c->d_h2, c->d_unz, d_offs, d_lens);
+    k_h2_pack<<<(n_groups + 31) / 32, 32, 0, c->stream>>>(d_aux, c->d_bytes, c->d_unz, d_resps, d_first, n_groups, c->d_h2, c->d_resp, d_offs, d_lens);
     CU(cudaMemcpyAsync(out_lens, d_lens, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(out, c->d_unz, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out, c->d_resp, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->uploaded = false; c->executed = false;
     return B2_OK;

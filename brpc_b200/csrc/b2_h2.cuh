@@ -236,9 +236,37 @@ __global__ void k_h2_scan(const uint8_t* bytes, const b2_run* runs, uint32_t n_r
 // that fail (or PING acks) leave the rest of their payload unread and the next "frame head" is parsed from there.
 constexpr uint32_t kH2Pending = B2_H2_MAX_PENDING, kH2StreamBytes = B2_H2_STREAM_BYTES, kH2HdrBytes = B2_H2_HEADER_BYTES;
 constexpr long long kH2MaxWindow = 2147483647ll;                 // H2Settings::MAX_WINDOW_SIZE
+// n bytes src -> dst by ONE thread: 16-byte words when the pointers agree mod 16, else 4-byte words assembled from
+// aligned loads (a connection is a serial state machine; its bulk copies are the only place worth widening)
+__device__ __forceinline__ void thread_copy(uint8_t* dst, const uint8_t* src, uint32_t n) {
+    uint32_t i = 0;
+    if ((((uintptr_t)dst ^ (uintptr_t)src) & 15u) == 0) {
+        while (i < n && ((uintptr_t)(dst + i) & 15u)) { dst[i] = src[i]; i++; }
+        for (; i + 64 <= n; i += 64) {
+            const uint4 a = *reinterpret_cast<const uint4*>(src + i), b = *reinterpret_cast<const uint4*>(src + i + 16);
+            const uint4 c = *reinterpret_cast<const uint4*>(src + i + 32), d = *reinterpret_cast<const uint4*>(src + i + 48);
+            *reinterpret_cast<uint4*>(dst + i) = a; *reinterpret_cast<uint4*>(dst + i + 16) = b;
+            *reinterpret_cast<uint4*>(dst + i + 32) = c; *reinterpret_cast<uint4*>(dst + i + 48) = d;
+        }
+        for (; i + 16 <= n; i += 16) *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+    } else {
+        while (i < n && ((uintptr_t)(dst + i) & 3u)) { dst[i] = src[i]; i++; }
+        const uint32_t sh = 8u * (uint32_t)((uintptr_t)(src + i) & 3u);
+        if (i + 8 <= n) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>((uintptr_t)(src + i) & ~(uintptr_t)3);
+            uint32_t w0 = q[0];
+            for (; i + 8 <= n; i += 4) {                         // (+8: the look-ahead word stays inside the source)
+                const uint32_t w1 = *++q;
+                *reinterpret_cast<uint32_t*>(dst + i) = sh ? __funnelshift_r(w0, w1, sh) : w0;
+                w0 = w1;
+            }
+        }
+    }
+    for (; i < n; i++) dst[i] = src[i];
+}
 struct H2Stream {
     int32_t id; uint32_t hdr_len, n_headers, body_len;
-    uint32_t stream_ended, pad;
+    uint32_t stream_ended, body_input_off;                       // body_input_off: the whole body is one DATA payload of THIS batch (0 = it lives in the slot)
     long long remote_window_left, deferred_wu;
 };
 struct H2Conn {
@@ -417,7 +445,8 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
                              uint8_t* out, uint32_t region) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_runs) return;
-    const uint8_t* in = bytes + runs[r].offset; const uint32_t n = runs[r].length;
+    const uint32_t run_off = runs[r].offset;
+    const uint8_t* in = bytes + run_off; const uint32_t n = runs[r].length;
     H2Conn& c = conns[(uint32_t)runs[r].socket_id];
     HpackState& hp = hps[(uint32_t)runs[r].socket_id];
     H2Out o; o.base = out + (size_t)r * region; o.ctrl_cap = region / 4; o.ctrl_len = 0; o.blob_off = region / 4; o.blob_end = region; o.overflow = false;
@@ -482,9 +511,15 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
                 break;
             }
             H2Stream& st = c.streams[k];
-            if (kH2HdrBytes + st.body_len + frag > kH2StreamBytes) { no_room = true; break; }
-            for (uint32_t i = 0; i < frag; i++) c.slots[k][kH2HdrBytes + st.body_len + i] = pl[used + i];
-            st.body_len += frag; used += frag + padl;
+            if (st.body_len == 0 && (flags & 0x1) && frag) {
+                // the usual unary call: one DATA frame that also ends the stream — the body stays where it is in the batch
+                st.body_input_off = run_off + pos + used; st.body_len = frag;
+            } else {
+                if (kH2HdrBytes + st.body_len + frag > kH2StreamBytes) { no_room = true; break; }
+                thread_copy(&c.slots[k][kH2HdrBytes + st.body_len], pl + used, frag);
+                st.body_len += frag;
+            }
+            used += frag + padl;
             const long long acc = (long long)frag + st.deferred_wu; st.deferred_wu += frag;
             const long long quota = (long long)(c.l_stream_window_size / (c.n_pending + 1));
             if (acc >= quota) {
@@ -510,7 +545,7 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
                 k = h2_find(c, -1);
                 if (k < 0) { no_room = true; break; }                // (device limit: B2_H2_MAX_PENDING)
                 H2Stream& st = c.streams[k];
-                st.id = sid; st.hdr_len = 0; st.n_headers = 0; st.body_len = 0; st.stream_ended = 0; st.deferred_wu = 0;
+                st.id = sid; st.hdr_len = 0; st.n_headers = 0; st.body_len = 0; st.stream_ended = 0; st.deferred_wu = 0; st.body_input_off = 0;
                 st.remote_window_left = (long long)c.r_stream_window_size;
                 c.n_pending++;
             } else {
@@ -614,19 +649,22 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
             // ---- the completed request, as ProcessHttpRequest first sees it
             const H2Stream& st = c.streams[res.slot];
             const uint8_t* slot = c.slots[res.slot];
-            const uint32_t need = ((st.hdr_len + 15u) & ~15u) + ((st.body_len + 15u) & ~15u);
+            const bool in_input = st.body_input_off != 0;
+            const uint32_t need = ((st.hdr_len + 15u) & ~15u) + (in_input ? 0u : ((st.body_len + 15u) & ~15u));
             if (n_msgs >= msg_cap_per_run || o.blob_off + need > o.blob_end) { no_room = true; continue; }
             b2_h2_msg m;
             m.run_idx = r; m.stream_id = (uint32_t)res.err_stream; m.reserved = 0;
             const uint32_t ho = o.blob_off, bo = ho + ((st.hdr_len + 15u) & ~15u);
-            for (uint32_t i = 0; i < st.hdr_len; i++) o.base[ho + i] = slot[i];
-            for (uint32_t i = 0; i < st.body_len; i++) o.base[bo + i] = slot[kH2HdrBytes + i];
+            thread_copy(o.base + ho, slot, st.hdr_len);
+            if (!in_input) thread_copy(o.base + bo, slot + kH2HdrBytes, st.body_len);
             o.blob_off += need;
             const uint32_t gbase = r * region;
             m.headers_off = gbase + ho; m.headers_len = st.hdr_len; m.n_headers = st.n_headers;
-            m.body_off = gbase + bo; m.body_len = st.body_len;
+            m.body_off = in_input ? st.body_input_off : gbase + bo; m.body_len = st.body_len;
             m.http_method = B2_H2_NO_METHOD; m.content_type = 0; m.flags = 0; m.method_idx = -1;
             m.msg_off = 0; m.msg_len = 0; m.path_off = 0; m.path_len = 0;
+            if (in_input) m.flags |= B2_H2_FLAG_BODY_IN_INPUT;
+            const uint8_t* body_p = in_input ? bytes + st.body_input_off : slot + kH2HdrBytes;
             bool is_grpc = false;
             const uint8_t* path = nullptr; uint32_t path_len = 0;
             for (uint32_t q = 0; q < st.hdr_len;) {
@@ -645,7 +683,7 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
                 // RemoveGrpcPrefix (policy/http_rpc_protocol.cpp:264-277)
                 if (st.body_len == 0) { m.flags |= B2_H2_FLAG_GRPC_PREFIX_OK; m.msg_off = m.body_off; }
                 else if (st.body_len >= 5) {
-                    const uint8_t* b = slot + kH2HdrBytes;
+                    const uint8_t* b = body_p;
                     if (b[0]) m.flags |= B2_H2_FLAG_GRPC_COMPRESSED;
                     if ((unsigned long long)load_be32(b + 1) + 5ull == st.body_len) { m.flags |= B2_H2_FLAG_GRPC_PREFIX_OK; m.msg_off = m.body_off + 5; m.msg_len = st.body_len - 5; }
                 }
@@ -664,7 +702,7 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
             mout[n_msgs++] = m;
         }
     }
-    b2_h2_run_status st; st.consumed = last_ok; st.parse_error = perr; st.n_msgs = n_msgs; st.first_msg = r * msg_cap_per_run;
+    b2_h2_run_status st; st.consumed = last_ok; st.parse_error = perr; st.n_msgs = n_msgs; st.first_msg = o.blob_off - region / 4;      // blob bytes used (the host turns this field into the list index)
     st.ctrl_off = r * region; st.ctrl_len = o.ctrl_len; st.remote_max_frame_size = c.r_max_frame_size; st.remote_stream_window_size = c.r_stream_window_size;
     rs[r] = st;
 }
@@ -727,7 +765,7 @@ __device__ __forceinline__ uint32_t put_dec_i32_h2(uint8_t* p, int32_t v) {     
     return o;
 }
 constexpr uint32_t kH2FragCap = 1024;      // encoded header block of one response (":status", "content-type", trailers)
-__global__ void k_h2_pack(const uint8_t* bytes, const b2_h2_response* resps, const uint32_t* group_first, uint32_t n_groups, H2Conn* conns,
+__global__ void k_h2_pack(const uint8_t* bytes, const uint8_t* last_input, const uint8_t* last_out, const b2_h2_response* resps, const uint32_t* group_first, uint32_t n_groups, H2Conn* conns,
                           uint8_t* out, const uint32_t* out_offs, uint32_t* out_lens) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
@@ -747,7 +785,7 @@ __global__ void k_h2_pack(const uint8_t* bytes, const b2_h2_response* resps, con
         uint8_t num[16];
         uint8_t* f = frag;
         { const uint32_t nn = put_dec_i32_h2(num, R.status_code); f = hp_encode(c.enc, f, (const uint8_t*)":status", 7, num, nn, never, tmp); }
-        if (R.content_type_len) f = hp_encode(c.enc, f, (const uint8_t*)"content-type", 12, bytes + R.content_type_off, R.content_type_len, never, tmp);
+        if (R.content_type_len) f = hp_encode(c.enc, f, (const uint8_t*)"content-type", 12, ((R.flags & B2_H2_RESP_CT_IN_OUT) ? last_out : bytes) + R.content_type_off, R.content_type_len, never, tmp);
         uint8_t* t = trailer;
         if (grpc) {
             const uint32_t nn = put_dec_i32_h2(num, R.grpc_status);
@@ -762,19 +800,15 @@ __global__ void k_h2_pack(const uint8_t* bytes, const b2_h2_response* resps, con
             h2_put_head(o, mfs, 1, hflags, R.stream_id); o += 9; for (uint32_t k = 0; k < mfs; k++) *o++ = frag[k];
             for (uint32_t at = mfs; at < fl;) { const uint32_t nn = min(fl - at, mfs); h2_put_head(o, nn, 9, at + nn == fl ? 0x4 : 0, R.stream_id); o += 9; for (uint32_t k = 0; k < nn; k++) *o++ = frag[at + k]; at += nn; }
         }
-        const uint8_t* body = bytes + R.body_off;
+        const uint8_t* body = ((R.flags & B2_H2_RESP_BODY_IN_INPUT) ? last_input : (R.flags & B2_H2_RESP_BODY_IN_OUT) ? last_out : bytes) + R.body_off;
         for (uint32_t at = 0; at < data_size;) {
             const uint32_t nn = min(data_size - at, mfs);
             const uint8_t dflags = (at + nn == data_size && tl == 0) ? 0x1 : 0;
             h2_put_head(o, nn, 0, dflags, R.stream_id); o += 9;
-            for (uint32_t k = 0; k < nn; k++) {
-                const uint32_t q = at + k;
-                uint8_t b;
-                if (grpc) { if (q == 0) b = 0; else if (q < 5) b = (uint8_t)(R.body_len >> (8 * (4 - q))); else b = body[q - 5]; }   // AddGrpcPrefix: flag 0 + BE32 length
-                else b = body[q];
-                *o++ = b;
-            }
-            at += nn;
+            uint32_t k = 0;
+            if (grpc) for (; k < nn && at + k < 5; k++) { const uint32_t q = at + k; o[k] = q == 0 ? 0 : (uint8_t)(R.body_len >> (8 * (4 - q))); }   // AddGrpcPrefix: flag 0 + BE32 length
+            thread_copy(o + k, body + (at + k - (grpc ? 5u : 0u)), nn - k);
+            o += nn; at += nn;
         }
         if (tl) { h2_put_head(o, tl, 1, 0x5, R.stream_id); o += 9; for (uint32_t k = 0; k < tl; k++) *o++ = trailer[k]; }
         if (c.deferred_window_update > 0) {                       // ReleaseDeferredWindowUpdate

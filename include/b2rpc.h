@@ -341,6 +341,7 @@ int  b2_hpack_decode_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes, cons
 #define B2_H2_FLAG_GRPC_PREFIX_OK  2u   /* RemoveGrpcPrefix succeeded: msg_off/msg_len are valid */
 #define B2_H2_FLAG_GRPC_COMPRESSED 4u   /* compressed flag of the 5-byte prefix */
 #define B2_H2_FLAG_HAS_PATH        8u
+#define B2_H2_FLAG_BODY_IN_INPUT  16u   /* body_off/msg_off index the INPUT bytes (a single DATA frame carried the whole body): zero copy */
 #define B2_H2_NO_METHOD 255u            /* no :method header (HttpHeader defaults to GET) */
 typedef struct b2_h2_run_status {
     uint32_t consumed, parse_error, n_msgs, first_msg;
@@ -373,8 +374,12 @@ int  b2_h2_process_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const 
  * (+CONTINUATION), DATA frames split at the peer's max_frame_size, trailers, and the deferred connection WINDOW_UPDATE.
  * Responses of one connection must be adjacent and in write order; the state is the connection's (b2_h2_process_batch).
  * Response i's bytes land at out + out_offs[i] (filled by the call), out_lens[i] long.  User-defined response headers
- * are not covered. */
+ * are not covered.  bytes may be NULL (nbytes 0) when every field uses a zero-copy source. */
 #define B2_H2_RESP_GRPC 1u
+/* zero-copy sources: the buffers of the LAST b2_h2_process_batch on this context are still on the device */
+#define B2_H2_RESP_BODY_IN_INPUT 2u   /* body_off indexes that call's input bytes (e.g. an echoed B2_H2_FLAG_BODY_IN_INPUT message) */
+#define B2_H2_RESP_BODY_IN_OUT   4u   /* body_off indexes that call's out buffer */
+#define B2_H2_RESP_CT_IN_OUT     8u   /* content_type_off indexes that call's out buffer (the request's own content-type value) */
 typedef struct b2_h2_response {
     uint32_t conn, stream_id;
     int32_t  status_code;                            /* :status */

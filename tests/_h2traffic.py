@@ -38,6 +38,7 @@ def hp_str(b):
 class HpackEncoder:
     def __init__(self, rng, max_size=4096):
         self.rng = rng; self.max_size = max_size; self.dyn = []      # newest first
+        self.fixed_mode = None                                       # e.g. "auto": indexed when possible, else incremental
 
     def _size(self):
         return sum(len(n) + len(v) + 32 for n, v in self.dyn)
@@ -59,7 +60,7 @@ class HpackEncoder:
 
     def field(self, n, v, mode=None):
         full, name = self._find(n, v)
-        mode = mode or self.rng.choice(["auto", "auto", "auto", "incr", "noidx", "never"])
+        mode = mode or self.fixed_mode or self.rng.choice(["auto", "auto", "auto", "incr", "noidx", "never"])
         if full and mode == "auto":
             return hp_int(full, 7, 0x80)
         if mode in ("auto", "incr"):

@@ -13,10 +13,12 @@ pytestmark = pytest.mark.gpu
 SEED = 20260921
 
 
-def _msg_tuple(m, blob):
+def _msg_tuple(m, blob, data=None):
+    """data: the batch input — a device message whose body was one DATA frame points into it (B2_H2_FLAG_BODY_IN_INPUT)."""
+    src = data if (int(m["flags"]) & 16) else blob
     return (int(m["stream_id"]), int(m["n_headers"]), bytes(blob[m["headers_off"]:m["headers_off"] + m["headers_len"]]),
-            bytes(blob[m["body_off"]:m["body_off"] + m["body_len"]]), int(m["http_method"]), int(m["content_type"]), int(m["flags"]),
-            int(m["method_idx"]), bytes(blob[m["msg_off"]:m["msg_off"] + m["msg_len"]]), bytes(blob[m["path_off"]:m["path_off"] + m["path_len"]]))
+            bytes(src[m["body_off"]:m["body_off"] + m["body_len"]]), int(m["http_method"]), int(m["content_type"]), int(m["flags"]) & ~16,
+            int(m["method_idx"]), bytes(src[m["msg_off"]:m["msg_off"] + m["msg_len"]]), bytes(blob[m["path_off"]:m["path_off"] + m["path_len"]]))
 
 
 def _run(n_conns, n_calls, violations, seed, step_choices):
@@ -47,7 +49,7 @@ def _run(n_conns, n_calls, violations, seed, step_choices):
             dm = msgs[st["first_msg"]:st["first_msg"] + st["n_msgs"]]
             for a, b in zip(dm, omsgs):
                 assert int(a["run_idx"]) == j
-                assert _msg_tuple(a, out) == _msg_tuple(b, oblob), (i, fed[i], int(b["stream_id"]))
+                assert _msg_tuple(a, out, data) == _msg_tuple(b, oblob), (i, fed[i], int(b["stream_id"]))
             total_msgs += len(omsgs); total_ctrl += len(octrl)
             buf[i] = buf[i][cons:]
             if e != 2:
@@ -111,16 +113,22 @@ def test_grpc_echo_responses_packed_on_the_device():
             assert int(st["n_msgs"]) == len(omsgs) and bytes(out[st["ctrl_off"]:st["ctrl_off"] + st["ctrl_len"]]) == octrl
             for m in msgs[st["first_msg"]:st["first_msg"] + st["n_msgs"]]:
                 assert m["flags"] & 2
-                body = bytes(out[m["msg_off"]:m["msg_off"] + m["msg_len"]])          # echo: the reply message is the request message
-                if rng.random() < 0.1: body = body * 6                               # some replies larger than a frame / than the window
-                h = O.parse_header_records(bytes(out[m["headers_off"]:m["headers_off"] + m["headers_len"]]))
-                ct = dict(h)[b"content-type"]
+                src = data if (m["flags"] & 16) else out
+                body = bytes(src[m["msg_off"]:m["msg_off"] + m["msg_len"]])          # echo: the reply message is the request message
+                hb = bytes(out[m["headers_off"]:m["headers_off"] + m["headers_len"]])
+                ct = dict(O.parse_header_records(hb))[b"content-type"]
+                ct_off = int(m["headers_off"]) + hb.index(ct)                        # the request's own content-type value, inside out
                 fail = rng.random() < 0.15
                 gm = b"Fail%20to%20find%20method%20" + str(rnd * 7 + i).encode() if fail else b""
-                if fail: body = b""
                 base = sum(len(x) for x in blob_parts)
-                blob_parts += [ct, body, gm]
-                resps.append((i, int(m["stream_id"]), 200, 1, base, len(ct), base + len(ct), len(body), 12 if fail else 0, base + len(ct) + len(body), len(gm), 0))
+                if fail:
+                    body = b""; blob_parts += [gm]
+                    resps.append((i, int(m["stream_id"]), 200, 1 | 8, ct_off, len(ct), 0, 0, 12, base, len(gm), 0))
+                elif rng.random() < 0.15:                                            # a reply built on the host: larger than a frame / than the window
+                    body = body * 6; blob_parts += [body]
+                    resps.append((i, int(m["stream_id"]), 200, 1 | 8, ct_off, len(ct), base, len(body), 0, 0, 0, 0))
+                else:                                                                # zero copy: body still on the device (input or out buffer)
+                    resps.append((i, int(m["stream_id"]), 200, 1 | 8 | (2 if (m["flags"] & 16) else 4), ct_off, len(ct), int(m["msg_off"]), len(body), 0, 0, 0, 0))
                 expect.append(orc[i].pack_response(int(m["stream_id"]), body, 200, ct, True, 12 if fail else 0, gm))
         if not resps:
             continue
