@@ -89,6 +89,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel, args):
+    """dram bytes read + written per launch of `kernel` from the committed `ncu --set full` capture of this same workload
+    (profiles/r1_ncu_summary.json), or None when the capture does not cover the configuration being run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) as f:
+            cap = json.load(f)
+        w = cap["workload"]
+        if (w["payload_bytes"], w["run_mib"], w["connections"]) != (args.payload, args.run_mib, N_SOCKETS) or args.checksum or args.payload_kind:
+            return None
+        k = cap["kernels"].get(kernel) or cap["kernels"].get(kernel + "_tma")
+        return None if k is None else (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6
+    except Exception:
+        return None
+
+
 def build_batch(run_mib, rank, pinned=True, payload=PAYLOAD, checksum=0, kind=0):
     from brpc_b200 import press
     from brpc_b200.abi import PinnedBuffer
@@ -554,32 +569,32 @@ def main():
     # ---- latency: one small batch at a time through the same ABI call (p99 of the metric) --------
     # 64 connections x 1 complete 1 KB request each = what 64 synchronous client threads
     # (multi_threaded_echo_c++ -thread_num=64) have in flight; host buffers, blocking call.
-    from brpc_b200 import press as _press
-    from brpc_b200.abi import PinnedBuffer as _Pinned
-    lat_ctx = brpc_b200.Context(device=dev, max_batch_bytes=1 << 20, max_msgs=4096, max_runs=N_SOCKETS, tile_bytes=args.tile)
-    _sp = _press.spec(payload_bytes=PAYLOAD)
-    if args.no_latency:
-        pass
-    _f = _press.frame(_sp, 12345)
-    _stride = (len(_f) + 15) // 16 * 16
-    lbuf = _Pinned(N_SOCKETS * _stride)
-    lruns = np.zeros(N_SOCKETS, dtype=brpc_b200.RUN_DT)
-    for s_ in range(N_SOCKETS):
-        fr = _press.frame(_sp, (s_ << 32) + 7)
-        lbuf.array[s_ * _stride:s_ * _stride + len(fr)] = np.frombuffer(fr, np.uint8)
-        lruns[s_] = (s_, s_ * _stride, len(fr), 1, 0)
-    for _ in range(50):
-        lat_ctx.process_batch_ptr(lbuf.ptr, N_SOCKETS * _stride, lruns)
-    lat = []
-    for _ in range(2000):
-        t1 = time.perf_counter()
-        lrs, lm, lresp, _i = lat_ctx.process_batch_ptr(lbuf.ptr, N_SOCKETS * _stride, lruns)
-        lat.append((time.perf_counter() - t1) * 1e6)
-    assert len(lm) == N_SOCKETS and np.all(lm["status"] == 0)
-    lat.sort()
-    latency = {"batch": "%d connections x 1 request (1 KB), blocking b2_process_batch, host buffers" % N_SOCKETS,
-               "p50_us": lat[len(lat) // 2], "p99_us": lat[int(len(lat) * 0.99)], "mean_us": sum(lat) / len(lat),
-               "iters": len(lat), "kernel_launches_per_batch": int(_i["n_launches"])}
+    latency = None
+    if not args.no_latency:
+        from brpc_b200 import press as _press
+        from brpc_b200.abi import PinnedBuffer as _Pinned
+        lat_ctx = brpc_b200.Context(device=dev, max_batch_bytes=1 << 20, max_msgs=4096, max_runs=N_SOCKETS, tile_bytes=args.tile)
+        _sp = _press.spec(payload_bytes=PAYLOAD)
+        _f = _press.frame(_sp, 12345)
+        _stride = (len(_f) + 15) // 16 * 16
+        lbuf = _Pinned(N_SOCKETS * _stride)
+        lruns = np.zeros(N_SOCKETS, dtype=brpc_b200.RUN_DT)
+        for s_ in range(N_SOCKETS):
+            fr = _press.frame(_sp, (s_ << 32) + 7)
+            lbuf.array[s_ * _stride:s_ * _stride + len(fr)] = np.frombuffer(fr, np.uint8)
+            lruns[s_] = (s_, s_ * _stride, len(fr), 1, 0)
+        for _ in range(50):
+            lat_ctx.process_batch_ptr(lbuf.ptr, N_SOCKETS * _stride, lruns)
+        lat = []
+        for _ in range(2000):
+            t1 = time.perf_counter()
+            lrs, lm, lresp, _i = lat_ctx.process_batch_ptr(lbuf.ptr, N_SOCKETS * _stride, lruns)
+            lat.append((time.perf_counter() - t1) * 1e6)
+        assert len(lm) == N_SOCKETS and np.all(lm["status"] == 0)
+        lat.sort()
+        latency = {"batch": "%d connections x 1 request (1 KB), blocking b2_process_batch, host buffers" % N_SOCKETS,
+                   "p50_us": lat[len(lat) // 2], "p99_us": lat[int(len(lat) * 0.99)], "mean_us": sum(lat) / len(lat),
+                   "iters": len(lat), "kernel_launches_per_batch": int(_i["n_launches"])}
 
     # ---- reduce over ranks: max time, summed messages; NCCL all-reduce of the bvar-like counters --
     t_dev = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
@@ -615,7 +630,7 @@ def main():
                         "ms_per_step": e2e_ms_max, "note": "b2_batch_submit/collect (the two halves of b2_process_batch), pinned host buffers, 3 batches in flight"},
                 "gpu_launches": int(n_launch),
                 "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / hbm_peak, "traffic": ncu_traffic("k_" + dom, args), "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": dom_alg, "kernel_ms": stages[dom]},
                 "roofline_pipeline": {"achieved": pipe_alg / (step_ms_rank0 * 1e-3) / 1e9,
                                       "frac": pipe_alg / (step_ms_rank0 * 1e-3) / 1e9 / hbm_peak,
