@@ -89,6 +89,23 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def pin_to_gpu_numa(gpu_index):
+    """Run this rank (and allocate its pinned buffers) on the CPUs next to its GPU: with 8 ranks the host<->device copies of
+    the e2e leg otherwise cross the socket interconnect (one pinned pool per NUMA node)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1 and 64 * w + b < n_cpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def ncu_traffic(kernel, args):
     """dram bytes read + written per launch of `kernel` from the committed `ncu --set full` capture of this same workload
     (profiles/r1_ncu_summary.json), or None when the capture does not cover the configuration being run."""
@@ -452,7 +469,8 @@ def main():
     workload = ("multi_threaded_echo_c++ baidu_std %d B payload: %d connections/GPU x %d MiB pending, "
                 "runs cut mid-frame; batch %d MiB > L2 (no flush needed)" % (args.payload, N_SOCKETS, args.run_mib, N_SOCKETS * args.run_mib))
     config = {"workload": workload, "payload_bytes": args.payload, "request_checksum": args.checksum, "connections_per_gpu": N_SOCKETS,
-              "run_mib": args.run_mib, "l2": "inputs larger than L2", "pipeline_depth": args.pipeline, "sharding": "socket_id %% %d" % max(1, world)}
+              "run_mib": args.run_mib, "l2": "inputs larger than L2", "pipeline_depth": args.pipeline, "sharding": "socket_id %% %d" % max(1, world),
+              "host": "each rank pinned to its GPU's NUMA node" if world > 1 else "single rank"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -483,6 +501,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank if use_dist else 0
     torch.cuda.set_device(dev)
+    numa_cpus = pin_to_gpu_numa(dev) if use_dist else 0
 
     buf, data, runs, n_full, nbytes = build_batch(args.run_mib, rank, payload=args.payload, checksum=args.checksum, kind=args.payload_kind)
     ctx = brpc_b200.Context(device=dev, max_batch_bytes=nbytes + (1 << 20), max_msgs=n_full + 4096,
