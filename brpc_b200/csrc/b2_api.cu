@@ -35,7 +35,7 @@ struct b2_ctx {
     std::vector<DevMethod> methods;
     // device
     uint8_t* d_bytes = nullptr; b2_run* d_runs = nullptr; uint32_t* d_run_tile_base = nullptr;
-    TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; uint32_t* d_tile_scratch = nullptr; b2_run_status* d_run_status = nullptr;
+    TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; uint32_t* d_tile_scratch = nullptr; uint32_t* d_tile_spec = nullptr; b2_run_status* d_run_status = nullptr;
     uint32_t* d_frame_off = nullptr; uint32_t* d_frame_run = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr; PackJob* d_jobs = nullptr; uint32_t* d_slow_idx = nullptr; uint8_t* d_heads = nullptr;
     uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr; uint8_t* d_unz = nullptr; uint16_t* d_snappy_tab = nullptr; HpackState* d_hpack = nullptr; H2Conn* d_h2 = nullptr; uint64_t h2_last_in = 0, h2_last_out = 0;   // sizes of the last h2 batch still on the device
     uint32_t* d_crc_adv = nullptr; unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
@@ -82,7 +82,7 @@ extern "C" void b2_block_free(void* p) { if (p) cudaFreeHost(p); }
 extern "C" void b2_ctx_destroy(b2_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->opt.device);
-    cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch);
+    cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch); cudaFree(c->d_tile_spec);
     cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_frame_run); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_slow_idx); cudaFree(c->d_heads); cudaFree(c->d_slot);
     cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_hpack); cudaFree(c->d_h2); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
     cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
@@ -129,6 +129,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     ALLOC(c->d_tiles, sizeof(TileRec) * (size_t)c->max_tiles);
     ALLOC(c->d_tile_base, 4 * (size_t)c->max_tiles);
     ALLOC(c->d_tile_scratch, 12 * (size_t)c->max_tiles);
+    ALLOC(c->d_tile_spec, 4 * (size_t)kSpecK * c->max_tiles);
     ALLOC(c->d_run_status, sizeof(b2_run_status) * (size_t)o->max_runs);
     ALLOC(c->d_frame_off, 4 * (size_t)o->max_msgs);
     ALLOC(c->d_frame_run, 4 * (size_t)o->max_msgs);
@@ -225,7 +226,7 @@ extern "C" int b2_register_method(b2_ctx* c, const b2_method* m) {
 static BatchPtrs make_ptrs(b2_ctx* c) {
     BatchPtrs B;
     B.bytes = c->d_bytes; B.runs = c->d_runs; B.run_tile_base = c->d_run_tile_base; B.tiles = c->d_tiles;
-    B.tile_base = c->d_tile_base; B.tile_scratch = c->d_tile_scratch; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.frame_run = c->d_frame_run; B.msgs = c->d_msgs;
+    B.tile_base = c->d_tile_base; B.tile_scratch = c->d_tile_scratch; B.tile_spec = c->d_tile_spec; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.frame_run = c->d_frame_run; B.msgs = c->d_msgs;
     B.aux = c->d_aux; B.jobs = c->d_jobs; B.slow_idx = c->d_slow_idx; B.heads = c->d_heads; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.unz = c->d_unz; B.snappy_tab = c->d_snappy_tab; B.counters = c->d_counters;
     B.totals = c->d_totals; B.methods = c->d_methods; B.crc_adv = c->d_crc_adv;
     B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes;
@@ -318,7 +319,7 @@ static int launch_pipeline(b2_ctx* c) {
         if (smem > 200 * 1024) smem = 0;
         k_resolve<<<c->n_runs, 256, smem, s>>>(B, C); launches++; mark("resolve");
     }
-    if (c->n_tiles) { k_frame_table<<<(c->n_tiles + 127) / 128, 128, 0, s>>>(B, C); launches++; mark("frame_table"); }
+    if (c->n_tiles) { k_frame_table<<<(c->n_tiles * kSpecK + 255) / 256, 256, 0, s>>>(B, C); launches++; mark("frame_table"); }
     // message-count dependent kernels are persistent: fixed grids (multiples of the SM count)
     // stride over the device-side message count, so no host round trip sizes a launch
     k_decode<<<sms * B2_DECODE_MIN_BLOCKS, kDecodeWarps * 32, 0, s>>>(B, C); launches++; mark("decode");

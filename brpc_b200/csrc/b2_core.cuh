@@ -412,7 +412,13 @@ B2_HD bool decode_echo_request(const uint8_t* p, uint32_t n, Span& msg) {
 
 // ---------------------------------------------------------------------------
 // encoders
-B2_HD uint32_t varint_len(uint64_t v) { uint32_t n = 1; while (v >= 0x80) { v >>= 7; n++; } return n; }
+B2_HD uint32_t varint_len(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)(64 - __clzll((long long)(v | 1)) + 6) / 7u;         // ceil(significant bits / 7)
+#else
+    uint32_t n = 1; while (v >= 0x80) { v >>= 7; n++; } return n;
+#endif
+}
 B2_HD uint8_t* put_varint(uint8_t* p, uint64_t v) { while (v >= 0x80) { *p++ = (uint8_t)(v | 0x80); v >>= 7; } *p++ = (uint8_t)v; return p; }
 B2_HD uint8_t* put_be32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; return p + 4; }
 B2_HD uint32_t dec_len(uint32_t v) { uint32_t n = 1; while (v >= 10) { v /= 10; n++; } return n; }

@@ -14,7 +14,7 @@
 //   k_resolve      CTA/run     verifies the speculation chain from tile 0 (exact),
 //                              falls back to a scalar walk where it fails, run status
 //   (run prefix)   first_msg of every run: the last CTA of k_resolve
-//   k_frame_table  thread/tile frame offsets of live tiles
+//   k_frame_table  16 thr/tile copies the frame offsets k_tile_walk kept (re-walks only what k_resolve changed)
 //   k_decode       thread/msg  RpcMeta / StreamFrameMeta / EchoRequest decode -> desc, aux, slot
 //   k_scan_*       exclusive scan of the slot sizes
 //   k_pack         warp/msg    response header+meta, payload copy (+CRC32C)
@@ -87,6 +87,7 @@ struct BatchPtrs {
     TileRec* tiles;
     uint32_t* tile_base;             // [n_tiles] run-relative index of the tile's first message
     uint32_t* tile_scratch;          // [3 * n_tiles] k_resolve spill when a run's tiles exceed shared memory
+    uint32_t* tile_spec;             // [kSpecK * n_tiles] frame offsets found by the speculative walk (first kSpecK of a tile)
     b2_run_status* run_status;
     uint32_t* frame_off;             // [max_msgs] frame offsets (batch-relative), bit 31 = protocol - 1
     uint32_t* frame_run;             // [max_msgs] run index of every message
@@ -130,6 +131,14 @@ B2_HD void walk_tile(const uint8_t* run, uint32_t len, uint32_t entry, int pf_in
     t.entry = entry; t.exit = pos; t.count = count; t.kind = kind; t.last_proto = (int8_t)last;
 }
 struct NoEmit { B2_HD void operator()(uint32_t, const Step&) const {} };
+constexpr uint32_t kSpecK = 16;            // speculative frame offsets kept per tile; tiles with more frames are re-walked by k_frame_table
+constexpr uint8_t kKindRewalked = 0x80;    // k_resolve re-walked the tile: its speculative offsets are void
+struct EmitSpec {
+    uint32_t* out; uint32_t run_off;
+    __device__ __forceinline__ void operator()(uint32_t i, const Step& s) const {
+        if (i < kSpecK) out[i] = (run_off + s.frame_pos) | ((uint32_t)(s.index - 1) << 31);
+    }
+};
 
 #if defined(__CUDACC__)
 
@@ -180,9 +189,16 @@ __global__ void __launch_bounds__(256) k_tile_search(BatchPtrs B, DevConfig C) {
                 const uint32_t w[5] = { v[u].x, v[u].y, v[u].z, v[u].w, nx[u] };
                 uint32_t mask = 0;
                 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const uint32_t word = __funnelshift_r(w[j >> 2], w[(j >> 2) + 1], (j & 3) * 8);
-                    if (is_magic(word) && p0 + j + 4 <= len && p0 + j < t1) mask |= 1u << j;
+                for (int k4 = 0; k4 < 4; k4++) {
+                    // byte prefilter: only positions holding 'P' or 'S' (first byte of "PRPC" / "STRM") are looked at
+                    uint32_t e = __vcmpeq4(w[k4], 0x50505050u) | __vcmpeq4(w[k4], 0x53535353u);
+                    while (e) {
+                        const int b = (__ffs(e) - 1) >> 3;
+                        e &= ~(0xffu << (8 * b));
+                        const int j = 4 * k4 + b;
+                        const uint32_t word = __funnelshift_r(w[k4], w[k4 + 1], b * 8);
+                        if (is_magic(word) && p0 + j + 4 <= len && p0 + j < t1) mask |= 1u << j;
+                    }
                 }
                 // candidates in position order: lanes ascending, bits ascending
                 uint32_t any = __ballot_sync(0xffffffffu, mask != 0);
@@ -215,8 +231,11 @@ __global__ void __launch_bounds__(128) k_tile_walk(BatchPtrs B, DevConfig C) {
     const b2_run run = B.runs[r];
     TileRec rec;
     rec.entry = B.tiles[t].entry; rec.exit = 0; rec.count = 0; rec.kind = kStop; rec.last_proto = 0; rec.live = 0; rec.pf_in = -1;
-    if (rec.entry != kNone)
-        walk_tile<true>(B.bytes + run.offset, run.length, rec.entry, -1, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, rec, NoEmit());
+    if (rec.entry != kNone) {
+        // the frame offsets met on the way are kept: if k_resolve accepts the tile as is, k_frame_table only has to copy them
+        EmitSpec e; e.out = B.tile_spec + (size_t)t * kSpecK; e.run_off = run.offset;
+        walk_tile<true>(B.bytes + run.offset, run.length, rec.entry, -1, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, rec, e);
+    }
     B.tiles[t] = rec;
 }
 
@@ -312,7 +331,7 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C) {
                 for (uint32_t j = k; j-- > 0;) if (live[j] && (cp[j] >> 2)) { pf = (int)(cp[j] & 3u); break; }
                 TileRec t; t.live = 0; t.pf_in = 0;
                 walk_tile<false>(base, len, pos, pf, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, t, NoEmit());
-                tiles[k].entry = t.entry; tiles[k].exit = t.exit; tiles[k].count = t.count; tiles[k].kind = t.kind; tiles[k].last_proto = t.last_proto;
+                tiles[k].entry = t.entry; tiles[k].exit = t.exit; tiles[k].count = t.count; tiles[k].kind = t.kind | kKindRewalked; tiles[k].last_proto = t.last_proto;
                 cp[k] = (t.count << 2) | ((uint32_t)t.last_proto & 3u);
                 v = make_link(t, tiles, nt, C.tile_shift);
                 link[k] = v;
@@ -386,23 +405,32 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C) {
     if (s_ticket == gridDim.x - 1) { __threadfence(); run_prefix_body(B, s_pw, &s_pc); }
 }
 
-// --- k_frame_table: one thread per tile --------------------------------------
+// --- k_frame_table ------------------------------------------------------------
 struct EmitFrame {
     uint32_t* out; uint32_t* out_run; uint32_t run_off; uint32_t run_idx; uint32_t cap_left;
     __device__ __forceinline__ void operator()(uint32_t i, const Step& s) const {
         if (i < cap_left) { out[i] = (run_off + s.frame_pos) | ((uint32_t)(s.index - 1) << 31); out_run[i] = run_idx; }
     }
 };
-__global__ void __launch_bounds__(128) k_frame_table(BatchPtrs B, DevConfig C) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+// kSpecK threads per tile: a live tile that k_resolve accepted as speculated hands over the offsets k_tile_walk
+// kept (plain copy, no header loads); a tile that was re-walked or holds more than kSpecK frames is walked again by
+// its first thread.
+__global__ void __launch_bounds__(256) k_frame_table(BatchPtrs B, DevConfig C) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = g / kSpecK, j = g % kSpecK;
     if (t >= B.n_tiles) return;
     const TileRec rec = B.tiles[t];
     if (!rec.live || rec.count == 0) return;
     if (B.totals[2] & 1u) return;
     const uint32_t r = __ldg(B.tile_run + t);
+    const uint32_t first = B.run_status[r].first_msg + B.tile_base[t];
+    if (!(rec.kind & kKindRewalked) && rec.count <= kSpecK) {
+        if (j < rec.count && first + j < B.max_msgs) { B.frame_off[first + j] = B.tile_spec[(size_t)t * kSpecK + j]; B.frame_run[first + j] = r; }
+        return;
+    }
+    if (j != 0) return;
     const uint32_t k = t - __ldg(B.run_tile_base + r);
     const b2_run run = B.runs[r];
-    const uint32_t first = B.run_status[r].first_msg + B.tile_base[t];
     TileRec tmp;
     EmitFrame e; e.out = B.frame_off + first; e.out_run = B.frame_run + first; e.run_off = run.offset; e.run_idx = r; e.cap_left = B.max_msgs - first;
     walk_tile<false>(B.bytes + run.offset, run.length, rec.entry, rec.pf_in, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, tmp, e);
@@ -430,7 +458,11 @@ __device__ __forceinline__ int find_method(const DevMethod* ms, uint32_t n, cons
                                            const uint8_t* mth, uint32_t mth_len, bool& no_service) {
     no_service = false;
     bool has_dot = false;
-    for (uint32_t i = 0; i < svc_len; i++) if (svc[i] == '.') { has_dot = true; break; }
+    for (uint32_t i = 0; i < svc_len && !has_dot; i += 4) {               // four bytes per step: any '.' among the valid ones
+        uint32_t e = __vcmpeq4(ld32_any(svc + i), 0x2e2e2e2eu);
+        if (svc_len - i < 4) e &= (1u << (8 * (svc_len - i))) - 1u;
+        has_dot = e != 0;
+    }
     const char* full = nullptr; uint32_t full_len = 0;
     if (!has_dot) {                                   // jprotobuf short service name (baidu_rpc_protocol.cpp:738-748)
         int sp = -1;
@@ -740,8 +772,12 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
             const uint32_t lead = min(n, (16u - (gs & 15u)) & 15u);
             const uint32_t hl = (a.pad + prefix + lead + 15u) & ~15u;
             uint8_t* h = shead;
-            uint8_t* p = h;
-            for (uint32_t k = 0; k < a.pad; k++) *p++ = 0;
+            {   // zero the record first (six 16-byte stores) instead of byte loops for the pad and the tail
+                uint4* hz = reinterpret_cast<uint4*>(h);
+                #pragma unroll
+                for (uint32_t k = 0; k < kHeadBytes / 16; k++) hz[k] = make_uint4(0, 0, 0, 0);
+            }
+            uint8_t* p = h + a.pad;
             p[0] = 'P'; p[1] = 'R'; p[2] = 'P'; p[3] = 'C';
             put_be32(p + 4, ml + 1 + vl + n); put_be32(p + 8, ml); p += 12;
             *p++ = 0x12; *p++ = 0x02; *p++ = 0x08; *p++ = 0x00; *p++ = 0x18; *p++ = 0x00;
@@ -752,7 +788,6 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
             for (uint32_t k = 0; k < a.cks_len; k++) *p++ = frame[a.cks_off + k];
             *p++ = 0x0a; p = put_varint(p, a.msg_len);
             for (uint32_t k = 0; k < lead; k++) *p++ = frame[a.msg_off + k];
-            while (p < h + hl) *p++ = 0;
             job.src_off = gs + lead; job.bulk_len = (n - lead + 15u) & ~15u; job.head_len = (uint16_t)hl;
             // a CRC32C-carrying request takes the bandwidth path once k_pack_slow's verify pass has checked it (fast 2 -> 1)
             job.fast = d.checksum_type == B2_CHECKSUM_TYPE_CRC32C ? 2 : 1;

@@ -342,3 +342,25 @@ def test_client_side_responses(b2):
         # the in-place message of an OK response equals the request's message
         ok = dev[1][(dev[1]["status"] == 7) & (dev[1]["error_code"] == 0) & (dev[1]["resp_len"] > 0)]
         assert len(ok) > 10 or opts.get("response_compress_type")
+
+
+def test_dense_and_sparse_tiles(b2):
+    """Tiles holding far more frames than the speculative walk keeps (tiny requests) next to tiles holding a few
+    (1 KB requests) and tiles with none (64 KB requests): k_frame_table's copy path and its re-walk path together."""
+    rng = random.Random(SEED + 99)
+    for tile in (0, 2048, 8192):
+        ctx = make_ctx(b2, tile_bytes=tile)
+        streams = []
+        for s in range(24):
+            fr = []
+            while sum(len(f) for f in fr) < 300_000:
+                kind = rng.random()
+                if kind < 0.5:
+                    fr += [echo_frame(rng, len(fr) + k, b"r" * rng.choice([0, 1, 16])) for k in range(rng.randrange(20, 200))]
+                elif kind < 0.9:
+                    fr += [echo_frame(rng, len(fr) + k, rnd62(rng, 1024)) for k in range(rng.randrange(1, 30))]
+                else:
+                    fr.append(echo_frame(rng, len(fr), rnd62(rng, 65536)))
+            streams.append(b"".join(fr)[:rng.randrange(250_000, 300_000)])
+        dev, _ = run_both(b2, ctx, streams, what="dense/sparse tile=%d" % tile)
+        assert len(dev[1]) > 20000
