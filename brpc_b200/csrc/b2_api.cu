@@ -39,7 +39,7 @@ struct b2_ctx {
     uint32_t* d_frame_off = nullptr; uint32_t* d_frame_run = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr; PackJob* d_jobs = nullptr; uint32_t* d_slow_idx = nullptr; uint8_t* d_heads = nullptr;
     uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr; uint8_t* d_unz = nullptr; uint16_t* d_snappy_tab = nullptr; HpackState* d_hpack = nullptr; H2Conn* d_h2 = nullptr; uint64_t h2_last_in = 0, h2_last_out = 0;   // sizes of the last h2 batch still on the device
     uint32_t* d_crc_adv = nullptr; unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
-    uint32_t max_tiles = 0; uint32_t n_sms = 148; bool use_tma_pack = true; uint32_t stage_mask = 7;  // debug: 1 front stages, 2 k_pack_tma, 4 k_pack_slow
+    size_t meta_tile_off = 0; uint32_t max_tiles = 0; uint32_t n_sms = 148; bool use_tma_pack = true; uint32_t stage_mask = 7;  // debug: 1 front stages, 2 k_pack_tma, 4 k_pack_slow
     // pinned host mirrors
     b2_run_status* h_run_status = nullptr; b2_msg_desc* h_msgs = nullptr; uint8_t* h_resp = nullptr;
     uint32_t* h_totals = nullptr; uint32_t* h_run_tile_base = nullptr;
@@ -149,9 +149,9 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     ALLOC(c->d_totals, 64);
     ALLOC(c->d_methods, sizeof(DevMethod) * 64);
     ALLOC(c->d_crc_adv, (kCrcHotWords + kCrcTreeWords) * 4);
-    ALLOC(c->d_meta, (size_t)o->max_runs * 28 + 4 * (size_t)c->max_tiles + 64);
+    ALLOC(c->d_meta, (size_t)o->max_runs * 28 + 16 * (size_t)c->max_tiles + 64);
     ALLOC(c->d_small, kSmallBlock);
-    HALLOC(c->h_meta, (size_t)o->max_runs * 28 + 4 * (size_t)c->max_tiles + 64);
+    HALLOC(c->h_meta, (size_t)o->max_runs * 28 + 16 * (size_t)c->max_tiles + 64);
     HALLOC(c->h_small, kSmallBlock);
     HALLOC(c->h_run_status, sizeof(b2_run_status) * (size_t)o->max_runs);
     HALLOC(c->h_msgs, sizeof(b2_msg_desc) * (size_t)o->max_msgs);
@@ -232,7 +232,7 @@ static BatchPtrs make_ptrs(b2_ctx* c) {
     B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes;
     B.runs = reinterpret_cast<const b2_run*>(c->d_meta);
     B.run_tile_base = reinterpret_cast<const uint32_t*>(c->d_meta + (size_t)c->n_runs * sizeof(b2_run));
-    B.tile_run = B.run_tile_base + c->n_runs + 1;
+    B.tile_info = reinterpret_cast<const uint4*>(c->d_meta + c->meta_tile_off);
     if (c->small) {
         B.totals = reinterpret_cast<uint32_t*>(c->d_small);
         B.run_status = reinterpret_cast<b2_run_status*>(c->d_small + c->small_off_rs);
@@ -266,13 +266,17 @@ extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, co
     if (nt > c->max_tiles) { set_err("too many tiles"); return B2_E_CAPACITY; }
     c->n_runs = n_runs; c->n_tiles = (uint32_t)nt; c->nbytes = nbytes; c->max_run_tiles = max_rt;
     // runs + tile bases travel as one compact block (24 B * n is 4-byte aligned)
-    const size_t meta_bytes = (size_t)n_runs * sizeof(b2_run) + 4 * ((size_t)n_runs + 1) + 4 * (size_t)nt;
+    const size_t tile_off = ((size_t)n_runs * sizeof(b2_run) + 4 * ((size_t)n_runs + 1) + 15) & ~(size_t)15;
+    const size_t meta_bytes = tile_off + 16 * (size_t)nt;
+    c->meta_tile_off = tile_off;
     if (n_runs) memcpy(c->h_meta, runs, (size_t)n_runs * sizeof(b2_run));
     memcpy(c->h_meta + (size_t)n_runs * sizeof(b2_run), c->h_run_tile_base, 4 * ((size_t)n_runs + 1));
-    {   // tile -> run map (replaces three binary searches per tile on the device)
-        uint32_t* tr = reinterpret_cast<uint32_t*>(c->h_meta + (size_t)n_runs * sizeof(b2_run) + 4 * ((size_t)n_runs + 1));
-        for (uint32_t r = 0; r < n_runs; r++)
-            for (uint32_t t = c->h_run_tile_base[r]; t < c->h_run_tile_base[r + 1]; t++) tr[t] = r;
+    {   // per-tile record {run offset, run length, tile index in the run, run | flags << 24}: one load per tile thread
+        uint32_t* ti = reinterpret_cast<uint32_t*>(c->h_meta + tile_off);
+        for (uint32_t r = 0; r < n_runs; r++) {
+            const uint32_t t0 = c->h_run_tile_base[r], t1 = c->h_run_tile_base[r + 1];
+            for (uint32_t t = t0; t < t1; t++) { uint32_t* q = ti + 4 * (size_t)t; q[0] = runs[r].offset; q[1] = runs[r].length; q[2] = t - t0; q[3] = r | (runs[r].flags << 24); }
+        }
     }
     if (nbytes) CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_meta, c->h_meta, meta_bytes, cudaMemcpyHostToDevice, c->stream));

@@ -83,7 +83,8 @@ struct BatchPtrs {
     const uint8_t* bytes;
     const b2_run* runs;
     const uint32_t* run_tile_base;   // [n_runs+1] first tile of each run
-    const uint32_t* tile_run;        // [n_tiles] run of every tile (host-built with the batch)
+    const uint4* tile_info;          // [n_tiles] {run offset, run length, tile index inside the run, run index | run flags << 24}: host-built with
+                                     // the batch so that a tile thread needs ONE load, not a tile->run->runs[] chain, before it can touch the bytes
     TileRec* tiles;
     uint32_t* tile_base;             // [n_tiles] run-relative index of the tile's first message
     uint32_t* tile_scratch;          // [3 * n_tiles] k_resolve spill when a run's tiles exceed shared memory
@@ -154,14 +155,13 @@ __device__ __forceinline__ bool is_magic(uint32_t w) { return w == kMagicPRPC ||
 // completely (header sane, whole body inside the run) and is followed by another
 // magic or the run tail.  Pure speculation: k_resolve accepts it only if the true
 // chain arrives exactly there.
-__global__ void __launch_bounds__(256) k_tile_search(BatchPtrs B, DevConfig C) {
+__global__ void __launch_bounds__(256, 6) k_tile_search(BatchPtrs B, DevConfig C) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B.n_tiles) return;
-    const uint32_t r = __ldg(B.tile_run + warp);
-    const uint32_t k = warp - __ldg(B.run_tile_base + r);
-    const b2_run run = B.runs[r];
-    const uint8_t* base = B.bytes + run.offset;
-    const uint32_t len = run.length;
+    const uint4 ti = __ldg(B.tile_info + warp);
+    const uint32_t k = ti.z;
+    const uint8_t* base = B.bytes + ti.x;
+    const uint32_t len = ti.y;
     uint32_t entry = kNone;
     if (k == 0) {
         entry = 0;
@@ -200,19 +200,32 @@ __global__ void __launch_bounds__(256) k_tile_search(BatchPtrs B, DevConfig C) {
                         if (is_magic(word) && p0 + j + 4 <= len && p0 + j < t1) mask |= 1u << j;
                     }
                 }
-                // candidates in position order: lanes ascending, bits ascending
+                // candidates in position order: lanes ascending, bits ascending.  A candidate is taken when its header is
+                // sane (meta_size <= body_size <= max_body_size): the twelve header bytes are already in registers — the
+                // lane's own 16 bytes plus its neighbour's — so no further load is needed; k_resolve is the exactness gate.
                 uint32_t any = __ballot_sync(0xffffffffu, mask != 0);
+                const uint32_t n5 = __shfl_down_sync(0xffffffffu, v[u].y, 1), n6 = __shfl_down_sync(0xffffffffu, v[u].z, 1);
                 while (any && entry == kNone) {
                     const int src = __ffs(any) - 1;
                     uint32_t m = __shfl_sync(0xffffffffu, mask, src);
                     while (m && entry == kNone) {
-                        const uint32_t p = w0 + src * 16 + (__ffs(m) - 1);
+                        const int jj = __ffs(m) - 1;
+                        const uint32_t p = w0 + src * 16 + jj;
                         m &= m - 1;
-                        const Step s = cut_input_message(base, len, p, -1, C.max_body_size);   // uniform across lanes
-                        if (s.err == B2_PARSE_OK && !s.popped) {
-                            const uint32_t q = s.new_pos;
-                            if (q + 4 > len || is_magic(load_le32(base + q))) entry = p;
-                        }
+                        uint32_t body_le = 0, meta_le = 0;
+                        if (src < 31) {
+                            const uint32_t q = (uint32_t)(jj + 4) >> 2, sh = ((uint32_t)(jj + 4) & 3u) * 8u;   // body_size sits at byte jj + 4
+                            const uint32_t a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4];
+                            const uint32_t x0 = q == 1 ? a1 : q == 2 ? a2 : q == 3 ? a3 : a4;
+                            const uint32_t x1 = q == 1 ? a2 : q == 2 ? a3 : q == 3 ? a4 : n5;
+                            const uint32_t x2 = q == 1 ? a3 : q == 2 ? a4 : q == 3 ? n5 : n6;
+                            body_le = __shfl_sync(0xffffffffu, __funnelshift_r(x0, x1, sh), src);
+                            meta_le = __shfl_sync(0xffffffffu, __funnelshift_r(x1, x2, sh), src);
+                        } else if (p + 12 <= len) {                      // (the header straddles two windows: read it)
+                            body_le = load_le32(base + p + 4); meta_le = load_le32(base + p + 8);
+                        } else continue;
+                        const uint32_t body = __byte_perm(body_le, 0, 0x0123), meta = __byte_perm(meta_le, 0, 0x0123);
+                        if (meta <= body && (uint64_t)body <= C.max_body_size) entry = p;
                     }
                     any &= any - 1;
                 }
@@ -226,9 +239,9 @@ __global__ void __launch_bounds__(256) k_tile_search(BatchPtrs B, DevConfig C) {
 __global__ void __launch_bounds__(128) k_tile_walk(BatchPtrs B, DevConfig C) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B.n_tiles) return;
-    const uint32_t r = __ldg(B.tile_run + t);
-    const uint32_t k = t - __ldg(B.run_tile_base + r);
-    const b2_run run = B.runs[r];
+    const uint4 ti = __ldg(B.tile_info + t);
+    const uint32_t k = ti.z;
+    b2_run run; run.offset = ti.x; run.length = ti.y; run.flags = ti.w >> 24;
     TileRec rec;
     rec.entry = B.tiles[t].entry; rec.exit = 0; rec.count = 0; rec.kind = kStop; rec.last_proto = 0; rec.live = 0; rec.pf_in = -1;
     if (rec.entry != kNone) {
@@ -422,15 +435,16 @@ __global__ void __launch_bounds__(256) k_frame_table(BatchPtrs B, DevConfig C) {
     const TileRec rec = B.tiles[t];
     if (!rec.live || rec.count == 0) return;
     if (B.totals[2] & 1u) return;
-    const uint32_t r = __ldg(B.tile_run + t);
+    const uint4 ti = __ldg(B.tile_info + t);
+    const uint32_t r = ti.w & 0xffffffu;
     const uint32_t first = B.run_status[r].first_msg + B.tile_base[t];
     if (!(rec.kind & kKindRewalked) && rec.count <= kSpecK) {
         if (j < rec.count && first + j < B.max_msgs) { B.frame_off[first + j] = B.tile_spec[(size_t)t * kSpecK + j]; B.frame_run[first + j] = r; }
         return;
     }
     if (j != 0) return;
-    const uint32_t k = t - __ldg(B.run_tile_base + r);
-    const b2_run run = B.runs[r];
+    const uint32_t k = ti.z;
+    b2_run run; run.offset = ti.x; run.length = ti.y; run.flags = ti.w >> 24;
     TileRec tmp;
     EmitFrame e; e.out = B.frame_off + first; e.out_run = B.frame_run + first; e.run_off = run.offset; e.run_idx = r; e.cap_left = B.max_msgs - first;
     walk_tile<false>(B.bytes + run.offset, run.length, rec.entry, rec.pf_in, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, tmp, e);
