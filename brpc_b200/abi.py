@@ -17,6 +17,9 @@ H2_FRAME_DT = np.dtype([("type", "u1"), ("flags", "u1"), ("pad", "<u2"), ("strea
 HPACK_BLOCK_DT = np.dtype([("conn", "<u4"), ("offset", "<u4"), ("length", "<u4"), ("reserved", "<u4")])
 H2_RUN_STATUS_DT = np.dtype([("consumed", "<u4"), ("parse_error", "<u4"), ("n_msgs", "<u4"), ("first_msg", "<u4"), ("ctrl_off", "<u4"), ("ctrl_len", "<u4"),
                              ("remote_max_frame_size", "<u4"), ("remote_stream_window_size", "<u4")])
+REQUEST_DT = np.dtype([("kind", "<u4"), ("flags", "<u4"), ("method_idx", "<i4"), ("timeout_ms", "<i4"), ("correlation_id", "<i8"), ("log_id", "<i8"),
+                       ("compress_type", "<i4"), ("checksum_type", "<i4"), ("frame_type", "<i4"), ("payload_off", "<u4"), ("payload_len", "<u4"),
+                       ("attachment_off", "<u4"), ("attachment_len", "<u4"), ("reserved", "<u4")])
 H2_RESPONSE_DT = np.dtype([("conn", "<u4"), ("stream_id", "<u4"), ("status_code", "<i4"), ("flags", "<u4"), ("content_type_off", "<u4"),
                            ("content_type_len", "<u4"), ("body_off", "<u4"), ("body_len", "<u4"), ("grpc_status", "<i4"),
                            ("grpc_message_off", "<u4"), ("grpc_message_len", "<u4"), ("reserved", "<u4")])
@@ -95,6 +98,7 @@ def _load():
     l.b2_h2_process_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                       C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32]
     l.b2_h2_pack_responses.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    l.b2_pack_requests.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     l.b2_counters_read.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     l.b2_counters_device_ptr.restype = C.c_void_p; l.b2_counters_device_ptr.argtypes = [C.c_void_p]
     return l
@@ -106,7 +110,7 @@ lib = _load()
 ABI_SYMBOLS = ["b2_ctx_create", "b2_ctx_destroy", "b2_last_error", "b2_version", "b2_register_method",
                "b2_set_server_identity", "b2_set_stream_handler", "b2_block_alloc", "b2_block_free", "b2_process_batch", "b2_batch_submit", "b2_batch_collect", "b2_batch_upload",
                "b2_batch_execute", "b2_batch_execute_many", "b2_batch_download", "b2_batch_launch", "b2_batch_wait",
-               "b2_elapsed_ms", "b2_stage_times", "b2_crc32c_batch", "b2_snappy_uncompress_batch", "b2_snappy_compress_batch", "b2_hpack_reset", "b2_hpack_decode_batch", "b2_h2_scan_batch", "b2_h2_conn_reset", "b2_h2_process_batch", "b2_h2_pack_responses", "b2_counters_read",
+               "b2_elapsed_ms", "b2_stage_times", "b2_crc32c_batch", "b2_snappy_uncompress_batch", "b2_snappy_compress_batch", "b2_hpack_reset", "b2_hpack_decode_batch", "b2_pack_requests", "b2_h2_scan_batch", "b2_h2_conn_reset", "b2_h2_process_batch", "b2_h2_pack_responses", "b2_counters_read",
                "b2_counters_device_ptr"]
 
 ECHO_METHOD = dict(service_full_name=b"example.EchoService", service_name=b"EchoService", method_name=b"Echo",
@@ -340,6 +344,15 @@ class Context:
         _check(lib.b2_h2_pack_responses(self._h, ptr, nb, resps.ctypes.data, n, out.ctypes.data, out_cap, offs.ctypes.data, lens.ctypes.data))
         if raw:
             return out, offs, lens
+        return [out[offs[i]:offs[i] + lens[i]].tobytes() for i in range(n)]
+
+    def pack_requests(self, data, reqs, out_cap=None):
+        """reqs: REQUEST_DT array (offsets into data).  Returns the packed frame of every request (b"" = rejected)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8); reqs = np.ascontiguousarray(reqs, dtype=REQUEST_DT)
+        n = len(reqs)
+        out_cap = out_cap or int((reqs["payload_len"].astype(np.int64) * 7 // 6 + reqs["attachment_len"] + 640).sum() + 4096)
+        out = np.empty(out_cap, np.uint8); offs = np.zeros(n, np.uint32); lens = np.zeros(n, np.uint32)
+        _check(lib.b2_pack_requests(self._h, data.ctypes.data, data.nbytes, reqs.ctypes.data, n, out.ctypes.data, out_cap, offs.ctypes.data, lens.ctypes.data))
         return [out[offs[i]:offs[i] + lens[i]].tobytes() for i in range(n)]
 
     def counters(self):

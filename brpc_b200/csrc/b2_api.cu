@@ -778,3 +778,33 @@ extern "C" int b2_h2_pack_responses(b2_ctx* c, const void* bytes, uint32_t nbyte
     c->uploaded = false; c->executed = false;
     return B2_OK;
 }
+
+extern "C" int b2_pack_requests(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_request* reqs, uint32_t n,
+                                void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens) {
+    if (!c || (!bytes && nbytes) || !reqs || !out || !out_offs || !out_lens) { set_err("null argument"); return B2_E_INVAL; }
+    static_assert(sizeof(b2_request) == 64 && sizeof(ReqDesc) == 64, "request ABI layout");
+    if (nbytes > c->opt.max_batch_bytes || n > c->opt.max_msgs || out_cap > c->opt.max_resp_bytes) { set_err("exceeds ctx capacity"); return B2_E_CAPACITY; }
+    if (n == 0) return B2_OK;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const b2_request& r = reqs[i];
+        if ((uint64_t)r.payload_off + r.payload_len > nbytes || (uint64_t)r.attachment_off + r.attachment_len > nbytes) { set_err("payload outside buffer"); return B2_E_INVAL; }
+        const uint64_t pb = 6ull + r.payload_len;
+        const uint64_t need = 12 + 512 + (r.compress_type == B2_COMPRESS_TYPE_SNAPPY ? snappy_max_compressed_length((uint32_t)pb) : pb) + r.attachment_len;
+        out_offs[i] = (uint32_t)total;
+        total = (total + need + 15) & ~15ull;
+        if (total > out_cap) { set_err("out_cap too small"); return B2_E_CAPACITY; }
+    }
+    CU(cudaSetDevice(c->opt.device));
+    ReqDesc* d_reqs = reinterpret_cast<ReqDesc*>(c->d_msgs);
+    uint32_t* d_offs = c->d_frame_off; uint32_t* d_lens = c->d_slot;
+    if (nbytes) CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_reqs, reqs, sizeof(b2_request) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_offs, out_offs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    k_pack_requests<<<c->n_sms * 4, 256, 0, c->stream>>>(c->d_bytes, d_reqs, n, c->d_methods, c->cfg.n_methods, c->d_resp, d_offs, d_lens, c->d_unz, c->d_snappy_tab, c->d_crc_adv);
+    CU(cudaMemcpyAsync(out_lens, d_lens, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out, c->d_resp, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->uploaded = false; c->executed = false;
+    return B2_OK;
+}

@@ -1671,6 +1671,103 @@ __global__ void __launch_bounds__(kPackWarps * 32, 1) k_pack_tma(BatchPtrs B, De
     bulk_wait<0>();
 }
 
+// --- k_pack_requests: the client mirror -------------------------------------------------------------
+// PackRpcRequest + SerializeRpcRequest (baidu_rpc_protocol.cpp:1015-1133) and PackStreamMessage
+// (streaming_rpc_protocol.cpp:42-58): one warp per frame.  The meta length does not depend on the body, so the
+// body is produced in place first (serialized / snappy-compressed, CRC over what was produced), then lane 0
+// writes header and meta in front of it.
+struct ReqDesc {                     // == b2_request
+    uint32_t kind, flags; int32_t method_idx, timeout_ms; long long correlation_id, log_id;
+    int32_t compress_type, checksum_type, frame_type; uint32_t payload_off, payload_len, attachment_off, attachment_len, reserved;
+};
+__global__ void __launch_bounds__(256) k_pack_requests(const uint8_t* bytes, const ReqDesc* reqs, uint32_t n, const DevMethod* methods, uint32_t n_methods,
+                                                       uint8_t* out, const uint32_t* out_offs, uint32_t* out_lens, uint8_t* scratch,
+                                                       uint16_t* snappy_tab, const uint32_t* crc_adv) {
+    __shared__ uint32_t s_hot[kCrcHotWords];
+    crc_tabs_to_smem(s_hot, crc_adv);
+    CrcTabs ct; ct.hot = s_hot; ct.tree = crc_adv + kCrcHotWords;
+    const uint32_t lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5, warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t i = warp_id; i < n; i += n_warps) {
+        const ReqDesc R = reqs[i];
+        uint8_t* o = out + out_offs[i];
+        const uint8_t* payload = bytes + R.payload_off;
+        if (R.kind == 1) {                                           // ---- PackStreamMessage
+            uint8_t meta[40]; uint8_t* m = meta;
+            *m++ = 0x08; m = put_varint(m, (uint64_t)R.correlation_id);
+            if (R.flags & 1u) { *m++ = 0x10; m = put_varint(m, (uint64_t)R.log_id); }
+            *m++ = 0x18; m = put_varint(m, (uint64_t)(long long)R.frame_type);
+            if (R.flags & 2u) { *m++ = 0x20; *m++ = (R.flags & 4u) ? 1 : 0; }
+            const uint32_t ml = (uint32_t)(m - meta);
+            if (lane == 0) {
+                o[0] = 'S'; o[1] = 'T'; o[2] = 'R'; o[3] = 'M'; put_be32(o + 4, ml + R.payload_len); put_be32(o + 8, ml);
+                for (uint32_t k = 0; k < ml; k++) o[12 + k] = meta[k];
+            }
+            warp_copy(o + 12 + ml, payload, R.payload_len, lane);
+            if (lane == 0) out_lens[i] = 12 + ml + R.payload_len;
+            continue;
+        }
+        if (R.method_idx < 0 || (uint32_t)R.method_idx >= n_methods ||
+            (R.compress_type != B2_COMPRESS_TYPE_NONE && R.compress_type != B2_COMPRESS_TYPE_SNAPPY)) { if (lane == 0) out_lens[i] = 0; continue; }
+        const DevMethod& M = methods[R.method_idx];
+        const uint32_t mth_len = M.full_method_len - M.service_full_len - 1;
+        const uint8_t* mth = reinterpret_cast<const uint8_t*>(M.full_method) + M.service_full_len + 1;
+        // RpcRequestMeta: service_name(1) method_name(2) [log_id(3)] [timeout_ms(8)]
+        uint32_t rl = 1 + varint_len(M.service_full_len) + M.service_full_len + 1 + varint_len(mth_len) + mth_len;
+        if (R.flags & 1u) rl += 1 + varint_len((uint64_t)R.log_id);
+        const bool has_to = (R.flags & 2u) && R.timeout_ms > 0;
+        if (has_to) rl += 1 + varint_len((uint64_t)(long long)R.timeout_ms);
+        const uint32_t cks_len = R.checksum_type == B2_CHECKSUM_TYPE_CRC32C ? 4u : 0u;
+        // RpcMeta: request(1) compress_type(3) correlation_id(4) [attachment_size(5)] content_type(10) checksum_type(11) checksum_value(12)
+        uint32_t ml = 1 + varint_len(rl) + rl + 1 + varint_len((uint64_t)(long long)R.compress_type) + 1 + varint_len((uint64_t)R.correlation_id);
+        if (R.attachment_len) ml += 1 + varint_len(R.attachment_len);
+        ml += 2 + 1 + varint_len((uint64_t)(long long)R.checksum_type) + 1 + 1 + cks_len;
+        uint8_t* body = o + 12 + ml;
+        const uint32_t vl = varint_len(R.payload_len), pb_len = 1 + vl + R.payload_len;
+        uint32_t body_len;
+        if (R.compress_type == B2_COMPRESS_TYPE_SNAPPY) {
+            uint8_t* pb = scratch + out_offs[i];                     // the serialized EchoRequest, then compressed into place
+            if (lane == 0) { pb[0] = 0x0a; put_varint(pb + 1, R.payload_len); }
+            warp_copy(pb + 1 + vl, payload, R.payload_len, lane);
+            __syncwarp();
+            body_len = warp_snappy_compress(pb, pb_len, body, snappy_tab + (size_t)(warp_id % kSnappyWarps) * kSnappyMaxTable, lane);
+        } else {
+            if (lane == 0) { body[0] = 0x0a; put_varint(body + 1, R.payload_len); }
+            warp_copy(body + 1 + vl, payload, R.payload_len, lane);
+            body_len = pb_len;
+        }
+        __syncwarp();
+        uint32_t crc_be = 0;
+        if (cks_len) {                                               // Crc32cCompute (policy/crc32c_checksum.cpp:28-42) over the body
+            uint32_t l = 0xffffffffu;
+            if (R.compress_type == B2_COMPRESS_TYPE_SNAPPY) { __threadfence_block(); l = warp_crc32c_update(l, body, body_len, lane, ct); }
+            else {                                                   // from the sources: field header, then the message bytes
+                uint8_t hdr[6]; hdr[0] = 0x0a; uint8_t* e = put_varint(hdr + 1, R.payload_len);
+                l = crc32c_bytes_serial(l, hdr, (uint32_t)(e - hdr));
+                l = warp_crc32c_update(l, payload, R.payload_len, lane, ct);
+            }
+            crc_be = crc32c_mask(l ^ 0xffffffffu);
+        }
+        if (R.attachment_len) warp_copy(body + body_len, bytes + R.attachment_off, R.attachment_len, lane);
+        if (lane == 0) {
+            uint8_t* p = o;
+            p[0] = 'P'; p[1] = 'R'; p[2] = 'P'; p[3] = 'C'; put_be32(p + 4, ml + body_len + R.attachment_len); put_be32(p + 8, ml); p += 12;
+            *p++ = 0x0a; p = put_varint(p, rl);
+            *p++ = 0x0a; p = put_varint(p, M.service_full_len); for (uint32_t k = 0; k < M.service_full_len; k++) *p++ = (uint8_t)M.service_full[k];
+            *p++ = 0x12; p = put_varint(p, mth_len); for (uint32_t k = 0; k < mth_len; k++) *p++ = mth[k];
+            if (R.flags & 1u) { *p++ = 0x18; p = put_varint(p, (uint64_t)R.log_id); }
+            if (has_to) { *p++ = 0x40; p = put_varint(p, (uint64_t)(long long)R.timeout_ms); }
+            *p++ = 0x18; p = put_varint(p, (uint64_t)(long long)R.compress_type);
+            *p++ = 0x20; p = put_varint(p, (uint64_t)R.correlation_id);
+            if (R.attachment_len) { *p++ = 0x28; p = put_varint(p, R.attachment_len); }
+            *p++ = 0x50; *p++ = 0x00;
+            *p++ = 0x58; p = put_varint(p, (uint64_t)(long long)R.checksum_type);
+            *p++ = 0x62; *p++ = (uint8_t)cks_len;
+            if (cks_len) p = put_be32(p, crc_be);
+            out_lens[i] = 12 + ml + body_len + R.attachment_len;
+        }
+    }
+}
+
 // --- k_pack_slow: everything that is not a plain OK echo ----------------------
 // error replies, CRC32C verify/compute, snappy requests, split attachments: warp per message,
 // high occupancy (these are latency-bound), skipping the messages k_pack_tma moves.

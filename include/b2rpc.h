@@ -294,6 +294,35 @@ int  b2_snappy_compress_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
                               const uint32_t* offs, const uint32_t* lens, uint32_t n,
                               void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens);
 
+/* ---- client mirror: PackRpcRequest (src/brpc/policy/baidu_rpc_protocol.cpp:1045-1133) with
+ * SerializeRpcRequest (:1015-1043: EchoRequest{message}, COMPRESS_TYPE_NONE / SNAPPY, CRC32C over the serialized body)
+ * and PackStreamMessage (policy/streaming_rpc_protocol.cpp:42-58), one warp per frame.  RpcRequestMeta carries the
+ * registered method's service_full_name / method_name (-baidu_protocol_use_fullname=true), log_id and timeout_ms when
+ * flagged; RpcMeta always carries compress_type, correlation_id, content_type(0), checksum_type and checksum_value (what
+ * PackRpcRequest sets unconditionally) and attachment_size when there is an attachment.  Tracing fields and request_id
+ * are not covered.  Frame i lands at out + out_offs[i] (filled by the call), out_lens[i] long (0 = could not be packed). */
+#define B2_REQ_BAIDU_STD     0
+#define B2_REQ_STREAM_FRAME  1
+#define B2_REQ_HAS_LOG_ID            1u   /* baidu_std */
+#define B2_REQ_HAS_TIMEOUT           2u   /* baidu_std: timeout_ms > 0 is written */
+#define B2_REQ_HAS_SOURCE_STREAM_ID  1u   /* stream frame */
+#define B2_REQ_HAS_CONTINUATION      2u   /* stream frame: has_continuation is present ... */
+#define B2_REQ_CONTINUATION_VALUE    4u   /* ... with this value */
+typedef struct b2_request {
+    uint32_t kind, flags;
+    int32_t  method_idx;             /* baidu_std: registered method */
+    int32_t  timeout_ms;             /* baidu_std */
+    int64_t  correlation_id;         /* stream frame: stream_id */
+    int64_t  log_id;                 /* stream frame: source_stream_id */
+    int32_t  compress_type, checksum_type;   /* baidu_std */
+    int32_t  frame_type;             /* stream frame: brpc::FrameType */
+    uint32_t payload_off, payload_len;        /* EchoRequest.message / the stream data */
+    uint32_t attachment_off, attachment_len;  /* baidu_std */
+    uint32_t reserved;
+} b2_request;                        /* 64 bytes */
+int  b2_pack_requests(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_request* reqs, uint32_t n,
+                      void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens);
+
 /* ---- h2 / gRPC building blocks (the stream state machine stays on the host) -----
  * b2_h2_scan_batch: H2Context::ConsumeFrameHead (src/brpc/policy/http2_rpc_protocol.cpp:438-465)
  * chained over every connection run.  runs[i].flags & B2_RUN_H2_PREFACE: the run starts a server-side
