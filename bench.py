@@ -222,8 +222,10 @@ def grpc_h2_main(args):
     data0, runs0 = brpc_b200.make_runs(first_batch)
     rs, msgs, out = ctx.h2_process_batch(data0, runs0)
     assert int(rs["n_msgs"].sum()) == n_conns
-    data, runs = brpc_b200.make_runs(batch)
-    data = np.array(data, dtype=np.uint8)
+    data_, runs = brpc_b200.make_runs(batch)
+    from brpc_b200.abi import PinnedBuffer
+    pin_in = PinnedBuffer(len(data_)); data = pin_in.array; data[:] = data_        # host buffers are pinned, like IOBuf blocks from b2_block_alloc
+    pin_out = PinnedBuffer(n_conns * (K * 1024 + 8192)); pin_pack = PinnedBuffer(n_conns * K * (msg_len + 256) + 4096)
     pos = []                                                   # offsets of every frame's stream-id field
     for r_ in runs:
         p_ = int(r_["offset"]); end = p_ + int(r_["length"])
@@ -243,7 +245,7 @@ def grpc_h2_main(args):
     hb0 = bytes(out[msgs[0]["headers_off"]:msgs[0]["headers_off"] + msgs[0]["headers_len"]]); ct_rel = hb0.index(ct)
     def one_step(t, check=False):
         set_round(t)
-        rs, msgs, out = ctx.h2_process_batch(data, runs, msg_cap=n_conns * (K + 2), out_cap=n_conns * (K * 1024 + 8192))
+        rs, msgs, out = ctx.h2_process_batch(data, runs, msg_cap=n_conns * (K + 2), out=pin_out.array)
         n = len(msgs)
         assert n == n_conns * K, (n, rs["parse_error"][:4])
         # echo: the reply message is the request message, still on the device (input buffer when one DATA frame carried it,
@@ -253,7 +255,7 @@ def grpc_h2_main(args):
         resps["flags"] = 1 | 8 | np.where(msgs["flags"] & 16, 2, 4)
         resps["content_type_off"] = msgs["headers_off"] + ct_rel; resps["content_type_len"] = len(ct)
         resps["body_off"] = msgs["msg_off"]; resps["body_len"] = msgs["msg_len"]
-        pout, poffs, plens = ctx.h2_pack_responses(None, resps, out_cap=n * (msg_len + 256) + 4096, raw=True)
+        pout, poffs, plens = ctx.h2_pack_responses(None, resps, raw=True, out=pin_pack.array)
         if check:
             assert np.all(plens > msg_len) and bytes(pout[poffs[0] + 9:poffs[0] + 10]) == b"\x88"       # HEADERS begin with :status 200 (static index 8)
         return n

@@ -320,23 +320,29 @@ class Context:
     def h2_conn_reset(self, conn):
         _check(lib.b2_h2_conn_reset(self._h, conn))
 
-    def h2_process_batch(self, data, runs, msg_cap=None, out_cap=None):
+    def h2_process_batch(self, data, runs, msg_cap=None, out_cap=None, out=None):
         """runs[i].socket_id = h2 connection index.  Returns (run_status, msgs, out)."""
         data = np.ascontiguousarray(data, dtype=np.uint8); runs = np.ascontiguousarray(runs, dtype=RUN_DT)
         n = len(runs)
         msg_cap = msg_cap or max(64, 64 * n)
         out_cap = out_cap or max(1 << 16, n * (1 << 17))
-        rs = np.zeros(n, H2_RUN_STATUS_DT); msgs = np.zeros(msg_cap, H2_MSG_DT); out = np.empty(out_cap, np.uint8); nm = C.c_uint32(0)
+        rs = np.zeros(n, H2_RUN_STATUS_DT); msgs = np.zeros(msg_cap, H2_MSG_DT); nm = C.c_uint32(0)
+        if out is None:
+            out = np.empty(out_cap, np.uint8)       # (pass a PinnedBuffer's array to keep the copies off pageable memory)
+        out_cap = out.nbytes
         _check(lib.b2_h2_process_batch(self._h, data.ctypes.data, data.nbytes, runs.ctypes.data, n, rs.ctypes.data, msgs.ctypes.data, msg_cap,
                                        C.byref(nm), out.ctypes.data, out_cap))
         return rs, msgs[:nm.value], out
 
-    def h2_pack_responses(self, data, resps, out_cap=None, raw=False):
+    def h2_pack_responses(self, data, resps, out_cap=None, raw=False, out=None):
         """resps: H2_RESPONSE_DT array (offsets into data).  Returns the packed bytes of every response."""
         resps = np.ascontiguousarray(resps, dtype=H2_RESPONSE_DT)
         n = len(resps)
         out_cap = out_cap or int(resps["body_len"].astype(np.int64).sum() * 2 + n * 2048 + 4096)
-        out = np.empty(out_cap, np.uint8); offs = np.zeros(n, np.uint32); lens = np.zeros(n, np.uint32)
+        offs = np.zeros(n, np.uint32); lens = np.zeros(n, np.uint32)
+        if out is None:
+            out = np.empty(out_cap, np.uint8)
+        out_cap = out.nbytes
         if data is None:                 # every field uses a zero-copy source (B2_H2_RESP_*_IN_INPUT / _IN_OUT)
             ptr, nb = None, 0
         else:

@@ -771,7 +771,7 @@ extern "C" int b2_h2_pack_responses(b2_ctx* c, const void* bytes, uint32_t nbyte
     CU(cudaMemcpyAsync(d_resps, resps, sizeof(b2_h2_response) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_first, first.data(), 4 * first.size(), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_offs, out_offs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    k_h2_pack<<<(n_groups + 31) / 32, 32, 0, c->stream>>>(d_aux, c->d_bytes, c->d_unz, d_resps, d_first, n_groups, c->d_h2, c->d_resp, d_offs, d_lens);
+    k_h2_pack<<<(n_groups + kH2PackWarps - 1) / kH2PackWarps, kH2PackWarps * 32, 0, c->stream>>>(d_aux, c->d_bytes, c->d_unz, d_resps, d_first, n_groups, c->d_h2, c->d_resp, d_offs, d_lens);
     CU(cudaMemcpyAsync(out_lens, d_lens, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(out, c->d_resp, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -103,7 +103,12 @@ __device__ __forceinline__ bool hp_copy_indexed(const HpackState& h, uint32_t in
         const uint32_t e = (h.head + (index - 62)) & 127u;
         nl = h.meta[e].nl; vl = with_value ? h.meta[e].vl : 0;
         if (nl + vl > cap) { overflow = true; return false; }
-        for (uint32_t i = 0; i < nl + vl; i++) out[i] = h.bytes[(h.meta[e].off + i) & 4095u];
+        const uint32_t off = h.meta[e].off, nb = nl + vl;
+        if (off + nb <= 4096u) {                                      // the entry does not wrap the ring: word copies
+            uint32_t i = 0;
+            for (; i + 4 <= nb; i += 4) { const uint32_t wv = ld32_any(h.bytes + off + i); out[i] = (uint8_t)wv; out[i + 1] = (uint8_t)(wv >> 8); out[i + 2] = (uint8_t)(wv >> 16); out[i + 3] = (uint8_t)(wv >> 24); }
+            for (; i < nb; i++) out[i] = h.bytes[off + i];
+        } else for (uint32_t i = 0; i < nb; i++) out[i] = h.bytes[(off + i) & 4095u];
         return true;
     }
     return false;
@@ -341,7 +346,15 @@ __device__ __forceinline__ bool ci_eq(const uint8_t* a, uint32_t n, const char* 
     }
     return i == n;
 }
-__device__ __forceinline__ uint32_t cstr_len(const uint8_t* p, uint32_t n) { uint32_t i = 0; while (i < n && p[i]) i++; return i; }
+__device__ __forceinline__ uint32_t cstr_len(const uint8_t* p, uint32_t n) {           // strnlen: four bytes per step
+    uint32_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const uint32_t z = __vcmpeq4(ld32_any(p + i), 0u);
+        if (z) return i + ((__ffs(z) - 1) >> 3);
+    }
+    while (i < n && p[i]) i++;
+    return i;
+}
 __device__ __forceinline__ bool lit_eq(const uint8_t* a, uint32_t n, const char* lit) {   // strcmp(c_str, lit) == 0
     uint32_t i = 0;
     for (; lit[i]; i++) if (i >= n || a[i] != (uint8_t)lit[i]) return false;
@@ -765,57 +778,82 @@ __device__ __forceinline__ uint32_t put_dec_i32_h2(uint8_t* p, int32_t v) {     
     return o;
 }
 constexpr uint32_t kH2FragCap = 1024;      // encoded header block of one response (":status", "content-type", trailers)
-__global__ void k_h2_pack(const uint8_t* bytes, const uint8_t* last_input, const uint8_t* last_out, const b2_h2_response* resps, const uint32_t* group_first, uint32_t n_groups, H2Conn* conns,
-                          uint8_t* out, const uint32_t* out_offs, uint32_t* out_lens) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr uint32_t kH2PackWarps = 4;
+// One WARP per connection: lane 0 runs the serial part (window check, HPACK encode against the connection's table,
+// deferred WINDOW_UPDATE) into shared memory, then the whole warp writes the frames — the DATA payload, which is
+// nearly all of the bytes, with coalesced 16-byte copies.
+__global__ void __launch_bounds__(kH2PackWarps * 32) k_h2_pack(const uint8_t* bytes, const uint8_t* last_input, const uint8_t* last_out, const b2_h2_response* resps,
+                                                               const uint32_t* group_first, uint32_t n_groups, H2Conn* conns,
+                                                               uint8_t* out, const uint32_t* out_offs, uint32_t* out_lens) {
+    __shared__ __align__(16) uint8_t s_buf[kH2PackWarps][3][kH2FragCap];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t g = blockIdx.x * kH2PackWarps + w;
     if (g >= n_groups) return;
-    uint8_t frag[kH2FragCap], trailer[kH2FragCap], tmp[kH2FragCap];
+    uint8_t* frag = s_buf[w][0]; uint8_t* trailer = s_buf[w][1]; uint8_t* tmp = s_buf[w][2];
     for (uint32_t i = group_first[g]; i < group_first[g + 1]; i++) {
         const b2_h2_response R = resps[i];
-        H2Conn& c = conns[R.conn];
         uint8_t* o0 = out + out_offs[i]; uint8_t* o = o0;
         const bool grpc = R.flags & B2_H2_RESP_GRPC;
         const uint32_t data_size = R.body_len + (grpc ? 5u : 0u);
-        // MinusWindowSize(&_remote_window_left, _data.size()) (:283-296)
-        if (c.remote_window_left < (long long)data_size) {
-            h2_put_head(o, 4, 3, 0, R.stream_id); put_be32(o + 9, 3); out_lens[i] = 13; continue;
+        uint32_t rst = 0, fl = 0, tl = 0, mfs = 0, cw = 0;
+        if (lane == 0) {
+            H2Conn& c = conns[R.conn];
+            // MinusWindowSize(&_remote_window_left, _data.size()) (:283-296)
+            if (c.remote_window_left < (long long)data_size) rst = 1;
+            else {
+                c.remote_window_left -= (long long)data_size;
+                const bool never = c.r_header_table_size == 0;
+                uint8_t num[16];
+                uint8_t* f = frag;
+                { const uint32_t nn = put_dec_i32_h2(num, R.status_code); f = hp_encode(c.enc, f, (const uint8_t*)":status", 7, num, nn, never, tmp); }
+                if (R.content_type_len) f = hp_encode(c.enc, f, (const uint8_t*)"content-type", 12, ((R.flags & B2_H2_RESP_CT_IN_OUT) ? last_out : bytes) + R.content_type_off, R.content_type_len, never, tmp);
+                uint8_t* t = trailer;
+                if (grpc) {
+                    const uint32_t nn = put_dec_i32_h2(num, R.grpc_status);
+                    t = hp_encode(c.enc, t, (const uint8_t*)"grpc-status", 11, num, nn, never, tmp);
+                    if (R.grpc_message_len) t = hp_encode(c.enc, t, (const uint8_t*)"grpc-message", 12, bytes + R.grpc_message_off, R.grpc_message_len, never, tmp);
+                }
+                fl = (uint32_t)(f - frag); tl = (uint32_t)(t - trailer); mfs = c.r_max_frame_size;
+                if (c.deferred_window_update > 0) { cw = (uint32_t)c.deferred_window_update; c.deferred_window_update = 0; }   // ReleaseDeferredWindowUpdate
+            }
         }
-        c.remote_window_left -= (long long)data_size;
-        const bool never = c.r_header_table_size == 0;
-        uint8_t num[16];
-        uint8_t* f = frag;
-        { const uint32_t nn = put_dec_i32_h2(num, R.status_code); f = hp_encode(c.enc, f, (const uint8_t*)":status", 7, num, nn, never, tmp); }
-        if (R.content_type_len) f = hp_encode(c.enc, f, (const uint8_t*)"content-type", 12, ((R.flags & B2_H2_RESP_CT_IN_OUT) ? last_out : bytes) + R.content_type_off, R.content_type_len, never, tmp);
-        uint8_t* t = trailer;
-        if (grpc) {
-            const uint32_t nn = put_dec_i32_h2(num, R.grpc_status);
-            t = hp_encode(c.enc, t, (const uint8_t*)"grpc-status", 11, num, nn, never, tmp);
-            if (R.grpc_message_len) t = hp_encode(c.enc, t, (const uint8_t*)"grpc-message", 12, bytes + R.grpc_message_off, R.grpc_message_len, never, tmp);
+        rst = __shfl_sync(0xffffffffu, rst, 0); fl = __shfl_sync(0xffffffffu, fl, 0); tl = __shfl_sync(0xffffffffu, tl, 0);
+        mfs = __shfl_sync(0xffffffffu, mfs, 0); cw = __shfl_sync(0xffffffffu, cw, 0);
+        __syncwarp();
+        if (rst) {                                                   // RST_STREAM(FLOW_CONTROL_ERROR) instead of the response (:1706-1712)
+            if (lane == 0) { h2_put_head(o, 4, 3, 0, R.stream_id); put_be32(o + 9, 3); out_lens[i] = 13; }
+            __syncwarp();
+            continue;
         }
-        const uint32_t fl = (uint32_t)(f - frag), tl = (uint32_t)(t - trailer), mfs = c.r_max_frame_size;
-        // ---- PackH2Message
-        uint8_t hflags = (data_size == 0 && tl == 0) ? 0x1 : 0;
-        if (fl <= mfs) { h2_put_head(o, fl, 1, hflags | 0x4, R.stream_id); o += 9; for (uint32_t k = 0; k < fl; k++) *o++ = frag[k]; }
-        else {                                                    // (cannot happen with kH2FragCap < 16384 <= max_frame_size; kept for the shape)
-            h2_put_head(o, mfs, 1, hflags, R.stream_id); o += 9; for (uint32_t k = 0; k < mfs; k++) *o++ = frag[k];
-            for (uint32_t at = mfs; at < fl;) { const uint32_t nn = min(fl - at, mfs); h2_put_head(o, nn, 9, at + nn == fl ? 0x4 : 0, R.stream_id); o += 9; for (uint32_t k = 0; k < nn; k++) *o++ = frag[at + k]; at += nn; }
+        // ---- PackH2Message (:1310-1380)
+        const uint8_t hflags = (data_size == 0 && tl == 0) ? 0x1 : 0;
+        if (fl <= mfs) {
+            if (lane == 0) h2_put_head(o, fl, 1, hflags | 0x4, R.stream_id);
+            for (uint32_t k = lane; k < fl; k += 32) o[9 + k] = frag[k];
+            o += 9 + fl;
+        } else {                                                     // (cannot happen with kH2FragCap < 16384 <= max_frame_size; kept for the shape)
+            if (lane == 0) {
+                uint8_t* q = o;
+                h2_put_head(q, mfs, 1, hflags, R.stream_id); q += 9; for (uint32_t k = 0; k < mfs; k++) *q++ = frag[k];
+                for (uint32_t at = mfs; at < fl;) { const uint32_t nn = min(fl - at, mfs); h2_put_head(q, nn, 9, at + nn == fl ? 0x4 : 0, R.stream_id); q += 9; for (uint32_t k = 0; k < nn; k++) *q++ = frag[at + k]; at += nn; }
+            }
+            o += fl + 9 * ((fl + mfs - 1) / mfs);
         }
         const uint8_t* body = ((R.flags & B2_H2_RESP_BODY_IN_INPUT) ? last_input : (R.flags & B2_H2_RESP_BODY_IN_OUT) ? last_out : bytes) + R.body_off;
         for (uint32_t at = 0; at < data_size;) {
             const uint32_t nn = min(data_size - at, mfs);
             const uint8_t dflags = (at + nn == data_size && tl == 0) ? 0x1 : 0;
-            h2_put_head(o, nn, 0, dflags, R.stream_id); o += 9;
+            if (lane == 0) h2_put_head(o, nn, 0, dflags, R.stream_id);
+            o += 9;
             uint32_t k = 0;
-            if (grpc) for (; k < nn && at + k < 5; k++) { const uint32_t q = at + k; o[k] = q == 0 ? 0 : (uint8_t)(R.body_len >> (8 * (4 - q))); }   // AddGrpcPrefix: flag 0 + BE32 length
-            thread_copy(o + k, body + (at + k - (grpc ? 5u : 0u)), nn - k);
+            if (grpc && at < 5) { k = min(nn, 5u - at); if (lane < k) { const uint32_t q = at + lane; o[lane] = q == 0 ? 0 : (uint8_t)(R.body_len >> (8 * (4 - q))); } }   // AddGrpcPrefix: flag 0 + BE32 length
+            warp_copy(o + k, body + (at + k - (grpc ? 5u : 0u)), nn - k, lane);
             o += nn; at += nn;
         }
-        if (tl) { h2_put_head(o, tl, 1, 0x5, R.stream_id); o += 9; for (uint32_t k = 0; k < tl; k++) *o++ = trailer[k]; }
-        if (c.deferred_window_update > 0) {                       // ReleaseDeferredWindowUpdate
-            const long long cw = c.deferred_window_update; c.deferred_window_update = 0;
-            h2_put_head(o, 4, 8, 0, 0); put_be32(o + 9, (uint32_t)cw); o += 13;
-        }
-        out_lens[i] = (uint32_t)(o - o0);
+        if (tl) { if (lane == 0) h2_put_head(o, tl, 1, 0x5, R.stream_id); for (uint32_t k = lane; k < tl; k += 32) o[9 + k] = trailer[k]; o += 9 + tl; }
+        if (cw) { if (lane == 0) { h2_put_head(o, 4, 8, 0, 0); put_be32(o + 9, cw); } o += 13; }
+        if (lane == 0) out_lens[i] = (uint32_t)(o - o0);
+        __syncwarp();                                                // the shared buffers are reused by the next response
     }
 }
 #endif
