@@ -53,7 +53,7 @@ struct b2_ctx {
     float last_kernel_ms = 0.f; uint32_t last_launches = 0;
     cudaEvent_t ev_first = nullptr, ev_last = nullptr; bool first_pending = true;
     bool profile_stages = false; bool allow_small = true;
-    bool adaptive_tile = false; uint32_t avg_frame = 0;   // tile size follows the message size of the previous batch      // per-stage events only when a harness asks for stage times
+    bool adaptive_tile = false; bool dense = false; uint32_t avg_frame = 0;   // tile size follows the message size of the previous batch      // per-stage events only when a harness asks for stage times
     // small-batch (latency) mode: one compact H2D block, one compact output block, one D2H, one sync
     uint8_t* d_meta = nullptr; uint8_t* h_meta = nullptr;       // [runs | run_tile_base]
     uint8_t* d_small = nullptr; uint8_t* h_small = nullptr;     // [totals | run_status | msgs | resp]
@@ -129,7 +129,11 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     ALLOC(c->d_tiles, sizeof(TileRec) * (size_t)c->max_tiles);
     ALLOC(c->d_tile_base, 4 * (size_t)c->max_tiles);
     ALLOC(c->d_tile_scratch, 12 * (size_t)c->max_tiles);
-    ALLOC(c->d_tile_spec, 4 * (size_t)kSpecK * c->max_tiles);
+    {   // kSpecK offsets per tile; dense mode (tiles >= 2 KiB holding many small frames) keeps kSpecKDense
+        size_t dense_tiles = (size_t)o->max_batch_bytes / 2048 + o->max_runs + 1; if (dense_tiles > c->max_tiles) dense_tiles = c->max_tiles;
+        size_t words = (size_t)kSpecK * c->max_tiles; if ((size_t)kSpecKDense * dense_tiles > words) words = (size_t)kSpecKDense * dense_tiles;
+        ALLOC(c->d_tile_spec, 4 * words);
+    }
     ALLOC(c->d_run_status, sizeof(b2_run_status) * (size_t)o->max_runs);
     ALLOC(c->d_frame_off, 4 * (size_t)o->max_msgs);
     ALLOC(c->d_frame_run, 4 * (size_t)o->max_msgs);
@@ -249,12 +253,16 @@ extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, co
     CU(cudaSetDevice(c->opt.device));
     if (c->adaptive_tile) {
         // like Socket::_avg_msg_size steering the read size (input_messenger.cpp:348-353): a tile should hold
-        // ~8 messages so the speculative entry search reads a small fraction of it
+        // 6-12 messages so the speculative entry search reads a small fraction of it
         uint32_t t = 8192;
-        while (t < (1u << 20) && t < 8u * c->avg_frame) t <<= 1;
+        while (t < (1u << 20) && t < 6u * c->avg_frame) t <<= 1;
         c->cfg.tile_bytes = t; c->cfg.tile_shift = 0; while ((1u << c->cfg.tile_shift) < t) c->cfg.tile_shift++;
     }
     const uint32_t shift = c->cfg.tile_shift, tile = c->cfg.tile_bytes;
+    // small requests (the previous batches' average says a tile holds more than kSpecK frames): k_tile_walk keeps longer offset
+    // lists so that k_frame_table still only copies (a measured 139 -> 29 us for 124-byte frames)
+    c->dense = tile >= 2048 && c->avg_frame && (uint64_t)c->avg_frame * kSpecK < tile;
+    c->cfg.spec_k = c->dense ? kSpecKDense : kSpecK;
     uint64_t nt = 0; uint32_t max_rt = 0;
     for (uint32_t r = 0; r < n_runs; r++) {
         if ((runs[r].offset & 15u) || (uint64_t)runs[r].offset + runs[r].length > nbytes) { set_err("run offset must be 16-aligned and inside the batch"); return B2_E_INVAL; }
@@ -323,7 +331,7 @@ static int launch_pipeline(b2_ctx* c) {
         if (smem > 200 * 1024) smem = 0;
         k_resolve<<<c->n_runs, 256, smem, s>>>(B, C); launches++; mark("resolve");
     }
-    if (c->n_tiles) { k_frame_table<<<(c->n_tiles * kSpecK + 255) / 256, 256, 0, s>>>(B, C); launches++; mark("frame_table"); }
+    if (c->n_tiles) { k_frame_table<<<(uint32_t)(((uint64_t)c->n_tiles * C.spec_k + 255) / 256), 256, 0, s>>>(B, C); launches++; mark("frame_table"); }
     // message-count dependent kernels are persistent: fixed grids (multiples of the SM count)
     // stride over the device-side message count, so no host round trip sizes a launch
     k_decode<<<sms * B2_DECODE_MIN_BLOCKS, kDecodeWarps * 32, 0, s>>>(B, C); launches++; mark("decode");
@@ -447,7 +455,7 @@ extern "C" int b2_batch_download(b2_ctx* c, b2_batch_result* out) {
         int rc = download_normal(c, out);
         if (rc != B2_OK) return rc;
     }
-    if (out->n_msgs) c->avg_frame = (uint32_t)(((uint64_t)c->avg_frame * 3 + c->nbytes / out->n_msgs) / 4);
+    if (out->n_msgs) { const uint32_t now = c->nbytes / out->n_msgs; c->avg_frame = c->avg_frame ? (uint32_t)(((uint64_t)c->avg_frame * 3 + now) / 4) : now; }
     out->kernel_ms = c->last_kernel_ms; out->n_launches = c->last_launches;
     return B2_OK;
 }

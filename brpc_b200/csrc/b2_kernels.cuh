@@ -76,6 +76,7 @@ struct DevConfig {
     uint32_t n_methods;
     uint32_t identity_len;
     uint32_t stream_handler;      // B2_STREAM_*
+    uint32_t spec_k;              // speculative frame offsets kept per tile: kSpecK, or kSpecKDense when tiles hold many small frames
     char identity[64];            // "ip:port" of Controller::AppendServerIdentiy
 };
 
@@ -133,11 +134,12 @@ B2_HD void walk_tile(const uint8_t* run, uint32_t len, uint32_t entry, int pf_in
 }
 struct NoEmit { B2_HD void operator()(uint32_t, const Step&) const {} };
 constexpr uint32_t kSpecK = 16;            // speculative frame offsets kept per tile; tiles with more frames are re-walked by k_frame_table
+constexpr uint32_t kSpecKDense = 128;      // ... when the previous batches say a tile holds more than kSpecK frames (small requests)
 constexpr uint8_t kKindRewalked = 0x80;    // k_resolve re-walked the tile: its speculative offsets are void
 struct EmitSpec {
-    uint32_t* out; uint32_t run_off;
+    uint32_t* out; uint32_t run_off, cap;
     __device__ __forceinline__ void operator()(uint32_t i, const Step& s) const {
-        if (i < kSpecK) out[i] = (run_off + s.frame_pos) | ((uint32_t)(s.index - 1) << 31);
+        if (i < cap) out[i] = (run_off + s.frame_pos) | ((uint32_t)(s.index - 1) << 31);
     }
 };
 
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(128) k_tile_walk(BatchPtrs B, DevConfig C) {
     rec.entry = B.tiles[t].entry; rec.exit = 0; rec.count = 0; rec.kind = kStop; rec.last_proto = 0; rec.live = 0; rec.pf_in = -1;
     if (rec.entry != kNone) {
         // the frame offsets met on the way are kept: if k_resolve accepts the tile as is, k_frame_table only has to copy them
-        EmitSpec e; e.out = B.tile_spec + (size_t)t * kSpecK; e.run_off = run.offset;
+        EmitSpec e; e.out = B.tile_spec + (size_t)t * C.spec_k; e.run_off = run.offset; e.cap = C.spec_k;
         walk_tile<true>(B.bytes + run.offset, run.length, rec.entry, -1, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, rec, e);
     }
     B.tiles[t] = rec;
@@ -430,7 +432,8 @@ struct EmitFrame {
 // its first thread.
 __global__ void __launch_bounds__(256) k_frame_table(BatchPtrs B, DevConfig C) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t t = g / kSpecK, j = g % kSpecK;
+    const uint32_t spec_k = C.spec_k;
+    const uint32_t t = g / spec_k, j = g % spec_k;
     if (t >= B.n_tiles) return;
     const TileRec rec = B.tiles[t];
     if (!rec.live || rec.count == 0) return;
@@ -438,8 +441,8 @@ __global__ void __launch_bounds__(256) k_frame_table(BatchPtrs B, DevConfig C) {
     const uint4 ti = __ldg(B.tile_info + t);
     const uint32_t r = ti.w & 0xffffffu;
     const uint32_t first = B.run_status[r].first_msg + B.tile_base[t];
-    if (!(rec.kind & kKindRewalked) && rec.count <= kSpecK) {
-        if (j < rec.count && first + j < B.max_msgs) { B.frame_off[first + j] = B.tile_spec[(size_t)t * kSpecK + j]; B.frame_run[first + j] = r; }
+    if (!(rec.kind & kKindRewalked) && rec.count <= spec_k) {
+        if (j < rec.count && first + j < B.max_msgs) { B.frame_off[first + j] = B.tile_spec[(size_t)t * spec_k + j]; B.frame_run[first + j] = r; }
         return;
     }
     if (j != 0) return;

@@ -364,3 +364,8 @@ def test_dense_and_sparse_tiles(b2):
             streams.append(b"".join(fr)[:rng.randrange(250_000, 300_000)])
         dev, _ = run_both(b2, ctx, streams, what="dense/sparse tile=%d" % tile)
         assert len(dev[1]) > 20000
+        # the context now knows the average request is small: the second batch takes the warp-staged (dense) tile walk
+        dev2, _ = run_both(b2, ctx, streams[::-1], what="dense/sparse tile=%d, second batch" % tile)
+        assert len(dev2[1]) == len(dev[1])
+        tiny = [b"".join(echo_frame(rng, k, b"r" * rng.choice([0, 1, 16, 64])) for k in range(3000))[:rng.randrange(150_000, 200_000)] for _ in range(16)]
+        run_both(b2, ctx, tiny, what="tiny requests tile=%d" % tile)
