@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 #include "../../brpc_b200/host/input_messenger.h"
+#include "../../brpc_b200/host/h2_messenger.h"
 #include "../../oracle/b2_oracle.h"
 
 #define CHECK(c) do { if (!(c)) { fprintf(stderr, "CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #c); exit(1); } } while (0)
@@ -142,9 +143,101 @@ static void test_messenger_gpu() {
            kSockets, total_msgs, rounds, checked, g_host_msgs);
 }
 
+// ---- h2 / gRPC through GpuH2Messenger, every written byte against the oracle (same chunking fed to both) ----
+static std::string h2_frame(int type, int flags, uint32_t sid, const std::string& payload) {
+    std::string f; const uint32_t n = (uint32_t)payload.size();
+    f.push_back((char)(n >> 16)); f.push_back((char)(n >> 8)); f.push_back((char)n); f.push_back((char)type); f.push_back((char)flags);
+    f.push_back((char)(sid >> 24)); f.push_back((char)(sid >> 16)); f.push_back((char)(sid >> 8)); f.push_back((char)sid);
+    return f + payload;
+}
+static std::string hp_lit(const std::string& n, const std::string& v) {      // literal header field without indexing, new name (RFC 7541 6.2.2)
+    std::string o; o.push_back(0); o.push_back((char)n.size()); o += n; o.push_back((char)v.size()); o += v; return o;
+}
+static int g_h2_host = 0;
+static void H2HostProcess(b2::InputMessageBase* base) { b2::H2Message* m = static_cast<b2::H2Message*>(base); CHECK(!m->headers.empty()); g_h2_host++; delete m; }
+
+static void test_h2_messenger_gpu() {
+    b2_options opt; memset(&opt, 0, sizeof opt);
+    opt.device = 0; opt.max_batch_bytes = 8 << 20; opt.max_msgs = 1 << 14; opt.max_runs = 64; opt.max_resp_bytes = 32 << 20;
+    b2::GpuH2Messenger messenger(opt);
+    b2_method echo = { "example.EchoService", "EchoService", "Echo", "example.EchoRequest", B2_HANDLER_ECHO, 1, 0, 0 };
+    CHECK(messenger.AddMethod(echo) == 0);
+    messenger.SetHostProcess(H2HostProcess);
+    const int kConns = 6, kCalls = 12;
+    std::vector<std::string> streams(kConns);
+    for (int c = 0; c < kConns; c++) {
+        std::string& st = streams[c];
+        st = "PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n"; st += h2_frame(4, 0, 0, "");
+        for (int k = 0; k < kCalls; k++) {
+            const uint32_t sid = 1 + 2 * k;
+            const bool other = (c == 2 && k % 4 == 1);                               // not a device-served method: goes to the host callback
+            std::string hb = hp_lit(":method", "POST") + hp_lit(":scheme", "http") + hp_lit(":path", other ? "/example.Other/Call" : "/example.EchoService/Echo") +
+                             hp_lit("content-type", k % 3 == 0 ? "application/grpc+proto" : "application/grpc") + hp_lit("te", "trailers");
+            std::string msg(10 + 37 * k + (k == 8 ? 9000 : 0), (char)('a' + k));
+            std::string pb = "\x0a"; { uint32_t n = (uint32_t)msg.size(); while (n >= 0x80) { pb.push_back((char)(n | 0x80)); n >>= 7; } pb.push_back((char)n); } pb += msg;
+            std::string body; body.push_back(0); body.push_back((char)(pb.size() >> 24)); body.push_back((char)(pb.size() >> 16)); body.push_back((char)(pb.size() >> 8)); body.push_back((char)pb.size()); body += pb;
+            st += h2_frame(1, 0x4, sid, hb);
+            if (k % 5 == 2) { st += h2_frame(0, 0, sid, body.substr(0, 7)); st += h2_frame(0, 0x1, sid, body.substr(7)); }     // two DATA frames: body assembled in the slot
+            else if (body.size() > 8000) { st += h2_frame(0, 0, sid, body.substr(0, 5000)); st += h2_frame(0, 0x1, sid, body.substr(5000)); }   // (device limit: 12 KiB per unfinished stream)
+            else st += h2_frame(0, 0x1, sid, body);
+            if (k % 4 == 3) st += h2_frame(6, 0, 0, "pingpong");
+            if (k % 6 == 5) st += h2_frame(8, 0, 0, std::string("\x00\x01\x00\x00", 4));
+        }
+    }
+    std::vector<b2::Socket*> socks; std::vector<size_t> pos(kConns, 0);
+    std::vector<orc_h2_conn*> oc(kConns); std::vector<std::string> obuf(kConns), expect(kConns);
+    for (int c = 0; c < kConns; c++) { socks.push_back(messenger.AddConnection(500 + c)); oc[c] = orc_h2_conn_new(); }
+    orc_config cfg; memset(&cfg, 0, sizeof cfg); b2_method ms[1] = { echo }; cfg.methods = ms; cfg.n_methods = 1;
+    unsigned seed = 777; int rounds = 0, total = 0;
+    std::vector<b2_h2_msg> om(256); std::vector<uint8_t> octrl(1 << 16), oblob(1 << 20), opack(1 << 18);
+    for (bool more = true; more; rounds++) {
+        more = false;
+        for (int c = 0; c < kConns; c++) {
+            seed = seed * 1103515245u + 12345u;
+            const size_t n = std::min(streams[c].size() - pos[c], (size_t)(seed >> 16) % 5000);
+            socks[c]->_read_buf.append(streams[c].data() + pos[c], n); obuf[c].append(streams[c].data() + pos[c], n); pos[c] += n;
+            if (pos[c] < streams[c].size()) more = true;
+        }
+        const int n = messenger.ProcessNewMessages(socks);
+        CHECK(n >= 0); total += n;
+        for (int c = 0; c < kConns; c++) {                       // the same round through the oracle
+            if (obuf[c].empty()) continue;
+            uint32_t cons = 0, nm = 0, cl = 0, bl = 0, mfs = 0, sws = 0;
+            const uint32_t err = orc_h2_consume(oc[c], &cfg, (const uint8_t*)obuf[c].data(), (uint32_t)obuf[c].size(), &cons, om.data(), 256, &nm,
+                                                octrl.data(), (uint32_t)octrl.size(), &cl, oblob.data(), (uint32_t)oblob.size(), &bl, &mfs, &sws);
+            CHECK(err == B2_PARSE_ERROR_NOT_ENOUGH_DATA);
+            expect[c].append((const char*)octrl.data(), cl);
+            for (uint32_t k = 0; k < nm; k++) {
+                if (om[k].method_idx != 0) continue;            // the host callback's business
+                std::string ct;
+                for (uint32_t q = 0; q < om[k].headers_len;) {
+                    const uint8_t* p = oblob.data() + om[k].headers_off + q; const uint32_t nl = p[0] | (p[1] << 8), vl = p[2] | (p[3] << 8);
+                    if (nl == 12 && memcmp(p + 4, "content-type", 12) == 0) ct.assign((const char*)p + 4 + nl, vl);
+                    q += 4 + nl + vl;
+                }
+                std::string blob = ct + std::string((const char*)oblob.data() + om[k].msg_off, om[k].msg_len);
+                b2_h2_response r; memset(&r, 0, sizeof r);
+                r.stream_id = om[k].stream_id; r.status_code = 200; r.flags = B2_H2_RESP_GRPC; r.content_type_len = (uint32_t)ct.size();
+                r.body_off = (uint32_t)ct.size(); r.body_len = om[k].msg_len;
+                const uint32_t pn = orc_h2_pack_response(oc[c], &r, (const uint8_t*)blob.data(), opack.data());
+                expect[c].append((const char*)opack.data(), pn);
+            }
+            obuf[c].erase(0, cons);
+        }
+    }
+    for (int c = 0; c < kConns; c++) {
+        CHECK(!socks[c]->Failed() && socks[c]->_read_buf.length() == obuf[c].size());
+        CHECK(socks[c]->_write_buf.length() == expect[c].size());
+        CHECK(socks[c]->_write_buf.to_string() == expect[c]);
+        orc_h2_conn_free(oc[c]);
+    }
+    CHECK(total == kConns * kCalls && g_h2_host == 3);
+    printf("h2 messenger ok: %d connections, %d gRPC calls in %d rounds, every written byte identical to the oracle, %d host-handled\n", kConns, total, rounds, g_h2_host);
+}
+
 int main(int argc, char** argv) {
     const std::string mode = argc > 1 ? argv[1] : "cpu";
     test_iobuf();
-    if (mode == "gpu") test_messenger_gpu();
+    if (mode == "gpu") { test_messenger_gpu(); test_h2_messenger_gpu(); }
     return 0;
 }
