@@ -360,11 +360,11 @@ int  b2_hpack_decode_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes, cons
  *                         u16 value_len, name, value — every decoded field in order) and the concatenated DATA
  *                         payloads live in out.
  * Device limits (the reference has none): B2_H2_MAX_PENDING concurrent streams per connection and
- * B2_H2_STREAM_BYTES (4 KiB header records + 12 KiB body) per unfinished stream; beyond them the run ends with
+ * B2_H2_STREAM_BYTES (4 KiB header records + 64 KiB body) per unfinished stream whose body spans several DATA frames; beyond them the run ends with
  * B2_PARSE_ERROR_NO_RESOURCE (the host takes the connection over or closes it, input_messenger.cpp:227-239). */
 #define B2_H2_MAX_CONNS 1024
 #define B2_H2_MAX_PENDING 8
-#define B2_H2_STREAM_BYTES 16384
+#define B2_H2_STREAM_BYTES 69632
 #define B2_H2_HEADER_BYTES 4096
 #define B2_H2_FLAG_GRPC            1u   /* content-type is application/grpc[+...] (is_grpc_ct) */
 #define B2_H2_FLAG_GRPC_PREFIX_OK  2u   /* RemoveGrpcPrefix succeeded: msg_off/msg_len are valid */

@@ -111,7 +111,7 @@ def request_frames(rng, enc, sid, path=b"/example.EchoService/Echo", message=b"h
     else:
         out.append(_headers(rng, sid, b"".join(fields), end_headers=True, end_stream=end_on_headers, pad=pad, priority=priority))
     if not end_on_headers:
-        chunk = chunk or rng.choice([len(body) or 1, 64, 1000, 4000])
+        chunk = min(chunk or rng.choice([len(body) or 1, 64, 1000, 4000]), 16000)      # a frame (with padding) never exceeds the default max_frame_size
         pieces = [body[i:i + chunk] for i in range(0, len(body), chunk)] or [b""]
         for j, pc in enumerate(pieces):
             last = j == len(pieces) - 1
@@ -144,7 +144,7 @@ def connection_script(rng, n_calls=12, violations=0.0, max_open=4):
     pending = []                                   # frames of calls whose emission is interleaved
     rnd62 = b"abcdefghijklmnopqrstuvwxyz0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ"
     for call in range(n_calls):
-        msg = bytes(rng.choice(rnd62) for _ in range(rng.choice([0, 5, 100, 1024, 4096, 9000])))
+        msg = bytes(rng.choice(rnd62) for _ in range(rng.choice([0, 5, 100, 1024, 4096, 9000, 30000])))
         kind = rng.random()
         kw = dict(split_headers=rng.random() < 0.3, pad=rng.random() < 0.3, priority=rng.random() < 0.2, trailers=rng.random() < 0.15)
         if kind < 0.08:

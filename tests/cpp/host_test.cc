@@ -178,7 +178,7 @@ static void test_h2_messenger_gpu() {
             std::string body; body.push_back(0); body.push_back((char)(pb.size() >> 24)); body.push_back((char)(pb.size() >> 16)); body.push_back((char)(pb.size() >> 8)); body.push_back((char)pb.size()); body += pb;
             st += h2_frame(1, 0x4, sid, hb);
             if (k % 5 == 2) { st += h2_frame(0, 0, sid, body.substr(0, 7)); st += h2_frame(0, 0x1, sid, body.substr(7)); }     // two DATA frames: body assembled in the slot
-            else if (body.size() > 8000) { st += h2_frame(0, 0, sid, body.substr(0, 5000)); st += h2_frame(0, 0x1, sid, body.substr(5000)); }   // (device limit: 12 KiB per unfinished stream)
+            else if (body.size() > 8000) { st += h2_frame(0, 0, sid, body.substr(0, 5000)); st += h2_frame(0, 0x1, sid, body.substr(5000)); }
             else st += h2_frame(0, 0x1, sid, body);
             if (k % 4 == 3) st += h2_frame(6, 0, 0, "pingpong");
             if (k % 6 == 5) st += h2_frame(8, 0, 0, std::string("\x00\x01\x00\x00", 4));

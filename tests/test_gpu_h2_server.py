@@ -39,7 +39,7 @@ def _run(n_conns, n_calls, violations, seed, step_choices):
             buf[i] += streams[i][fed[i]:fed[i] + k]; fed[i] += k
         data, runs = brpc_b200.make_runs([buf[i] for i in batch])
         runs["socket_id"] = np.array(batch, dtype=np.uint64)
-        rs, msgs, out = ctx.h2_process_batch(data, runs)
+        rs, msgs, out = ctx.h2_process_batch(data, runs, out_cap=len(batch) * (512 << 10))
         for j, i in enumerate(batch):
             e, cons, omsgs, octrl, oblob, mfs, sws = orc[i].consume(buf[i])
             st = rs[j]
@@ -76,7 +76,7 @@ def test_device_limits_end_the_run_with_no_resource():
     ctx.h2_conn_reset(0); ctx.h2_conn_reset(1)
     many = T.PREFACE + b"".join(T.request_frames(rng, enc, 1 + 2 * k, message=b"m")[0] for k in range(12))     # 12 HEADERS, no END_STREAM
     enc2 = T.HpackEncoder(rng)
-    big = T.PREFACE + b"".join(T.request_frames(rng, enc2, 1, message=b"z" * 14000, chunk=4000))
+    big = T.PREFACE + b"".join(T.request_frames(rng, enc2, 1, message=b"z" * 70000, chunk=9000))
     data, runs = brpc_b200.make_runs([many, big])
     rs, msgs, out = ctx.h2_process_batch(data, runs)
     assert list(rs["parse_error"]) == [4, 4] and len(msgs) == 0
