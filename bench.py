@@ -481,7 +481,7 @@ def main():
                 "runs cut mid-frame; batch %d MiB > L2 (no flush needed)" % (args.payload, N_SOCKETS, args.run_mib, N_SOCKETS * args.run_mib))
     config = {"workload": workload, "payload_bytes": args.payload, "request_checksum": args.checksum, "connections_per_gpu": N_SOCKETS,
               "run_mib": args.run_mib, "l2": "inputs larger than L2", "pipeline_depth": args.pipeline, "sharding": "socket_id %% %d" % max(1, world),
-              "host": "each rank pinned to its GPU's NUMA node" if world > 1 else "single rank"}
+              "host": "each rank pinned to its GPU's NUMA node"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -512,7 +512,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank if use_dist else 0
     torch.cuda.set_device(dev)
-    numa_cpus = pin_to_gpu_numa(dev) if use_dist else 0
+    numa_cpus = pin_to_gpu_numa(dev)        # pinned buffers are allocated (first touched) on the GPU's own NUMA node
 
     buf, data, runs, n_full, nbytes = build_batch(args.run_mib, rank, payload=args.payload, checksum=args.checksum, kind=args.payload_kind)
     ctx = brpc_b200.Context(device=dev, max_batch_bytes=nbytes + (1 << 20), max_msgs=n_full + 4096,
