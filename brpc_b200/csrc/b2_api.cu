@@ -181,7 +181,8 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     }
     CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(k_pack_slow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * kSnapRing)));
-    CU(cudaFuncSetAttribute(k_pack_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PackWarpSmem) * kPackWarps)));
+    CU(cudaFuncSetAttribute(k_pack_tma<kPackGroup>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PackWarpSmem) * kPackWarps)));
+    CU(cudaFuncSetAttribute(k_pack_tma<kPackGroupSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PackWarpSmem) * kPackWarps)));
     if (const char* e = getenv("B2_PACK")) c->use_tma_pack = strcmp(e, "reg") != 0;
     if (const char* e = getenv("B2_SMALL")) c->use_fused_small = strcmp(e, "off") != 0;
     CU(cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
@@ -342,7 +343,12 @@ static int launch_pipeline(b2_ctx* c) {
     if (c->use_tma_pack) {
         // k_pack_slow first: its verify pass decides which CRC-carrying echoes k_pack_tma may move
         if (mask & 4) { k_pack_slow<<<sms * B2_SLOW_MIN_BLOCKS, 256, 8 * kSnapRing, s>>>(B, C); launches++; mark("pack_slow"); }
-        if (mask & 2) { k_pack_tma<<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C); launches++; mark("pack"); }
+        if (mask & 2) {
+            // small requests: 32 messages per warp round instead of 8 (measured +30 % at 64 B payloads, -3 % at 1 KB)
+            if (c->avg_frame && c->avg_frame < 640) k_pack_tma<kPackGroupSmall><<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C);
+            else k_pack_tma<kPackGroup><<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C);
+            launches++; mark("pack");
+        }
     } else { k_pack<<<sms * B2_PACK_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack"); }
     if (!prof) { c->stage_names[0] = "pipeline"; cudaEventRecord(c->ev[1], s); st = 1; }
     c->n_stages = st; c->last_launches = launches;

@@ -1538,7 +1538,8 @@ constexpr uint32_t kPackWarps = B2_PACK_WARPS;
 #ifndef B2_STAGE_BYTES
 #define B2_STAGE_BYTES 9216
 #endif
-constexpr uint32_t kPackGroup = B2_PACK_GROUP;    // messages per warp round (one lane each), power of two
+constexpr uint32_t kPackGroup = B2_PACK_GROUP;    // messages per warp round (one lane each), power of two: replies of 1 KB and more
+constexpr uint32_t kPackGroupSmall = 32;          // ... and when the average request is small (more messages per barrier round)
 constexpr uint32_t kStageBytes = B2_STAGE_BYTES;  // per buffer, two buffers per warp
 struct PackWarpSmem {
     alignas(128) uint8_t stage[2][kStageBytes];
@@ -1574,6 +1575,7 @@ template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.
 // 16-byte aligned remainder of the payload) into one staging slot and one TMA bulk store of
 // the whole slot.  Lane l of a warp owns message base+l of the round; two staging buffers per
 // warp keep one round's stores draining while the next round's loads are in flight.
+template <uint32_t kGroup>
 __global__ void __launch_bounds__(kPackWarps * 32, 1) k_pack_tma(BatchPtrs B, DevConfig C) {
     extern __shared__ __align__(128) uint8_t pack_smem_raw[];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1585,15 +1587,15 @@ __global__ void __launch_bounds__(kPackWarps * 32, 1) k_pack_tma(BatchPtrs B, De
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    const uint32_t stride = gridDim.x * kPackWarps * kPackGroup;
+    const uint32_t stride = gridDim.x * kPackWarps * kGroup;
     uint32_t it = 0, phase0 = 0, phase1 = 0;        // mbarrier phases advance only in rounds that arm them
     PackJob job; job.fast = 0; job.slot_len = 0; job.head_len = 0; job.bulk_len = 0; job.src_off = 0; job.pad = 0;
     uint32_t slot_off = 0;
-    uint32_t base = (blockIdx.x * kPackWarps + wid) * kPackGroup;
+    uint32_t base = (blockIdx.x * kPackWarps + wid) * kGroup;
     auto fetch = [&](uint32_t bse, PackJob& j, uint32_t& so) {
         const uint32_t i = bse + lane;
         j.fast = 0; j.slot_len = 0;
-        if (lane < kPackGroup && i < n_msgs) {
+        if (lane < kGroup && i < n_msgs) {
             const uint4 v = __ldg(reinterpret_cast<const uint4*>(B.jobs + i));
             j = *reinterpret_cast<const PackJob*>(&v);
             so = B.slot[i] + B.scan_tmp[i / (kScanBlock * kScanItems)];
@@ -1647,12 +1649,12 @@ __global__ void __launch_bounds__(kPackWarps * 32, 1) k_pack_tma(BatchPtrs B, De
             const bool mine = (pending >> lane) & 1u;
             uint32_t need = mine ? job.slot_len : 0, incl = need;
             #pragma unroll
-            for (int d = 1; d < (int)kPackGroup; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += y; }
+            for (int d = 1; d < (int)kGroup; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += y; }
             const bool take = mine && incl <= kStageBytes;
             const uint32_t soff = incl - need;
             uint32_t tx = take ? (uint32_t)job.head_len + job.bulk_len : 0;
             #pragma unroll
-            for (int d = 1; d < (int)kPackGroup; d <<= 1) tx += __shfl_xor_sync(0xffffffffu, tx, d);
+            for (int d = 1; d < (int)kGroup; d <<= 1) tx += __shfl_xor_sync(0xffffffffu, tx, d);
             tx = __shfl_sync(0xffffffffu, tx, 0);
             begin_round(b);
             if (lane == 0) mbar_arrive_expect_tx(&S.mbar[b], tx);
