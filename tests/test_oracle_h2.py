@@ -103,3 +103,24 @@ def test_grpc_response_bytes_first_and_later_calls():
     # connection window exhausted: RST_STREAM(FLOW_CONTROL_ERROR) instead of the response (:1706-1712)
     c3 = O.H2Conn(); c3.consume(T.PREFACE + T.settings())
     assert c3.pack_response(1, b"y" * 70000) == bytes.fromhex("000004030000000001" "00000003")
+
+
+def test_settings_case_of_the_reference_unit_test():
+    """test/brpc_http_rpc_protocol_unittest.cpp:1382-1412 (HttpTest.http2_settings): a SETTINGS frame serialized from
+    H2Settings{header_table_size 8192, max_concurrent_streams 1024, stream_window_size 2^29-1} is answered with exactly one
+    9-byte SETTINGS frame, flags ACK, stream 0, and the remote settings take the values.  SerializeH2Settings (:213-250)
+    writes the non-default fields in id order; enable_push=false differs from DEFAULT_ENABLE_PUSH, so id 2 is present."""
+    frame = T.settings([(1, 8192), (2, 0), (3, 1024), (4, (1 << 29) - 1)])
+    assert len(frame) == 9 + 24
+    c = O.H2Conn()
+    c.consume(T.PREFACE)                                   # the unit test forces H2_CONNECTION_READY; here the preface does
+    err, cons, msgs, ctrl, blob, mfs, sws = c.consume(frame)
+    assert (err, cons, len(msgs)) == (2, len(frame), 0)
+    assert ctrl == ACK and ctrl[3] == 4 and ctrl[4] == 1 and ctrl[5:9] == b"\x00\x00\x00\x00"
+    assert sws == (1 << 29) - 1 and mfs == 16384
+    # max_frame_size outside [DEFAULT_MAX_FRAME_SIZE, MAX_OF_MAX_FRAME_SIZE] is invalid (ParseH2Settings :193-199, the bounds
+    # HttpTest.http2_invalid_settings checks on the server options): connection error, GOAWAY(PROTOCOL_ERROR)
+    for bad in (16383, 16777216):
+        c2 = O.H2Conn(); c2.consume(T.PREFACE)
+        err, cons, msgs, ctrl, *_ = c2.consume(T.settings([(5, bad)]))
+        assert ctrl == bytes.fromhex("000008070000000000" "ffffffff" "00000001")
