@@ -527,7 +527,10 @@ __host__ __device__ __forceinline__ uint32_t snappy_max_compressed_length(uint32
 // k_decode stages the first kRowBytes of every frame (header + RpcMeta + first body bytes) in
 // shared memory with coalesced 4-byte loads (one row per lane) and decodes from there; the head
 // records are assembled in shared memory and leave with coalesced 16-byte stores.
-constexpr uint32_t kRowBytes = 160, kRowVecs = kRowBytes / 16;
+#ifndef B2_ROW_BYTES
+#define B2_ROW_BYTES 160
+#endif
+constexpr uint32_t kRowBytes = B2_ROW_BYTES, kRowVecs = kRowBytes / 16;
 constexpr uint32_t kDecodeWarps = 4;
 #ifndef B2_DECODE_MIN_BLOCKS
 #define B2_DECODE_MIN_BLOCKS 6
