@@ -237,6 +237,51 @@ __global__ void __launch_bounds__(256, 6) k_tile_search(BatchPtrs B, DevConfig C
     if (lane == 0) B.tiles[warp].entry = entry;
 }
 
+// The speculative walk of k_tile_walk: same result as walk_tile<true>, but (1) a step whose twelve header bytes show a known
+// magic and sane sizes is decided from registers (the generic CutInputMessage restatement is called for everything else:
+// short tails, oversize bodies, meta > body, unknown bytes), and (2) while the header at `pos` is still on its way from
+// DRAM the header at pos + (length of the previous frame) is requested too — requests of one connection tend to repeat
+// their size, so the dependent chain "header -> next position -> header" often advances two frames per round trip.
+struct HdrWords { uint32_t w0, w1, w2, w3; };
+__device__ __forceinline__ HdrWords load_hdr_words(const uint8_t* p) {          // the 16 aligned-ish bytes around p (buffer is padded)
+    const uint32_t* q = reinterpret_cast<const uint32_t*>((uintptr_t)p & ~(uintptr_t)3);
+    HdrWords h; h.w0 = __ldg(q); h.w1 = __ldg(q + 1); h.w2 = __ldg(q + 2); h.w3 = __ldg(q + 3);
+    return h;
+}
+template <typename Emit>
+__device__ __forceinline__ void walk_tile_spec(const uint8_t* run, uint32_t len, uint32_t entry, uint32_t tile_end,
+                                               uint64_t max_body, bool client, TileRec& t, Emit emit) {
+    uint32_t pos = entry, count = 0, prev_len = 0, pre_pos = kNone;
+    int pf = -1, last = 0;
+    uint8_t kind = kRanOff;
+    HdrWords pre; pre.w0 = pre.w1 = pre.w2 = pre.w3 = 0;
+    while (pos < tile_end) {
+        Step s;
+        bool fast = false;
+        if (len - pos >= 12) {
+            const HdrWords h = pre_pos == pos ? pre : load_hdr_words(run + pos);
+            const uint32_t guess = pos + prev_len;
+            if (prev_len && guess < tile_end && len - guess >= 12) { pre = load_hdr_words(run + guess); pre_pos = guess; }   // in flight while h is used
+            else pre_pos = kNone;
+            const uint32_t sh = 8u * (pos & 3u);                      // run offsets are 16-byte aligned: alignment of run + pos is pos & 3
+            const uint32_t h0 = sh ? __funnelshift_r(h.w0, h.w1, sh) : h.w0, h1 = sh ? __funnelshift_r(h.w1, h.w2, sh) : h.w1,
+                           h2 = sh ? __funnelshift_r(h.w2, h.w3, sh) : h.w2;
+            const int idx = h0 == kMagicPRPC ? 1 : h0 == kMagicSTRM ? 2 : 0;
+            const uint32_t body = __byte_perm(h1, 0, 0x0123), meta = __byte_perm(h2, 0, 0x0123);
+            if (idx && (uint64_t)body <= max_body && (uint64_t)(len - pos) >= 12ull + body && meta <= body) {
+                s.err = B2_PARSE_OK; s.index = idx; s.pf = idx; s.frame_pos = pos; s.new_pos = pos + 12 + body; s.body = body; s.meta = meta; s.popped = false;
+                fast = true;
+            }
+        }
+        if (!fast) s = cut_input_message(run, len, pos, pf, max_body, client);
+        if (count == 0 && s.popped) { kind = kAmbig; break; }
+        if (s.err != B2_PARSE_OK) { kind = kStop; break; }
+        emit(count, s);
+        count++; last = s.index; pf = s.index; prev_len = s.new_pos - pos; pos = s.new_pos;
+    }
+    t.entry = entry; t.exit = pos; t.count = count; t.kind = kind; t.last_proto = (int8_t)last;
+}
+
 // --- k_tile_walk: one thread per tile ---------------------------------------
 __global__ void __launch_bounds__(128) k_tile_walk(BatchPtrs B, DevConfig C) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -249,7 +294,7 @@ __global__ void __launch_bounds__(128) k_tile_walk(BatchPtrs B, DevConfig C) {
     if (rec.entry != kNone) {
         // the frame offsets met on the way are kept: if k_resolve accepts the tile as is, k_frame_table only has to copy them
         EmitSpec e; e.out = B.tile_spec + (size_t)t * C.spec_k; e.run_off = run.offset; e.cap = C.spec_k;
-        walk_tile<true>(B.bytes + run.offset, run.length, rec.entry, -1, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, rec, e);
+        walk_tile_spec(B.bytes + run.offset, run.length, rec.entry, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, rec, e);
     }
     B.tiles[t] = rec;
 }
