@@ -151,6 +151,9 @@ __device__ __forceinline__ uint32_t find_run(const uint32_t* base, uint32_t n_ru
     return lo;
 }
 __device__ __forceinline__ bool is_magic(uint32_t w) { return w == kMagicPRPC || w == kMagicSTRM; }
+#ifndef B2_SEARCH_FIRST
+#define B2_SEARCH_FIRST 2
+#endif
 
 // --- k_tile_search: one warp per tile ---------------------------------------
 // Finds the first position p in the tile where a frame of either protocol parses
@@ -171,8 +174,8 @@ __global__ void __launch_bounds__(256, 6) k_tile_search(BatchPtrs B, DevConfig C
         const uint32_t t0 = k << C.tile_shift;
         const uint32_t t1 = min(t0 + C.tile_bytes, len);
         // four 512-byte windows per trip: all eight loads of a lane are issued before the first use
-        for (uint32_t c0 = t0; c0 < t1 && entry == kNone; c0 += (c0 == t0 ? 512u : 2048u)) {
-            const int nwin = c0 == t0 ? 1 : 4;      // the first 512-byte window usually holds the entry; later trips go 4 wide
+        for (uint32_t c0 = t0; c0 < t1 && entry == kNone; c0 += (c0 == t0 ? 512u * B2_SEARCH_FIRST : 2048u)) {
+            const int nwin = c0 == t0 ? B2_SEARCH_FIRST : 4;      // the first trip (B2_SEARCH_FIRST x 512 bytes) usually holds the entry; later trips go 4 wide
             uint4 v[4]; uint32_t nx[4];
             #pragma unroll
             for (int u = 0; u < 4; u++) {
