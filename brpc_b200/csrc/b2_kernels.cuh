@@ -1715,12 +1715,25 @@ __global__ void __launch_bounds__(kPackWarps * 32, 1) k_pack_tma(BatchPtrs B, De
                 if (job.bulk_len) bulk_g2s(stage + soff + job.head_len, B.bytes + job.src_off, job.bulk_len, &S.mbar[b]);
             }
             wait_round(b);
-            if (take) {
+            const uint32_t took = __ballot_sync(0xffffffffu, take);
+            if (kGroup > 8) {
+                // small replies: the slots of consecutive messages are adjacent in resp, and so are their images in the staging
+                // buffer when the taken lanes form one unbroken range — then ONE bulk store moves the whole round
+                const uint32_t lo = __ffs(took) - 1, span = took >> lo;
+                const bool contiguous = took && (span & (span + 1)) == 0;          // took == 0..0 1..1 0..0
+                uint32_t total = take ? job.slot_len : 0;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+                // (adjacency in resp also needs every taken message's slot to follow its left neighbour's: true for consecutive messages)
+                if (contiguous) { if (lane == lo) bulk_s2g(B.resp + slot_off, stage + soff, total); }
+                else if (take) bulk_s2g(B.resp + slot_off, stage + soff, job.slot_len);
+                if (take) B.msgs[base + lane].resp_off = slot_off + job.pad;
+            } else if (take) {
                 bulk_s2g(B.resp + slot_off, stage + soff, job.slot_len);
                 B.msgs[base + lane].resp_off = slot_off + job.pad;
             }
             bulk_commit();
-            pending &= ~__ballot_sync(0xffffffffu, take);
+            pending &= ~took;
         }
         job = njob; slot_off = nslot;
     }
