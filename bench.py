@@ -115,7 +115,8 @@ def ncu_traffic(kernel, args):
         w = cap["workload"]
         if (w["payload_bytes"], w["run_mib"], w["connections"]) != (args.payload, args.run_mib, N_SOCKETS) or args.checksum or args.payload_kind:
             return None
-        k = cap["kernels"].get(kernel) or cap["kernels"].get(kernel + "_tma")
+        ks = {n.replace("void ", "").split("<")[0].strip(): v for n, v in cap["kernels"].items()}
+        k = ks.get(kernel) or ks.get(kernel + "_tma")
         return None if k is None else (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6
     except Exception:
         return None
