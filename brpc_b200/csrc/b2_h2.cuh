@@ -3,8 +3,8 @@
 //   HPACK decode    <- HPacker::Decode               src/brpc/details/hpack.cpp:765-843 (+ :531-635, :403-473, :72-229)
 // Both are per-connection serial state machines (frame chain; dynamic table), so the unit of
 // parallelism is the connection: one thread per connection, thousands of connections per batch.
-// The h2 stream state machine, SETTINGS/WINDOW_UPDATE/GOAWAY side effects and response framing
-// stay on the host (SURVEY §8a "parity-critical details").
+// Further down: the whole server side of ParseH2Message (k_h2_consume: stream state machine, SETTINGS / WINDOW_UPDATE /
+// GOAWAY side effects as the bytes to write back) and the reply framing with HPACK encoding (k_h2_pack).
 #pragma once
 #include <cuda_runtime.h>
 #include "b2_core.cuh"

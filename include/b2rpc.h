@@ -323,7 +323,7 @@ typedef struct b2_request {
 int  b2_pack_requests(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_request* reqs, uint32_t n,
                       void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens);
 
-/* ---- h2 / gRPC building blocks (the stream state machine stays on the host) -----
+/* ---- h2 / gRPC: leaf calls first, then the whole server-side parser and the reply framing -----
  * b2_h2_scan_batch: H2Context::ConsumeFrameHead (src/brpc/policy/http2_rpc_protocol.cpp:438-465)
  * chained over every connection run.  runs[i].flags & B2_RUN_H2_PREFACE: the run starts a server-side
  * connection, the 24-byte client preface (:119-120, :469-479) is checked and skipped first.
