@@ -123,7 +123,9 @@ struct Reader { const uint8_t* p; const uint8_t* end; };
 B2_HD bool rd_varint(Reader& r, uint64_t& out) {       // VarintParse<uint64_t>: <= 10 bytes
     if (r.p < r.end && *r.p < 0x80) { out = *r.p++; return true; }
     uint64_t v = 0;
+#if defined(__CUDA_ARCH__)
     #pragma unroll 1
+#endif
     for (int i = 0; i < 10; i++) {
         if (r.p >= r.end) return false;
         const uint8_t b = *r.p++;
@@ -135,7 +137,9 @@ B2_HD bool rd_varint(Reader& r, uint64_t& out) {       // VarintParse<uint64_t>:
 B2_HD bool rd_tag(Reader& r, uint32_t& tag) {           // ReadTag: <= 5 bytes
     if (r.p < r.end && *r.p < 0x80) { tag = *r.p++; return true; }
     uint32_t v = 0;
+#if defined(__CUDA_ARCH__)
     #pragma unroll 1
+#endif
     for (int i = 0; i < 5; i++) {
         if (r.p >= r.end) return false;
         const uint8_t b = *r.p++;
@@ -151,7 +155,9 @@ B2_HD bool rd_size(Reader& r, uint32_t& n) {            // ReadSize: <= 5 bytes,
         n = v1; return true;
     }
     uint32_t v = 0;
+#if defined(__CUDA_ARCH__)
     #pragma unroll 1
+#endif
     for (int i = 0; i < 5; i++) {
         if (r.p >= r.end) return false;
         const uint8_t b = *r.p++;

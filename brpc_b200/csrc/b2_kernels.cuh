@@ -1845,7 +1845,6 @@ __global__ void __launch_bounds__(256) k_pack_requests(const uint8_t* bytes, con
 #endif
 __global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs B, DevConfig C) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t n_msgs = B.totals[0];
     if (B.totals[2] & 3u) return;
     finalize_runs(B);                                  // (was a separate launch)
     const uint32_t n_verify = B.totals[7];
