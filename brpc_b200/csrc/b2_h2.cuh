@@ -504,7 +504,8 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
         switch (type) {
         case 0: {                                                    // ---- OnData (:700-723) + H2StreamContext::OnData (:725-779)
             uint32_t frag = length, padl = 0;
-            if (flags & 0x8) { frag--; padl = pl[used++]; }          // (a zero-length padded frame underflows like the reference's uint32)
+            if ((flags & 0x8) && length == 0) { res = h2_err(6); break; }   // no room for the pad-length byte (the reference would read past the frame)
+            if (flags & 0x8) { frag--; padl = pl[used++]; }
             if (frag < padl) { res = h2_err(6); break; }
             frag -= padl;
             const int k = h2_find(c, sid);

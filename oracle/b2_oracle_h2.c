@@ -249,6 +249,7 @@ uint32_t orc_h2_consume(orc_h2_conn* c, const orc_config* cfg, const uint8_t* in
         switch (type) {
         case 0: {                                                    /* OnData :700-779 */
             uint32_t frag = length, padl = 0;
+            if ((flags & 0x8) && length == 0) { res = res_err(6, 0); break; }   /* deviation: the reference reads the pad length past the frame */
             if (flags & 0x8) { frag--; padl = pl[used++]; }
             if (frag < padl) { res = res_err(6, 0); break; }
             frag -= padl;

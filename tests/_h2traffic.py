@@ -180,7 +180,7 @@ def connection_script(rng, n_calls=12, violations=0.0, max_open=4):
             out.extend(fr[:rng.randrange(1, len(fr))]); out.append(frame(3, 0, sid, (8).to_bytes(4, "big"))); sid += 2
         elif r < 0.29: out.append(frame(7, 0, 0, (sid).to_bytes(4, "big") + (0).to_bytes(4, "big") + b"bye"))
         if violations and rng.random() < violations:
-            v = rng.randrange(12)
+            v = rng.randrange(13)
             if v == 0: out.append(frame(2, 0, 1, bytes(5)))                                        # PRIORITY -> GOAWAY, payload left unread
             elif v == 1: out.append(frame(0, 0x1, sid + 100, b"stray"))                            # DATA on an unknown stream
             elif v == 2: out.append(frame(6, 0x1, 0, bytes(8)))                                    # PING ack: payload left unread
@@ -193,6 +193,7 @@ def connection_script(rng, n_calls=12, violations=0.0, max_open=4):
             elif v == 9: out.append(frame(4, 0, 0, (2).to_bytes(2, "big") + (7).to_bytes(4, "big")))   # ENABLE_PUSH = 7
             elif v == 10: out.append(frame(5, 0, 1, b""))                                           # PUSH_PROMISE
             elif v == 11: out.append(frame(1, 0x5, sid, b"\x83\xbe")); sid += 2                    # index past the table
+            elif v == 12: out.append(frame(0, 0x8, max(1, sid - 2), b""))                           # PADDED DATA with no room for the pad length
     for fr in pending:
         out.extend(fr)
     return out
