@@ -16,6 +16,9 @@
  * StreamFrameMeta of each message, runs the registered device handler (echo)
  * and packs the response frames (SendRpcResponse,
  * src/brpc/policy/baidu_rpc_protocol.cpp:273-460).
+ * Further down: leaf codecs (CRC32C, snappy), the client mirror (b2_pack_requests), and the h2/gRPC server path
+ * (b2_h2_process_batch = ParseH2Message, b2_h2_pack_responses = H2UnsentResponse + PackH2Message) whose per-connection
+ * state lives on the device between calls.
  */
 #ifndef B2RPC_H_
 #define B2RPC_H_
