@@ -57,8 +57,12 @@ class Socket {
 public:
     explicit Socket(uint64_t id) : _id(id) {}
     uint64_t id() const { return _id; }
-    IOBuf _read_buf;                     // bytes read from the fd, not yet cut (Socket::_read_buf)
+    IOPortal _read_buf;                  // bytes read from the fd, not yet cut (Socket::_read_buf)
     IOBuf _write_buf;                    // what Socket::Write would hand to writev, in order
+    // Socket::DoRead (src/brpc/socket.cpp:2042-2122): one readv of at most `size_hint' bytes into the read buffer's blocks
+    ssize_t DoRead(int fd, size_t size_hint) { return _read_buf.append_from_file_descriptor(fd, size_hint); }
+    // Socket::DoWrite (:1856-1889): one writev over the queued reply blocks; returns what writev returned
+    ssize_t DoWrite(int fd) { return _write_buf.cut_into_file_descriptor(fd); }
     int preferred_index() const { return _preferred_index; }
     void set_preferred_index(int i) { _preferred_index = i; }
     bool Failed() const { return _failed; }

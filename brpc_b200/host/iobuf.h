@@ -18,11 +18,14 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <string.h>
+#include <sys/uio.h>
+#include <unistd.h>
 #include <atomic>
 #include <deque>
 #include <functional>
 #include <new>
 #include <string>
+#include <vector>
 
 namespace b2 {
 namespace iobuf {
@@ -190,7 +193,43 @@ public:
     }
     int block_nshared(size_t i) const { return i < _refs.size() ? _refs[i].block->nshared.load() : -1; }
 
-private:
+    // Write the front of this buffer to `fd' with ONE writev over its block refs (at most IOV_MAX_REFS of them, stopping once
+    // `size_hint' bytes are covered) and pop what was written — IOBuf::cut_into_file_descriptor, src/butil/iobuf.cpp:827-857.
+    // Returns writev's result.
+    static const size_t IOV_MAX_REFS = 256;
+    ssize_t cut_into_file_descriptor(int fd, size_t size_hint = 1024 * 1024) {
+        if (empty()) return 0;
+        struct iovec vec[IOV_MAX_REFS];
+        size_t nvec = 0, covered = 0;
+        for (auto& r : _refs) {
+            if (nvec >= IOV_MAX_REFS || covered >= size_hint) break;
+            vec[nvec].iov_base = r.block->data + r.offset; vec[nvec].iov_len = r.length;
+            covered += r.length; nvec++;
+        }
+        const ssize_t nw = ::writev(fd, vec, (int)nvec);
+        if (nw > 0) pop_front((size_t)nw);
+        return nw;
+    }
+    // Several buffers (the replies queued on one socket) in one writev — what KeepWrite/DoWrite do with up to 256 IOBufs
+    // (src/brpc/socket.cpp:1780-1889, iobuf.cpp:954-992); the written prefix is popped piece by piece.
+    static ssize_t cut_multiple_into_file_descriptor(int fd, IOBuf* const* pieces, size_t count) {
+        if (count == 0) return 0;
+        struct iovec vec[IOV_MAX_REFS];
+        size_t nvec = 0;
+        for (size_t i = 0; i < count && nvec < IOV_MAX_REFS; i++)
+            for (auto& r : pieces[i]->_refs) {
+                if (nvec >= IOV_MAX_REFS) break;
+                vec[nvec].iov_base = r.block->data + r.offset; vec[nvec].iov_len = r.length; nvec++;
+            }
+        if (nvec == 0) return 0;
+        const ssize_t nw = ::writev(fd, vec, (int)nvec);
+        if (nw <= 0) return nw;
+        size_t left = (size_t)nw;
+        for (size_t i = 0; i < count && left; i++) left -= pieces[i]->pop_front(left);
+        return nw;
+    }
+
+protected:
     static Block* create_block() {
         void* mem = iobuf::blockmem_allocate(DEFAULT_BLOCK_SIZE);
         if (!mem) return nullptr;
@@ -218,5 +257,80 @@ private:
 };
 
 inline void swap(IOBuf& a, IOBuf& b) { a.swap(b); }
+
+// IOPortal — an IOBuf that reads from a file descriptor straight into blocks (src/butil/iobuf.h:445-492,
+// IOPortal::pappend_from_file_descriptor iobuf.cpp:1481-1541): one readv over the free tail of the last block plus fresh
+// blocks, at most MAX_APPEND_IOVEC of them or `max_count' bytes; blocks that stayed empty are kept for the next read.
+// With blockmem_allocate pointed at b2_block_alloc the bytes land in CUDA-pinned memory (Socket::DoRead, socket.cpp:2042-2122).
+class IOPortal : public IOBuf {
+public:
+    static const int MAX_APPEND_IOVEC = 64;
+    IOPortal() {}
+    ~IOPortal() { return_cached_blocks(); }
+    IOPortal(const IOPortal&) = delete;
+    void operator=(const IOPortal&) = delete;
+
+    ssize_t append_from_file_descriptor(int fd, size_t max_count) {
+        struct iovec vec[MAX_APPEND_IOVEC];
+        Block* blk[MAX_APPEND_IOVEC];
+        int nvec = 0; size_t space = 0;
+        // the tail block of the buffer, when our last ref ends where the block's data ends
+        if (!_refs.empty()) {
+            BlockRef& r = _refs.back();
+            if (!r.block->user_deleter && !r.block->full() && r.offset + r.length == r.block->size) {   // (others may share earlier bytes of the block)
+                blk[nvec] = r.block; vec[nvec].iov_base = r.block->data + r.block->size;
+                vec[nvec].iov_len = r.block->left_space() < max_count ? r.block->left_space() : max_count;
+                space += vec[nvec].iov_len; nvec++;
+            }
+        }
+        const int first_fresh = nvec;
+        while (space < max_count && nvec < MAX_APPEND_IOVEC) {
+            Block* b;
+            if (!_cached.empty()) { b = _cached.back(); _cached.pop_back(); }
+            else { b = create_block(); if (!b) { if (nvec == 0) { errno = ENOMEM; return -1; } break; } }
+            blk[nvec] = b; vec[nvec].iov_base = b->data;
+            vec[nvec].iov_len = b->cap < max_count - space ? b->cap : max_count - space;
+            space += vec[nvec].iov_len; nvec++;
+        }
+        const ssize_t nr = ::readv(fd, vec, nvec);
+        size_t left = nr > 0 ? (size_t)nr : 0;
+        for (int i = 0; i < nvec; i++) {
+            const size_t got = left < vec[i].iov_len ? left : vec[i].iov_len;
+            left -= got;
+            if (i < first_fresh) {                                  // extended the existing tail ref
+                if (got) { blk[i]->size += (uint32_t)got; _refs.back().length += (uint32_t)got; _nbytes += got; }
+            } else if (got) {
+                blk[i]->size = (uint32_t)got;
+                _refs.push_back(BlockRef{0, (uint32_t)got, blk[i]}); _nbytes += got;   // the block's creation reference becomes the buffer's
+            } else _cached.push_back(blk[i]);                       // untouched: keep it for the next read
+        }
+        return nr;
+    }
+    void return_cached_blocks() { for (Block* b : _cached) b->dec_ref(); _cached.clear(); }
+    size_t cached_block_num() const { return _cached.size(); }
+
+private:
+    std::vector<Block*> _cached;
+};
+
+// Forward byte iterator over an IOBuf that does not modify it (butil::IOBufBytesIterator, src/butil/iobuf.h:688-727) —
+// what the reference's h2 parser walks frames with.
+class IOBufBytesIterator {
+public:
+    explicit IOBufBytesIterator(const IOBuf& buf) : _buf(&buf), _block(0), _off(0), _left(buf.length()) { settle(); }
+    uint8_t operator*() const { return (uint8_t)_buf->backing_block(_block).first[_off]; }
+    operator const void*() const { return _left ? this : nullptr; }
+    void operator++() { if (_left) { _left--; _off++; settle(); } }
+    size_t bytes_left() const { return _left; }
+    size_t forward(size_t n) { const size_t k = n < _left ? n : _left; size_t m = k; while (m) { const size_t in = _buf->backing_block(_block).second - _off; const size_t s = in < m ? in : m; _off += s; _left -= s; m -= s; settle(); } return k; }
+    size_t copy_and_forward(void* out, size_t n) {
+        uint8_t* o = static_cast<uint8_t*>(out); const size_t k = n < _left ? n : _left; size_t m = k;
+        while (m) { auto b = _buf->backing_block(_block); const size_t s = (b.second - _off) < m ? (b.second - _off) : m; memcpy(o, b.first + _off, s); o += s; _off += s; _left -= s; m -= s; settle(); }
+        return k;
+    }
+private:
+    void settle() { while (_left && _off >= _buf->backing_block(_block).second) { _block++; _off = 0; } }
+    const IOBuf* _buf; size_t _block, _off, _left;
+};
 
 }  // namespace b2

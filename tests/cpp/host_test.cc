@@ -73,6 +73,57 @@ static void test_iobuf() {
     printf("iobuf ok (%d blocks allocated and freed)\n", g_total_allocs);
 }
 
+// IOPortal / writev cuts / byte iterator over a socketpair (test/iobuf_unittest.cpp cut_into_fd / append_from_fd cases :462-520, :1400-1460)
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/socket.h>
+static void test_portal_and_fd() {
+    using b2::IOBuf; using b2::IOPortal;
+    b2::iobuf::blockmem_allocate = counting_alloc; b2::iobuf::blockmem_deallocate = counting_free;
+    const int live_before = g_live_blocks;
+    {
+        int sv[2]; CHECK(socketpair(AF_UNIX, SOCK_STREAM, 0, sv) == 0);
+        CHECK(fcntl(sv[1], F_SETFL, fcntl(sv[1], F_GETFL) | O_NONBLOCK) == 0);
+        std::string s(50000, 0); for (size_t i = 0; i < s.size(); i++) s[i] = (char)(i * 131 + 7);
+        IOBuf out; out.append(s.substr(0, 20000)); IOBuf out2; out2.append(s.substr(20000, 17000)); IOBuf out3; out3.append(s.substr(37000));
+        // three queued replies in one writev, then the rest piece by piece
+        IOBuf* pieces[3] = { &out, &out2, &out3 };
+        size_t sent = 0; IOPortal in; std::string got;
+        while (sent < s.size() || in.length() + got.size() < s.size()) {
+            if (sent < s.size()) { const ssize_t nw = IOBuf::cut_multiple_into_file_descriptor(sv[0], pieces, 3); CHECK(nw > 0); sent += (size_t)nw; }
+            for (;;) {                                               // Socket::DoRead until EAGAIN, like OnNewMessages
+                const ssize_t nr = in.append_from_file_descriptor(sv[1], 12345);
+                if (nr < 0) { CHECK(errno == EAGAIN || errno == EWOULDBLOCK); break; }
+                CHECK(nr > 0 && nr <= 12345);
+            }
+            if (in.length() > 30000) { std::string part; in.cutn(&part, 11111); got += part; }   // the messenger pops consumed bytes in between
+        }
+        CHECK(out.empty() && out2.empty() && out3.empty() && sent == s.size());
+        got += in.to_string();
+        CHECK(got == s);
+        CHECK(in.backing_block_num() <= in.length() / 8160 + 2);     // reads fill blocks, they do not allocate one per readv
+        // an unread portal keeps spare blocks for the next read and gives them back at the end
+        IOPortal idle; CHECK(idle.append_from_file_descriptor(sv[1], 100) < 0 && idle.cached_block_num() == 1 && idle.empty());
+        // single-buffer cut with a size hint: at most the refs needed to cover it go into the writev
+        IOBuf w; for (int i = 0; i < 5; i++) w.append(s.substr(i * 8160, 8160));
+        CHECK(w.backing_block_num() == 5);
+        const ssize_t nw = w.cut_into_file_descriptor(sv[0], 9000); CHECK(nw == 2 * 8160 && w.length() == 3 * 8160);
+        IOPortal drain; while (drain.length() < (size_t)nw) CHECK(drain.append_from_file_descriptor(sv[1], 1 << 16) > 0);
+        CHECK(drain.to_string() == s.substr(0, 2 * 8160));
+        // byte iterator: the h2 frame head walk (LoadUint8 / LoadUint32 / copy_and_forward / forward)
+        b2::IOBufBytesIterator it(drain);
+        CHECK(it.bytes_left() == 2 * 8160 && *it == (uint8_t)s[0]);
+        ++it; CHECK(*it == (uint8_t)s[1]);
+        char buf[16]; CHECK(it.copy_and_forward(buf, 16) == 16 && memcmp(buf, s.data() + 1, 16) == 0);
+        CHECK(it.forward(8160) == 8160 && *it == (uint8_t)s[17 + 8160] && it.bytes_left() == 2 * 8160 - 17 - 8160);
+        CHECK(it.forward(1 << 20) == 2 * 8160 - 17 - 8160 && !it && it.bytes_left() == 0);
+        close(sv[0]); close(sv[1]);
+    }
+    CHECK(g_live_blocks == live_before);
+    b2::iobuf::blockmem_allocate = b2::iobuf::default_alloc; b2::iobuf::blockmem_deallocate = b2::iobuf::default_free;
+    printf("portal ok (readv into blocks, writev cuts, byte iterator)\n");
+}
+
 static int g_host_msgs = 0;
 static void HostProcess(b2::InputMessageBase* base) {
     b2::MostCommonMessage* m = static_cast<b2::MostCommonMessage*>(base);
@@ -238,6 +289,7 @@ static void test_h2_messenger_gpu() {
 int main(int argc, char** argv) {
     const std::string mode = argc > 1 ? argv[1] : "cpu";
     test_iobuf();
+    test_portal_and_fd();
     if (mode == "gpu") { test_messenger_gpu(); test_h2_messenger_gpu(); }
     return 0;
 }
