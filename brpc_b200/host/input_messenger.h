@@ -9,6 +9,7 @@
 // cut loop, RpcMeta decode, echo service and response packing done by the CUDA kernels behind
 // include/b2rpc.h.  There is no parsing in this file.
 #pragma once
+#include <errno.h>
 #include <stdint.h>
 #include <string.h>
 #include <memory>
@@ -63,6 +64,27 @@ public:
     ssize_t DoRead(int fd, size_t size_hint) { return _read_buf.append_from_file_descriptor(fd, size_hint); }
     // Socket::DoWrite (:1856-1889): one writev over the queued reply blocks; returns what writev returned
     ssize_t DoWrite(int fd) { return _write_buf.cut_into_file_descriptor(fd); }
+    // The read-size policy of InputMessenger::OnNewMessages (input_messenger.cpp:346-353): 16 x the average message size,
+    // clamped to [MIN_ONCE_READ 4 KiB, MAX_ONCE_READ 512 KiB]; the average is the windowed mean ProcessNewMessage keeps (:243-261).
+    static const size_t MIN_ONCE_READ = 4096, MAX_ONCE_READ = 524288, MSG_SIZE_WINDOW = 10;
+    size_t once_read() const { const size_t n = _avg_msg_size * 16; return n < MIN_ONCE_READ ? MIN_ONCE_READ : n > MAX_ONCE_READ ? MAX_ONCE_READ : n; }
+    void OnMessageCut(size_t msg_bytes) { _avg_msg_size = _avg_msg_size ? (_avg_msg_size * (MSG_SIZE_WINDOW - 1) + msg_bytes) / MSG_SIZE_WINDOW : msg_bytes; }
+    size_t avg_msg_size() const { return _avg_msg_size; }
+    // Read until the fd would block (or EOF / an error): the inner loop of OnNewMessages without the per-read parse — parsing is
+    // batched over all readable sockets by the messenger.  Returns the bytes read; *eof is set on a zero-length read.
+    ssize_t ReadUntilWouldBlock(int fd, bool* eof) {
+        ssize_t total = 0; *eof = false;
+        for (;;) {
+            const ssize_t nr = DoRead(fd, once_read());
+            if (nr > 0) { total += nr; continue; }
+            if (nr == 0) { *eof = true; break; }
+            if (errno == EINTR) continue;
+            if (errno != EAGAIN && errno != EWOULDBLOCK) SetFailed(errno, "Fail to read");
+            break;
+        }
+        if (_read_buf.empty()) _read_buf.return_cached_blocks();   // good timing to give spare blocks back (:245-251)
+        return total;
+    }
     int preferred_index() const { return _preferred_index; }
     void set_preferred_index(int i) { _preferred_index = i; }
     bool Failed() const { return _failed; }
@@ -76,7 +98,7 @@ public:
     uint64_t in_msgs() const { return _in_msgs; }
 private:
     uint64_t _id; int _preferred_index = -1; bool _failed = false; int _error_code = 0; std::string _error_text;
-    uint64_t _in_bytes = 0, _in_msgs = 0;
+    uint64_t _in_bytes = 0, _in_msgs = 0; size_t _avg_msg_size = 0;
 };
 
 class GpuInputMessenger {
@@ -120,7 +142,7 @@ public:
             const b2_run_status& st = res.runs[i];
             s->AddInputBytes(st.consumed); s->AddInputMessages(st.n_msgs);
             s->set_preferred_index(st.preferred_proto);
-            for (uint32_t m = st.first_msg; m < st.first_msg + st.n_msgs; m++) Deliver(s, res.msgs[m], res.resp, runs[i]);
+            for (uint32_t m = st.first_msg; m < st.first_msg + st.n_msgs; m++) { s->OnMessageCut(12u + res.msgs[m].body_size); Deliver(s, res.msgs[m], res.resp, runs[i]); }
             s->_read_buf.pop_front(st.consumed);              // exactly what the handlers cut (protocol.h:82-92)
             if (st.parse_error != B2_PARSE_ERROR_NOT_ENOUGH_DATA)   // input_messenger.cpp:227-239
                 s->SetFailed(22 /*EINVAL*/, std::string("Close socket: ") + ParseErrorToString((ParseError)st.parse_error));

@@ -84,13 +84,14 @@ static void test_portal_and_fd() {
     {
         int sv[2]; CHECK(socketpair(AF_UNIX, SOCK_STREAM, 0, sv) == 0);
         CHECK(fcntl(sv[1], F_SETFL, fcntl(sv[1], F_GETFL) | O_NONBLOCK) == 0);
+        CHECK(fcntl(sv[0], F_SETFL, fcntl(sv[0], F_GETFL) | O_NONBLOCK) == 0);     // a full socket buffer must not hang the test
         std::string s(50000, 0); for (size_t i = 0; i < s.size(); i++) s[i] = (char)(i * 131 + 7);
         IOBuf out; out.append(s.substr(0, 20000)); IOBuf out2; out2.append(s.substr(20000, 17000)); IOBuf out3; out3.append(s.substr(37000));
         // three queued replies in one writev, then the rest piece by piece
         IOBuf* pieces[3] = { &out, &out2, &out3 };
         size_t sent = 0; IOPortal in; std::string got;
         while (sent < s.size() || in.length() + got.size() < s.size()) {
-            if (sent < s.size()) { const ssize_t nw = IOBuf::cut_multiple_into_file_descriptor(sv[0], pieces, 3); CHECK(nw > 0); sent += (size_t)nw; }
+            if (sent < s.size()) { const ssize_t nw = IOBuf::cut_multiple_into_file_descriptor(sv[0], pieces, 3); if (nw > 0) sent += (size_t)nw; else CHECK(errno == EAGAIN || errno == EWOULDBLOCK); }
             for (;;) {                                               // Socket::DoRead until EAGAIN, like OnNewMessages
                 const ssize_t nr = in.append_from_file_descriptor(sv[1], 12345);
                 if (nr < 0) { CHECK(errno == EAGAIN || errno == EWOULDBLOCK); break; }
@@ -117,7 +118,22 @@ static void test_portal_and_fd() {
         char buf[16]; CHECK(it.copy_and_forward(buf, 16) == 16 && memcmp(buf, s.data() + 1, 16) == 0);
         CHECK(it.forward(8160) == 8160 && *it == (uint8_t)s[17 + 8160] && it.bytes_left() == 2 * 8160 - 17 - 8160);
         CHECK(it.forward(1 << 20) == 2 * 8160 - 17 - 8160 && !it && it.bytes_left() == 0);
-        close(sv[0]); close(sv[1]);
+        // Socket: read-size policy and the read-until-EAGAIN loop (input_messenger.cpp:243-261, :346-372)
+        b2::Socket sock(7);
+        CHECK(sock.once_read() == 4096 && sock.avg_msg_size() == 0);
+        sock.OnMessageCut(1085); CHECK(sock.avg_msg_size() == 1085 && sock.once_read() == 16 * 1085);
+        sock.OnMessageCut(2085); CHECK(sock.avg_msg_size() == (1085 * 9 + 2085) / 10);
+        for (int i = 0; i < 200; i++) sock.OnMessageCut(1 << 20);
+        CHECK(sock.once_read() == 524288);
+        IOBuf big; big.append(s); big.append(s);
+        size_t pushed = 0; while (!big.empty()) { const ssize_t nw = big.cut_into_file_descriptor(sv[0]); if (nw < 0) break; pushed += (size_t)nw; }
+        bool eof = true;
+        const ssize_t nread = sock.ReadUntilWouldBlock(sv[1], &eof);
+        CHECK(nread == (ssize_t)pushed && !eof && !sock.Failed() && sock._read_buf.length() == pushed);
+        CHECK(sock._read_buf.to_string() == (s + s).substr(0, pushed));
+        close(sv[0]);
+        CHECK(sock.ReadUntilWouldBlock(sv[1], &eof) == 0 && eof);                    // peer closed: EOF
+        close(sv[1]);
     }
     CHECK(g_live_blocks == live_before);
     b2::iobuf::blockmem_allocate = b2::iobuf::default_alloc; b2::iobuf::blockmem_deallocate = b2::iobuf::default_free;
