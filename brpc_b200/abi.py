@@ -95,6 +95,7 @@ def _load():
     l.b2_h2_scan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
     l.b2_h2_conn_reset.argtypes = [C.c_void_p, C.c_uint32]
+    l.b2_h2_configure.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
     l.b2_h2_process_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                       C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32]
     l.b2_h2_pack_responses.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -110,7 +111,7 @@ lib = _load()
 ABI_SYMBOLS = ["b2_ctx_create", "b2_ctx_destroy", "b2_last_error", "b2_version", "b2_register_method",
                "b2_set_server_identity", "b2_set_stream_handler", "b2_block_alloc", "b2_block_free", "b2_process_batch", "b2_batch_submit", "b2_batch_collect", "b2_batch_upload",
                "b2_batch_execute", "b2_batch_execute_many", "b2_batch_download", "b2_batch_launch", "b2_batch_wait",
-               "b2_elapsed_ms", "b2_stage_times", "b2_crc32c_batch", "b2_snappy_uncompress_batch", "b2_snappy_compress_batch", "b2_hpack_reset", "b2_hpack_decode_batch", "b2_pack_requests", "b2_h2_scan_batch", "b2_h2_conn_reset", "b2_h2_process_batch", "b2_h2_pack_responses", "b2_counters_read",
+               "b2_elapsed_ms", "b2_stage_times", "b2_crc32c_batch", "b2_snappy_uncompress_batch", "b2_snappy_compress_batch", "b2_hpack_reset", "b2_hpack_decode_batch", "b2_pack_requests", "b2_h2_scan_batch", "b2_h2_conn_reset", "b2_h2_configure", "b2_h2_process_batch", "b2_h2_pack_responses", "b2_counters_read",
                "b2_counters_device_ptr"]
 
 ECHO_METHOD = dict(service_full_name=b"example.EchoService", service_name=b"EchoService", method_name=b"Echo",
@@ -316,6 +317,9 @@ class Context:
         _check(lib.b2_h2_scan_batch(self._h, data.ctypes.data, data.nbytes, runs.ctypes.data, n, max_frame_size, frames.ctypes.data, cap_per_run,
                                     nf.ctypes.data, cons.ctypes.data, err.ctypes.data))
         return [frames[i * cap_per_run:i * cap_per_run + min(int(nf[i]), cap_per_run)] for i in range(n)], nf, cons, err
+
+    def h2_configure(self, max_conns=1024, max_pending=8, stream_bytes=69632):
+        _check(lib.b2_h2_configure(self._h, max_conns, max_pending, stream_bytes))
 
     def h2_conn_reset(self, conn):
         _check(lib.b2_h2_conn_reset(self._h, conn))

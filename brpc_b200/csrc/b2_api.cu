@@ -37,7 +37,7 @@ struct b2_ctx {
     uint8_t* d_bytes = nullptr; b2_run* d_runs = nullptr; uint32_t* d_run_tile_base = nullptr;
     TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; uint32_t* d_tile_scratch = nullptr; uint32_t* d_tile_spec = nullptr; b2_run_status* d_run_status = nullptr;
     uint32_t* d_frame_off = nullptr; uint32_t* d_frame_run = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr; PackJob* d_jobs = nullptr; uint32_t* d_slow_idx = nullptr; uint8_t* d_heads = nullptr;
-    uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr; uint8_t* d_unz = nullptr; uint16_t* d_snappy_tab = nullptr; HpackState* d_hpack = nullptr; H2Conn* d_h2 = nullptr; uint64_t h2_last_in = 0, h2_last_out = 0;   // sizes of the last h2 batch still on the device
+    uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr; uint8_t* d_unz = nullptr; uint16_t* d_snappy_tab = nullptr; HpackState* d_hpack = nullptr; H2Conn* d_h2 = nullptr; H2Stream* d_h2_streams = nullptr; uint8_t* d_h2_slots = nullptr; uint32_t h2_max_conns = B2_H2_MAX_CONNS, h2_pending = B2_H2_MAX_PENDING, h2_stream_bytes = B2_H2_STREAM_BYTES; uint64_t h2_last_in = 0, h2_last_out = 0;   // sizes of the last h2 batch still on the device
     uint32_t* d_crc_adv = nullptr; unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
     size_t meta_tile_off = 0; uint32_t max_tiles = 0; uint32_t n_sms = 148; bool use_tma_pack = true; uint32_t stage_mask = 7;  // debug: 1 front stages, 2 k_pack_tma, 4 k_pack_slow
     // pinned host mirrors
@@ -84,7 +84,7 @@ extern "C" void b2_ctx_destroy(b2_ctx* c) {
     cudaSetDevice(c->opt.device);
     cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch); cudaFree(c->d_tile_spec);
     cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_frame_run); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_slow_idx); cudaFree(c->d_heads); cudaFree(c->d_slot);
-    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_hpack); cudaFree(c->d_h2); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
+    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_hpack); cudaFree(c->d_h2); cudaFree(c->d_h2_streams); cudaFree(c->d_h2_slots); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
     cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
     cudaFreeHost(c->h_run_tile_base);
     for (int i = 0; i <= kMaxStages; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -694,14 +694,29 @@ extern "C" int b2_h2_scan_batch(b2_ctx* c, const void* bytes, uint32_t nbytes, c
 static int h2_ensure(b2_ctx* c) {
     if (c->d_h2) return B2_OK;
     CU(cudaSetDevice(c->opt.device));
-    CU(cudaMalloc(&c->d_h2, sizeof(H2Conn) * (size_t)B2_H2_MAX_CONNS));
-    CU(cudaMemset(c->d_h2, 0, sizeof(H2Conn) * (size_t)B2_H2_MAX_CONNS));
+    const size_t n_streams = (size_t)c->h2_max_conns * c->h2_pending;
+    CU(cudaMalloc(&c->d_h2, sizeof(H2Conn) * (size_t)c->h2_max_conns));
+    if (cudaMalloc(&c->d_h2_streams, sizeof(H2Stream) * n_streams) != cudaSuccess || cudaMalloc(&c->d_h2_slots, n_streams * c->h2_stream_bytes) != cudaSuccess) {
+        cudaFree(c->d_h2); cudaFree(c->d_h2_streams); c->d_h2 = nullptr; c->d_h2_streams = nullptr;
+        set_err("h2 stream pool does not fit: lower b2_h2_configure's capacities"); return B2_E_NOMEM;
+    }
+    CU(cudaMemset(c->d_h2, 0, sizeof(H2Conn) * (size_t)c->h2_max_conns));
+    CU(cudaMemset(c->d_h2_streams, 0xff, sizeof(H2Stream) * n_streams));           // id = -1: free
+    return B2_OK;
+}
+static H2Pool h2_pool(const b2_ctx* c) { H2Pool p; p.streams = c->d_h2_streams; p.slots = c->d_h2_slots; p.pending = c->h2_pending; p.stream_bytes = c->h2_stream_bytes; return p; }
+extern "C" int b2_h2_configure(b2_ctx* c, uint32_t max_conns, uint32_t max_pending, uint32_t stream_bytes) {
+    if (!c || c->d_h2) { set_err("b2_h2_configure must precede the first h2 call on the context"); return B2_E_INVAL; }
+    if (max_conns == 0 || max_conns > B2_HPACK_MAX_CONNS || max_pending == 0 || max_pending > 65536 || stream_bytes < B2_H2_HEADER_BYTES + 16 || (stream_bytes & 15u)) {
+        set_err("bad h2 capacities"); return B2_E_INVAL;
+    }
+    c->h2_max_conns = max_conns; c->h2_pending = max_pending; c->h2_stream_bytes = stream_bytes;
     return B2_OK;
 }
 extern "C" int b2_h2_conn_reset(b2_ctx* c, uint32_t conn) {
-    if (!c || conn >= B2_H2_MAX_CONNS) { set_err("bad connection index"); return B2_E_INVAL; }
+    if (!c || conn >= c->h2_max_conns) { set_err("bad connection index"); return B2_E_INVAL; }
     int rc = h2_ensure(c); if (rc != B2_OK) return rc;
-    k_h2_conn_reset<<<1, 1, 0, c->stream>>>(c->d_h2, c->d_hpack, conn);
+    k_h2_conn_reset<<<1, 1, 0, c->stream>>>(c->d_h2, c->d_hpack, conn, h2_pool(c));
     CU(cudaStreamSynchronize(c->stream));
     return B2_OK;
 }
@@ -715,7 +730,7 @@ extern "C" int b2_h2_process_batch(b2_ctx* c, const void* bytes, uint32_t nbytes
     if (n_runs == 0) return B2_OK;
     for (uint32_t r = 0; r < n_runs; r++) {
         if ((uint64_t)runs[r].offset + runs[r].length > nbytes) { set_err("run outside buffer"); return B2_E_INVAL; }
-        if (runs[r].socket_id >= B2_H2_MAX_CONNS) { set_err("connection index out of range"); return B2_E_INVAL; }
+        if (runs[r].socket_id >= c->h2_max_conns) { set_err("connection index out of range"); return B2_E_INVAL; }
         for (uint32_t q = 0; q < r; q++) if (runs[q].socket_id == runs[r].socket_id) { set_err("one run per connection and batch"); return B2_E_INVAL; }
     }
     const uint32_t region = (out_cap / n_runs) & ~63u, per_run_msgs = msg_cap / n_runs;
@@ -728,7 +743,7 @@ extern "C" int b2_h2_process_batch(b2_ctx* c, const void* bytes, uint32_t nbytes
     CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_meta, runs, sizeof(b2_run) * (size_t)n_runs, cudaMemcpyHostToDevice, c->stream));
     k_h2_consume<<<(n_runs + 31) / 32, 32, 0, c->stream>>>(c->d_bytes, (const b2_run*)c->d_meta, n_runs, c->d_h2, c->d_hpack, c->d_methods, c->cfg.n_methods,
-                                                            d_rs, d_msgs, per_run_msgs, c->d_unz, region);
+                                                            d_rs, d_msgs, per_run_msgs, c->d_unz, region, h2_pool(c));
     CU(cudaMemcpyAsync(rs, d_rs, sizeof(b2_h2_run_status) * (size_t)n_runs, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     // fetch only what was produced: every run owns `region` bytes (acks from its start, records/bodies from region/4) and
@@ -769,7 +784,7 @@ extern "C" int b2_h2_pack_responses(b2_ctx* c, const void* bytes, uint32_t nbyte
         const b2_h2_response& r = resps[i];
         const uint64_t body_lim = (r.flags & B2_H2_RESP_BODY_IN_INPUT) ? c->h2_last_in : (r.flags & B2_H2_RESP_BODY_IN_OUT) ? c->h2_last_out : nbytes;
         const uint64_t ct_lim = (r.flags & B2_H2_RESP_CT_IN_OUT) ? c->h2_last_out : nbytes;
-        if (r.conn >= B2_H2_MAX_CONNS || (uint64_t)r.body_off + r.body_len > body_lim || (uint64_t)r.content_type_off + r.content_type_len > ct_lim ||
+        if (r.conn >= c->h2_max_conns || (uint64_t)r.body_off + r.body_len > body_lim || (uint64_t)r.content_type_off + r.content_type_len > ct_lim ||
             (uint64_t)r.grpc_message_off + r.grpc_message_len > nbytes || r.content_type_len > 256 || r.grpc_message_len > 512) { set_err("bad response descriptor"); return B2_E_INVAL; }
         if ((r.flags & (B2_H2_RESP_BODY_IN_OUT | B2_H2_RESP_CT_IN_OUT)) && c->h2_last_out > c->opt.max_resp_bytes) { set_err("last h2 out buffer too large to stay resident"); return B2_E_CAPACITY; }
         if (i == 0 || r.conn != resps[i - 1].conn) first.push_back(i);

@@ -239,7 +239,7 @@ __global__ void k_h2_scan(const uint8_t* bytes, const b2_run* runs, uint32_t n_r
 // settings, windows, pending streams), so connections are the unit of parallelism, exactly like the reference
 // runs one input bthread per socket.  Every quirk of the reference that shapes the byte stream is kept: handlers
 // that fail (or PING acks) leave the rest of their payload unread and the next "frame head" is parsed from there.
-constexpr uint32_t kH2Pending = B2_H2_MAX_PENDING, kH2StreamBytes = B2_H2_STREAM_BYTES, kH2HdrBytes = B2_H2_HEADER_BYTES;
+constexpr uint32_t kH2HdrBytes = B2_H2_HEADER_BYTES;
 constexpr long long kH2MaxWindow = 2147483647ll;                 // H2Settings::MAX_WINDOW_SIZE
 // n bytes src -> dst by ONE thread: 16-byte words when the pointers agree mod 16, else 4-byte words assembled from
 // aligned loads (a connection is a serial state machine; its bulk copies are the only place worth widening)
@@ -279,21 +279,22 @@ struct H2Conn {
     uint32_t r_header_table_size, r_enable_push, r_max_concurrent_streams, r_stream_window_size, r_max_frame_size, r_max_header_list_size;
     uint32_t l_stream_window_size, l_max_frame_size;
     long long remote_window_left, deferred_window_update;
-    H2Stream streams[kH2Pending];
     HpackState enc;                                              // HPacker::_encode_table (responses)
-    uint8_t slots[kH2Pending][kH2StreamBytes];                   // [0, kH2HdrBytes) header records, then the body
 };
+// Pending streams live outside H2Conn so that their number and size are run-time choices (b2_h2_configure): connection i
+// owns streams[i * pending ...] and slots[(i * pending + k) * stream_bytes ...]: [0, kH2HdrBytes) header records, then the body.
+struct H2Pool { H2Stream* streams; uint8_t* slots; uint32_t pending, stream_bytes; };
 struct H2Out {                      // this run's slice of the output buffer
     uint8_t* base; uint32_t ctrl_cap, ctrl_len, blob_off, blob_end; bool overflow;
 };
-__device__ __forceinline__ void h2_conn_init(H2Conn& c) {
+__device__ __forceinline__ void h2_conn_init(H2Conn& c, H2Stream* S, uint32_t P) {
     c.conn_state = 0; c.last_received_stream_id = -1; c.remote_settings_received = 0; c.n_pending = 0;
     // _remote_settings: H2Settings() with the windows maximised (H2Context ctor, :323-345)
     c.r_header_table_size = 4096; c.r_enable_push = 0; c.r_max_concurrent_streams = 0xffffffffu;
     c.r_stream_window_size = (uint32_t)kH2MaxWindow; c.r_max_frame_size = 16384; c.r_max_header_list_size = 0xffffffffu;
     c.l_stream_window_size = 256 * 1024; c.l_max_frame_size = 16384;     // H2Settings() defaults, http2.cpp:26-34
     c.remote_window_left = kH2MaxWindow; c.deferred_window_update = 0;
-    for (uint32_t i = 0; i < kH2Pending; i++) c.streams[i].id = -1;
+    for (uint32_t i = 0; i < P; i++) S[i].id = -1;
     c.enc.max_size = 4096; c.enc.size = 0; c.enc.count = 0; c.enc.head = 0; c.enc.byte_head = 0;   // _hpacker.Init(header_table_size), :367
 }
 __device__ __forceinline__ void h2_put_head(uint8_t* p, uint32_t payload, uint8_t type, uint8_t flags, uint32_t sid) {   // SerializeFrameHead :123-136
@@ -324,16 +325,16 @@ __device__ __forceinline__ void h2_defer_wu(H2Conn& c, H2Out& o, long long size)
         if (conn_wu > 0) h2_write_wu(o, 0, conn_wu);
     }
 }
-__device__ __forceinline__ int h2_find(const H2Conn& c, int32_t id) {
-    for (uint32_t i = 0; i < kH2Pending; i++) if (c.streams[i].id == id) return (int)i;
+__device__ __forceinline__ int h2_find(const H2Stream* S, uint32_t P, int32_t id) {
+    for (uint32_t i = 0; i < P; i++) if (S[i].id == id) return (int)i;
     return -1;
 }
 // RemoveStreamAndDeferWU (:378-392); returns the slot (the caller still reads the stream's data) or -1
-__device__ __forceinline__ int h2_remove_stream(H2Conn& c, H2Out& o, int32_t id) {
-    const int k = h2_find(c, id);
+__device__ __forceinline__ int h2_remove_stream(H2Conn& c, H2Stream* S, uint32_t P, H2Out& o, int32_t id) {
+    const int k = h2_find(S, P, id);
     if (k < 0) return -1;
-    c.streams[k].id = -1; c.n_pending--;
-    const long long d = c.streams[k].deferred_wu; c.streams[k].deferred_wu = 0;
+    S[k].id = -1; c.n_pending--;
+    const long long d = S[k].deferred_wu; S[k].deferred_wu = 0;
     h2_defer_wu(c, o, d);
     return k;
 }
@@ -442,22 +443,25 @@ __device__ __forceinline__ int h2_consume_headers(H2Conn& c, HpackState& hp, H2S
     return 0;
 }
 // OnEndStream (:823-846): the stream leaves the pending map; the caller emits the message from its slot
-__device__ __forceinline__ H2Res h2_end_stream(H2Conn& c, H2Out& o, int32_t id) {
-    const int k = h2_remove_stream(c, o, id);
+__device__ __forceinline__ H2Res h2_end_stream(H2Conn& c, H2Stream* S, uint32_t P, H2Out& o, int32_t id) {
+    const int k = h2_remove_stream(c, S, P, o, id);
     if (k < 0) return h2_ok();
     H2Res r = h2_ok(); r.kind = 1; r.slot = k; r.err_stream = id; return r;
 }
 
-__global__ void k_h2_conn_reset(H2Conn* conns, HpackState* hps, uint32_t conn) {
-    h2_conn_init(conns[conn]);
+__global__ void k_h2_conn_reset(H2Conn* conns, HpackState* hps, uint32_t conn, H2Pool pool) {
+    h2_conn_init(conns[conn], pool.streams + (size_t)conn * pool.pending, pool.pending);
     HpackState& h = hps[conn]; h.max_size = 4096; h.size = 0; h.count = 0; h.head = 0; h.byte_head = 0;
 }
 
 __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t n_runs, H2Conn* conns, HpackState* hps,
                              const DevMethod* methods, uint32_t n_methods, b2_h2_run_status* rs, b2_h2_msg* msgs, uint32_t msg_cap_per_run,
-                             uint8_t* out, uint32_t region) {
+                             uint8_t* out, uint32_t region, H2Pool pool) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_runs) return;
+    const uint32_t P = pool.pending, kH2StreamBytes = pool.stream_bytes;
+    H2Stream* const S = pool.streams + (size_t)(uint32_t)runs[r].socket_id * P;
+    uint8_t* const slots = pool.slots + (size_t)(uint32_t)runs[r].socket_id * P * kH2StreamBytes;
     const uint32_t run_off = runs[r].offset;
     const uint8_t* in = bytes + run_off; const uint32_t n = runs[r].length;
     H2Conn& c = conns[(uint32_t)runs[r].socket_id];
@@ -508,7 +512,7 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
             if (flags & 0x8) { frag--; padl = pl[used++]; }
             if (frag < padl) { res = h2_err(6); break; }
             frag -= padl;
-            const int k = h2_find(c, sid);
+            const int k = h2_find(S, P, sid);
             if (k < 0) {
                 // stream unknown: the bytes are still counted against the connection window, then STREAM_CLOSED
                 used += frag + padl;
@@ -524,13 +528,13 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
                 res = h2_err(5, sid);
                 break;
             }
-            H2Stream& st = c.streams[k];
+            H2Stream& st = S[k];
             if (st.body_len == 0 && (flags & 0x1) && frag) {
                 // the usual unary call: one DATA frame that also ends the stream — the body stays where it is in the batch
                 st.body_input_off = run_off + pos + used; st.body_len = frag;
             } else {
                 if (kH2HdrBytes + st.body_len + frag > kH2StreamBytes) { no_room = true; break; }
-                thread_copy(&c.slots[k][kH2HdrBytes + st.body_len], pl + used, frag);
+                thread_copy(slots + (size_t)k * kH2StreamBytes + kH2HdrBytes + st.body_len, pl + used, frag);
                 st.body_len += frag;
             }
             used += frag + padl;
@@ -541,7 +545,7 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
                 const long long swu = st.deferred_wu; st.deferred_wu = 0;
                 if (swu > 0) { h2_write_wu(o, (uint32_t)sid, swu); const long long cw = swu + c.deferred_window_update; c.deferred_window_update = 0; h2_write_wu(o, 0, cw); }
             }
-            if (flags & 0x1) res = h2_end_stream(c, o, sid);
+            if (flags & 0x1) res = h2_end_stream(c, S, P, o, sid);
             break; }
         case 1: {                                                    // ---- OnHeaders (:545-613) + H2StreamContext::OnHeaders (:615-655)
             if (sid == 0) { res = h2_err(1); break; }
@@ -556,27 +560,27 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
             if (sid > c.last_received_stream_id) {                   // new stream
                 if ((sid & 1) == 0) { res = h2_err(1); break; }
                 c.last_received_stream_id = sid;
-                k = h2_find(c, -1);
+                k = h2_find(S, P, -1);
                 if (k < 0) { no_room = true; break; }                // (device limit: B2_H2_MAX_PENDING)
-                H2Stream& st = c.streams[k];
+                H2Stream& st = S[k];
                 st.id = sid; st.hdr_len = 0; st.n_headers = 0; st.body_len = 0; st.stream_ended = 0; st.deferred_wu = 0; st.body_input_off = 0;
                 st.remote_window_left = (long long)c.r_stream_window_size;
                 c.n_pending++;
             } else {
-                k = h2_find(c, sid);
+                k = h2_find(S, P, sid);
                 if (k < 0) { res = h2_err(1); break; }
             }
-            H2Stream& st = c.streams[k];
-            if (h2_consume_headers(c, hp, st, c.slots[k], pl + used, frag, no_room) < 0) { if (!no_room) res = h2_err(1); break; }
+            H2Stream& st = S[k];
+            if (h2_consume_headers(c, hp, st, slots + (size_t)k * kH2StreamBytes, pl + used, frag, no_room) < 0) { if (!no_room) res = h2_err(1); break; }
             used += frag + padl;
-            if (flags & 0x4) { if (flags & 0x1) res = h2_end_stream(c, o, sid); }
+            if (flags & 0x4) { if (flags & 0x1) res = h2_end_stream(c, S, P, o, sid); }
             else if (flags & 0x1) st.stream_ended = 1;
             break; }
         case 2: res = h2_err(1); break;                              // OnPriority (:917-921)
         case 3: {                                                    // ---- OnResetStream (:781-821)
             if (length != 4) { res = h2_err(6); break; }
             used += 4;
-            (void)h2_remove_stream(c, o, sid);                       // server side: the stream is dropped, no message
+            (void)h2_remove_stream(c, S, P, o, sid);                       // server side: the stream is dropped, no message
             break; }
         case 4: {                                                    // ---- OnSettings (:848-915)
             if (sid != 0) { res = h2_err(1); break; }
@@ -607,7 +611,7 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
             if (!okp) { res = h2_err(1); break; }
             const long long diff = (long long)c.r_stream_window_size - old_sw;
             bool flow_ok = true;
-            if (diff) for (uint32_t i = 0; i < kH2Pending; i++) if (c.streams[i].id >= 0) { if (!h2_add_window(c.streams[i].remote_window_left, diff)) { flow_ok = false; break; } }
+            if (diff) for (uint32_t i = 0; i < P; i++) if (S[i].id >= 0) { if (!h2_add_window(S[i].remote_window_left, diff)) { flow_ok = false; break; } }
             if (!flow_ok) { res = h2_err(3); break; }
             uint8_t* p = h2_ack_room(o, 9); if (p) h2_put_head(p, 0, 4, 1, 0);
             break; }
@@ -631,17 +635,17 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
             const uint32_t inc = load_be32(pl); used += 4;
             if ((inc & 0x80000000u) || inc == 0) { res = h2_err(1); break; }
             if (sid == 0) { if (!h2_add_window(c.remote_window_left, (long long)inc)) res = h2_err(3); break; }
-            const int k = h2_find(c, sid);
+            const int k = h2_find(S, P, sid);
             if (k < 0) break;
-            if (!h2_add_window(c.streams[k].remote_window_left, (long long)inc)) res = h2_err(3);
+            if (!h2_add_window(S[k].remote_window_left, (long long)inc)) res = h2_err(3);
             break; }
         case 9: {                                                    // ---- OnContinuation (:657-698)
-            const int k = h2_find(c, sid);
+            const int k = h2_find(S, P, sid);
             if (k < 0) { res = h2_err(1); break; }
-            H2Stream& st = c.streams[k];
+            H2Stream& st = S[k];
             used += length;                                          // the payload moves into _remaining_header_fragment first
-            if (h2_consume_headers(c, hp, st, c.slots[k], pl, length, no_room) < 0) { if (!no_room) res = h2_err(1); break; }
-            if ((flags & 0x4) && st.stream_ended) res = h2_end_stream(c, o, sid);
+            if (h2_consume_headers(c, hp, st, slots + (size_t)k * kH2StreamBytes, pl, length, no_room) < 0) { if (!no_room) res = h2_err(1); break; }
+            if ((flags & 0x4) && st.stream_ended) res = h2_end_stream(c, S, P, o, sid);
             break; }
         }
         if (no_room) continue;
@@ -650,7 +654,7 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
             if (res.err_stream) {                                    // RST_STREAM, then the stream is forgotten (:507-527)
                 uint8_t* p = h2_ack_room(o, 13);
                 if (p) { h2_put_head(p, 4, 3, 0, (uint32_t)res.err_stream); put_be32(p + 9, res.err); }
-                (void)h2_remove_stream(c, o, res.err_stream);
+                (void)h2_remove_stream(c, S, P, o, res.err_stream);
             } else {                                                 // GOAWAY (:528-538); parsing goes on
                 uint8_t* p = h2_ack_room(o, 17);
                 if (p) { h2_put_head(p, 8, 7, 0, 0); put_be32(p + 9, (uint32_t)c.last_received_stream_id); put_be32(p + 13, res.err); }
@@ -661,8 +665,8 @@ __global__ void k_h2_consume(const uint8_t* bytes, const b2_run* runs, uint32_t 
         last_ok = pos;
         if (res.kind == 1) {
             // ---- the completed request, as ProcessHttpRequest first sees it
-            const H2Stream& st = c.streams[res.slot];
-            const uint8_t* slot = c.slots[res.slot];
+            const H2Stream& st = S[res.slot];
+            const uint8_t* slot = slots + (size_t)res.slot * kH2StreamBytes;
             const bool in_input = st.body_input_off != 0;
             const uint32_t need = ((st.hdr_len + 15u) & ~15u) + (in_input ? 0u : ((st.body_len + 15u) & ~15u));
             if (n_msgs >= msg_cap_per_run || o.blob_off + need > o.blob_end) { no_room = true; continue; }

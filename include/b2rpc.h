@@ -362,12 +362,18 @@ int  b2_hpack_decode_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes, cons
  *   msgs                : one per completed request, in parse order per run; header records (u16 name_len,
  *                         u16 value_len, name, value — every decoded field in order) and the concatenated DATA
  *                         payloads live in out.
- * Device limits (the reference has none): B2_H2_MAX_PENDING concurrent streams per connection and
- * B2_H2_STREAM_BYTES (4 KiB header records + 64 KiB body) per unfinished stream whose body spans several DATA frames; beyond them the run ends with
- * B2_PARSE_ERROR_NO_RESOURCE (the host takes the connection over or closes it, input_messenger.cpp:227-239). */
+ * Device capacities (the reference has none; they are run-time choices, b2_h2_configure): `max_pending` concurrent unfinished
+ * streams per connection and `stream_bytes` (4 KiB of header records + the body) per unfinished stream whose body spans
+ * several DATA frames (a body carried by one DATA frame is referenced in the input and needs none); beyond them the run ends
+ * with B2_PARSE_ERROR_NO_RESOURCE (the host takes the connection over or closes it, input_messenger.cpp:227-239).
+ * Defaults: B2_H2_MAX_CONNS connections x B2_H2_MAX_PENDING streams x B2_H2_STREAM_BYTES.  gRPC clients keep up to 100
+ * calls in flight per connection (the server side of brpc advertises no SETTINGS_MAX_CONCURRENT_STREAMS): size
+ * max_pending for that, e.g. b2_h2_configure(ctx, 256, 128, 69632) = 2.2 GB of the 180 GB HBM. */
 #define B2_H2_MAX_CONNS 1024
 #define B2_H2_MAX_PENDING 8
 #define B2_H2_STREAM_BYTES 69632
+/* Must precede the first h2 call on the context (the pool is allocated then).  stream_bytes: multiple of 16, > 4 KiB. */
+int  b2_h2_configure(b2_ctx* ctx, uint32_t max_conns, uint32_t max_pending, uint32_t stream_bytes);
 #define B2_H2_HEADER_BYTES 4096
 #define B2_H2_FLAG_GRPC            1u   /* content-type is application/grpc[+...] (is_grpc_ct) */
 #define B2_H2_FLAG_GRPC_PREFIX_OK  2u   /* RemoveGrpcPrefix succeeded: msg_off/msg_len are valid */
