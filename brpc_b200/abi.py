@@ -50,7 +50,11 @@ class BatchResult(C.Structure):
     _fields_ = [("runs", C.c_void_p), ("n_runs", C.c_uint32),
                 ("msgs", C.c_void_p), ("n_msgs", C.c_uint32),
                 ("resp", C.c_void_p), ("resp_bytes", C.c_uint32),
-                ("kernel_ms", C.c_float), ("n_launches", C.c_uint32)]
+                ("kernel_ms", C.c_float), ("n_launches", C.c_uint32), ("refs", C.c_void_p)]
+
+
+REF_DT = np.dtype([("prefix_len", "<u4"), ("src_off", "<u4"), ("src_len", "<u4"), ("reserved", "<u4")])
+INPUT_COPY, INPUT_PULL, RESP_COPY, RESP_BY_REF = 0, 1, 0, 1
 
 
 class B2Error(RuntimeError):
@@ -73,6 +77,8 @@ def _load():
     l.b2_set_stream_handler.argtypes = [C.c_void_p, C.c_int]
     l.b2_block_alloc.restype = C.c_void_p; l.b2_block_alloc.argtypes = [C.c_size_t]
     l.b2_block_free.argtypes = [C.c_void_p]
+    l.b2_block_pool_host_allocs.restype = C.c_uint64
+    l.b2_set_modes.argtypes = [C.c_void_p, C.c_int, C.c_int]
     l.b2_process_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(BatchResult)]
     l.b2_batch_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
     l.b2_batch_collect.argtypes = [C.c_void_p, C.POINTER(BatchResult)]
@@ -109,7 +115,7 @@ lib = _load()
 
 # every symbol include/b2rpc.h declares (tests check the library exports them)
 ABI_SYMBOLS = ["b2_ctx_create", "b2_ctx_destroy", "b2_last_error", "b2_version", "b2_register_method",
-               "b2_set_server_identity", "b2_set_stream_handler", "b2_block_alloc", "b2_block_free", "b2_process_batch", "b2_batch_submit", "b2_batch_collect", "b2_batch_upload",
+               "b2_set_server_identity", "b2_set_stream_handler", "b2_block_alloc", "b2_block_free", "b2_block_pool_host_allocs", "b2_set_modes", "b2_process_batch", "b2_batch_submit", "b2_batch_collect", "b2_batch_upload",
                "b2_batch_execute", "b2_batch_execute_many", "b2_batch_download", "b2_batch_launch", "b2_batch_wait",
                "b2_elapsed_ms", "b2_stage_times", "b2_crc32c_batch", "b2_snappy_uncompress_batch", "b2_snappy_compress_batch", "b2_hpack_reset", "b2_hpack_decode_batch", "b2_pack_requests", "b2_h2_scan_batch", "b2_h2_conn_reset", "b2_h2_configure", "b2_h2_process_batch", "b2_h2_pack_responses", "b2_counters_read",
                "b2_counters_device_ptr"]
@@ -190,6 +196,16 @@ class Context:
             if res.resp_bytes else np.zeros(0, np.uint8)
         return runs, msgs, resp
 
+    @staticmethod
+    def _info(res):
+        refs = None
+        if res.refs and res.n_msgs:
+            refs = np.ctypeslib.as_array((C.c_uint8 * (16 * res.n_msgs)).from_address(res.refs)).view(REF_DT)
+        return {"kernel_ms": res.kernel_ms, "n_launches": res.n_launches, "refs": refs}
+
+    def set_modes(self, input_mode=INPUT_COPY, resp_mode=RESP_COPY):
+        _check(lib.b2_set_modes(self._h, input_mode, resp_mode))
+
     def process_batch(self, data, runs):
         """Host buffers in, host (pinned) views out: (run_status, msgs, resp, info)."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
@@ -197,7 +213,7 @@ class Context:
         res = BatchResult()
         _check(lib.b2_process_batch(self._h, data.ctypes.data, data.nbytes, runs.ctypes.data, len(runs), C.byref(res)))
         rs, msgs, resp = self._views(res)
-        return rs, msgs, resp, {"kernel_ms": res.kernel_ms, "n_launches": res.n_launches}
+        return rs, msgs, resp, self._info(res)
 
     def upload(self, data, runs):
         data = np.ascontiguousarray(data, dtype=np.uint8)
@@ -233,14 +249,14 @@ class Context:
         res = BatchResult()
         _check(lib.b2_batch_download(self._h, C.byref(res)))
         rs, msgs, resp = self._views(res)
-        return rs, msgs, resp, {"kernel_ms": res.kernel_ms, "n_launches": res.n_launches}
+        return rs, msgs, resp, self._info(res)
 
     def process_batch_ptr(self, ptr, nbytes, runs):
         runs = np.ascontiguousarray(runs, dtype=RUN_DT)
         res = BatchResult()
         _check(lib.b2_process_batch(self._h, ptr, nbytes, runs.ctypes.data, len(runs), C.byref(res)))
         rs, msgs, resp = self._views(res)
-        return rs, msgs, resp, {"kernel_ms": res.kernel_ms, "n_launches": res.n_launches}
+        return rs, msgs, resp, self._info(res)
 
     def submit_ptr(self, ptr, nbytes, runs):
         runs = np.ascontiguousarray(runs, dtype=RUN_DT)
@@ -251,7 +267,7 @@ class Context:
         res = BatchResult()
         _check(lib.b2_batch_collect(self._h, C.byref(res)))
         rs, msgs, resp = self._views(res)
-        return rs, msgs, resp, {"kernel_ms": res.kernel_ms, "n_launches": res.n_launches}
+        return rs, msgs, resp, self._info(res)
 
     def stage_times(self):
         names = (C.c_char_p * 16)()

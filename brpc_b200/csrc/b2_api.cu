@@ -5,7 +5,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "b2_kernels.cuh"
 #include "b2_h2.cuh"
@@ -25,7 +27,7 @@ namespace {
 constexpr int kMaxStages = 16;
 constexpr uint32_t kSmallBytes = 128 << 10;        // batches up to this size take the latency path
 constexpr uint32_t kSmallRuns = 512, kSmallMsgs = 1024;   // == kSmallThreads, 2 * kSmallThreads of k_small
-constexpr size_t kSmallBlock = 64 + kSmallRuns * 32 + kSmallMsgs * 64 + (kSmallBytes + kSmallMsgs * 80 + 4096);
+constexpr size_t kSmallBlock = 64 + kSmallRuns * 32 + kSmallMsgs * (64 + 16) + (kSmallBytes + kSmallMsgs * 80 + 4096);
 struct Stage { const char* name; cudaEvent_t ev; };
 }
 
@@ -38,6 +40,7 @@ struct b2_ctx {
     TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; uint32_t* d_tile_scratch = nullptr; uint32_t* d_tile_spec = nullptr; b2_run_status* d_run_status = nullptr;
     uint32_t* d_frame_off = nullptr; uint32_t* d_frame_run = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr; PackJob* d_jobs = nullptr; uint32_t* d_slow_idx = nullptr; uint8_t* d_heads = nullptr;
     uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr; uint8_t* d_unz = nullptr; uint16_t* d_snappy_tab = nullptr; HpackState* d_hpack = nullptr; H2Conn* d_h2 = nullptr; H2Stream* d_h2_streams = nullptr; uint8_t* d_h2_slots = nullptr; uint32_t h2_max_conns = B2_H2_MAX_CONNS, h2_pending = B2_H2_MAX_PENDING, h2_stream_bytes = B2_H2_STREAM_BYTES; uint64_t h2_last_in = 0, h2_last_out = 0;   // sizes of the last h2 batch still on the device
+    uint4* d_refs = nullptr; b2_resp_ref* h_refs = nullptr; int input_mode = B2_INPUT_COPY, resp_mode = B2_RESP_COPY; const uint8_t* pull_bytes = nullptr; uint32_t small_off_refs = 0;
     uint32_t* d_crc_adv = nullptr; unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
     size_t meta_tile_off = 0; uint32_t max_tiles = 0; uint32_t n_sms = 148; bool use_tma_pack = true; uint32_t stage_mask = 7;  // debug: 1 front stages, 2 k_pack_tma, 4 k_pack_slow
     // pinned host mirrors
@@ -72,19 +75,62 @@ static void crc_table_init() {
 extern "C" const char* b2_last_error(void) { return g_err; }
 extern "C" const char* b2_version(void) { return "brpc_b200 0.1 (sm_100a)"; }
 
+// ---- pinned block pool (seam 3: butil::iobuf::blockmem_allocate / blockmem_deallocate, src/butil/iobuf.cpp:168-169; same role as
+// rdma::block_pool, src/brpc/rdma/block_pool.h:74-105).  cudaHostAlloc / cudaFreeHost cost tens of microseconds and serialise
+// with the device, so they are paid per SLAB, never per block: blocks of up to 8 KiB (IOBuf::DEFAULT_BLOCK_SIZE) are carved out
+// of 4 MiB slabs and recycled through a free list; larger requests (socket read arenas, batch buffers) are rounded up to a power
+// of two (+ 1 KiB of slack so 16-byte over-reads of a device kernel stay inside the mapping) and cached per size class when
+// freed.  All memory is mapped (cudaHostAllocMapped | Portable): a kernel can read it in place (B2_INPUT_PULL).
+namespace {
+struct BlockPool {
+    std::mutex mu;
+    static constexpr size_t kSmall = 8192, kSlab = 4u << 20;
+    std::vector<uint8_t*> slabs; std::vector<void*> small_free;
+    std::unordered_map<void*, int> large_class;          // live + cached large blocks -> size class (log2)
+    std::vector<void*> large_free[40];
+    uint64_t n_host_alloc = 0;
+    void* alloc(size_t size) {
+        std::lock_guard<std::mutex> g(mu);
+        if (size <= kSmall) {
+            if (small_free.empty()) {
+                uint8_t* slab = nullptr;
+                if (cudaHostAlloc((void**)&slab, kSlab, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+                n_host_alloc++; slabs.push_back(slab);
+                for (size_t o = 0; o + kSmall <= kSlab; o += kSmall) small_free.push_back(slab + o);
+            }
+            void* p = small_free.back(); small_free.pop_back(); return p;
+        }
+        int cls = 14; while (((size_t)1 << cls) < size) cls++;
+        if (cls >= 40) return nullptr;
+        if (!large_free[cls].empty()) { void* p = large_free[cls].back(); large_free[cls].pop_back(); return p; }
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, ((size_t)1 << cls) + 1024, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+        n_host_alloc++; large_class[p] = cls;
+        return p;
+    }
+    void free(void* p) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = large_class.find(p);
+        if (it != large_class.end()) { large_free[it->second].push_back(p); return; }
+        small_free.push_back(p);                           // (a slab block; slabs live until process exit)
+    }
+};
+BlockPool& block_pool() { static BlockPool* p = new BlockPool; return *p; }
+}
 extern "C" void* b2_block_alloc(size_t size) {
-    void* p = nullptr;
-    if (cudaHostAlloc(&p, size, cudaHostAllocPortable) != cudaSuccess) { set_err("cudaHostAlloc failed"); return nullptr; }
+    void* p = block_pool().alloc(size ? size : 1);
+    if (!p) set_err("cudaHostAlloc failed");
     return p;
 }
-extern "C" void b2_block_free(void* p) { if (p) cudaFreeHost(p); }
+extern "C" void b2_block_free(void* p) { if (p) block_pool().free(p); }
+extern "C" uint64_t b2_block_pool_host_allocs(void) { std::lock_guard<std::mutex> g(block_pool().mu); return block_pool().n_host_alloc; }
 
 extern "C" void b2_ctx_destroy(b2_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->opt.device);
     cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch); cudaFree(c->d_tile_spec);
     cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_frame_run); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_slow_idx); cudaFree(c->d_heads); cudaFree(c->d_slot);
-    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_hpack); cudaFree(c->d_h2); cudaFree(c->d_h2_streams); cudaFree(c->d_h2_slots); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
+    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_refs); cudaFreeHost(c->h_refs); cudaFree(c->d_hpack); cudaFree(c->d_h2); cudaFree(c->d_h2_streams); cudaFree(c->d_h2_slots); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
     cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
     cudaFreeHost(c->h_run_tile_base);
     for (int i = 0; i <= kMaxStages; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -140,6 +186,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     ALLOC(c->d_msgs, sizeof(b2_msg_desc) * (size_t)o->max_msgs);
     ALLOC(c->d_aux, sizeof(MsgAux) * (size_t)o->max_msgs);
     ALLOC(c->d_jobs, sizeof(PackJob) * (size_t)o->max_msgs);
+    ALLOC(c->d_refs, sizeof(uint4) * (size_t)o->max_msgs);
     ALLOC(c->d_slow_idx, sizeof(uint32_t) * (size_t)o->max_msgs);
     ALLOC(c->d_heads, (size_t)kHeadBytes * (size_t)o->max_msgs);
     ALLOC(c->d_slot, 4 * ((size_t)o->max_msgs + 1));
@@ -159,6 +206,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     HALLOC(c->h_small, kSmallBlock);
     HALLOC(c->h_run_status, sizeof(b2_run_status) * (size_t)o->max_runs);
     HALLOC(c->h_msgs, sizeof(b2_msg_desc) * (size_t)o->max_msgs);
+    HALLOC(c->h_refs, sizeof(b2_resp_ref) * (size_t)o->max_msgs);
     HALLOC(c->h_resp, (size_t)c->opt.max_resp_bytes);
     HALLOC(c->h_totals, 16);
     HALLOC(c->h_run_tile_base, 4 * ((size_t)o->max_runs + 1));
@@ -200,6 +248,14 @@ extern "C" int b2_set_server_identity(b2_ctx* c, const char* ip_port) {
     return B2_OK;
 }
 
+extern "C" int b2_set_modes(b2_ctx* c, int input_mode, int resp_mode) {
+    if (!c || (input_mode != B2_INPUT_COPY && input_mode != B2_INPUT_PULL) || (resp_mode != B2_RESP_COPY && resp_mode != B2_RESP_BY_REF)) { set_err("bad mode"); return B2_E_INVAL; }
+    static_assert(sizeof(b2_resp_ref) == sizeof(uint4), "b2_resp_ref is 16 bytes");
+    c->input_mode = input_mode; c->resp_mode = resp_mode; c->cfg.by_ref = resp_mode == B2_RESP_BY_REF;
+    c->uploaded = false; c->executed = false;
+    return B2_OK;
+}
+
 extern "C" int b2_set_stream_handler(b2_ctx* c, int kind) {
     if (!c || (kind != B2_STREAM_DESC_ONLY && kind != B2_STREAM_SNAPPY_UNCOMPRESS)) { set_err("bad stream handler"); return B2_E_INVAL; }
     c->cfg.stream_handler = (uint32_t)kind;
@@ -232,13 +288,15 @@ static BatchPtrs make_ptrs(b2_ctx* c) {
     BatchPtrs B;
     B.bytes = c->d_bytes; B.runs = c->d_runs; B.run_tile_base = c->d_run_tile_base; B.tiles = c->d_tiles;
     B.tile_base = c->d_tile_base; B.tile_scratch = c->d_tile_scratch; B.tile_spec = c->d_tile_spec; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.frame_run = c->d_frame_run; B.msgs = c->d_msgs;
-    B.aux = c->d_aux; B.jobs = c->d_jobs; B.slow_idx = c->d_slow_idx; B.heads = c->d_heads; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.unz = c->d_unz; B.snappy_tab = c->d_snappy_tab; B.counters = c->d_counters;
+    B.aux = c->d_aux; B.jobs = c->d_jobs; B.refs = c->d_refs; B.slow_idx = c->d_slow_idx; B.heads = c->d_heads; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.unz = c->d_unz; B.snappy_tab = c->d_snappy_tab; B.counters = c->d_counters;
     B.totals = c->d_totals; B.methods = c->d_methods; B.crc_adv = c->d_crc_adv;
     B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes;
     B.runs = reinterpret_cast<const b2_run*>(c->d_meta);
     B.run_tile_base = reinterpret_cast<const uint32_t*>(c->d_meta + (size_t)c->n_runs * sizeof(b2_run));
     B.tile_info = reinterpret_cast<const uint4*>(c->d_meta + c->meta_tile_off);
+    if (c->input_mode == B2_INPUT_PULL) B.bytes = c->pull_bytes;          // the caller's pinned + mapped batch buffer, read in place
     if (c->small) {
+        B.refs = reinterpret_cast<uint4*>(c->d_small + c->small_off_refs);
         B.totals = reinterpret_cast<uint32_t*>(c->d_small);
         B.run_status = reinterpret_cast<b2_run_status*>(c->d_small + c->small_off_rs);
         B.msgs = reinterpret_cast<b2_msg_desc*>(c->d_small + c->small_off_msgs);
@@ -256,7 +314,10 @@ extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, co
         // like Socket::_avg_msg_size steering the read size (input_messenger.cpp:348-353): a tile should hold
         // 6-12 messages so the speculative entry search reads a small fraction of it
         uint32_t t = 8192;
-        while (t < (1u << 20) && t < 6u * c->avg_frame) t <<= 1;
+        // (B2_INPUT_PULL: the speculative scan window of every tile crosses PCIe, so tiles are 4x larger)
+        const uint32_t per_tile = c->input_mode == B2_INPUT_PULL ? 24u : 6u;
+        if (c->input_mode == B2_INPUT_PULL && t < 32768) t = 32768;
+        while (t < (1u << 20) && t < per_tile * c->avg_frame) t <<= 1;
         c->cfg.tile_bytes = t; c->cfg.tile_shift = 0; while ((1u << c->cfg.tile_shift) < t) c->cfg.tile_shift++;
     }
     const uint32_t shift = c->cfg.tile_shift, tile = c->cfg.tile_bytes;
@@ -288,14 +349,23 @@ extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, co
         }
     }
     c->h2_last_in = 0; c->h2_last_out = 0;       // the device copies of the last h2 batch are about to be overwritten
-    if (nbytes) CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
+    if (c->input_mode == B2_INPUT_PULL) {
+        // no copy: the kernels read the caller's pinned block in place (it must stay untouched until collect)
+        void* dp = nullptr;
+        if (nbytes && cudaHostGetDevicePointer(&dp, const_cast<void*>(bytes), 0) != cudaSuccess) {
+            cudaGetLastError(); set_err("B2_INPUT_PULL: bytes must be pinned + mapped memory from b2_block_alloc"); return B2_E_INVAL;
+        }
+        c->pull_bytes = static_cast<const uint8_t*>(dp);
+    } else if (nbytes) CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_meta, c->h_meta, meta_bytes, cudaMemcpyHostToDevice, c->stream));
     // latency path: outputs of a small batch live in one compact block -> one D2H copy, one sync
     c->small = c->allow_small && nbytes <= kSmallBytes && n_runs <= kSmallRuns && n_runs > 0;
     if (c->small) {
         uint32_t mb = nbytes / 12 + 1; if (mb > kSmallMsgs) mb = kSmallMsgs;
+        if (mb > c->opt.max_msgs) mb = c->opt.max_msgs;      // d_frame_off / d_aux / d_jobs / d_heads ... are sized by opt.max_msgs
         c->small_msgs = mb; c->small_resp = nbytes + mb * 80 + 2048;
-        c->small_off_rs = 64; c->small_off_msgs = 64 + n_runs * 32; c->small_off_resp = (c->small_off_msgs + mb * 64 + 255u) & ~255u;
+        c->small_off_rs = 64; c->small_off_msgs = 64 + n_runs * 32; c->small_off_refs = c->small_off_msgs + mb * 64;
+        c->small_off_resp = (c->small_off_refs + mb * 16 + 255u) & ~255u;
         c->small_total = c->small_off_resp + c->small_resp;
     }
     if (const char* e = getenv("B2_STAGE_MASK")) c->stage_mask = (uint32_t)atoi(e);   // timing experiments only (tools/overlap_probe.py)
@@ -330,8 +400,8 @@ static int launch_pipeline(b2_ctx* c) {
     }
     {
         size_t smem = (size_t)c->max_run_tiles * 12;
-        if (smem > 200 * 1024) smem = 0;
-        k_resolve<<<c->n_runs, 256, smem, s>>>(B, C); launches++; mark("resolve");
+        if (smem > 200 * 1024) smem = 0;                 // some run does not fit: EVERY run of this launch uses the global scratch
+        k_resolve<<<c->n_runs, 256, smem, s>>>(B, C, smem == 0 ? 1u : 0u); launches++; mark("resolve");
     }
     if (c->n_tiles) { k_frame_table<<<(uint32_t)(((uint64_t)c->n_tiles * C.spec_k + 255) / 256), 256, 0, s>>>(B, C); launches++; mark("frame_table"); }
     // message-count dependent kernels are persistent: fixed grids (multiples of the SM count)
@@ -345,7 +415,7 @@ static int launch_pipeline(b2_ctx* c) {
         if (mask & 4) { k_pack_slow<<<sms * B2_SLOW_MIN_BLOCKS, 256, 8 * kSnapRing, s>>>(B, C); launches++; mark("pack_slow"); }
         if (mask & 2) {
             // small requests: 32 messages per warp round instead of 8 (measured +30 % at 64 B payloads, -3 % at 1 KB)
-            if (c->avg_frame && c->avg_frame < 640) k_pack_tma<kPackGroupSmall><<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C);
+            if ((c->avg_frame && c->avg_frame < 640) || c->cfg.by_ref) k_pack_tma<kPackGroupSmall><<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C);
             else k_pack_tma<kPackGroup><<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C);
             launches++; mark("pack");
         }
@@ -430,7 +500,9 @@ static int download_normal(b2_ctx* c, b2_batch_result* out) {
     if (c->n_runs) CU(cudaMemcpyAsync(c->h_run_status, c->d_run_status, sizeof(b2_run_status) * c->n_runs, cudaMemcpyDeviceToHost, c->stream));
     if (n_msgs) CU(cudaMemcpyAsync(c->h_msgs, c->d_msgs, sizeof(b2_msg_desc) * (size_t)n_msgs, cudaMemcpyDeviceToHost, c->stream));
     if (resp_bytes) CU(cudaMemcpyAsync(c->h_resp, c->d_resp, resp_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (n_msgs && c->cfg.by_ref) CU(cudaMemcpyAsync(c->h_refs, c->d_refs, sizeof(b2_resp_ref) * (size_t)n_msgs, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    out->refs = c->cfg.by_ref ? c->h_refs : nullptr;
     out->runs = c->h_run_status; out->n_runs = c->n_runs;
     out->msgs = c->h_msgs; out->n_msgs = n_msgs;
     out->resp = c->h_resp; out->resp_bytes = resp_bytes;
@@ -457,6 +529,7 @@ extern "C" int b2_batch_download(b2_ctx* c, b2_batch_result* out) {
             out->runs = reinterpret_cast<const b2_run_status*>(c->h_small + c->small_off_rs); out->n_runs = c->n_runs;
             out->msgs = reinterpret_cast<const b2_msg_desc*>(c->h_small + c->small_off_msgs); out->n_msgs = tot[0];
             out->resp = c->h_small + c->small_off_resp; out->resp_bytes = tot[1];
+            out->refs = c->cfg.by_ref ? reinterpret_cast<const b2_resp_ref*>(c->h_small + c->small_off_refs) : nullptr;
         }
     } else {
         int rc = download_normal(c, out);

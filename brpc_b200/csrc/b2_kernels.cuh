@@ -77,6 +77,7 @@ struct DevConfig {
     uint32_t identity_len;
     uint32_t stream_handler;      // B2_STREAM_*
     uint32_t spec_k;              // speculative frame offsets kept per tile: kSpecK, or kSpecKDense when tiles hold many small frames
+    uint32_t by_ref;              // B2_RESP_BY_REF: OK echo replies are {prefix, reference into the request bytes}
     char identity[64];            // "ip:port" of Controller::AppendServerIdentiy
 };
 
@@ -96,6 +97,7 @@ struct BatchPtrs {
     b2_msg_desc* msgs;
     MsgAux* aux;
     PackJob* jobs;                   // [max_msgs]
+    uint4* refs;                     // [max_msgs] b2_resp_ref {prefix_len, src_off, src_len, 0} (B2_RESP_BY_REF)
     uint32_t* slow_idx;              // [max_msgs] messages k_pack_slow has to serve (unordered), count in totals[3]
     uint8_t* heads;                  // [max_msgs * kHeadBytes] reply prefixes pre-shifted to their slot alignment
     uint32_t* slot;                  // [max_msgs+1] slot sizes -> exclusive offsets
@@ -348,7 +350,7 @@ __device__ __forceinline__ uint32_t make_link(const TileRec& t, const TileRec* t
     return (tiles[j].entry == t.exit ? kLinkOk : kLinkBroken) | j;
 }
 
-__global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C) {
+__global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C, uint32_t use_scratch) {
     extern __shared__ uint32_t sm[];
     const uint32_t r = blockIdx.x;
     const b2_run run = B.runs[r];
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C) {
     const uint32_t len = run.length;
     const uint32_t tb = B.run_tile_base[r], nt = B.run_tile_base[r + 1] - tb;
     TileRec* tiles = B.tiles + tb;
-    const bool fits = nt * 12u <= 200u * 1024u;
+    const bool fits = !use_scratch;                              // decided per LAUNCH by the host: no dynamic shared memory was allocated otherwise
     uint32_t* link = fits ? sm : B.tile_scratch + 3ull * tb;     // [nt]
     uint32_t* cp = link + nt;                                     // [nt] count << 2 | last_proto
     uint32_t* live = cp + nt;                                     // [nt]
@@ -667,6 +669,7 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
     MsgAux a; a.msg_off = a.msg_len = a.att_len = a.att_off = a.cks_off = a.cks_len = 0;
     a.svc_off = a.svc_len = a.mth_off = a.mth_len = 0; a.pad = 0; a.err_kind = kErrNone;
     uint32_t resp_len = 0, reserve = 0;               // reserve: slot bytes beyond resp_len a second outcome may need
+    uint32_t ref_prefix = 0;                          // B2_RESP_BY_REF: bytes of the reply that are materialised (0 = the whole reply)
     const uint8_t* meta_p = frame + 12;
     const uint32_t req_size = d.body_size - d.meta_size;
     if (proto == B2_PROTOCOL_STREAMING_RPC) {
@@ -800,6 +803,9 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                         const uint32_t prefix = 12 + ml + 1 + varint_len(msg.len);
                         resp_len = prefix + msg.len + a.att_len;
                         a.pad = (fo + a.msg_off - prefix) & 15u;       // payload keeps its (mod 16) alignment
+                        // B2_RESP_BY_REF: only the prefix is materialised (same conditions as the bandwidth path below)
+                        if (C.by_ref && mp->response_checksum_type == B2_CHECKSUM_TYPE_NONE && mp->response_compress_type == B2_COMPRESS_TYPE_NONE &&
+                            (a.att_len == 0 || a.att_off == a.msg_off + a.msg_len) && prefix <= 64) { a.pad = 0; ref_prefix = prefix; }
                         if (mp->response_compress_type == B2_COMPRESS_TYPE_SNAPPY) {
                             resp_len = 12 + ml + snappy_max_compressed_length(1 + varint_len(msg.len) + msg.len) + a.att_len; a.pad = 0;
                         }
@@ -816,15 +822,16 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                 b2_msg_desc e = d; MsgAux ea = a; e.error_code = B2_EREQUEST; ea.err_kind = kErrParseRequest;
                 const uint32_t tl = error_text_len(C, B.methods, e, ea, frame);
                 const uint32_t el = 12 + response_meta_len(B2_EREQUEST, tl, 0, m.correlation_id, 0, 0, a.cks_len);
-                if (a.pad + resp_len < el) reserve = el - a.pad;    // slot must hold either reply (error reply is packed at pad 0)
+                if (a.pad + (ref_prefix ? ref_prefix : resp_len) < el) reserve = el - a.pad;    // slot must hold either reply (error reply is packed at pad 0)
             }
         }
     }
     d.resp_len = resp_len;
     B.msgs[i] = d;
     B.aux[i] = a;
-    const uint32_t slot_len = resp_len ? ((a.pad + max(resp_len, reserve) + 15u) & ~15u) : 0u;
+    const uint32_t slot_len = resp_len ? ((a.pad + max(ref_prefix ? ref_prefix : resp_len, reserve) + 15u) & ~15u) : 0u;
     B.slot[i] = slot_len;
+    uint4 ref = make_uint4(0, 0, 0, 0);
     // ---- bandwidth path: pre-build the reply prefix, shifted to the slot alignment -------------
     PackJob job; job.src_off = 0; job.bulk_len = 0; job.head_len = 0; job.pad = (uint8_t)a.pad; job.fast = 0; job.slot_len = slot_len;
     if (d.status == B2_MSG_ECHOED && d.compress_type == B2_COMPRESS_TYPE_NONE &&
@@ -837,7 +844,7 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
         if (prefix <= 64) {
             const uint32_t n = a.msg_len + a.att_len;
             const uint32_t gs = fo + a.msg_off;
-            const uint32_t lead = min(n, (16u - (gs & 15u)) & 15u);
+            const uint32_t lead = ref_prefix ? 0u : min(n, (16u - (gs & 15u)) & 15u);
             const uint32_t hl = (a.pad + prefix + lead + 15u) & ~15u;
             uint8_t* h = shead;
             {   // zero the record first (six 16-byte stores) instead of byte loops for the pad and the tail
@@ -856,12 +863,14 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
             for (uint32_t k = 0; k < a.cks_len; k++) *p++ = frame[a.cks_off + k];
             *p++ = 0x0a; p = put_varint(p, a.msg_len);
             for (uint32_t k = 0; k < lead; k++) *p++ = frame[a.msg_off + k];
-            job.src_off = gs + lead; job.bulk_len = (n - lead + 15u) & ~15u; job.head_len = (uint16_t)hl;
+            job.src_off = gs + lead; job.bulk_len = ref_prefix ? 0u : ((n - lead + 15u) & ~15u); job.head_len = (uint16_t)hl;
+            if (ref_prefix) ref = make_uint4(prefix, gs, n, 0);
             // a CRC32C-carrying request takes the bandwidth path once k_pack_slow's verify pass has checked it (fast 2 -> 1)
             job.fast = d.checksum_type == B2_CHECKSUM_TYPE_CRC32C ? 2 : 1;
         }
     }
     B.jobs[i] = job;
+    if (C.by_ref) B.refs[i] = ref;
 }
 
 // --- exclusive scan of slot sizes: 2 kernels ---------------------------------
@@ -1513,6 +1522,7 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
             if (d.status == B2_MSG_ECHOED) { e.error_code = B2_EREQUEST; ea.err_kind = kErrParseRequest; }
             n = pack_error_reply(B.resp + slot_off, C, B.methods, e, ea, frame);
             B.msgs[i].resp_off = slot_off; B.msgs[i].resp_len = n;
+            if (C.by_ref) B.refs[i] = make_uint4(0, 0, 0, 0);          // the whole (error) reply is materialised
             if (d.status == B2_MSG_ECHOED) { B.msgs[i].status = B2_MSG_ERROR_REPLIED; B.msgs[i].error_code = B2_EREQUEST; }
         }
         return;
@@ -1524,6 +1534,13 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
     const uint32_t ml = response_meta_len(0, 0, r_compress, d.correlation_id, a.att_len, r_cks_type, cks_len);
     const uint32_t vl = varint_len(msg_len);
     uint8_t* out = B.resp + slot_off + a.pad;
+    if (C.by_ref && B.refs[i].x != 0) {
+        // B2_RESP_BY_REF (a CRC-verified request served by the latency path): the slot holds the prefix only
+        const uint32_t prefix = 12 + ml + 1 + vl;
+        write_echo_prefix(out, lane, d.correlation_id, a.att_len, r_cks_type, cks_len, 0, frame + a.cks_off, msg_len, ml, vl, prefix);
+        if (lane == 0) B.msgs[i].resp_off = slot_off;
+        return;
+    }
     if (r_compress == B2_COMPRESS_TYPE_SNAPPY) {
         // SnappyCompress (policy/snappy_compress.cpp:28-49): serialize the EchoResponse, then compress it
         uint8_t* pb = B.unz + (size_t)B.max_resp + slot_off;

@@ -195,6 +195,13 @@ typedef struct b2_options {
     uint64_t max_body_size;    /* FLAGS_max_body_size (protocol.cpp:52), 0 = 64 MiB */
 } b2_options;
 
+/* B2_RESP_BY_REF: where reply i's payload lives.  Reply i = resp[msgs[i].resp_off, +prefix_len) followed by
+ * bytes[src_off, +src_len) of the REQUEST batch — exactly how SendRpcResponse builds res_buf: header + meta, then
+ * res_buf.append(res_body.movable()) / append(attachment) by reference (baidu_rpc_protocol.cpp:383-389).
+ * msgs[i].resp_len = prefix_len + src_len.  src_len == 0: the whole reply is in resp (error replies, checksummed or
+ * compressed replies, client-side results). */
+typedef struct b2_resp_ref { uint32_t prefix_len, src_off, src_len, reserved; } b2_resp_ref;   /* 16 bytes */
+
 /* Pointers into ctx-owned PINNED host memory, valid until the next batch call. */
 typedef struct b2_batch_result {
     const b2_run_status* runs;     uint32_t n_runs;
@@ -202,6 +209,7 @@ typedef struct b2_batch_result {
     const uint8_t*       resp;     uint32_t resp_bytes;   /* span of the resp region used */
     float kernel_ms;               /* device time of the kernels (CUDA events) */
     uint32_t n_launches;           /* kernels launched for this batch */
+    const b2_resp_ref*   refs;     /* [n_msgs] in B2_RESP_BY_REF mode, else NULL */
 } b2_batch_result;
 
 typedef struct b2_ctx b2_ctx;
@@ -232,9 +240,28 @@ int  b2_set_server_identity(b2_ctx* ctx, const char* ip_port);
 
 /* ---- block pool: assignable to butil::iobuf::blockmem_allocate/deallocate
  * (src/butil/iobuf.cpp:168-169), same role as rdma::block_pool
- * (src/brpc/rdma/rdma_helper.cpp:579-582).  Memory is cudaHostAlloc'ed. ------ */
+ * (src/brpc/rdma/rdma_helper.cpp:579-582, rdma/block_pool.h:74-105).  Pinned AND mapped memory, pooled: blocks
+ * <= 8 KiB come from 4 MiB slabs, larger ones are cached per power-of-two class; cudaHostAlloc runs per slab, never
+ * per block.  Thread-safe. ------ */
 void* b2_block_alloc(size_t size);
 void  b2_block_free(void* p);
+uint64_t b2_block_pool_host_allocs(void);   /* cudaHostAlloc calls so far (pool diagnostics) */
+
+/* ---- how bytes cross PCIe (both default to COPY) ---------------------------------------------------------
+ * input:  B2_INPUT_COPY  cudaMemcpyAsync of the batch bytes into HBM, kernels read HBM.
+ *         B2_INPUT_PULL  `bytes` of every batch call MUST be memory from b2_block_alloc (pinned + mapped; the socket
+ *                        read blocks themselves, like the RDMA transport's registered blocks): the kernels read it IN
+ *                        PLACE over PCIe, so only what the parse touches crosses the link — frame headers, RpcMeta, the
+ *                        first body bytes, the speculative scan windows; bodies only when a checksum / codec needs them.
+ * resp:   B2_RESP_COPY   every reply frame is materialised in the resp region and copied back.
+ *         B2_RESP_BY_REF an OK echo reply is {prefix in resp, payload = a span of the request bytes} (b2_resp_ref), what
+ *                        SendRpcResponse does with IOBuf references; only descriptors, refs and <= 64-byte prefixes
+ *                        come back.  Everything else (errors, CRC'd / compressed replies) is still materialised. */
+#define B2_INPUT_COPY 0
+#define B2_INPUT_PULL 1
+#define B2_RESP_COPY   0
+#define B2_RESP_BY_REF 1
+int  b2_set_modes(b2_ctx* ctx, int input_mode, int resp_mode);
 
 /* ---- the hot path, host-facing (H2D + kernels + D2H inside) ---------------
  * Replaces, for every run: InputMessenger::ProcessNewMessage

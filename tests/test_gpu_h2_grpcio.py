@@ -51,12 +51,21 @@ def test_live_grpcio_client_against_the_device():
             for i in range(200):                                 # one at a time
                 msg = pb(SIZES[i % len(SIZES)] % 66000, bytes([97 + i % 26]))
                 assert call(msg, timeout=30) == msg
+            import threading
+            gate = threading.BoundedSemaphore(128)               # 128 calls in flight on the one connection (the pool holds 192 streams)
             futs = []
-            for i in range(800):                                 # grpc keeps 100+ of these in flight on the one connection
+            for i in range(800):
                 msg = pb(SIZES[(7 * i) % len(SIZES)] % 66000, bytes([65 + i % 26]))
-                futs.append((msg, call.future(msg, timeout=120, metadata=(("x-trace", "t%d" % (i % 9)),))))
+                gate.acquire()
+                f = call.future(msg, timeout=120, metadata=(("x-trace", "t%d" % (i % 9)),))
+                f.add_done_callback(lambda _f: gate.release())
+                futs.append((msg, f))
             for msg, f in futs:
-                assert f.result() == msg
+                try:
+                    got = f.result()
+                except grpc.RpcError as e:
+                    raise AssertionError("call failed: %s; server loop errors: %r" % (e, srv.errors))
+                assert got == msg
             with pytest.raises(grpc.RpcError) as e:
                 ch.unary_unary("/example.EchoService/Nope", request_serializer=lambda b: b, response_deserializer=lambda b: b)(b"x", timeout=30)
             assert e.value.code() == grpc.StatusCode.UNIMPLEMENTED
