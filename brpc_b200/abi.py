@@ -79,6 +79,11 @@ def _load():
     l.b2_block_free.argtypes = [C.c_void_p]
     l.b2_block_pool_host_allocs.restype = C.c_uint64
     l.b2_set_modes.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    l.b2_ring_start.argtypes = [C.c_void_p]; l.b2_ring_stop.argtypes = [C.c_void_p]
+    l.b2_ring_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+    l.b2_ring_wait.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(BatchResult)]
+    l.b2_ring_launches.restype = C.c_uint64; l.b2_ring_launches.argtypes = [C.c_void_p]
+    l.b2_latency_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
     l.b2_process_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(BatchResult)]
     l.b2_batch_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
     l.b2_batch_collect.argtypes = [C.c_void_p, C.POINTER(BatchResult)]
@@ -115,7 +120,7 @@ lib = _load()
 
 # every symbol include/b2rpc.h declares (tests check the library exports them)
 ABI_SYMBOLS = ["b2_ctx_create", "b2_ctx_destroy", "b2_last_error", "b2_version", "b2_register_method",
-               "b2_set_server_identity", "b2_set_stream_handler", "b2_block_alloc", "b2_block_free", "b2_block_pool_host_allocs", "b2_set_modes", "b2_process_batch", "b2_batch_submit", "b2_batch_collect", "b2_batch_upload",
+               "b2_set_server_identity", "b2_set_stream_handler", "b2_block_alloc", "b2_block_free", "b2_block_pool_host_allocs", "b2_set_modes", "b2_ring_start", "b2_ring_stop", "b2_ring_submit", "b2_ring_wait", "b2_ring_launches", "b2_latency_probe", "b2_process_batch", "b2_batch_submit", "b2_batch_collect", "b2_batch_upload",
                "b2_batch_execute", "b2_batch_execute_many", "b2_batch_download", "b2_batch_launch", "b2_batch_wait",
                "b2_elapsed_ms", "b2_stage_times", "b2_crc32c_batch", "b2_snappy_uncompress_batch", "b2_snappy_compress_batch", "b2_hpack_reset", "b2_hpack_decode_batch", "b2_pack_requests", "b2_h2_scan_batch", "b2_h2_conn_reset", "b2_h2_configure", "b2_h2_process_batch", "b2_h2_pack_responses", "b2_counters_read",
                "b2_counters_device_ptr"]
@@ -202,6 +207,37 @@ class Context:
         if res.refs and res.n_msgs:
             refs = np.ctypeslib.as_array((C.c_uint8 * (16 * res.n_msgs)).from_address(res.refs)).view(REF_DT)
         return {"kernel_ms": res.kernel_ms, "n_launches": res.n_launches, "refs": refs}
+
+    # ---- the persistent latency kernel (b2_ring_*) ----
+    def ring_start(self):
+        _check(lib.b2_ring_start(self._h))
+
+    def ring_stop(self):
+        _check(lib.b2_ring_stop(self._h))
+
+    def ring_submit(self, data, runs, ptr=None, nbytes=None):
+        runs = np.ascontiguousarray(runs, dtype=RUN_DT)
+        if ptr is None:
+            data = np.ascontiguousarray(data, dtype=np.uint8); ptr, nbytes = data.ctypes.data, data.nbytes
+            self._ring_keep = data
+        t = C.c_uint32(0)
+        _check(lib.b2_ring_submit(self._h, ptr, nbytes, runs.ctypes.data, len(runs), C.byref(t)))
+        return t.value
+
+    def ring_wait(self, ticket):
+        res = BatchResult()
+        _check(lib.b2_ring_wait(self._h, ticket, C.byref(res)))
+        rs, msgs, resp = self._views(res)
+        return rs, msgs, resp, self._info(res)
+
+    def latency_probe(self, ptr, nbytes, runs, iters, use_ring):
+        runs = np.ascontiguousarray(runs, dtype=RUN_DT)
+        us = np.zeros(iters, np.float32)
+        _check(lib.b2_latency_probe(self._h, ptr, nbytes, runs.ctypes.data, len(runs), iters, 1 if use_ring else 0, us.ctypes.data))
+        return us
+
+    def ring_launches(self):
+        return int(lib.b2_ring_launches(self._h))
 
     def set_modes(self, input_mode=INPUT_COPY, resp_mode=RESP_COPY):
         _check(lib.b2_set_modes(self._h, input_mode, resp_mode))

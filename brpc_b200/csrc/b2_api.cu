@@ -3,6 +3,7 @@
 // without a CUDA device every entry point fails with B2_E_NO_DEVICE.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <time.h>
 #include <stdlib.h>
 #include <string.h>
 #include <mutex>
@@ -40,6 +41,11 @@ struct b2_ctx {
     TileRec* d_tiles = nullptr; uint32_t* d_tile_base = nullptr; uint32_t* d_tile_scratch = nullptr; uint32_t* d_tile_spec = nullptr; b2_run_status* d_run_status = nullptr;
     uint32_t* d_frame_off = nullptr; uint32_t* d_frame_run = nullptr; b2_msg_desc* d_msgs = nullptr; MsgAux* d_aux = nullptr; PackJob* d_jobs = nullptr; uint32_t* d_slow_idx = nullptr; uint8_t* d_heads = nullptr;
     uint32_t* d_slot = nullptr; uint32_t* d_scan_tmp = nullptr; uint8_t* d_resp = nullptr; uint8_t* d_unz = nullptr; uint16_t* d_snappy_tab = nullptr; HpackState* d_hpack = nullptr; H2Conn* d_h2 = nullptr; H2Stream* d_h2_streams = nullptr; uint8_t* d_h2_slots = nullptr; uint32_t h2_max_conns = B2_H2_MAX_CONNS, h2_pending = B2_H2_MAX_PENDING, h2_stream_bytes = B2_H2_STREAM_BYTES; uint64_t h2_last_in = 0, h2_last_out = 0;   // sizes of the last h2 batch still on the device
+    uint32_t* d_frame_row = nullptr; uint4* d_rows = nullptr;
+    // persistent latency kernel (b2_ring_*): pinned + mapped submit ring, its own stream
+    uint8_t* ring_slots = nullptr; volatile uint32_t* ring_ctl = nullptr; uint32_t* d_ring_ticket = nullptr; cudaStream_t ring_stream = nullptr;
+    uint32_t ring_next = 1, ring_stride = 0, ring_off_runs = 0, ring_off_in = 0, ring_off_out = 0; bool ring_collected[8] = { true, true, true, true, true, true, true, true };
+    const void* ring_bytes[8] = {}; const void* ring_pin_base = nullptr; unsigned long long ring_pin_dev = 0; uint64_t ring_launches = 0;
     uint4* d_refs = nullptr; b2_resp_ref* h_refs = nullptr; int input_mode = B2_INPUT_COPY, resp_mode = B2_RESP_COPY; const uint8_t* pull_bytes = nullptr; uint32_t small_off_refs = 0;
     uint32_t* d_crc_adv = nullptr; unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
     size_t meta_tile_off = 0; uint32_t max_tiles = 0; uint32_t n_sms = 148; bool use_tma_pack = true; uint32_t stage_mask = 7;  // debug: 1 front stages, 2 k_pack_tma, 4 k_pack_slow
@@ -125,12 +131,18 @@ extern "C" void* b2_block_alloc(size_t size) {
 extern "C" void b2_block_free(void* p) { if (p) block_pool().free(p); }
 extern "C" uint64_t b2_block_pool_host_allocs(void) { std::lock_guard<std::mutex> g(block_pool().mu); return block_pool().n_host_alloc; }
 
+static void ring_halt(b2_ctx* c);
 extern "C" void b2_ctx_destroy(b2_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->opt.device);
+    ring_halt(c);
+    if (c->ring_stream) cudaStreamDestroy(c->ring_stream);
+    if (c->ring_slots) cudaFreeHost(c->ring_slots);
+    if (c->ring_ctl) cudaFreeHost((void*)c->ring_ctl);
+    cudaFree(c->d_ring_ticket);
     cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch); cudaFree(c->d_tile_spec);
     cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_frame_run); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_slow_idx); cudaFree(c->d_heads); cudaFree(c->d_slot);
-    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_refs); cudaFreeHost(c->h_refs); cudaFree(c->d_hpack); cudaFree(c->d_h2); cudaFree(c->d_h2_streams); cudaFree(c->d_h2_slots); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
+    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_refs); cudaFree(c->d_frame_row); cudaFree(c->d_rows); cudaFreeHost(c->h_refs); cudaFree(c->d_hpack); cudaFree(c->d_h2); cudaFree(c->d_h2_streams); cudaFree(c->d_h2_slots); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
     cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
     cudaFreeHost(c->h_run_tile_base);
     for (int i = 0; i <= kMaxStages; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -251,7 +263,18 @@ extern "C" int b2_set_server_identity(b2_ctx* c, const char* ip_port) {
 extern "C" int b2_set_modes(b2_ctx* c, int input_mode, int resp_mode) {
     if (!c || (input_mode != B2_INPUT_COPY && input_mode != B2_INPUT_PULL) || (resp_mode != B2_RESP_COPY && resp_mode != B2_RESP_BY_REF)) { set_err("bad mode"); return B2_E_INVAL; }
     static_assert(sizeof(b2_resp_ref) == sizeof(uint4), "b2_resp_ref is 16 bytes");
-    c->input_mode = input_mode; c->resp_mode = resp_mode; c->cfg.by_ref = resp_mode == B2_RESP_BY_REF;
+    if (input_mode == B2_INPUT_PULL && !c->d_rows) {
+        // row stash of the pull walk: spec_k rows of 128 bytes per tile (tiles are >= 32 KiB in this mode unless the caller fixed them)
+        CU(cudaSetDevice(c->opt.device));
+        const uint32_t tile = c->adaptive_tile ? 32768u : c->opt.tile_bytes;
+        const size_t tiles = (size_t)c->opt.max_batch_bytes / tile + c->opt.max_runs + 1;
+        const size_t rows = tiles * (tile >= 2048 ? kSpecKDense : kSpecK);
+        if (cudaMalloc((void**)&c->d_rows, rows * 128) != cudaSuccess || cudaMalloc((void**)&c->d_frame_row, 4 * (size_t)c->opt.max_msgs) != cudaSuccess) {
+            cudaFree(c->d_rows); c->d_rows = nullptr; cudaGetLastError(); set_err("cudaMalloc of the pull-mode row stash failed"); return B2_E_NOMEM;
+        }
+    }
+    ring_halt(c);
+    c->input_mode = input_mode; c->resp_mode = resp_mode; c->cfg.by_ref = resp_mode == B2_RESP_BY_REF; c->cfg.pull = input_mode == B2_INPUT_PULL;
     c->uploaded = false; c->executed = false;
     return B2_OK;
 }
@@ -277,6 +300,7 @@ extern "C" int b2_register_method(b2_ctx* c, const b2_method* m) {
     d.request_type_len = (uint32_t)strlen(m->request_type_name); memcpy(d.request_type, m->request_type_name, d.request_type_len);
     d.handler = m->handler; d.echo_attachment = m->echo_attachment;
     d.response_checksum_type = m->response_checksum_type; d.response_compress_type = m->response_compress_type;
+    ring_halt(c);                                  // (DevConfig is a launch argument of the resident kernel)
     c->methods.push_back(d);
     c->cfg.n_methods = (uint32_t)c->methods.size();
     CU(cudaSetDevice(c->opt.device));
@@ -287,7 +311,7 @@ extern "C" int b2_register_method(b2_ctx* c, const b2_method* m) {
 static BatchPtrs make_ptrs(b2_ctx* c) {
     BatchPtrs B;
     B.bytes = c->d_bytes; B.runs = c->d_runs; B.run_tile_base = c->d_run_tile_base; B.tiles = c->d_tiles;
-    B.tile_base = c->d_tile_base; B.tile_scratch = c->d_tile_scratch; B.tile_spec = c->d_tile_spec; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.frame_run = c->d_frame_run; B.msgs = c->d_msgs;
+    B.tile_base = c->d_tile_base; B.tile_scratch = c->d_tile_scratch; B.tile_spec = c->d_tile_spec; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.frame_run = c->d_frame_run; B.frame_row = c->d_frame_row; B.rows = c->d_rows; B.msgs = c->d_msgs;
     B.aux = c->d_aux; B.jobs = c->d_jobs; B.refs = c->d_refs; B.slow_idx = c->d_slow_idx; B.heads = c->d_heads; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.unz = c->d_unz; B.snappy_tab = c->d_snappy_tab; B.counters = c->d_counters;
     B.totals = c->d_totals; B.methods = c->d_methods; B.crc_adv = c->d_crc_adv;
     B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes;
@@ -315,7 +339,7 @@ extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, co
         // 6-12 messages so the speculative entry search reads a small fraction of it
         uint32_t t = 8192;
         // (B2_INPUT_PULL: the speculative scan window of every tile crosses PCIe, so tiles are 4x larger)
-        const uint32_t per_tile = c->input_mode == B2_INPUT_PULL ? 24u : 6u;
+        const uint32_t per_tile = c->input_mode == B2_INPUT_PULL ? 48u : 6u;
         if (c->input_mode == B2_INPUT_PULL && t < 32768) t = 32768;
         while (t < (1u << 20) && t < per_tile * c->avg_frame) t <<= 1;
         c->cfg.tile_bytes = t; c->cfg.tile_shift = 0; while ((1u << c->cfg.tile_shift) < t) c->cfg.tile_shift++;
@@ -396,7 +420,9 @@ static int launch_pipeline(b2_ctx* c) {
     if (mask & 1) {
     if (c->n_tiles) {
         k_tile_search<<<(c->n_tiles * 32 + 255) / 256, 256, 0, s>>>(B, C); launches++; mark("tile_search");
-        k_tile_walk<<<(c->n_tiles + 127) / 128, 128, 0, s>>>(B, C); launches++; mark("tile_walk");
+        if (C.pull) k_tile_walk_pull<<<(uint32_t)(((uint64_t)c->n_tiles * 8 + 127) / 128), 128, 0, s>>>(B, C);
+        else k_tile_walk<<<(c->n_tiles + 127) / 128, 128, 0, s>>>(B, C);
+        launches++; mark("tile_walk");
     }
     {
         size_t smem = (size_t)c->max_run_tiles * 12;
@@ -564,6 +590,147 @@ extern "C" int b2_process_batch(b2_ctx* c, const void* bytes, uint32_t nbytes, c
     int rc = b2_batch_submit(c, bytes, nbytes, runs, n_runs);
     if (rc != B2_OK) return rc;
     return b2_batch_collect(c, out);
+}
+
+
+// ---- the persistent latency path: submit ring + resident kernel (k_ring) ---------------------------------------------------------
+static void ring_halt(b2_ctx* c) {
+    if (!c->ring_ctl) return;
+    c->ring_ctl[0] = 1; __sync_synchronize();
+    cudaStreamSynchronize(c->ring_stream);
+    c->ring_ctl[0] = 0; c->ring_ctl[1] = 0; __sync_synchronize();
+}
+static int ring_launch(b2_ctx* c) {
+    RingDev R;
+    R.slots = c->ring_slots; R.slot_stride = c->ring_stride; R.off_runs = c->ring_off_runs; R.off_in = c->ring_off_in; R.off_out = c->ring_off_out;
+    R.ctl = c->ring_ctl; R.next_ticket = c->d_ring_ticket;
+    unsigned long long idle_ms = 20; if (const char* e = getenv("B2_RING_IDLE_MS")) idle_ms = (unsigned long long)atoi(e);
+    R.idle_ns = idle_ms * 1000000ull;
+    R.d_bytes = c->d_bytes; R.d_meta = c->d_meta; R.d_small = c->d_small;
+    const bool was_small = c->small; c->small = false;
+    BatchPtrs B = make_ptrs(c);
+    c->small = was_small;
+    B.bytes = c->d_bytes;
+    c->ring_ctl[1] = 1; __sync_synchronize();
+    k_ring<<<1, kSmallThreads, sizeof(SmallSmem), c->ring_stream>>>(R, B, c->cfg);
+    c->ring_launches++;
+    CU(cudaGetLastError());
+    return B2_OK;
+}
+extern "C" int b2_ring_start(b2_ctx* c) {
+    if (!c) return B2_E_INVAL;
+    CU(cudaSetDevice(c->opt.device));
+    if (!c->ring_slots) {
+        c->ring_off_runs = sizeof(RingSlotHdr);
+        c->ring_off_in = (c->ring_off_runs + kSmallRuns * (uint32_t)sizeof(b2_run) + 255u) & ~255u;
+        c->ring_off_out = (c->ring_off_in + kSmallBytes + 1024u + 255u) & ~255u;
+        c->ring_stride = (uint32_t)((c->ring_off_out + kSmallBlock + 4095u) & ~4095u);
+        CU(cudaHostAlloc((void**)&c->ring_slots, (size_t)c->ring_stride * kRingSlots, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(c->ring_slots, 0, (size_t)c->ring_stride * kRingSlots);
+        CU(cudaHostAlloc((void**)&c->ring_ctl, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset((void*)c->ring_ctl, 0, 64);
+        CU(cudaMalloc((void**)&c->d_ring_ticket, 4));
+        const uint32_t one = 1; CU(cudaMemcpy(c->d_ring_ticket, &one, 4, cudaMemcpyHostToDevice));
+        CU(cudaStreamCreateWithFlags(&c->ring_stream, cudaStreamNonBlocking));
+        CU(cudaFuncSetAttribute(k_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
+    }
+    if (!c->ring_ctl[1]) return ring_launch(c);
+    return B2_OK;
+}
+extern "C" int b2_ring_stop(b2_ctx* c) { if (!c) return B2_E_INVAL; cudaSetDevice(c->opt.device); ring_halt(c); return B2_OK; }
+
+extern "C" int b2_ring_submit(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs, uint32_t* ticket) {
+    if (!c || !bytes || !runs || !ticket || n_runs == 0) { set_err("null argument"); return B2_E_INVAL; }
+    if (nbytes > kSmallBytes || n_runs > kSmallRuns) { set_err("b2_ring_submit serves batches up to 128 KiB / 512 runs: use b2_batch_submit"); return B2_E_CAPACITY; }
+    if (!c->ring_slots) { int rc = b2_ring_start(c); if (rc != B2_OK) return rc; }
+    const uint32_t t = c->ring_next, si = t % kRingSlots;
+    if (!c->ring_collected[si]) { set_err("submit ring full: b2_ring_wait the oldest ticket first"); return B2_E_CAPACITY; }
+    for (uint32_t r = 0; r < n_runs; r++)
+        if ((runs[r].offset & 15u) || (uint64_t)runs[r].offset + runs[r].length > nbytes) { set_err("run offset must be 16-aligned and inside the batch"); return B2_E_INVAL; }
+    uint8_t* slot = c->ring_slots + (size_t)si * c->ring_stride;
+    RingSlotHdr* h = reinterpret_cast<RingSlotHdr*>(slot);
+    // the batch bytes: in place when they already live in pinned + mapped memory (b2_block_alloc), else staged into the slot
+    unsigned long long dev = 0;
+    if (bytes == c->ring_pin_base) dev = c->ring_pin_dev;
+    else {
+        cudaPointerAttributes at; memset(&at, 0, sizeof at);
+        if (cudaPointerGetAttributes(&at, bytes) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+            dev = (unsigned long long)(uintptr_t)at.devicePointer; c->ring_pin_base = bytes; c->ring_pin_dev = dev;
+        } else cudaGetLastError();
+    }
+    if (!dev) { memcpy(slot + c->ring_off_in, bytes, nbytes); dev = (unsigned long long)(uintptr_t)(slot + c->ring_off_in); }
+    memcpy(slot + c->ring_off_runs, runs, sizeof(b2_run) * (size_t)n_runs);
+    uint32_t mb = nbytes / 12 + 1; if (mb > kSmallMsgs) mb = kSmallMsgs; if (mb > c->opt.max_msgs) mb = c->opt.max_msgs;
+    h->n_runs = n_runs; h->nbytes = nbytes; h->small_msgs = mb; h->small_resp = nbytes + mb * 80 + 2048;
+    h->off_rs = 64; h->off_msgs = 64 + n_runs * 32; h->off_refs = h->off_msgs + mb * 64; h->off_resp = (h->off_refs + mb * 16 + 255u) & ~255u;
+    h->total = h->off_resp + h->small_resp; h->by_ref = c->cfg.by_ref; h->bytes_dev = dev;
+    c->ring_bytes[si] = bytes; c->ring_collected[si] = false;
+    __sync_synchronize();
+    h->submit = t;
+    __sync_synchronize();
+    c->ring_next = t + 1;
+    *ticket = t;
+    if (!c->ring_ctl[1]) { CU(cudaSetDevice(c->opt.device)); return ring_launch(c); }   // the kernel idled out (or was never started)
+    return B2_OK;
+}
+
+extern "C" int b2_ring_wait(b2_ctx* c, uint32_t ticket, b2_batch_result* out) {
+    if (!c || !out || !c->ring_slots || ticket == 0 || ticket >= c->ring_next || ticket + kRingSlots < c->ring_next) { set_err("bad ring ticket"); return B2_E_INVAL; }
+    const uint32_t si = ticket % kRingSlots;
+    uint8_t* slot = c->ring_slots + (size_t)si * c->ring_stride;
+    RingSlotHdr* h = reinterpret_cast<RingSlotHdr*>(slot);
+    if (c->ring_collected[si]) { set_err("ticket already collected"); return B2_E_INVAL; }
+    uint64_t spins = 0;
+    while (h->done != ticket) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((++spins & 0xfffff) == 0) {
+            if (!c->ring_ctl[1]) { CU(cudaSetDevice(c->opt.device)); int rc = ring_launch(c); if (rc != B2_OK) return rc; }   // lost the exit race: start it again
+            if (cudaStreamQuery(c->ring_stream) != cudaErrorNotReady && h->done != ticket && !c->ring_ctl[1]) continue;
+            if (spins > (1ull << 34)) { set_err("ring kernel did not answer"); return B2_E_CUDA; }
+        }
+    }
+    __sync_synchronize();
+    c->ring_collected[si] = true;
+    memset(out, 0, sizeof *out);
+    const uint8_t* ob = slot + c->ring_off_out;
+    const uint32_t* tot = reinterpret_cast<const uint32_t*>(ob);
+    if (tot[2] & 3u) {
+        // more messages / reply bytes than the compact block holds: the big pipeline serves this batch (after the ring is quiet)
+        for (uint32_t k = 0; k < kRingSlots; k++) if (!c->ring_collected[k]) { set_err("ring overflow fallback needs the other tickets collected first"); return B2_E_CAPACITY; }
+        ring_halt(c);
+        const bool allow = c->allow_small; c->allow_small = false;
+        const int rc = b2_process_batch(c, c->ring_bytes[si], h->nbytes, reinterpret_cast<const b2_run*>(slot + c->ring_off_runs), h->n_runs, out);
+        c->allow_small = allow;
+        return rc;
+    }
+    out->runs = reinterpret_cast<const b2_run_status*>(ob + h->off_rs); out->n_runs = h->n_runs;
+    out->msgs = reinterpret_cast<const b2_msg_desc*>(ob + h->off_msgs); out->n_msgs = tot[0];
+    out->resp = ob + h->off_resp; out->resp_bytes = tot[1];
+    out->refs = h->by_ref ? reinterpret_cast<const b2_resp_ref*>(ob + h->off_refs) : nullptr;
+    out->n_launches = 0; out->kernel_ms = 0.f;
+    if (out->n_msgs) { const uint32_t now = h->nbytes / out->n_msgs; c->avg_frame = c->avg_frame ? (uint32_t)(((uint64_t)c->avg_frame * 3 + now) / 4) : now; }
+    return B2_OK;
+}
+extern "C" uint64_t b2_ring_launches(b2_ctx* c) { return c ? c->ring_launches : 0; }
+
+// measurement helper: wall-clock microseconds of `iters` back-to-back calls, one batch each, timed inside the library so that
+// the caller's language runtime is not part of the number (bench.py's latency line)
+extern "C" int b2_latency_probe(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs, uint32_t iters, int use_ring, float* us_out) {
+    if (!c || !us_out) return B2_E_INVAL;
+    b2_batch_result res;
+    for (uint32_t i = 0; i < iters; i++) {
+        timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
+        int rc;
+        if (use_ring) { uint32_t t = 0; rc = b2_ring_submit(c, bytes, nbytes, runs, n_runs, &t); if (rc == B2_OK) rc = b2_ring_wait(c, t, &res); }
+        else rc = b2_process_batch(c, bytes, nbytes, runs, n_runs, &res);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        if (rc != B2_OK) return rc;
+        if (res.n_msgs == 0) { set_err("latency probe batch produced no messages"); return B2_E_INVAL; }
+        us_out[i] = (float)((t1.tv_sec - t0.tv_sec) * 1e6 + (t1.tv_nsec - t0.tv_nsec) * 1e-3);
+    }
+    return B2_OK;
 }
 
 extern "C" int b2_stage_times(b2_ctx* c, const char** names, float* ms, int cap) {

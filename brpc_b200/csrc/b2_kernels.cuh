@@ -78,6 +78,7 @@ struct DevConfig {
     uint32_t stream_handler;      // B2_STREAM_*
     uint32_t spec_k;              // speculative frame offsets kept per tile: kSpecK, or kSpecKDense when tiles hold many small frames
     uint32_t by_ref;              // B2_RESP_BY_REF: OK echo replies are {prefix, reference into the request bytes}
+    uint32_t pull;                // B2_INPUT_PULL: `bytes` is mapped host memory; the walk stashes each frame's first 128 bytes in HBM
     char identity[64];            // "ip:port" of Controller::AppendServerIdentiy
 };
 
@@ -94,6 +95,8 @@ struct BatchPtrs {
     b2_run_status* run_status;
     uint32_t* frame_off;             // [max_msgs] frame offsets (batch-relative), bit 31 = protocol - 1
     uint32_t* frame_run;             // [max_msgs] run index of every message
+    uint32_t* frame_row;             // [max_msgs] B2_INPUT_PULL: index of the frame's stashed row (kNone = read the bytes in place)
+    uint4* rows;                     // [n_tiles * spec_k][8] B2_INPUT_PULL: the 128 bytes at (frame start & ~15), fetched ONCE over PCIe by the walk
     b2_msg_desc* msgs;
     MsgAux* aux;
     PackJob* jobs;                   // [max_msgs]
@@ -304,6 +307,64 @@ __global__ void __launch_bounds__(128) k_tile_walk(BatchPtrs B, DevConfig C) {
     B.tiles[t] = rec;
 }
 
+// --- k_tile_walk_pull: B2_INPUT_PULL, eight lanes per tile ----------------------------------------------
+// The batch lives in mapped host memory: every load is a PCIe read (~2 us, <= 575 M requests/s, ~50 GB/s).  The walk
+// is the only stage that HAS to touch each frame, so it fetches, per hop, the 128 bytes at (position & ~15) with ONE
+// coalesced load of the tile's eight lanes, decides the step from the header inside them (same rules as
+// walk_tile_spec) and stashes the row in HBM; k_decode then finds header, RpcMeta and the first body bytes of every
+// message in that stash and never goes back over the link.  One ~128-byte read per message is all that crosses.
+__global__ void __launch_bounds__(128) k_tile_walk_pull(BatchPtrs B, DevConfig C) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = g >> 3, sub = threadIdx.x & 7u, lane = threadIdx.x & 31u;
+    if (t >= B.n_tiles) return;                                       // (whole groups of eight leave together)
+    const uint32_t gmask = 0xffu << (lane & 24u), l0 = lane & 24u;
+    const uint4 ti = __ldg(B.tile_info + t);
+    const uint32_t k = ti.z, len = ti.y;
+    const uint8_t* run = B.bytes + ti.x;
+    const bool client = ((ti.w >> 24) & B2_RUN_CLIENT) != 0;
+    const uint32_t tile_end = (k + 1) << C.tile_shift, cap = C.spec_k;
+    uint32_t* spec = B.tile_spec + (size_t)t * cap;
+    uint4* rows = B.rows + (size_t)t * cap * 8;
+    TileRec rec;
+    rec.entry = B.tiles[t].entry; rec.exit = 0; rec.count = 0; rec.kind = kStop; rec.last_proto = 0; rec.live = 0; rec.pf_in = -1;
+    if (rec.entry != kNone) {
+        uint32_t pos = rec.entry, count = 0; int pf = -1, last = 0; uint8_t kind = kRanOff;
+        while (pos < tile_end) {
+            bool fast = false; uint32_t new_pos = pos, frame_pos = pos; int idx = 0, err = B2_PARSE_OK; bool popped = false;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (len - pos >= 12) {
+                v = __ldg(reinterpret_cast<const uint4*>(run + (pos & ~15u)) + sub);      // (the buffer has 1 KiB of slack past its end)
+                // the 12 header bytes start at byte (pos & 15) of the row: words from lanes 0 and 1 of the group
+                const uint32_t a0 = __shfl_sync(gmask, v.x, l0), a1 = __shfl_sync(gmask, v.y, l0), a2 = __shfl_sync(gmask, v.z, l0), a3 = __shfl_sync(gmask, v.w, l0);
+                const uint32_t b0 = __shfl_sync(gmask, v.x, l0 + 1), b1 = __shfl_sync(gmask, v.y, l0 + 1), b2 = __shfl_sync(gmask, v.z, l0 + 1);
+                const uint32_t q = (pos & 15u) >> 2, sh = 8u * (pos & 3u);
+                const uint32_t w0 = q == 0 ? a0 : q == 1 ? a1 : q == 2 ? a2 : a3, w1 = q == 0 ? a1 : q == 1 ? a2 : q == 2 ? a3 : b0;
+                const uint32_t w2 = q == 0 ? a2 : q == 1 ? a3 : q == 2 ? b0 : b1, w3 = q == 0 ? a3 : q == 1 ? b0 : q == 2 ? b1 : b2;
+                const uint32_t h0 = sh ? __funnelshift_r(w0, w1, sh) : w0, h1 = sh ? __funnelshift_r(w1, w2, sh) : w1, h2 = sh ? __funnelshift_r(w2, w3, sh) : w2;
+                idx = h0 == kMagicPRPC ? 1 : h0 == kMagicSTRM ? 2 : 0;
+                const uint32_t body = __byte_perm(h1, 0, 0x0123), meta = __byte_perm(h2, 0, 0x0123);
+                if (idx && (uint64_t)body <= C.max_body_size && (uint64_t)(len - pos) >= 12ull + body && meta <= body) { fast = true; new_pos = pos + 12 + body; }
+            }
+            if (!fast) {                                              // short tails, oversize bodies, meta > body, unknown bytes: the generic restatement
+                Step s; s.err = 0; s.index = 0; s.new_pos = 0; s.frame_pos = 0; s.popped = false;
+                if (sub == 0) s = cut_input_message(run, len, pos, pf, C.max_body_size, client);
+                err = __shfl_sync(gmask, s.err, l0); idx = __shfl_sync(gmask, s.index, l0); new_pos = __shfl_sync(gmask, s.new_pos, l0);
+                frame_pos = __shfl_sync(gmask, s.frame_pos, l0); popped = __shfl_sync(gmask, (int)s.popped, l0) != 0;
+                if (count == 0 && popped) { kind = kAmbig; break; }
+                if (err != B2_PARSE_OK) { kind = kStop; break; }
+                v = __ldg(reinterpret_cast<const uint4*>(run + (frame_pos & ~15u)) + sub);
+            }
+            if (count < cap) {
+                if (sub == 0) spec[count] = (ti.x + frame_pos) | ((uint32_t)(idx - 1) << 31);
+                rows[(size_t)count * 8 + sub] = v;
+            }
+            count++; last = idx; pf = idx; pos = new_pos;
+        }
+        rec.exit = pos; rec.count = count; rec.kind = kind; rec.last_proto = (int8_t)last;
+    }
+    if (sub == 0) B.tiles[t] = rec;
+}
+
 // --- run prefix: exclusive scan of n_msgs over runs, done by the LAST CTA of k_resolve to finish -------
 __device__ __forceinline__ void run_prefix_body(const BatchPtrs& B, uint32_t* s_warp, uint32_t* s_carry) {
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -472,9 +533,9 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C, uint3
 
 // --- k_frame_table ------------------------------------------------------------
 struct EmitFrame {
-    uint32_t* out; uint32_t* out_run; uint32_t run_off; uint32_t run_idx; uint32_t cap_left;
+    uint32_t* out; uint32_t* out_run; uint32_t run_off; uint32_t run_idx; uint32_t cap_left; uint32_t* out_row;
     __device__ __forceinline__ void operator()(uint32_t i, const Step& s) const {
-        if (i < cap_left) { out[i] = (run_off + s.frame_pos) | ((uint32_t)(s.index - 1) << 31); out_run[i] = run_idx; }
+        if (i < cap_left) { out[i] = (run_off + s.frame_pos) | ((uint32_t)(s.index - 1) << 31); out_run[i] = run_idx; if (out_row) out_row[i] = kNone; }
     }
 };
 // kSpecK threads per tile: a live tile that k_resolve accepted as speculated hands over the offsets k_tile_walk
@@ -492,7 +553,10 @@ __global__ void __launch_bounds__(256) k_frame_table(BatchPtrs B, DevConfig C) {
     const uint32_t r = ti.w & 0xffffffu;
     const uint32_t first = B.run_status[r].first_msg + B.tile_base[t];
     if (!(rec.kind & kKindRewalked) && rec.count <= spec_k) {
-        if (j < rec.count && first + j < B.max_msgs) { B.frame_off[first + j] = B.tile_spec[(size_t)t * spec_k + j]; B.frame_run[first + j] = r; }
+        if (j < rec.count && first + j < B.max_msgs) {
+            B.frame_off[first + j] = B.tile_spec[(size_t)t * spec_k + j]; B.frame_run[first + j] = r;
+            if (C.pull) B.frame_row[first + j] = t * spec_k + j;
+        }
         return;
     }
     if (j != 0) return;
@@ -500,6 +564,7 @@ __global__ void __launch_bounds__(256) k_frame_table(BatchPtrs B, DevConfig C) {
     b2_run run; run.offset = ti.x; run.length = ti.y; run.flags = ti.w >> 24;
     TileRec tmp;
     EmitFrame e; e.out = B.frame_off + first; e.out_run = B.frame_run + first; e.run_off = run.offset; e.run_idx = r; e.cap_left = B.max_msgs - first;
+    e.out_row = C.pull ? B.frame_row + first : nullptr;
     walk_tile<false>(B.bytes + run.offset, run.length, rec.entry, rec.pf_in, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, tmp, e);
 }
 
@@ -591,22 +656,25 @@ struct DecodeWarpSmem {
 };
 
 __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
-                                           const uint8_t* srow, uint8_t* shead);
+                                           const uint8_t* srow, uint8_t* shead, uint32_t row_bytes);
 
 // one warp round: 32 consecutive messages starting at i0 (staging, decode, head write-out)
 __device__ __forceinline__ void decode_round(const BatchPtrs& B, const DevConfig& C, DecodeWarpSmem& S, uint32_t i0, uint32_t n_msgs, uint32_t lane) {
     const uint32_t i = i0 + lane;
     const uint32_t fo_raw = i < n_msgs ? B.frame_off[i] : 0;
+    const uint32_t my_row = (C.pull && i < n_msgs) ? B.frame_row[i] : kNone;      // B2_INPUT_PULL: the walk stashed this frame's first 128 bytes
     const uint32_t nm = min(32u, n_msgs - i0);
     // stage: row m <- the 16-byte aligned vectors covering frame m's first bytes; half a warp per row
     const uint32_t sub = lane & 15, half = lane >> 4;
     for (uint32_t m2 = 0; m2 < nm; m2 += 2) {
         const uint32_t m = m2 + half;
         const uint32_t f = __shfl_sync(0xffffffffu, fo_raw, m & 31) & 0x7fffffffu;
-        if (m < nm && sub < kRowVecs) {
+        const uint32_t row = __shfl_sync(0xffffffffu, my_row, m & 31);
+        if (m < nm && sub < kRowVecs && (row == kNone || sub < 8)) {
             // cp.async (LDGSTS): global -> shared without a register round trip, so all 16 trips are in flight together
             const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.row[m][sub]);
-            const uint4* src = reinterpret_cast<const uint4*>(B.bytes + (f & ~15u)) + sub;       // (buffer is padded past its end)
+            const uint4* src = row == kNone ? reinterpret_cast<const uint4*>(B.bytes + (f & ~15u)) + sub       // (buffer is padded past its end)
+                                            : B.rows + (size_t)row * 8 + sub;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
         }
     }
@@ -615,7 +683,7 @@ __device__ __forceinline__ void decode_round(const BatchPtrs& B, const DevConfig
     __syncwarp();
     bool is_slow = false, is_verify = false;
     if (i < n_msgs) {
-        decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 15u), S.head[lane]);
+        decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 15u), S.head[lane], my_row == kNone ? kRowBytes : 128u);
         const uint32_t f = B.jobs[i].fast; is_slow = f == 0; is_verify = f == 2;
     }
     const uint32_t slow_mask = __ballot_sync(0xffffffffu, is_slow);
@@ -653,13 +721,13 @@ __global__ void __launch_bounds__(kDecodeWarps * 32, B2_DECODE_MIN_BLOCKS) k_dec
 }
 
 __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
-                                           const uint8_t* srow, uint8_t* shead) {
+                                           const uint8_t* srow, uint8_t* shead, uint32_t row_bytes) {
     const uint32_t fo = fo_raw & 0x7fffffffu;
     const int proto = (int)(fo_raw >> 31) + 1;
     const uint8_t* gframe = B.bytes + fo;
     // decode from the staged copy when header + meta + the first body bytes are inside it
     const uint32_t meta_size_peek = load_be32(srow + 8);
-    const bool staged = (uint64_t)(fo_raw & 15u) + 12ull + meta_size_peek + 40ull <= kRowBytes;
+    const bool staged = (uint64_t)(fo_raw & 15u) + 12ull + meta_size_peek + 40ull <= row_bytes;
     const uint8_t* frame = staged ? srow : gframe;
     b2_msg_desc d;
     d.frame_off = fo; d.body_size = load_be32(frame + 4); d.meta_size = load_be32(frame + 8);
@@ -1927,11 +1995,8 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_t
     total = tot;
     return base + x - v;
 }
-__global__ void __launch_bounds__(kSmallThreads, 1) k_small(BatchPtrs B, DevConfig C) {
-    extern __shared__ __align__(128) uint8_t small_raw[];
-    SmallSmem& S = *reinterpret_cast<SmallSmem*>(small_raw);
+__device__ __forceinline__ void small_body(const BatchPtrs& B, const DevConfig& C, SmallSmem& S) {
     const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    crc_tabs_to_smem(S.s_hot, B.crc_adv);
     CrcTabs ct; ct.hot = S.s_hot; ct.tree = B.crc_adv + kCrcHotWords;
     // ---- cut loop: thread per run (ProcessNewMessage over the whole run)
     uint32_t my_count = 0; b2_run_status st; st.consumed = 0; st.parse_error = B2_PARSE_ERROR_NOT_ENOUGH_DATA; st.n_msgs = 0;
@@ -1961,7 +2026,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(BatchPtrs B, DevConf
             const Step sp = cut_input_message(B.bytes + run.offset, run.length, pos, pf, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0);
             if (sp.err != B2_PARSE_OK) break;
             B.frame_off[first + k] = (run.offset + sp.frame_pos) | ((uint32_t)(sp.index - 1) << 31);
-            B.frame_run[first + k] = tid; k++;
+            B.frame_run[first + k] = tid; if (C.pull) B.frame_row[first + k] = kNone; k++;
             pos = sp.new_pos; pf = sp.pf;
         }
         B.run_status[tid] = st;
@@ -2009,6 +2074,123 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(BatchPtrs B, DevConf
         if (st.parse_error != B2_PARSE_ERROR_NOT_ENOUGH_DATA) atomicAdd(B.counters + 4, 1ull);
         if (tid == 0) atomicAdd(B.counters + 5, 1ull);
     }
+}
+
+__global__ void __launch_bounds__(kSmallThreads, 1) k_small(BatchPtrs B, DevConfig C) {
+    extern __shared__ __align__(128) uint8_t small_raw[];
+    SmallSmem& S = *reinterpret_cast<SmallSmem*>(small_raw);
+    crc_tabs_to_smem(S.s_hot, B.crc_adv);
+    small_body(B, C, S);
+}
+
+// --- k_ring: the persistent latency kernel ----------------------------------------------------------------------
+// One resident CTA per context polls a submit ring in pinned + mapped host memory (the doorbell is a plain host store,
+// there is no launch and no cudaMemcpy per batch): when slot (ticket % kRingSlots) carries `ticket`, the CTA pulls the
+// slot's runs and the batch bytes out of host memory with coalesced 16-byte loads into HBM, runs small_body (the same
+// device code as k_small) and pushes the compact result block straight into the slot's pinned output area with posted
+// PCIe writes, then releases `done = ticket` system-wide.  It leaves on `stop` or after idle_ns without work (so that
+// device-wide synchronisation points — cudaFree, cudaDeviceSynchronize — are never held for long); the host relaunches
+// it with the next submission.
+constexpr uint32_t kRingSlots = 8;
+struct RingSlotHdr {                 // in mapped host memory, one per slot; the host fills everything, then stores `submit` last
+    volatile uint32_t submit;        // ticket of the submission this slot carries
+    uint32_t n_runs, nbytes, small_msgs;
+    uint32_t small_resp, off_rs, off_msgs, off_refs;
+    uint32_t off_resp, total, by_ref, reserved;
+    unsigned long long bytes_dev;    // device-visible address of the batch bytes (the caller's pinned block, or the slot's staging area)
+    unsigned long long pad0;
+    volatile uint32_t done;          // device: ticket, after the output block is visible
+    uint32_t pad1[15];
+};                                   // 128 bytes
+struct RingDev {
+    uint8_t* slots;                  // mapped host memory: kRingSlots x slot_stride
+    uint32_t slot_stride, off_runs, off_in, off_out;     // layout of one slot: [RingSlotHdr | runs | staged input | output block]
+    volatile uint32_t* ctl;          // mapped host memory: [0] stop  [1] running  [2] batches served
+    uint32_t* next_ticket;           // device memory: ticket the kernel waits for next (survives relaunches)
+    unsigned long long idle_ns;
+    uint8_t* d_bytes; uint8_t* d_meta; uint8_t* d_small;   // device staging: batch bytes, runs, compact output block
+};
+__device__ __forceinline__ uint32_t ld_sys_u32(const volatile uint32_t* p) {
+    uint32_t v; asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_sys_u32(volatile uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+__global__ void __launch_bounds__(kSmallThreads, 1) k_ring(RingDev R, BatchPtrs B0, DevConfig C) {
+    extern __shared__ __align__(128) uint8_t small_raw[];
+    SmallSmem& S = *reinterpret_cast<SmallSmem*>(small_raw);
+    __shared__ uint32_t s_go;
+    __shared__ RingSlotHdr s_hdr;
+    const uint32_t tid = threadIdx.x;
+    crc_tabs_to_smem(S.s_hot, B0.crc_adv);
+    uint32_t ticket = *R.next_ticket;
+    for (;;) {
+        uint8_t* slot = R.slots + (size_t)(ticket % kRingSlots) * R.slot_stride;
+        RingSlotHdr* hdr = reinterpret_cast<RingSlotHdr*>(slot);
+        if (tid == 0) {
+            const unsigned long long t0 = globaltimer_ns();
+            uint32_t go = 0;
+            for (;;) {
+                if (ld_sys_u32(&hdr->submit) == ticket) { go = 1; break; }
+                if (ld_sys_u32(R.ctl + 0)) break;
+                if (globaltimer_ns() - t0 > R.idle_ns) {
+                    // leave: announce it first, then look once more so that a submission racing with the exit is not lost
+                    st_sys_u32(R.ctl + 1, 0); __threadfence_system();
+                    if (ld_sys_u32(&hdr->submit) == ticket) { st_sys_u32(R.ctl + 1, 1); go = 1; }
+                    break;
+                }
+            }
+            s_go = go;
+        }
+        __syncthreads();
+        if (!s_go) break;
+        // the slot header (the host's stores are ordered before `submit` by its release fence)
+        if (tid < sizeof(RingSlotHdr) / 4) reinterpret_cast<uint32_t*>(&s_hdr)[tid] = ld_sys_u32(reinterpret_cast<const volatile uint32_t*>(slot) + tid);
+        __syncthreads();
+        const uint32_t n_runs = s_hdr.n_runs, nbytes = s_hdr.nbytes;
+        {   // pull: runs (24 B each) + per-run tile base placeholder, then the batch bytes, 16 bytes per thread per trip
+            const uint4* src = reinterpret_cast<const uint4*>(slot + R.off_runs);
+            uint4* dst = reinterpret_cast<uint4*>(R.d_meta);
+            for (uint32_t k = tid; k < (n_runs * 24u + 15u) / 16u; k += kSmallThreads) dst[k] = src[k];
+            const uint4* bs = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(s_hdr.bytes_dev));
+            uint4* bd = reinterpret_cast<uint4*>(R.d_bytes);
+            const uint32_t nv = (nbytes + 15u) / 16u;
+            uint32_t k = tid;
+            for (; k + 3 * kSmallThreads < nv; k += 4 * kSmallThreads) {              // four loads in flight per thread
+                const uint4 a = bs[k], b = bs[k + kSmallThreads], c = bs[k + 2 * kSmallThreads], d = bs[k + 3 * kSmallThreads];
+                bd[k] = a; bd[k + kSmallThreads] = b; bd[k + 2 * kSmallThreads] = c; bd[k + 3 * kSmallThreads] = d;
+            }
+            for (; k < nv; k += kSmallThreads) bd[k] = bs[k];
+        }
+        BatchPtrs B = B0;
+        B.bytes = R.d_bytes; B.runs = reinterpret_cast<const b2_run*>(R.d_meta); B.n_runs = n_runs;
+        B.totals = reinterpret_cast<uint32_t*>(R.d_small);
+        B.run_status = reinterpret_cast<b2_run_status*>(R.d_small + s_hdr.off_rs);
+        B.msgs = reinterpret_cast<b2_msg_desc*>(R.d_small + s_hdr.off_msgs);
+        B.refs = reinterpret_cast<uint4*>(R.d_small + s_hdr.off_refs);
+        B.resp = R.d_small + s_hdr.off_resp;
+        B.max_msgs = s_hdr.small_msgs; B.max_resp = s_hdr.small_resp;
+        DevConfig Cb = C; Cb.by_ref = s_hdr.by_ref; Cb.pull = 0;
+        if (tid < 16) B.totals[tid] = 0;
+        __threadfence();
+        __syncthreads();
+        small_body(B, Cb, S);
+        __threadfence();
+        __syncthreads();
+        {   // push the compact block [totals | run_status | msgs | refs | resp] into the slot's output area
+            const uint32_t used = (B.totals[2] & 3u) ? 64u : s_hdr.off_resp + ((B.totals[1] + 15u) & ~15u);
+            const uint4* src = reinterpret_cast<const uint4*>(R.d_small);
+            uint4* dst = reinterpret_cast<uint4*>(slot + R.off_out);
+            for (uint32_t k = tid; k < (used + 15u) / 16u; k += kSmallThreads) dst[k] = __ldcg(src + k);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) { st_sys_u32(&hdr->done, ticket); st_sys_u32(R.ctl + 2, ticket + 1); }
+        ticket++;
+    }
+    if (tid == 0) *R.next_ticket = ticket;
 }
 
 #endif  // __CUDACC__

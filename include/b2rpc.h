@@ -280,6 +280,30 @@ int  b2_process_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
 int  b2_batch_submit(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs);
 int  b2_batch_collect(b2_ctx* ctx, b2_batch_result* out);
 
+/* ---- the latency path: a PERSISTENT kernel per context fed through a submit ring (north star: "a persistent per-GPU kernel
+ * pulls batches of raw socket bytes staged into pinned host IOBuf blocks") -----------------------------------------------
+ * For batches of up to 128 KiB / 512 runs / 1024 messages — what a set of synchronous clients keeps in flight — there is no
+ * kernel launch, no cudaMemcpy and no stream synchronisation per batch: b2_ring_submit fills a slot of a ring that lives in
+ * pinned + mapped host memory and rings its doorbell with a plain store; the resident kernel (one CTA, started by
+ * b2_ring_start or by the first submission) polls the doorbell over PCIe, pulls runs and bytes (in place when `bytes` is
+ * b2_block_alloc memory, else from the slot's staging copy), runs the same cut / decode / echo / pack code as
+ * b2_process_batch and writes descriptors + replies straight into the slot's pinned output block; b2_ring_wait spins on the
+ * slot's completion word.  Same role as the RDMA transport's always-polling completion loop (RdmaEndpoint::PollCq,
+ * src/brpc/rdma/rdma_endpoint.cpp:1470-1591).  Up to 8 tickets may be in flight; a result stays valid until 8 further
+ * submissions.  The kernel retires after 20 ms without work (B2_RING_IDLE_MS) so that it never blocks device-wide
+ * synchronisation for long, and comes back with the next submission.  A batch whose results do not fit the compact block is
+ * served by the big pipeline inside b2_ring_wait (needs every other ticket collected).  Not to be mixed with concurrent
+ * batch calls on the same context. */
+int  b2_ring_start(b2_ctx* ctx);
+int  b2_ring_stop(b2_ctx* ctx);
+int  b2_ring_submit(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs, uint32_t* ticket);
+int  b2_ring_wait(b2_ctx* ctx, uint32_t ticket, b2_batch_result* out);
+uint64_t b2_ring_launches(b2_ctx* ctx);   /* how many times the resident kernel was (re)started: the launches of the ring path */
+/* Measurement helper: us_out[i] = wall-clock microseconds of the i-th of `iters` back-to-back single-batch calls —
+ * b2_process_batch (use_ring 0) or b2_ring_submit + b2_ring_wait (use_ring 1) — timed inside the library. */
+int  b2_latency_probe(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs,
+                      uint32_t iters, int use_ring, float* us_out);
+
 /* ---- the same path split in three, for measurement with inputs resident in
  * HBM (bench.py `value`): upload once, execute many times, download. -------- */
 int  b2_batch_upload(b2_ctx* ctx, const void* bytes, uint32_t nbytes,

@@ -1,30 +1,33 @@
-"""Latency probe (not product): where the ~70 us of a 64-request b2_process_batch go."""
+"""latency probe (not product): 64 connections x one 1 KB request per batch — blocking b2_process_batch vs the persistent
+ring (b2_ring_submit + b2_ring_wait), pinned host buffers."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import brpc_b200
 from brpc_b200 import press
 from brpc_b200.abi import PinnedBuffer
-torch.cuda.set_device(0)
 N = 64
 ctx = brpc_b200.Context(device=0, max_batch_bytes=1 << 20, max_msgs=4096, max_runs=N)
-sp = press.spec(payload_bytes=1024)
-f = press.frame(sp, 1); stride = (len(f) + 15) // 16 * 16
+sp = press.spec(payload_bytes=1024); f = press.frame(sp, 1); stride = (len(f) + 15) // 16 * 16
 buf = PinnedBuffer(N * stride); runs = np.zeros(N, dtype=brpc_b200.RUN_DT)
 for s in range(N):
     fr = press.frame(sp, (s << 32) + 7); buf.array[s * stride:s * stride + len(fr)] = np.frombuffer(fr, np.uint8); runs[s] = (s, s * stride, len(fr), 1, 0)
-def med(fn, n=2000):
-    for _ in range(100): fn()
-    t = []
-    for _ in range(n):
-        t0 = time.perf_counter(); fn(); t.append((time.perf_counter() - t0) * 1e6)
-    t.sort(); return t[len(t) // 2]
-whole = med(lambda: ctx.process_batch_ptr(buf.ptr, N * stride, runs))
-def up_only(): ctx.upload_ptr(buf.ptr, N * stride, runs); torch.cuda.synchronize()
-def up_exec(): ctx.upload_ptr(buf.ptr, N * stride, runs); ctx.launch(); ctx.wait()
-def up_exec_dl(): ctx.upload_ptr(buf.ptr, N * stride, runs); ctx.launch(); ctx.wait(); ctx.download()
-a, b, c = med(up_only), med(up_exec), med(up_exec_dl)
-ctx.upload_ptr(buf.ptr, N * stride, runs)
-kern = med(lambda: (ctx.launch(), ctx.wait()))
-noop = med(lambda: torch.cuda.synchronize())
-print("process_batch %.1f us | upload+sync %.1f | upload+kernel+wait %.1f | +download %.1f | launch+wait alone %.1f | bare sync %.1f" % (whole, a, b, c, kern, noop))
+def pct(v, p): v = sorted(v); return v[int(len(v) * p)]
+for by_ref in (0, 1):
+    ctx.set_modes(0, by_ref)
+    for _ in range(50): ctx.process_batch_ptr(buf.ptr, N * stride, runs)
+    lat = []
+    for _ in range(3000):
+        t0 = time.perf_counter(); r = ctx.process_batch_ptr(buf.ptr, N * stride, runs); lat.append((time.perf_counter() - t0) * 1e6)
+    print("by_ref=%d blocking call: p50 %.1f us  p99 %.1f us" % (by_ref, pct(lat, .5), pct(lat, .99)))
+    ctx.ring_start()
+    for _ in range(50): ctx.ring_wait(ctx.ring_submit(None, runs, ptr=buf.ptr, nbytes=N * stride))
+    lat = []
+    for _ in range(3000):
+        t0 = time.perf_counter(); r = ctx.ring_wait(ctx.ring_submit(None, runs, ptr=buf.ptr, nbytes=N * stride)); lat.append((time.perf_counter() - t0) * 1e6)
+    assert len(r[1]) == N and np.all(r[1]["status"] == 0)
+    print("by_ref=%d ring         : p50 %.1f us  p99 %.1f us  (kernel (re)starts: %d)" % (by_ref, pct(lat, .5), pct(lat, .99), ctx.ring_launches()))
+    for ring in (0, 1):
+        us = np.sort(ctx.latency_probe(buf.ptr, N * stride, runs, 3000, ring))
+        print("by_ref=%d C-timed %s: p50 %.1f us  p99 %.1f us  min %.1f" % (by_ref, "ring    " if ring else "blocking", us[1500], us[2970], us[0]))
+    ctx.ring_stop()
