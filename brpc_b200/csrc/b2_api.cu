@@ -61,7 +61,7 @@ struct b2_ctx {
     int n_stages = 0;
     float last_kernel_ms = 0.f; uint32_t last_launches = 0;
     cudaEvent_t ev_first = nullptr, ev_last = nullptr; bool first_pending = true;
-    bool profile_stages = false; bool allow_small = true;
+    bool profile_stages = false; bool allow_small = true; bool use_fused = true; bool fused_last = false; bool slow_heavy = false;   // slow_heavy: the previous batch sent > 1/8 of its messages to k_pack_slow (CRC'd / compressed traffic): the classic pipeline serves that better
     bool adaptive_tile = false; bool dense = false; uint32_t avg_frame = 0;   // tile size follows the message size of the previous batch      // per-stage events only when a harness asks for stage times
     // small-batch (latency) mode: one compact H2D block, one compact output block, one D2H, one sync
     uint8_t* d_meta = nullptr; uint8_t* h_meta = nullptr;       // [runs | run_tile_base]
@@ -220,7 +220,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     HALLOC(c->h_msgs, sizeof(b2_msg_desc) * (size_t)o->max_msgs);
     HALLOC(c->h_refs, sizeof(b2_resp_ref) * (size_t)o->max_msgs);
     HALLOC(c->h_resp, (size_t)c->opt.max_resp_bytes);
-    HALLOC(c->h_totals, 16);
+    HALLOC(c->h_totals, 64);
     HALLOC(c->h_run_tile_base, 4 * ((size_t)o->max_runs + 1));
     CU(cudaMemset(c->d_counters, 0, 8 * B2_N_COUNTERS));
     CU(cudaMemset(c->d_bytes, 0, (size_t)o->max_batch_bytes + 1024));
@@ -245,6 +245,8 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     CU(cudaFuncSetAttribute(k_pack_tma<kPackGroupSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PackWarpSmem) * kPackWarps)));
     if (const char* e = getenv("B2_PACK")) c->use_tma_pack = strcmp(e, "reg") != 0;
     if (const char* e = getenv("B2_SMALL")) c->use_fused_small = strcmp(e, "off") != 0;
+    if (const char* e = getenv("B2_FUSED")) c->use_fused = strcmp(e, "off") != 0;
+    CU(cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FusedWarpSmem) * kFusedWarps)));
     CU(cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
     *out = c;
     return B2_OK;
@@ -399,7 +401,11 @@ extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, co
 
 static int launch_pipeline(b2_ctx* c) {
     const BatchPtrs B = make_ptrs(c);
-    const DevConfig C = c->cfg;
+    DevConfig C = c->cfg;
+    // the fused decode+pack kernel serves batches whose bytes and replies both live in HBM
+    const bool fused = c->use_fused && !c->slow_heavy && !c->small && c->input_mode == B2_INPUT_COPY && c->resp_mode == B2_RESP_COPY && c->use_tma_pack &&
+                       (((uint64_t)c->nbytes + 255) & ~255ull) + 4096 <= c->opt.max_resp_bytes;
+    C.fused = fused ? 1u : 0u; C.ovf_base = (c->nbytes + 255u) & ~255u; c->fused_last = fused;
     cudaStream_t s = c->stream;
     int st = 0; uint32_t launches = 0;
     const bool prof = c->profile_stages;
@@ -429,6 +435,10 @@ static int launch_pipeline(b2_ctx* c) {
         if (smem > 200 * 1024) smem = 0;                 // some run does not fit: EVERY run of this launch uses the global scratch
         k_resolve<<<c->n_runs, 256, smem, s>>>(B, C, smem == 0 ? 1u : 0u); launches++; mark("resolve");
     }
+    if (fused) {
+        // one pass over the bytes: decode + echo + pack per live tile (k_frame_table / k_decode / k_scan / k_pack_tma are not needed)
+        if (c->n_tiles) { k_fused<<<sms, kFusedWarps * 32, sizeof(FusedWarpSmem) * kFusedWarps, s>>>(B, C); launches++; mark("fused"); }
+    } else {
     if (c->n_tiles) { k_frame_table<<<(uint32_t)(((uint64_t)c->n_tiles * C.spec_k + 255) / 256), 256, 0, s>>>(B, C); launches++; mark("frame_table"); }
     // message-count dependent kernels are persistent: fixed grids (multiples of the SM count)
     // stride over the device-side message count, so no host round trip sizes a launch
@@ -436,7 +446,10 @@ static int launch_pipeline(b2_ctx* c) {
     k_scan_blocks<<<sms, kScanBlock, 0, s>>>(B); launches++;
     mark("scan");
     }
-    if (c->use_tma_pack) {
+    }
+    if (fused) {
+        if (mask & 4) { k_pack_slow<<<sms * B2_SLOW_MIN_BLOCKS, 256, 8 * kSnapRing, s>>>(B, C); launches++; mark("pack_slow"); }
+    } else if (c->use_tma_pack) {
         // k_pack_slow first: its verify pass decides which CRC-carrying echoes k_pack_tma may move
         if (mask & 4) { k_pack_slow<<<sms * B2_SLOW_MIN_BLOCKS, 256, 8 * kSnapRing, s>>>(B, C); launches++; mark("pack_slow"); }
         if (mask & 2) {
@@ -517,8 +530,22 @@ extern "C" int b2_elapsed_ms(b2_ctx* a, b2_ctx* b, float* ms) {
 }
 
 static int download_normal(b2_ctx* c, b2_batch_result* out) {
-    CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 32, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    if (c->n_runs && c->fused_last) {
+        // the fused kernel keeps slow replies in an overflow area behind the batch-shaped part of resp: traffic that is mostly
+        // CRC'd / compressed / errors is better served (and may only fit) through the slot-scan pipeline
+        const bool heavy = (uint64_t)c->h_totals[3] * 8 > c->h_totals[0];
+        if ((c->h_totals[2] & 2u) && !(c->h_totals[2] & 1u)) {
+            c->slow_heavy = true;
+            int rc = launch_pipeline(c); if (rc != B2_OK) return rc;
+            CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 32, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+        c->slow_heavy = heavy || c->slow_heavy;
+    } else if (c->n_runs && c->slow_heavy && !c->small) {
+        c->slow_heavy = ((uint64_t)c->h_totals[3] + c->h_totals[7]) * 8 > c->h_totals[0];   // ([7]: CRC-carrying echoes the classic pipeline verifies)
+    }
     if (c->n_runs && (c->h_totals[2] & 3u)) {
         set_err(c->h_totals[2] & 1u ? "more messages than max_msgs" : "responses exceed max_resp_bytes"); return B2_E_CAPACITY;
     }

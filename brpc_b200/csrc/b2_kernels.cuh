@@ -78,6 +78,8 @@ struct DevConfig {
     uint32_t stream_handler;      // B2_STREAM_*
     uint32_t spec_k;              // speculative frame offsets kept per tile: kSpecK, or kSpecKDense when tiles hold many small frames
     uint32_t by_ref;              // B2_RESP_BY_REF: OK echo replies are {prefix, reference into the request bytes}
+    uint32_t fused;               // the fused decode+pack kernel serves this batch: replies sit at their request's own offset, slow ones in the overflow area
+    uint32_t ovf_base;            // ... which starts here in the resp region
     uint32_t pull;                // B2_INPUT_PULL: `bytes` is mapped host memory; the walk stashes each frame's first 128 bytes in HBM
     char identity[64];            // "ip:port" of Controller::AppendServerIdentiy
 };
@@ -655,8 +657,17 @@ struct DecodeWarpSmem {
     alignas(16) uint4 row[32][kRowVecs + 1];       // +1: odd 16-byte stride spreads the rows over the banks
 };
 
+// k_fused: a reply that cannot sit at its request's offset (errors, CRC'd / compressed bodies, outputs of decoders) gets a slot in the
+// overflow area behind the batch-shaped part of the resp region; order there is first come, first served (replies are iovec-style)
+__device__ __forceinline__ uint32_t fused_overflow_slot(const BatchPtrs& B, const DevConfig& C, uint32_t slot_len) {
+    const uint32_t so = atomicAdd(B.totals + 9, slot_len);
+    if ((uint64_t)C.ovf_base + so + slot_len > B.max_resp) { atomicOr(B.totals + 2, 2u); return 0; }
+    return C.ovf_base + so;
+}
+struct DecodeOut { uint32_t prefix, rs; bool fast, slow; };        // k_fused: reply prefix length, where the reply starts in resp, disposition
+template <bool kFused = false>
 __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
-                                           const uint8_t* srow, uint8_t* shead, uint32_t row_bytes);
+                                           const uint8_t* srow, uint8_t* shead, uint32_t row_bytes, uint32_t run_idx = kNone, DecodeOut* out = nullptr);
 
 // one warp round: 32 consecutive messages starting at i0 (staging, decode, head write-out)
 __device__ __forceinline__ void decode_round(const BatchPtrs& B, const DevConfig& C, DecodeWarpSmem& S, uint32_t i0, uint32_t n_msgs, uint32_t lane) {
@@ -720,8 +731,9 @@ __global__ void __launch_bounds__(kDecodeWarps * 32, B2_DECODE_MIN_BLOCKS) k_dec
         decode_round(B, C, smem[wid], i0, n_msgs, lane);
 }
 
+template <bool kFused>
 __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
-                                           const uint8_t* srow, uint8_t* shead, uint32_t row_bytes) {
+                                           const uint8_t* srow, uint8_t* shead, uint32_t row_bytes, uint32_t run_idx, DecodeOut* out) {
     const uint32_t fo = fo_raw & 0x7fffffffu;
     const int proto = (int)(fo_raw >> 31) + 1;
     const uint8_t* gframe = B.bytes + fo;
@@ -733,7 +745,7 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
     d.frame_off = fo; d.body_size = load_be32(frame + 4); d.meta_size = load_be32(frame + 8);
     d.correlation_id = 0; d.log_id = 0; d.attachment_size = 0; d.compress_type = 0; d.checksum_type = 0; d.error_code = 0;
     d.has_bits = 0; d.protocol = (uint8_t)proto; d.content_type = 0; d.method_idx = -1; d.status = 0; d.resp_off = 0; d.resp_len = 0;
-    d.run_idx = B.frame_run[i];
+    d.run_idx = kFused ? run_idx : B.frame_run[i];
     MsgAux a; a.msg_off = a.msg_len = a.att_len = a.att_off = a.cks_off = a.cks_len = 0;
     a.svc_off = a.svc_len = a.mth_off = a.mth_len = 0; a.pad = 0; a.err_kind = kErrNone;
     uint32_t resp_len = 0, reserve = 0;               // reserve: slot bytes beyond resp_len a second outcome may need
@@ -799,7 +811,13 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                 }
                 d.resp_len = resp_len;
                 B.msgs[i] = d; B.aux[i] = a;
-                B.slot[i] = d.status == B2_MSG_RESPONSE_UNZ ? ((resp_len + 15u) & ~15u) : 0u;
+                const uint32_t csl = d.status == B2_MSG_RESPONSE_UNZ ? ((resp_len + 15u) & ~15u) : 0u;
+                if (kFused) {
+                    out->fast = false; out->prefix = 0; out->rs = 0; out->slow = resp_len > 0;
+                    B.slot[i] = csl ? fused_overflow_slot(B, C, csl) : 0u;
+                    return;
+                }
+                B.slot[i] = csl;
                 PackJob cj; cj.src_off = 0; cj.bulk_len = 0; cj.head_len = 0; cj.pad = 0; cj.fast = 0; cj.slot_len = 0;
                 B.jobs[i] = cj;
                 return;
@@ -872,8 +890,11 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                         resp_len = prefix + msg.len + a.att_len;
                         a.pad = (fo + a.msg_off - prefix) & 15u;       // payload keeps its (mod 16) alignment
                         // B2_RESP_BY_REF: only the prefix is materialised (same conditions as the bandwidth path below)
-                        if (C.by_ref && mp->response_checksum_type == B2_CHECKSUM_TYPE_NONE && mp->response_compress_type == B2_COMPRESS_TYPE_NONE &&
-                            (a.att_len == 0 || a.att_off == a.msg_off + a.msg_len) && prefix <= 64) { a.pad = 0; ref_prefix = prefix; }
+                        // k_fused: the reply is assembled IN PLACE over the request's own bytes (prefix right in front of the payload), so
+                        // it also has to fit there; CRC-carrying requests are verified by k_pack_slow
+                        if ((C.by_ref || kFused) && mp->response_checksum_type == B2_CHECKSUM_TYPE_NONE && mp->response_compress_type == B2_COMPRESS_TYPE_NONE &&
+                            (a.att_len == 0 || a.att_off == a.msg_off + a.msg_len) && prefix <= 64 &&
+                            (!kFused || (prefix <= a.msg_off && m.checksum_type != B2_CHECKSUM_TYPE_CRC32C))) { a.pad = 0; ref_prefix = prefix; }
                         if (mp->response_compress_type == B2_COMPRESS_TYPE_SNAPPY) {
                             resp_len = 12 + ml + snappy_max_compressed_length(1 + varint_len(msg.len) + msg.len) + a.att_len; a.pad = 0;
                         }
@@ -895,10 +916,9 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
         }
     }
     d.resp_len = resp_len;
-    B.msgs[i] = d;
-    B.aux[i] = a;
+    if (!kFused) { B.msgs[i] = d; B.aux[i] = a; }
     const uint32_t slot_len = resp_len ? ((a.pad + max(ref_prefix ? ref_prefix : resp_len, reserve) + 15u) & ~15u) : 0u;
-    B.slot[i] = slot_len;
+    if (!kFused) B.slot[i] = slot_len;
     uint4 ref = make_uint4(0, 0, 0, 0);
     // ---- bandwidth path: pre-build the reply prefix, shifted to the slot alignment -------------
     PackJob job; job.src_off = 0; job.bulk_len = 0; job.head_len = 0; job.pad = (uint8_t)a.pad; job.fast = 0; job.slot_len = slot_len;
@@ -936,6 +956,14 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
             // a CRC32C-carrying request takes the bandwidth path once k_pack_slow's verify pass has checked it (fast 2 -> 1)
             job.fast = d.checksum_type == B2_CHECKSUM_TYPE_CRC32C ? 2 : 1;
         }
+    }
+    if (kFused) {
+        const bool fast = job.fast == 1 && ref_prefix != 0;
+        if (fast) d.resp_off = fo + a.msg_off - ref_prefix;               // final: the reply sits right in front of its payload
+        B.msgs[i] = d;
+        out->fast = fast; out->prefix = ref_prefix; out->rs = d.resp_off; out->slow = !fast && resp_len > 0;
+        if (out->slow) { B.aux[i] = a; B.slot[i] = slot_len ? fused_overflow_slot(B, C, slot_len) : 0u; }
+        return;
     }
     B.jobs[i] = job;
     if (C.by_ref) B.refs[i] = ref;
@@ -1006,16 +1034,23 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_blocks(BatchPtrs B) {
     if (s_ticket == gridDim.x - 1) { __threadfence(); scan_top_body(B, s_warp, &s_carry); }
 }
 // --- finalize: per-run response span + counters (prologue of the last pack kernel) ----------------
-__device__ __forceinline__ void finalize_runs(const BatchPtrs& B) {
+__device__ __forceinline__ void finalize_runs(const BatchPtrs& B, const DevConfig& C) {
     const uint32_t n_msgs = B.totals[0];
+    if (C.fused && blockIdx.x == 0 && threadIdx.x == 0) {          // span of the resp region in use: the batch-shaped part (+ the overflow area)
+        const uint32_t ovf = B.totals[9];
+        B.totals[1] = ovf ? C.ovf_base + ovf : C.ovf_base;
+    }
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < B.n_runs; r += gridDim.x * blockDim.x) {
         b2_run_status st = B.run_status[r];
         auto off_of = [&](uint32_t i) -> uint32_t {
             if (i >= n_msgs) return B.totals[1];
             return B.slot[i] + B.scan_tmp[i / (kScanBlock * kScanItems)];
         };
+        if (C.fused) { st.resp_off = B.runs[r].offset; st.resp_bytes = st.consumed; }      // replies sit at their requests' offsets
+        else {
         st.resp_off = off_of(st.first_msg);
         st.resp_bytes = off_of(st.first_msg + st.n_msgs) - st.resp_off;
+        }
         B.run_status[r] = st;
         atomicAdd(B.counters + 0, (unsigned long long)st.consumed);
         atomicAdd(B.counters + 1, (unsigned long long)st.n_msgs);
@@ -1513,7 +1548,7 @@ __global__ void __launch_bounds__(256, B2_PACK_MIN_BLOCKS) k_pack(BatchPtrs B, D
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_msgs = B.totals[0];
     if (B.totals[2] & 3u) return;
-    finalize_runs(B);
+    finalize_runs(B, C);
     __shared__ uint32_t s_hot[kCrcHotWords];
     crc_tabs_to_smem(s_hot, B.crc_adv);
     CrcTabs ct; ct.hot = s_hot; ct.tree = B.crc_adv + kCrcHotWords;
@@ -1523,7 +1558,7 @@ __global__ void __launch_bounds__(256, B2_PACK_MIN_BLOCKS) k_pack(BatchPtrs B, D
 
 __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t lane, const CrcTabs& ct) {
     const uint32_t bi = i / (kScanBlock * kScanItems);
-    const uint32_t slot_off = B.slot[i] + B.scan_tmp[bi];
+    const uint32_t slot_off = C.fused ? B.slot[i] : B.slot[i] + B.scan_tmp[bi];
     const b2_msg_desc d = B.msgs[i];
     if (d.resp_len == 0) { if (lane == 0 && d.status != B2_MSG_RESPONSE) B.msgs[i].resp_off = slot_off; return; }
     const MsgAux a = B.aux[i];
@@ -1825,6 +1860,148 @@ __global__ void __launch_bounds__(kPackWarps * 32, 1) k_pack_tma(BatchPtrs B, De
     bulk_wait<0>();
 }
 
+
+// --- k_fused: decode + echo + pack in ONE pass over the bytes ------------------------------------------------------------
+// One warp per live tile (the frames that START in the tile, as k_resolve verified them).  The tile's byte range is pulled
+// into shared memory with one TMA bulk load; the warp finds the frame starts (the offsets k_tile_walk kept, or a walk over
+// the shared-memory copy), decodes one message per lane straight from shared memory, and writes each OK echo's reply prefix
+// IN PLACE, right in front of the payload it answers: the reply to the request at batch offset o lives at the same offset
+// of the resp region (a reply is never longer than its request there: same payload, shorter meta), so the patched image
+// of the whole tile goes back out with ONE TMA bulk store — no head records, no slot scan, no per-message copies, every
+// byte read once and written once.  Replies that cannot be built that way (errors, CRC-carrying or compressed bodies,
+// client-side and stream outputs) get a slot in the overflow area behind the batch-shaped part of resp and are served by
+// k_pack_slow.  A tile larger than the staging buffer (big frames) decodes from 160-byte rows and streams its range through
+// the buffer in chunks, patching the prefixes that fall into each chunk.
+constexpr uint32_t kFusedWarps = 16, kFusedBuf = 10752, kFusedRowStride = 176;
+struct FusedWarpSmem {
+    alignas(128) uint8_t buf[kFusedBuf];
+    alignas(16) uint8_t pfx[32][kHeadBytes];       // reply prefix of each message of the round (decode_one's head record)
+    uint32_t foff[32];
+    alignas(8) unsigned long long mbar;
+};
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// resp[a, b) <- the shared-memory image whose byte 0 is batch offset `img_off`; 16-byte aligned interior by TMA, edges by bytes
+__device__ __forceinline__ void fused_store(uint8_t* resp, const uint8_t* img, uint32_t img_off, uint32_t a, uint32_t b, uint32_t lane) {
+    if (a >= b) return;
+    const uint32_t a0 = (a + 15u) & ~15u, b0 = b & ~15u;
+    if (a0 >= b0) { for (uint32_t k = a + lane; k < b; k += 32) resp[k] = img[k - img_off]; return; }
+    if (lane == 0) bulk_s2g(resp + a0, img + (a0 - img_off), b0 - a0);
+    if (lane < a0 - a) resp[a + lane] = img[a + lane - img_off];
+    if (lane >= 16 && lane - 16 < b - b0) resp[b0 + lane - 16] = img[b0 + lane - 16 - img_off];
+}
+
+__global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(BatchPtrs B, DevConfig C) {
+    extern __shared__ __align__(128) uint8_t fused_raw[];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    FusedWarpSmem& S = reinterpret_cast<FusedWarpSmem*>(fused_raw)[wid];
+    if (B.totals[2] & 1u) return;
+    if (lane == 0) { mbar_init(&S.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncwarp();
+    uint32_t phase = 0;
+    const uint32_t n_warps = gridDim.x * kFusedWarps;
+    for (uint32_t t = blockIdx.x * kFusedWarps + wid; t < B.n_tiles; t += n_warps) {
+        const TileRec rec = B.tiles[t];
+        const uint32_t count = rec.count;
+        if (!rec.live || count == 0) continue;
+        const uint4 ti = __ldg(B.tile_info + t);
+        const uint32_t r = ti.w & 0xffffffu, run_off = ti.x, run_len = ti.y;
+        const bool client = ((ti.w >> 24) & B2_RUN_CLIENT) != 0;
+        const uint32_t first = B.run_status[r].first_msg + B.tile_base[t];
+        const uint32_t hi = run_off + rec.exit;
+        const bool spec_ok = !(rec.kind & kKindRewalked) && count <= C.spec_k;
+        const uint32_t* spec = B.tile_spec + (size_t)t * C.spec_k;
+        uint32_t sub_lo = run_off + rec.entry, wpos = rec.entry; int wpf = rec.pf_in;
+        for (uint32_t done = 0; done < count; done += 32) {
+            const uint32_t cnt = min(32u, count - done);
+            // ---- frame starts of this round of <= 32 messages, and where the round's bytes end
+            uint32_t fo_raw = 0, sub_hi;
+            if (spec_ok) {
+                if (lane < cnt) fo_raw = __ldg(spec + done + lane);
+                sub_hi = done + cnt < count ? (__ldg(spec + done + cnt) & 0x7fffffffu) : hi;
+            } else {
+                if (lane == 0) {                                        // a tile k_resolve re-walked (or a dense one): the chain again, true preferred index
+                    for (uint32_t k = 0; k < cnt; k++) {
+                        const Step sp = cut_input_message(B.bytes + run_off, run_len, wpos, wpf, C.max_body_size, client);
+                        S.foff[k] = (run_off + sp.frame_pos) | ((uint32_t)(sp.index - 1) << 31);
+                        wpos = sp.new_pos; wpf = sp.pf;
+                    }
+                }
+                wpos = __shfl_sync(0xffffffffu, wpos, 0); wpf = __shfl_sync(0xffffffffu, wpf, 0);
+                __syncwarp();
+                if (lane < cnt) fo_raw = S.foff[lane];
+                sub_hi = done + cnt < count ? run_off + wpos : hi;
+            }
+            const uint32_t lo16 = sub_lo & ~15u, hi16 = (sub_hi + 15u) & ~15u, span = hi16 - lo16;
+            const uint32_t i = first + done + lane;
+            const uint32_t fo = fo_raw & 0x7fffffffu;
+            DecodeOut o; o.fast = false; o.slow = false; o.prefix = 0; o.rs = 0;
+            const bool fits = span <= kFusedBuf;
+            if (fits) {
+                // ---- the whole round in one buffer: load, decode in place, patch, store
+                if (lane == 0) { bulk_wait_read<0>(); mbar_arrive_expect_tx(&S.mbar, span); bulk_g2s(S.buf, B.bytes + lo16, span, &S.mbar); }
+                __syncwarp();
+                mbar_wait(&S.mbar, phase & 1u); phase++;
+                if (lane < cnt && i < B.max_msgs) decode_one<true>(B, C, i, fo_raw, S.buf + (fo - lo16), S.pfx[lane], 0xffffffffu, r, &o);
+            } else {
+                // ---- big frames: decode from 160-byte rows staged in the (idle) buffer
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+                const uint32_t sub = lane & 15, half = lane >> 4;
+                for (uint32_t m2 = 0; m2 < cnt; m2 += 2) {
+                    const uint32_t m = m2 + half;
+                    const uint32_t f = __shfl_sync(0xffffffffu, fo, m & 31);
+                    if (m < cnt && sub < kRowVecs) {
+                        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(S.buf + m * kFusedRowStride + sub * 16);
+                        const uint4* src = reinterpret_cast<const uint4*>(B.bytes + (f & ~15u)) + sub;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                if (lane < cnt && i < B.max_msgs) decode_one<true>(B, C, i, fo_raw, S.buf + lane * kFusedRowStride + (fo & 15u), S.pfx[lane], kRowBytes, r, &o);
+                __syncwarp();
+            }
+            // ---- everything that is not an in-place echo goes to k_pack_slow
+            const uint32_t slow_mask = __ballot_sync(0xffffffffu, o.slow);
+            if (slow_mask) {
+                uint32_t sbase = 0;
+                if (lane == 0) sbase = atomicAdd(B.totals + 3, (uint32_t)__popc(slow_mask));
+                sbase = __shfl_sync(0xffffffffu, sbase, 0);
+                if (o.slow) B.slow_idx[sbase + __popc(slow_mask & ((1u << lane) - 1u))] = i;
+            }
+            if (fits) {
+                if (o.fast) { uint8_t* dst = S.buf + (o.rs - lo16); const uint8_t* src = S.pfx[lane]; for (uint32_t k = 0; k < o.prefix; k++) dst[k] = src[k]; }
+                fence_proxy_async();
+                __syncwarp();
+                fused_store(B.resp, S.buf, lo16, sub_lo, sub_hi, lane);
+                if (lane == 0) bulk_commit();
+                __syncwarp();                                           // (the edge bytes were read from the buffer by other lanes)
+            } else {
+                // ---- stream [sub_lo, sub_hi) through the buffer, patching the prefixes that fall into each chunk
+                for (uint32_t c0 = lo16; c0 < hi16; c0 += kFusedBuf) {
+                    const uint32_t c1 = min(c0 + kFusedBuf, hi16);
+                    if (lane == 0) { bulk_wait_read<0>(); mbar_arrive_expect_tx(&S.mbar, c1 - c0); bulk_g2s(S.buf, B.bytes + c0, c1 - c0, &S.mbar); }
+                    __syncwarp();
+                    mbar_wait(&S.mbar, phase & 1u); phase++;
+                    if (o.fast) {
+                        const uint32_t p0 = max(o.rs, c0), p1 = min(o.rs + o.prefix, c1);
+                        for (uint32_t k = p0; k < p1; k++) S.buf[k - c0] = S.pfx[lane][k - o.rs];
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    fused_store(B.resp, S.buf, c0, max(sub_lo, c0), min(sub_hi, c1), lane);
+                    if (lane == 0) bulk_commit();
+                    __syncwarp();
+                }
+            }
+            sub_lo = sub_hi;
+        }
+    }
+    if (lane == 0) bulk_wait<0>();
+}
+
 // --- k_pack_requests: the client mirror -------------------------------------------------------------
 // PackRpcRequest + SerializeRpcRequest (baidu_rpc_protocol.cpp:1015-1133) and PackStreamMessage
 // (streaming_rpc_protocol.cpp:42-58): one warp per frame.  The meta length does not depend on the body, so the
@@ -1931,7 +2108,7 @@ __global__ void __launch_bounds__(256) k_pack_requests(const uint8_t* bytes, con
 __global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs B, DevConfig C) {
     const uint32_t lane = threadIdx.x & 31;
     if (B.totals[2] & 3u) return;
-    finalize_runs(B);                                  // (was a separate launch)
+    finalize_runs(B, C);                               // (was a separate launch)
     const uint32_t n_verify = B.totals[7];
     if (B.totals[3] == 0 && n_verify == 0) return;
     __shared__ uint32_t s_hot[kCrcHotWords];

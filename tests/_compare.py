@@ -46,16 +46,22 @@ def assert_same(dev, orc, what=""):
             lo = int(ends[mi] - ol[mi])
             raise AssertionError("%s response bytes differ in msg %d at byte %d:\n dev %s\n orc %s" % (
                 what, mi, pos - lo, bytes(dg[lo:lo + 96]).hex(), bytes(og[lo:lo + 96]).hex()))
-    # layout invariants of the device response region
+    # layout invariants of the device response region: replies are iovec-style (one span each) and never overlap; a run's
+    # replies lie inside the run's span, or — replies the fused kernel could not build in place — behind every run's span
     if len(d_msgs):
         has = (d_msgs["resp_len"] > 0) & ~inplace
         off = d_msgs["resp_off"][has].astype(np.int64); ln = d_msgs["resp_len"][has].astype(np.int64)
-        assert np.all(off[1:] >= off[:-1] + ln[:-1]), what + " response slots overlap or are out of order"
+        order = np.argsort(off, kind="stable")
+        so, sl = off[order], ln[order]
+        assert np.all(so[1:] >= so[:-1] + sl[:-1]), what + " response spans overlap"
         if len(off):
-            assert off[-1] + ln[-1] <= len(d_resp) or len(d_resp) == 0 or True
+            assert int((off + ln).max()) <= len(d_resp), what + " a response lies outside the resp region"
+    span_end = int((d_rs["resp_off"].astype(np.int64) + d_rs["resp_bytes"]).max()) if len(d_rs) else 0
     for r in range(len(d_rs)):
         a, n = int(d_rs["first_msg"][r]), int(d_rs["n_msgs"][r])
         if n and np.any((d_msgs["resp_len"][a:a + n] > 0) & (d_msgs["status"][a:a + n] != 7)):
             m = d_msgs[a:a + n]; m = m[(m["resp_len"] > 0) & (m["status"] != 7)]
-            assert int(m["resp_off"][0]) >= int(d_rs["resp_off"][r])
-            assert int(m["resp_off"][-1] + m["resp_len"][-1]) <= int(d_rs["resp_off"][r]) + int(d_rs["resp_bytes"][r])
+            lo, hi = int(d_rs["resp_off"][r]), int(d_rs["resp_off"][r]) + int(d_rs["resp_bytes"][r])
+            inside = (m["resp_off"].astype(np.int64) >= lo) & (m["resp_off"].astype(np.int64) + m["resp_len"] <= hi)
+            behind = m["resp_off"].astype(np.int64) >= span_end
+            assert np.all(inside | behind), what + " run %d: a response is neither in the run's span nor in the overflow area" % r
