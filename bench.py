@@ -108,9 +108,10 @@ def pin_to_gpu_numa(gpu_index):
 
 def ncu_traffic(kernel, args):
     """dram bytes read + written per launch of `kernel` from the committed `ncu --set full` capture of this same workload
-    (profiles/r1_ncu_summary.json), or None when the capture does not cover the configuration being run."""
+    (profiles/r2_ncu_summary.json; it names the kernels it saw, so a renamed / restructured kernel reads as None rather
+    than as a stale number), or None when the capture does not cover the configuration being run."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_summary.json")) as f:
             cap = json.load(f)
         w = cap["workload"]
         if (w["payload_bytes"], w["run_mib"], w["connections"]) != (args.payload, args.run_mib, N_SOCKETS) or args.checksum or args.payload_kind:
@@ -213,6 +214,12 @@ def grpc_h2_main(args):
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
+    use_dist = world > 1
+    if use_dist:                                                # one process per GPU, connections sharded by rank: no exchange step
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    pin_to_gpu_numa(dev)
     hbm_peak, peak_src = read_peaks()
     n_conns, K, msg_len = 256, args.frames_per_stream, args.payload if args.payload != 1024 else 4096
     steps, warmup = max(1, min(args.steps, 200)), max(3, args.warmup)
@@ -272,15 +279,22 @@ def grpc_h2_main(args):
     for t in range(warmup):
         one_step(t, check=True)
     sampler = ClockSampler(dev); sampler.start()
+    if use_dist:
+        dist.barrier()
     torch.cuda.synchronize(); t0 = time.perf_counter(); total = 0
     for t in range(steps):
         total += one_step(warmup + t)
     torch.cuda.synchronize()
+    if use_dist:
+        dist.barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
+    if use_dist:                                                # max time over ranks, summed calls; the bvar-like counters go through NCCL too
+        tw = torch.tensor([wall], dtype=torch.float64, device="cuda"); dist.all_reduce(tw, op=dist.ReduceOp.MAX); wall = tw.item()
+        tt = torch.tensor([float(total)], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.SUM); total = tt.item()
     ms = wall * 1e3 / steps
     if rank == 0:
-        line = {"metric": "h2/gRPC echo QPS, %d B messages" % msg_len, "value": total / wall, "unit": "msgs/s", "n_gpus": 1, "steps": steps, "warmup": warmup,
+        line = {"metric": "h2/gRPC echo QPS, %d B messages" % msg_len, "value": total / wall, "unit": "msgs/s", "n_gpus": world if use_dist else 1, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": "grpc_c++-style unary calls over h2: %d connections/GPU x %d calls per batch, %d B messages, HPACK dynamic-table hits" % (n_conns, K, msg_len),
                            "note": "timed through the synchronous C ABI with host buffers (copies and the Python glue that builds the response list included)"},
@@ -302,6 +316,8 @@ def grpc_h2_main(args):
             line["cpu_baseline"] = {"value": n / (time.perf_counter() - t1), "unit": "msgs/s", "cores": 1, "kind": "port",
                                     "sample": "8 of the %d connections, parse + pack through the oracle (Python glue included), ~5 s" % n_conns}
         print(json.dumps(line))
+    if use_dist:
+        dist.destroy_process_group()
     return 0
 
 
@@ -451,6 +467,45 @@ def stream_snappy_main(args):
     return 0
 
 
+def load_press():
+    """tools/libb2press.so (the rpc_press-like traffic source, host code) without importing the product package."""
+    class Spec(C.Structure):
+        _fields_ = [("service", C.c_char_p), ("method", C.c_char_p), ("payload_bytes", C.c_uint32), ("attachment_bytes", C.c_uint32),
+                    ("payload_kind", C.c_int32), ("checksum_type", C.c_int32), ("seed", C.c_uint64)]
+    so = os.path.join(ROOT, "brpc_b200", "tools", "libb2press.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(ROOT, "brpc_b200", "tools", "rpc_press.cpp")])
+    lib = C.CDLL(so)
+    lib.b2press_fill_run.restype = C.c_uint64
+    lib.b2press_fill_run.argtypes = [C.POINTER(Spec), C.POINTER(C.c_uint64), C.c_void_p, C.c_size_t]
+    return lib, Spec
+
+
+RUN_DT = np.dtype([("socket_id", "<u8"), ("offset", "<u4"), ("length", "<u4"), ("preferred_proto", "<i4"), ("flags", "<u4")])
+
+
+def socket_ids_of(rank, world):
+    """The connections rank `rank` serves: gpu = SlotOfVRefId(socket_id) % n_gpus (brpc_b200/shard.py:owner_of)."""
+    ids = np.arange(N_SOCKETS * max(1, world), dtype=np.uint64)
+    own = (ids & np.uint64(0xffffffff)) % np.uint64(max(1, world))
+    return ids[own == rank]
+
+
+def fill_batch_plain(data, run_mib, rank, world, payload=PAYLOAD, checksum=0, kind=0):
+    lib, Spec = load_press()
+    run_bytes = (run_mib << 20) - 16 * 7
+    stride = (run_bytes + 15) // 16 * 16
+    sp = Spec(b"example.EchoService", b"Echo", payload, 0, kind, checksum, 20260921)
+    ids = socket_ids_of(rank, world)
+    runs = np.zeros(N_SOCKETS, dtype=RUN_DT)
+    total = 0
+    for s_ in range(N_SOCKETS):
+        idx = C.c_uint64((int(ids[s_]) << 32) + 1000003 * rank)
+        total += lib.b2press_fill_run(C.byref(sp), C.byref(idx), data.ctypes.data + s_ * stride, run_bytes)
+        runs[s_] = (int(ids[s_]), s_ * stride, run_bytes, -1, 0)
+    return runs, int(total), N_SOCKETS * stride
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -465,8 +520,9 @@ def main():
     ap.add_argument("--payload-kind", type=int, default=0, help="0 = 'r' fill, 1 = random over 62 symbols")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--pipeline", type=int, default=2, help="resident batches in flight per GPU (one ctx + stream each)")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="the timed region of `value` lasts at least this long: a step repeats the pass")
     ap.add_argument("--workload", default="echo", choices=["echo", "stream_snappy", "grpc_h2"],
-                    help="echo = the headline metric; stream_snappy = BASELINE configs[4] (256 KiB snappy streaming frames), a side measurement")
+                    help="echo = the headline metric; stream_snappy = BASELINE configs[4] (256 KiB snappy streaming frames), grpc_h2 = configs[3]")
     ap.add_argument("--frames-per-stream", type=int, default=8)
     args = ap.parse_args()
     if args.workload == "stream_snappy":
@@ -481,15 +537,20 @@ def main():
     workload = ("multi_threaded_echo_c++ baidu_std %d B payload: %d connections/GPU x %d MiB pending, "
                 "runs cut mid-frame; batch %d MiB > L2 (no flush needed)" % (args.payload, N_SOCKETS, args.run_mib, N_SOCKETS * args.run_mib))
     config = {"workload": workload, "payload_bytes": args.payload, "request_checksum": args.checksum, "connections_per_gpu": N_SOCKETS,
-              "run_mib": args.run_mib, "l2": "inputs larger than L2", "pipeline_depth": args.pipeline, "sharding": "socket_id %% %d" % max(1, world),
+              "run_mib": args.run_mib, "l2": "inputs larger than L2", "pipeline_depth": args.pipeline,
+              "sharding": "gpu = (socket_id & 0xffffffff) %% %d (shard.owner_of)" % max(1, world),
               "host": "each rank pinned to its GPU's NUMA node"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        _, data, runs, n_full, nbytes = build_batch(min(args.run_mib, 2), 0, pinned=False)
+        nb = N_SOCKETS * (((args.run_mib << 20) - 112 + 15) // 16 * 16)
+        data = np.zeros(nb, np.uint8)
+        runs, n_full, nbytes = fill_batch_plain(data, args.run_mib, 0, 1, payload=args.payload, checksum=args.checksum, kind=args.payload_kind)
         t0 = time.perf_counter()
         qps, msgs, passes = cpu_arm(data, runs, ncores, min_seconds=min(20.0, 1.0 * steps))
+        config["reference_arm"] = ("oracle port of the reference path on %d host threads; every connection is split at frame boundaries by an UNTIMED pass so that all "
+                                   "threads have work (brpc hands each cut message to its own bthread); brpc itself cannot be built here" % ncores)
         line = {"impl": "reference", "metric": "echo QPS, 1 KB baidu_std", "value": qps, "unit": "msgs/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * msgs / qps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -497,7 +558,7 @@ def main():
                 "cpu_baseline": {"value": qps, "unit": "msgs/s", "cores": ncores, "kind": "port",
                                  "sample": "%d connections x %d MiB (%d msgs/pass) split at frame boundaries over the threads, "
                                            "best of %d passes, %d threads; oracle port of the reference path (brpc itself cannot be built here)"
-                                           % (N_SOCKETS, min(args.run_mib, 2), msgs, passes, ncores)},
+                                           % (N_SOCKETS, args.run_mib, msgs, passes, ncores)},
                 "e2e": {"value": qps, "unit": "msgs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "wall_s": time.perf_counter() - t0}
         print(json.dumps(line))
@@ -505,6 +566,7 @@ def main():
 
     import torch
     import brpc_b200
+    from brpc_b200.abi import PinnedBuffer
     use_dist = world > 1
     if use_dist:
         os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
@@ -515,9 +577,14 @@ def main():
     torch.cuda.set_device(dev)
     numa_cpus = pin_to_gpu_numa(dev)        # pinned buffers are allocated (first touched) on the GPU's own NUMA node
 
-    buf, data, runs, n_full, nbytes = build_batch(args.run_mib, rank, payload=args.payload, checksum=args.checksum, kind=args.payload_kind)
-    ctx = brpc_b200.Context(device=dev, max_batch_bytes=nbytes + (1 << 20), max_msgs=n_full + 4096,
-                            max_runs=N_SOCKETS, tile_bytes=args.tile, max_resp_bytes=nbytes + 96 * n_full + (4 << 20))
+    nb = N_SOCKETS * (((args.run_mib << 20) - 112 + 15) // 16 * 16)
+    buf = PinnedBuffer(nb); data = buf.array
+    runs, n_full, nbytes = fill_batch_plain(data, args.run_mib, rank, world, payload=args.payload, checksum=args.checksum, kind=args.payload_kind)
+    from brpc_b200 import shard
+    assert np.all(shard.owner_of(runs["socket_id"], world) == rank)
+    mk = lambda: brpc_b200.Context(device=dev, max_batch_bytes=nbytes + (1 << 20), max_msgs=n_full + 4096,
+                                   max_runs=N_SOCKETS, tile_bytes=args.tile, max_resp_bytes=2 * nbytes + 96 * n_full + (8 << 20))
+    ctx = mk()
 
     def barrier():
         if use_dist:
@@ -527,37 +594,46 @@ def main():
     # ---- correctness gate before timing: every message echoed, lengths obey the frame law -------
     rs, msgs, resp, info = ctx.process_batch_ptr(buf.ptr, nbytes, runs)
     assert len(msgs) == n_full and np.all(msgs["status"] == 0), "bench batch did not echo cleanly"
-    launches_per_step = info["n_launches"]
     req_bytes = int(rs["consumed"].sum())
     resp_frame_bytes = int(msgs["resp_len"].sum())
-    d2h_bytes = int(len(msgs) * 64 + len(rs) * 32 + int(rs["resp_bytes"].sum()))
-    h2d_bytes = int(nbytes + runs.nbytes + 4 * (len(runs) + 1))
+    n_msgs = len(msgs)
 
     # ---- value: resident batches, kernel pipeline only -----------------------------------------
-    # `--pipeline D` contexts (own buffers + stream) hold the same batch; steps alternate over
-    # them so the latency-bound scan/decode stages of one step overlap the TMA pack of another.
+    # `--pipeline D` contexts (own buffers + stream) hold the same batch; passes alternate over them so the latency-bound
+    # front stages of one pass overlap the bandwidth kernel of another.  A STEP is `passes_per_step` passes over the batch:
+    # enough for the timed region to last --min-seconds whatever --steps is, so the clock samples below cover it.
     depth = max(1, args.pipeline)
-    ctxs = [ctx] + [brpc_b200.Context(device=dev, max_batch_bytes=nbytes + (1 << 20), max_msgs=n_full + 4096,
-                                      max_runs=N_SOCKETS, tile_bytes=args.tile, max_resp_bytes=nbytes + 96 * n_full + (4 << 20))
-                    for _ in range(depth - 1)]
+    ctxs = [ctx] + [mk() for _ in range(depth - 1)]
     for cx in ctxs:
         cx.upload_ptr(buf.ptr, nbytes, runs)
     for s_ in range(warmup * depth):
         ctxs[s_ % depth].launch()
     for cx in ctxs:
         cx.wait()
+    t0 = time.perf_counter()
+    for s_ in range(8 * depth):
+        ctxs[s_ % depth].launch()
+    for cx in ctxs:
+        cx.wait()
+    est = (time.perf_counter() - t0) / (8 * depth)
+    ppass = max(1, int(np.ceil(args.min_seconds / max(1e-9, steps * est))))
+    if use_dist:
+        t_pp = torch.tensor([ppass], dtype=torch.int64, device="cuda"); dist.all_reduce(t_pp, op=dist.ReduceOp.MAX); ppass = int(t_pp.item())
+    launches_per_pass = ctx.execute()[1]
+    fused = ctx.batch_info()["fused"]
+    for cx in ctxs:
+        cx.wait()
     sampler = ClockSampler(dev); sampler.start()
     barrier()
     t0 = time.perf_counter()
-    for s_ in range(steps):
+    for s_ in range(steps * ppass):
         ctxs[s_ % depth].launch()
     for cx in ctxs:
         cx.wait()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop()
-    dev_ms = max(ctxs[0].elapsed_ms_to(cx) for cx in ctxs[:min(depth, steps)])
-    n_launch = steps * launches_per_step
+    dev_ms = max(ctxs[0].elapsed_ms_to(cx) for cx in ctxs[:min(depth, steps * ppass)])
+    n_launch = steps * ppass * launches_per_pass
     for cx in ctxs[1:]:       # every in-flight copy produced the same, correct result
         r2, m2, p2, _ = cx.download()
         assert len(m2) == n_full and np.array_equal(m2["resp_len"], msgs["resp_len"]) and np.array_equal(m2["status"], msgs["status"])
@@ -570,65 +646,99 @@ def main():
     stages = {k: statistics.mean(v) for k, v in stage_acc.items()}
 
     # ---- e2e: host buffers, copies inside the timed region --------------------------------------
-    # three contexts in flight: the H2D copy of one batch, the kernels of the next and the D2H copy
-    # of a third overlap (submit/collect halves of b2_process_batch); every step moves all its
-    # request bytes host->device and all descriptors + responses device->host.
+    # Three contexts in flight (submit/collect halves of b2_process_batch): the transfers of one batch overlap the kernels of
+    # the next.  Three ways of crossing PCIe, all bit-exact (tests/test_gpu_modes.py):
+    #   copy      H2D copy of every request byte, D2H copy of descriptors + every reply byte (round 1's e2e)
+    #   by_ref    H2D copy; replies come back as {<= 64-byte prefix, reference into the request bytes} (SendRpcResponse's own
+    #             append-by-reference): D2H = descriptors + refs + prefixes
+    #   pull      no H2D copy: the kernels read the pinned request blocks in place, one 128-byte row per message + the scan
+    #             windows cross the link; replies by reference.  THE HEADLINE: what a brpc GpuTransport would run.
     e2e_depth = 3
     while len(ctxs) < e2e_depth:
-        ctxs.append(brpc_b200.Context(device=dev, max_batch_bytes=nbytes + (1 << 20), max_msgs=n_full + 4096,
-                                      max_runs=N_SOCKETS, tile_bytes=args.tile, max_resp_bytes=nbytes + 96 * n_full + (4 << 20)))
-    e2e_steps = max(6, min(steps, 30))
-    for cx in ctxs[:e2e_depth]:
-        cx.submit_ptr(buf.ptr, nbytes, runs)
-    for cx in ctxs[:e2e_depth]:
-        cx.collect()
-    barrier()
-    t0 = time.perf_counter()
-    for s_ in range(min(e2e_depth, e2e_steps)):
-        ctxs[s_].submit_ptr(buf.ptr, nbytes, runs)
-    e2e_ok = True
-    for s_ in range(e2e_steps):
-        cx = ctxs[s_ % e2e_depth]
-        r3, m3, p3, _ = cx.collect()
-        e2e_ok = e2e_ok and len(m3) == n_full and int(m3["resp_len"][-1]) == int(msgs["resp_len"][-1])
-        if s_ + e2e_depth < e2e_steps:
-            cx.submit_ptr(buf.ptr, nbytes, runs)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    assert e2e_ok, "e2e batches returned wrong results"
+        ctxs.append(mk())
 
-    # ---- latency: one small batch at a time through the same ABI call (p99 of the metric) --------
-    # 64 connections x 1 complete 1 KB request each = what 64 synchronous client threads
-    # (multi_threaded_echo_c++ -thread_num=64) have in flight; host buffers, blocking call.
+    def e2e_mode(im, rm, min_s):
+        for cx in ctxs[:e2e_depth]:
+            cx.set_modes(im, rm)
+            cx.process_batch_ptr(buf.ptr, nbytes, runs); cx.process_batch_ptr(buf.ptr, nbytes, runs)
+        info_ = ctxs[0].batch_info()
+        t1 = time.perf_counter()
+        r3, m3, p3, i3 = ctxs[0].process_batch_ptr(buf.ptr, nbytes, runs)
+        one = time.perf_counter() - t1
+        n_steps = max(9, int(np.ceil(min_s / max(one / 2, 1e-6))))
+        if use_dist:
+            t_n = torch.tensor([n_steps], dtype=torch.int64, device="cuda"); dist.all_reduce(t_n, op=dist.ReduceOp.MAX); n_steps = int(t_n.item())
+        barrier()
+        t1 = time.perf_counter()
+        for s_ in range(min(e2e_depth, n_steps)):
+            ctxs[s_].submit_ptr(buf.ptr, nbytes, runs)
+        ok = True
+        for s_ in range(n_steps):
+            cx = ctxs[s_ % e2e_depth]
+            r3, m3, p3, i3 = cx.collect()
+            ok = ok and len(m3) == n_full and int(m3["resp_len"][-1]) == int(msgs["resp_len"][-1])
+            if s_ + e2e_depth < n_steps:
+                cx.submit_ptr(buf.ptr, nbytes, runs)
+        barrier()
+        ms = (time.perf_counter() - t1) * 1e3 / n_steps
+        assert ok, "e2e batches returned wrong results"
+        if rm:
+            refs = i3["refs"]
+            assert refs is not None and np.all(refs["src_len"] + refs["prefix_len"] == m3["resp_len"])
+        d2h = int(len(m3) * 64 + len(r3) * 32 + int(r3["resp_bytes"].sum()) + (16 * len(m3) if rm else 0))
+        meta = int(runs.nbytes + 4 * (len(runs) + 1) + 16 * info_["n_tiles"])
+        # pull: each message's stashed row is one 128-byte PCIe read; every tile's speculative entry scan reads two 512-byte windows
+        h2d = meta + (int(128 * len(m3) + 1024 * info_["n_tiles"]) if im else int(nbytes))
+        return {"ms_per_step": ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_steps, "tile_bytes": info_["tile_bytes"]}
+
+    e2e_modes = {"copy": e2e_mode(0, 0, 0.4), "copy_by_ref": e2e_mode(0, 1, 0.4), "pull_by_ref": e2e_mode(1, 1, 0.6)}
+    clocks = sampler.stop()
+    for cx in ctxs:
+        cx.set_modes(0, 0)
+
+    # ---- latency: one small batch at a time (p99 of the metric) -----------------------------------
+    # 64 connections x 1 complete 1 KB request each = what 64 synchronous client threads (multi_threaded_echo_c++
+    # -thread_num=64) have in flight; pinned host buffers; timed inside the library (b2_latency_probe) around
+    #   ring:     b2_ring_submit + b2_ring_wait — the persistent kernel, no launch / memcpy / sync per batch
+    #   blocking: b2_process_batch — one k_small launch + two copies + a stream sync
     latency = None
     if not args.no_latency:
-        from brpc_b200 import press as _press
-        from brpc_b200.abi import PinnedBuffer as _Pinned
-        lat_ctx = brpc_b200.Context(device=dev, max_batch_bytes=1 << 20, max_msgs=4096, max_runs=N_SOCKETS, tile_bytes=args.tile)
-        _sp = _press.spec(payload_bytes=PAYLOAD)
-        _f = _press.frame(_sp, 12345)
-        _stride = (len(_f) + 15) // 16 * 16
-        lbuf = _Pinned(N_SOCKETS * _stride)
-        lruns = np.zeros(N_SOCKETS, dtype=brpc_b200.RUN_DT)
+        lib, Spec = load_press()
+        lib.b2press_frame.restype = C.c_size_t
+        lib.b2press_frame.argtypes = [C.POINTER(Spec), C.c_uint64, C.c_void_p, C.c_size_t]
+        sp = Spec(b"example.EchoService", b"Echo", PAYLOAD, 0, 0, 0, 20260921)
+        tmp = C.create_string_buffer(4096)
+        flen = lib.b2press_frame(C.byref(sp), 12345, tmp, 4096)
+        stride = (flen + 15) // 16 * 16
+        lbuf = PinnedBuffer(N_SOCKETS * stride)
+        lruns = np.zeros(N_SOCKETS, dtype=RUN_DT)
         for s_ in range(N_SOCKETS):
-            fr = _press.frame(_sp, (s_ << 32) + 7)
-            lbuf.array[s_ * _stride:s_ * _stride + len(fr)] = np.frombuffer(fr, np.uint8)
-            lruns[s_] = (s_, s_ * _stride, len(fr), 1, 0)
-        for _ in range(50):
-            lat_ctx.process_batch_ptr(lbuf.ptr, N_SOCKETS * _stride, lruns)
-        lat = []
-        for _ in range(2000):
-            t1 = time.perf_counter()
-            lrs, lm, lresp, _i = lat_ctx.process_batch_ptr(lbuf.ptr, N_SOCKETS * _stride, lruns)
-            lat.append((time.perf_counter() - t1) * 1e6)
+            n_ = lib.b2press_frame(C.byref(sp), (s_ << 32) + 7, lbuf.ptr + s_ * stride, stride)
+            lruns[s_] = (s_, s_ * stride, n_, 1, 0)
+        lat_ctx = brpc_b200.Context(device=dev, max_batch_bytes=1 << 20, max_msgs=4096, max_runs=N_SOCKETS, tile_bytes=args.tile)
+        lrs, lm, lresp, _i = lat_ctx.process_batch_ptr(lbuf.ptr, N_SOCKETS * stride, lruns)
         assert len(lm) == N_SOCKETS and np.all(lm["status"] == 0)
-        lat.sort()
-        latency = {"batch": "%d connections x 1 request (1 KB), blocking b2_process_batch, host buffers" % N_SOCKETS,
-                   "p50_us": lat[len(lat) // 2], "p99_us": lat[int(len(lat) * 0.99)], "mean_us": sum(lat) / len(lat),
-                   "iters": len(lat), "kernel_launches_per_batch": int(_i["n_launches"])}
+        lat_ctx.latency_probe(lbuf.ptr, N_SOCKETS * stride, lruns, 200, False)
+        blk = np.sort(lat_ctx.latency_probe(lbuf.ptr, N_SOCKETS * stride, lruns, 3000, False))
+        lat_ctx.ring_start()
+        lat_ctx.latency_probe(lbuf.ptr, N_SOCKETS * stride, lruns, 200, True)
+        r0 = lat_ctx.ring_launches()
+        rng_ = np.sort(lat_ctx.latency_probe(lbuf.ptr, N_SOCKETS * stride, lruns, 5000, True))
+        ring_launches = lat_ctx.ring_launches() - r0
+        t_ = lat_ctx.ring_submit(None, lruns, ptr=lbuf.ptr, nbytes=N_SOCKETS * stride)
+        qrs, qm, qresp, _q = lat_ctx.ring_wait(t_)
+        assert len(qm) == N_SOCKETS and np.all(qm["status"] == 0) and np.array_equal(qm["resp_len"], lm["resp_len"])
+        lat_ctx.ring_stop()
+        pc = lambda v, q: float(v[min(len(v) - 1, int(len(v) * q))])
+        latency = {"batch": "%d connections x 1 request (1 KB), pinned host buffers, timed inside the library" % N_SOCKETS,
+                   "path": "persistent kernel + submit ring (b2_ring_submit / b2_ring_wait)",
+                   "p50_us": pc(rng_, .5), "p99_us": pc(rng_, .99), "mean_us": float(rng_.mean()), "iters": len(rng_),
+                   "kernel_launches_per_batch": ring_launches / float(len(rng_)),
+                   "blocking_call": {"p50_us": pc(blk, .5), "p99_us": pc(blk, .99), "kernel_launches_per_batch": int(_i["n_launches"]), "iters": len(blk)}}
 
     # ---- reduce over ranks: max time, summed messages; NCCL all-reduce of the bvar-like counters --
-    t_dev = torch.tensor([dev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
+    tv = [dev_ms, wall_ms] + [e2e_modes[k]["ms_per_step"] for k in ("copy", "copy_by_ref", "pull_by_ref")]
+    t_dev = torch.tensor(tv, dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(n_full)], dtype=torch.float64, device="cuda")
     if use_dist:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
@@ -638,36 +748,44 @@ def main():
         counters = counters.tolist()
     else:
         counters = ctx.counters()
-    dev_ms_max, e2e_ms_max, wall_ms_max = t_dev.tolist()
+    dev_ms_max, wall_ms_max, e_copy, e_ref, e_pull = t_dev.tolist()
     total_msgs = tot.item()
     ms_per_step = dev_ms_max / steps
-    value = total_msgs / (ms_per_step * 1e-3)
-    e2e_value = total_msgs / (e2e_ms_max * 1e-3)
+    value = total_msgs * ppass / (ms_per_step * 1e-3)
 
     if rank == 0:
+        config["passes_per_step"] = ppass
+        config["value_path"] = "k_fused (decode + echo + pack in one pass)" if fused else "slot-scan pipeline (k_decode, k_scan_blocks, k_pack_tma)"
         # roofline of the dominant kernel, from THIS rank's stage times
         dom = max(stages, key=stages.get)
-        pack_alg = float(int(msgs["resp_len"].sum()) + len(msgs) * (args.payload + DESC_BYTES))   # resp written + payload & desc read
-        alg = {"pack": pack_alg}
-        dom_alg = alg.get(dom, float(req_bytes + resp_frame_bytes + DESC_BYTES * len(msgs)))
+        pipe_alg = float(req_bytes + resp_frame_bytes + DESC_BYTES * n_msgs)                  # req + resp + 64 B desc
+        pack_alg = float(resp_frame_bytes + n_msgs * (args.payload + DESC_BYTES))             # k_pack_tma: resp written + payload & desc read
+        dom_alg = {"pack": pack_alg, "fused": pipe_alg}.get(dom, pipe_alg)
         achieved = dom_alg / (stages[dom] * 1e-3) / 1e9
-        pipe_alg = float(req_bytes + resp_frame_bytes + DESC_BYTES * len(msgs))               # req + resp + 64 B desc
         pipe_ms = sum(stages.values())                                                            # one pass alone (serial stages)
-        step_ms_rank0 = dev_ms / steps                                                            # with `depth` passes in flight
+        step_ms_rank0 = dev_ms / (steps * ppass)                                                  # with `depth` passes in flight
+        mk_e2e = lambda ms_, m_: {"value": total_msgs / (ms_ * 1e-3), "unit": "msgs/s", "h2d_bytes_per_step": m_["h2d_bytes_per_step"],
+                                  "d2h_bytes_per_step": m_["d2h_bytes_per_step"], "ms_per_step": ms_, "steps": m_["steps"]}
+        e2e = mk_e2e(e_pull, e2e_modes["pull_by_ref"])
+        e2e["mode"] = "pull_by_ref"
+        e2e["note"] = ("b2_batch_submit/collect (the two halves of b2_process_batch) on pinned host blocks, 3 batches in flight, B2_INPUT_PULL + "
+                       "B2_RESP_BY_REF: the kernels read the pinned request blocks in place (h2d = one 128-byte row per message + the scan windows "
+                       "+ run/tile records, counted from the access pattern), replies come back as prefix + reference; e2e_modes holds the copy variants")
         line = {"metric": "echo QPS, 1 KB baidu_std", "value": value, "unit": "msgs/s", "n_gpus": world if use_dist else 1,
                 "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-                "e2e": {"value": e2e_value, "unit": "msgs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                        "ms_per_step": e2e_ms_max, "note": "b2_batch_submit/collect (the two halves of b2_process_batch), pinned host buffers, 3 batches in flight"},
+                "e2e": e2e,
+                "e2e_modes": {"copy": mk_e2e(e_copy, e2e_modes["copy"]), "copy_by_ref": mk_e2e(e_ref, e2e_modes["copy_by_ref"]), "pull_by_ref": mk_e2e(e_pull, e2e_modes["pull_by_ref"])},
                 "gpu_launches": int(n_launch),
                 "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved / hbm_peak, "traffic": ncu_traffic("k_" + dom, args), "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": dom_alg, "kernel_ms": stages[dom]},
                 "roofline_pipeline": {"achieved": pipe_alg / (step_ms_rank0 * 1e-3) / 1e9,
                                       "frac": pipe_alg / (step_ms_rank0 * 1e-3) / 1e9 / hbm_peak,
-                                      "algorithmic_bytes_per_msg": pipe_alg / len(msgs), "single_pass_ms": pipe_ms,
-                                      "stage_ms": stages, "note": "whole hot path: (req + resp + 64 B desc) x msgs / measured step time"},
-                "latency": latency, "clocks": clocks, "wall_ms_per_step": wall_ms_max / steps, "msgs_per_step": total_msgs,
+                                      "algorithmic_bytes_per_msg": pipe_alg / n_msgs, "single_pass_ms": pipe_ms, "launches_per_pass": int(launches_per_pass),
+                                      "stage_ms": stages, "note": "whole hot path: (req + resp + 64 B desc) x msgs / measured time per pass"},
+                "latency": latency, "clocks": clocks, "wall_ms_per_step": wall_ms_max / steps,
+                "value_by_wall_clock": total_msgs * ppass * steps / (wall_ms_max * 1e-3), "msgs_per_step": total_msgs * ppass,
                 "counters_allreduced": counters}
         if not args.no_cpu_baseline:
             # bounded sample: the first 8 connections of the same batch, 1 thread, ~10 s

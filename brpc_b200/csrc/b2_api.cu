@@ -772,6 +772,13 @@ extern "C" int b2_stage_times(b2_ctx* c, const char** names, float* ms, int cap)
     return c->n_stages;
 }
 
+// what the last upload / launch decided: [0] tile bytes [1] tiles [2] frame offsets kept per tile [3] 1 = the fused kernel served it
+extern "C" int b2_batch_info(b2_ctx* c, uint32_t out[4]) {
+    if (!c || !out) return B2_E_INVAL;
+    out[0] = c->cfg.tile_bytes; out[1] = c->n_tiles; out[2] = c->cfg.spec_k; out[3] = c->fused_last ? 1u : 0u;
+    return B2_OK;
+}
+
 extern "C" int b2_counters_read(b2_ctx* c, int64_t out[B2_N_COUNTERS]) {
     if (!c || !out) return B2_E_INVAL;
     CU(cudaSetDevice(c->opt.device));
@@ -784,13 +791,13 @@ extern "C" void* b2_counters_device_ptr(b2_ctx* c) { return c ? (void*)c->d_coun
 extern "C" void* b2_debug_resp_device_ptr(b2_ctx* c) { return c ? (void*)c->d_resp : nullptr; }
 
 __global__ void k_crc32c_batch(const uint8_t* bytes, const uint32_t* offs, const uint32_t* lens, uint32_t n, uint32_t* out,
-                               const uint32_t* adv) {
+                               const uint32_t* adv, uint32_t init_crc = 0) {
     __shared__ uint32_t s_hot[kCrcHotWords];
     crc_tabs_to_smem(s_hot, adv);
     CrcTabs ct; ct.hot = s_hot; ct.tree = adv + kCrcHotWords;
     const uint32_t lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += n_warps) {
-        const uint32_t c = warp_crc32c_update(0xffffffffu, bytes + offs[i], lens[i], lane, ct) ^ 0xffffffffu;
+        const uint32_t c = warp_crc32c_update(init_crc ^ 0xffffffffu, bytes + offs[i], lens[i], lane, ct) ^ 0xffffffffu;   // Extend(init_crc, ...)
         if (lane == 0) out[i] = c;
     }
 }
@@ -893,6 +900,74 @@ extern "C" int b2_snappy_compress_batch(b2_ctx* c, const void* bytes, uint32_t n
     CU(cudaStreamSynchronize(c->stream));
     c->uploaded = false; c->executed = false;
     return B2_OK;
+}
+
+
+// ---- leaf codecs with the REFERENCE's own signatures (seam 4: what a CompressHandler / ChecksumHandler body or any direct caller of
+// butil::crc32c / butil::snappy would be re-pointed at).  They run on a process-wide default context (device $B2_DEVICE or 0, created on
+// first use); one buffer per call is the latency-bound way to use a GPU — the batch forms above are the throughput path.
+static std::mutex g_leaf_mu;
+static b2_ctx* g_leaf_ctx = nullptr;
+static b2_ctx* leaf_ctx(size_t need_bytes) {
+    if (g_leaf_ctx && need_bytes + 4096 <= g_leaf_ctx->opt.max_batch_bytes) return g_leaf_ctx;
+    if (g_leaf_ctx) { b2_ctx_destroy(g_leaf_ctx); g_leaf_ctx = nullptr; }
+    b2_options o; memset(&o, 0, sizeof o);
+    o.device = getenv("B2_DEVICE") ? atoi(getenv("B2_DEVICE")) : 0;
+    size_t cap = 8u << 20; while (cap < need_bytes + 4096 && cap < (1ull << 30)) cap <<= 1;
+    o.max_batch_bytes = (uint32_t)cap; o.max_msgs = 4096; o.max_runs = 16; o.max_resp_bytes = (uint32_t)(cap + cap / 4 + (1u << 20));
+    if (b2_ctx_create(&o, &g_leaf_ctx) != B2_OK) g_leaf_ctx = nullptr;
+    return g_leaf_ctx;
+}
+// butil::crc32c::Extend (src/butil/crc32c.h:24, crc32c.cc:379-454)
+extern "C" uint32_t b2_crc32c_extend(uint32_t init_crc, const char* data, size_t n) {
+    if (n == 0) return init_crc;
+    std::lock_guard<std::mutex> g(g_leaf_mu);
+    b2_ctx* c = leaf_ctx(n);
+    if (!c || n > c->opt.max_batch_bytes) return 0;
+    cudaSetDevice(c->opt.device);
+    const uint32_t off = 0, len = (uint32_t)n; uint32_t out = 0;
+    if (cudaMemcpyAsync(c->d_bytes, data, n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) return 0;
+    cudaMemcpyAsync(c->d_frame_off, &off, 4, cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(c->d_slot, &len, 4, cudaMemcpyHostToDevice, c->stream);
+    k_crc32c_batch<<<1, 32, 0, c->stream>>>(c->d_bytes, c->d_frame_off, c->d_slot, 1, (uint32_t*)c->d_aux, c->d_crc_adv, init_crc);
+    cudaMemcpyAsync(&out, c->d_aux, 4, cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    c->uploaded = false; c->executed = false;
+    return out;
+}
+// butil::snappy::MaxCompressedLength / RawCompress / GetUncompressedLength / RawUncompress (third_party/snappy/snappy.h:112-141)
+extern "C" size_t b2_snappy_max_compressed_length(size_t n) { return 32 + n + n / 6; }
+extern "C" void b2_snappy_raw_compress(const char* input, size_t input_length, char* compressed, size_t* compressed_length) {
+    *compressed_length = 0;
+    std::lock_guard<std::mutex> g(g_leaf_mu);
+    b2_ctx* c = leaf_ctx(input_length + input_length / 4);
+    if (!c) return;
+    const uint32_t off = 0, len = (uint32_t)input_length; uint32_t ooff = 0, olen = 0;
+    const uint8_t dummy = 0;
+    if (b2_snappy_compress_batch(c, input_length ? (const void*)input : (const void*)&dummy, len, &off, &len, 1, compressed,
+                                 (uint32_t)(((b2_snappy_max_compressed_length(input_length) + 15) & ~(size_t)15)), &ooff, &olen) == B2_OK) *compressed_length = olen;
+}
+extern "C" int b2_snappy_get_uncompressed_length(const char* compressed, size_t n, size_t* result) {   // varint32 preamble (snappy.cc:690-711)
+    uint32_t v = 0, shift = 0; size_t k = 0;
+    for (;;) {
+        if (shift >= 32 || k >= n) return 0;
+        const uint32_t b = (uint8_t)compressed[k++]; v |= (b & 0x7f) << shift;
+        if (b < 128) break;
+        shift += 7;
+    }
+    *result = v; return 1;
+}
+extern "C" int b2_snappy_raw_uncompress(const char* compressed, size_t compressed_length, char* uncompressed) {
+    size_t ulen = 0;
+    if (!b2_snappy_get_uncompressed_length(compressed, compressed_length, &ulen)) return 0;
+    std::lock_guard<std::mutex> g(g_leaf_mu);
+    b2_ctx* c = leaf_ctx(compressed_length > ulen ? compressed_length : ulen);
+    if (!c) return 0;
+    const uint32_t off = 0, len = (uint32_t)compressed_length; uint32_t ooff = 0; int32_t olen = -1;
+    std::vector<char> tmp(((ulen + 15) & ~(size_t)15) + 16);
+    if (b2_snappy_uncompress_batch(c, compressed, len, &off, &len, 1, tmp.data(), (uint32_t)tmp.size(), &ooff, &olen) != B2_OK || olen < 0 || (size_t)olen != ulen) return 0;
+    memcpy(uncompressed, tmp.data() + ooff, ulen);
+    return 1;
 }
 
 extern "C" int b2_hpack_reset(b2_ctx* c, uint32_t conn, uint32_t max_table_size) {

@@ -1873,6 +1873,88 @@ __global__ void __launch_bounds__(kPackWarps * 32, 1) k_pack_tma(BatchPtrs B, De
 // k_pack_slow.  A tile larger than the staging buffer (big frames) decodes from 160-byte rows and streams its range through
 // the buffer in chunks, patching the prefixes that fall into each chunk.
 constexpr uint32_t kFusedWarps = 16, kFusedBuf = 10752, kFusedRowStride = 176;
+// The plain echo request exactly as PackRpcRequest emits it (baidu_rpc_protocol.cpp:1045-1133) — known fields once each, ascending,
+// one-byte tags and lengths, compress / content / checksum type 0, no attachment, no checksum bytes, body "0a <len> <message>" —
+// decoded, looked up and ANSWERED in ~300 instructions: descriptor to HBM, reply prefix written right in front of the payload
+// (pfx_out == nullptr: in place inside the staged tile) or into pfx_out.  Returns false on ANY deviation: the caller then runs
+// decode_one<true>, which alone defines the semantics; for what it accepts the result is identical (tests/test_gpu_parity.py,
+// tools/fuzz_parity.py run both).
+__device__ __forceinline__ bool fused_fast_echo(const BatchPtrs& B, const DevMethod* ms, uint32_t n_ms, uint32_t i, uint32_t fo, uint32_t run_idx,
+                                                uint8_t* f, uint32_t avail, uint8_t* pfx_out, DecodeOut& o) {
+    if (ld32_any(f) != kMagicPRPC) return false;
+    const uint32_t body = __byte_perm(ld32_any(f + 4), 0, 0x0123), meta = __byte_perm(ld32_any(f + 8), 0, 0x0123);
+    if (meta < 8 || (uint64_t)12 + meta + 8 > avail || meta > body) return false;
+    const uint8_t* m = f + 12; const uint8_t* te = m + meta;
+    if (m[0] != 0x0a) return false;
+    const uint32_t L = m[1];
+    if (L >= 128 || L < 4 || 2 + L > meta) return false;
+    const uint8_t* q = m + 2; const uint8_t* e = q + L;
+    if (q[0] != 0x0a) return false;
+    const uint32_t sl = q[1];
+    if (sl >= 128 || sl + 4 > L) return false;
+    const uint8_t* svc = q + 2; q = svc + sl;
+    if (q[0] != 0x12) return false;
+    const uint32_t ml = q[1];
+    if (ml >= 128 || (uint32_t)(e - q) < 2 + ml) return false;
+    const uint8_t* mth = q + 2; q = mth + ml;
+    uint32_t has = B2_HAS_REQUEST; uint64_t v = 0; long long log_id = 0;
+    if (q < e) {
+        if (*q != 0x18) return false;
+        Reader r; r.p = q + 1; r.end = e;
+        if (!rd_varint(r, v) || r.p != e) return false;
+        log_id = (long long)v; has |= B2_HAS_LOG_ID;
+    }
+    const uint8_t* t = e;
+    if (t + 2 <= te && t[0] == 0x18) { if (t[1] != 0) return false; has |= B2_HAS_COMPRESS_TYPE; t += 2; }
+    long long cid = 0;
+    if (t < te && t[0] == 0x20) { Reader r; r.p = t + 1; r.end = te; if (!rd_varint(r, v)) return false; cid = (long long)v; has |= B2_HAS_CORRELATION_ID; t = r.p; }
+    if (t + 2 <= te && t[0] == 0x50) { if (t[1] != 0) return false; has |= B2_HAS_CONTENT_TYPE; t += 2; }
+    if (t + 2 <= te && t[0] == 0x58) { if (t[1] != 0) return false; has |= B2_HAS_CHECKSUM_TYPE; t += 2; }
+    if (t + 2 <= te && t[0] == 0x62) { if (t[1] != 0) return false; has |= B2_HAS_CHECKSUM_VALUE; t += 2; }
+    if (t != te) return false;
+    // Server::FindMethodPropertyByFullName on a service name that carries its package (the jprotobuf short form goes the generic way)
+    bool has_dot = false;
+    for (uint32_t k = 0; k < sl && !has_dot; k += 4) {
+        uint32_t eq = __vcmpeq4(ld32_any(svc + k), 0x2e2e2e2eu);
+        if (sl - k < 4) eq &= (1u << (8 * (sl - k))) - 1u;
+        has_dot = eq != 0;
+    }
+    if (!has_dot) return false;
+    int idx = -1;
+    for (uint32_t k = 0; k < n_ms; k++) {
+        const DevMethod& d = ms[k];
+        if (d.full_method_len == sl + 1 + ml && d.full_method[sl] == '.' && bytes_eq(svc, d.full_method, sl) && bytes_eq(mth, d.full_method + sl + 1, ml)) { idx = (int)k; break; }
+    }
+    if (idx < 0) return false;
+    const DevMethod& M = ms[idx];
+    if (M.handler != B2_HANDLER_ECHO || M.response_checksum_type != B2_CHECKSUM_TYPE_NONE || M.response_compress_type != B2_COMPRESS_TYPE_NONE) return false;
+    // EchoRequest{message}: "0a <len> <bytes>" filling the body exactly
+    const uint32_t req_size = body - meta;
+    if (req_size < 2 || te[0] != 0x0a) return false;
+    Reader r; r.p = te + 1; r.end = te + (req_size < 6 ? req_size : 6);
+    if (!rd_varint(r, v)) return false;
+    const uint32_t hdr = (uint32_t)(r.p - te);
+    if (v > 0x7fffffefull || (uint64_t)hdr + v != req_size) return false;
+    const uint32_t msg_len = (uint32_t)v, msg_off = 12 + meta + hdr;
+    // SendRpcResponse: 12 02 08 00 | 18 00 | 20 cid | 50 00 | 58 00 | 62 00, then the EchoResponse field header
+    const uint32_t cidn = varint_len((uint64_t)cid), mlr = 13 + cidn, vl = varint_len(msg_len), prefix = 12 + mlr + 1 + vl;
+    if (prefix > msg_off) return false;
+    uint8_t* p = pfx_out ? pfx_out : f + msg_off - prefix;
+    p[0] = 'P'; p[1] = 'R'; p[2] = 'P'; p[3] = 'C';
+    put_be32(p + 4, mlr + 1 + vl + msg_len); put_be32(p + 8, mlr); p += 12;
+    p[0] = 0x12; p[1] = 0x02; p[2] = 0x08; p[3] = 0x00; p[4] = 0x18; p[5] = 0x00; p[6] = 0x20; p += 7;
+    p = put_varint(p, (uint64_t)cid);
+    p[0] = 0x50; p[1] = 0x00; p[2] = 0x58; p[3] = 0x00; p[4] = 0x62; p[5] = 0x00; p[6] = 0x0a; p += 7;
+    put_varint(p, msg_len);
+    b2_msg_desc d;
+    d.run_idx = run_idx; d.frame_off = fo; d.body_size = body; d.meta_size = meta; d.correlation_id = cid; d.log_id = log_id;
+    d.attachment_size = 0; d.compress_type = 0; d.checksum_type = 0; d.error_code = 0; d.has_bits = (uint16_t)has; d.protocol = B2_PROTOCOL_BAIDU_STD;
+    d.content_type = 0; d.method_idx = (int16_t)idx; d.status = B2_MSG_ECHOED; d.resp_off = fo + msg_off - prefix; d.resp_len = prefix + msg_len;
+    B.msgs[i] = d;
+    o.fast = true; o.slow = false; o.prefix = prefix; o.rs = d.resp_off;
+    return true;
+}
+
 struct FusedWarpSmem {
     alignas(128) uint8_t buf[kFusedBuf];
     alignas(16) uint8_t pfx[32][kHeadBytes];       // reply prefix of each message of the round (decode_one's head record)
@@ -1896,6 +1978,15 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(BatchPtrs B, DevC
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     FusedWarpSmem& S = reinterpret_cast<FusedWarpSmem*>(fused_raw)[wid];
     if (B.totals[2] & 1u) return;
+    // the method table of a typical server (one or two methods) is read from shared memory by every message
+    __shared__ __align__(16) DevMethod s_methods[2];
+    {
+        const uint32_t nw = min(C.n_methods, 2u) * (uint32_t)(sizeof(DevMethod) / 4);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(B.methods); uint32_t* dst = reinterpret_cast<uint32_t*>(s_methods);
+        for (uint32_t k = threadIdx.x; k < nw; k += blockDim.x) dst[k] = src[k];
+    }
+    __syncthreads();
+    const DevMethod* ms = C.n_methods <= 2 ? s_methods : B.methods;
     if (lane == 0) { mbar_init(&S.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncwarp();
     uint32_t phase = 0;
@@ -1942,7 +2033,13 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(BatchPtrs B, DevC
                 if (lane == 0) { bulk_wait_read<0>(); mbar_arrive_expect_tx(&S.mbar, span); bulk_g2s(S.buf, B.bytes + lo16, span, &S.mbar); }
                 __syncwarp();
                 mbar_wait(&S.mbar, phase & 1u); phase++;
-                if (lane < cnt && i < B.max_msgs) decode_one<true>(B, C, i, fo_raw, S.buf + (fo - lo16), S.pfx[lane], 0xffffffffu, r, &o);
+                bool in_place = false;
+                if (lane < cnt && i < B.max_msgs) {
+                    uint8_t* f = S.buf + (fo - lo16);
+                    in_place = !client && !(fo_raw >> 31) && fused_fast_echo(B, ms, C.n_methods, i, fo, r, f, hi16 - fo, nullptr, o);
+                    if (!in_place) decode_one<true>(B, C, i, fo_raw, f, S.pfx[lane], 0xffffffffu, r, &o);
+                }
+                if (in_place) o.prefix = 0;                                 // (already written where it belongs)
             } else {
                 // ---- big frames: decode from 160-byte rows staged in the (idle) buffer
                 if (lane == 0) bulk_wait_read<0>();
@@ -1960,7 +2057,11 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(BatchPtrs B, DevC
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 __syncwarp();
-                if (lane < cnt && i < B.max_msgs) decode_one<true>(B, C, i, fo_raw, S.buf + lane * kFusedRowStride + (fo & 15u), S.pfx[lane], kRowBytes, r, &o);
+                if (lane < cnt && i < B.max_msgs) {
+                    uint8_t* f = S.buf + lane * kFusedRowStride + (fo & 15u);
+                    if (client || (fo_raw >> 31) || !fused_fast_echo(B, ms, C.n_methods, i, fo, r, f, kRowBytes - (fo & 15u), S.pfx[lane], o))
+                        decode_one<true>(B, C, i, fo_raw, f, S.pfx[lane], kRowBytes, r, &o);
+                }
                 __syncwarp();
             }
             // ---- everything that is not an in-place echo goes to k_pack_slow
@@ -1972,7 +2073,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(BatchPtrs B, DevC
                 if (o.slow) B.slow_idx[sbase + __popc(slow_mask & ((1u << lane) - 1u))] = i;
             }
             if (fits) {
-                if (o.fast) { uint8_t* dst = S.buf + (o.rs - lo16); const uint8_t* src = S.pfx[lane]; for (uint32_t k = 0; k < o.prefix; k++) dst[k] = src[k]; }
+                if (o.fast && o.prefix) { uint8_t* dst = S.buf + (o.rs - lo16); const uint8_t* src = S.pfx[lane]; for (uint32_t k = 0; k < o.prefix; k++) dst[k] = src[k]; }
                 fence_proxy_async();
                 __syncwarp();
                 fused_store(B.resp, S.buf, lo16, sub_lo, sub_hi, lane);

@@ -322,6 +322,10 @@ int  b2_batch_launch(b2_ctx* ctx);
 int  b2_batch_wait(b2_ctx* ctx);
 int  b2_elapsed_ms(b2_ctx* a, b2_ctx* b, float* ms);
 
+/* What the last upload / launch decided: out[0] tile bytes, [1] tiles, [2] frame offsets kept per tile, [3] 1 = the fused
+ * decode+pack kernel served the batch (0 = the slot-scan pipeline). */
+int  b2_batch_info(b2_ctx* ctx, uint32_t out[4]);
+
 /* Device time of each stage of the last execute, in launch order.  Writes up to
  * `cap` entries of (name, ms); returns the number of stages. */
 int  b2_stage_times(b2_ctx* ctx, const char** names, float* ms, int cap);
@@ -347,6 +351,21 @@ int  b2_snappy_uncompress_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
 int  b2_snappy_compress_batch(b2_ctx* ctx, const void* bytes, uint32_t nbytes,
                               const uint32_t* offs, const uint32_t* lens, uint32_t n,
                               void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens);
+
+/* ---- the same leaves with the REFERENCE's own signatures, for direct substitution at seam 4 (the bodies of the
+ * CompressHandler / ChecksumHandler registered in src/brpc/global.cpp:400-418, or any direct caller):
+ *   b2_crc32c_extend                  == butil::crc32c::Extend          (src/butil/crc32c.h:24)
+ *   b2_snappy_max_compressed_length   == butil::snappy::MaxCompressedLength   (third_party/snappy/snappy.h:112)
+ *   b2_snappy_raw_compress            == butil::snappy::RawCompress     (snappy.h:125)   bit-exact output
+ *   b2_snappy_get_uncompressed_length == butil::snappy::GetUncompressedLength (snappy.h:141), returns 1/0 for true/false
+ *   b2_snappy_raw_uncompress          == butil::snappy::RawUncompress   (snappy.h:135), returns 1/0
+ * They run on a process-wide default context (device $B2_DEVICE, default 0), one buffer per call: correct, not fast — the
+ * batch forms above are the throughput path. */
+uint32_t b2_crc32c_extend(uint32_t init_crc, const char* data, size_t n);
+size_t   b2_snappy_max_compressed_length(size_t source_bytes);
+void     b2_snappy_raw_compress(const char* input, size_t input_length, char* compressed, size_t* compressed_length);
+int      b2_snappy_get_uncompressed_length(const char* compressed, size_t compressed_length, size_t* result);
+int      b2_snappy_raw_uncompress(const char* compressed, size_t compressed_length, char* uncompressed);
 
 /* ---- client mirror: PackRpcRequest (src/brpc/policy/baidu_rpc_protocol.cpp:1045-1133) with
  * SerializeRpcRequest (:1015-1043: EchoRequest{message}, COMPRESS_TYPE_NONE / SNAPPY, CRC32C over the serialized body)
