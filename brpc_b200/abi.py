@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "libb2rpc.so")
+lib_path = os.environ.get("B2RPC_LIB") or os.path.join(_HERE, "libb2rpc.so")      # (B2RPC_LIB: A/B builds of the same library for tuning runs)
 
 B2_OK, B2_E_INVAL, B2_E_NO_DEVICE, B2_E_CUDA, B2_E_CAPACITY, B2_E_NOMEM = 0, -1, -2, -3, -4, -5
 

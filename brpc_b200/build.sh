@@ -5,4 +5,4 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
     -Xcompiler -fPIC,-Wall -Xptxas -v -shared $B2_NVCC_DEFS \
-    -o "$HERE/libb2rpc.so" "$HERE/csrc/b2_api.cu" 2>&1
+    -o "${B2_OUT:-$HERE/libb2rpc.so}" "$HERE/csrc/b2_api.cu" 2>&1

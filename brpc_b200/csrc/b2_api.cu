@@ -240,7 +240,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
         CU(cudaMemcpy(c->d_crc_adv, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
     }
     CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(k_pack_slow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * kSnapRing)));
+    CU(cudaFuncSetAttribute(k_pack_slow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * kSnapRing)));
     CU(cudaFuncSetAttribute(k_pack_tma<kPackGroup>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PackWarpSmem) * kPackWarps)));
     CU(cudaFuncSetAttribute(k_pack_tma<kPackGroupSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(PackWarpSmem) * kPackWarps)));
     if (const char* e = getenv("B2_PACK")) c->use_tma_pack = strcmp(e, "reg") != 0;
@@ -448,10 +448,10 @@ static int launch_pipeline(b2_ctx* c) {
     }
     }
     if (fused) {
-        if (mask & 4) { k_pack_slow<<<sms * B2_SLOW_MIN_BLOCKS, 256, 8 * kSnapRing, s>>>(B, C); launches++; mark("pack_slow"); }
+        if (mask & 4) { k_pack_slow<true><<<sms * B2_SLOW_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack_slow"); }
     } else if (c->use_tma_pack) {
         // k_pack_slow first: its verify pass decides which CRC-carrying echoes k_pack_tma may move
-        if (mask & 4) { k_pack_slow<<<sms * B2_SLOW_MIN_BLOCKS, 256, 8 * kSnapRing, s>>>(B, C); launches++; mark("pack_slow"); }
+        if (mask & 4) { k_pack_slow<false><<<sms * B2_SLOW_MIN_BLOCKS, 256, 8 * kSnapRing, s>>>(B, C); launches++; mark("pack_slow"); }
         if (mask & 2) {
             // small requests: 32 messages per warp round instead of 8 (measured +30 % at 64 B payloads, -3 % at 1 KB)
             if ((c->avg_frame && c->avg_frame < 640) || c->cfg.by_ref) k_pack_tma<kPackGroupSmall><<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C);

@@ -1872,7 +1872,14 @@ __global__ void __launch_bounds__(kPackWarps * 32, 1) k_pack_tma(BatchPtrs B, De
 // client-side and stream outputs) get a slot in the overflow area behind the batch-shaped part of resp and are served by
 // k_pack_slow.  A tile larger than the staging buffer (big frames) decodes from 160-byte rows and streams its range through
 // the buffer in chunks, patching the prefixes that fall into each chunk.
-constexpr uint32_t kFusedWarps = 16, kFusedBuf = 10752, kFusedRowStride = 176;
+#ifndef B2_FUSED_BUF
+#define B2_FUSED_BUF 10240
+#endif
+// (16 x ~13.5 KB leave ~12 KB of the SM's shared memory to k_resolve of the next batch, which runs beside this kernel)
+#ifndef B2_FUSED_WARPS
+#define B2_FUSED_WARPS 16      // measured: 16 warps x 128 registers 115 us per 256 MiB batch; 20 x 96 the same (spills), 21 x 96 does not launch
+#endif
+constexpr uint32_t kFusedWarps = B2_FUSED_WARPS, kFusedBuf = B2_FUSED_BUF, kFusedRowStride = 176;
 // The plain echo request exactly as PackRpcRequest emits it (baidu_rpc_protocol.cpp:1045-1133) — known fields once each, ascending,
 // one-byte tags and lengths, compress / content / checksum type 0, no attachment, no checksum bytes, body "0a <len> <message>" —
 // decoded, looked up and ANSWERED in ~300 instructions: descriptor to HBM, reply prefix written right in front of the payload
@@ -1957,10 +1964,11 @@ __device__ __forceinline__ bool fused_fast_echo(const BatchPtrs& B, const DevMet
 
 struct FusedWarpSmem {
     alignas(128) uint8_t buf[kFusedBuf];
-    alignas(16) uint8_t pfx[32][kHeadBytes];       // reply prefix of each message of the round (decode_one's head record)
     uint32_t foff[32];
     alignas(8) unsigned long long mbar;
 };
+// (the reply prefix of a message the GENERIC decoder answers is staged in HBM — B.heads, 96 bytes per message — not in shared
+// memory: the exact-shape path writes its prefix in place and needs no staging, and shared memory buys resident warps)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // resp[a, b) <- the shared-memory image whose byte 0 is batch offset `img_off`; 16-byte aligned interior by TMA, edges by bytes
@@ -1973,7 +1981,11 @@ __device__ __forceinline__ void fused_store(uint8_t* resp, const uint8_t* img, u
     if (lane >= 16 && lane - 16 < b - b0) resp[b0 + lane - 16] = img[b0 + lane - 16 - img_off];
 }
 
-__global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(BatchPtrs B, DevConfig C) {
+#ifndef B2_FUSED_REGS
+#define B2_FUSED_REGS 128
+#endif
+static_assert(B2_FUSED_REGS * B2_FUSED_WARPS * 32 <= 65536, "k_fused: registers x threads must fit the SM's register file");
+__global__ void __maxnreg__(B2_FUSED_REGS) k_fused(BatchPtrs B, DevConfig C) {
     extern __shared__ __align__(128) uint8_t fused_raw[];
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     FusedWarpSmem& S = reinterpret_cast<FusedWarpSmem*>(fused_raw)[wid];
@@ -1991,14 +2003,21 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(BatchPtrs B, DevC
     __syncwarp();
     uint32_t phase = 0;
     const uint32_t n_warps = gridDim.x * kFusedWarps;
-    for (uint32_t t = blockIdx.x * kFusedWarps + wid; t < B.n_tiles; t += n_warps) {
-        const TileRec rec = B.tiles[t];
+    // the records of the NEXT tile are requested before the current one is worked on (they would otherwise cost a DRAM round trip per tile)
+    uint32_t t = blockIdx.x * kFusedWarps + wid;
+    uint4 rec_raw = make_uint4(0, 0, 0, 0), ti = make_uint4(0, 0, 0, 0); uint32_t tbase = 0;
+    if (t < B.n_tiles) { rec_raw = *reinterpret_cast<const uint4*>(B.tiles + t); ti = __ldg(B.tile_info + t); tbase = B.tile_base[t]; }
+    for (; t < B.n_tiles; t += n_warps) {
+        const uint4 rec_cur = rec_raw, ti_cur = ti; const uint32_t tbase_cur = tbase;
+        const uint32_t tn = t + n_warps;
+        if (tn < B.n_tiles) { rec_raw = *reinterpret_cast<const uint4*>(B.tiles + tn); ti = __ldg(B.tile_info + tn); tbase = B.tile_base[tn]; }
+        TileRec rec; *reinterpret_cast<uint4*>(&rec) = rec_cur;
         const uint32_t count = rec.count;
         if (!rec.live || count == 0) continue;
-        const uint4 ti = __ldg(B.tile_info + t);
+        const uint4 ti = ti_cur;
         const uint32_t r = ti.w & 0xffffffu, run_off = ti.x, run_len = ti.y;
         const bool client = ((ti.w >> 24) & B2_RUN_CLIENT) != 0;
-        const uint32_t first = B.run_status[r].first_msg + B.tile_base[t];
+        const uint32_t first = B.run_status[r].first_msg + tbase_cur;
         const uint32_t hi = run_off + rec.exit;
         const bool spec_ok = !(rec.kind & kKindRewalked) && count <= C.spec_k;
         const uint32_t* spec = B.tile_spec + (size_t)t * C.spec_k;
@@ -2037,7 +2056,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(BatchPtrs B, DevC
                 if (lane < cnt && i < B.max_msgs) {
                     uint8_t* f = S.buf + (fo - lo16);
                     in_place = !client && !(fo_raw >> 31) && fused_fast_echo(B, ms, C.n_methods, i, fo, r, f, hi16 - fo, nullptr, o);
-                    if (!in_place) decode_one<true>(B, C, i, fo_raw, f, S.pfx[lane], 0xffffffffu, r, &o);
+                    if (!in_place) decode_one<true>(B, C, i, fo_raw, f, B.heads + (size_t)i * kHeadBytes, 0xffffffffu, r, &o);
                 }
                 if (in_place) o.prefix = 0;                                 // (already written where it belongs)
             } else {
@@ -2059,8 +2078,8 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(BatchPtrs B, DevC
                 __syncwarp();
                 if (lane < cnt && i < B.max_msgs) {
                     uint8_t* f = S.buf + lane * kFusedRowStride + (fo & 15u);
-                    if (client || (fo_raw >> 31) || !fused_fast_echo(B, ms, C.n_methods, i, fo, r, f, kRowBytes - (fo & 15u), S.pfx[lane], o))
-                        decode_one<true>(B, C, i, fo_raw, f, S.pfx[lane], kRowBytes, r, &o);
+                    if (client || (fo_raw >> 31) || !fused_fast_echo(B, ms, C.n_methods, i, fo, r, f, kRowBytes - (fo & 15u), B.heads + (size_t)i * kHeadBytes, o))
+                        decode_one<true>(B, C, i, fo_raw, f, B.heads + (size_t)i * kHeadBytes, kRowBytes, r, &o);
                 }
                 __syncwarp();
             }
@@ -2073,7 +2092,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(BatchPtrs B, DevC
                 if (o.slow) B.slow_idx[sbase + __popc(slow_mask & ((1u << lane) - 1u))] = i;
             }
             if (fits) {
-                if (o.fast && o.prefix) { uint8_t* dst = S.buf + (o.rs - lo16); const uint8_t* src = S.pfx[lane]; for (uint32_t k = 0; k < o.prefix; k++) dst[k] = src[k]; }
+                if (o.fast && o.prefix) { uint8_t* dst = S.buf + (o.rs - lo16); const uint8_t* src = B.heads + (size_t)i * kHeadBytes; for (uint32_t k = 0; k < o.prefix; k++) dst[k] = src[k]; }
                 fence_proxy_async();
                 __syncwarp();
                 fused_store(B.resp, S.buf, lo16, sub_lo, sub_hi, lane);
@@ -2088,7 +2107,8 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(BatchPtrs B, DevC
                     mbar_wait(&S.mbar, phase & 1u); phase++;
                     if (o.fast) {
                         const uint32_t p0 = max(o.rs, c0), p1 = min(o.rs + o.prefix, c1);
-                        for (uint32_t k = p0; k < p1; k++) S.buf[k - c0] = S.pfx[lane][k - o.rs];
+                        const uint8_t* pf = B.heads + (size_t)i * kHeadBytes;
+                        for (uint32_t k = p0; k < p1; k++) S.buf[k - c0] = pf[k - o.rs];
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -2206,16 +2226,20 @@ __global__ void __launch_bounds__(256) k_pack_requests(const uint8_t* bytes, con
 #ifndef B2_SLOW_MIN_BLOCKS
 #define B2_SLOW_MIN_BLOCKS 3
 #endif
+// kLite: no shared memory at all (CRC tables read through L1, no snappy ring) — the variant launched behind k_fused, where slow messages
+// are rare by construction and the kernel must be able to start on SMs whose shared memory the next batch's k_fused already holds
+template <bool kLite>
 __global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs B, DevConfig C) {
     const uint32_t lane = threadIdx.x & 31;
     if (B.totals[2] & 3u) return;
     finalize_runs(B, C);                               // (was a separate launch)
     const uint32_t n_verify = B.totals[7];
     if (B.totals[3] == 0 && n_verify == 0) return;
-    __shared__ uint32_t s_hot[kCrcHotWords];
+    __shared__ uint32_t s_hot[kLite ? 1 : kCrcHotWords];
     extern __shared__ __align__(16) uint8_t s_rings[];           // kSnapRing bytes per warp
-    crc_tabs_to_smem(s_hot, B.crc_adv);
-    CrcTabs ct; ct.hot = s_hot; ct.tree = B.crc_adv + kCrcHotWords; ct.ring = s_rings + (threadIdx.x >> 5) * kSnapRing;
+    CrcTabs ct; ct.tree = B.crc_adv + kCrcHotWords;
+    if (kLite) { ct.hot = B.crc_adv; ct.ring = nullptr; }
+    else { crc_tabs_to_smem(s_hot, B.crc_adv); ct.hot = s_hot; ct.ring = s_rings + (threadIdx.x >> 5) * kSnapRing; }
     // the slow messages were listed by k_decode; warps pull them one at a time (sizes vary from an error
     // text to a 256 KiB snappy stream, so the queue is dynamic: totals[6] is the ticket)
     // verify pass: Crc32cVerify (policy/crc32c_checksum.cpp:44-61) of the plain echoes whose reply k_pack_tma moves;

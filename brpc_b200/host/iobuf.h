@@ -115,6 +115,21 @@ public:
         return 0;
     }
 
+    // One refcounted Block over memory this library does not own — the pinned reply area of a GPU batch, a connection's
+    // registered read region — and cheap references into it (no allocation per reference: what a zero-copy reply is made of).
+    // The creator holds one reference (release_external_block drops it); `deleter(data)' runs when the last one dies.
+    static Block* create_external_block(void* data, size_t size, std::function<void(void*)> deleter) {
+        if (size > 0xffffffffull) return nullptr;
+        Block* b = static_cast<Block*>(::operator new(sizeof(Block), std::nothrow));
+        if (!b) return nullptr;
+        new (b) Block();
+        b->nshared.store(1); b->size = (uint32_t)size; b->cap = (uint32_t)size; b->data = static_cast<char*>(data);
+        b->user_deleter = new std::function<void(void*)>(std::move(deleter));
+        return b;
+    }
+    static void release_external_block(Block* b) { if (b) b->dec_ref(); }
+    void append_block_range(Block* b, uint32_t offset, uint32_t length) { BlockRef r; r.offset = offset; r.length = length; r.block = b; push_ref(r, true); }
+
     size_t pop_front(size_t n) {
         const size_t saved = n < _nbytes ? n : _nbytes; n = saved;
         while (n) {
