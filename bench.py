@@ -787,6 +787,18 @@ def main():
                 "latency": latency, "clocks": clocks, "wall_ms_per_step": wall_ms_max / steps,
                 "value_by_wall_clock": total_msgs * ppass * steps / (wall_ms_max * 1e-3), "msgs_per_step": total_msgs * ppass,
                 "counters_allreduced": counters}
+        if not use_dist:
+            # the same e2e through the C++ host side a brpc transport would run (b2::GpuTransport: registered read regions, three
+            # batches in flight, pull + by-reference replies gathered by writev into /dev/null; tests/cpp/transport_test.cc bench)
+            tb = os.path.join(ROOT, "tests", "cpp", "transport_test")
+            if os.path.exists(tb):
+                try:
+                    for cx in ctxs:
+                        cx.close()
+                    out = subprocess.run([tb, "bench", str(args.run_mib), "90", "1", "1"], capture_output=True, text=True, timeout=120)
+                    line["e2e_messenger"] = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else {"error": (out.stderr or out.stdout)[-300:]}
+                except Exception as e:      # noqa: BLE001
+                    line["e2e_messenger"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
             # bounded sample: the first 8 connections of the same batch, 1 thread, ~10 s
             sub = runs[:8].copy()

@@ -175,6 +175,7 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     }
     memset(&c->cfg, 0, sizeof c->cfg);
     c->cfg.max_body_size = o->max_body_size ? o->max_body_size : (64ull << 20);
+    c->cfg.proto_mask = kProtoMaskDefault;
     c->cfg.tile_bytes = tile;
     c->cfg.tile_shift = 0; while ((1u << c->cfg.tile_shift) < tile) c->cfg.tile_shift++;
     c->max_tiles = o->max_batch_bytes / tile + o->max_runs + 1;
@@ -281,6 +282,14 @@ extern "C" int b2_set_modes(b2_ctx* c, int input_mode, int resp_mode) {
     return B2_OK;
 }
 
+extern "C" int b2_set_protocols(b2_ctx* c, uint32_t mask) {
+    const uint32_t known = (1u << 1) | (1u << 2) | (1u << 3) | (1u << 4) | (1u << 12);
+    if (!c || mask == 0 || (mask & ~known)) { set_err("unknown protocol in mask (baidu_std 1, streaming_rpc 2, hulu_pbrpc 3, sofa_pbrpc 4, nshead 12)"); return B2_E_INVAL; }
+    ring_halt(c);
+    c->cfg.proto_mask = mask;
+    return B2_OK;
+}
+
 extern "C" int b2_set_stream_handler(b2_ctx* c, int kind) {
     if (!c || (kind != B2_STREAM_DESC_ONLY && kind != B2_STREAM_SNAPPY_UNCOMPRESS)) { set_err("bad stream handler"); return B2_E_INVAL; }
     c->cfg.stream_handler = (uint32_t)kind;
@@ -334,7 +343,12 @@ static BatchPtrs make_ptrs(b2_ctx* c) {
 
 extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs) {
     if (!c || (!bytes && nbytes) || (!runs && n_runs)) { set_err("null argument"); return B2_E_INVAL; }
-    if (nbytes > c->opt.max_batch_bytes || n_runs > c->opt.max_runs) { set_err("batch exceeds ctx capacity"); return B2_E_CAPACITY; }
+    // (B2_INPUT_PULL: `bytes` is the caller's whole pinned arena and nothing is copied — what is bounded is the bytes the runs cover)
+    if ((c->input_mode != B2_INPUT_PULL && nbytes > c->opt.max_batch_bytes) || nbytes >= (1u << 31) || n_runs > c->opt.max_runs) { set_err("batch exceeds ctx capacity"); return B2_E_CAPACITY; }
+    if (c->input_mode == B2_INPUT_PULL) {
+        uint64_t covered = 0; for (uint32_t r = 0; r < n_runs; r++) covered += runs[r].length;
+        if (covered > c->opt.max_batch_bytes) { set_err("runs exceed ctx capacity"); return B2_E_CAPACITY; }
+    }
     CU(cudaSetDevice(c->opt.device));
     if (c->adaptive_tile) {
         // like Socket::_avg_msg_size steering the read size (input_messenger.cpp:348-353): a tile should hold

@@ -65,8 +65,71 @@ B2_HD Cut parse_prefixed(const uint8_t* p, uint32_t n, uint32_t magic, uint64_t 
     return c;
 }
 
-// One CutInputMessage call on a server-side socket with handlers
-// {1: baidu_std, 2: streaming_rpc}.
+// The other length-prefixed protocols that share MostCommonMessage, handler index == ProtocolType
+// (src/brpc/options.proto:38-67) so that the probing order of CutInputMessage is the reference's:
+//   3  hulu_pbrpc  ParseHuluMessage   policy/hulu_pbrpc_protocol.cpp:178-223  "HULU" body_size meta_size, host (little-endian) order
+//   4  sofa_pbrpc  ParseSofaMessage   policy/sofa_pbrpc_protocol.cpp:165-205  "SOFA" meta_size(32) body_size(64) msg_size(64), little-endian
+//   12 nshead      ParseNsheadMessage policy/nshead_protocol.cpp:154-182      36-byte nshead_t, magic 0xfb709394 at +24, body_len at +32
+constexpr uint32_t kMagicHULU = 0x554c5548u;   // "HULU"
+constexpr uint32_t kMagicSOFA = 0x41464f53u;   // "SOFA"
+constexpr uint32_t kMagicNshead = 0xfb709394u; // NSHEAD_MAGICNUM, src/brpc/nshead.h:27
+constexpr uint32_t kProtoMaskDefault = (1u << 1) | (1u << 2);
+B2_HD uint32_t frame_header_len(int idx) { return idx == 4 ? 24u : idx == 12 ? 36u : 12u; }
+B2_HD uint64_t load_le64(const uint8_t* p) { return (uint64_t)load_le32(p) | ((uint64_t)load_le32(p + 4) << 32); }
+
+// Protocol::parse of handler `idx` on the bytes at p.  Cut.pop = bytes the handler removed (a whole message, or the garbage it
+// popped before answering TRY_OTHERS); Cut.body = bytes behind the header that belong to the message, Cut.meta = its meta part.
+B2_HD Cut parse_frame(const uint8_t* p, uint32_t n, int idx, uint64_t max_body) {
+    if (idx == 1 || idx == 2) return parse_prefixed(p, n, magic_of(idx), max_body);
+    Cut c; c.err = B2_PARSE_OK; c.pop = 0; c.body = 0; c.meta = 0;
+    if (idx == 3 || idx == 4) {
+        const uint32_t magic = idx == 3 ? kMagicHULU : kMagicSOFA;
+        if (n >= 4) { if (load_le32(p) != magic) { c.err = B2_PARSE_ERROR_TRY_OTHERS; return c; } }
+        else for (uint32_t i = 0; i < n; i++) if (p[i] != (uint8_t)(magic >> (8 * i))) { c.err = B2_PARSE_ERROR_TRY_OTHERS; return c; }
+        if (idx == 3) {
+            if (n < 12) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+            const uint32_t body = load_le32(p + 4), meta = load_le32(p + 8);
+            if ((uint64_t)body > max_body) { c.err = B2_PARSE_ERROR_TOO_BIG_DATA; return c; }
+            if ((uint64_t)n < 12ull + body) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+            if (meta > body) { c.pop = 12 + body; c.err = B2_PARSE_ERROR_TRY_OTHERS; return c; }
+            c.pop = 12 + body; c.body = body; c.meta = meta;
+            return c;
+        }
+        if (n < 24) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+        const uint32_t meta = load_le32(p + 4);
+        const uint64_t body = load_le64(p + 8), msg = load_le64(p + 16);
+        if (msg != (uint64_t)meta + body) { c.err = B2_PARSE_ERROR_TRY_OTHERS; return c; }            // (nothing is popped)
+        if (body > max_body) { c.err = B2_PARSE_ERROR_TOO_BIG_DATA; return c; }
+        if ((uint64_t)n < 24ull + msg) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+        c.pop = 24 + (uint32_t)msg; c.body = (uint32_t)msg; c.meta = meta;
+        return c;
+    }
+    // nshead: the magic sits behind id, version, log_id and provider[16]
+    if (n < 28) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+    if (load_le32(p + 24) != kMagicNshead) { c.err = B2_PARSE_ERROR_TRY_OTHERS; return c; }
+    if (n < 36) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+    const uint32_t body = load_le32(p + 32);
+    if ((uint64_t)body > max_body) { c.err = B2_PARSE_ERROR_TOO_BIG_DATA; return c; }
+    if ((uint64_t)n < 36ull + body) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+    c.pop = 36 + body; c.body = body; c.meta = 0;
+    return c;
+}
+B2_HD int next_handler(uint32_t mask, int after) {             // handlers in index order: 1, 2, 3, 4, 12
+    for (int i = after + 1; i <= 12; i++) if ((mask >> i) & 1u) return i;
+    return -1;
+}
+
+// nshead has no magic in front: it answers NOT_ENOUGH_DATA to ANY 27 bytes and claims whatever carries its magic at +24.  When it is the
+// socket's preferred handler it is asked first, so a step at `pos` that another handler would accept comes out differently — the one way
+// (besides a handler popping garbage) in which the outcome of CutInputMessage depends on the preferred index.  Speculative walks that
+// do not know the preferred index hand such steps to the resolver.
+B2_HD bool nshead_claims(const uint8_t* run, uint32_t len, uint32_t pos, uint64_t max_body, uint32_t mask) {
+    if (!((mask >> 12) & 1u)) return false;
+    return parse_frame(run + pos, len - pos, 12, max_body).err != B2_PARSE_ERROR_TRY_OTHERS;
+}
+
+// One CutInputMessage call on a socket whose messenger holds the handlers enabled in `mask`
+// (default {1: baidu_std, 2: streaming_rpc}; b2_set_protocols adds 3 hulu_pbrpc, 4 sofa_pbrpc, 12 nshead).
 struct Step {
     int err;             // B2_PARSE_OK => one message cut
     int index;           // protocol of the message
@@ -77,14 +140,15 @@ struct Step {
     bool popped;         // some handler popped bytes and answered TRY_OTHERS (pf-sensitive path)
 };
 
-B2_HD Step cut_input_message(const uint8_t* run, uint32_t len, uint32_t pos, int pf, uint64_t max_body, bool client = false) {
+B2_HD Step cut_input_message(const uint8_t* run, uint32_t len, uint32_t pos, int pf, uint64_t max_body, bool client = false,
+                             uint32_t mask = kProtoMaskDefault) {
     Step s; s.err = B2_PARSE_ERROR_TRY_OTHERS; s.index = -1; s.pf = pf; s.frame_pos = pos; s.new_pos = pos;
     s.body = 0; s.meta = 0; s.popped = false;
     const int pref = pf;
-    if (pref >= 1 && pref <= 2) {
+    if (pref >= 1 && pref <= 12 && ((mask >> pref) & 1u)) {
         int cur = pref;
         for (;;) {
-            Cut c = parse_prefixed(run + pos, len - pos, magic_of(cur), max_body);
+            Cut c = parse_frame(run + pos, len - pos, cur, max_body);
             if (c.err == B2_PARSE_OK || c.err == B2_PARSE_ERROR_NOT_ENOUGH_DATA) {
                 s.err = c.err; s.index = cur; s.pf = cur;
                 if (c.err == B2_PARSE_OK) { s.frame_pos = pos; s.new_pos = pos + c.pop; s.body = c.body; s.meta = c.meta; }
@@ -96,14 +160,14 @@ B2_HD Step cut_input_message(const uint8_t* run, uint32_t len, uint32_t pos, int
             if (!client) break;
             // client side (CreatedByConnect): baidu_std may fall to streaming_rpc and back, once;
             // anything else is fixed by the channel's protocol (input_messenger.cpp:122-138)
-            if (cur == pref) { cur = 3 - pref; continue; }
+            if (cur == pref && (cur == 1 || cur == 2)) { cur = 3 - pref; continue; }
             s.err = B2_PARSE_ERROR_ABSOLUTELY_WRONG; return s;
         }
         s.pf = -1;
     }
-    for (int i = 1; i <= 2; i++) {
+    for (int i = next_handler(mask, 0); i > 0; i = next_handler(mask, i)) {
         if (i == pref) continue;
-        Cut c = parse_prefixed(run + pos, len - pos, magic_of(i), max_body);
+        Cut c = parse_frame(run + pos, len - pos, i, max_body);
         if (c.err == B2_PARSE_OK || c.err == B2_PARSE_ERROR_NOT_ENOUGH_DATA) {
             s.err = c.err; s.index = i; s.pf = i;
             if (c.err == B2_PARSE_OK) { s.frame_pos = pos; s.new_pos = pos + c.pop; s.body = c.body; s.meta = c.meta; }

@@ -78,6 +78,7 @@ struct DevConfig {
     uint32_t stream_handler;      // B2_STREAM_*
     uint32_t spec_k;              // speculative frame offsets kept per tile: kSpecK, or kSpecKDense when tiles hold many small frames
     uint32_t by_ref;              // B2_RESP_BY_REF: OK echo replies are {prefix, reference into the request bytes}
+    uint32_t proto_mask;          // handlers of the messenger (bit = ProtocolType): default baidu_std | streaming_rpc; b2_set_protocols adds hulu / sofa / nshead
     uint32_t fused;               // the fused decode+pack kernel serves this batch: replies sit at their request's own offset, slow ones in the overflow area
     uint32_t ovf_base;            // ... which starts here in the resp region
     uint32_t pull;                // B2_INPUT_PULL: `bytes` is mapped host memory; the walk stashes each frame's first 128 bytes in HBM
@@ -126,13 +127,13 @@ struct BatchPtrs {
 // the tile is handed to the resolver (kAmbig).
 template <bool kSpec, typename Emit>
 B2_HD void walk_tile(const uint8_t* run, uint32_t len, uint32_t entry, int pf_in, uint32_t tile_end,
-                     uint64_t max_body, bool client, TileRec& t, Emit emit) {
+                     uint64_t max_body, bool client, TileRec& t, Emit emit, uint32_t mask = kProtoMaskDefault) {
     uint32_t pos = entry, count = 0;
     int pf = kSpec ? -1 : pf_in, last = 0;
     uint8_t kind = kRanOff;
     while (pos < tile_end) {
-        const Step s = cut_input_message(run, len, pos, pf, max_body, client);
-        if (kSpec && count == 0 && s.popped) { kind = kAmbig; break; }
+        const Step s = cut_input_message(run, len, pos, pf, max_body, client, mask);
+        if (kSpec && count == 0 && (s.popped || (s.index != 12 && nshead_claims(run, len, pos, max_body, mask)))) { kind = kAmbig; break; }
         if (s.err != B2_PARSE_OK) { kind = kStop; break; }
         emit(count, s);
         count++; last = s.index; pf = s.index; pos = s.new_pos;
@@ -146,7 +147,7 @@ constexpr uint8_t kKindRewalked = 0x80;    // k_resolve re-walked the tile: its 
 struct EmitSpec {
     uint32_t* out; uint32_t run_off, cap;
     __device__ __forceinline__ void operator()(uint32_t i, const Step& s) const {
-        if (i < cap) out[i] = (run_off + s.frame_pos) | ((uint32_t)(s.index - 1) << 31);
+        if (i < cap) out[i] = (run_off + s.frame_pos) | ((uint32_t)(s.index != 1) << 31);
     }
 };
 
@@ -199,17 +200,20 @@ __global__ void __launch_bounds__(256, 6) k_tile_search(BatchPtrs B, DevConfig C
                 // lane owns 16 positions [p0, p0+16); needs 3 more bytes for the last windows
                 const uint32_t w0 = c0 + u * 512, p0 = w0 + lane * 16;
                 const uint32_t w[5] = { v[u].x, v[u].y, v[u].z, v[u].w, nx[u] };
-                uint32_t mask = 0;
+                uint32_t mask = 0, mkind = 0;                        // mask: a magic starts at this position; mkind: 2 bits each — 0 PRPC/STRM, 1 HULU, 2 SOFA
+                const bool ext = (C.proto_mask & ((1u << 3) | (1u << 4))) != 0;
                 #pragma unroll
                 for (int k4 = 0; k4 < 4; k4++) {
-                    // byte prefilter: only positions holding 'P' or 'S' (first byte of "PRPC" / "STRM") are looked at
+                    // byte prefilter: only positions holding 'P' or 'S' (first byte of "PRPC" / "STRM" / "SOFA"; 'H' for "HULU") are looked at
                     uint32_t e = __vcmpeq4(w[k4], 0x50505050u) | __vcmpeq4(w[k4], 0x53535353u);
+                    if (ext) e |= __vcmpeq4(w[k4], 0x48484848u);
                     while (e) {
                         const int b = (__ffs(e) - 1) >> 3;
                         e &= ~(0xffu << (8 * b));
                         const int j = 4 * k4 + b;
                         const uint32_t word = __funnelshift_r(w[k4], w[k4 + 1], b * 8);
-                        if (is_magic(word) && p0 + j + 4 <= len && p0 + j < t1) mask |= 1u << j;
+                        const bool other = ext && ((word == kMagicHULU && (C.proto_mask & 8u)) || (word == kMagicSOFA && (C.proto_mask & 16u)));
+                        if ((is_magic(word) || other) && p0 + j + 4 <= len && p0 + j < t1) { mask |= 1u << j; if (other) mkind |= (word == kMagicHULU ? 1u : 2u) << (2 * j); }
                     }
                 }
                 // candidates in position order: lanes ascending, bits ascending.  A candidate is taken when its header is
@@ -220,10 +224,13 @@ __global__ void __launch_bounds__(256, 6) k_tile_search(BatchPtrs B, DevConfig C
                 while (any && entry == kNone) {
                     const int src = __ffs(any) - 1;
                     uint32_t m = __shfl_sync(0xffffffffu, mask, src);
+                    const uint32_t kinds = __shfl_sync(0xffffffffu, mkind, src);
                     while (m && entry == kNone) {
                         const int jj = __ffs(m) - 1;
                         const uint32_t p = w0 + src * 16 + jj;
                         m &= m - 1;
+                        const uint32_t kind = (kinds >> (2 * jj)) & 3u;
+                        if (kind == 2) { entry = p; break; }                 // "SOFA": taken on the magic alone (k_resolve is the exactness gate)
                         uint32_t body_le = 0, meta_le = 0;
                         if (src < 31) {
                             const uint32_t q = (uint32_t)(jj + 4) >> 2, sh = ((uint32_t)(jj + 4) & 3u) * 8u;   // body_size sits at byte jj + 4
@@ -236,7 +243,7 @@ __global__ void __launch_bounds__(256, 6) k_tile_search(BatchPtrs B, DevConfig C
                         } else if (p + 12 <= len) {                      // (the header straddles two windows: read it)
                             body_le = load_le32(base + p + 4); meta_le = load_le32(base + p + 8);
                         } else continue;
-                        const uint32_t body = __byte_perm(body_le, 0, 0x0123), meta = __byte_perm(meta_le, 0, 0x0123);
+                        const uint32_t body = kind == 1 ? body_le : __byte_perm(body_le, 0, 0x0123), meta = kind == 1 ? meta_le : __byte_perm(meta_le, 0, 0x0123);   // hulu: host order
                         if (meta <= body && (uint64_t)body <= C.max_body_size) entry = p;
                     }
                     any &= any - 1;
@@ -260,7 +267,7 @@ __device__ __forceinline__ HdrWords load_hdr_words(const uint8_t* p) {          
 }
 template <typename Emit>
 __device__ __forceinline__ void walk_tile_spec(const uint8_t* run, uint32_t len, uint32_t entry, uint32_t tile_end,
-                                               uint64_t max_body, bool client, TileRec& t, Emit emit) {
+                                               uint64_t max_body, bool client, TileRec& t, Emit emit, uint32_t mask) {
     uint32_t pos = entry, count = 0, prev_len = 0, pre_pos = kNone;
     int pf = -1, last = 0;
     uint8_t kind = kRanOff;
@@ -278,13 +285,14 @@ __device__ __forceinline__ void walk_tile_spec(const uint8_t* run, uint32_t len,
                            h2 = sh ? __funnelshift_r(h.w2, h.w3, sh) : h.w2;
             const int idx = h0 == kMagicPRPC ? 1 : h0 == kMagicSTRM ? 2 : 0;
             const uint32_t body = __byte_perm(h1, 0, 0x0123), meta = __byte_perm(h2, 0, 0x0123);
-            if (idx && (uint64_t)body <= max_body && (uint64_t)(len - pos) >= 12ull + body && meta <= body) {
+            // (a preferred nshead handler is asked first and may claim these bytes: pf == 12 goes the generic way)
+            if (idx && pf != 12 && (uint64_t)body <= max_body && (uint64_t)(len - pos) >= 12ull + body && meta <= body) {
                 s.err = B2_PARSE_OK; s.index = idx; s.pf = idx; s.frame_pos = pos; s.new_pos = pos + 12 + body; s.body = body; s.meta = meta; s.popped = false;
                 fast = true;
             }
         }
-        if (!fast) s = cut_input_message(run, len, pos, pf, max_body, client);
-        if (count == 0 && s.popped) { kind = kAmbig; break; }
+        if (!fast) s = cut_input_message(run, len, pos, pf, max_body, client, mask);
+        if (count == 0 && (s.popped || (s.index != 12 && nshead_claims(run, len, pos, max_body, mask)))) { kind = kAmbig; break; }
         if (s.err != B2_PARSE_OK) { kind = kStop; break; }
         emit(count, s);
         count++; last = s.index; pf = s.index; prev_len = s.new_pos - pos; pos = s.new_pos;
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(128) k_tile_walk(BatchPtrs B, DevConfig C) {
     if (rec.entry != kNone) {
         // the frame offsets met on the way are kept: if k_resolve accepts the tile as is, k_frame_table only has to copy them
         EmitSpec e; e.out = B.tile_spec + (size_t)t * C.spec_k; e.run_off = run.offset; e.cap = C.spec_k;
-        walk_tile_spec(B.bytes + run.offset, run.length, rec.entry, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, rec, e);
+        walk_tile_spec(B.bytes + run.offset, run.length, rec.entry, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, rec, e, C.proto_mask);
     }
     B.tiles[t] = rec;
 }
@@ -345,11 +353,16 @@ __global__ void __launch_bounds__(128) k_tile_walk_pull(BatchPtrs B, DevConfig C
                 const uint32_t h0 = sh ? __funnelshift_r(w0, w1, sh) : w0, h1 = sh ? __funnelshift_r(w1, w2, sh) : w1, h2 = sh ? __funnelshift_r(w2, w3, sh) : w2;
                 idx = h0 == kMagicPRPC ? 1 : h0 == kMagicSTRM ? 2 : 0;
                 const uint32_t body = __byte_perm(h1, 0, 0x0123), meta = __byte_perm(h2, 0, 0x0123);
-                if (idx && (uint64_t)body <= C.max_body_size && (uint64_t)(len - pos) >= 12ull + body && meta <= body) { fast = true; new_pos = pos + 12 + body; }
+                if (idx && pf != 12 && (uint64_t)body <= C.max_body_size && (uint64_t)(len - pos) >= 12ull + body && meta <= body) { fast = true; new_pos = pos + 12 + body; }
+            }
+            if (count == 0 && ((C.proto_mask >> 12) & 1u)) {          // unknown preferred index + an nshead handler that would claim the bytes: the resolver decides
+                int amb = 0;
+                if (sub == 0) amb = nshead_claims(run, len, pos, C.max_body_size, C.proto_mask) ? 1 : 0;
+                if (__shfl_sync(gmask, amb, l0)) { kind = kAmbig; break; }
             }
             if (!fast) {                                              // short tails, oversize bodies, meta > body, unknown bytes: the generic restatement
                 Step s; s.err = 0; s.index = 0; s.new_pos = 0; s.frame_pos = 0; s.popped = false;
-                if (sub == 0) s = cut_input_message(run, len, pos, pf, C.max_body_size, client);
+                if (sub == 0) s = cut_input_message(run, len, pos, pf, C.max_body_size, client, C.proto_mask);
                 err = __shfl_sync(gmask, s.err, l0); idx = __shfl_sync(gmask, s.index, l0); new_pos = __shfl_sync(gmask, s.new_pos, l0);
                 frame_pos = __shfl_sync(gmask, s.frame_pos, l0); popped = __shfl_sync(gmask, (int)s.popped, l0) != 0;
                 if (count == 0 && popped) { kind = kAmbig; break; }
@@ -357,7 +370,7 @@ __global__ void __launch_bounds__(128) k_tile_walk_pull(BatchPtrs B, DevConfig C
                 v = __ldg(reinterpret_cast<const uint4*>(run + (frame_pos & ~15u)) + sub);
             }
             if (count < cap) {
-                if (sub == 0) spec[count] = (ti.x + frame_pos) | ((uint32_t)(idx - 1) << 31);
+                if (sub == 0) spec[count] = (ti.x + frame_pos) | ((uint32_t)(idx != 1) << 31);
                 rows[(size_t)count * 8 + sub] = v;
             }
             count++; last = idx; pf = idx; pos = new_pos;
@@ -429,7 +442,7 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C, uint3
     for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) {
         const TileRec t = tiles[k];
         link[k] = (k == 0 && t.entry != 0) ? kLinkRewalk : make_link(t, tiles, nt, C.tile_shift);
-        cp[k] = (t.count << 2) | ((uint32_t)t.last_proto & 3u);
+        cp[k] = (t.count << 4) | ((uint32_t)t.last_proto & 15u);     // (protocol indices go up to 12: nshead)
         live[k] = 0;
     }
     // dense shortcut: the leading stretch of tiles whose verified link goes to the next tile is
@@ -456,11 +469,11 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C, uint3
                 if (via_ok) pos = tiles[k].entry;
                 // the true chain enters tile k at `pos` but the speculation has nothing usable there
                 int pf = run.preferred_proto;
-                for (uint32_t j = k; j-- > 0;) if (live[j] && (cp[j] >> 2)) { pf = (int)(cp[j] & 3u); break; }
+                for (uint32_t j = k; j-- > 0;) if (live[j] && (cp[j] >> 4)) { pf = (int)(cp[j] & 15u); break; }
                 TileRec t; t.live = 0; t.pf_in = 0;
-                walk_tile<false>(base, len, pos, pf, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, t, NoEmit());
+                walk_tile<false>(base, len, pos, pf, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, t, NoEmit(), C.proto_mask);
                 tiles[k].entry = t.entry; tiles[k].exit = t.exit; tiles[k].count = t.count; tiles[k].kind = t.kind | kKindRewalked; tiles[k].last_proto = t.last_proto;
-                cp[k] = (t.count << 2) | ((uint32_t)t.last_proto & 3u);
+                cp[k] = (t.count << 4) | ((uint32_t)t.last_proto & 15u);
                 v = make_link(t, tiles, nt, C.tile_shift);
                 link[k] = v;
             }
@@ -487,8 +500,8 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C, uint3
     for (uint32_t k0 = 0; k0 < nt; k0 += blockDim.x) {
         const uint32_t k = k0 + threadIdx.x;
         const uint32_t lv = k < nt ? live[k] : 0;
-        const uint32_t c = lv ? (cp[k] >> 2) : 0;
-        const uint32_t pr = (lv && c) ? (cp[k] & 3u) : 0;
+        const uint32_t c = lv ? (cp[k] >> 4) : 0;
+        const uint32_t pr = (lv && c) ? (cp[k] & 15u) : 0;
         uint32_t x = c, y = pr;
         #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -518,7 +531,7 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C, uint3
         const int pf_true = s_carry_pf ? (int)s_carry_pf : run.preferred_proto;
         // the step that ends ProcessNewMessage's loop, with the true preferred index (never OK:
         // every tile walk stops only on a non-OK step or past the last tile, where no bytes remain)
-        const Step s = cut_input_message(base, len, pos, pf_true, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0);
+        const Step s = cut_input_message(base, len, pos, pf_true, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, C.proto_mask);
         b2_run_status st;
         st.consumed = s.new_pos; st.parse_error = (uint32_t)s.err; st.n_msgs = s_carry_sum; st.first_msg = 0;
         st.preferred_proto = s.pf; st.reserved0 = 0; st.resp_off = 0; st.resp_bytes = 0;
@@ -537,7 +550,7 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C, uint3
 struct EmitFrame {
     uint32_t* out; uint32_t* out_run; uint32_t run_off; uint32_t run_idx; uint32_t cap_left; uint32_t* out_row;
     __device__ __forceinline__ void operator()(uint32_t i, const Step& s) const {
-        if (i < cap_left) { out[i] = (run_off + s.frame_pos) | ((uint32_t)(s.index - 1) << 31); out_run[i] = run_idx; if (out_row) out_row[i] = kNone; }
+        if (i < cap_left) { out[i] = (run_off + s.frame_pos) | ((uint32_t)(s.index != 1) << 31); out_run[i] = run_idx; if (out_row) out_row[i] = kNone; }
     }
 };
 // kSpecK threads per tile: a live tile that k_resolve accepted as speculated hands over the offsets k_tile_walk
@@ -567,7 +580,7 @@ __global__ void __launch_bounds__(256) k_frame_table(BatchPtrs B, DevConfig C) {
     TileRec tmp;
     EmitFrame e; e.out = B.frame_off + first; e.out_run = B.frame_run + first; e.run_off = run.offset; e.run_idx = r; e.cap_left = B.max_msgs - first;
     e.out_row = C.pull ? B.frame_row + first : nullptr;
-    walk_tile<false>(B.bytes + run.offset, run.length, rec.entry, rec.pf_in, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, tmp, e);
+    walk_tile<false>(B.bytes + run.offset, run.length, rec.entry, rec.pf_in, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, tmp, e, C.proto_mask);
 }
 
 // --- k_decode: one thread per message ----------------------------------------
@@ -735,8 +748,29 @@ template <bool kFused>
 __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
                                            const uint8_t* srow, uint8_t* shead, uint32_t row_bytes, uint32_t run_idx, DecodeOut* out) {
     const uint32_t fo = fo_raw & 0x7fffffffu;
-    const int proto = (int)(fo_raw >> 31) + 1;
+    // bit 31 of a frame offset says "not baidu_std": which of the other handlers cut it is read off its magic
+    int proto = B2_PROTOCOL_BAIDU_STD;
+    if (fo_raw >> 31) { const uint32_t mg = load_le32(srow); proto = mg == kMagicSTRM ? 2 : mg == kMagicHULU ? 3 : mg == kMagicSOFA ? 4 : 12; }
     const uint8_t* gframe = B.bytes + fo;
+    if (proto > 2) {
+        // hulu_pbrpc / sofa_pbrpc / nshead: framed on the device, processed by the host (ProcessHuluRequest ... stay there): the descriptor
+        // carries protocol, frame_off, meta_size and body_size (the bytes behind the 12 / 24 / 36-byte header)
+        b2_msg_desc d;
+        d.run_idx = kFused ? run_idx : B.frame_run[i]; d.frame_off = fo;
+        if (proto == 3) { d.body_size = load_le32(srow + 4); d.meta_size = load_le32(srow + 8); }
+        else if (proto == 4) { d.meta_size = load_le32(srow + 4); d.body_size = load_le32(srow + 16); }
+        else { d.meta_size = 0; d.body_size = load_le32(srow + 32); }
+        d.correlation_id = 0; d.log_id = 0; d.attachment_size = 0; d.compress_type = 0; d.checksum_type = 0; d.error_code = 0;
+        d.has_bits = 0; d.protocol = (uint8_t)proto; d.content_type = 0; d.method_idx = -1; d.status = B2_MSG_FRAMED; d.resp_off = 0; d.resp_len = 0;
+        B.msgs[i] = d;
+        if (kFused) { out->fast = false; out->slow = false; out->prefix = 0; out->rs = 0; return; }
+        MsgAux a; a.msg_off = a.msg_len = a.att_len = a.att_off = a.cks_off = a.cks_len = 0; a.svc_off = a.svc_len = a.mth_off = a.mth_len = 0; a.pad = 0; a.err_kind = kErrNone;
+        B.aux[i] = a; B.slot[i] = 0;
+        PackJob job; job.src_off = 0; job.bulk_len = 0; job.head_len = 0; job.pad = 0; job.fast = 0; job.slot_len = 0;      // (pack_one returns at once: no reply)
+        B.jobs[i] = job;
+        if (C.by_ref) B.refs[i] = make_uint4(0, 0, 0, 0);
+        return;
+    }
     // decode from the staged copy when header + meta + the first body bytes are inside it
     const uint32_t meta_size_peek = load_be32(srow + 8);
     const bool staged = (uint64_t)(fo_raw & 15u) + 12ull + meta_size_peek + 40ull <= row_bytes;
@@ -2032,8 +2066,8 @@ __global__ void __maxnreg__(B2_FUSED_REGS) k_fused(BatchPtrs B, DevConfig C) {
             } else {
                 if (lane == 0) {                                        // a tile k_resolve re-walked (or a dense one): the chain again, true preferred index
                     for (uint32_t k = 0; k < cnt; k++) {
-                        const Step sp = cut_input_message(B.bytes + run_off, run_len, wpos, wpf, C.max_body_size, client);
-                        S.foff[k] = (run_off + sp.frame_pos) | ((uint32_t)(sp.index - 1) << 31);
+                        const Step sp = cut_input_message(B.bytes + run_off, run_len, wpos, wpf, C.max_body_size, client, C.proto_mask);
+                        S.foff[k] = (run_off + sp.frame_pos) | ((uint32_t)(sp.index != 1) << 31);
                         wpos = sp.new_pos; wpf = sp.pf;
                     }
                 }
@@ -2122,6 +2156,7 @@ __global__ void __maxnreg__(B2_FUSED_REGS) k_fused(BatchPtrs B, DevConfig C) {
     }
     if (lane == 0) bulk_wait<0>();
 }
+
 
 // --- k_pack_requests: the client mirror -------------------------------------------------------------
 // PackRpcRequest + SerializeRpcRequest (baidu_rpc_protocol.cpp:1015-1133) and PackStreamMessage
@@ -2308,7 +2343,7 @@ __device__ __forceinline__ void small_body(const BatchPtrs& B, const DevConfig& 
         run = B.runs[tid];
         uint32_t pos = 0; int pf = run.preferred_proto;
         for (;;) {
-            const Step sp = cut_input_message(B.bytes + run.offset, run.length, pos, pf, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0);
+            const Step sp = cut_input_message(B.bytes + run.offset, run.length, pos, pf, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, C.proto_mask);
             pos = sp.new_pos; pf = sp.pf;
             if (sp.err != B2_PARSE_OK) { st.parse_error = (uint32_t)sp.err; break; }
             my_count++;
@@ -2325,9 +2360,9 @@ __device__ __forceinline__ void small_body(const BatchPtrs& B, const DevConfig& 
         st.first_msg = first;
         uint32_t pos = 0, k = 0; int pf = run.preferred_proto;
         for (;;) {
-            const Step sp = cut_input_message(B.bytes + run.offset, run.length, pos, pf, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0);
+            const Step sp = cut_input_message(B.bytes + run.offset, run.length, pos, pf, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, C.proto_mask);
             if (sp.err != B2_PARSE_OK) break;
-            B.frame_off[first + k] = (run.offset + sp.frame_pos) | ((uint32_t)(sp.index - 1) << 31);
+            B.frame_off[first + k] = (run.offset + sp.frame_pos) | ((uint32_t)(sp.index != 1) << 31);
             B.frame_run[first + k] = tid; if (C.pull) B.frame_row[first + k] = kNone; k++;
             pos = sp.new_pos; pf = sp.pf;
         }

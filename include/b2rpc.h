@@ -50,6 +50,9 @@ extern "C" {
 #define B2_PROTOCOL_UNKNOWN       0
 #define B2_PROTOCOL_BAIDU_STD     1
 #define B2_PROTOCOL_STREAMING_RPC 2
+#define B2_PROTOCOL_HULU_PBRPC    3   /* framing only: b2_set_protocols */
+#define B2_PROTOCOL_SOFA_PBRPC    4
+#define B2_PROTOCOL_NSHEAD        12
 
 /* ---- CompressType / ChecksumType / ContentType, options.proto:69-88 ------ */
 #define B2_COMPRESS_TYPE_NONE   0
@@ -81,6 +84,9 @@ extern "C" {
                                    would get (0 = OK); resp_off/resp_len = the EchoResponse.message bytes,
                                    located in the BATCH buffer */
 #define B2_MSG_RESPONSE_UNZ  8  /* same, the response was snappy-compressed: message bytes are in the resp region */
+#define B2_MSG_FRAMED        9  /* a message of another length-prefixed protocol (hulu_pbrpc, sofa_pbrpc, nshead): cut by the
+                                   device, processed by the host; protocol / frame_off / meta_size / body_size are set, body_size
+                                   counts the bytes behind the 12- (hulu), 24- (sofa) or 36-byte (nshead) header */
 
 /* ---- has_bits of b2_msg_desc --------------------------------------------- */
 #define B2_HAS_REQUEST          (1u << 0)
@@ -224,6 +230,14 @@ const char* b2_version(void);
  * (FindMethodPropertyByFullName, baidu_rpc_protocol.cpp:749-756).
  * Returns the method index (>= 0) or a negative B2_E_*. */
 int  b2_register_method(b2_ctx* ctx, const b2_method* m);
+
+/* Which Protocol::parse handlers the messenger holds (InputMessenger::AddHandler, one bit per ProtocolType, probed in index order
+ * exactly like CutInputMessage): default (1 << B2_PROTOCOL_BAIDU_STD) | (1 << B2_PROTOCOL_STREAMING_RPC).  The other length-prefixed
+ * protocols that share MostCommonMessage can be added — ParseHuluMessage (policy/hulu_pbrpc_protocol.cpp:178-223), ParseSofaMessage
+ * (policy/sofa_pbrpc_protocol.cpp:165-205), ParseNsheadMessage (policy/nshead_protocol.cpp:154-182): their messages are cut in the
+ * same loop (preferred-index switching included) and surface as B2_MSG_FRAMED descriptors.  b2_run.preferred_proto may name any
+ * enabled handler. */
+int  b2_set_protocols(b2_ctx* ctx, uint32_t protocol_mask);
 
 /* What the device does with streaming_rpc DATA frames beyond cutting them and decoding StreamFrameMeta:
  * B2_STREAM_DESC_ONLY (default) or B2_STREAM_SNAPPY_UNCOMPRESS — the frame payload is a snappy stream

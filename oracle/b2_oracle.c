@@ -439,20 +439,65 @@ static cut_t parse_prefixed(const uint8_t* p, uint64_t n, const char* magic, uin
     c.pop = 12 + body; c.body_size = body; c.meta_size = meta;
     return c;
 }
-static const char* k_magic[3] = { NULL, "PRPC", "STRM" };   /* handler index == ProtocolType */
+static const char* k_magic[5] = { NULL, "PRPC", "STRM", "HULU", "SOFA" };   /* handler index == ProtocolType */
+static uint32_t le32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint64_t le64(const uint8_t* p) { return (uint64_t)le32(p) | ((uint64_t)le32(p + 4) << 32); }
 
-/* InputMessenger::CutInputMessage, input_messenger.cpp:84-179, for a
- * server-side socket (CreatedByConnect() false) with handlers {1: baidu_std,
- * 2: streaming_rpc}.  *pos advances by what the handlers popped.             */
+/* ParseHuluMessage, policy/hulu_pbrpc_protocol.cpp:178-223: "HULU", body_size and meta_size in HOST order (HuluRawUnpacker :110-135) */
+static cut_t parse_hulu(const uint8_t* p, uint64_t n, uint64_t max_body) {
+    cut_t c = { B2_PARSE_OK, 0, 0, 0 };
+    if (memcmp(p, "HULU", n >= 4 ? 4 : (size_t)n) != 0) { c.err = B2_PARSE_ERROR_TRY_OTHERS; return c; }
+    if (n < 12) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+    uint32_t body = le32(p + 4);
+    if ((uint64_t)body > max_body) { c.err = B2_PARSE_ERROR_TOO_BIG_DATA; return c; }
+    if (n < 12 + (uint64_t)body) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+    uint32_t meta = le32(p + 8);
+    if (meta > body) { c.pop = 12 + body; c.err = B2_PARSE_ERROR_TRY_OTHERS; return c; }   /* pop the message */
+    c.pop = 12 + body; c.body_size = body; c.meta_size = meta;
+    return c;
+}
+/* ParseSofaMessage, policy/sofa_pbrpc_protocol.cpp:165-205: 24-byte header "SOFA" meta_size(32) body_size(64) msg_size(64) */
+static cut_t parse_sofa(const uint8_t* p, uint64_t n, uint64_t max_body) {
+    cut_t c = { B2_PARSE_OK, 0, 0, 0 };
+    if (memcmp(p, "SOFA", n >= 4 ? 4 : (size_t)n) != 0) { c.err = B2_PARSE_ERROR_TRY_OTHERS; return c; }
+    if (n < 24) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+    uint32_t meta = le32(p + 4); uint64_t body = le64(p + 8), msg = le64(p + 16);
+    if (msg != (uint64_t)meta + body) { c.err = B2_PARSE_ERROR_TRY_OTHERS; return c; }
+    if (body > max_body) { c.err = B2_PARSE_ERROR_TOO_BIG_DATA; return c; }
+    if (n < 24 + msg) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+    c.pop = 24 + (uint32_t)msg; c.body_size = (uint32_t)msg; c.meta_size = meta;      /* descriptor: the bytes behind the header */
+    return c;
+}
+/* ParseNsheadMessage, policy/nshead_protocol.cpp:154-182 over nshead_t (src/brpc/nshead.h:28-36): magic_num at +24, body_len at +32 */
+static cut_t parse_nshead(const uint8_t* p, uint64_t n, uint64_t max_body) {
+    cut_t c = { B2_PARSE_OK, 0, 0, 0 };
+    if (n < 28) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+    if (le32(p + 24) != 0xfb709394u) { c.err = B2_PARSE_ERROR_TRY_OTHERS; return c; }
+    if (n < 36) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+    uint32_t body = le32(p + 32);
+    if ((uint64_t)body > max_body) { c.err = B2_PARSE_ERROR_TOO_BIG_DATA; return c; }
+    if (n < 36 + (uint64_t)body) { c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return c; }
+    c.pop = 36 + body; c.body_size = body; c.meta_size = 0;
+    return c;
+}
+static cut_t parse_handler(int idx, const uint8_t* p, uint64_t n, uint64_t max_body) {
+    if (idx == 3) return parse_hulu(p, n, max_body);
+    if (idx == 4) return parse_sofa(p, n, max_body);
+    if (idx == 12) return parse_nshead(p, n, max_body);
+    return parse_prefixed(p, n, k_magic[idx], max_body);
+}
+
+/* InputMessenger::CutInputMessage, input_messenger.cpp:84-179, over the handlers enabled in `mask` (_handlers[i].parse != NULL),
+ * probed in index order.  *pos advances by what the handlers popped.             */
 static cut_t cut_input_message(const uint8_t* run, uint32_t len, uint32_t* pos, int* preferred,
-                               int* index, uint64_t max_body, int created_by_connect) {
-    const int max_index = 2;
+                               int* index, uint64_t max_body, int created_by_connect, uint32_t mask) {
+    const int max_index = 12;
     const int pref = *preferred;
     cut_t c;
-    if (pref >= 1 && pref <= max_index) {
+    if (pref >= 0 && pref <= max_index && ((mask >> pref) & 1u)) {
         int cur_index = pref;
         do {
-            c = parse_prefixed(run + *pos, len - *pos, k_magic[cur_index], max_body);
+            c = parse_handler(cur_index, run + *pos, len - *pos, max_body);
             if (c.err == B2_PARSE_OK || c.err == B2_PARSE_ERROR_NOT_ENOUGH_DATA) {
                 if (c.err == B2_PARSE_OK) *pos += c.pop;
                 *preferred = cur_index; *index = cur_index; return c;
@@ -469,9 +514,9 @@ static cut_t cut_input_message(const uint8_t* run, uint32_t len, uint32_t* pos, 
         } while (1);
         *preferred = -1;
     }
-    for (int i = 1; i <= max_index; i++) {
-        if (i == pref) continue;
-        c = parse_prefixed(run + *pos, len - *pos, k_magic[i], max_body);
+    for (int i = 0; i <= max_index; i++) {
+        if (i == pref || !((mask >> i) & 1u)) continue;
+        c = parse_handler(i, run + *pos, len - *pos, max_body);
         if (c.err == B2_PARSE_OK || c.err == B2_PARSE_ERROR_NOT_ENOUGH_DATA) {
             if (c.err == B2_PARSE_OK) *pos += c.pop;
             *preferred = i; *index = i; return c;
@@ -767,6 +812,7 @@ int orc_process_batch(const orc_config* cfg, const uint8_t* bytes, uint32_t nbyt
                       uint8_t* resp, uint32_t resp_cap, uint32_t* resp_bytes) {
     uint32_t nm = 0; size_t rb = 0;
     uint64_t max_body = cfg->max_body_size ? cfg->max_body_size : (64ull << 20);
+    const uint32_t mask = cfg->protocols ? cfg->protocols : ((1u << 1) | (1u << 2));
     (void)nbytes;
     for (uint32_t r = 0; r < n_runs; r++) {
         const uint8_t* run = bytes + runs[r].offset;
@@ -777,7 +823,7 @@ int orc_process_batch(const orc_config* cfg, const uint8_t* bytes, uint32_t nbyt
         for (;;) {
             uint32_t before = pos;
             const int client = (runs[r].flags & B2_RUN_CLIENT) != 0;
-            cut_t c = cut_input_message(run, len, &pos, &preferred, &index, max_body, client);
+            cut_t c = cut_input_message(run, len, &pos, &preferred, &index, max_body, client, mask);
             if (c.err != B2_PARSE_OK) { rs[r].parse_error = (uint32_t)c.err; break; }
             if (nm >= msg_cap) return -1;
             b2_msg_desc* d = &msgs[nm];
@@ -792,9 +838,12 @@ int orc_process_batch(const orc_config* cfg, const uint8_t* bytes, uint32_t nbyt
             } else if (index == B2_PROTOCOL_BAIDU_STD) {
                 if (process_rpc_request(cfg, bytes + d->frame_off, d, resp + rb, resp_cap - rb, &rl) != 0) return -1;
                 d->resp_off = (uint32_t)rb; d->resp_len = (uint32_t)rl;
-            } else {
+            } else if (index == B2_PROTOCOL_STREAMING_RPC) {
                 process_stream_frame(cfg, bytes + d->frame_off, d, resp + rb, resp_cap - rb, &rl);
                 d->resp_off = (uint32_t)rb; d->resp_len = (uint32_t)rl;
+            } else {
+                /* hulu_pbrpc / sofa_pbrpc / nshead: the path frames them; ProcessHuluRequest & co. stay on the host */
+                d->status = B2_MSG_FRAMED; d->method_idx = -1;
             }
             rb += rl; nm++; rs[r].n_msgs++;
         }

@@ -69,6 +69,7 @@ typedef struct orc_config {
     const char* server_identity;  /* "ip:port" of Controller::AppendServerIdentiy, or NULL */
     const b2_method* methods; uint32_t n_methods;
     int stream_handler;           /* B2_STREAM_* */
+    uint32_t protocols;           /* handlers of the messenger, bit = ProtocolType; 0 = baidu_std | streaming_rpc */
 } orc_config;
 
 /* ---- leaf codecs ---------------------------------------------------------- */

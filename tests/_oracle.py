@@ -43,7 +43,7 @@ class Method(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("max_body_size", C.c_uint64), ("server_identity", C.c_char_p),
-                ("methods", C.POINTER(Method)), ("n_methods", C.c_uint32), ("stream_handler", C.c_int)]
+                ("methods", C.POINTER(Method)), ("n_methods", C.c_uint32), ("stream_handler", C.c_int), ("protocols", C.c_uint32)]
 
 
 class RequestSpec(C.Structure):
@@ -141,13 +141,13 @@ ECHO_METHOD = dict(service_full_name=b"example.EchoService", service_name=b"Echo
                    response_checksum_type=0, response_compress_type=0)
 
 
-def make_config(methods=None, max_body_size=0, server_identity=None, stream_handler=0):
+def make_config(methods=None, max_body_size=0, server_identity=None, stream_handler=0, protocols=0):
     methods = [ECHO_METHOD] if methods is None else methods
     arr = (Method * max(1, len(methods)))()
     for i, m in enumerate(methods):
         for k, v in m.items():
             setattr(arr[i], k, v)
-    cfg = Config(max_body_size, server_identity, arr, len(methods), stream_handler)
+    cfg = Config(max_body_size, server_identity, arr, len(methods), stream_handler, protocols)
     cfg._keep = arr
     return cfg
 

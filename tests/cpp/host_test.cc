@@ -11,6 +11,7 @@
 #include <vector>
 #include "../../brpc_b200/host/input_messenger.h"
 #include "../../brpc_b200/host/h2_messenger.h"
+#include "../../brpc_b200/host/protocol.h"
 #include "../../oracle/b2_oracle.h"
 
 #define CHECK(c) do { if (!(c)) { fprintf(stderr, "CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #c); exit(1); } } while (0)
@@ -152,7 +153,7 @@ static void test_messenger_gpu() {
     // pinned IOBuf blocks, as a brpc integration would install them
     b2::iobuf::blockmem_allocate = b2_block_alloc; b2::iobuf::blockmem_deallocate = b2_block_free;
     b2_options opt; memset(&opt, 0, sizeof opt);
-    opt.device = 0; opt.max_batch_bytes = 8 << 20; opt.max_msgs = 1 << 16; opt.max_runs = 256;
+    opt.device = 0; opt.max_batch_bytes = 8 << 20; opt.max_msgs = 1 << 16; opt.max_runs = 256; opt.max_body_size = 4 << 20;
     b2::GpuInputMessenger messenger(opt);
     b2_method echo = { "example.EchoService", "EchoService", "Echo", "example.EchoRequest", B2_HANDLER_ECHO, 1, 0, 0 };
     b2_method other = { "example.Other", "Other", "Call", "example.OtherRequest", B2_HANDLER_HOST, 0, 0, 0 };
@@ -208,6 +209,59 @@ static void test_messenger_gpu() {
     CHECK(checked >= kSockets - 2 && g_host_msgs == 8);
     printf("messenger ok: %d sockets, %d messages in %d rounds, %d streams byte-identical to the oracle, %d host-handled\n",
            kSockets, total_msgs, rounds, checked, g_host_msgs);
+}
+
+
+// ---- seam (1): the Protocol table with the GPU-backed parse entry, driven like InputMessenger::CutInputMessage drives a handler ----
+static void test_protocol_shim_gpu() {
+    using namespace b2;
+    CHECK(RegisterProtocol(PROTOCOL_B2_GPU, policy::GpuProtocol()) == 0);
+    CHECK(RegisterProtocol(PROTOCOL_B2_GPU, policy::GpuProtocol()) == -1);            // once-only per type (protocol.cpp:90-93)
+    Protocol none = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, CONNECTION_TYPE_ALL, "none" };
+    CHECK(RegisterProtocol((ProtocolType)101, none) == -1 && RegisterProtocol((ProtocolType)200, policy::GpuProtocol()) == -1);
+    const Protocol* proto = FindProtocol(PROTOCOL_B2_GPU);
+    CHECK(proto && proto->support_server() && !proto->support_client() && FindProtocol(PROTOCOL_BAIDU_STD) == nullptr);
+    b2_options opt; memset(&opt, 0, sizeof opt);
+    opt.device = 0; opt.max_batch_bytes = 4 << 20; opt.max_msgs = 1 << 14; opt.max_runs = 8;
+    b2_ctx* ctx = nullptr; CHECK(b2_ctx_create(&opt, &ctx) == B2_OK);
+    b2_method echo = { "example.EchoService", "EchoService", "Echo", "example.EchoRequest", B2_HANDLER_ECHO, 1, 0, 0 };
+    CHECK(b2_register_method(ctx, &echo) == 0);
+    CHECK(b2_set_protocols(ctx, (1u << 1) | (1u << 2) | (1u << 3) | (1u << 12)) == B2_OK);
+    policy::GpuParser parser(ctx, 4 << 20);
+    // a stream of baidu_std echo requests, one hulu frame, one nshead frame, then garbage
+    std::string stream; std::vector<uint8_t> f(1 << 16); std::vector<std::pair<int, size_t>> expect;   // (protocol, bytes behind the header)
+    for (int i = 0; i < 30; i++) {
+        b2press_spec sp = { "example.EchoService", "Echo", (uint32_t)(10 + 37 * i), 0, 1, 0, 20260921 };
+        const size_t n = b2press_frame(&sp, 900 + i, f.data(), f.size());
+        stream.append((const char*)f.data(), n); expect.push_back(std::make_pair(1, n - 12));
+        if (i == 10) { std::string h("HULU"); uint32_t b = 25, m = 5; h.append((const char*)&b, 4); h.append((const char*)&m, 4); h.append(25, 'h'); stream += h; expect.push_back(std::make_pair(3, (size_t)25)); }
+        if (i == 20) { std::string h(36, '\0'); uint32_t mg = 0xfb709394u, bl = 9; memcpy(&h[24], &mg, 4); memcpy(&h[32], &bl, 4); h.append(9, 'n'); stream += h; expect.push_back(std::make_pair(12, (size_t)9)); }
+    }
+    stream += "XXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXXX";
+    Socket sock(42); IOBuf source; size_t fed = 0, got = 0; unsigned seed = 7; int fatal = -1;
+    orc_config cfg; memset(&cfg, 0, sizeof cfg); cfg.methods = &echo; cfg.n_methods = 1; cfg.protocols = (1u << 1) | (1u << 2) | (1u << 3) | (1u << 12);
+    while (fatal < 0) {
+        ParseResult r = proto->parse(&source, &sock, false, &parser);
+        if (r.is_ok()) {
+            policy::GpuMessage* m = static_cast<policy::GpuMessage*>(r.message());
+            CHECK(got < expect.size() && m->desc.protocol == expect[got].first && m->meta.length() + m->payload.length() == expect[got].second + (m->desc.protocol == 12 ? 36 : 0));
+            if (m->desc.protocol == 1) CHECK(m->desc.status == B2_MSG_ECHOED && !m->reply.empty());
+            got++;
+            proto->process_request(m);                                   // writes the device-packed reply into sock._write_buf
+        } else if (r.error() == PARSE_ERROR_NOT_ENOUGH_DATA) {
+            if (fed == stream.size()) break;
+            seed = seed * 1103515245u + 12345u;
+            const size_t n = std::min(stream.size() - fed, (size_t)1 + (seed >> 16) % 3000);
+            source.append(stream.data() + fed, n); fed += n;
+        } else fatal = (int)r.error();
+    }
+    CHECK(got == expect.size() && fatal == PARSE_ERROR_TRY_OTHERS);          // the garbage tail: no handler takes it, the socket would be closed
+    // every reply byte == the oracle's response stream for the same bytes
+    b2_run run = { 0, 0, (uint32_t)stream.size(), -1, 0 }; b2_run_status rs; std::vector<b2_msg_desc> msgs(256); std::vector<uint8_t> resp(1 << 20); uint32_t nm = 0, rb = 0;
+    CHECK(orc_process_batch(&cfg, (const uint8_t*)stream.data(), run.length, &run, 1, &rs, msgs.data(), 256, &nm, resp.data(), (uint32_t)resp.size(), &rb) == 0);
+    CHECK(nm == expect.size() && sock._write_buf.to_string() == std::string((const char*)resp.data(), rb));
+    b2_ctx_destroy(ctx);
+    printf("protocol shim ok: %zu messages of 3 protocols cut through Protocol::parse, replies byte-identical to the oracle\n", got);
 }
 
 // ---- h2 / gRPC through GpuH2Messenger, every written byte against the oracle (same chunking fed to both) ----
@@ -306,6 +360,6 @@ int main(int argc, char** argv) {
     const std::string mode = argc > 1 ? argv[1] : "cpu";
     test_iobuf();
     test_portal_and_fd();
-    if (mode == "gpu") { test_messenger_gpu(); test_h2_messenger_gpu(); }
+    if (mode == "gpu") { test_messenger_gpu(); test_h2_messenger_gpu(); test_protocol_shim_gpu(); }
     return 0;
 }

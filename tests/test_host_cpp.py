@@ -12,7 +12,7 @@ BIN = os.path.join(ROOT, "tests", "cpp", "host_test")
 
 def _build():
     src = os.path.join(ROOT, "tests", "cpp", "host_test.cc")
-    deps = [src, os.path.join(ROOT, "brpc_b200", "host", "iobuf.h"), os.path.join(ROOT, "brpc_b200", "host", "input_messenger.h"), os.path.join(ROOT, "brpc_b200", "host", "h2_messenger.h")]
+    deps = [src, os.path.join(ROOT, "brpc_b200", "host", "iobuf.h"), os.path.join(ROOT, "brpc_b200", "host", "input_messenger.h"), os.path.join(ROOT, "brpc_b200", "host", "h2_messenger.h"), os.path.join(ROOT, "brpc_b200", "host", "protocol.h")]
     if os.path.exists(BIN) and all(os.path.getmtime(BIN) >= os.path.getmtime(d) for d in deps):
         return
     subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-Wall", "-o", BIN, src,
@@ -75,4 +75,4 @@ def test_gpu_input_messenger_cpp():
     _build()
     out = subprocess.run([BIN, "gpu"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "messenger ok" in out.stdout
+    assert "messenger ok" in out.stdout and "protocol shim ok" in out.stdout
