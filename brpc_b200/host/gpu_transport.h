@@ -11,7 +11,8 @@
 //     ReadUntilWouldBlock (each connection)  ->  Submit(g)  ...  Collect(g)  ->  replies written, consumed bytes popped
 // and while group g's batch is on the GPU the other groups are being read / collected, so the PCIe transfers, the kernels and the
 // host's socket work overlap (b2_batch_submit / b2_batch_collect, one context per group).  A connection belongs to exactly one
-// group and has at most one batch in flight: its input is processed serially, as brpc guarantees per socket.
+// group and has at most one batch in flight: its input is processed serially, as brpc guarantees per socket.  Groups share nothing
+// but the arena: each may be driven (Read / Submit / Collect) by its own thread.
 // With the default modes (B2_INPUT_PULL + B2_RESP_BY_REF) no payload byte moves on the host or across PCIe: the kernels read
 // headers and metas in place, and an echo reply is {prefix reference into the batch's pinned reply block, payload reference into
 // the connection's own read region}, written out by one writev per <= 128 replies.
@@ -56,7 +57,8 @@ public:
             if (b2_ctx_create(&o.ctx, &c) != B2_OK || b2_set_modes(c, o.input_mode, o.resp_mode) != B2_OK) { Destroy(); throw std::runtime_error(std::string("GpuTransport: ") + b2_last_error()); }
             _ctx.push_back(c);
         }
-        _groups.resize(o.pipeline); _inflight.assign(o.pipeline, false); _runs.resize(o.pipeline); _live.resize(o.pipeline);
+        _groups.resize(o.pipeline); _inflight.assign(o.pipeline, 0); _runs.resize(o.pipeline); _live.resize(o.pipeline); _iov.resize(o.pipeline); _pop.resize(o.pipeline);
+        _outstanding.reset(new std::atomic<int>[o.pipeline]); for (uint32_t g = 0; g < o.pipeline; g++) _outstanding[g].store(0);
     }
     ~GpuTransport() { Destroy(); }
     GpuTransport(const GpuTransport&) = delete;
@@ -111,19 +113,20 @@ public:
         const uint32_t span_end = runs.back().offset + runs.back().length;
         const int rc = b2_batch_submit(_ctx[g], _arena, span_end, runs.data(), (uint32_t)runs.size());
         if (rc != B2_OK) return -1;
-        _inflight[g] = true;
+        _inflight[g] = 1;
         return (int)runs.size();
     }
     // Wait for group g's batch; deliver its messages (replies through Socket::Write / the sink, host-handled ones through the
     // process callback), pop what was consumed.  Returns the number of messages cut, -1 on an ABI error.
     int Collect(uint32_t g) {
         if (!_inflight[g]) return 0;
-        _inflight[g] = false;
+        _inflight[g] = 0;
         b2_batch_result res;
         if (b2_batch_collect(_ctx[g], &res) != B2_OK) return -1;
         std::vector<b2_run>& runs = _runs[g]; std::vector<Conn*>& live = _live[g];
         // one external block over the batch's pinned reply area, one per connection region: every reply is two references
-        std::atomic<int>* outstanding = &_outstanding;
+        std::atomic<int>* outstanding = &_outstanding[g];
+        std::vector<struct iovec>& _iov = this->_iov[g]; std::vector<std::pair<Conn*, uint32_t>>& _pop = this->_pop[g];
         IOBuf::Block* resp_blk = nullptr;
         if (!_sink && res.resp_bytes) { outstanding->fetch_add(1); resp_blk = IOBuf::create_external_block(const_cast<uint8_t*>(res.resp), res.resp_bytes, [outstanding](void*) { outstanding->fetch_sub(1); }); }
         for (uint32_t k = 0; k < res.n_runs; k++) {
@@ -170,7 +173,7 @@ public:
         IOBuf::release_external_block(resp_blk);
         // the references point into the reply block and the read regions: both are reused next round, so the writes must be done
         // (KeepWrite runs to completion on the default executor; a caller-set executor must drain before the next Submit)
-        while (_outstanding.load(std::memory_order_acquire) != 0) sched_yield();
+        while (outstanding->load(std::memory_order_acquire) != 0) sched_yield();
         for (auto& pc : _pop) {                                                         // pop_front(consumed): the partial tail moves to the region's start
             Conn* c = pc.first; const uint32_t used = pc.second;
             if (used && used < c->fill) memmove(c->base, c->base + used, c->fill - used);
@@ -186,9 +189,9 @@ private:
     void Destroy() { for (b2_ctx* c : _ctx) b2_ctx_destroy(c); _ctx.clear(); if (_arena) { b2_block_free(_arena); _arena = nullptr; } }
     Options _opt; uint8_t* _arena = nullptr; size_t _arena_bytes = 0;
     std::vector<b2_ctx*> _ctx; std::vector<std::unique_ptr<Conn>> _conns; std::vector<std::vector<Conn*>> _groups;
-    std::vector<bool> _inflight; std::vector<std::vector<b2_run>> _runs; std::vector<std::vector<Conn*>> _live;
-    std::vector<struct iovec> _iov; std::vector<std::pair<Conn*, uint32_t>> _pop;
-    std::atomic<int> _outstanding{0}; Process _process = nullptr; ReplySink _sink;
+    std::vector<char> _inflight; std::vector<std::vector<b2_run>> _runs; std::vector<std::vector<Conn*>> _live;
+    std::vector<std::vector<struct iovec>> _iov; std::vector<std::vector<std::pair<Conn*, uint32_t>>> _pop;      // per group: groups may be driven by different threads
+    std::unique_ptr<std::atomic<int>[]> _outstanding; Process _process = nullptr; ReplySink _sink;
 };
 
 }  // namespace b2

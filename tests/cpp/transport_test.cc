@@ -4,9 +4,13 @@
 //                                   (modelled on test/brpc_socket_unittest.cpp's multi-threaded write tests)
 //   transport_test gpu              K connections over socketpairs, request streams fed in uneven chunks, pipelined rounds;
 //                                   every byte the clients read back == the oracle's response stream (tests may link the oracle)
-//   transport_test bench [mib] [rounds] [mode]   pre-filled read regions (the message-processing path without socket syscalls on
+//   transport_test bench [mib] [rounds] [input] [resp] [groups]   pre-filled read regions (the message-processing path without socket syscalls on
 //                                   the read side, like the reference arm), replies gathered by writev into /dev/null; one JSON line
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 #include <fcntl.h>
+#include <sched.h>
 #include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,6 +30,22 @@ extern "C" {
 typedef struct b2press_spec { const char* service; const char* method; uint32_t payload_bytes, attachment_bytes; int32_t payload_kind, checksum_type; uint64_t seed; } b2press_spec;
 size_t b2press_frame(const b2press_spec* s, uint64_t index, uint8_t* out, size_t cap);
 uint64_t b2press_fill_run(const b2press_spec* s, uint64_t* index, uint8_t* out, size_t run_bytes);
+}
+// run on (and first-touch pinned memory from) the CPUs next to the GPU: zero-copy PCIe reads that cross the socket interconnect lose most
+// of their rate (bench.py does the same through NVML)
+static void pin_to_gpu_numa(int device) {
+    char bus[32] = {0};
+    extern int cudaDeviceGetPCIBusId(char*, int, int) __attribute__((weak));
+    if (!cudaDeviceGetPCIBusId || cudaDeviceGetPCIBusId(bus, sizeof bus, device) != 0) return;
+    for (char* p = bus; *p; p++) if (*p >= 'A' && *p <= 'Z') *p = (char)(*p - 'A' + 'a');
+    char path[128]; snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = fopen(path, "r"); if (!f) return;
+    char list[512] = {0}; if (!fgets(list, sizeof list, f)) { fclose(f); return; } fclose(f);
+    cpu_set_t set; CPU_ZERO(&set); int n = 0;
+    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a, b; if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b; c++) { CPU_SET(c, &set); n++; } } else if (sscanf(tok, "%d", &a) == 1) { CPU_SET(a, &set); n++; }
+    }
+    if (n) sched_setaffinity(0, sizeof set, &set);
 }
 static double now_s() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + t.tv_nsec * 1e-9; }
 static void set_nonblock(int fd) { fcntl(fd, F_SETFL, fcntl(fd, F_GETFL) | O_NONBLOCK); }
@@ -139,13 +159,17 @@ static void test_transport_gpu(int input_mode, int resp_mode) {
     printf("transport ok (input=%d resp=%d): %d connections, %d messages in %d pipelined rounds, reply streams byte-identical to the oracle\n", input_mode, resp_mode, K, total, rounds);
 }
 
-static int bench(int run_mib, int rounds, int input_mode, int resp_mode) {
+static int bench(int run_mib, int rounds, int input_mode, int resp_mode, int groups) {
     const int K = 64;
+    pin_to_gpu_numa(0);
     b2::GpuTransport::Options o; memset(&o.ctx, 0, sizeof o.ctx);
     const uint32_t region = (uint32_t)run_mib << 20;
-    o.ctx.device = 0; o.ctx.max_batch_bytes = input_mode == B2_INPUT_PULL ? (uint32_t)(K / 3 + 1) * region + (1u << 20) : (uint32_t)K * region + (1u << 20) /* COPY moves the arena span that holds the group's regions */; o.ctx.max_msgs = (uint32_t)((uint64_t)(K / 3 + 1) * region / 1000 + 4096);
+    const uint32_t per_group = (uint32_t)(K + groups - 1) / groups;
+    o.ctx.device = 0;
+    o.ctx.max_batch_bytes = input_mode == B2_INPUT_PULL ? per_group * region + (1u << 20) : (uint32_t)K * region + (1u << 20) /* COPY moves the arena span that holds the group's regions */;
+    o.ctx.max_msgs = (uint32_t)((uint64_t)per_group * region / 1000 + 4096);
     o.ctx.max_runs = K; o.ctx.max_resp_bytes = o.ctx.max_batch_bytes + (64u << 20);
-    o.pipeline = 3; o.region_bytes = region; o.max_connections = K; o.input_mode = input_mode; o.resp_mode = resp_mode;
+    o.pipeline = (uint32_t)groups; o.region_bytes = region; o.max_connections = K; o.input_mode = input_mode; o.resp_mode = resp_mode;
     b2::GpuTransport tr(o);
     b2_method echo = { "example.EchoService", "EchoService", "Echo", "example.EchoRequest", B2_HANDLER_ECHO, 1, 0, 0 };
     CHECK(tr.AddMethod(echo) == 0);
@@ -160,32 +184,31 @@ static int bench(int run_mib, int rounds, int input_mode, int resp_mode) {
         uint64_t idx = ((uint64_t)s << 32);
         b2press_fill_run(&sp, &idx, fresh[s].data(), run_bytes);
     }
-    uint64_t out_bytes = 0, out_iov = 0;
-    tr.SetReplySink([&](b2::GpuTransport::Conn* c, const struct iovec* v, size_t n) {   // what KeepWrite does: <= 1024 references per writev
-        for (size_t i = 0; i < n; i += 1024) { const ssize_t w = writev(c->fd, v + i, (int)std::min<size_t>(1024, n - i)); if (w > 0) out_bytes += (uint64_t)w; }
-        out_iov += n;
+    std::vector<uint64_t> out_bytes(groups, 0), out_iov(groups, 0), msgs(groups, 0);
+    tr.SetReplySink([&](b2::GpuTransport::Conn* c, const struct iovec* v, size_t n) {   // what KeepWrite does: one writev per <= 1024 references
+        for (size_t i = 0; i < n; i += 1024) { const ssize_t w = writev(c->fd, v + i, (int)std::min<size_t>(1024, n - i)); if (w > 0) out_bytes[c->group] += (uint64_t)w; }
+        out_iov[c->group] += n;
     });
-    // every round a group's connections have a fresh run pending (the partial frame at the tail stays, as after a real read)
     auto refill = [&](uint32_t g) { for (int s = 0; s < K; s++) if (conns[s]->group == g) { conns[s]->fill = 0; tr.Feed(conns[s], fresh[s].data(), run_bytes); } };
-    uint64_t msgs = 0;
     // warm-up; it also tells where each connection's last complete frame ends: the timed rounds submit exactly that much, so nothing is
     // left to move to the region's front and the regions stay as they are (a real read would append behind the tail)
     std::vector<uint32_t> whole(K, 0);
-    for (uint32_t g = 0; g < 3; g++) { refill(g); CHECK(tr.Submit(g) > 0); CHECK(tr.Collect(g) > 0); }
+    for (int g = 0; g < groups; g++) { refill(g); CHECK(tr.Submit(g) > 0); CHECK(tr.Collect(g) > 0); }
     for (int s = 0; s < K; s++) { whole[s] = (uint32_t)run_bytes - conns[s]->fill; CHECK(whole[s] > run_bytes / 2 && !conns[s]->sock.Failed()); }
     auto arm = [&](uint32_t g) { for (int s = 0; s < K; s++) if (conns[s]->group == g) conns[s]->fill = whole[s]; };
-    for (uint32_t g = 0; g < 3; g++) { refill(g); arm(g); CHECK(tr.Submit(g) > 0); CHECK(tr.Collect(g) > 0); }
-    for (uint32_t g = 0; g < 3; g++) { arm(g); CHECK(tr.Submit(g) > 0); }
+    for (int g = 0; g < groups; g++) { refill(g); arm(g); CHECK(tr.Submit(g) > 0); CHECK(tr.Collect(g) > 0); }
+    // one host thread per group (each owns a context): submit, collect + deliver, again — the groups' transfers, kernels and host work overlap
     const double t0 = now_s();
-    for (int r = 0; r < rounds; r++) {
-        const uint32_t g = r % 3;
-        const int c = tr.Collect(g); CHECK(c > 0); msgs += (uint64_t)c;
-        if (r + 3 < rounds) { arm(g); CHECK(tr.Submit(g) > 0); }
-    }
+    std::vector<std::thread> th;
+    for (int g = 0; g < groups; g++) th.emplace_back([&, g]() {
+        for (int r = 0; r < rounds; r++) { arm(g); CHECK(tr.Submit(g) > 0); const int c = tr.Collect(g); CHECK(c > 0); msgs[g] += (uint64_t)c; }
+    });
+    for (auto& t : th) t.join();
     const double dt = now_s() - t0;
-    printf("{\"via\": \"b2::GpuTransport (C++)\", \"msgs_per_s\": %.1f, \"rounds\": %d, \"connections\": %d, \"run_mib\": %d, \"input_mode\": %d, \"resp_mode\": %d, "
-           "\"reply_bytes_written\": %llu, \"iovecs\": %llu, \"seconds\": %.4f}\n", msgs / dt, rounds, K, run_mib, input_mode, resp_mode,
-           (unsigned long long)out_bytes, (unsigned long long)out_iov, dt);
+    uint64_t tm = 0, tb = 0, ti = 0; for (int g = 0; g < groups; g++) { tm += msgs[g]; tb += out_bytes[g]; ti += out_iov[g]; }
+    printf("{\"via\": \"b2::GpuTransport (C++)\", \"msgs_per_s\": %.1f, \"rounds_per_group\": %d, \"groups_and_host_threads\": %d, \"connections\": %d, \"run_mib\": %d, \"input_mode\": %d, \"resp_mode\": %d, "
+           "\"reply_bytes_written\": %llu, \"iovecs\": %llu, \"seconds\": %.4f}\n", tm / dt, rounds, groups, K, run_mib, input_mode, resp_mode,
+           (unsigned long long)tb, (unsigned long long)ti, dt);
     close(devnull);
     return 0;
 }
@@ -195,6 +218,6 @@ int main(int argc, char** argv) {
     const std::string mode = argc > 1 ? argv[1] : "queue";
     if (mode == "queue") { test_write_queue(); return 0; }
     if (mode == "gpu") { test_transport_gpu(B2_INPUT_PULL, B2_RESP_BY_REF); test_transport_gpu(B2_INPUT_COPY, B2_RESP_COPY); test_transport_gpu(B2_INPUT_COPY, B2_RESP_BY_REF); return 0; }
-    if (mode == "bench") return bench(argc > 2 ? atoi(argv[2]) : 4, argc > 3 ? atoi(argv[3]) : 60, argc > 4 ? atoi(argv[4]) : B2_INPUT_PULL, argc > 5 ? atoi(argv[5]) : B2_RESP_BY_REF);
+    if (mode == "bench") return bench(argc > 2 ? atoi(argv[2]) : 4, argc > 3 ? atoi(argv[3]) : 20, argc > 4 ? atoi(argv[4]) : B2_INPUT_PULL, argc > 5 ? atoi(argv[5]) : B2_RESP_BY_REF, argc > 6 ? atoi(argv[6]) : 4);
     fprintf(stderr, "usage: transport_test queue|gpu|bench\n"); return 2;
 }
