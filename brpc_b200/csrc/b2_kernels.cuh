@@ -286,7 +286,7 @@ __device__ __forceinline__ void walk_tile_spec(const uint8_t* run, uint32_t len,
             const int idx = h0 == kMagicPRPC ? 1 : h0 == kMagicSTRM ? 2 : 0;
             const uint32_t body = __byte_perm(h1, 0, 0x0123), meta = __byte_perm(h2, 0, 0x0123);
             // (a preferred nshead handler is asked first and may claim these bytes: pf == 12 goes the generic way)
-            if (idx && pf != 12 && (uint64_t)body <= max_body && (uint64_t)(len - pos) >= 12ull + body && meta <= body) {
+            if (idx && ((mask >> idx) & 1u) && pf != 12 && (uint64_t)body <= max_body && (uint64_t)(len - pos) >= 12ull + body && meta <= body) {
                 s.err = B2_PARSE_OK; s.index = idx; s.pf = idx; s.frame_pos = pos; s.new_pos = pos + 12 + body; s.body = body; s.meta = meta; s.popped = false;
                 fast = true;
             }
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(128) k_tile_walk_pull(BatchPtrs B, DevConfig C
                 const uint32_t h0 = sh ? __funnelshift_r(w0, w1, sh) : w0, h1 = sh ? __funnelshift_r(w1, w2, sh) : w1, h2 = sh ? __funnelshift_r(w2, w3, sh) : w2;
                 idx = h0 == kMagicPRPC ? 1 : h0 == kMagicSTRM ? 2 : 0;
                 const uint32_t body = __byte_perm(h1, 0, 0x0123), meta = __byte_perm(h2, 0, 0x0123);
-                if (idx && pf != 12 && (uint64_t)body <= C.max_body_size && (uint64_t)(len - pos) >= 12ull + body && meta <= body) { fast = true; new_pos = pos + 12 + body; }
+                if (idx && ((C.proto_mask >> idx) & 1u) && pf != 12 && (uint64_t)body <= C.max_body_size && (uint64_t)(len - pos) >= 12ull + body && meta <= body) { fast = true; new_pos = pos + 12 + body; }
             }
             if (count == 0 && ((C.proto_mask >> 12) & 1u)) {          // unknown preferred index + an nshead handler that would claim the bytes: the resolver decides
                 int amb = 0;
