@@ -795,7 +795,7 @@ def main():
                 try:
                     for cx in ctxs:
                         cx.close()
-                    out = subprocess.run([tb, "bench", str(args.run_mib), "40", "1", "1", "4"], capture_output=True, text=True, timeout=120)
+                    out = subprocess.run([tb, "bench", str(args.run_mib), "40", "1", "1", "8"], capture_output=True, text=True, timeout=120)
                     line["e2e_messenger"] = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else {"error": (out.stderr or out.stdout)[-300:]}
                 except Exception as e:      # noqa: BLE001
                     line["e2e_messenger"] = {"error": repr(e)}

@@ -46,7 +46,7 @@ public:
     typedef void (*Process)(InputMessageBase* msg);
 
     explicit GpuTransport(const Options& o) : _opt(o) {
-        if (o.pipeline == 0 || o.pipeline > 8) throw std::runtime_error("GpuTransport: pipeline must be 1..8");
+        if (o.pipeline == 0 || o.pipeline > 16) throw std::runtime_error("GpuTransport: pipeline must be 1..16");
         const size_t arena = (size_t)o.region_bytes * o.max_connections;
         if (arena >= (1ull << 31)) throw std::runtime_error("GpuTransport: arena must stay below 2 GiB (32-bit batch offsets)");
         _arena = static_cast<uint8_t*>(b2_block_alloc(arena));

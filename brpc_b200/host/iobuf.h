@@ -130,6 +130,17 @@ public:
     static void release_external_block(Block* b) { if (b) b->dec_ref(); }
     void append_block_range(Block* b, uint32_t offset, uint32_t length) { BlockRef r; r.offset = offset; r.length = length; r.block = b; push_ref(r, true); }
 
+    // (IOBufAsZeroCopyOutputStream::Next) make the free tail of the last block part of the buffer — or start a fresh block — and
+    // return where it begins; *len = how many bytes were added
+    char* extend_tail(size_t* len) {
+        Block* b = nullptr;
+        if (!_refs.empty()) { BlockRef& r = _refs.back(); if (!r.block->user_deleter && !r.block->full() && r.offset + r.length == r.block->size && r.block->nshared.load() == 1) b = r.block; }
+        if (b) { BlockRef& r = _refs.back(); const size_t n = b->left_space(); char* p = b->data + b->size; b->size += (uint32_t)n; r.length += (uint32_t)n; _nbytes += n; *len = n; return p; }
+        b = create_block(); if (!b) return nullptr;
+        const size_t n = b->cap; b->size = (uint32_t)n; _refs.push_back(BlockRef{0, (uint32_t)n, b}); _nbytes += n; *len = n;
+        return b->data;
+    }
+
     size_t pop_front(size_t n) {
         const size_t saved = n < _nbytes ? n : _nbytes; n = saved;
         while (n) {
@@ -326,6 +337,104 @@ public:
 
 private:
     std::vector<Block*> _cached;
+};
+
+
+// ---- the adapters every function of the path reads / writes IOBufs through --------------------------------
+// IOBufAsZeroCopyInputStream / IOBufAsZeroCopyOutputStream (src/butil/iobuf.h:559-607, iobuf.cpp:1826-1875,1877-2011): the
+// google::protobuf::io::ZeroCopy{Input,Output}Stream contract (Next / BackUp / Skip / ByteCount) over block references — what
+// ParsePbFromIOBuf (protocol.cpp:202-239) and SerializeRpcHeaderAndMeta (baidu_rpc_protocol.cpp:83-103) hand to libprotobuf.
+// Here they are plain classes with the same members (protobuf is not linked in this repo).
+class IOBufAsZeroCopyInputStream {
+public:
+    explicit IOBufAsZeroCopyInputStream(const IOBuf& buf) : _ref_index(0), _add_offset(0), _byte_count(0), _buf(&buf) {}
+    bool Next(const void** data, int* size) {
+        const std::pair<const char*, size_t> b = _buf->backing_block((size_t)_ref_index);
+        if (b.first == nullptr) return false;
+        *data = b.first + _add_offset; *size = (int)(b.second - (size_t)_add_offset);
+        _byte_count += (int64_t)(b.second - (size_t)_add_offset);
+        ++_ref_index; _add_offset = 0;
+        return true;
+    }
+    void BackUp(int count) {                           // only right after a Next: `count` bytes of its block were not used
+        if (_ref_index > 0) {
+            const std::pair<const char*, size_t> b = _buf->backing_block((size_t)--_ref_index);
+            _add_offset = (int)b.second - count; _byte_count -= count;
+        }
+    }
+    bool Skip(int count) {
+        for (;;) {
+            const std::pair<const char*, size_t> b = _buf->backing_block((size_t)_ref_index);
+            if (b.first == nullptr) return count == 0;
+            const int left = (int)b.second - _add_offset;
+            if (count < left) { _add_offset += count; _byte_count += count; return true; }
+            count -= left; _byte_count += left; ++_ref_index; _add_offset = 0;
+            if (count == 0) return true;
+        }
+    }
+    int64_t ByteCount() const { return _byte_count; }
+private:
+    int _ref_index, _add_offset; int64_t _byte_count; const IOBuf* _buf;
+};
+
+class IOBufAsZeroCopyOutputStream {
+public:
+    explicit IOBufAsZeroCopyOutputStream(IOBuf* buf) : _buf(buf), _byte_count(0), _last(0) {}
+    // hands out the free tail of the buffer's last block (a fresh block when it is full); the bytes count as written until BackUp
+    bool Next(void** data, int* size) {
+        const size_t before = _buf->length();
+        char* p = _buf->extend_tail(&_last);
+        if (!p) return false;
+        *data = p; *size = (int)_last; _byte_count += (int64_t)(_buf->length() - before);
+        return true;
+    }
+    void BackUp(int count) {                           // `count' can be as long as ByteCount() (iobuf.h:597)
+        _buf->pop_back((size_t)count); _byte_count -= count;
+    }
+    int64_t ByteCount() const { return _byte_count; }
+private:
+    IOBuf* _buf; int64_t _byte_count; size_t _last;
+};
+
+// IOBufCutter (src/butil/iobuf.h:509-556, iobuf_inl.h:463-578): cuts from the front with the current block's span cached, the
+// fast way to parse many small fields off one buffer.
+class IOBufCutter {
+public:
+    explicit IOBufCutter(IOBuf* buf) : _buf(buf) {}
+    size_t cutn(IOBuf* out, size_t n) { return _buf->cutn(out, n); }
+    size_t cutn(std::string* out, size_t n) { return _buf->cutn(out, n); }
+    size_t cutn(void* out, size_t n) { return _buf->cutn(out, n); }
+    bool cut1(void* data) { return _buf->cutn(data, 1) == 1; }
+    size_t copy_to(void* data, size_t n) { return _buf->copy_to(data, n, 0); }
+    const void* fetch1() { const std::pair<const char*, size_t> b = _buf->backing_block(0); return b.first && b.second ? b.first : nullptr; }
+    size_t pop_front(size_t n) { return _buf->pop_front(n); }
+    size_t remaining_bytes() const { return _buf->length(); }
+private:
+    IOBuf* _buf;
+};
+
+// IOBufAppender (src/butil/iobuf.h:684-724): appends through a cached span of the tail block; buf() / move_to() give the bytes back.
+class IOBufAppender {
+public:
+    IOBufAppender() : _data(nullptr), _data_end(nullptr), _zc_stream(&_buf) {}
+    int append(const void* src, size_t n) {
+        const char* s = static_cast<const char*>(src);
+        while (n) {
+            if (_data == _data_end && add_block() != 0) return -1;
+            const size_t k = n < (size_t)(_data_end - _data) ? n : (size_t)(_data_end - _data);
+            memcpy(_data, s, k); _data += k; s += k; n -= k;
+        }
+        return 0;
+    }
+    int append(const std::string& s) { return append(s.data(), s.size()); }
+    int append_decimal(long d) { char tmp[24]; const int n = snprintf(tmp, sizeof tmp, "%ld", d); return append(tmp, (size_t)n); }
+    int push_back(char c) { if (_data == _data_end && add_block() != 0) return -1; *_data++ = c; return 0; }
+    IOBuf& buf() { shrink(); return _buf; }
+    void move_to(IOBuf& target) { IOBuf& b = buf(); target.clear(); target.swap(b); }
+private:
+    void shrink() { const size_t unused = (size_t)(_data_end - _data); if (unused) { _zc_stream.BackUp((int)unused); _data = _data_end = nullptr; } }
+    int add_block() { void* p = nullptr; int n = 0; if (!_zc_stream.Next(&p, &n)) return -1; _data = static_cast<char*>(p); _data_end = _data + n; return 0; }
+    char* _data; char* _data_end; IOBuf _buf; IOBufAsZeroCopyOutputStream _zc_stream;
 };
 
 // Forward byte iterator over an IOBuf that does not modify it (butil::IOBufBytesIterator, src/butil/iobuf.h:688-727) —

@@ -141,6 +141,53 @@ static void test_portal_and_fd() {
     printf("portal ok (readv into blocks, writev cuts, byte iterator)\n");
 }
 
+
+// IOBufAsZeroCopy{Input,Output}Stream, IOBufCutter, IOBufAppender (cases after test/iobuf_unittest.cpp:1240-1420 "as_zero_copy_*", "cutter", "appender")
+static void test_iobuf_adapters() {
+    using namespace b2;
+    std::string s(20000, 'x'); for (size_t i = 0; i < s.size(); i++) s[i] = (char)('A' + i % 53);
+    IOBuf b; b.append(s);
+    {   // input stream: blocks come out in order; BackUp returns the tail of the last block; Skip crosses blocks; ByteCount follows
+        IOBufAsZeroCopyInputStream in(b);
+        const void* d; int n; std::string got;
+        CHECK(in.Next(&d, &n) && n == 8160 && memcmp(d, s.data(), 8160) == 0 && in.ByteCount() == 8160);
+        in.BackUp(100); CHECK(in.ByteCount() == 8060);
+        CHECK(in.Next(&d, &n) && n == 100 && memcmp(d, s.data() + 8060, 100) == 0);
+        CHECK(in.Skip(8160 + 10) && in.ByteCount() == 8160 * 2 + 10);
+        CHECK(in.Next(&d, &n) && n == (int)(20000 - 8160 * 2 - 10) && memcmp(d, s.data() + 8160 * 2 + 10, (size_t)n) == 0);
+        CHECK(!in.Next(&d, &n) && in.ByteCount() == 20000 && !in.Skip(1) && in.Skip(0));
+        CHECK(b.length() == 20000);                                         // the source is never modified
+    }
+    {   // output stream: Next hands out block space, BackUp gives back what was not written; appending goes on where the stream stopped
+        IOBuf o; o.append("head:");
+        IOBufAsZeroCopyOutputStream out(&o);
+        void* d; int n; size_t written = 0;
+        while (written < 12000) { CHECK(out.Next(&d, &n) && n > 0); const size_t k = std::min((size_t)n, 12000 - written); memcpy(d, s.data() + written, k); written += k; if (k < (size_t)n) out.BackUp(n - (int)k); }
+        CHECK(out.ByteCount() == 12000 && o.length() == 12005 && o.to_string() == "head:" + s.substr(0, 12000));
+        o.append("|tail"); CHECK(o.to_string() == "head:" + s.substr(0, 12000) + "|tail");
+        IOBuf e; IOBufAsZeroCopyOutputStream eo(&e); CHECK(eo.Next(&d, &n)); eo.BackUp(n); CHECK(e.empty() && eo.ByteCount() == 0);
+    }
+    {   // cutter
+        IOBuf c(b); IOBufCutter cut(&c);
+        char ch; CHECK(cut.fetch1() && *(const char*)cut.fetch1() == s[0] && cut.cut1(&ch) && ch == s[0] && cut.remaining_bytes() == 19999);
+        char hdr[12]; CHECK(cut.copy_to(hdr, 12) == 12 && memcmp(hdr, s.data() + 1, 12) == 0 && cut.remaining_bytes() == 19999);
+        IOBuf meta; std::string str; CHECK(cut.cutn(&meta, 8200) == 8200 && cut.cutn(&str, 50) == 50 && cut.pop_front(49) == 49);
+        CHECK(meta.to_string() == s.substr(1, 8200) && str == s.substr(8201, 50) && cut.remaining_bytes() == 20000 - 1 - 8200 - 50 - 49);
+        char rest[16]; CHECK(cut.cutn(rest, 16) == 16 && memcmp(rest, s.data() + 8300, 16) == 0);
+        CHECK(cut.pop_front(1 << 30) == 20000 - 8316 && cut.remaining_bytes() == 0 && !cut.cut1(&ch) && cut.fetch1() == nullptr);
+    }
+    {   // appender
+        IOBufAppender ap; std::string want;
+        for (int i = 0; i < 9000; i++) { CHECK(ap.push_back((char)('a' + i % 26)) == 0); want.push_back((char)('a' + i % 26)); }
+        CHECK(ap.append("-mid-", 5) == 0 && ap.append_decimal(-1234567) == 0 && ap.append(s) == 0); want += "-mid--1234567" + s;
+        CHECK(ap.buf().length() == want.size() && ap.buf().to_string() == want);
+        CHECK(ap.push_back('!') == 0); want.push_back('!');                  // keeps appending after buf()
+        IOBuf target; target.append("old"); ap.move_to(target);
+        CHECK(target.to_string() == want && ap.buf().empty());
+    }
+    printf("adapters ok (zero-copy input/output streams, cutter, appender)\n");
+}
+
 static int g_host_msgs = 0;
 static void HostProcess(b2::InputMessageBase* base) {
     b2::MostCommonMessage* m = static_cast<b2::MostCommonMessage*>(base);
@@ -360,6 +407,7 @@ int main(int argc, char** argv) {
     const std::string mode = argc > 1 ? argv[1] : "cpu";
     test_iobuf();
     test_portal_and_fd();
+    test_iobuf_adapters();
     if (mode == "gpu") { test_messenger_gpu(); test_h2_messenger_gpu(); test_protocol_shim_gpu(); }
     return 0;
 }

@@ -32,7 +32,7 @@ def _build_transport():
     deps = [src] + [os.path.join(ROOT, "brpc_b200", "host", h) for h in ("iobuf.h", "input_messenger.h", "gpu_transport.h")]
     if os.path.exists(TBIN) and all(os.path.getmtime(TBIN) >= os.path.getmtime(d) for d in deps):
         return
-    subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-Wall", "-pthread", "-o", TBIN, src,
+    subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-Wall", "-pthread", "-o", TBIN, src, "-L/usr/local/cuda/lib64", "-lcudart",
                            "-L" + os.path.join(ROOT, "brpc_b200"), "-lb2rpc",
                            "-L" + os.path.join(ROOT, "brpc_b200", "tools"), "-lb2press",
                            "-L" + os.path.join(ROOT, "oracle"), "-loracle",
@@ -66,7 +66,7 @@ def test_iobuf_contract_cpp():
     _build()
     out = subprocess.run([BIN, "cpu"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
-    assert "iobuf ok" in out.stdout
+    assert "iobuf ok" in out.stdout and "adapters ok" in out.stdout
 
 
 @pytest.mark.gpu
