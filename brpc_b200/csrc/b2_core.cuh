@@ -74,6 +74,8 @@ constexpr uint32_t kMagicHULU = 0x554c5548u;   // "HULU"
 constexpr uint32_t kMagicSOFA = 0x41464f53u;   // "SOFA"
 constexpr uint32_t kMagicNshead = 0xfb709394u; // NSHEAD_MAGICNUM, src/brpc/nshead.h:27
 constexpr uint32_t kProtoMaskDefault = (1u << 1) | (1u << 2);
+constexpr uint32_t kProtoMaskDump = 1u << 31;      // the run is an rpc_dump file, not a socket: records are cut like SampleIterator::Pop
+B2_HD uint32_t run_mask(uint32_t ctx_mask, uint32_t run_flags) { return (run_flags & B2_RUN_RPC_DUMP) ? kProtoMaskDump : ctx_mask; }
 B2_HD uint32_t frame_header_len(int idx) { return idx == 4 ? 24u : idx == 12 ? 36u : 12u; }
 B2_HD uint64_t load_le64(const uint8_t* p) { return (uint64_t)load_le32(p) | ((uint64_t)load_le32(p + 4) << 32); }
 
@@ -144,6 +146,20 @@ B2_HD Step cut_input_message(const uint8_t* run, uint32_t len, uint32_t pos, int
                              uint32_t mask = kProtoMaskDefault) {
     Step s; s.err = B2_PARSE_ERROR_TRY_OTHERS; s.index = -1; s.pf = pf; s.frame_pos = pos; s.new_pos = pos;
     s.body = 0; s.meta = 0; s.popped = false;
+    if (mask & kProtoMaskDump) {
+        // SampleIterator::Pop (src/brpc/rpc_dump.cpp:322-361): records of a dump file carry the baidu_std header
+        // (RpcDumpContext::Serialize :237-258); anything malformed is a format error that ends the file — nothing is popped or retried
+        const uint32_t n = len - pos; const uint8_t* p = run + pos;
+        s.index = B2_PROTOCOL_BAIDU_STD;
+        if (n < 12) { s.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return s; }
+        if (load_le32(p) != kMagicPRPC) { s.err = B2_PARSE_ERROR_ABSOLUTELY_WRONG; return s; }
+        const uint32_t body = load_be32(p + 4), meta = load_be32(p + 8);
+        if ((uint64_t)body > max_body) { s.err = B2_PARSE_ERROR_ABSOLUTELY_WRONG; return s; }
+        if ((uint64_t)n < 12ull + body) { s.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA; return s; }
+        if (meta > body) { s.err = B2_PARSE_ERROR_ABSOLUTELY_WRONG; return s; }
+        s.err = B2_PARSE_OK; s.pf = B2_PROTOCOL_BAIDU_STD; s.new_pos = pos + 12 + body; s.body = body; s.meta = meta;
+        return s;
+    }
     const int pref = pf;
     if (pref >= 1 && pref <= 12 && ((mask >> pref) & 1u)) {
         int cur = pref;
@@ -480,6 +496,34 @@ B2_HD bool decode_echo_request(const uint8_t* p, uint32_t n, Span& msg) {
     return has;
 }
 
+// RpcDumpMeta (src/brpc/rpc_dump.proto:23-48), proto2, every field optional: what rpc_replay needs to re-issue a sampled request.
+struct DumpMetaOut { uint32_t has; Span service_name, method_name; int32_t compress_type, protocol_type, attachment_size; };
+enum { kDumpHasService = 1, kDumpHasMethod = 2, kDumpHasCompress = 4, kDumpHasProtocol = 8, kDumpHasAttachment = 16 };
+B2_HD bool decode_dump_meta(const uint8_t* p, uint32_t n, DumpMetaOut& o) {
+    Reader r; r.p = p; r.end = p + n;
+    o.has = 0; o.service_name.off = o.service_name.len = 0; o.method_name = o.service_name; o.compress_type = 0; o.protocol_type = 0; o.attachment_size = 0;
+    while (r.p < r.end) {
+        uint32_t tag;
+        if (!rd_tag(r, tag)) return false;
+        if (tag == 0 || (tag & 7) == 4 || (tag >> 3) == 0) return false;
+        const uint32_t fn = tag >> 3, wt = tag & 7;
+        uint64_t v; Span sp; bool handled = false;
+        if (wt == 2 && (fn == 1 || fn == 2 || (fn >= 7 && fn <= 9))) {
+            if (!rd_span(r, p, sp)) return false;
+            handled = true;
+            if (fn == 1) { o.service_name = sp; o.has |= kDumpHasService; } else if (fn == 2) { o.method_name = sp; o.has |= kDumpHasMethod; }
+        } else if (wt == 0 && fn >= 3 && fn <= 6) {
+            if (!rd_varint(r, v)) return false;
+            handled = true;
+            const int32_t e = (int32_t)(uint32_t)v;
+            if (fn == 4) { if (e >= 0 && e <= 4) { o.compress_type = e; o.has |= kDumpHasCompress; } }        // closed enums: unknown numbers stay unset
+            else if (fn == 5) { if (e >= 0 && e <= 27) { o.protocol_type = e; o.has |= kDumpHasProtocol; } }
+            else if (fn == 6) { o.attachment_size = e; o.has |= kDumpHasAttachment; }
+        }
+        if (!handled && !skip_field(r, tag, 100)) return false;
+    }
+    return true;
+}
 // ---------------------------------------------------------------------------
 // encoders
 B2_HD uint32_t varint_len(uint64_t v) {
@@ -502,6 +546,15 @@ B2_HD uint8_t* put_dec_i32(uint8_t* p, int32_t v) {    // printf("%d")
     return put_dec(p, (uint32_t)v);
 }
 B2_HD uint32_t dec_len_i32(int32_t v) { return v < 0 ? 1 + dec_len((uint32_t)(-(int64_t)v)) : dec_len((uint32_t)v); }
+
+// bytes of the RpcMeta PackRpcRequest builds when it REPLAYS a sampled request (baidu_rpc_protocol.cpp:1067-1075,1080,1106-1120): request{service_name,
+// method_name}, compress_type, correlation_id, [attachment_size], content_type — no checksum fields on this branch
+B2_HD uint32_t replay_meta_len(uint32_t svc_len, uint32_t mth_len, int32_t compress_type, int64_t correlation_id, uint32_t attached) {
+    const uint32_t rl = 1 + varint_len(svc_len) + svc_len + 1 + varint_len(mth_len) + mth_len;
+    uint32_t n = 1 + varint_len(rl) + rl + 1 + varint_len((uint64_t)(int64_t)compress_type) + 1 + varint_len((uint64_t)correlation_id);
+    if (attached) n += 1 + varint_len(attached);
+    return n + 2;
+}
 
 // CRC-32C Mask, src/butil/crc32c.h:38-47
 B2_HD uint32_t crc32c_mask(uint32_t crc) { return ((crc >> 15) | (crc << 17)) + 0xa282ead8u; }

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(128) k_tile_walk(BatchPtrs B, DevConfig C) {
     if (rec.entry != kNone) {
         // the frame offsets met on the way are kept: if k_resolve accepts the tile as is, k_frame_table only has to copy them
         EmitSpec e; e.out = B.tile_spec + (size_t)t * C.spec_k; e.run_off = run.offset; e.cap = C.spec_k;
-        walk_tile_spec(B.bytes + run.offset, run.length, rec.entry, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, rec, e, C.proto_mask);
+        walk_tile_spec(B.bytes + run.offset, run.length, rec.entry, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, rec, e, run_mask(C.proto_mask, run.flags));
     }
     B.tiles[t] = rec;
 }
@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(128) k_tile_walk_pull(BatchPtrs B, DevConfig C
     const uint32_t k = ti.z, len = ti.y;
     const uint8_t* run = B.bytes + ti.x;
     const bool client = ((ti.w >> 24) & B2_RUN_CLIENT) != 0;
+    const uint32_t pmask = run_mask(C.proto_mask, ti.w >> 24);
     const uint32_t tile_end = (k + 1) << C.tile_shift, cap = C.spec_k;
     uint32_t* spec = B.tile_spec + (size_t)t * cap;
     uint4* rows = B.rows + (size_t)t * cap * 8;
@@ -353,16 +354,16 @@ __global__ void __launch_bounds__(128) k_tile_walk_pull(BatchPtrs B, DevConfig C
                 const uint32_t h0 = sh ? __funnelshift_r(w0, w1, sh) : w0, h1 = sh ? __funnelshift_r(w1, w2, sh) : w1, h2 = sh ? __funnelshift_r(w2, w3, sh) : w2;
                 idx = h0 == kMagicPRPC ? 1 : h0 == kMagicSTRM ? 2 : 0;
                 const uint32_t body = __byte_perm(h1, 0, 0x0123), meta = __byte_perm(h2, 0, 0x0123);
-                if (idx && ((C.proto_mask >> idx) & 1u) && pf != 12 && (uint64_t)body <= C.max_body_size && (uint64_t)(len - pos) >= 12ull + body && meta <= body) { fast = true; new_pos = pos + 12 + body; }
+                if (idx && ((pmask >> idx) & 1u) && pf != 12 && (uint64_t)body <= C.max_body_size && (uint64_t)(len - pos) >= 12ull + body && meta <= body) { fast = true; new_pos = pos + 12 + body; }
             }
-            if (count == 0 && ((C.proto_mask >> 12) & 1u)) {          // unknown preferred index + an nshead handler that would claim the bytes: the resolver decides
+            if (count == 0 && ((pmask >> 12) & 1u)) {          // unknown preferred index + an nshead handler that would claim the bytes: the resolver decides
                 int amb = 0;
-                if (sub == 0) amb = nshead_claims(run, len, pos, C.max_body_size, C.proto_mask) ? 1 : 0;
+                if (sub == 0) amb = nshead_claims(run, len, pos, C.max_body_size, pmask) ? 1 : 0;
                 if (__shfl_sync(gmask, amb, l0)) { kind = kAmbig; break; }
             }
             if (!fast) {                                              // short tails, oversize bodies, meta > body, unknown bytes: the generic restatement
                 Step s; s.err = 0; s.index = 0; s.new_pos = 0; s.frame_pos = 0; s.popped = false;
-                if (sub == 0) s = cut_input_message(run, len, pos, pf, C.max_body_size, client, C.proto_mask);
+                if (sub == 0) s = cut_input_message(run, len, pos, pf, C.max_body_size, client, pmask);
                 err = __shfl_sync(gmask, s.err, l0); idx = __shfl_sync(gmask, s.index, l0); new_pos = __shfl_sync(gmask, s.new_pos, l0);
                 frame_pos = __shfl_sync(gmask, s.frame_pos, l0); popped = __shfl_sync(gmask, (int)s.popped, l0) != 0;
                 if (count == 0 && popped) { kind = kAmbig; break; }
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C, uint3
                 int pf = run.preferred_proto;
                 for (uint32_t j = k; j-- > 0;) if (live[j] && (cp[j] >> 4)) { pf = (int)(cp[j] & 15u); break; }
                 TileRec t; t.live = 0; t.pf_in = 0;
-                walk_tile<false>(base, len, pos, pf, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, t, NoEmit(), C.proto_mask);
+                walk_tile<false>(base, len, pos, pf, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, t, NoEmit(), run_mask(C.proto_mask, run.flags));
                 tiles[k].entry = t.entry; tiles[k].exit = t.exit; tiles[k].count = t.count; tiles[k].kind = t.kind | kKindRewalked; tiles[k].last_proto = t.last_proto;
                 cp[k] = (t.count << 4) | ((uint32_t)t.last_proto & 15u);
                 v = make_link(t, tiles, nt, C.tile_shift);
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C, uint3
         const int pf_true = s_carry_pf ? (int)s_carry_pf : run.preferred_proto;
         // the step that ends ProcessNewMessage's loop, with the true preferred index (never OK:
         // every tile walk stops only on a non-OK step or past the last tile, where no bytes remain)
-        const Step s = cut_input_message(base, len, pos, pf_true, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, C.proto_mask);
+        const Step s = cut_input_message(base, len, pos, pf_true, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, run_mask(C.proto_mask, run.flags));
         b2_run_status st;
         st.consumed = s.new_pos; st.parse_error = (uint32_t)s.err; st.n_msgs = s_carry_sum; st.first_msg = 0;
         st.preferred_proto = s.pf; st.reserved0 = 0; st.resp_off = 0; st.resp_bytes = 0;
@@ -580,7 +581,7 @@ __global__ void __launch_bounds__(256) k_frame_table(BatchPtrs B, DevConfig C) {
     TileRec tmp;
     EmitFrame e; e.out = B.frame_off + first; e.out_run = B.frame_run + first; e.run_off = run.offset; e.run_idx = r; e.cap_left = B.max_msgs - first;
     e.out_row = C.pull ? B.frame_row + first : nullptr;
-    walk_tile<false>(B.bytes + run.offset, run.length, rec.entry, rec.pf_in, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, tmp, e, C.proto_mask);
+    walk_tile<false>(B.bytes + run.offset, run.length, rec.entry, rec.pf_in, (k + 1) << C.tile_shift, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, tmp, e, run_mask(C.proto_mask, run.flags));
 }
 
 // --- k_decode: one thread per message ----------------------------------------
@@ -752,11 +753,48 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
     int proto = B2_PROTOCOL_BAIDU_STD;
     if (fo_raw >> 31) { const uint32_t mg = load_le32(srow); proto = mg == kMagicSTRM ? 2 : mg == kMagicHULU ? 3 : mg == kMagicSOFA ? 4 : 12; }
     const uint8_t* gframe = B.bytes + fo;
+    const uint32_t my_run = kFused ? run_idx : B.frame_run[i];
+    if (B.runs[my_run].flags & B2_RUN_RPC_DUMP) {
+        // a record of an rpc_dump file: RpcDumpMeta + the sampled request; a baidu_std sample becomes the request frame rpc_replay would send
+        // (the frame itself is written by pack_one: status B2_MSG_REPLAY)
+        b2_msg_desc d;
+        d.run_idx = my_run; d.frame_off = fo; d.body_size = load_be32(gframe + 4); d.meta_size = load_be32(gframe + 8);
+        d.correlation_id = 0; d.log_id = 0; d.attachment_size = 0; d.compress_type = 0; d.checksum_type = 0; d.error_code = 0;
+        d.has_bits = 0; d.protocol = 0; d.content_type = 0; d.method_idx = -1; d.status = B2_MSG_BAD_META; d.resp_off = 0; d.resp_len = 0;
+        MsgAux a; a.msg_off = a.msg_len = a.att_len = a.att_off = a.cks_off = a.cks_len = 0; a.svc_off = a.svc_len = a.mth_off = a.mth_len = 0; a.pad = 0; a.err_kind = kErrNone;
+        DumpMetaOut dm; uint32_t slot_len = 0;
+        if (decode_dump_meta(gframe + 12, d.meta_size, dm)) {
+            d.protocol = (uint8_t)dm.protocol_type; d.compress_type = dm.compress_type; d.attachment_size = dm.attachment_size; d.has_bits = (uint16_t)dm.has;
+            const uint32_t first = B.run_status[my_run].first_msg;
+            d.correlation_id = (long long)(B.runs[my_run].socket_id + (unsigned long long)(i - first));
+            if (dm.protocol_type != B2_PROTOCOL_BAIDU_STD) d.status = B2_MSG_UNSUPPORTED;           // rpc_replay sends it on another protocol's channel
+            else {
+                d.status = B2_MSG_REPLAY;
+                const uint32_t req = d.body_size - d.meta_size;
+                const uint32_t att = dm.attachment_size > 0 ? (uint32_t)dm.attachment_size : 0u;      // (rpc_replay.cpp:184-188)
+                a.svc_off = 12 + dm.service_name.off; a.svc_len = dm.service_name.len; a.mth_off = 12 + dm.method_name.off; a.mth_len = dm.method_name.len;
+                a.att_len = att; a.msg_len = req;
+                d.resp_len = 12 + replay_meta_len(a.svc_len, a.mth_len, dm.compress_type, d.correlation_id, att) + req;
+                slot_len = (d.resp_len + 15u) & ~15u;
+            }
+        }
+        B.msgs[i] = d;
+        if (kFused) {
+            out->fast = false; out->prefix = 0; out->rs = 0; out->slow = d.status == B2_MSG_REPLAY;
+            if (out->slow) { B.aux[i] = a; B.slot[i] = fused_overflow_slot(B, C, slot_len); }
+            return;
+        }
+        B.aux[i] = a; B.slot[i] = slot_len;
+        PackJob job; job.src_off = 0; job.bulk_len = 0; job.head_len = 0; job.pad = 0; job.fast = 0; job.slot_len = slot_len;
+        B.jobs[i] = job;
+        if (C.by_ref) B.refs[i] = make_uint4(0, 0, 0, 0);
+        return;
+    }
     if (proto > 2) {
         // hulu_pbrpc / sofa_pbrpc / nshead: framed on the device, processed by the host (ProcessHuluRequest ... stay there): the descriptor
         // carries protocol, frame_off, meta_size and body_size (the bytes behind the 12 / 24 / 36-byte header)
         b2_msg_desc d;
-        d.run_idx = kFused ? run_idx : B.frame_run[i]; d.frame_off = fo;
+        d.run_idx = my_run; d.frame_off = fo;
         if (proto == 3) { d.body_size = load_le32(srow + 4); d.meta_size = load_le32(srow + 8); }
         else if (proto == 4) { d.meta_size = load_le32(srow + 4); d.body_size = load_le32(srow + 16); }
         else { d.meta_size = 0; d.body_size = load_le32(srow + 32); }
@@ -1597,6 +1635,27 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
     if (d.resp_len == 0) { if (lane == 0 && d.status != B2_MSG_RESPONSE) B.msgs[i].resp_off = slot_off; return; }
     const MsgAux a = B.aux[i];
     const uint8_t* frame = B.bytes + d.frame_off;
+    if (d.status == B2_MSG_REPLAY) {
+        // PackRpcRequest replaying a sampled request (baidu_rpc_protocol.cpp:1067-1075 + :1080-1131): header, RpcMeta{request{service_name,
+        // method_name}, compress_type, correlation_id, [attachment_size], content_type}, then the sampled bytes (body + attachment) as they were
+        uint8_t* out = B.resp + slot_off;
+        const uint32_t ml = replay_meta_len(a.svc_len, a.mth_len, d.compress_type, d.correlation_id, a.att_len);
+        if (lane == 0) {
+            uint8_t* p = out;
+            p[0] = 'P'; p[1] = 'R'; p[2] = 'P'; p[3] = 'C'; put_be32(p + 4, ml + a.msg_len); put_be32(p + 8, ml); p += 12;
+            const uint32_t rl = 1 + varint_len(a.svc_len) + a.svc_len + 1 + varint_len(a.mth_len) + a.mth_len;
+            *p++ = 0x0a; p = put_varint(p, rl);
+            *p++ = 0x0a; p = put_varint(p, a.svc_len); for (uint32_t k = 0; k < a.svc_len; k++) *p++ = frame[a.svc_off + k];
+            *p++ = 0x12; p = put_varint(p, a.mth_len); for (uint32_t k = 0; k < a.mth_len; k++) *p++ = frame[a.mth_off + k];
+            *p++ = 0x18; p = put_varint(p, (uint64_t)(long long)d.compress_type);
+            *p++ = 0x20; p = put_varint(p, (uint64_t)d.correlation_id);
+            if (a.att_len) { *p++ = 0x28; p = put_varint(p, a.att_len); }
+            *p++ = 0x50; *p++ = 0x00;
+            B.msgs[i].resp_off = slot_off;
+        }
+        warp_copy(out + 12 + ml, frame + 12 + d.meta_size, a.msg_len, lane);
+        return;
+    }
     if (d.status == B2_MSG_STREAM_FRAME) {
         // the application-level SnappyDecompress of a streaming DATA frame's payload
         uint32_t produced = 0;
@@ -2050,7 +2109,7 @@ __global__ void __maxnreg__(B2_FUSED_REGS) k_fused(BatchPtrs B, DevConfig C) {
         if (!rec.live || count == 0) continue;
         const uint4 ti = ti_cur;
         const uint32_t r = ti.w & 0xffffffu, run_off = ti.x, run_len = ti.y;
-        const bool client = ((ti.w >> 24) & B2_RUN_CLIENT) != 0;
+        const bool client = ((ti.w >> 24) & B2_RUN_CLIENT) != 0, dump = ((ti.w >> 24) & B2_RUN_RPC_DUMP) != 0;
         const uint32_t first = B.run_status[r].first_msg + tbase_cur;
         const uint32_t hi = run_off + rec.exit;
         const bool spec_ok = !(rec.kind & kKindRewalked) && count <= C.spec_k;
@@ -2066,7 +2125,7 @@ __global__ void __maxnreg__(B2_FUSED_REGS) k_fused(BatchPtrs B, DevConfig C) {
             } else {
                 if (lane == 0) {                                        // a tile k_resolve re-walked (or a dense one): the chain again, true preferred index
                     for (uint32_t k = 0; k < cnt; k++) {
-                        const Step sp = cut_input_message(B.bytes + run_off, run_len, wpos, wpf, C.max_body_size, client, C.proto_mask);
+                        const Step sp = cut_input_message(B.bytes + run_off, run_len, wpos, wpf, C.max_body_size, client, run_mask(C.proto_mask, ti.w >> 24));
                         S.foff[k] = (run_off + sp.frame_pos) | ((uint32_t)(sp.index != 1) << 31);
                         wpos = sp.new_pos; wpf = sp.pf;
                     }
@@ -2089,7 +2148,7 @@ __global__ void __maxnreg__(B2_FUSED_REGS) k_fused(BatchPtrs B, DevConfig C) {
                 bool in_place = false;
                 if (lane < cnt && i < B.max_msgs) {
                     uint8_t* f = S.buf + (fo - lo16);
-                    in_place = !client && !(fo_raw >> 31) && fused_fast_echo(B, ms, C.n_methods, i, fo, r, f, hi16 - fo, nullptr, o);
+                    in_place = !client && !dump && !(fo_raw >> 31) && fused_fast_echo(B, ms, C.n_methods, i, fo, r, f, hi16 - fo, nullptr, o);
                     if (!in_place) decode_one<true>(B, C, i, fo_raw, f, B.heads + (size_t)i * kHeadBytes, 0xffffffffu, r, &o);
                 }
                 if (in_place) o.prefix = 0;                                 // (already written where it belongs)
@@ -2112,7 +2171,7 @@ __global__ void __maxnreg__(B2_FUSED_REGS) k_fused(BatchPtrs B, DevConfig C) {
                 __syncwarp();
                 if (lane < cnt && i < B.max_msgs) {
                     uint8_t* f = S.buf + lane * kFusedRowStride + (fo & 15u);
-                    if (client || (fo_raw >> 31) || !fused_fast_echo(B, ms, C.n_methods, i, fo, r, f, kRowBytes - (fo & 15u), B.heads + (size_t)i * kHeadBytes, o))
+                    if (client || dump || (fo_raw >> 31) || !fused_fast_echo(B, ms, C.n_methods, i, fo, r, f, kRowBytes - (fo & 15u), B.heads + (size_t)i * kHeadBytes, o))
                         decode_one<true>(B, C, i, fo_raw, f, B.heads + (size_t)i * kHeadBytes, kRowBytes, r, &o);
                 }
                 __syncwarp();
@@ -2343,7 +2402,7 @@ __device__ __forceinline__ void small_body(const BatchPtrs& B, const DevConfig& 
         run = B.runs[tid];
         uint32_t pos = 0; int pf = run.preferred_proto;
         for (;;) {
-            const Step sp = cut_input_message(B.bytes + run.offset, run.length, pos, pf, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, C.proto_mask);
+            const Step sp = cut_input_message(B.bytes + run.offset, run.length, pos, pf, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, run_mask(C.proto_mask, run.flags));
             pos = sp.new_pos; pf = sp.pf;
             if (sp.err != B2_PARSE_OK) { st.parse_error = (uint32_t)sp.err; break; }
             my_count++;
@@ -2360,7 +2419,7 @@ __device__ __forceinline__ void small_body(const BatchPtrs& B, const DevConfig& 
         st.first_msg = first;
         uint32_t pos = 0, k = 0; int pf = run.preferred_proto;
         for (;;) {
-            const Step sp = cut_input_message(B.bytes + run.offset, run.length, pos, pf, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, C.proto_mask);
+            const Step sp = cut_input_message(B.bytes + run.offset, run.length, pos, pf, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, run_mask(C.proto_mask, run.flags));
             if (sp.err != B2_PARSE_OK) break;
             B.frame_off[first + k] = (run.offset + sp.frame_pos) | ((uint32_t)(sp.index != 1) << 31);
             B.frame_run[first + k] = tid; if (C.pull) B.frame_row[first + k] = kNone; k++;

@@ -84,6 +84,9 @@ extern "C" {
                                    would get (0 = OK); resp_off/resp_len = the EchoResponse.message bytes,
                                    located in the BATCH buffer */
 #define B2_MSG_RESPONSE_UNZ  8  /* same, the response was snappy-compressed: message bytes are in the resp region */
+#define B2_MSG_REPLAY       10  /* a record of an rpc_dump file (B2_RUN_RPC_DUMP) re-packed as a baidu_std request frame: resp_off/resp_len;
+                                   compress_type / attachment_size = the sample's; protocol = the sample's protocol_type (only baidu_std
+                                   samples are re-packed, others are B2_MSG_UNSUPPORTED) */
 #define B2_MSG_FRAMED        9  /* a message of another length-prefixed protocol (hulu_pbrpc, sofa_pbrpc, nshead): cut by the
                                    device, processed by the host; protocol / frame_off / meta_size / body_size are set, body_size
                                    counts the bytes behind the 12- (hulu), 24- (sofa) or 36-byte (nshead) header */
@@ -125,6 +128,10 @@ typedef struct b2_run {
     int32_t  preferred_proto;  /* Socket::preferred_index(): B2_PROTOCOL_* or -1 */
     uint32_t flags;            /* B2_RUN_* */
 } b2_run;                      /* 24 bytes */
+#define B2_RUN_RPC_DUMP 4u     /* the run is not a socket but an rpc_dump FILE (src/brpc/rpc_dump.cpp:237-258: records "PRPC" BE32(meta+request) BE32(meta)
+                                  RpcDumpMeta request): records are cut like SampleIterator::Pop (:322-361) and every baidu_std sample is turned into the
+                                  request frame rpc_replay would send (PackRpcRequest's replay branch, baidu_rpc_protocol.cpp:1067-1075): status
+                                  B2_MSG_REPLAY, the frame in the resp region, correlation_id = socket_id + index of the record in the run */
 #define B2_RUN_CLIENT 1u       /* Socket::CreatedByConnect(): client-side protocol rules of CutInputMessage
                                   (input_messenger.cpp:122-138) and ProcessRpcResponse instead of ProcessRpcRequest */
 

@@ -805,6 +805,67 @@ static void process_stream_frame(const orc_config* cfg, const uint8_t* frame, b2
     }
 }
 
+
+/* ---- rpc_dump replay source --------------------------------------------------------------------------
+ * A dump file is a sequence of records "PRPC" BE32(meta+request) BE32(meta) RpcDumpMeta request (RpcDumpContext::Serialize,
+ * src/brpc/rpc_dump.cpp:237-258), read back by SampleIterator::Pop (:322-361).  rpc_replay (tools/rpc_replay/rpc_replay.cpp:148-200) sends
+ * every sample through a Channel of its protocol_type with cntl->reset_sampled_request(sample); for baidu_std PackRpcRequest then takes the
+ * replay branch (baidu_rpc_protocol.cpp:1067-1075): service/method names from the sample, compress_type from the sample when it has one,
+ * no checksum fields; the request bytes are the sample's (the last attachment_size bytes travel as the attachment). */
+typedef struct { uint32_t has; orc_span service_name, method_name; int32_t compress_type, protocol_type, attachment_size; } dump_meta_t;
+static int parse_dump_meta(const uint8_t* p, size_t n, dump_meta_t* o) {      /* rpc_dump.proto:23-48, all optional */
+    rd_t r = { p, p + n };
+    memset(o, 0, sizeof *o);
+    while (r.p < r.end) {
+        uint32_t tag;
+        if (!rd_tag(&r, &tag)) return 0;
+        if (tag == 0 || (tag & 7) == 4 || (tag >> 3) == 0) return 0;
+        uint32_t fn = tag >> 3, wt = tag & 7; uint64_t v; int handled = 0;
+        if (wt == 2 && (fn == 1 || fn == 2 || (fn >= 7 && fn <= 9))) {
+            uint32_t len;
+            if (!rd_size(&r, &len)) return 0;
+            if (fn == 1) { o->service_name.off = (uint32_t)(r.p - p); o->service_name.len = len; o->has |= 1; }
+            else if (fn == 2) { o->method_name.off = (uint32_t)(r.p - p); o->method_name.len = len; o->has |= 2; }
+            r.p += len; handled = 1;
+        } else if (wt == 0 && fn >= 3 && fn <= 6) {
+            if (!rd_varint(&r, &v)) return 0;
+            int32_t e = (int32_t)(uint32_t)v; handled = 1;
+            if (fn == 4) { if (e >= 0 && e <= 4) { o->compress_type = e; o->has |= 4; } }          /* closed enum CompressType, options.proto:69-75 */
+            else if (fn == 5) { if (e >= 0 && e <= 27) { o->protocol_type = e; o->has |= 8; } }      /* closed enum ProtocolType, :38-67 */
+            else if (fn == 6) { o->attachment_size = e; o->has |= 16; }
+        }
+        if (!handled && !skip_field(&r, tag, 100)) return 0;
+    }
+    return 1;
+}
+static int process_dump_record(const uint8_t* frame, b2_msg_desc* d, int64_t correlation_id, uint8_t* resp, size_t resp_cap, size_t* resp_len) {
+    dump_meta_t m;
+    *resp_len = 0; d->method_idx = -1;
+    if (!parse_dump_meta(frame + 12, d->meta_size, &m)) { d->status = B2_MSG_BAD_META; return 0; }     /* "Fail to parse RpcDumpMeta": format error */
+    d->protocol = (uint8_t)m.protocol_type; d->compress_type = m.compress_type; d->attachment_size = m.attachment_size; d->has_bits = (uint16_t)m.has;
+    d->correlation_id = correlation_id;
+    if (m.protocol_type != B2_PROTOCOL_BAIDU_STD) { d->status = B2_MSG_UNSUPPORTED; return 0; }
+    const uint32_t req = d->body_size - d->meta_size;
+    const uint32_t att = m.attachment_size > 0 ? (uint32_t)m.attachment_size : 0;
+    uint8_t rq[1200]; wr_t rw = { rq, rq + sizeof rq, 0 };
+    wr_len(&rw, 1, frame + 12 + m.service_name.off, m.service_name.len);
+    wr_len(&rw, 2, frame + 12 + m.method_name.off, m.method_name.len);
+    uint8_t meta[1400]; wr_t mw = { meta, meta + sizeof meta, 0 };
+    wr_len(&mw, 1, rq, (size_t)(rw.p - rq));
+    wr_i32(&mw, 3, m.compress_type);
+    wr_i64(&mw, 4, correlation_id);
+    if (att) wr_i32(&mw, 5, (int32_t)att);
+    wr_i32(&mw, 10, 0);
+    if (rw.ovf || mw.ovf) { d->status = B2_MSG_UNSUPPORTED; return 0; }
+    uint32_t ml = (uint32_t)(mw.p - meta);
+    wr_t w = { resp, resp + resp_cap, 0 };
+    pack_header(&w, "PRPC", ml, req);
+    wr_raw(&w, meta, ml); wr_raw(&w, frame + 12 + d->meta_size, req);
+    if (w.ovf) return -1;
+    d->status = B2_MSG_REPLAY; *resp_len = (size_t)(w.p - resp);
+    return 0;
+}
+
 /* InputMessenger::ProcessNewMessage, input_messenger.cpp:206-322, per run. */
 int orc_process_batch(const orc_config* cfg, const uint8_t* bytes, uint32_t nbytes,
                       const b2_run* runs, uint32_t n_runs, b2_run_status* rs,
@@ -823,7 +884,21 @@ int orc_process_batch(const orc_config* cfg, const uint8_t* bytes, uint32_t nbyt
         for (;;) {
             uint32_t before = pos;
             const int client = (runs[r].flags & B2_RUN_CLIENT) != 0;
-            cut_t c = cut_input_message(run, len, &pos, &preferred, &index, max_body, client, mask);
+            cut_t c;
+            if (runs[r].flags & B2_RUN_RPC_DUMP) {          /* SampleIterator::Pop: baidu_std header, malformed = format error, nothing popped */
+                memset(&c, 0, sizeof c); index = B2_PROTOCOL_BAIDU_STD;
+                const uint32_t n = len - pos; const uint8_t* p = run + pos;
+                if (n < 12) c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA;
+                else if (memcmp(p, "PRPC", 4) != 0) c.err = B2_PARSE_ERROR_ABSOLUTELY_WRONG;
+                else {
+                    uint32_t body = ((uint32_t)p[4] << 24) | ((uint32_t)p[5] << 16) | ((uint32_t)p[6] << 8) | p[7];
+                    uint32_t meta = ((uint32_t)p[8] << 24) | ((uint32_t)p[9] << 16) | ((uint32_t)p[10] << 8) | p[11];
+                    if ((uint64_t)body > max_body) c.err = B2_PARSE_ERROR_ABSOLUTELY_WRONG;
+                    else if ((uint64_t)n < 12ull + body) c.err = B2_PARSE_ERROR_NOT_ENOUGH_DATA;
+                    else if (meta > body) c.err = B2_PARSE_ERROR_ABSOLUTELY_WRONG;
+                    else { c.err = B2_PARSE_OK; c.pop = 12 + body; c.body_size = body; c.meta_size = meta; pos += c.pop; preferred = B2_PROTOCOL_BAIDU_STD; }
+                }
+            } else c = cut_input_message(run, len, &pos, &preferred, &index, max_body, client, mask);
             if (c.err != B2_PARSE_OK) { rs[r].parse_error = (uint32_t)c.err; break; }
             if (nm >= msg_cap) return -1;
             b2_msg_desc* d = &msgs[nm];
@@ -832,7 +907,11 @@ int orc_process_batch(const orc_config* cfg, const uint8_t* bytes, uint32_t nbyt
             d->body_size = c.body_size; d->meta_size = c.meta_size; d->protocol = (uint8_t)index;
             (void)before;
             size_t rl = 0;
-            if (index == B2_PROTOCOL_BAIDU_STD && client) {
+            if (runs[r].flags & B2_RUN_RPC_DUMP) {
+                d->protocol = 0;
+                if (process_dump_record(bytes + d->frame_off, d, (int64_t)(runs[r].socket_id + rs[r].n_msgs), resp + rb, resp_cap - rb, &rl) != 0) return -1;
+                d->resp_off = (uint32_t)rb; d->resp_len = (uint32_t)rl;
+            } else if (index == B2_PROTOCOL_BAIDU_STD && client) {
                 if (process_rpc_response(bytes + d->frame_off, d, resp + rb, resp_cap - rb, &rl) != 0) return -1;
                 if (d->status == B2_MSG_RESPONSE_UNZ) d->resp_off += (uint32_t)rb;       /* message inside the decompressed bytes */
             } else if (index == B2_PROTOCOL_BAIDU_STD) {
