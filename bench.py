@@ -687,8 +687,8 @@ def main():
             assert refs is not None and np.all(refs["src_len"] + refs["prefix_len"] == m3["resp_len"])
         d2h = int(len(m3) * 64 + len(r3) * 32 + int(r3["resp_bytes"].sum()) + (16 * len(m3) if rm else 0))
         meta = int(runs.nbytes + 4 * (len(runs) + 1) + 16 * info_["n_tiles"])
-        # pull: each message's stashed row is one 128-byte PCIe read; every tile's speculative entry scan reads two 512-byte windows
-        h2d = meta + (int(128 * len(m3) + 1024 * info_["n_tiles"]) if im else int(nbytes))
+        # pull: each message's stashed row is one 96-byte (by-ref; else 128-byte) PCIe read; every tile's speculative entry scan reads two 512-byte windows
+        h2d = meta + (int((96 if rm else 128) * len(m3) + 1024 * info_["n_tiles"]) if im else int(nbytes))
         return {"ms_per_step": ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_steps, "tile_bytes": info_["tile_bytes"]}
 
     e2e_modes = {"copy": e2e_mode(0, 0, 0.4), "copy_by_ref": e2e_mode(0, 1, 0.4), "pull_by_ref": e2e_mode(1, 1, 0.6)}
@@ -720,20 +720,29 @@ def main():
         assert len(lm) == N_SOCKETS and np.all(lm["status"] == 0)
         lat_ctx.latency_probe(lbuf.ptr, N_SOCKETS * stride, lruns, 200, False)
         blk = np.sort(lat_ctx.latency_probe(lbuf.ptr, N_SOCKETS * stride, lruns, 3000, False))
-        lat_ctx.ring_start()
-        lat_ctx.latency_probe(lbuf.ptr, N_SOCKETS * stride, lruns, 200, True)
-        r0 = lat_ctx.ring_launches()
-        rng_ = np.sort(lat_ctx.latency_probe(lbuf.ptr, N_SOCKETS * stride, lruns, 5000, True))
-        ring_launches = lat_ctx.ring_launches() - r0
-        t_ = lat_ctx.ring_submit(None, lruns, ptr=lbuf.ptr, nbytes=N_SOCKETS * stride)
-        qrs, qm, qresp, _q = lat_ctx.ring_wait(t_)
-        assert len(qm) == N_SOCKETS and np.all(qm["status"] == 0) and np.array_equal(qm["resp_len"], lm["resp_len"])
-        lat_ctx.ring_stop()
         pc = lambda v, q: float(v[min(len(v) - 1, int(len(v) * q))])
+        ring = {}
+        for label, rm in (("by_ref", 1), ("copy", 0)):
+            lat_ctx.set_modes(0, rm)
+            lat_ctx.ring_start()
+            lat_ctx.latency_probe(lbuf.ptr, N_SOCKETS * stride, lruns, 200, True)
+            r0 = lat_ctx.ring_launches()
+            us = np.sort(lat_ctx.latency_probe(lbuf.ptr, N_SOCKETS * stride, lruns, 5000, True))
+            launches = lat_ctx.ring_launches() - r0
+            t_ = lat_ctx.ring_submit(None, lruns, ptr=lbuf.ptr, nbytes=N_SOCKETS * stride)
+            qrs, qm, qresp, qi = lat_ctx.ring_wait(t_)
+            assert len(qm) == N_SOCKETS and np.all(qm["status"] == 0) and np.array_equal(qm["resp_len"], lm["resp_len"])
+            if rm:
+                assert qi["refs"] is not None and np.all(qi["refs"]["src_len"] == PAYLOAD)
+            ring[label] = {"p50_us": pc(us, .5), "p99_us": pc(us, .99), "mean_us": float(us.mean()), "iters": len(us), "kernel_launches_per_batch": launches / float(len(us)),
+                           "device_phase_ns": dict(zip(["header_read", "bytes_pulled", "body_done", "results_pushed"], lat_ctx.ring_phase_ns(t_)))}
+            lat_ctx.ring_stop()
+        lat_ctx.set_modes(0, 0)
         latency = {"batch": "%d connections x 1 request (1 KB), pinned host buffers, timed inside the library" % N_SOCKETS,
-                   "path": "persistent kernel + submit ring (b2_ring_submit / b2_ring_wait)",
-                   "p50_us": pc(rng_, .5), "p99_us": pc(rng_, .99), "mean_us": float(rng_.mean()), "iters": len(rng_),
-                   "kernel_launches_per_batch": ring_launches / float(len(rng_)),
+                   "path": "persistent kernel + submit ring (b2_ring_submit / b2_ring_wait)", "mode": "replies by reference (B2_RESP_BY_REF)",
+                   "p50_us": ring["by_ref"]["p50_us"], "p99_us": ring["by_ref"]["p99_us"], "mean_us": ring["by_ref"]["mean_us"], "iters": ring["by_ref"]["iters"],
+                   "kernel_launches_per_batch": ring["by_ref"]["kernel_launches_per_batch"], "device_phase_ns": ring["by_ref"]["device_phase_ns"],
+                   "ring_copy_replies": ring["copy"],
                    "blocking_call": {"p50_us": pc(blk, .5), "p99_us": pc(blk, .99), "kernel_launches_per_batch": int(_i["n_launches"]), "iters": len(blk)}}
 
     # ---- reduce over ranks: max time, summed messages; NCCL all-reduce of the bvar-like counters --
@@ -769,7 +778,7 @@ def main():
         e2e = mk_e2e(e_pull, e2e_modes["pull_by_ref"])
         e2e["mode"] = "pull_by_ref"
         e2e["note"] = ("b2_batch_submit/collect (the two halves of b2_process_batch) on pinned host blocks, 3 batches in flight, B2_INPUT_PULL + "
-                       "B2_RESP_BY_REF: the kernels read the pinned request blocks in place (h2d = one 128-byte row per message + the scan windows "
+                       "B2_RESP_BY_REF: the kernels read the pinned request blocks in place (h2d = one 96-byte row per message + the scan windows "
                        "+ run/tile records, counted from the access pattern), replies come back as prefix + reference; e2e_modes holds the copy variants")
         line = {"metric": "echo QPS, 1 KB baidu_std", "value": value, "unit": "msgs/s", "n_gpus": world if use_dist else 1,
                 "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

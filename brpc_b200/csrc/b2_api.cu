@@ -277,7 +277,7 @@ extern "C" int b2_set_modes(b2_ctx* c, int input_mode, int resp_mode) {
         }
     }
     ring_halt(c);
-    c->input_mode = input_mode; c->resp_mode = resp_mode; c->cfg.by_ref = resp_mode == B2_RESP_BY_REF; c->cfg.pull = input_mode == B2_INPUT_PULL;
+    c->input_mode = input_mode; c->resp_mode = resp_mode; c->cfg.by_ref = resp_mode == B2_RESP_BY_REF; c->cfg.pull = input_mode == B2_INPUT_PULL; c->cfg.pull_vecs = resp_mode == B2_RESP_BY_REF ? 6u : 8u;
     c->uploaded = false; c->executed = false;
     return B2_OK;
 }
@@ -464,8 +464,11 @@ static int launch_pipeline(b2_ctx* c) {
     if (fused) {
         if (mask & 4) { k_pack_slow<true><<<sms * B2_SLOW_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack_slow"); }
     } else if (c->use_tma_pack) {
-        // k_pack_slow first: its verify pass decides which CRC-carrying echoes k_pack_tma may move
-        if (mask & 4) { k_pack_slow<false><<<sms * B2_SLOW_MIN_BLOCKS, 256, 8 * kSnapRing, s>>>(B, C); launches++; mark("pack_slow"); }
+        // the verify pass decides which CRC-carrying echoes k_pack_tma may move; k_pack_slow answers the ones that fail
+        if (mask & 4) {
+            if (c->slow_heavy || c->cfg.by_ref) { C.verify_done = 1; k_crc_verify<<<sms * 6, 256, 0, s>>>(B, C); launches++; mark("crc_verify"); }
+            k_pack_slow<false><<<sms * B2_SLOW_MIN_BLOCKS, 256, 8 * kSnapRing, s>>>(B, C); launches++; mark("pack_slow");
+        }
         if (mask & 2) {
             // small requests: 32 messages per warp round instead of 8 (measured +30 % at 64 B payloads, -3 % at 1 KB)
             if ((c->avg_frame && c->avg_frame < 640) || c->cfg.by_ref) k_pack_tma<kPackGroupSmall><<<sms, kPackWarps * 32, sizeof(PackWarpSmem) * kPackWarps, s>>>(B, C);
@@ -755,6 +758,13 @@ extern "C" int b2_ring_wait(b2_ctx* c, uint32_t ticket, b2_batch_result* out) {
     return B2_OK;
 }
 extern "C" uint64_t b2_ring_launches(b2_ctx* c) { return c ? c->ring_launches : 0; }
+// device-side phase times of a collected ticket, ns since the kernel saw the doorbell: [0] header read [1] runs + bytes pulled [2] cut / decode / pack done [3] results pushed
+extern "C" int b2_ring_phase_ns(b2_ctx* c, uint32_t ticket, uint64_t out[4]) {
+    if (!c || !c->ring_slots || !out) return B2_E_INVAL;
+    const RingSlotHdr* h = reinterpret_cast<const RingSlotHdr*>(c->ring_slots + (size_t)(ticket % kRingSlots) * c->ring_stride);
+    for (int k = 0; k < 4; k++) out[k] = h->stamps[k + 1] - h->stamps[0];
+    return B2_OK;
+}
 
 // measurement helper: wall-clock microseconds of `iters` back-to-back calls, one batch each, timed inside the library so that
 // the caller's language runtime is not part of the number (bench.py's latency line)

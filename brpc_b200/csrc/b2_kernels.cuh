@@ -78,9 +78,11 @@ struct DevConfig {
     uint32_t stream_handler;      // B2_STREAM_*
     uint32_t spec_k;              // speculative frame offsets kept per tile: kSpecK, or kSpecKDense when tiles hold many small frames
     uint32_t by_ref;              // B2_RESP_BY_REF: OK echo replies are {prefix, reference into the request bytes}
+    uint32_t verify_done;         // k_crc_verify already checked the CRC-carrying echoes: k_pack_slow skips its own verify pass
     uint32_t proto_mask;          // handlers of the messenger (bit = ProtocolType): default baidu_std | streaming_rpc; b2_set_protocols adds hulu / sofa / nshead
     uint32_t fused;               // the fused decode+pack kernel serves this batch: replies sit at their request's own offset, slow ones in the overflow area
     uint32_t ovf_base;            // ... which starts here in the resp region
+    uint32_t pull_vecs;           // 16-byte vectors per stashed row: 8 (128 B), or 6 (96 B) with B2_RESP_BY_REF — the decoder then needs header + meta + 6 body bytes only
     uint32_t pull;                // B2_INPUT_PULL: `bytes` is mapped host memory; the walk stashes each frame's first 128 bytes in HBM
     char identity[64];            // "ip:port" of Controller::AppendServerIdentiy
 };
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(128) k_tile_walk_pull(BatchPtrs B, DevConfig C
             bool fast = false; uint32_t new_pos = pos, frame_pos = pos; int idx = 0, err = B2_PARSE_OK; bool popped = false;
             uint4 v = make_uint4(0, 0, 0, 0);
             if (len - pos >= 12) {
-                v = __ldg(reinterpret_cast<const uint4*>(run + (pos & ~15u)) + sub);      // (the buffer has 1 KiB of slack past its end)
+                if (sub < C.pull_vecs) v = __ldg(reinterpret_cast<const uint4*>(run + (pos & ~15u)) + sub);      // (the buffer has 1 KiB of slack past its end)
                 // the 12 header bytes start at byte (pos & 15) of the row: words from lanes 0 and 1 of the group
                 const uint32_t a0 = __shfl_sync(gmask, v.x, l0), a1 = __shfl_sync(gmask, v.y, l0), a2 = __shfl_sync(gmask, v.z, l0), a3 = __shfl_sync(gmask, v.w, l0);
                 const uint32_t b0 = __shfl_sync(gmask, v.x, l0 + 1), b1 = __shfl_sync(gmask, v.y, l0 + 1), b2 = __shfl_sync(gmask, v.z, l0 + 1);
@@ -368,11 +370,11 @@ __global__ void __launch_bounds__(128) k_tile_walk_pull(BatchPtrs B, DevConfig C
                 frame_pos = __shfl_sync(gmask, s.frame_pos, l0); popped = __shfl_sync(gmask, (int)s.popped, l0) != 0;
                 if (count == 0 && popped) { kind = kAmbig; break; }
                 if (err != B2_PARSE_OK) { kind = kStop; break; }
-                v = __ldg(reinterpret_cast<const uint4*>(run + (frame_pos & ~15u)) + sub);
+                if (sub < C.pull_vecs) v = __ldg(reinterpret_cast<const uint4*>(run + (frame_pos & ~15u)) + sub);
             }
             if (count < cap) {
                 if (sub == 0) spec[count] = (ti.x + frame_pos) | ((uint32_t)(idx != 1) << 31);
-                rows[(size_t)count * 8 + sub] = v;
+                if (sub < C.pull_vecs) rows[(size_t)count * 8 + sub] = v;
             }
             count++; last = idx; pf = idx; pos = new_pos;
         }
@@ -695,7 +697,7 @@ __device__ __forceinline__ void decode_round(const BatchPtrs& B, const DevConfig
         const uint32_t m = m2 + half;
         const uint32_t f = __shfl_sync(0xffffffffu, fo_raw, m & 31) & 0x7fffffffu;
         const uint32_t row = __shfl_sync(0xffffffffu, my_row, m & 31);
-        if (m < nm && sub < kRowVecs && (row == kNone || sub < 8)) {
+        if (m < nm && sub < kRowVecs && (row == kNone || sub < C.pull_vecs)) {
             // cp.async (LDGSTS): global -> shared without a register round trip, so all 16 trips are in flight together
             const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.row[m][sub]);
             const uint4* src = row == kNone ? reinterpret_cast<const uint4*>(B.bytes + (f & ~15u)) + sub       // (buffer is padded past its end)
@@ -708,7 +710,7 @@ __device__ __forceinline__ void decode_round(const BatchPtrs& B, const DevConfig
     __syncwarp();
     bool is_slow = false, is_verify = false;
     if (i < n_msgs) {
-        decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 15u), S.head[lane], my_row == kNone ? kRowBytes : 128u);
+        decode_one(B, C, i, fo_raw, reinterpret_cast<const uint8_t*>(S.row[lane]) + (fo_raw & 15u), S.head[lane], my_row == kNone ? kRowBytes : 16u * C.pull_vecs);
         const uint32_t f = B.jobs[i].fast; is_slow = f == 0; is_verify = f == 2;
     }
     const uint32_t slow_mask = __ballot_sync(0xffffffffu, is_slow);
@@ -811,7 +813,9 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
     }
     // decode from the staged copy when header + meta + the first body bytes are inside it
     const uint32_t meta_size_peek = load_be32(srow + 8);
-    const bool staged = (uint64_t)(fo_raw & 15u) + 12ull + meta_size_peek + 40ull <= row_bytes;
+    // (the staged bytes must hold header, meta, the pb field header of the body and — when the reply is materialised — the <= 15 payload
+    // bytes that travel in the head record; by-reference replies take none of the payload)
+    const bool staged = (uint64_t)(fo_raw & 15u) + 12ull + meta_size_peek + (C.by_ref ? 8ull : 40ull) <= row_bytes;
     const uint8_t* frame = staged ? srow : gframe;
     b2_msg_desc d;
     d.frame_off = fo; d.body_size = load_be32(frame + 4); d.meta_size = load_be32(frame + 8);
@@ -1446,12 +1450,22 @@ __device__ __forceinline__ uint32_t warp_crc32c_update(uint32_t l, const uint8_t
     const uint32_t k0 = lead >> 2, sh = 8 * (lead & 3u);
     const uint32_t x_lo = l << sh, x_hi = sh ? l >> (32 - sh) : 0u;
     uint32_t R = 0;
-    for (uint32_t r = 0; r < rows; r++) {
-        const int32_t v = (int32_t)(r * 32 + lane) - (int32_t)off;
-        uint4 blk = make_uint4(0, 0, 0, 0);
-        if (v >= 0) {
-            blk = __ldg(a0 + v);
-            if (v <= 1) {                                            // zero the bytes in front of the message, fold the register in
+    for (uint32_t r0 = 0; r0 < rows; r0 += 4) {
+        // four rows (2 KB of the message) are requested before the first is folded in: the loop is a chain of table look-ups, the loads
+        // must not sit inside it
+        uint4 pre[4];
+        #pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int32_t v = (int32_t)((r0 + u) * 32 + lane) - (int32_t)off;
+            pre[u] = make_uint4(0, 0, 0, 0);
+            if (r0 + u < rows && v >= 0) pre[u] = __ldg(a0 + v);
+        }
+        #pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (r0 + u >= rows) break;
+            const int32_t v = (int32_t)((r0 + u) * 32 + lane) - (int32_t)off;
+            uint4 blk = pre[u];
+            if (v >= 0 && v <= 1) {                                  // zero the bytes in front of the message, fold the register in
                 uint32_t w[4] = { blk.x, blk.y, blk.z, blk.w };
                 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -1462,8 +1476,8 @@ __device__ __forceinline__ uint32_t warp_crc32c_update(uint32_t l, const uint8_t
                 }
                 blk = make_uint4(w[0], w[1], w[2], w[3]);
             }
+            R = crc_adv4(ct.hot + 16 * 256, R) ^ crc_s16(ct.hot, blk);
         }
-        R = crc_adv4(ct.hot + 16 * 256, R) ^ crc_s16(ct.hot, blk);
     }
     #pragma unroll
     for (int t = 0; t < 5; t++) {
@@ -2327,7 +2341,7 @@ __global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs
     const uint32_t lane = threadIdx.x & 31;
     if (B.totals[2] & 3u) return;
     finalize_runs(B, C);                               // (was a separate launch)
-    const uint32_t n_verify = B.totals[7];
+    const uint32_t n_verify = C.verify_done ? 0u : B.totals[7];
     if (B.totals[3] == 0 && n_verify == 0) return;
     __shared__ uint32_t s_hot[kLite ? 1 : kCrcHotWords];
     extern __shared__ __align__(16) uint8_t s_rings[];           // kSnapRing bytes per warp
@@ -2338,7 +2352,7 @@ __global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs
     // text to a 256 KiB snappy stream, so the queue is dynamic: totals[6] is the ticket)
     // verify pass: Crc32cVerify (policy/crc32c_checksum.cpp:44-61) of the plain echoes whose reply k_pack_tma moves;
     // a request that fails is answered here (EREQUEST) and taken off the bandwidth path
-    for (;;) {
+    for (; !C.verify_done;) {
         uint32_t k = 0;
         if (lane == 0) k = atomicAdd(B.totals + 8, 1u);
         k = __shfl_sync(0xffffffffu, k, 0);
@@ -2360,6 +2374,34 @@ __global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n_slow) break;
         pack_one(B, C, B.slow_idx[k], lane, ct);
+    }
+}
+
+
+// --- k_crc_verify: Crc32cVerify (policy/crc32c_checksum.cpp:44-61) of every CRC-carrying plain echo, as a kernel of its own -----------
+// The verify pass is a chain of shared-memory table look-ups per message: what it needs is many resident warps and loads issued ahead of
+// the chain, not the 80 registers of the general slow path.  48 warps per SM, one message per warp at a time; a request that passes is
+// released to the bandwidth path (jobs[i].fast = 1), one that fails joins k_pack_slow's list and is answered EREQUEST there.
+__global__ void __launch_bounds__(256, 6) k_crc_verify(BatchPtrs B, DevConfig C) {
+    if (B.totals[2] & 3u) return;
+    const uint32_t n_verify = B.totals[7];
+    if (n_verify == 0) return;
+    __shared__ uint32_t s_hot[kCrcHotWords];
+    crc_tabs_to_smem(s_hot, B.crc_adv);
+    CrcTabs ct; ct.hot = s_hot; ct.tree = B.crc_adv + kCrcHotWords; ct.ring = nullptr;
+    const uint32_t lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_verify; k += n_warps) {
+        const uint32_t i = B.slow_idx[B.max_msgs - 1 - k];
+        const uint32_t fo = B.msgs[i].frame_off, meta_size = B.msgs[i].meta_size;
+        const uint32_t req_size = B.msgs[i].body_size - meta_size;
+        int64_t bwo = (int64_t)req_size - (int64_t)B.msgs[i].attachment_size; if (bwo > (int64_t)req_size) bwo = req_size;
+        const uint8_t* frame = B.bytes + fo;
+        const uint32_t crc = warp_crc32c_update(0xffffffffu, frame + 12 + meta_size, (uint32_t)bwo, lane, ct) ^ 0xffffffffu;
+        const bool good = crc == crc32c_unmask(load_be32(frame + B.aux[i].cks_off));
+        if (lane == 0) {
+            if (good) B.jobs[i].fast = 1;
+            else { B.jobs[i].fast = 0; B.slow_idx[atomicAdd(B.totals + 3, 1u)] = i; }
+        }
     }
 }
 
@@ -2496,7 +2538,8 @@ struct RingSlotHdr {                 // in mapped host memory, one per slot; the
     unsigned long long bytes_dev;    // device-visible address of the batch bytes (the caller's pinned block, or the slot's staging area)
     unsigned long long pad0;
     volatile uint32_t done;          // device: ticket, after the output block is visible
-    uint32_t pad1[15];
+    uint32_t pad1[3];
+    unsigned long long stamps[6];    // device %globaltimer (ns): doorbell seen, header read, bytes pulled, body done, results pushed, (spare)
 };                                   // 128 bytes
 struct RingDev {
     uint8_t* slots;                  // mapped host memory: kRingSlots x slot_stride
@@ -2542,10 +2585,13 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_ring(RingDev R, BatchPtrs 
         }
         __syncthreads();
         if (!s_go) break;
+        unsigned long long t_seen = 0, t_hdr = 0, t_pull = 0, t_body = 0;
+        if (tid == 0) t_seen = globaltimer_ns();
         // the slot header (the host's stores are ordered before `submit` by its release fence)
         if (tid < sizeof(RingSlotHdr) / 4) reinterpret_cast<uint32_t*>(&s_hdr)[tid] = ld_sys_u32(reinterpret_cast<const volatile uint32_t*>(slot) + tid);
         __syncthreads();
         const uint32_t n_runs = s_hdr.n_runs, nbytes = s_hdr.nbytes;
+        if (tid == 0) t_hdr = globaltimer_ns();
         {   // pull: runs (24 B each) + per-run tile base placeholder, then the batch bytes, 16 bytes per thread per trip
             const uint4* src = reinterpret_cast<const uint4*>(slot + R.off_runs);
             uint4* dst = reinterpret_cast<uint4*>(R.d_meta);
@@ -2572,15 +2618,18 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_ring(RingDev R, BatchPtrs 
         if (tid < 16) B.totals[tid] = 0;
         __threadfence();
         __syncthreads();
+        if (tid == 0) t_pull = globaltimer_ns();
         small_body(B, Cb, S);
         __threadfence();
         __syncthreads();
+        if (tid == 0) t_body = globaltimer_ns();
         {   // push the compact block [totals | run_status | msgs | refs | resp] into the slot's output area
             const uint32_t used = (B.totals[2] & 3u) ? 64u : s_hdr.off_resp + ((B.totals[1] + 15u) & ~15u);
             const uint4* src = reinterpret_cast<const uint4*>(R.d_small);
             uint4* dst = reinterpret_cast<uint4*>(slot + R.off_out);
             for (uint32_t k = tid; k < (used + 15u) / 16u; k += kSmallThreads) dst[k] = __ldcg(src + k);
         }
+        if (tid == 0) { hdr->stamps[0] = t_seen; hdr->stamps[1] = t_hdr; hdr->stamps[2] = t_pull; hdr->stamps[3] = t_body; hdr->stamps[4] = globaltimer_ns(); }
         __threadfence_system();
         __syncthreads();
         if (tid == 0) { st_sys_u32(&hdr->done, ticket); st_sys_u32(R.ctl + 2, ticket + 1); }

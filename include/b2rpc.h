@@ -320,6 +320,9 @@ int  b2_ring_stop(b2_ctx* ctx);
 int  b2_ring_submit(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs, uint32_t* ticket);
 int  b2_ring_wait(b2_ctx* ctx, uint32_t ticket, b2_batch_result* out);
 uint64_t b2_ring_launches(b2_ctx* ctx);   /* how many times the resident kernel was (re)started: the launches of the ring path */
+/* Device-side phases of a collected ticket (diagnostics), nanoseconds since the resident kernel saw the doorbell:
+ * [0] slot header read, [1] runs + bytes pulled into HBM, [2] cut / decode / echo / pack done, [3] results pushed to the host. */
+int  b2_ring_phase_ns(b2_ctx* ctx, uint32_t ticket, uint64_t out[4]);
 /* Measurement helper: us_out[i] = wall-clock microseconds of the i-th of `iters` back-to-back single-batch calls —
  * b2_process_batch (use_ring 0) or b2_ring_submit + b2_ring_wait (use_ring 1) — timed inside the library. */
 int  b2_latency_probe(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_run* runs, uint32_t n_runs,

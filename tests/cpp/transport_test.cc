@@ -33,10 +33,10 @@ uint64_t b2press_fill_run(const b2press_spec* s, uint64_t* index, uint8_t* out, 
 }
 // run on (and first-touch pinned memory from) the CPUs next to the GPU: zero-copy PCIe reads that cross the socket interconnect lose most
 // of their rate (bench.py does the same through NVML)
+extern "C" int cudaDeviceGetPCIBusId(char*, int, int) __attribute__((weak));
 static void pin_to_gpu_numa(int device) {
     char bus[32] = {0};
-    extern int cudaDeviceGetPCIBusId(char*, int, int) __attribute__((weak));
-    if (!cudaDeviceGetPCIBusId || cudaDeviceGetPCIBusId(bus, sizeof bus, device) != 0) return;
+    if (!cudaDeviceGetPCIBusId || cudaDeviceGetPCIBusId(bus, sizeof bus, device) != 0) { fprintf(stderr, "(no NUMA pinning: cudart not linked)\n"); return; }
     for (char* p = bus; *p; p++) if (*p >= 'A' && *p <= 'Z') *p = (char)(*p - 'A' + 'a');
     char path[128]; snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
     FILE* f = fopen(path, "r"); if (!f) return;
@@ -46,6 +46,7 @@ static void pin_to_gpu_numa(int device) {
         int a, b; if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b; c++) { CPU_SET(c, &set); n++; } } else if (sscanf(tok, "%d", &a) == 1) { CPU_SET(a, &set); n++; }
     }
     if (n) sched_setaffinity(0, sizeof set, &set);
+    fprintf(stderr, "(pinned to %d CPUs next to GPU %d)\n", n, device);
 }
 static double now_s() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + t.tv_nsec * 1e-9; }
 static void set_nonblock(int fd) { fcntl(fd, F_SETFL, fcntl(fd, F_GETFL) | O_NONBLOCK); }

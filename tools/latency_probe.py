@@ -30,4 +30,6 @@ for by_ref in (0, 1):
     for ring in (0, 1):
         us = np.sort(ctx.latency_probe(buf.ptr, N * stride, runs, 3000, ring))
         print("by_ref=%d C-timed %s: p50 %.1f us  p99 %.1f us  min %.1f" % (by_ref, "ring    " if ring else "blocking", us[1500], us[2970], us[0]))
+    t = ctx.ring_submit(None, runs, ptr=buf.ptr, nbytes=N * stride); ctx.ring_wait(t)
+    print("   device phases (ns since doorbell seen): header %d, pulled %d, body done %d, pushed %d" % tuple(ctx.ring_phase_ns(t)))
     ctx.ring_stop()
