@@ -4,6 +4,7 @@
 // answers gRPC calls of device-served (echo) methods through b2_h2_pack_responses without the payload ever leaving the GPU,
 // and gives every other completed request to the host callback the way ProcessHttpRequest would receive an H2StreamContext.
 #pragma once
+#include <algorithm>
 #include <utility>
 #include "input_messenger.h"
 
@@ -19,11 +20,17 @@ struct H2Message : public InputMessageBase {           // an H2StreamContext aft
 class GpuH2Messenger {
 public:
     typedef void (*Process)(InputMessageBase* msg);
-    explicit GpuH2Messenger(const b2_options& opt, uint32_t out_cap = 32u << 20) : _cap(opt.max_batch_bytes), _out_cap(out_cap) {
+    // max_conns / max_pending / stream_bytes: the device's h2 stream pool (b2_h2_configure); a gRPC client keeps up to 100 calls in flight
+    explicit GpuH2Messenger(const b2_options& opt, uint32_t out_cap = 32u << 20, uint32_t max_conns = B2_H2_MAX_CONNS, uint32_t max_pending = B2_H2_MAX_PENDING,
+                            uint32_t stream_bytes = B2_H2_STREAM_BYTES) : _cap(opt.max_batch_bytes), _out_cap(out_cap), _max_conns(max_conns), _msg_cap(opt.max_msgs) {
         if (b2_ctx_create(&opt, &_ctx) != B2_OK) throw std::runtime_error(std::string("b2_ctx_create: ") + b2_last_error());
         _batch = static_cast<uint8_t*>(b2_block_alloc(_cap)); _out = static_cast<uint8_t*>(b2_block_alloc(_out_cap));
         _pack = static_cast<uint8_t*>(b2_block_alloc(_out_cap));
-        if (!_batch || !_out || !_pack) throw std::runtime_error("b2_block_alloc failed");
+        if (!_batch || !_out || !_pack || b2_h2_configure(_ctx, max_conns, max_pending, stream_bytes) != B2_OK) {
+            b2_block_free(_batch); b2_block_free(_out); b2_block_free(_pack); b2_ctx_destroy(_ctx);      // (nothing leaks when construction fails)
+            throw std::runtime_error(std::string("GpuH2Messenger: ") + b2_last_error());
+        }
+        for (uint32_t k = max_conns; k-- > 0;) _free_conns.push_back(k);
     }
     ~GpuH2Messenger() { b2_block_free(_batch); b2_block_free(_out); b2_block_free(_pack); b2_ctx_destroy(_ctx); }
     GpuH2Messenger(const GpuH2Messenger&) = delete;
@@ -31,10 +38,22 @@ public:
     int AddMethod(const b2_method& m) { const int i = b2_register_method(_ctx, &m); if (i >= 0) { _handlers.resize(i + 1); _handlers[i] = m.handler; } return i; }
     void SetHostProcess(Process p) { _process = p; }
     // a new server-side connection: H2Context is created when the first bytes arrive (:1108-1120)
+    // Device connection slots are a free list: RemoveConnection gives the slot back.  nullptr = no slot left (the caller keeps such a
+    // connection on the host parser) or the device refused the reset.
     Socket* AddConnection(uint64_t id) {
-        auto& s = _sockets[id];
-        if (!s) { s.reset(new Socket(id)); _conn_of[id] = (uint32_t)_conn_of.size(); b2_h2_conn_reset(_ctx, _conn_of[id]); }
-        return s.get();
+        auto it = _sockets.find(id);
+        if (it != _sockets.end()) return it->second.get();
+        if (_free_conns.empty()) return nullptr;
+        const uint32_t slot = _free_conns.back();
+        if (b2_h2_conn_reset(_ctx, slot) != B2_OK) return nullptr;
+        _free_conns.pop_back();
+        _conn_of[id] = slot;
+        return (_sockets[id] = std::unique_ptr<Socket>(new Socket(id))).get();
+    }
+    void RemoveConnection(uint64_t id) {
+        auto it = _conn_of.find(id);
+        if (it == _conn_of.end()) return;
+        _free_conns.push_back(it->second); _conn_of.erase(it); _sockets.erase(id);
     }
 
     // One round over the readable connections.  Returns the number of completed requests, -1 on an ABI error.
@@ -44,14 +63,17 @@ public:
         for (Socket* s : readable) {
             if (s->Failed() || s->_read_buf.empty()) continue;
             const size_t n = s->_read_buf.length();
-            if (total + n + 16 > _cap) break;
+            if (n + 16 > _cap) { s->SetFailed(22, "Close socket: pending h2 bytes exceed the batch capacity"); continue; }
+            if (total + n + 16 > _cap) continue;                  // served next round; later (smaller) connections still fit
             s->_read_buf.copy_to(_batch + total, n, 0);
             b2_run r; r.socket_id = _conn_of[s->id()]; r.offset = (uint32_t)total; r.length = (uint32_t)n; r.preferred_proto = -1; r.flags = 0;
             runs.push_back(r); live.push_back(s);
             total = (total + n + 15) & ~(size_t)15;
         }
         if (runs.empty()) return 0;
-        std::vector<b2_h2_run_status> rs(runs.size()); std::vector<b2_h2_msg> msgs(64 * runs.size()); uint32_t n_msgs = 0;
+        // (the ABI splits msg_cap evenly over the runs: give every connection what a full batch of minimal requests could complete)
+        const size_t per_run = std::max<size_t>(64, std::min<size_t>(_msg_cap / runs.size(), 4096));
+        std::vector<b2_h2_run_status> rs(runs.size()); std::vector<b2_h2_msg> msgs(per_run * runs.size()); uint32_t n_msgs = 0;
         if (b2_h2_process_batch(_ctx, _batch, (uint32_t)total, runs.data(), (uint32_t)runs.size(), rs.data(), msgs.data(), (uint32_t)msgs.size(),
                                 &n_msgs, _out, _out_cap) != B2_OK) return -1;
         std::vector<b2_h2_response> resps; std::vector<Socket*> resp_sock;
@@ -106,7 +128,8 @@ private:
             q += 4 + nl + vl;
         }
     }
-    b2_ctx* _ctx = nullptr; uint8_t* _batch = nullptr; uint8_t* _out = nullptr; uint8_t* _pack = nullptr; size_t _cap; uint32_t _out_cap;
+    b2_ctx* _ctx = nullptr; uint8_t* _batch = nullptr; uint8_t* _out = nullptr; uint8_t* _pack = nullptr; size_t _cap; uint32_t _out_cap, _max_conns; size_t _msg_cap;
+    std::vector<uint32_t> _free_conns;
     Process _process = nullptr; std::vector<int> _handlers;
     std::unordered_map<uint64_t, std::unique_ptr<Socket>> _sockets;
     std::unordered_map<uint64_t, uint32_t> _conn_of;
