@@ -53,7 +53,7 @@ struct b2_ctx {
     b2_run_status* h_run_status = nullptr; b2_msg_desc* h_msgs = nullptr; uint8_t* h_resp = nullptr;
     uint32_t* h_totals = nullptr; uint32_t* h_run_tile_base = nullptr;
     // current batch
-    uint32_t n_runs = 0, n_tiles = 0, nbytes = 0, max_run_tiles = 0;
+    uint32_t n_runs = 0, n_tiles = 0, nbytes = 0, max_run_tiles = 0; uint64_t covered = 0;
     bool uploaded = false, executed = false;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[kMaxStages + 1];
@@ -345,10 +345,9 @@ extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, co
     if (!c || (!bytes && nbytes) || (!runs && n_runs)) { set_err("null argument"); return B2_E_INVAL; }
     // (B2_INPUT_PULL: `bytes` is the caller's whole pinned arena and nothing is copied — what is bounded is the bytes the runs cover)
     if ((c->input_mode != B2_INPUT_PULL && nbytes > c->opt.max_batch_bytes) || nbytes >= (1u << 31) || n_runs > c->opt.max_runs) { set_err("batch exceeds ctx capacity"); return B2_E_CAPACITY; }
-    if (c->input_mode == B2_INPUT_PULL) {
-        uint64_t covered = 0; for (uint32_t r = 0; r < n_runs; r++) covered += runs[r].length;
-        if (covered > c->opt.max_batch_bytes) { set_err("runs exceed ctx capacity"); return B2_E_CAPACITY; }
-    }
+    uint64_t covered = 0; for (uint32_t r = 0; r < n_runs; r++) covered += runs[r].length;
+    if (c->input_mode == B2_INPUT_PULL && covered > c->opt.max_batch_bytes) { set_err("runs exceed ctx capacity"); return B2_E_CAPACITY; }
+    c->covered = covered;                           // (what the runs hold: with B2_INPUT_PULL nbytes spans the caller's whole arena)
     CU(cudaSetDevice(c->opt.device));
     if (c->adaptive_tile) {
         // like Socket::_avg_msg_size steering the read size (input_messenger.cpp:348-353): a tile should hold
@@ -605,7 +604,7 @@ extern "C" int b2_batch_download(b2_ctx* c, b2_batch_result* out) {
         int rc = download_normal(c, out);
         if (rc != B2_OK) return rc;
     }
-    if (out->n_msgs) { const uint32_t now = c->nbytes / out->n_msgs; c->avg_frame = c->avg_frame ? (uint32_t)(((uint64_t)c->avg_frame * 3 + now) / 4) : now; }
+    if (out->n_msgs) { const uint32_t now = (uint32_t)(c->covered / out->n_msgs); c->avg_frame = c->avg_frame ? (uint32_t)(((uint64_t)c->avg_frame * 3 + now) / 4) : now; }
     out->kernel_ms = c->last_kernel_ms; out->n_launches = c->last_launches;
     return B2_OK;
 }
@@ -800,6 +799,12 @@ extern "C" int b2_stage_times(b2_ctx* c, const char** names, float* ms, int cap)
 extern "C" int b2_batch_info(b2_ctx* c, uint32_t out[4]) {
     if (!c || !out) return B2_E_INVAL;
     out[0] = c->cfg.tile_bytes; out[1] = c->n_tiles; out[2] = c->cfg.spec_k; out[3] = c->fused_last ? 1u : 0u;
+    return B2_OK;
+}
+
+extern "C" int b2_device_pci_bus_id(int device, char* out, int cap) {
+    if (!out || cap < 13) return B2_E_INVAL;
+    if (cudaDeviceGetPCIBusId(out, cap, device) != cudaSuccess) { cudaGetLastError(); return B2_E_CUDA; }
     return B2_OK;
 }
 

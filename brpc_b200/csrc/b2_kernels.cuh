@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "b2_core.cuh"
+#include "b2_inflate.cuh"
 
 namespace b2 {
 
@@ -681,9 +682,21 @@ __device__ __forceinline__ uint32_t fused_overflow_slot(const BatchPtrs& B, cons
     return C.ovf_base + so;
 }
 struct DecodeOut { uint32_t prefix, rs; bool fast, slow; };        // k_fused: reply prefix length, where the reply starts in resp, disposition
+// decode_one = decode_one_impl<kFused, false>, which stops short (returns true, nothing written) at a gzip / zlib body: sizing one walks a
+// DEFLATE stream, and that code must not sit inside the hot instantiation (registers, spills).  Such a message is decoded again by the
+// out-of-line decode_one_gz = decode_one_impl<kFused, true>.
+template <bool kFused, bool kGz>
+__device__ __forceinline__ bool decode_one_impl(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
+                                                const uint8_t* srow, uint8_t* shead, uint32_t row_bytes, uint32_t run_idx, DecodeOut* out);
+template <bool kFused>
+__device__ __noinline__ void decode_one_gz(BatchPtrs B, DevConfig C, uint32_t i, uint32_t fo_raw,
+                                           const uint8_t* srow, uint8_t* shead, uint32_t row_bytes, uint32_t run_idx, DecodeOut* out);
 template <bool kFused = false>
 __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
-                                           const uint8_t* srow, uint8_t* shead, uint32_t row_bytes, uint32_t run_idx = kNone, DecodeOut* out = nullptr);
+                                           const uint8_t* srow, uint8_t* shead, uint32_t row_bytes, uint32_t run_idx = kNone, DecodeOut* out = nullptr) {
+    if (decode_one_impl<kFused, false>(B, C, i, fo_raw, srow, shead, row_bytes, run_idx, out))
+        decode_one_gz<kFused>(B, C, i, fo_raw, srow, shead, row_bytes, run_idx, out);
+}
 
 // one warp round: 32 consecutive messages starting at i0 (staging, decode, head write-out)
 __device__ __forceinline__ void decode_round(const BatchPtrs& B, const DevConfig& C, DecodeWarpSmem& S, uint32_t i0, uint32_t n_msgs, uint32_t lane) {
@@ -748,8 +761,13 @@ __global__ void __launch_bounds__(kDecodeWarps * 32, B2_DECODE_MIN_BLOCKS) k_dec
 }
 
 template <bool kFused>
-__device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
+__device__ __noinline__ void decode_one_gz(BatchPtrs B, DevConfig C, uint32_t i, uint32_t fo_raw,
                                            const uint8_t* srow, uint8_t* shead, uint32_t row_bytes, uint32_t run_idx, DecodeOut* out) {
+    decode_one_impl<kFused, true>(B, C, i, fo_raw, srow, shead, row_bytes, run_idx, out);
+}
+template <bool kFused, bool kGz>
+__device__ __forceinline__ bool decode_one_impl(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
+                                                const uint8_t* srow, uint8_t* shead, uint32_t row_bytes, uint32_t run_idx, DecodeOut* out) {
     const uint32_t fo = fo_raw & 0x7fffffffu;
     // bit 31 of a frame offset says "not baidu_std": which of the other handlers cut it is read off its magic
     int proto = B2_PROTOCOL_BAIDU_STD;
@@ -784,13 +802,13 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
         if (kFused) {
             out->fast = false; out->prefix = 0; out->rs = 0; out->slow = d.status == B2_MSG_REPLAY;
             if (out->slow) { B.aux[i] = a; B.slot[i] = fused_overflow_slot(B, C, slot_len); }
-            return;
+            return false;
         }
         B.aux[i] = a; B.slot[i] = slot_len;
         PackJob job; job.src_off = 0; job.bulk_len = 0; job.head_len = 0; job.pad = 0; job.fast = 0; job.slot_len = slot_len;
         B.jobs[i] = job;
         if (C.by_ref) B.refs[i] = make_uint4(0, 0, 0, 0);
-        return;
+        return false;
     }
     if (proto > 2) {
         // hulu_pbrpc / sofa_pbrpc / nshead: framed on the device, processed by the host (ProcessHuluRequest ... stay there): the descriptor
@@ -803,13 +821,13 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
         d.correlation_id = 0; d.log_id = 0; d.attachment_size = 0; d.compress_type = 0; d.checksum_type = 0; d.error_code = 0;
         d.has_bits = 0; d.protocol = (uint8_t)proto; d.content_type = 0; d.method_idx = -1; d.status = B2_MSG_FRAMED; d.resp_off = 0; d.resp_len = 0;
         B.msgs[i] = d;
-        if (kFused) { out->fast = false; out->slow = false; out->prefix = 0; out->rs = 0; return; }
+        if (kFused) { out->fast = false; out->slow = false; out->prefix = 0; out->rs = 0; return false; }
         MsgAux a; a.msg_off = a.msg_len = a.att_len = a.att_off = a.cks_off = a.cks_len = 0; a.svc_off = a.svc_len = a.mth_off = a.mth_len = 0; a.pad = 0; a.err_kind = kErrNone;
         B.aux[i] = a; B.slot[i] = 0;
         PackJob job; job.src_off = 0; job.bulk_len = 0; job.head_len = 0; job.pad = 0; job.fast = 0; job.slot_len = 0;      // (pack_one returns at once: no reply)
         B.jobs[i] = job;
         if (C.by_ref) B.refs[i] = make_uint4(0, 0, 0, 0);
-        return;
+        return false;
     }
     // decode from the staged copy when header + meta + the first body bytes are inside it
     const uint32_t meta_size_peek = load_be32(srow + 8);
@@ -869,7 +887,7 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                     if (bwo > (int64_t)res_size) bwo = res_size;
                     const uint32_t body_len = (uint32_t)bwo;
                     if (m.content_type != B2_CONTENT_TYPE_PB) d.status = B2_MSG_UNSUPPORTED;
-                    else if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) d.status = B2_MSG_UNSUPPORTED;
+                    else if ((m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) && body_len > kGzMaxIn) d.status = B2_MSG_UNSUPPORTED;
                     else {
                         bool ok = !(m.checksum_type == B2_CHECKSUM_TYPE_CRC32C && a.cks_len != 4);
                         if (ok && m.compress_type == B2_COMPRESS_TYPE_NONE) {
@@ -881,8 +899,16 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                             ok = snappy_preamble(gframe + 12 + d.meta_size, body_len, ulen, used);
                             if (ok && (uint64_t)ulen > 32ull * body_len + 64ull) ok = false;
                             if (ok) { d.status = B2_MSG_RESPONSE_UNZ; a.msg_off = kNone; a.msg_len = ulen; a.att_off = body_len; resp_len = ulen ? ulen : 1; }
+                        } else if (ok && (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB)) {
+                            // GzipDecompress / ZlibDecompress (policy/gzip_compress.cpp:75-89): sized here, inflated by the pack stage
+                            if (!kGz) return true;
+                            bool big = false;
+                            const uint32_t ulen = gz_input_stream<false>(gframe + 12 + d.meta_size, body_len, m.compress_type, nullptr, kGzMaxOut, &big);
+                            if (big) { d.status = B2_MSG_UNSUPPORTED; }
+                            else { d.status = B2_MSG_RESPONSE_UNZ; a.msg_off = kNone; a.msg_len = ulen; a.att_off = body_len; resp_len = ulen ? ulen : 1; }
                         } else ok = false;
                         if (!ok) { d.error_code = B2_EREQUEST; resp_len = 0; d.status = B2_MSG_RESPONSE; }  // :999-1007
+                        if (d.status == B2_MSG_UNSUPPORTED) resp_len = 0;
                     }
                 }
                 d.resp_len = resp_len;
@@ -891,12 +917,12 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                 if (kFused) {
                     out->fast = false; out->prefix = 0; out->rs = 0; out->slow = resp_len > 0;
                     B.slot[i] = csl ? fused_overflow_slot(B, C, csl) : 0u;
-                    return;
+                    return false;
                 }
                 B.slot[i] = csl;
                 PackJob cj; cj.src_off = 0; cj.bulk_len = 0; cj.head_len = 0; cj.pad = 0; cj.fast = 0; cj.slot_len = 0;
                 B.jobs[i] = cj;
-                return;
+                return false;
             }
             if ((m.has & B2_HAS_ATTACHMENT_SIZE) && (int64_t)req_size < att) {
                 a.err_kind = kErrAttachment; d.error_code = B2_EREQUEST;
@@ -914,17 +940,24 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                 const uint32_t body_wo_att = (uint32_t)bwo;
                 const uint32_t in_att_len = att > 0 ? (uint32_t)att : 0;
                 if (m.content_type != B2_CONTENT_TYPE_PB) d.status = B2_MSG_UNSUPPORTED;
-                else if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) d.status = B2_MSG_UNSUPPORTED;
                 else if (mp->response_compress_type != B2_COMPRESS_TYPE_NONE && mp->response_compress_type != B2_COMPRESS_TYPE_SNAPPY) d.status = B2_MSG_UNSUPPORTED;
-                else if (m.compress_type == B2_COMPRESS_TYPE_SNAPPY) {
+                else if ((m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) && body_wo_att > kGzMaxIn) d.status = B2_MSG_UNSUPPORTED;
+                else if (m.compress_type == B2_COMPRESS_TYPE_SNAPPY || m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) {
                     // SnappyDecompress (policy/snappy_compress.cpp:51-70) happens in the pack stage; here only the
                     // announced length is read to reserve the reply slot.  A stream cannot expand more than ~22x
                     // (a 3-byte copy yields <= 64 bytes), so an announced length beyond 32x + 64 must fail.
+                    // GzipDecompress / ZlibDecompress (policy/gzip_compress.cpp:75-89) announce nothing: a sizing pass walks the stream
                     uint32_t ulen = 0, used = 0;
-                    bool ok = !(m.checksum_type == B2_CHECKSUM_TYPE_CRC32C && a.cks_len != 4);
+                    bool ok = !(m.checksum_type == B2_CHECKSUM_TYPE_CRC32C && a.cks_len != 4), big = false;
+                    if (m.compress_type == B2_COMPRESS_TYPE_SNAPPY) {
                     if (ok) ok = snappy_preamble(gframe + 12 + d.meta_size, body_wo_att, ulen, used);
                     if (ok && (uint64_t)ulen > 32ull * body_wo_att + 64ull) ok = false;
-                    if (!ok) { a.err_kind = kErrParseRequest; d.error_code = B2_EREQUEST; }
+                    } else if (ok) {
+                        if (!kGz) return true;
+                        ulen = gz_input_stream<false>(gframe + 12 + d.meta_size, body_wo_att, m.compress_type, nullptr, kGzMaxOut, &big);
+                    }
+                    if (big) d.status = B2_MSG_UNSUPPORTED;
+                    else if (!ok) { a.err_kind = kErrParseRequest; d.error_code = B2_EREQUEST; }
                     else {
                         d.status = B2_MSG_ECHOED;
                         a.msg_off = kNone; a.msg_len = ulen;        // resolved after decompression
@@ -983,7 +1016,7 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
                 resp_len = 12 + response_meta_len(d.error_code, tl, 0, m.correlation_id, 0, 0, a.cks_len);
             }
             // a CRC-verified request can still turn into an EREQUEST reply in k_pack: reserve for both
-            if (d.status == B2_MSG_ECHOED && (m.checksum_type == B2_CHECKSUM_TYPE_CRC32C || m.compress_type == B2_COMPRESS_TYPE_SNAPPY)) {
+            if (d.status == B2_MSG_ECHOED && (m.checksum_type == B2_CHECKSUM_TYPE_CRC32C || m.compress_type != B2_COMPRESS_TYPE_NONE)) {
                 b2_msg_desc e = d; MsgAux ea = a; e.error_code = B2_EREQUEST; ea.err_kind = kErrParseRequest;
                 const uint32_t tl = error_text_len(C, B.methods, e, ea, frame);
                 const uint32_t el = 12 + response_meta_len(B2_EREQUEST, tl, 0, m.correlation_id, 0, 0, a.cks_len);
@@ -1039,10 +1072,11 @@ __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& 
         B.msgs[i] = d;
         out->fast = fast; out->prefix = ref_prefix; out->rs = d.resp_off; out->slow = !fast && resp_len > 0;
         if (out->slow) { B.aux[i] = a; B.slot[i] = slot_len ? fused_overflow_slot(B, C, slot_len) : 0u; }
-        return;
+        return false;
     }
     B.jobs[i] = job;
     if (C.by_ref) B.refs[i] = ref;
+    return false;
 }
 
 // --- exclusive scan of slot sizes: 2 kernels ---------------------------------
@@ -1691,7 +1725,11 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
         uint32_t off = d.resp_off, len = d.resp_len;
         if (ok && d.status == B2_MSG_RESPONSE_UNZ) {
             uint32_t produced = 0;
-            ok = warp_snappy_decode(body, body_len, B.resp + slot_off, a.msg_len, lane, produced, ct.ring);
+            if (d.compress_type == B2_COMPRESS_TYPE_SNAPPY) ok = warp_snappy_decode(body, body_len, B.resp + slot_off, a.msg_len, lane, produced, ct.ring);
+            else {
+                if (lane == 0) { bool big; produced = gz_input_stream<true>(body, body_len, d.compress_type, B.resp + slot_off, a.msg_len, &big); }
+                produced = __shfl_sync(0xffffffffu, produced, 0);
+            }
             Span msg; msg.off = 0; msg.len = 0;
             if (ok) ok = decode_echo_request(B.resp + slot_off, produced, msg);
             off = slot_off + msg.off; len = msg.len;
@@ -1723,6 +1761,19 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
         Span msg; msg.off = 0; msg.len = 0;
         if (ok) ok = decode_echo_request(scratch, produced, msg);
         if (!ok) status = B2_MSG_ERROR_REPLIED;
+        else { msg_src = scratch + msg.off; msg_len = msg.len; }
+    }
+    if (status == B2_MSG_ECHOED && (d.compress_type == B2_COMPRESS_TYPE_GZIP || d.compress_type == B2_COMPRESS_TYPE_ZLIB)) {
+        // GzipDecompress / ZlibDecompress (policy/gzip_compress.cpp:75-89): lane 0 walks the DEFLATE stream into the scratch slot; the parser
+        // gets what the GzipInputStream would have handed it (a corrupt stream is end-of-input to it)
+        const uint32_t req_size = d.body_size - d.meta_size;
+        int64_t bwo = (int64_t)req_size - (int64_t)d.attachment_size; if (bwo > (int64_t)req_size) bwo = req_size;
+        uint8_t* scratch = B.unz + slot_off;
+        uint32_t produced = 0;
+        if (lane == 0) { bool big; produced = gz_input_stream<true>(frame + 12 + d.meta_size, (uint32_t)bwo, d.compress_type, scratch, a.msg_len, &big); }
+        produced = __shfl_sync(0xffffffffu, produced, 0);
+        Span msg; msg.off = 0; msg.len = 0;
+        if (!decode_echo_request(scratch, produced, msg)) status = B2_MSG_ERROR_REPLIED;
         else { msg_src = scratch + msg.off; msg_len = msg.len; }
     }
     if (status == B2_MSG_ERROR_REPLIED) {

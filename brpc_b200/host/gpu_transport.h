@@ -18,6 +18,7 @@
 // the connection's own read region}, written out by one writev per <= 128 replies.
 #pragma once
 #include <sys/uio.h>
+#include <time.h>
 #include <unistd.h>
 #include <memory>
 #include <stdexcept>
@@ -57,7 +58,7 @@ public:
             if (b2_ctx_create(&o.ctx, &c) != B2_OK || b2_set_modes(c, o.input_mode, o.resp_mode) != B2_OK) { Destroy(); throw std::runtime_error(std::string("GpuTransport: ") + b2_last_error()); }
             _ctx.push_back(c);
         }
-        _groups.resize(o.pipeline); _inflight.assign(o.pipeline, 0); _runs.resize(o.pipeline); _live.resize(o.pipeline); _iov.resize(o.pipeline); _pop.resize(o.pipeline);
+        _groups.resize(o.pipeline); _inflight.assign(o.pipeline, 0); _runs.resize(o.pipeline); _live.resize(o.pipeline); _iov.resize(o.pipeline); _pop.resize(o.pipeline); _stats.resize(o.pipeline);
         _outstanding.reset(new std::atomic<int>[o.pipeline]); for (uint32_t g = 0; g < o.pipeline; g++) _outstanding[g].store(0);
     }
     ~GpuTransport() { Destroy(); }
@@ -98,6 +99,7 @@ public:
     // Enqueue group g's pending bytes on the GPU.  Returns the number of runs submitted (0 = nothing pending), -1 on an ABI error.
     int Submit(uint32_t g) {
         if (_inflight[g]) return -1;
+        const double t_sub0 = mono_s();
         std::vector<b2_run>& runs = _runs[g]; std::vector<Conn*>& live = _live[g];
         runs.clear(); live.clear();
         uint64_t bytes = 0;
@@ -113,6 +115,7 @@ public:
         const uint32_t span_end = runs.back().offset + runs.back().length;
         const int rc = b2_batch_submit(_ctx[g], _arena, span_end, runs.data(), (uint32_t)runs.size());
         if (rc != B2_OK) return -1;
+        _stats[g].submit_s += mono_s() - t_sub0;
         _inflight[g] = 1;
         return (int)runs.size();
     }
@@ -122,7 +125,10 @@ public:
         if (!_inflight[g]) return 0;
         _inflight[g] = 0;
         b2_batch_result res;
+        const double t_wait0 = mono_s();
         if (b2_batch_collect(_ctx[g], &res) != B2_OK) return -1;
+        const double t_wait1 = mono_s();
+        _stats[g].wait_s += t_wait1 - t_wait0;
         std::vector<b2_run>& runs = _runs[g]; std::vector<Conn*>& live = _live[g];
         // one external block over the batch's pinned reply area, one per connection region: every reply is two references
         std::atomic<int>* outstanding = &_outstanding[g];
@@ -180,17 +186,23 @@ public:
             c->fill -= used;
         }
         _pop.clear();
+        _stats[g].deliver_s += mono_s() - t_wait1; _stats[g].batches++;
         return (int)res.n_msgs;
     }
+    // where a group's host thread spent its time: in b2_batch_submit, waiting in b2_batch_collect, delivering messages
+    struct GroupStats { double submit_s = 0, wait_s = 0, deliver_s = 0; uint64_t batches = 0; };
+    const GroupStats& stats(uint32_t g) const { return _stats[g]; }
     const std::vector<std::unique_ptr<Conn>>& connections() const { return _conns; }
     uint8_t* arena() const { return _arena; }
 
 private:
+    static double mono_s() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + (double)t.tv_nsec * 1e-9; }
     void Destroy() { for (b2_ctx* c : _ctx) b2_ctx_destroy(c); _ctx.clear(); if (_arena) { b2_block_free(_arena); _arena = nullptr; } }
     Options _opt; uint8_t* _arena = nullptr; size_t _arena_bytes = 0;
     std::vector<b2_ctx*> _ctx; std::vector<std::unique_ptr<Conn>> _conns; std::vector<std::vector<Conn*>> _groups;
     std::vector<char> _inflight; std::vector<std::vector<b2_run>> _runs; std::vector<std::vector<Conn*>> _live;
     std::vector<std::vector<struct iovec>> _iov; std::vector<std::vector<std::pair<Conn*, uint32_t>>> _pop;      // per group: groups may be driven by different threads
+    std::vector<GroupStats> _stats;
     std::unique_ptr<std::atomic<int>[]> _outstanding; Process _process = nullptr; ReplySink _sink;
 };
 

@@ -78,12 +78,13 @@ extern "C" {
 #define B2_MSG_STREAM_FRAME  4  /* streaming_rpc frame, meta decoded, host routes it */
 #define B2_MSG_BAD_STREAM_META 5 /* StreamFrameMeta failed to parse: frame dropped
                                    (streaming_rpc_protocol.cpp:97-100)              */
-#define B2_MSG_UNSUPPORTED   6  /* codec/content type outside this path (gzip, json) */
+#define B2_MSG_UNSUPPORTED   6  /* left to the host untouched: a non-pb content type (json ...), a reply the method wants gzip / zlib
+                                   COMPRESSED, or a gzip / zlib body beyond 1 MiB (compressed or inflated; one thread walks a DEFLATE stream) */
 #define B2_MSG_RESPONSE      7  /* client-side socket: a response was processed (ProcessRpcResponse,
                                    baidu_rpc_protocol.cpp:911-1013).  error_code = what Controller::SetFailed
                                    would get (0 = OK); resp_off/resp_len = the EchoResponse.message bytes,
                                    located in the BATCH buffer */
-#define B2_MSG_RESPONSE_UNZ  8  /* same, the response was snappy-compressed: message bytes are in the resp region */
+#define B2_MSG_RESPONSE_UNZ  8  /* same, the response was snappy / gzip / zlib compressed: message bytes are in the resp region */
 #define B2_MSG_REPLAY       10  /* a record of an rpc_dump file (B2_RUN_RPC_DUMP) re-packed as a baidu_std request frame: resp_off/resp_len;
                                    compress_type / attachment_size = the sample's; protocol = the sample's protocol_type (only baidu_std
                                    samples are re-packed, others are B2_MSG_UNSUPPORTED) */
@@ -349,6 +350,11 @@ int  b2_elapsed_ms(b2_ctx* a, b2_ctx* b, float* ms);
 /* What the last upload / launch decided: out[0] tile bytes, [1] tiles, [2] frame offsets kept per tile, [3] 1 = the fused
  * decode+pack kernel served the batch (0 = the slot-scan pipeline). */
 int  b2_batch_info(b2_ctx* ctx, uint32_t out[4]);
+
+/* PCI bus id ("0000:1b:00.0") of a device, for a host side that wants to run its polling threads and first-touch its pinned blocks on
+ * the CPUs next to the GPU (/sys/bus/pci/devices/<id>/local_cpulist): zero-copy reads that cross the socket interconnect lose most of
+ * their rate.  No ctx needed.  (brpc pins nothing itself; its RDMA endpoint leaves NUMA placement to the deployment as well.) */
+int  b2_device_pci_bus_id(int device, char* out, int cap);
 
 /* Device time of each stage of the last execute, in launch order.  Writes up to
  * `cap` entries of (name, ms); returns the number of stages. */

@@ -674,9 +674,15 @@ static int process_rpc_request(const orc_config* cfg, const uint8_t* frame, b2_m
         /* DeserializeRpcMessage :498-566 */
         int ok = 1;
         if (m.content_type != B2_CONTENT_TYPE_PB) { d->status = B2_MSG_UNSUPPORTED; return 0; }
-        /* scope decision: DEFLATE codecs and non-pb content types are outside
-         * this path; such requests are surfaced untouched, before any checksum work */
-        if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) { d->status = B2_MSG_UNSUPPORTED; return 0; }
+        /* scope decision: non-pb content types are outside this path; so are replies a method wants
+         * gzip / zlib COMPRESSED (bit-exact deflate is zlib-version specific) — such requests are surfaced untouched, before any checksum work */
+        if (mp->response_compress_type != B2_COMPRESS_TYPE_NONE && mp->response_compress_type != B2_COMPRESS_TYPE_SNAPPY) { d->status = B2_MSG_UNSUPPORTED; return 0; }
+        /* device limit (one thread walks a DEFLATE stream): big gzip / zlib bodies go to the host as they are */
+        if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) {
+            if (req_buf_len > ORC_GZ_MAX_IN) { d->status = B2_MSG_UNSUPPORTED; return 0; }
+            if (!(m.checksum_type == B2_CHECKSUM_TYPE_CRC32C && req_cks_len != 4) &&
+                orc_gzip_sizing_bound(req_buf, req_buf_len, m.compress_type, ORC_GZ_MAX_OUT) > ORC_GZ_MAX_OUT) { d->status = B2_MSG_UNSUPPORTED; return 0; }
+        }
         if (m.checksum_type == B2_CHECKSUM_TYPE_CRC32C) {                  /* Crc32cVerify, crc32c_checksum.cpp:44-61 */
             if (req_cks_len != 4) ok = 0;   /* reference CHECK_EQ-aborts here; treated as a failed verify */
             else {
@@ -698,6 +704,12 @@ static int process_rpc_request(const orc_config* cfg, const uint8_t* frame, b2_m
                     if (!g_sn_u((const char*)req_buf, req_buf_len, (char*)unz, ulen, &got)) ok = 0;
                     pb = unz; pb_len = got;
                 }
+            } else if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) {
+                /* GzipDecompress / ZlibDecompress(const IOBuf&, Message*), gzip_compress.cpp:75-89: the parser reads what the
+                 * GzipInputStream yields; a corrupt stream is end-of-input to it, not an error */
+                size_t got = 0;
+                if (orc_gzip_input_stream(req_buf, req_buf_len, m.compress_type, &unz, &got)) return -1;
+                pb = unz; pb_len = got;
             } else ok = 0;                                                   /* FindCompressHandler == NULL */
         }
         if (ok) ok = orc_parse_echo_request(pb, pb_len, &msg);
@@ -759,7 +771,12 @@ static int process_rpc_response(const uint8_t* frame, b2_msg_desc* d, uint8_t* r
         body_len = (size_t)bwo;
     }
     if (m.content_type != B2_CONTENT_TYPE_PB) { d->status = B2_MSG_UNSUPPORTED; return 0; }
-    if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) { d->status = B2_MSG_UNSUPPORTED; return 0; }
+    if (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB) {      /* device limit, as on the request side */
+        const size_t cl = (m.has & B2_HAS_CHECKSUM_VALUE) ? m.checksum_value.len : 0;
+        if (body_len > ORC_GZ_MAX_IN) { d->status = B2_MSG_UNSUPPORTED; return 0; }
+        if (!(m.checksum_type == B2_CHECKSUM_TYPE_CRC32C && cl != 4) &&
+            orc_gzip_sizing_bound(payload, body_len, m.compress_type, ORC_GZ_MAX_OUT) > ORC_GZ_MAX_OUT) { d->status = B2_MSG_UNSUPPORTED; return 0; }
+    }
     int ok = 1;
     const uint8_t* cks = meta_p + m.checksum_value.off; size_t cks_len = (m.has & B2_HAS_CHECKSUM_VALUE) ? m.checksum_value.len : 0;
     if (m.checksum_type == B2_CHECKSUM_TYPE_CRC32C) {
@@ -780,6 +797,13 @@ static int process_rpc_response(const uint8_t* frame, b2_msg_desc* d, uint8_t* r
         else if (!g_sn_u((const char*)payload, body_len, (char*)resp, ulen, &got)) ok = 0;
         else ok = orc_parse_echo_request(resp, got, &msg);
         if (ok) { d->status = B2_MSG_RESPONSE_UNZ; *resp_len = got; d->resp_len = msg.len; d->resp_off = msg.off; /* + slot, by caller */ }
+    } else if (ok && (m.compress_type == B2_COMPRESS_TYPE_GZIP || m.compress_type == B2_COMPRESS_TYPE_ZLIB)) {
+        uint8_t* u = NULL; size_t got = 0;                                                           /* gzip_compress.cpp:75-89 */
+        if (orc_gzip_input_stream(payload, body_len, m.compress_type, &u, &got)) return -1;
+        if (got > resp_cap) { free(u); return -1; }
+        memcpy(resp, u, got); free(u);
+        ok = orc_parse_echo_request(resp, got, &msg);
+        if (ok) { d->status = B2_MSG_RESPONSE_UNZ; *resp_len = got; d->resp_len = msg.len; d->resp_off = msg.off; }
     } else if (ok) ok = 0;                                                                           /* no such handler */
     if (!ok) { d->error_code = B2_EREQUEST; d->resp_off = 0; d->resp_len = 0; d->status = B2_MSG_RESPONSE; }   /* :999-1007 */
     return 0;

@@ -158,6 +158,15 @@ uint32_t orc_h2_consume(orc_h2_conn* c, const orc_config* cfg, const uint8_t* in
 uint32_t orc_h2_pack_response(orc_h2_conn* c, const b2_h2_response* r, const uint8_t* bytes, uint8_t* out);
 uint32_t orc_h2_scan(const uint8_t* in, uint32_t n, uint32_t max_frame_size, orc_h2_frame* frames, uint32_t cap,
                      uint32_t* consumed, uint32_t* err);
+/* What GzipInputStream(format = B2_COMPRESS_TYPE_GZIP | B2_COMPRESS_TYPE_ZLIB) over `in` (one block) yields before it reports
+ * end-of-stream (b2_oracle_gzip.c).  *out is malloc'ed; release with orc_free.  0, or -1 when out of memory. */
+int orc_gzip_input_stream(const uint8_t* in, size_t n, int format, uint8_t** out, size_t* out_len);
+void orc_free(void* p);
+/* the device's sizing pass over the same stream (no data checks): bound of the bytes handed over, limit + 1 when beyond `limit` */
+size_t orc_gzip_sizing_bound(const uint8_t* in, size_t n, int format, size_t limit);
+#define ORC_GZ_MAX_IN  (1u << 20)   /* b2_inflate.cuh kGzMaxIn / kGzMaxOut: larger bodies are left to the host (B2_MSG_UNSUPPORTED) */
+#define ORC_GZ_MAX_OUT (1u << 20)
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,19 @@ lib.orc_process_batch.argtypes = [C.POINTER(Config), C.c_void_p, C.c_uint32, C.c
 lib.orc_have_ref.restype = C.c_int
 
 
+lib.orc_gzip_input_stream.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+lib.orc_free.argtypes = [C.c_void_p]
+
+
+def gzip_input_stream(b, fmt):
+    """What GzipInputStream(fmt = 2 gzip | 3 zlib) hands to the parser for the body `b` (oracle/b2_oracle_gzip.c)."""
+    out = C.c_void_p(); n = C.c_size_t()
+    assert lib.orc_gzip_input_stream(bytes(b), len(b), fmt, C.byref(out), C.byref(n)) == 0
+    r = C.string_at(out, n.value)
+    lib.orc_free(out)
+    return r
+
+
 def crc32c(b, init=0):
     return lib.orc_crc32c_extend(init, bytes(b), len(b))
 

@@ -91,3 +91,47 @@ def split_runs(rng, streams, cut_tail=True):
             b = b[:len(b) - len(frames[-1]) + cut]
         chunks.append(b)
     return chunks
+
+
+# ---- hand-built baidu_std frames (any body bytes, any compress_type): what a peer using another codec puts on the wire ----
+def _varint(v):
+    v &= (1 << 64) - 1
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7f) | 0x80); v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def _fld(num, wt, payload):
+    return _varint((num << 3) | wt) + payload
+
+
+def echo_pb(message):
+    """EchoRequest / EchoResponse {message}"""
+    return _fld(1, 2, _varint(len(message)) + message)
+
+
+def raw_request_frame(body, correlation_id, compress_type=0, checksum_value=None, checksum_type=0, attachment=b"",
+                      service=b"example.EchoService", method=b"Echo", log_id=None):
+    """PackRpcRequest's frame (baidu_rpc_protocol.cpp:1045-1133) around an already serialized (compressed) body."""
+    req = _fld(1, 2, _varint(len(service)) + service) + _fld(2, 2, _varint(len(method)) + method)
+    if log_id is not None:
+        req += _fld(3, 0, _varint(log_id))
+    meta = _fld(1, 2, _varint(len(req)) + req) + _fld(3, 0, _varint(compress_type)) + _fld(4, 0, _varint(correlation_id))
+    if attachment:
+        meta += _fld(5, 0, _varint(len(attachment)))
+    meta += _fld(10, 0, _varint(0)) + _fld(11, 0, _varint(checksum_type))
+    meta += _fld(12, 2, _varint(len(checksum_value or b"")) + (checksum_value or b""))
+    return b"PRPC" + (len(meta) + len(body) + len(attachment)).to_bytes(4, "big") + len(meta).to_bytes(4, "big") + meta + body + attachment
+
+
+def raw_response_frame(body, correlation_id, compress_type=0, checksum_value=None, checksum_type=0, attachment=b""):
+    """SendRpcResponse's frame (baidu_rpc_protocol.cpp:339-352) around an already serialized (compressed) body."""
+    resp = _fld(1, 0, _varint(0))
+    meta = _fld(2, 2, _varint(len(resp)) + resp) + _fld(3, 0, _varint(compress_type)) + _fld(4, 0, _varint(correlation_id))
+    if attachment:
+        meta += _fld(5, 0, _varint(len(attachment)))
+    meta += _fld(10, 0, _varint(0)) + _fld(11, 0, _varint(checksum_type))
+    meta += _fld(12, 2, _varint(len(checksum_value or b"")) + (checksum_value or b""))
+    return b"PRPC" + (len(meta) + len(body) + len(attachment)).to_bytes(4, "big") + len(meta).to_bytes(4, "big") + meta + body + attachment

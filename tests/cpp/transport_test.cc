@@ -33,17 +33,22 @@ uint64_t b2press_fill_run(const b2press_spec* s, uint64_t* index, uint8_t* out, 
 }
 // run on (and first-touch pinned memory from) the CPUs next to the GPU: zero-copy PCIe reads that cross the socket interconnect lose most
 // of their rate (bench.py does the same through NVML)
-extern "C" int cudaDeviceGetPCIBusId(char*, int, int) __attribute__((weak));
+static std::vector<int> g_local_cpus;          // CPUs next to the GPU, in sysfs order (the first half of a socket's list = one hardware thread per core)
+static void pin_thread_to_local_cpu(int k) {
+    if (g_local_cpus.empty()) return;
+    cpu_set_t one; CPU_ZERO(&one); CPU_SET(g_local_cpus[(size_t)k % g_local_cpus.size()], &one);
+    sched_setaffinity(0, sizeof one, &one);
+}
 static void pin_to_gpu_numa(int device) {
     char bus[32] = {0};
-    if (!cudaDeviceGetPCIBusId || cudaDeviceGetPCIBusId(bus, sizeof bus, device) != 0) { fprintf(stderr, "(no NUMA pinning: cudart not linked)\n"); return; }
+    if (b2_device_pci_bus_id(device, bus, sizeof bus) != B2_OK) { fprintf(stderr, "(no NUMA pinning: bus id unknown)\n"); return; }
     for (char* p = bus; *p; p++) if (*p >= 'A' && *p <= 'Z') *p = (char)(*p - 'A' + 'a');
     char path[128]; snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
     FILE* f = fopen(path, "r"); if (!f) return;
     char list[512] = {0}; if (!fgets(list, sizeof list, f)) { fclose(f); return; } fclose(f);
     cpu_set_t set; CPU_ZERO(&set); int n = 0;
     for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
-        int a, b; if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b; c++) { CPU_SET(c, &set); n++; } } else if (sscanf(tok, "%d", &a) == 1) { CPU_SET(a, &set); n++; }
+        int a, b; if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b; c++) { CPU_SET(c, &set); g_local_cpus.push_back(c); n++; } } else if (sscanf(tok, "%d", &a) == 1) { CPU_SET(a, &set); g_local_cpus.push_back(a); n++; }
     }
     if (n) sched_setaffinity(0, sizeof set, &set);
     fprintf(stderr, "(pinned to %d CPUs next to GPU %d)\n", n, device);
@@ -160,7 +165,7 @@ static void test_transport_gpu(int input_mode, int resp_mode) {
     printf("transport ok (input=%d resp=%d): %d connections, %d messages in %d pipelined rounds, reply streams byte-identical to the oracle\n", input_mode, resp_mode, K, total, rounds);
 }
 
-static int bench(int run_mib, int rounds, int input_mode, int resp_mode, int groups) {
+static int bench(int run_mib, int rounds, int input_mode, int resp_mode, int groups, int per_thread) {
     const int K = 64;
     pin_to_gpu_numa(0);
     b2::GpuTransport::Options o; memset(&o.ctx, 0, sizeof o.ctx);
@@ -185,10 +190,13 @@ static int bench(int run_mib, int rounds, int input_mode, int resp_mode, int gro
         uint64_t idx = ((uint64_t)s << 32);
         b2press_fill_run(&sp, &idx, fresh[s].data(), run_bytes);
     }
-    std::vector<uint64_t> out_bytes(groups, 0), out_iov(groups, 0), msgs(groups, 0);
+    const bool no_write = getenv("B2_BENCH_NOWRITE") != nullptr;                       // (experiment: what the writev syscalls cost)
+    struct alignas(64) Tally { uint64_t bytes = 0, iov = 0, msgs = 0; };               // one cache line per group: the groups' threads share nothing
+    std::vector<Tally> tally(groups);
     tr.SetReplySink([&](b2::GpuTransport::Conn* c, const struct iovec* v, size_t n) {   // what KeepWrite does: one writev per <= 1024 references
-        for (size_t i = 0; i < n; i += 1024) { const ssize_t w = writev(c->fd, v + i, (int)std::min<size_t>(1024, n - i)); if (w > 0) out_bytes[c->group] += (uint64_t)w; }
-        out_iov[c->group] += n;
+        Tally& t = tally[c->group];
+        if (!no_write) for (size_t i = 0; i < n; i += 1024) { const ssize_t w = writev(c->fd, v + i, (int)std::min<size_t>(1024, n - i)); if (w > 0) t.bytes += (uint64_t)w; }
+        t.iov += n;
     });
     auto refill = [&](uint32_t g) { for (int s = 0; s < K; s++) if (conns[s]->group == g) { conns[s]->fill = 0; tr.Feed(conns[s], fresh[s].data(), run_bytes); } };
     // warm-up; it also tells where each connection's last complete frame ends: the timed rounds submit exactly that much, so nothing is
@@ -202,21 +210,24 @@ static int bench(int run_mib, int rounds, int input_mode, int resp_mode, int gro
     // batch is on the GPU — transfers, kernels and host work overlap inside a thread as well as across threads
     const double t0 = now_s();
     std::vector<std::thread> th;
-    for (int g0 = 0; g0 < groups; g0 += 2) th.emplace_back([&, g0]() {
-        const int g1 = g0 + 1 < groups ? g0 + 1 : -1;
+    for (int g0 = 0; g0 < groups; g0 += per_thread) th.emplace_back([&, g0]() {
+        const int g1 = (per_thread == 2 && g0 + 1 < groups) ? g0 + 1 : -1;
+        if (!getenv("B2_BENCH_NOPIN")) pin_thread_to_local_cpu(1 + g0 / per_thread);     // one core per delivering thread
         arm(g0); CHECK(tr.Submit(g0) > 0);
         for (int r = 0; r < rounds; r++) {
             if (g1 >= 0) { arm(g1); CHECK(tr.Submit(g1) > 0); }
-            int c = tr.Collect(g0); CHECK(c > 0); msgs[g0] += (uint64_t)c;
+            int c = tr.Collect(g0); CHECK(c > 0); tally[g0].msgs += (uint64_t)c;
             if (r + 1 < rounds) { arm(g0); CHECK(tr.Submit(g0) > 0); }
-            if (g1 >= 0) { c = tr.Collect(g1); CHECK(c > 0); msgs[g1] += (uint64_t)c; }
+            if (g1 >= 0) { c = tr.Collect(g1); CHECK(c > 0); tally[g1].msgs += (uint64_t)c; }
         }
     });
     for (auto& t : th) t.join();
     const double dt = now_s() - t0;
-    uint64_t tm = 0, tb = 0, ti = 0; for (int g = 0; g < groups; g++) { tm += msgs[g]; tb += out_bytes[g]; ti += out_iov[g]; }
+    uint64_t tm = 0, tb = 0, ti = 0; for (int g = 0; g < groups; g++) { tm += tally[g].msgs; tb += tally[g].bytes; ti += tally[g].iov; }
+    double ws = 0, ds = 0, ss = 0; for (int g = 0; g < groups; g++) { ws += tr.stats(g).wait_s; ds += tr.stats(g).deliver_s; ss += tr.stats(g).submit_s; }
+    fprintf(stderr, "(per group over the whole run incl. warm-up: submit %.1f ms, wait %.1f ms, deliver %.1f ms)\n", ss / groups * 1e3, ws / groups * 1e3, ds / groups * 1e3);
     printf("{\"via\": \"b2::GpuTransport (C++)\", \"msgs_per_s\": %.1f, \"rounds_per_group\": %d, \"groups\": %d, \"host_threads\": %d, \"connections\": %d, \"run_mib\": %d, \"input_mode\": %d, \"resp_mode\": %d, "
-           "\"reply_bytes_written\": %llu, \"iovecs\": %llu, \"seconds\": %.4f}\n", tm / dt, rounds, groups, (groups + 1) / 2, K, run_mib, input_mode, resp_mode,
+           "\"reply_bytes_written\": %llu, \"iovecs\": %llu, \"seconds\": %.4f}\n", tm / dt, rounds, groups, (groups + per_thread - 1) / per_thread, K, run_mib, input_mode, resp_mode,
            (unsigned long long)tb, (unsigned long long)ti, dt);
     close(devnull);
     return 0;
@@ -227,6 +238,6 @@ int main(int argc, char** argv) {
     const std::string mode = argc > 1 ? argv[1] : "queue";
     if (mode == "queue") { test_write_queue(); return 0; }
     if (mode == "gpu") { test_transport_gpu(B2_INPUT_PULL, B2_RESP_BY_REF); test_transport_gpu(B2_INPUT_COPY, B2_RESP_COPY); test_transport_gpu(B2_INPUT_COPY, B2_RESP_BY_REF); return 0; }
-    if (mode == "bench") return bench(argc > 2 ? atoi(argv[2]) : 4, argc > 3 ? atoi(argv[3]) : 20, argc > 4 ? atoi(argv[4]) : B2_INPUT_PULL, argc > 5 ? atoi(argv[5]) : B2_RESP_BY_REF, argc > 6 ? atoi(argv[6]) : 4);
+    if (mode == "bench") return bench(argc > 2 ? atoi(argv[2]) : 4, argc > 3 ? atoi(argv[3]) : 20, argc > 4 ? atoi(argv[4]) : B2_INPUT_PULL, argc > 5 ? atoi(argv[5]) : B2_RESP_BY_REF, argc > 6 ? atoi(argv[6]) : 4, argc > 7 && atoi(argv[7]) == 1 ? 1 : 2);
     fprintf(stderr, "usage: transport_test queue|gpu|bench\n"); return 2;
 }
