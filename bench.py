@@ -797,14 +797,15 @@ def main():
                 "value_by_wall_clock": total_msgs * ppass * steps / (wall_ms_max * 1e-3), "msgs_per_step": total_msgs * ppass,
                 "counters_allreduced": counters}
         if not use_dist:
-            # the same e2e through the C++ host side a brpc transport would run (b2::GpuTransport: registered read regions, three
-            # batches in flight, pull + by-reference replies gathered by writev into /dev/null; tests/cpp/transport_test.cc bench)
+            # the same e2e through the C++ host side a brpc transport would run (b2::GpuTransport: registered read regions, 8 groups of
+            # connections = 8 batches in flight driven by 4 host threads, B2_INPUT_PULL + B2_RESP_IOVEC: the device writes the gather list
+            # and every connection's replies leave through writev (into /dev/null) as they stand; tests/cpp/transport_test.cc bench)
             tb = os.path.join(ROOT, "tests", "cpp", "transport_test")
             if os.path.exists(tb):
                 try:
                     for cx in ctxs:
                         cx.close()
-                    out = subprocess.run([tb, "bench", str(args.run_mib), "40", "1", "1", "8"], capture_output=True, text=True, timeout=120)
+                    out = subprocess.run([tb, "bench", str(args.run_mib), "40", "1", "2", "8", "2"], capture_output=True, text=True, timeout=120)
                     line["e2e_messenger"] = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else {"error": (out.stderr or out.stdout)[-300:]}
                 except Exception as e:      # noqa: BLE001
                     line["e2e_messenger"] = {"error": repr(e)}

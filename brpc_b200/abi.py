@@ -12,7 +12,7 @@ B2_OK, B2_E_INVAL, B2_E_NO_DEVICE, B2_E_CUDA, B2_E_CAPACITY, B2_E_NOMEM = 0, -1,
 RUN_DT = np.dtype([("socket_id", "<u8"), ("offset", "<u4"), ("length", "<u4"),
                    ("preferred_proto", "<i4"), ("flags", "<u4")])
 RUN_STATUS_DT = np.dtype([("consumed", "<u4"), ("parse_error", "<u4"), ("n_msgs", "<u4"), ("first_msg", "<u4"),
-                          ("preferred_proto", "<i4"), ("reserved0", "<u4"), ("resp_off", "<u4"), ("resp_bytes", "<u4")])
+                          ("preferred_proto", "<i4"), ("n_unanswered", "<u4"), ("resp_off", "<u4"), ("resp_bytes", "<u4")])
 H2_FRAME_DT = np.dtype([("type", "u1"), ("flags", "u1"), ("pad", "<u2"), ("stream_id", "<u4"), ("payload_off", "<u4"), ("payload_len", "<u4")])
 HPACK_BLOCK_DT = np.dtype([("conn", "<u4"), ("offset", "<u4"), ("length", "<u4"), ("reserved", "<u4")])
 H2_RUN_STATUS_DT = np.dtype([("consumed", "<u4"), ("parse_error", "<u4"), ("n_msgs", "<u4"), ("first_msg", "<u4"), ("ctrl_off", "<u4"), ("ctrl_len", "<u4"),
@@ -20,6 +20,11 @@ H2_RUN_STATUS_DT = np.dtype([("consumed", "<u4"), ("parse_error", "<u4"), ("n_ms
 REQUEST_DT = np.dtype([("kind", "<u4"), ("flags", "<u4"), ("method_idx", "<i4"), ("timeout_ms", "<i4"), ("correlation_id", "<i8"), ("log_id", "<i8"),
                        ("compress_type", "<i4"), ("checksum_type", "<i4"), ("frame_type", "<i4"), ("payload_off", "<u4"), ("payload_len", "<u4"),
                        ("attachment_off", "<u4"), ("attachment_len", "<u4"), ("reserved", "<u4")])
+REPLY_DT = np.dtype([("flags", "<u4"), ("error_code", "<i4"), ("correlation_id", "<i8"), ("compress_type", "<i4"), ("checksum_type", "<i4"),
+                     ("content_type", "<i4"), ("error_text_off", "<u4"), ("error_text_len", "<u4"), ("body_off", "<u4"), ("body_len", "<u4"),
+                     ("attachment_off", "<u4"), ("attachment_len", "<u4"), ("checksum_value_off", "<u4"), ("checksum_value_len", "<u4"),
+                     ("extra_streams_off", "<u4"), ("n_extra_streams", "<u4"), ("user_fields_off", "<u4"), ("n_user_fields", "<u4"),
+                     ("reserved", "<u4"), ("stream_id", "<i8")])          # == b2_reply, 88 bytes
 H2_RESPONSE_DT = np.dtype([("conn", "<u4"), ("stream_id", "<u4"), ("status_code", "<i4"), ("flags", "<u4"), ("content_type_off", "<u4"),
                            ("content_type_len", "<u4"), ("body_off", "<u4"), ("body_len", "<u4"), ("grpc_status", "<i4"),
                            ("grpc_message_off", "<u4"), ("grpc_message_len", "<u4"), ("reserved", "<u4")])
@@ -50,11 +55,12 @@ class BatchResult(C.Structure):
     _fields_ = [("runs", C.c_void_p), ("n_runs", C.c_uint32),
                 ("msgs", C.c_void_p), ("n_msgs", C.c_uint32),
                 ("resp", C.c_void_p), ("resp_bytes", C.c_uint32),
-                ("kernel_ms", C.c_float), ("n_launches", C.c_uint32), ("refs", C.c_void_p)]
+                ("kernel_ms", C.c_float), ("n_launches", C.c_uint32), ("refs", C.c_void_p), ("iov", C.c_void_p)]
 
 
 REF_DT = np.dtype([("prefix_len", "<u4"), ("src_off", "<u4"), ("src_len", "<u4"), ("reserved", "<u4")])
-INPUT_COPY, INPUT_PULL, RESP_COPY, RESP_BY_REF = 0, 1, 0, 1
+IOVEC_DT = np.dtype([("base", "<u8"), ("len", "<u8")])          # struct iovec
+INPUT_COPY, INPUT_PULL, RESP_COPY, RESP_BY_REF, RESP_IOVEC = 0, 1, 0, 1, 2
 
 
 class B2Error(RuntimeError):
@@ -120,6 +126,7 @@ def _load():
                                       C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32]
     l.b2_h2_pack_responses.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     l.b2_pack_requests.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    l.b2_pack_responses.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     l.b2_counters_read.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     l.b2_counters_device_ptr.restype = C.c_void_p; l.b2_counters_device_ptr.argtypes = [C.c_void_p]
     return l
@@ -131,7 +138,7 @@ lib = _load()
 ABI_SYMBOLS = ["b2_ctx_create", "b2_ctx_destroy", "b2_last_error", "b2_version", "b2_register_method",
                "b2_set_server_identity", "b2_set_stream_handler", "b2_set_protocols", "b2_block_alloc", "b2_block_free", "b2_block_pool_host_allocs", "b2_set_modes", "b2_ring_start", "b2_ring_stop", "b2_ring_submit", "b2_ring_wait", "b2_ring_launches", "b2_ring_phase_ns", "b2_latency_probe", "b2_process_batch", "b2_batch_submit", "b2_batch_collect", "b2_batch_upload",
                "b2_batch_execute", "b2_batch_execute_many", "b2_batch_download", "b2_batch_launch", "b2_batch_wait",
-               "b2_elapsed_ms", "b2_batch_info", "b2_device_pci_bus_id", "b2_stage_times", "b2_crc32c_batch", "b2_crc32c_extend", "b2_snappy_max_compressed_length", "b2_snappy_raw_compress", "b2_snappy_get_uncompressed_length", "b2_snappy_raw_uncompress", "b2_snappy_uncompress_batch", "b2_snappy_compress_batch", "b2_hpack_reset", "b2_hpack_decode_batch", "b2_pack_requests", "b2_h2_scan_batch", "b2_h2_conn_reset", "b2_h2_configure", "b2_h2_process_batch", "b2_h2_pack_responses", "b2_counters_read",
+               "b2_elapsed_ms", "b2_batch_info", "b2_device_pci_bus_id", "b2_stage_times", "b2_crc32c_batch", "b2_crc32c_extend", "b2_snappy_max_compressed_length", "b2_snappy_raw_compress", "b2_snappy_get_uncompressed_length", "b2_snappy_raw_uncompress", "b2_snappy_uncompress_batch", "b2_snappy_compress_batch", "b2_hpack_reset", "b2_hpack_decode_batch", "b2_pack_requests", "b2_pack_responses", "b2_h2_scan_batch", "b2_h2_conn_reset", "b2_h2_configure", "b2_h2_process_batch", "b2_h2_pack_responses", "b2_counters_read",
                "b2_counters_device_ptr"]
 
 ECHO_METHOD = dict(service_full_name=b"example.EchoService", service_name=b"EchoService", method_name=b"Echo",
@@ -215,7 +222,10 @@ class Context:
         refs = None
         if res.refs and res.n_msgs:
             refs = np.ctypeslib.as_array((C.c_uint8 * (16 * res.n_msgs)).from_address(res.refs)).view(REF_DT)
-        return {"kernel_ms": res.kernel_ms, "n_launches": res.n_launches, "refs": refs}
+        iov = None
+        if res.iov and res.n_msgs:
+            iov = np.ctypeslib.as_array((C.c_uint8 * (32 * res.n_msgs)).from_address(res.iov)).view(IOVEC_DT)
+        return {"kernel_ms": res.kernel_ms, "n_launches": res.n_launches, "refs": refs, "iov": iov}
 
     # ---- the persistent latency kernel (b2_ring_*) ----
     def ring_start(self):
@@ -437,6 +447,15 @@ class Context:
         out_cap = out_cap or int((reqs["payload_len"].astype(np.int64) * 7 // 6 + reqs["attachment_len"] + 640).sum() + 4096)
         out = np.empty(out_cap, np.uint8); offs = np.zeros(n, np.uint32); lens = np.zeros(n, np.uint32)
         _check(lib.b2_pack_requests(self._h, data.ctypes.data, data.nbytes, reqs.ctypes.data, n, out.ctypes.data, out_cap, offs.ctypes.data, lens.ctypes.data))
+        return [out[offs[i]:offs[i] + lens[i]].tobytes() for i in range(n)]
+
+    def pack_responses(self, data, replies, out_cap=None):
+        """replies: REPLY_DT array (offsets into data).  Returns the frame of every reply (b"" = not packable)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8); replies = np.ascontiguousarray(replies, dtype=REPLY_DT)
+        n = len(replies)
+        out_cap = out_cap or int((replies["body_len"].astype(np.int64) * 7 // 6 + replies["attachment_len"] + replies["error_text_len"] + 1024).sum() + data.nbytes + 4096)
+        out = np.empty(out_cap, np.uint8); offs = np.zeros(n, np.uint32); lens = np.zeros(n, np.uint32)
+        _check(lib.b2_pack_responses(self._h, data.ctypes.data, data.nbytes, replies.ctypes.data, n, out.ctypes.data, out_cap, offs.ctypes.data, lens.ctypes.data))
         return [out[offs[i]:offs[i] + lens[i]].tobytes() for i in range(n)]
 
     def counters(self):

@@ -46,6 +46,7 @@ struct b2_ctx {
     uint8_t* ring_slots = nullptr; volatile uint32_t* ring_ctl = nullptr; uint32_t* d_ring_ticket = nullptr; cudaStream_t ring_stream = nullptr;
     uint32_t ring_next = 1, ring_stride = 0, ring_off_runs = 0, ring_off_in = 0, ring_off_out = 0; bool ring_collected[8] = { true, true, true, true, true, true, true, true };
     const void* ring_bytes[8] = {}; const void* ring_pin_base = nullptr; unsigned long long ring_pin_dev = 0; uint64_t ring_launches = 0;
+    ulonglong2* d_iov = nullptr; b2_iovec* h_iov = nullptr; const void* host_bytes = nullptr;      // B2_RESP_IOVEC
     uint4* d_refs = nullptr; b2_resp_ref* h_refs = nullptr; int input_mode = B2_INPUT_COPY, resp_mode = B2_RESP_COPY; const uint8_t* pull_bytes = nullptr; uint32_t small_off_refs = 0;
     uint32_t* d_crc_adv = nullptr; unsigned long long* d_counters = nullptr; uint32_t* d_totals = nullptr; DevMethod* d_methods = nullptr;
     size_t meta_tile_off = 0; uint32_t max_tiles = 0; uint32_t n_sms = 148; bool use_tma_pack = true; uint32_t stage_mask = 7;  // debug: 1 front stages, 2 k_pack_tma, 4 k_pack_slow
@@ -142,7 +143,7 @@ extern "C" void b2_ctx_destroy(b2_ctx* c) {
     cudaFree(c->d_ring_ticket);
     cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch); cudaFree(c->d_tile_spec);
     cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_frame_run); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_slow_idx); cudaFree(c->d_heads); cudaFree(c->d_slot);
-    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_refs); cudaFree(c->d_frame_row); cudaFree(c->d_rows); cudaFreeHost(c->h_refs); cudaFree(c->d_hpack); cudaFree(c->d_h2); cudaFree(c->d_h2_streams); cudaFree(c->d_h2_slots); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
+    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_refs); cudaFree(c->d_iov); cudaFreeHost(c->h_iov); cudaFree(c->d_frame_row); cudaFree(c->d_rows); cudaFreeHost(c->h_refs); cudaFree(c->d_hpack); cudaFree(c->d_h2); cudaFree(c->d_h2_streams); cudaFree(c->d_h2_slots); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
     cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
     cudaFreeHost(c->h_run_tile_base);
     for (int i = 0; i <= kMaxStages; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -264,8 +265,15 @@ extern "C" int b2_set_server_identity(b2_ctx* c, const char* ip_port) {
 }
 
 extern "C" int b2_set_modes(b2_ctx* c, int input_mode, int resp_mode) {
-    if (!c || (input_mode != B2_INPUT_COPY && input_mode != B2_INPUT_PULL) || (resp_mode != B2_RESP_COPY && resp_mode != B2_RESP_BY_REF)) { set_err("bad mode"); return B2_E_INVAL; }
+    if (!c || (input_mode != B2_INPUT_COPY && input_mode != B2_INPUT_PULL) || (resp_mode != B2_RESP_COPY && resp_mode != B2_RESP_BY_REF && resp_mode != B2_RESP_IOVEC)) { set_err("bad mode"); return B2_E_INVAL; }
     static_assert(sizeof(b2_resp_ref) == sizeof(uint4), "b2_resp_ref is 16 bytes");
+    static_assert(sizeof(b2_iovec) == sizeof(ulonglong2) && sizeof(void*) == 8, "b2_iovec is a 16-byte struct iovec");
+    if (resp_mode == B2_RESP_IOVEC && !c->d_iov) {
+        CU(cudaSetDevice(c->opt.device));
+        if (cudaMalloc((void**)&c->d_iov, 32 * (size_t)c->opt.max_msgs) != cudaSuccess || cudaHostAlloc((void**)&c->h_iov, 32 * (size_t)c->opt.max_msgs, cudaHostAllocDefault) != cudaSuccess) {
+            cudaFree(c->d_iov); c->d_iov = nullptr; cudaGetLastError(); set_err("allocation of the iovec list failed"); return B2_E_NOMEM;
+        }
+    }
     if (input_mode == B2_INPUT_PULL && !c->d_rows) {
         // row stash of the pull walk: spec_k rows of 128 bytes per tile (tiles are >= 32 KiB in this mode unless the caller fixed them)
         CU(cudaSetDevice(c->opt.device));
@@ -277,7 +285,7 @@ extern "C" int b2_set_modes(b2_ctx* c, int input_mode, int resp_mode) {
         }
     }
     ring_halt(c);
-    c->input_mode = input_mode; c->resp_mode = resp_mode; c->cfg.by_ref = resp_mode == B2_RESP_BY_REF; c->cfg.pull = input_mode == B2_INPUT_PULL; c->cfg.pull_vecs = resp_mode == B2_RESP_BY_REF ? 6u : 8u;
+    c->input_mode = input_mode; c->resp_mode = resp_mode; c->cfg.by_ref = resp_mode != B2_RESP_COPY; c->cfg.pull = input_mode == B2_INPUT_PULL; c->cfg.pull_vecs = resp_mode != B2_RESP_COPY ? 6u : 8u;
     c->uploaded = false; c->executed = false;
     return B2_OK;
 }
@@ -373,7 +381,7 @@ extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, co
     }
     c->h_run_tile_base[n_runs] = (uint32_t)nt;
     if (nt > c->max_tiles) { set_err("too many tiles"); return B2_E_CAPACITY; }
-    c->n_runs = n_runs; c->n_tiles = (uint32_t)nt; c->nbytes = nbytes; c->max_run_tiles = max_rt;
+    c->n_runs = n_runs; c->n_tiles = (uint32_t)nt; c->nbytes = nbytes; c->max_run_tiles = max_rt; c->host_bytes = bytes;
     // runs + tile bases travel as one compact block (24 B * n is 4-byte aligned)
     const size_t tile_off = ((size_t)n_runs * sizeof(b2_run) + 4 * ((size_t)n_runs + 1) + 15) & ~(size_t)15;
     const size_t meta_bytes = tile_off + 16 * (size_t)nt;
@@ -475,6 +483,10 @@ static int launch_pipeline(b2_ctx* c) {
             launches++; mark("pack");
         }
     } else { k_pack<<<sms * B2_PACK_MIN_BLOCKS, 256, 0, s>>>(B, C); launches++; mark("pack"); }
+    if (c->resp_mode == B2_RESP_IOVEC && !c->small) {
+        k_emit_iov<<<sms * 4, 256, 0, s>>>(B, c->d_iov, (unsigned long long)(uintptr_t)c->h_resp, (unsigned long long)(uintptr_t)c->host_bytes);
+        launches++; mark("emit_iov");
+    }
     if (!prof) { c->stage_names[0] = "pipeline"; cudaEventRecord(c->ev[1], s); st = 1; }
     c->n_stages = st; c->last_launches = launches;
     CU(cudaGetLastError());
@@ -545,6 +557,23 @@ extern "C" int b2_elapsed_ms(b2_ctx* a, b2_ctx* b, float* ms) {
     return B2_OK;
 }
 
+// B2_RESP_IOVEC on the latency path (a handful of messages in one compact block): the list is built here from the refs that came back
+static void refs_to_iov(b2_ctx* c, b2_batch_result* out, const void* host_bytes) {
+    b2_run_status* rs = const_cast<b2_run_status*>(out->runs);
+    for (uint32_t r = 0; r < out->n_runs; r++) rs[r].n_unanswered = 0;
+    for (uint32_t i = 0; i < out->n_msgs; i++) {
+        const b2_msg_desc& d = out->msgs[i];
+        b2_iovec a = { const_cast<uint8_t*>(out->resp), 0 }, b = a;
+        if (d.status == B2_MSG_ECHOED || d.status == B2_MSG_ERROR_REPLIED) {
+            const b2_resp_ref rf = d.status == B2_MSG_ECHOED ? out->refs[i] : b2_resp_ref{0, 0, 0, 0};
+            a.iov_base = const_cast<uint8_t*>(out->resp) + d.resp_off; a.iov_len = rf.src_len ? rf.prefix_len : d.resp_len;
+            if (rf.src_len) { b.iov_base = const_cast<uint8_t*>(static_cast<const uint8_t*>(host_bytes)) + rf.src_off; b.iov_len = rf.src_len; }
+        } else rs[d.run_idx].n_unanswered++;
+        c->h_iov[2 * (size_t)i] = a; c->h_iov[2 * (size_t)i + 1] = b;
+    }
+    out->iov = c->h_iov; out->refs = nullptr;
+}
+
 static int download_normal(b2_ctx* c, b2_batch_result* out) {
     CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 32, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -569,9 +598,12 @@ static int download_normal(b2_ctx* c, b2_batch_result* out) {
     if (c->n_runs) CU(cudaMemcpyAsync(c->h_run_status, c->d_run_status, sizeof(b2_run_status) * c->n_runs, cudaMemcpyDeviceToHost, c->stream));
     if (n_msgs) CU(cudaMemcpyAsync(c->h_msgs, c->d_msgs, sizeof(b2_msg_desc) * (size_t)n_msgs, cudaMemcpyDeviceToHost, c->stream));
     if (resp_bytes) CU(cudaMemcpyAsync(c->h_resp, c->d_resp, resp_bytes, cudaMemcpyDeviceToHost, c->stream));
-    if (n_msgs && c->cfg.by_ref) CU(cudaMemcpyAsync(c->h_refs, c->d_refs, sizeof(b2_resp_ref) * (size_t)n_msgs, cudaMemcpyDeviceToHost, c->stream));
+    const bool iovec = c->resp_mode == B2_RESP_IOVEC;
+    if (n_msgs && c->cfg.by_ref && !iovec) CU(cudaMemcpyAsync(c->h_refs, c->d_refs, sizeof(b2_resp_ref) * (size_t)n_msgs, cudaMemcpyDeviceToHost, c->stream));
+    if (n_msgs && iovec) CU(cudaMemcpyAsync(c->h_iov, c->d_iov, 32 * (size_t)n_msgs, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    out->refs = c->cfg.by_ref ? c->h_refs : nullptr;
+    out->refs = c->cfg.by_ref && !iovec ? c->h_refs : nullptr;
+    out->iov = iovec ? c->h_iov : nullptr;
     out->runs = c->h_run_status; out->n_runs = c->n_runs;
     out->msgs = c->h_msgs; out->n_msgs = n_msgs;
     out->resp = c->h_resp; out->resp_bytes = resp_bytes;
@@ -599,6 +631,7 @@ extern "C" int b2_batch_download(b2_ctx* c, b2_batch_result* out) {
             out->msgs = reinterpret_cast<const b2_msg_desc*>(c->h_small + c->small_off_msgs); out->n_msgs = tot[0];
             out->resp = c->h_small + c->small_off_resp; out->resp_bytes = tot[1];
             out->refs = c->cfg.by_ref ? reinterpret_cast<const b2_resp_ref*>(c->h_small + c->small_off_refs) : nullptr;
+            if (c->resp_mode == B2_RESP_IOVEC) refs_to_iov(c, out, c->host_bytes);
         }
     } else {
         int rc = download_normal(c, out);
@@ -752,6 +785,7 @@ extern "C" int b2_ring_wait(b2_ctx* c, uint32_t ticket, b2_batch_result* out) {
     out->msgs = reinterpret_cast<const b2_msg_desc*>(ob + h->off_msgs); out->n_msgs = tot[0];
     out->resp = ob + h->off_resp; out->resp_bytes = tot[1];
     out->refs = h->by_ref ? reinterpret_cast<const b2_resp_ref*>(ob + h->off_refs) : nullptr;
+    if (c->resp_mode == B2_RESP_IOVEC) refs_to_iov(c, out, c->ring_bytes[si]);
     out->n_launches = 0; out->kernel_ms = 0.f;
     if (out->n_msgs) { const uint32_t now = h->nbytes / out->n_msgs; c->avg_frame = c->avg_frame ? (uint32_t)(((uint64_t)c->avg_frame * 3 + now) / 4) : now; }
     return B2_OK;
@@ -1210,6 +1244,47 @@ extern "C" int b2_pack_requests(b2_ctx* c, const void* bytes, uint32_t nbytes, c
     CU(cudaMemcpyAsync(d_reqs, reqs, sizeof(b2_request) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(d_offs, out_offs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     k_pack_requests<<<c->n_sms * 4, 256, 0, c->stream>>>(c->d_bytes, d_reqs, n, c->d_methods, c->cfg.n_methods, c->d_resp, d_offs, d_lens, c->d_unz, c->d_snappy_tab, c->d_crc_adv);
+    CU(cudaMemcpyAsync(out_lens, d_lens, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out, c->d_resp, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->uploaded = false; c->executed = false;
+    return B2_OK;
+}
+
+// SendRpcResponse for replies the host produced: see include/b2rpc.h
+extern "C" int b2_pack_responses(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_reply* reps, uint32_t n,
+                                 void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens) {
+    if (!c || (!bytes && nbytes) || !reps || !out || !out_offs || !out_lens) { set_err("null argument"); return B2_E_INVAL; }
+    static_assert(sizeof(b2_reply) == 88 && sizeof(ReplyDesc) == 88, "reply ABI layout");
+    if (nbytes > c->opt.max_batch_bytes || (uint64_t)n * sizeof(b2_reply) > (uint64_t)c->opt.max_msgs * 64 || out_cap > c->opt.max_resp_bytes) { set_err("exceeds ctx capacity"); return B2_E_CAPACITY; }
+    if (n == 0) return B2_OK;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const b2_reply& r = reps[i];
+        if ((uint64_t)r.body_off + r.body_len > nbytes || (uint64_t)r.attachment_off + r.attachment_len > nbytes || (uint64_t)r.error_text_off + r.error_text_len > nbytes ||
+            (uint64_t)r.checksum_value_off + r.checksum_value_len > nbytes || (r.extra_streams_off & 7u) || (uint64_t)r.extra_streams_off + 8ull * r.n_extra_streams > nbytes ||
+            r.user_fields_off > nbytes) { set_err("reply field outside buffer"); return B2_E_INVAL; }
+        uint64_t uf = 0, at = r.user_fields_off;                       // every record must lie inside the buffer: the kernel walks them
+        for (uint32_t k = 0; k < r.n_user_fields; k++) {
+            if (at + 8 > nbytes) { set_err("user field outside buffer"); return B2_E_INVAL; }
+            uint32_t kl, vl; memcpy(&kl, static_cast<const uint8_t*>(bytes) + at, 4); memcpy(&vl, static_cast<const uint8_t*>(bytes) + at + 4, 4);
+            if (at + 8 + (uint64_t)kl + vl > nbytes) { set_err("user field outside buffer"); return B2_E_INVAL; }
+            uf += 24ull + kl + vl; at += 8ull + kl + vl;
+        }
+        const uint64_t body = r.compress_type == B2_COMPRESS_TYPE_SNAPPY ? snappy_max_compressed_length(r.body_len) : r.body_len;
+        const uint64_t need = 12 + 128 + r.error_text_len + r.checksum_value_len + 11ull * r.n_extra_streams + uf + body + r.attachment_len;
+        out_offs[i] = (uint32_t)total;
+        total = (total + need + 15) & ~15ull;
+        if (total > out_cap) { set_err("out_cap too small"); return B2_E_CAPACITY; }
+    }
+    CU(cudaSetDevice(c->opt.device));
+    ReplyDesc* d_reps = reinterpret_cast<ReplyDesc*>(c->d_msgs);
+    uint32_t* d_offs = c->d_frame_off; uint32_t* d_lens = c->d_slot;
+    c->h2_last_in = 0; c->h2_last_out = 0;
+    if (nbytes) CU(cudaMemcpyAsync(c->d_bytes, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_reps, reps, sizeof(b2_reply) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_offs, out_offs, 4 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    k_pack_responses<<<c->n_sms * 4, 256, 0, c->stream>>>(c->d_bytes, d_reps, n, c->d_resp, d_offs, d_lens, c->d_unz, c->d_snappy_tab, c->d_crc_adv);
     CU(cudaMemcpyAsync(out_lens, d_lens, 4 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(out, c->d_resp, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C, uint3
         const Step s = cut_input_message(base, len, pos, pf_true, C.max_body_size, (run.flags & B2_RUN_CLIENT) != 0, run_mask(C.proto_mask, run.flags));
         b2_run_status st;
         st.consumed = s.new_pos; st.parse_error = (uint32_t)s.err; st.n_msgs = s_carry_sum; st.first_msg = 0;
-        st.preferred_proto = s.pf; st.reserved0 = 0; st.resp_off = 0; st.resp_bytes = 0;
+        st.preferred_proto = s.pf; st.n_unanswered = 0; st.resp_off = 0; st.resp_bytes = 0;
         B.run_status[r] = st;
     }
     // the last CTA to get here turns the per-run counts into first_msg (was a separate launch)
@@ -2379,6 +2379,123 @@ __global__ void __launch_bounds__(256) k_pack_requests(const uint8_t* bytes, con
     }
 }
 
+// --- k_emit_iov: B2_RESP_IOVEC -------------------------------------------------------------------------------------------------
+// The gather list of the write, with host addresses: what IOBuf::cut_multiple_into_file_descriptor (butil/iobuf.cpp:954-992) builds from
+// the block references of queued replies.  Thread per message, after the pack kernels fixed every resp_off.
+__global__ void __launch_bounds__(256) k_emit_iov(BatchPtrs B, ulonglong2* iov, unsigned long long resp_base, unsigned long long bytes_base) {
+    if (B.totals[2] & 3u) return;
+    const uint32_t n = B.totals[0];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const b2_msg_desc* d = B.msgs + i;
+        const uint32_t status = d->status;
+        ulonglong2 a = make_ulonglong2(resp_base, 0ull), b = a;
+        if (status == B2_MSG_ECHOED || status == B2_MSG_ERROR_REPLIED) {
+            const uint4 rf = status == B2_MSG_ECHOED ? B.refs[i] : make_uint4(0, 0, 0, 0);
+            a = make_ulonglong2(resp_base + d->resp_off, rf.z ? rf.x : d->resp_len);
+            if (rf.z) b = make_ulonglong2(bytes_base + rf.y, rf.z);
+        } else atomicAdd(&B.run_status[d->run_idx].n_unanswered, 1u);
+        iov[2 * (size_t)i] = a; iov[2 * (size_t)i + 1] = b;
+    }
+}
+
+// --- k_pack_responses: SendRpcResponse (policy/baidu_rpc_protocol.cpp:273-460) for replies the host produced ------------------------
+// one warp per reply: body (copied, or snappy-compressed into place), CRC32C over it, then lane 0 writes header + RpcMeta
+struct ReplyDesc {                   // == b2_reply
+    uint32_t flags; int32_t error_code; long long correlation_id; int32_t compress_type, checksum_type, content_type;
+    uint32_t error_text_off, error_text_len, body_off, body_len, attachment_off, attachment_len, checksum_value_off, checksum_value_len,
+             extra_streams_off, n_extra_streams, user_fields_off, n_user_fields, reserved;
+    long long stream_id;
+};
+__device__ __forceinline__ uint32_t reply_user_fields_len(const uint8_t* uf, uint32_t n) {     // sum over entries of tag + len + entry
+    uint32_t total = 0;
+    for (uint32_t k = 0; k < n; k++) {
+        const uint32_t kl = load_le32(uf), vl = load_le32(uf + 4);
+        const uint32_t el = 1 + varint_len(kl) + kl + 1 + varint_len(vl) + vl;
+        total += 1 + varint_len(el) + el; uf += 8 + kl + vl;
+    }
+    return total;
+}
+__global__ void __launch_bounds__(256) k_pack_responses(const uint8_t* bytes, const ReplyDesc* reps, uint32_t n, uint8_t* out, const uint32_t* out_offs,
+                                                        uint32_t* out_lens, uint8_t* scratch, uint16_t* snappy_tab, const uint32_t* crc_adv) {
+    __shared__ uint32_t s_hot[kCrcHotWords];
+    crc_tabs_to_smem(s_hot, crc_adv);
+    CrcTabs ct; ct.hot = s_hot; ct.tree = crc_adv + kCrcHotWords;
+    const uint32_t lane = threadIdx.x & 31, n_warps = (gridDim.x * blockDim.x) >> 5, warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (uint32_t i = warp_id; i < n; i += n_warps) {
+        const ReplyDesc R = reps[i];
+        uint8_t* o = out + out_offs[i];
+        const int32_t err = R.error_code == -1 ? B2_EINTERNAL : R.error_code;                  // :333-337
+        const bool append_body = err == 0;                                                       // :316-330
+        if (append_body && R.compress_type != B2_COMPRESS_TYPE_NONE && R.compress_type != B2_COMPRESS_TYPE_SNAPPY) { if (lane == 0) out_lens[i] = 0; continue; }
+        const bool own_cks = append_body && R.checksum_type == B2_CHECKSUM_TYPE_CRC32C;
+        const uint32_t cks_len = own_cks ? 4u : R.checksum_value_len;
+        const uint32_t att_len = append_body ? R.attachment_len : 0u;
+        // RpcResponseMeta: error_code(1) [error_text(2)]
+        uint32_t rl = 1 + varint_len((uint64_t)(long long)err);
+        if (R.error_text_len) rl += 1 + varint_len(R.error_text_len) + R.error_text_len;
+        // StreamSettings: stream_id(1) need_feedback(2) writable(3) extra_stream_ids(4)*
+        uint32_t sl = 0;
+        const long long* extra = reinterpret_cast<const long long*>(bytes + R.extra_streams_off);
+        if (R.flags & B2_RSP_HAS_STREAM) {
+            sl = 1 + varint_len((uint64_t)R.stream_id) + 2 + 2;
+            for (uint32_t k = 0; k < R.n_extra_streams; k++) sl += 1 + varint_len((uint64_t)extra[k]);
+        }
+        const uint32_t ufl = R.n_user_fields ? reply_user_fields_len(bytes + R.user_fields_off, R.n_user_fields) : 0u;
+        uint32_t ml = 1 + varint_len(rl) + rl + 1 + varint_len((uint64_t)(long long)R.compress_type) + 1 + varint_len((uint64_t)R.correlation_id);
+        if (att_len) ml += 1 + varint_len(att_len);
+        if (R.flags & B2_RSP_HAS_STREAM) ml += 1 + varint_len(sl) + sl;
+        ml += ufl;
+        ml += 1 + varint_len((uint64_t)(long long)R.content_type) + 1 + varint_len((uint64_t)(long long)R.checksum_type) + 1 + varint_len(cks_len) + cks_len;
+        uint8_t* body = o + 12 + ml;
+        uint32_t body_len = 0;
+        if (append_body) {
+            if (R.compress_type == B2_COMPRESS_TYPE_SNAPPY)
+                body_len = warp_snappy_compress(bytes + R.body_off, R.body_len, body, snappy_tab + (size_t)(warp_id % kSnappyWarps) * kSnappyMaxTable, lane);
+            else { warp_copy(body, bytes + R.body_off, R.body_len, lane); body_len = R.body_len; }
+        }
+        __syncwarp();
+        uint32_t crc_be = 0;
+        if (own_cks) {                                                                           // Crc32cCompute over what goes on the wire
+            const uint8_t* src = R.compress_type == B2_COMPRESS_TYPE_SNAPPY ? body : bytes + R.body_off;
+            if (R.compress_type == B2_COMPRESS_TYPE_SNAPPY) __threadfence_block();
+            crc_be = crc32c_mask(warp_crc32c_update(0xffffffffu, src, body_len, lane, ct) ^ 0xffffffffu);
+        }
+        if (att_len) warp_copy(body + body_len, bytes + R.attachment_off, att_len, lane);
+        if (lane == 0) {
+            uint8_t* p = o;
+            p[0] = 'P'; p[1] = 'R'; p[2] = 'P'; p[3] = 'C'; put_be32(p + 4, ml + body_len + att_len); put_be32(p + 8, ml); p += 12;
+            *p++ = 0x12; p = put_varint(p, rl);
+            *p++ = 0x08; p = put_varint(p, (uint64_t)(long long)err);
+            if (R.error_text_len) { *p++ = 0x12; p = put_varint(p, R.error_text_len); for (uint32_t k = 0; k < R.error_text_len; k++) *p++ = bytes[R.error_text_off + k]; }
+            *p++ = 0x18; p = put_varint(p, (uint64_t)(long long)R.compress_type);
+            *p++ = 0x20; p = put_varint(p, (uint64_t)R.correlation_id);
+            if (att_len) { *p++ = 0x28; p = put_varint(p, att_len); }
+            if (R.flags & B2_RSP_HAS_STREAM) {
+                *p++ = 0x42; p = put_varint(p, sl);
+                *p++ = 0x08; p = put_varint(p, (uint64_t)R.stream_id);
+                *p++ = 0x10; *p++ = (R.flags & B2_RSP_STREAM_NEED_FEEDBACK) ? 1 : 0;
+                *p++ = 0x18; *p++ = (R.flags & B2_RSP_STREAM_WRITABLE) ? 1 : 0;
+                for (uint32_t k = 0; k < R.n_extra_streams; k++) { *p++ = 0x20; p = put_varint(p, (uint64_t)extra[k]); }
+            }
+            const uint8_t* uf = bytes + R.user_fields_off;
+            for (uint32_t k = 0; k < R.n_user_fields; k++) {                                     // map<string,string> user_fields = 9: entry {key = 1, value = 2}
+                const uint32_t kl = load_le32(uf), vl = load_le32(uf + 4);
+                const uint32_t el = 1 + varint_len(kl) + kl + 1 + varint_len(vl) + vl;
+                *p++ = 0x4a; p = put_varint(p, el);
+                *p++ = 0x0a; p = put_varint(p, kl); for (uint32_t q = 0; q < kl; q++) *p++ = uf[8 + q];
+                *p++ = 0x12; p = put_varint(p, vl); for (uint32_t q = 0; q < vl; q++) *p++ = uf[8 + kl + q];
+                uf += 8 + kl + vl;
+            }
+            *p++ = 0x50; p = put_varint(p, (uint64_t)(long long)R.content_type);
+            *p++ = 0x58; p = put_varint(p, (uint64_t)(long long)R.checksum_type);
+            *p++ = 0x62; p = put_varint(p, cks_len);
+            if (own_cks) p = put_be32(p, crc_be);
+            else for (uint32_t k = 0; k < cks_len; k++) *p++ = bytes[R.checksum_value_off + k];
+            out_lens[i] = 12 + ml + body_len + att_len;
+        }
+    }
+}
+
 // --- k_pack_slow: everything that is not a plain OK echo ----------------------
 // error replies, CRC32C verify/compute, snappy requests, split attachments: warp per message,
 // high occupancy (these are latency-bound), skipping the messages k_pack_tma moves.
@@ -2489,7 +2606,7 @@ __device__ __forceinline__ void small_body(const BatchPtrs& B, const DevConfig& 
     CrcTabs ct; ct.hot = S.s_hot; ct.tree = B.crc_adv + kCrcHotWords;
     // ---- cut loop: thread per run (ProcessNewMessage over the whole run)
     uint32_t my_count = 0; b2_run_status st; st.consumed = 0; st.parse_error = B2_PARSE_ERROR_NOT_ENOUGH_DATA; st.n_msgs = 0;
-    st.first_msg = 0; st.preferred_proto = -1; st.reserved0 = 0; st.resp_off = 0; st.resp_bytes = 0;
+    st.first_msg = 0; st.preferred_proto = -1; st.n_unanswered = 0; st.resp_off = 0; st.resp_bytes = 0;
     b2_run run; run.offset = 0; run.length = 0; run.preferred_proto = -1; run.flags = 0; run.socket_id = 0;
     if (tid < B.n_runs) {
         run = B.runs[tid];

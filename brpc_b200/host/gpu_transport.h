@@ -139,6 +139,20 @@ public:
             Conn* c = live[k]; Socket* s = &c->sock;
             const b2_run_status& st = res.runs[k];
             s->AddInputBytes(st.consumed); s->AddInputMessages(st.n_msgs); s->set_preferred_index(st.preferred_proto);
+            if (res.iov && _sink) {
+                // B2_RESP_IOVEC: the device wrote the gather list of this connection's replies (what cut_multiple_into_file_descriptor
+                // would assemble, iobuf.cpp:954-992): no per-message work unless the run holds messages the device did not answer
+                s->OnMessagesCut(st.consumed, st.n_msgs);
+                if (st.n_msgs) _sink(c, reinterpret_cast<const struct iovec*>(res.iov) + 2 * (size_t)st.first_msg, 2 * (size_t)st.n_msgs);
+                if (st.n_unanswered)
+                    for (uint32_t m = st.first_msg; m < st.first_msg + st.n_msgs; m++) {
+                        const b2_msg_desc& d = res.msgs[m];
+                        if (d.status == B2_MSG_BAD_META) s->SetFailed(1003 /*EREQUEST*/, "Fail to parse RpcMeta");
+                        else if (d.status != B2_MSG_ECHOED && d.status != B2_MSG_ERROR_REPLIED && _process) HandOver(s, d);
+                    }
+                FinishRun(c, s, st, _pop);
+                continue;
+            }
             IOBuf::Block* reg_blk = nullptr;
             if (!_sink && st.n_msgs) { outstanding->fetch_add(1); reg_blk = IOBuf::create_external_block(c->base, c->fill, [outstanding](void*) { outstanding->fetch_sub(1); }); }
             _iov.clear();
@@ -147,7 +161,13 @@ public:
                 const b2_msg_desc& d = res.msgs[m];
                 s->OnMessageCut(12u + d.body_size);
                 if (d.status == B2_MSG_ECHOED || d.status == B2_MSG_ERROR_REPLIED) {
-                    const b2_resp_ref* rf = res.refs ? res.refs + m : nullptr;
+                    b2_resp_ref from_iov;                                              // (B2_RESP_IOVEC without a sink: the pair says the same)
+                    if (res.iov) {
+                        const b2_iovec& a = res.iov[2 * (size_t)m]; const b2_iovec& b = res.iov[2 * (size_t)m + 1];
+                        from_iov.prefix_len = (uint32_t)a.iov_len; from_iov.src_len = (uint32_t)b.iov_len; from_iov.reserved = 0;
+                        from_iov.src_off = b.iov_len ? (uint32_t)(static_cast<const uint8_t*>(b.iov_base) - _arena) : 0;
+                    }
+                    const b2_resp_ref* rf = res.iov ? &from_iov : res.refs ? res.refs + m : nullptr;
                     const uint32_t plen = (rf && rf->src_len) ? rf->prefix_len : d.resp_len;
                     if (_sink) {
                         struct iovec v; v.iov_base = const_cast<uint8_t*>(res.resp) + d.resp_off; v.iov_len = plen; _iov.push_back(v);
@@ -159,22 +179,12 @@ public:
                     }
                 } else if (d.status == B2_MSG_BAD_META) {
                     s->SetFailed(1003 /*EREQUEST*/, "Fail to parse RpcMeta");          // baidu_rpc_protocol.cpp:577-582
-                } else if ((d.status == B2_MSG_HOST || d.status == B2_MSG_STREAM_FRAME || d.status == B2_MSG_UNSUPPORTED) && _process) {
-                    MostCommonMessage* msg = new MostCommonMessage;
-                    msg->socket = s; msg->desc = d;
-                    const uint8_t* f = _arena + d.frame_off;                            // (copied: the region is reused after this round)
-                    msg->meta.append(f + 12, d.meta_size); msg->payload.append(f + 12 + d.meta_size, d.body_size - d.meta_size);
-                    _process(msg);
-                }
+                } else if ((d.status == B2_MSG_HOST || d.status == B2_MSG_STREAM_FRAME || d.status == B2_MSG_UNSUPPORTED) && _process) HandOver(s, d);
             }
             if (_sink) { if (!_iov.empty()) _sink(c, _iov.data(), _iov.size()); }
             else if (!out.empty()) s->Write(&out);
             IOBuf::release_external_block(reg_blk);
-            if (st.parse_error != B2_PARSE_ERROR_NOT_ENOUGH_DATA)                       // input_messenger.cpp:227-239
-                s->SetFailed(22 /*EINVAL*/, std::string("Close socket: ") + ParseErrorToString((ParseError)st.parse_error));
-            else if (st.consumed == 0 && c->fill == c->cap)
-                s->SetFailed(22, std::string("Close socket: ") + ParseErrorToString(PARSE_ERROR_TOO_BIG_DATA) + " (one frame exceeds the connection's read region)");
-            _pop.push_back(std::make_pair(c, st.consumed));
+            FinishRun(c, s, st, _pop);
         }
         IOBuf::release_external_block(resp_blk);
         // the references point into the reply block and the read regions: both are reused next round, so the writes must be done
@@ -196,6 +206,21 @@ public:
     uint8_t* arena() const { return _arena; }
 
 private:
+    // a message the device left to the host (B2_HANDLER_HOST methods, stream frames, other codecs / protocols): handed to the process callback
+    void HandOver(Socket* s, const b2_msg_desc& d) {
+        MostCommonMessage* msg = new MostCommonMessage;
+        msg->socket = s; msg->desc = d;
+        const uint8_t* f = _arena + d.frame_off;                                        // (copied: the region is reused after this round)
+        msg->meta.append(f + 12, d.meta_size); msg->payload.append(f + 12 + d.meta_size, d.body_size - d.meta_size);
+        _process(msg);
+    }
+    static void FinishRun(Conn* c, Socket* s, const b2_run_status& st, std::vector<std::pair<Conn*, uint32_t>>& pop) {
+        if (st.parse_error != B2_PARSE_ERROR_NOT_ENOUGH_DATA)                           // input_messenger.cpp:227-239
+            s->SetFailed(22 /*EINVAL*/, std::string("Close socket: ") + ParseErrorToString((ParseError)st.parse_error));
+        else if (st.consumed == 0 && c->fill == c->cap)
+            s->SetFailed(22, std::string("Close socket: ") + ParseErrorToString(PARSE_ERROR_TOO_BIG_DATA) + " (one frame exceeds the connection's read region)");
+        pop.push_back(std::make_pair(c, st.consumed));
+    }
     static double mono_s() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + (double)t.tv_nsec * 1e-9; }
     void Destroy() { for (b2_ctx* c : _ctx) b2_ctx_destroy(c); _ctx.clear(); if (_arena) { b2_block_free(_arena); _arena = nullptr; } }
     Options _opt; uint8_t* _arena = nullptr; size_t _arena_bytes = 0;

@@ -73,6 +73,8 @@ public:
     static const size_t MIN_ONCE_READ = 4096, MAX_ONCE_READ = 524288, MSG_SIZE_WINDOW = 10;
     size_t once_read() const { const size_t n = _avg_msg_size * 16; return n < MIN_ONCE_READ ? MIN_ONCE_READ : n > MAX_ONCE_READ ? MAX_ONCE_READ : n; }
     void OnMessageCut(size_t msg_bytes) { _avg_msg_size = _avg_msg_size ? (_avg_msg_size * (MSG_SIZE_WINDOW - 1) + msg_bytes) / MSG_SIZE_WINDOW : msg_bytes; }
+    // n messages of `bytes` in total were cut at once (the device cut them): the same smoothing, applied with their mean size
+    void OnMessagesCut(size_t bytes, size_t n) { if (!n) return; const size_t mean = bytes / n; for (size_t k = n < 64 ? n : 64; k; k--) OnMessageCut(mean); }
     size_t avg_msg_size() const { return _avg_msg_size; }
     // Read until the fd would block (or EOF / an error): the inner loop of OnNewMessages without the per-read parse — parsing is
     // batched over all readable sockets by the messenger.  Returns the bytes read; *eof is set on a zero-length read.

@@ -67,6 +67,7 @@ extern "C" {
 #define B2_ENOSERVICE 1001
 #define B2_ENOMETHOD  1002
 #define B2_EREQUEST   1003
+#define B2_EINTERNAL  2001
 #define B2_ERESPONSE  2002
 
 /* ---- per-message disposition (b2_msg_desc.status) ------------------------ */
@@ -148,8 +149,10 @@ typedef struct b2_run_status {
     uint32_t n_msgs;           /* messages cut (Socket::AddInputMessages) */
     uint32_t first_msg;        /* index of this run's first b2_msg_desc */
     int32_t  preferred_proto;  /* Socket::preferred_index() after the loop */
-    uint32_t reserved0;        /* (the _avg_msg_size read-size hint, input_messenger.cpp:242-261,
-                                  stays on the host: it is consumed / n_msgs smoothed) */
+    uint32_t n_unanswered;     /* B2_RESP_IOVEC only (else 0): messages of this run that are NOT a device-written reply
+                                  (B2_MSG_HOST, stream frames, framed-only protocols, unsupported codecs, bad metas ...), i.e.
+                                  the ones the host must pick out of msgs[].  (The _avg_msg_size read-size hint,
+                                  input_messenger.cpp:242-261, stays on the host: it is consumed / n_msgs smoothed.) */
     uint32_t resp_off;         /* first response byte of this run in the resp region */
     uint32_t resp_bytes;       /* span (incl. alignment padding) of this run's responses */
 } b2_run_status;               /* 32 bytes */
@@ -216,6 +219,14 @@ typedef struct b2_options {
  * compressed replies, client-side results). */
 typedef struct b2_resp_ref { uint32_t prefix_len, src_off, src_len, reserved; } b2_resp_ref;   /* 16 bytes */
 
+/* B2_RESP_IOVEC: the same replies as ready-made `struct iovec` pairs (layout of <sys/uio.h>) with HOST addresses — what
+ * IOBuf::cut_multiple_into_file_descriptor (src/butil/iobuf.cpp:954-992) assembles from the block references of the queued
+ * replies before its writev, written by the GPU instead: iov[2*i] = reply i's bytes in the pinned resp block (the prefix, or the
+ * whole reply), iov[2*i + 1] = its payload inside the caller's request bytes (length 0 when there is none).  A message the device
+ * did not answer has two zero-length entries, so a run's replies are writev(fd, iov + 2*first_msg, 2*n_msgs) as they stand, and
+ * b2_run_status.n_unanswered says whether the host has to look at that run's descriptors at all. */
+typedef struct b2_iovec { void* iov_base; size_t iov_len; } b2_iovec;
+
 /* Pointers into ctx-owned PINNED host memory, valid until the next batch call. */
 typedef struct b2_batch_result {
     const b2_run_status* runs;     uint32_t n_runs;
@@ -224,6 +235,7 @@ typedef struct b2_batch_result {
     float kernel_ms;               /* device time of the kernels (CUDA events) */
     uint32_t n_launches;           /* kernels launched for this batch */
     const b2_resp_ref*   refs;     /* [n_msgs] in B2_RESP_BY_REF mode, else NULL */
+    const b2_iovec*      iov;      /* [2 * n_msgs] in B2_RESP_IOVEC mode (refs is NULL then), else NULL */
 } b2_batch_result;
 
 typedef struct b2_ctx b2_ctx;
@@ -278,11 +290,14 @@ uint64_t b2_block_pool_host_allocs(void);   /* cudaHostAlloc calls so far (pool 
  * resp:   B2_RESP_COPY   every reply frame is materialised in the resp region and copied back.
  *         B2_RESP_BY_REF an OK echo reply is {prefix in resp, payload = a span of the request bytes} (b2_resp_ref), what
  *                        SendRpcResponse does with IOBuf references; only descriptors, refs and <= 64-byte prefixes
- *                        come back.  Everything else (errors, CRC'd / compressed replies) is still materialised. */
+ *                        come back.  Everything else (errors, CRC'd / compressed replies) is still materialised.
+ *         B2_RESP_IOVEC  BY_REF with the references already turned into the iovec list of the write (b2_iovec): the host
+ *                        side does no per-message work for device-answered traffic. */
 #define B2_INPUT_COPY 0
 #define B2_INPUT_PULL 1
 #define B2_RESP_COPY   0
 #define B2_RESP_BY_REF 1
+#define B2_RESP_IOVEC  2   /* BY_REF, and the device also writes the gather list: b2_batch_result.iov (below) */
 int  b2_set_modes(b2_ctx* ctx, int input_mode, int resp_mode);
 
 /* ---- the hot path, host-facing (H2D + kernels + D2H inside) ---------------
@@ -425,6 +440,41 @@ typedef struct b2_request {
 } b2_request;                        /* 64 bytes */
 int  b2_pack_requests(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_request* reqs, uint32_t n,
                       void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens);
+
+/* ---- replies the HOST produced (B2_HANDLER_HOST methods, any service above the transport): SendRpcResponse
+ * (src/brpc/policy/baidu_rpc_protocol.cpp:273-460) as a batch, one warp per reply.  `bytes` holds what the host has: the response
+ * message as its Serializer wrote it (UNcompressed), the attachment, the error text, the request's checksum bytes, user fields.
+ *   - body: SerializeResponse (:218-246) -> SerializeRpcMessage (:148-216): COMPRESS_TYPE_NONE copies it, SNAPPY compresses it here
+ *     (bit-exact with the vendored snappy); response_checksum_type CRC32C is computed here over the (compressed) body
+ *     (Crc32cCompute, policy/crc32c_checksum.cpp:28-42).  gzip / zlib replies are not packed (out_lens[i] = 0): bit-exact deflate
+ *     output is zlib-version specific.
+ *   - error_code != 0 (cntl->Failed()): no body, no attachment, nothing compressed or checksummed (:316-330); -1 becomes
+ *     EINTERNAL (:333-337); error_text is written only when non-empty (:343-347).
+ *   - RpcMeta (:339-380): response{error_code,[error_text]}, compress_type, correlation_id, [attachment_size], [stream_settings
+ *     {stream_id, need_feedback, writable, extra_stream_ids}] (Stream::FillSettings, stream.cpp:678-682), [user_fields], content_type,
+ *     checksum_type, checksum_value.  checksum_value = the CRC when one was computed, else the bytes at checksum_value_off — the
+ *     REQUEST's checksum_value, which the Controller still holds (:608 + :349).  user_fields are written in the order given (a
+ *     protobuf map has no defined wire order; with one entry there is nothing to order).
+ * Reply i lands at out + out_offs[i] (filled by the call), out_lens[i] long (0 = could not be packed). */
+#define B2_RSP_HAS_STREAM         1u
+#define B2_RSP_STREAM_NEED_FEEDBACK 2u
+#define B2_RSP_STREAM_WRITABLE    4u
+typedef struct b2_reply {
+    uint32_t flags;
+    int32_t  error_code;
+    int64_t  correlation_id;
+    int32_t  compress_type, checksum_type, content_type;
+    uint32_t error_text_off, error_text_len;
+    uint32_t body_off, body_len;
+    uint32_t attachment_off, attachment_len;
+    uint32_t checksum_value_off, checksum_value_len;
+    uint32_t extra_streams_off, n_extra_streams;   /* int64 little-endian each, 8-byte aligned offset */
+    uint32_t user_fields_off, n_user_fields;       /* records: u32 key_len, u32 value_len, key bytes, value bytes (unaligned, back to back) */
+    uint32_t reserved;
+    int64_t  stream_id;
+} b2_reply;                          /* 88 bytes */
+int  b2_pack_responses(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_reply* replies, uint32_t n,
+                       void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens);
 
 /* ---- h2 / gRPC: leaf calls first, then the whole server-side parser and the reply framing -----
  * b2_h2_scan_batch: H2Context::ConsumeFrameHead (src/brpc/policy/http2_rpc_protocol.cpp:438-465)

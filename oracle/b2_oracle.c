@@ -583,6 +583,73 @@ static size_t send_rpc_response(uint8_t* out, size_t cap, int32_t error_code,
     return bad ? (size_t)-1 : (size_t)(w.p - out);
 }
 
+/* SendRpcResponse for a reply the HOST produced (the checker of b2_pack_responses): SerializeResponse :218-246 (compress, then
+ * checksum over what goes on the wire), error / append_body rules :316-337, RpcMeta :339-380 incl. stream_settings
+ * (Stream::FillSettings, stream.cpp:678-682) and user_fields in the order given, SerializeRpcHeaderAndMeta :83-103.
+ * Returns the frame length, 0 when the reply cannot be packed (gzip / zlib), (size_t)-1 when out is too small. */
+size_t orc_pack_response(const b2_reply* r, const uint8_t* bytes, uint8_t* out, size_t cap) {
+    const int32_t err = r->error_code == -1 ? B2_EINTERNAL : r->error_code;
+    const int append_body = err == 0;
+    if (append_body && r->compress_type != B2_COMPRESS_TYPE_NONE && r->compress_type != B2_COMPRESS_TYPE_SNAPPY) return 0;
+    uint8_t* body = NULL; size_t body_len = 0; uint8_t cks4[4];
+    const uint8_t* cks = bytes + r->checksum_value_off; size_t cks_len = r->checksum_value_len;
+    if (append_body) {
+        if (r->compress_type == B2_COMPRESS_TYPE_SNAPPY) {
+            if (!ref_load()) return 0;
+            size_t olen = g_sn_max(r->body_len);
+            body = (uint8_t*)malloc(olen ? olen : 1);
+            if (!g_sn_c((const char*)bytes + r->body_off, r->body_len, (char*)body, &olen)) { free(body); return 0; }
+            body_len = olen;
+        } else { body = (uint8_t*)malloc(r->body_len ? r->body_len : 1); memcpy(body, bytes + r->body_off, r->body_len); body_len = r->body_len; }
+        if (r->checksum_type == B2_CHECKSUM_TYPE_CRC32C) {
+            const uint32_t c = orc_crc32c_mask(orc_crc32c_extend(0, body, body_len));
+            cks4[0] = (uint8_t)(c >> 24); cks4[1] = (uint8_t)(c >> 16); cks4[2] = (uint8_t)(c >> 8); cks4[3] = (uint8_t)c;
+            cks = cks4; cks_len = 4;
+        }
+    }
+    const size_t att_len = append_body ? r->attachment_len : 0;
+    size_t meta_cap = 256 + r->error_text_len + cks_len + 11u * (size_t)r->n_extra_streams;
+    { const uint8_t* uf = bytes + r->user_fields_off;
+      for (uint32_t k = 0; k < r->n_user_fields; k++) { uint32_t kl, vl; memcpy(&kl, uf, 4); memcpy(&vl, uf + 4, 4); meta_cap += 24u + kl + vl; uf += 8u + kl + vl; } }
+    uint8_t* rm = (uint8_t*)malloc(32 + r->error_text_len); wr_t rw = { rm, rm + 32 + r->error_text_len, 0 };
+    wr_i32(&rw, 1, err);
+    if (r->error_text_len) wr_len(&rw, 2, bytes + r->error_text_off, r->error_text_len);
+    uint8_t* meta = (uint8_t*)malloc(meta_cap); wr_t mw = { meta, meta + meta_cap, 0 };
+    wr_len(&mw, 2, rm, (size_t)(rw.p - rm));
+    wr_i32(&mw, 3, r->compress_type);
+    wr_i64(&mw, 4, r->correlation_id);
+    if (att_len) wr_i32(&mw, 5, (int32_t)att_len);
+    if (r->flags & B2_RSP_HAS_STREAM) {
+        size_t sc = 32 + 11u * (size_t)r->n_extra_streams; uint8_t* ss = (uint8_t*)malloc(sc); wr_t sw = { ss, ss + sc, 0 };
+        wr_i64(&sw, 1, r->stream_id);
+        wr_varint(&sw, (2 << 3) | 0); wr_varint(&sw, (r->flags & B2_RSP_STREAM_NEED_FEEDBACK) ? 1 : 0);
+        wr_varint(&sw, (3 << 3) | 0); wr_varint(&sw, (r->flags & B2_RSP_STREAM_WRITABLE) ? 1 : 0);
+        for (uint32_t k = 0; k < r->n_extra_streams; k++) { int64_t v; memcpy(&v, bytes + r->extra_streams_off + 8u * k, 8); wr_i64(&sw, 4, v); }
+        wr_len(&mw, 8, ss, (size_t)(sw.p - ss));
+        if (sw.ovf) mw.ovf = 1;
+        free(ss);
+    }
+    { const uint8_t* uf = bytes + r->user_fields_off;
+      for (uint32_t k = 0; k < r->n_user_fields; k++) {
+          uint32_t kl, vl; memcpy(&kl, uf, 4); memcpy(&vl, uf + 4, 4);
+          size_t ec = 24u + kl + vl; uint8_t* e = (uint8_t*)malloc(ec); wr_t ew = { e, e + ec, 0 };
+          wr_len(&ew, 1, uf + 8, kl); wr_len(&ew, 2, uf + 8 + kl, vl);
+          wr_len(&mw, 9, e, (size_t)(ew.p - e));
+          free(e); uf += 8u + kl + vl;
+      } }
+    wr_i32(&mw, 10, r->content_type);
+    wr_i32(&mw, 11, r->checksum_type);
+    wr_len(&mw, 12, cks, cks_len);
+    const uint32_t meta_size = (uint32_t)(mw.p - meta);
+    wr_t w = { out, out + cap, 0 };
+    pack_header(&w, "PRPC", meta_size, (uint32_t)(body_len + att_len));
+    wr_raw(&w, meta, meta_size);
+    if (append_body) { wr_raw(&w, body, body_len); if (att_len) wr_raw(&w, bytes + r->attachment_off, att_len); }
+    const int bad = rw.ovf || mw.ovf || w.ovf;
+    free(rm); free(meta); free(body);
+    return bad ? (size_t)-1 : (size_t)(w.p - out);
+}
+
 static const b2_method* find_method(const orc_config* cfg, const uint8_t* svc, uint32_t svc_len,
                                     const uint8_t* mth, uint32_t mth_len, int* idx, int* no_service) {
     /* baidu_rpc_protocol.cpp:738-756: a service name without '.' is looked up as a

@@ -158,6 +158,10 @@ uint32_t orc_h2_consume(orc_h2_conn* c, const orc_config* cfg, const uint8_t* in
 uint32_t orc_h2_pack_response(orc_h2_conn* c, const b2_h2_response* r, const uint8_t* bytes, uint8_t* out);
 uint32_t orc_h2_scan(const uint8_t* in, uint32_t n, uint32_t max_frame_size, orc_h2_frame* frames, uint32_t cap,
                      uint32_t* consumed, uint32_t* err);
+/* SendRpcResponse (baidu_rpc_protocol.cpp:273-460) for a reply the host produced: the checker of b2_pack_responses.
+ * Frame length; 0 = not packable (gzip / zlib reply); (size_t)-1 = out too small. */
+size_t orc_pack_response(const b2_reply* r, const uint8_t* bytes, uint8_t* out, size_t cap);
+
 /* What GzipInputStream(format = B2_COMPRESS_TYPE_GZIP | B2_COMPRESS_TYPE_ZLIB) over `in` (one block) yields before it reports
  * end-of-stream (b2_oracle_gzip.c).  *out is malloc'ed; release with orc_free.  0, or -1 when out of memory. */
 int orc_gzip_input_stream(const uint8_t* in, size_t n, int format, uint8_t** out, size_t* out_len);

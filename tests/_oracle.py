@@ -59,7 +59,7 @@ class RequestSpec(C.Structure):
 RUN_DT = np.dtype([("socket_id", "<u8"), ("offset", "<u4"), ("length", "<u4"),
                    ("preferred_proto", "<i4"), ("flags", "<u4")])
 RUN_STATUS_DT = np.dtype([("consumed", "<u4"), ("parse_error", "<u4"), ("n_msgs", "<u4"), ("first_msg", "<u4"),
-                          ("preferred_proto", "<i4"), ("reserved0", "<u4"), ("resp_off", "<u4"), ("resp_bytes", "<u4")])
+                          ("preferred_proto", "<i4"), ("n_unanswered", "<u4"), ("resp_off", "<u4"), ("resp_bytes", "<u4")])
 MSG_DT = np.dtype([("run_idx", "<u4"), ("frame_off", "<u4"), ("body_size", "<u4"), ("meta_size", "<u4"),
                    ("correlation_id", "<i8"), ("log_id", "<i8"),
                    ("attachment_size", "<i4"), ("compress_type", "<i4"), ("checksum_type", "<i4"), ("error_code", "<i4"),
@@ -85,6 +85,21 @@ lib.orc_have_ref.restype = C.c_int
 
 lib.orc_gzip_input_stream.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
 lib.orc_free.argtypes = [C.c_void_p]
+
+
+lib.orc_pack_response.restype = C.c_size_t
+lib.orc_pack_response.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
+
+
+def pack_response(reply, data):
+    """reply: one REPLY_DT record (numpy, offsets into data).  The frame SendRpcResponse writes; b"" = not packable."""
+    import numpy as np
+    r = np.ascontiguousarray(reply).reshape(1)
+    cap = int(r["body_len"][0]) * 2 + len(data) + 4096
+    out = C.create_string_buffer(cap)
+    n = lib.orc_pack_response(r.ctypes.data, bytes(data), out, cap)
+    assert n != (1 << 64) - 1
+    return out.raw[:n]
 
 
 def gzip_input_stream(b, fmt):

@@ -114,7 +114,7 @@ static std::vector<std::string> make_streams(int k, int frames) {
     return streams;
 }
 
-static void test_transport_gpu(int input_mode, int resp_mode) {
+static void test_transport_gpu(int input_mode, int resp_mode, bool use_sink = false) {
     b2::GpuTransport::Options o; memset(&o.ctx, 0, sizeof o.ctx);
     o.ctx.device = 0; o.ctx.max_batch_bytes = 20 << 20; o.ctx.max_msgs = 1 << 16; o.ctx.max_runs = 64;
     o.pipeline = 3; o.region_bytes = 1 << 20; o.max_connections = 16; o.input_mode = input_mode; o.resp_mode = resp_mode;
@@ -133,6 +133,18 @@ static void test_transport_gpu(int input_mode, int resp_mode) {
     std::vector<size_t> pos(K, 0); std::vector<std::string> got(K);
     unsigned seed = 99; int total = 0, rounds = 0; char rb[1 << 16];
     auto drain = [&]() { for (int s = 0; s < K; s++) for (;;) { const ssize_t n = read(cli[s], rb, sizeof rb); if (n <= 0) break; got[s].append(rb, (size_t)n); } };
+    // the reply sink: the gather list goes to writev as it is (zero-length entries included), resuming after partial writes
+    if (use_sink) tr.SetReplySink([&](b2::GpuTransport::Conn* c, const struct iovec* v, size_t n) {
+        std::vector<struct iovec> w(v, v + n); size_t at = 0;
+        while (at < n) {
+            const ssize_t k = writev(c->fd, w.data() + at, (int)std::min<size_t>(1024, n - at));
+            if (k < 0) { CHECK(errno == EAGAIN || errno == EWOULDBLOCK || errno == EINTR); drain(); continue; }
+            size_t left = (size_t)k;
+            while (at < n && left >= w[at].iov_len) { left -= w[at].iov_len; at++; }
+            if (at < n && left) { w[at].iov_base = (char*)w[at].iov_base + left; w[at].iov_len -= left; }
+            if (k == 0) { while (at < n && w[at].iov_len == 0) at++; }
+        }
+    });
     for (bool more = true; more || rounds % 3; rounds++) {
         more = false;
         const uint32_t g = rounds % tr.pipeline();
@@ -237,7 +249,9 @@ int main(int argc, char** argv) {
     signal(SIGPIPE, SIG_IGN);                      // as brpc's global init does: a dead peer is an EPIPE from writev, not a signal
     const std::string mode = argc > 1 ? argv[1] : "queue";
     if (mode == "queue") { test_write_queue(); return 0; }
-    if (mode == "gpu") { test_transport_gpu(B2_INPUT_PULL, B2_RESP_BY_REF); test_transport_gpu(B2_INPUT_COPY, B2_RESP_COPY); test_transport_gpu(B2_INPUT_COPY, B2_RESP_BY_REF); return 0; }
+    if (mode == "gpu") { test_transport_gpu(B2_INPUT_PULL, B2_RESP_BY_REF); test_transport_gpu(B2_INPUT_COPY, B2_RESP_COPY); test_transport_gpu(B2_INPUT_COPY, B2_RESP_BY_REF);
+                         test_transport_gpu(B2_INPUT_PULL, B2_RESP_IOVEC, true); test_transport_gpu(B2_INPUT_COPY, B2_RESP_IOVEC, true); test_transport_gpu(B2_INPUT_PULL, B2_RESP_IOVEC, false);
+                         test_transport_gpu(B2_INPUT_PULL, B2_RESP_BY_REF, true); return 0; }
     if (mode == "bench") return bench(argc > 2 ? atoi(argv[2]) : 4, argc > 3 ? atoi(argv[3]) : 20, argc > 4 ? atoi(argv[4]) : B2_INPUT_PULL, argc > 5 ? atoi(argv[5]) : B2_RESP_BY_REF, argc > 6 ? atoi(argv[6]) : 4, argc > 7 && atoi(argv[7]) == 1 ? 1 : 2);
     fprintf(stderr, "usage: transport_test queue|gpu|bench\n"); return 2;
 }

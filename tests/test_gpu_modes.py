@@ -2,6 +2,7 @@
 B2_INPUT_PULL (kernels read the pinned batch buffer in place over PCIe) and B2_RESP_BY_REF (an OK echo reply is
 {prefix, reference into the request bytes}; gathering prefix + reference must reproduce the oracle's reply byte for byte,
 SendRpcResponse's append-by-reference, baidu_rpc_protocol.cpp:383-389)."""
+import ctypes as C
 import random
 
 import numpy as np
@@ -48,6 +49,21 @@ def check(b2, ctx, chunks, cfg, modes, what):
             assert np.array_equal(msgs[f], o_msgs[f]), tag + " msgs." + f
         refs = info["refs"]
         assert (refs is not None) == (rm == 1) or len(msgs) == 0
+        if rm == 2 and len(msgs):
+            # B2_RESP_IOVEC: the device-written gather list, host addresses into the pinned reply block and the request bytes
+            iov = info["iov"]
+            assert iov is not None and len(iov) == 2 * len(msgs)
+            answered = (msgs["status"] == 0) | (msgs["status"] == 1)
+            for k in range(len(msgs)):
+                g = b"".join(C.string_at(int(iov["base"][j]), int(iov["len"][j])) for j in (2 * k, 2 * k + 1) if iov["len"][j])
+                assert g == (want[k] if answered[k] else b""), "%s iovec reply %d differs (status %d)" % (tag, k, msgs["status"][k])
+            lo, hi = pin.ptr, pin.ptr + len(data)
+            second = iov[1::2]
+            assert np.all((second["len"] == 0) | ((second["base"] >= lo) & (second["base"] + second["len"] <= hi)))
+            for r in range(len(rs)):
+                f0, n = int(rs["first_msg"][r]), int(rs["n_msgs"][r])
+                assert int(rs["n_unanswered"][r]) == int((~answered[f0:f0 + n]).sum()), tag
+            continue
         got = replies(pin.array, msgs, resp, refs)
         for k, (g, w) in enumerate(zip(got, want)):
             assert g == w, "%s reply %d differs (status %d)" % (tag, k, msgs["status"][k])
@@ -58,7 +74,7 @@ def check(b2, ctx, chunks, cfg, modes, what):
     ctx.set_modes(0, 0)
 
 
-ALL = [(0, 0), (1, 0), (0, 1), (1, 1)]
+ALL = [(0, 0), (1, 0), (0, 1), (1, 1), (0, 2), (1, 2)]
 
 
 def test_modes_on_mixed_traffic_small_and_large_batches(monkeypatch):
@@ -112,6 +128,12 @@ def test_bench_shaped_batch_by_ref_pull():
         assert len(msgs) == n_full == len(o_msgs)
         for f in MSG_FIELDS:
             assert np.array_equal(msgs[f], o_msgs[f]), f
+        if rm == 2:
+            iov = info["iov"]
+            assert np.all(iov["len"][1::2] == 1024) and np.all(iov["len"][0::2] <= 48) and np.all(rs["n_unanswered"] == 0)
+            got = [C.string_at(int(iov["base"][2 * k]), int(iov["len"][2 * k])) + C.string_at(int(iov["base"][2 * k + 1]), 1024) for k in range(0, n_full, 97)]
+            assert got == want[::97]
+            continue
         got = replies(pin.array, msgs, resp, info["refs"])
         assert got == want
         if rm == 1:
