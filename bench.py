@@ -682,16 +682,20 @@ def main():
         barrier()
         ms = (time.perf_counter() - t1) * 1e3 / n_steps
         assert ok, "e2e batches returned wrong results"
-        if rm:
+        if rm == 1:
             refs = i3["refs"]
             assert refs is not None and np.all(refs["src_len"] + refs["prefix_len"] == m3["resp_len"])
-        d2h = int(len(m3) * 64 + len(r3) * 32 + int(r3["resp_bytes"].sum()) + (16 * len(m3) if rm else 0))
+        if rm == 2:
+            iov = i3["iov"]
+            assert iov is not None and np.all(iov["len"][0::2] + iov["len"][1::2] == m3["resp_len"]) and int(r3["n_unanswered"].sum()) == 0
+        d2h = int(len(m3) * 64 + len(r3) * 32 + int(r3["resp_bytes"].sum()) + (16 * rm * len(m3) if rm else 0))
         meta = int(runs.nbytes + 4 * (len(runs) + 1) + 16 * info_["n_tiles"])
         # pull: each message's stashed row is one 96-byte (by-ref; else 128-byte) PCIe read; every tile's speculative entry scan reads two 512-byte windows
         h2d = meta + (int((96 if rm else 128) * len(m3) + 1024 * info_["n_tiles"]) if im else int(nbytes))
         return {"ms_per_step": ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_steps, "tile_bytes": info_["tile_bytes"]}
 
-    e2e_modes = {"copy": e2e_mode(0, 0, 0.4), "copy_by_ref": e2e_mode(0, 1, 0.4), "pull_by_ref": e2e_mode(1, 1, 0.6)}
+    #   iovec     pull, and the device also writes the writev gather list of the replies (what b2::GpuTransport runs: e2e_messenger)
+    e2e_modes = {"copy": e2e_mode(0, 0, 0.4), "copy_by_ref": e2e_mode(0, 1, 0.4), "pull_by_ref": e2e_mode(1, 1, 0.6), "pull_iovec": e2e_mode(1, 2, 0.4)}
     clocks = sampler.stop()
     for cx in ctxs:
         cx.set_modes(0, 0)
@@ -746,7 +750,7 @@ def main():
                    "blocking_call": {"p50_us": pc(blk, .5), "p99_us": pc(blk, .99), "kernel_launches_per_batch": int(_i["n_launches"]), "iters": len(blk)}}
 
     # ---- reduce over ranks: max time, summed messages; NCCL all-reduce of the bvar-like counters --
-    tv = [dev_ms, wall_ms] + [e2e_modes[k]["ms_per_step"] for k in ("copy", "copy_by_ref", "pull_by_ref")]
+    tv = [dev_ms, wall_ms] + [e2e_modes[k]["ms_per_step"] for k in ("copy", "copy_by_ref", "pull_by_ref", "pull_iovec")]
     t_dev = torch.tensor(tv, dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(n_full)], dtype=torch.float64, device="cuda")
     if use_dist:
@@ -757,7 +761,7 @@ def main():
         counters = counters.tolist()
     else:
         counters = ctx.counters()
-    dev_ms_max, wall_ms_max, e_copy, e_ref, e_pull = t_dev.tolist()
+    dev_ms_max, wall_ms_max, e_copy, e_ref, e_pull, e_iov = t_dev.tolist()
     total_msgs = tot.item()
     ms_per_step = dev_ms_max / steps
     value = total_msgs * ppass / (ms_per_step * 1e-3)
@@ -784,7 +788,8 @@ def main():
                 "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "e2e": e2e,
-                "e2e_modes": {"copy": mk_e2e(e_copy, e2e_modes["copy"]), "copy_by_ref": mk_e2e(e_ref, e2e_modes["copy_by_ref"]), "pull_by_ref": mk_e2e(e_pull, e2e_modes["pull_by_ref"])},
+                "e2e_modes": {"copy": mk_e2e(e_copy, e2e_modes["copy"]), "copy_by_ref": mk_e2e(e_ref, e2e_modes["copy_by_ref"]), "pull_by_ref": mk_e2e(e_pull, e2e_modes["pull_by_ref"]),
+                              "pull_iovec": mk_e2e(e_iov, e2e_modes["pull_iovec"])},
                 "gpu_launches": int(n_launch),
                 "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved / hbm_peak, "traffic": ncu_traffic("k_" + dom, args), "peak_source": peak_src,

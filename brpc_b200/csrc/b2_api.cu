@@ -575,7 +575,7 @@ static void refs_to_iov(b2_ctx* c, b2_batch_result* out, const void* host_bytes)
 }
 
 static int download_normal(b2_ctx* c, b2_batch_result* out) {
-    CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 32, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 48, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (c->n_runs && c->fused_last) {
         // the fused kernel keeps slow replies in an overflow area behind the batch-shaped part of resp: traffic that is mostly
@@ -584,7 +584,7 @@ static int download_normal(b2_ctx* c, b2_batch_result* out) {
         if ((c->h_totals[2] & 2u) && !(c->h_totals[2] & 1u)) {
             c->slow_heavy = true;
             int rc = launch_pipeline(c); if (rc != B2_OK) return rc;
-            CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 32, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 48, cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
         }
         c->slow_heavy = heavy || c->slow_heavy;
@@ -594,6 +594,8 @@ static int download_normal(b2_ctx* c, b2_batch_result* out) {
     if (c->n_runs && (c->h_totals[2] & 3u)) {
         set_err(c->h_totals[2] & 1u ? "more messages than max_msgs" : "responses exceed max_resp_bytes"); return B2_E_CAPACITY;
     }
+    // (k_fused / k_pack_slow: replies of parked messages are placed after the kernel's own end-of-area note, so the span is taken from the allocator)
+    if (c->n_runs && c->fused_last) c->h_totals[1] = ((c->nbytes + 255u) & ~255u) + c->h_totals[9];
     const uint32_t n_msgs = c->n_runs ? c->h_totals[0] : 0, resp_bytes = c->n_runs ? c->h_totals[1] : 0;
     if (c->n_runs) CU(cudaMemcpyAsync(c->h_run_status, c->d_run_status, sizeof(b2_run_status) * c->n_runs, cudaMemcpyDeviceToHost, c->stream));
     if (n_msgs) CU(cudaMemcpyAsync(c->h_msgs, c->d_msgs, sizeof(b2_msg_desc) * (size_t)n_msgs, cudaMemcpyDeviceToHost, c->stream));

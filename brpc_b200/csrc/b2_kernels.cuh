@@ -681,6 +681,7 @@ __device__ __forceinline__ uint32_t fused_overflow_slot(const BatchPtrs& B, cons
     if ((uint64_t)C.ovf_base + so + slot_len > B.max_resp) { atomicOr(B.totals + 2, 2u); return 0; }
     return C.ovf_base + so;
 }
+constexpr uint16_t kDeferred = 0xffff;        // b2_msg_desc.status between k_fused and k_pack_slow: decode not done yet (a gzip / zlib body)
 struct DecodeOut { uint32_t prefix, rs; bool fast, slow; };        // k_fused: reply prefix length, where the reply starts in resp, disposition
 // decode_one = decode_one_impl<kFused, false>, which stops short (returns true, nothing written) at a gzip / zlib body: sizing one walks a
 // DEFLATE stream, and that code must not sit inside the hot instantiation (registers, spills).  Such a message is decoded again by the
@@ -694,8 +695,14 @@ __device__ __noinline__ void decode_one_gz(BatchPtrs B, DevConfig C, uint32_t i,
 template <bool kFused = false>
 __device__ __forceinline__ void decode_one(const BatchPtrs& B, const DevConfig& C, uint32_t i, uint32_t fo_raw,
                                            const uint8_t* srow, uint8_t* shead, uint32_t row_bytes, uint32_t run_idx = kNone, DecodeOut* out = nullptr) {
-    if (decode_one_impl<kFused, false>(B, C, i, fo_raw, srow, shead, row_bytes, run_idx, out))
-        decode_one_gz<kFused>(B, C, i, fo_raw, srow, shead, row_bytes, run_idx, out);
+    if (decode_one_impl<kFused, false>(B, C, i, fo_raw, srow, shead, row_bytes, run_idx, out)) {
+        if (kFused) {
+            // k_fused keeps no call in its loop at all: the message is parked (kDeferred) and decoded by k_pack_slow, which runs behind it
+            b2_msg_desc d; d.run_idx = run_idx; d.frame_off = fo_raw; d.status = kDeferred; d.resp_len = 0; d.resp_off = 0;
+            B.msgs[i] = d;
+            out->fast = false; out->prefix = 0; out->rs = 0; out->slow = true;
+        } else decode_one_gz<kFused>(B, C, i, fo_raw, srow, shead, row_bytes, run_idx, out);
+    }
 }
 
 // one warp round: 32 consecutive messages starting at i0 (staging, decode, head write-out)
@@ -2541,7 +2548,16 @@ __global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs
         if (lane == 0) k = atomicAdd(B.totals + 6, 1u);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n_slow) break;
-        pack_one(B, C, B.slow_idx[k], lane, ct);
+        const uint32_t i = B.slow_idx[k];
+        if (C.fused && B.msgs[i].status == kDeferred) {              // parked by k_fused: the out-of-line decode (sizing pass included), then the pack
+            if (lane == 0) {
+                const uint32_t fo_raw = B.msgs[i].frame_off; DecodeOut o;
+                decode_one_gz<true>(B, C, i, fo_raw, B.bytes + (fo_raw & 0x7fffffffu), B.heads + (size_t)i * kHeadBytes, 0xffffffffu, B.msgs[i].run_idx, &o);
+            }
+            __threadfence_block();
+            __syncwarp();
+        }
+        pack_one(B, C, i, lane, ct);
     }
 }
 

@@ -8,6 +8,8 @@ python bench.py --impl reference --steps 20 > gpurun_out/r2_bench_reference.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches.csv python tools/prof_pass.py 3 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_tile_search|k_tile_walk|k_resolve|k_fused|k_pack_slow" -s 5 -c 5 -o gpurun_out/r2_prof_pipeline \
     python tools/prof_pass.py 1 > gpurun_out/r2_prof_pipeline.log 2>&1
-ncu --set full --clock-control none -k regex:"k_tile_walk_pull|k_decode|k_pack_tma|k_scan_blocks|k_frame_table" -s 10 -c 5 -o gpurun_out/r2_prof_pull \
-    python tools/prof_pass.py 1 1024 0 pull > gpurun_out/r2_prof_pull.log 2>&1
+ncu --set full --clock-control none -k regex:"k_tile_walk_pull|k_decode|k_pack_tma|k_scan_blocks|k_frame_table|k_emit_iov" -s 12 -c 6 -o gpurun_out/r2_prof_pull \
+    python tools/prof_pass.py 1 1024 0 iovec > gpurun_out/r2_prof_pull.log 2>&1
+ncu --set full --clock-control none -k regex:"k_crc_verify" -s 2 -c 1 -o gpurun_out/r2_prof_crc \
+    python tools/prof_pass.py 1 1024 1 > gpurun_out/r2_prof_crc.log 2>&1
 python __graft_entry__.py smoke > gpurun_out/r2_smoke.txt 2>&1
