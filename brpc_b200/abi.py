@@ -335,7 +335,7 @@ class Context:
     def batch_info(self):
         out = (C.c_uint32 * 4)()
         _check(lib.b2_batch_info(self._h, out))
-        return {"tile_bytes": out[0], "n_tiles": out[1], "spec_k": out[2], "fused": bool(out[3]), "onepass": out[3] == 2}
+        return {"tile_bytes": out[0], "n_tiles": out[1], "spec_k": out[2], "fused": bool(out[3])}
 
     def stage_times(self):
         names = (C.c_char_p * 16)()

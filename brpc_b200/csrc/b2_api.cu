@@ -62,9 +62,6 @@ struct b2_ctx {
     int n_stages = 0;
     float last_kernel_ms = 0.f; uint32_t last_launches = 0;
     cudaEvent_t ev_first = nullptr, ev_last = nullptr; bool first_pending = true;
-    // k_onepass: staging arrays in the tile-strided message numbering (allocated on first use), and how it went last time
-    bool use_onepass = true, onepass_last = false; uint32_t onepass_skip = 0; size_t stage_cap = 0; uint32_t* d_spec_count = nullptr;
-    b2_msg_desc* d_msgs_stage = nullptr; MsgAux* d_aux_stage = nullptr; uint8_t* d_heads_stage = nullptr; uint32_t* d_slot_stage = nullptr; uint32_t* d_slow_stage = nullptr;
     bool profile_stages = false; bool allow_small = true; bool use_fused = true; bool fused_last = false; bool slow_heavy = false;   // slow_heavy: the previous batch sent > 1/8 of its messages to k_pack_slow (CRC'd / compressed traffic): the classic pipeline serves that better
     bool adaptive_tile = false; bool dense = false; uint32_t avg_frame = 0;   // tile size follows the message size of the previous batch      // per-stage events only when a harness asks for stage times
     // small-batch (latency) mode: one compact H2D block, one compact output block, one D2H, one sync
@@ -146,8 +143,7 @@ extern "C" void b2_ctx_destroy(b2_ctx* c) {
     cudaFree(c->d_ring_ticket);
     cudaFree(c->d_bytes); cudaFree(c->d_runs); cudaFree(c->d_run_tile_base); cudaFree(c->d_tiles); cudaFree(c->d_tile_base); cudaFree(c->d_tile_scratch); cudaFree(c->d_tile_spec);
     cudaFree(c->d_run_status); cudaFree(c->d_frame_off); cudaFree(c->d_frame_run); cudaFree(c->d_msgs); cudaFree(c->d_aux); cudaFree(c->d_jobs); cudaFree(c->d_slow_idx); cudaFree(c->d_heads); cudaFree(c->d_slot);
-    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_spec_count); cudaFree(c->d_msgs_stage); cudaFree(c->d_aux_stage); cudaFree(c->d_heads_stage); cudaFree(c->d_slot_stage); cudaFree(c->d_slow_stage);
-    cudaFree(c->d_refs); cudaFree(c->d_iov); cudaFreeHost(c->h_iov); cudaFree(c->d_frame_row); cudaFree(c->d_rows); cudaFreeHost(c->h_refs); cudaFree(c->d_hpack); cudaFree(c->d_h2); cudaFree(c->d_h2_streams); cudaFree(c->d_h2_slots); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
+    cudaFree(c->d_scan_tmp); cudaFree(c->d_resp); cudaFree(c->d_unz); cudaFree(c->d_snappy_tab); cudaFree(c->d_refs); cudaFree(c->d_iov); cudaFreeHost(c->h_iov); cudaFree(c->d_frame_row); cudaFree(c->d_rows); cudaFreeHost(c->h_refs); cudaFree(c->d_hpack); cudaFree(c->d_h2); cudaFree(c->d_h2_streams); cudaFree(c->d_h2_slots); cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFree(c->d_methods); cudaFree(c->d_crc_adv); cudaFree(c->d_meta); cudaFree(c->d_small); cudaFreeHost(c->h_meta); cudaFreeHost(c->h_small);
     cudaFreeHost(c->h_run_status); cudaFreeHost(c->h_msgs); cudaFreeHost(c->h_resp); cudaFreeHost(c->h_totals);
     cudaFreeHost(c->h_run_tile_base);
     for (int i = 0; i <= kMaxStages; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -252,7 +248,6 @@ extern "C" int b2_ctx_create(const b2_options* o, b2_ctx** out) {
     if (const char* e = getenv("B2_PACK")) c->use_tma_pack = strcmp(e, "reg") != 0;
     if (const char* e = getenv("B2_SMALL")) c->use_fused_small = strcmp(e, "off") != 0;
     if (const char* e = getenv("B2_FUSED")) c->use_fused = strcmp(e, "off") != 0;
-    if (const char* e = getenv("B2_ONEPASS")) c->use_onepass = strcmp(e, "off") != 0;
     CU(cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(FusedWarpSmem) * kFusedWarps)));
     CU(cudaFuncSetAttribute(k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)));
     *out = c;
@@ -338,7 +333,7 @@ static BatchPtrs make_ptrs(b2_ctx* c) {
     B.tile_base = c->d_tile_base; B.tile_scratch = c->d_tile_scratch; B.tile_spec = c->d_tile_spec; B.run_status = c->d_run_status; B.frame_off = c->d_frame_off; B.frame_run = c->d_frame_run; B.frame_row = c->d_frame_row; B.rows = c->d_rows; B.msgs = c->d_msgs;
     B.aux = c->d_aux; B.jobs = c->d_jobs; B.refs = c->d_refs; B.slow_idx = c->d_slow_idx; B.heads = c->d_heads; B.slot = c->d_slot; B.scan_tmp = c->d_scan_tmp; B.resp = c->d_resp; B.unz = c->d_unz; B.snappy_tab = c->d_snappy_tab; B.counters = c->d_counters;
     B.totals = c->d_totals; B.methods = c->d_methods; B.crc_adv = c->d_crc_adv;
-    B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes; B.spec_count = c->d_spec_count;
+    B.n_runs = c->n_runs; B.n_tiles = c->n_tiles; B.max_msgs = c->opt.max_msgs; B.max_resp = c->opt.max_resp_bytes;
     B.runs = reinterpret_cast<const b2_run*>(c->d_meta);
     B.run_tile_base = reinterpret_cast<const uint32_t*>(c->d_meta + (size_t)c->n_runs * sizeof(b2_run));
     B.tile_info = reinterpret_cast<const uint4*>(c->d_meta + c->meta_tile_off);
@@ -425,7 +420,6 @@ extern "C" int b2_batch_upload(b2_ctx* c, const void* bytes, uint32_t nbytes, co
     return B2_OK;
 }
 
-static bool prof_staged(const b2_ctx*) { return false; }      // (hook for timing experiments that need the staged kernels one by one)
 static int launch_pipeline(b2_ctx* c) {
     const BatchPtrs B = make_ptrs(c);
     DevConfig C = c->cfg;
@@ -450,36 +444,6 @@ static int launch_pipeline(b2_ctx* c) {
         return B2_OK;
     }
     const uint32_t sms = c->n_sms;
-    // ---- one load per tile: k_onepass does search + walk + decode + echo + pack on speculation, k_resolve then verifies and numbers
-    bool onepass = fused && c->use_onepass && !prof_staged(c) && c->onepass_skip == 0 && c->cfg.tile_bytes == 8192 && c->cfg.spec_k == kSpecK && mask == 7 && c->n_tiles;
-    if (c->onepass_skip) c->onepass_skip--;
-    if (onepass && !c->d_msgs_stage) {
-        const size_t cap = ((size_t)c->opt.max_batch_bytes / 8192 + c->opt.max_runs + 1) * kSpecK;
-        bool ok = cudaMalloc((void**)&c->d_msgs_stage, cap * sizeof(b2_msg_desc)) == cudaSuccess && cudaMalloc((void**)&c->d_aux_stage, cap * sizeof(MsgAux)) == cudaSuccess &&
-                  cudaMalloc((void**)&c->d_heads_stage, cap * kHeadBytes) == cudaSuccess && cudaMalloc((void**)&c->d_slot_stage, cap * 4) == cudaSuccess &&
-                  cudaMalloc((void**)&c->d_slow_stage, cap * 4) == cudaSuccess && cudaMalloc((void**)&c->d_spec_count, (cap / kSpecK) * 4) == cudaSuccess;
-        if (!ok) { cudaGetLastError(); c->use_onepass = false; onepass = false; } else c->stage_cap = cap;
-    }
-    c->onepass_last = onepass;
-    if (onepass) {
-        BatchPtrs Bs = B; Bs.msgs = c->d_msgs_stage; Bs.aux = c->d_aux_stage; Bs.heads = c->d_heads_stage; Bs.slot = c->d_slot_stage; Bs.slow_idx = c->d_slow_stage;
-        Bs.max_msgs = (uint32_t)c->stage_cap; Bs.spec_count = c->d_spec_count;
-        C.onepass = 1;
-        // room behind the tile for the tail of its last frame: 1.5 x the average frame of the previous batches, at least 1 KiB
-        uint32_t over = c->avg_frame ? c->avg_frame + c->avg_frame / 2 + 64 : kFusedBuf; if (over < 1024) over = 1024; over = (over + 15u) & ~15u;
-        if (over > kFusedBuf - 8192) over = kFusedBuf - 8192;
-        C.op_window = 8192 + over;
-        k_onepass<<<sms, kFusedWarps * 32, sizeof(FusedWarpSmem) * kFusedWarps, s>>>(Bs, C); launches++; mark("onepass");
-        size_t smem = (size_t)c->max_run_tiles * 12;
-        if (smem > 200 * 1024) smem = 0;
-        k_resolve<<<c->n_runs, 256, smem, s>>>(Bs, C, smem == 0 ? 1u : 0u); launches++; mark("resolve");
-        k_pack_slow<true><<<sms * B2_SLOW_MIN_BLOCKS, 256, 0, s>>>(Bs, C); launches++; mark("pack_slow");
-        k_compact<<<(uint32_t)(((uint64_t)c->n_tiles * kSpecK * 4 + 255) / 256), 256, 0, s>>>(Bs, c->d_msgs, c->opt.max_msgs, C); launches++; mark("compact");
-        if (!prof) { c->stage_names[0] = "pipeline"; cudaEventRecord(c->ev[1], s); st = 1; }
-        c->n_stages = st; c->last_launches = launches;
-        CU(cudaGetLastError());
-        return B2_OK;
-    }
     if (mask & 1) {
     if (c->n_tiles) {
         k_tile_search<<<(c->n_tiles * 32 + 255) / 256, 256, 0, s>>>(B, C); launches++; mark("tile_search");
@@ -613,14 +577,6 @@ static void refs_to_iov(b2_ctx* c, b2_batch_result* out, const void* host_bytes)
 static int download_normal(b2_ctx* c, b2_batch_result* out) {
     CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 48, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (c->n_runs && c->onepass_last && (c->h_totals[2] & 4u) && !(c->h_totals[2] & 1u)) {
-        // k_resolve did not confirm k_onepass's speculative work (payload bytes that look like frames, frames larger than a tile, parse
-        // errors inside a run ...): the staged pipeline serves this batch, and the next few, from the same resident bytes
-        c->onepass_skip = 16;
-        int rc = launch_pipeline(c); if (rc != B2_OK) return rc;
-        CU(cudaMemcpyAsync(c->h_totals, c->d_totals, 48, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-    }
     if (c->n_runs && c->fused_last) {
         // the fused kernel keeps slow replies in an overflow area behind the batch-shaped part of resp: traffic that is mostly
         // CRC'd / compressed / errors is better served (and may only fit) through the slot-scan pipeline
@@ -878,7 +834,7 @@ extern "C" int b2_stage_times(b2_ctx* c, const char** names, float* ms, int cap)
 // what the last upload / launch decided: [0] tile bytes [1] tiles [2] frame offsets kept per tile [3] 1 = the fused kernel served it
 extern "C" int b2_batch_info(b2_ctx* c, uint32_t out[4]) {
     if (!c || !out) return B2_E_INVAL;
-    out[0] = c->cfg.tile_bytes; out[1] = c->n_tiles; out[2] = c->cfg.spec_k; out[3] = c->onepass_last ? 2u : c->fused_last ? 1u : 0u;
+    out[0] = c->cfg.tile_bytes; out[1] = c->n_tiles; out[2] = c->cfg.spec_k; out[3] = c->fused_last ? 1u : 0u;
     return B2_OK;
 }
 

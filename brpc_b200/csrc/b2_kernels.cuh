@@ -79,8 +79,6 @@ struct DevConfig {
     uint32_t stream_handler;      // B2_STREAM_*
     uint32_t spec_k;              // speculative frame offsets kept per tile: kSpecK, or kSpecKDense when tiles hold many small frames
     uint32_t by_ref;              // B2_RESP_BY_REF: OK echo replies are {prefix, reference into the request bytes}
-    uint32_t onepass;             // the batch went through k_onepass: k_resolve also judges whether its speculative work stands
-    uint32_t op_window;           // k_onepass: bytes loaded per tile (tile + room for the last frame's tail)
     uint32_t verify_done;         // k_crc_verify already checked the CRC-carrying echoes: k_pack_slow skips its own verify pass
     uint32_t proto_mask;          // handlers of the messenger (bit = ProtocolType): default baidu_std | streaming_rpc; b2_set_protocols adds hulu / sofa / nshead
     uint32_t fused;               // the fused decode+pack kernel serves this batch: replies sit at their request's own offset, slow ones in the overflow area
@@ -123,7 +121,6 @@ struct BatchPtrs {
     const DevMethod* methods;
     const uint32_t* crc_adv;         // warp CRC tables: hot [20][256] then tree [5][4][256]
     uint32_t n_runs, n_tiles, max_msgs, max_resp;
-    uint32_t* spec_count;            // k_onepass: messages it decoded in each tile on speculation (kNone = it could not serve the tile)
 };
 
 // ---------------------------------------------------------------------------
@@ -532,22 +529,6 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C, uint3
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) { s_carry_sum = carry_sum + wsum + x; s_carry_pf = incl_pf; }
         __syncthreads();
-    }
-    if (C.onepass) {
-        // k_onepass decoded and answered every tile as IT walked it; that work stands only if the verified chain uses exactly those walks:
-        // a live tile as speculated (same count, not re-walked), no messages in a tile it could not serve, nothing decoded in a dead tile
-        // (its replies went on top of a live frame's bytes).  Anything else: totals[2] |= 4, the host re-runs the batch on the staged pipeline.
-        __syncthreads();
-        bool bad = false;
-        for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) {
-            const TileRec t = tiles[k];
-            const uint32_t spec = B.spec_count[tb + k];
-            const bool rew = (t.kind & kKindRewalked) != 0;
-            if (spec == kNone) bad |= t.live && t.count > 0;
-            else if (t.live) bad |= rew ? (t.count > 0 || spec > 0) : (t.count != spec);
-            else bad |= spec > 0;
-        }
-        if (bad) atomicOr(B.totals + 2, 4u);
     }
     if (threadIdx.x == 0) {
         const uint32_t pos = s_final_pos;
@@ -2308,172 +2289,6 @@ __global__ void __maxnreg__(B2_FUSED_REGS) k_fused(BatchPtrs B, DevConfig C) {
 }
 
 
-// --- k_onepass: search + walk + decode + echo + pack of a tile from ONE load of its bytes -----------------------------------------------
-// k_tile_search and k_tile_walk read headers out of HBM that k_fused then loads again with the whole tile.  Here a warp loads its tile
-// (plus room for the tail of the last frame that starts in it) once, finds the speculative entry and walks the frame chain IN SHARED
-// MEMORY (same rules as k_tile_search / walk_tile_spec), decodes and answers the messages in place like k_fused, and stores the reply
-// bytes.  Message numbers are not known yet (they need every earlier tile's count), so descriptors go to a tile-strided staging array
-// (tile t, j-th message -> t * spec_k + j) and k_compact moves them once k_resolve — which runs AFTER this kernel, on the TileRecs written
-// here — has verified the chain and numbered the tiles.  k_resolve stays the exactness gate: if the verified chain does not use exactly
-// these walks (a tile re-walked, a speculated tile dead, a tile this kernel could not serve), the batch is flagged and re-run staged.
-__device__ __forceinline__ uint32_t onepass_search(const uint8_t* sb, uint32_t t0, uint32_t t1, uint32_t len, const DevConfig& C, uint32_t lane) {
-    uint32_t entry = kNone;
-    const bool ext = (C.proto_mask & ((1u << 3) | (1u << 4))) != 0;
-    for (uint32_t w0 = t0; w0 < t1 && entry == kNone; w0 += 512u) {
-        const uint32_t p0 = w0 + lane * 16;
-        uint4 v = make_uint4(0, 0, 0, 0); uint32_t nx = 0;
-        if (p0 < t1) { v = *reinterpret_cast<const uint4*>(sb + (p0 - t0)); nx = *reinterpret_cast<const uint32_t*>(sb + (p0 - t0) + 16); }
-        const uint32_t w[5] = { v.x, v.y, v.z, v.w, nx };
-        uint32_t mask = 0, mkind = 0;
-        #pragma unroll
-        for (int k4 = 0; k4 < 4; k4++) {
-            uint32_t e = __vcmpeq4(w[k4], 0x50505050u) | __vcmpeq4(w[k4], 0x53535353u);
-            if (ext) e |= __vcmpeq4(w[k4], 0x48484848u);
-            while (e) {
-                const int b = (__ffs(e) - 1) >> 3;
-                e &= ~(0xffu << (8 * b));
-                const int j = 4 * k4 + b;
-                const uint32_t word = __funnelshift_r(w[k4], w[k4 + 1], b * 8);
-                const bool other = ext && ((word == kMagicHULU && (C.proto_mask & 8u)) || (word == kMagicSOFA && (C.proto_mask & 16u)));
-                if ((is_magic(word) || other) && p0 + j + 4 <= len && p0 + j < t1) { mask |= 1u << j; if (other) mkind |= (word == kMagicHULU ? 1u : 2u) << (2 * j); }
-            }
-        }
-        uint32_t any = __ballot_sync(0xffffffffu, mask != 0);
-        while (any && entry == kNone) {
-            const int src = __ffs(any) - 1;
-            uint32_t m = __shfl_sync(0xffffffffu, mask, src);
-            const uint32_t kinds = __shfl_sync(0xffffffffu, mkind, src);
-            while (m && entry == kNone) {
-                const int jj = __ffs(m) - 1;
-                const uint32_t p = w0 + src * 16 + jj;
-                m &= m - 1;
-                const uint32_t kind = (kinds >> (2 * jj)) & 3u;
-                if (kind == 2) { entry = p; break; }
-                if (p + 12 > len) continue;
-                const uint8_t* h = sb + (p - t0);                       // (the whole header is in the tile image: a warp-uniform read)
-                const uint32_t body = kind == 1 ? load_le32(h + 4) : load_be32(h + 4), meta = kind == 1 ? load_le32(h + 8) : load_be32(h + 8);
-                if (meta <= body && (uint64_t)body <= C.max_body_size) entry = p;
-            }
-            any &= any - 1;
-        }
-    }
-    return entry;
-}
-
-__global__ void __maxnreg__(B2_FUSED_REGS) k_onepass(BatchPtrs B, DevConfig C) {
-    extern __shared__ __align__(128) uint8_t fused_raw[];
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    FusedWarpSmem& S = reinterpret_cast<FusedWarpSmem*>(fused_raw)[wid];
-    __shared__ __align__(16) DevMethod s_methods[2];
-    {
-        const uint32_t nw = min(C.n_methods, 2u) * (uint32_t)(sizeof(DevMethod) / 4);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(B.methods); uint32_t* dst = reinterpret_cast<uint32_t*>(s_methods);
-        for (uint32_t k = threadIdx.x; k < nw; k += blockDim.x) dst[k] = src[k];
-    }
-    __syncthreads();
-    const DevMethod* ms = C.n_methods <= 2 ? s_methods : B.methods;
-    if (lane == 0) { mbar_init(&S.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    __syncwarp();
-    uint32_t phase = 0;
-    const uint32_t n_warps = gridDim.x * kFusedWarps, K = C.spec_k;
-    uint32_t t = blockIdx.x * kFusedWarps + wid;
-    uint4 ti_next = make_uint4(0, 0, 0, 0);
-    if (t < B.n_tiles) ti_next = __ldg(B.tile_info + t);
-    for (; t < B.n_tiles; t += n_warps) {
-        const uint4 ti = ti_next;
-        if (t + n_warps < B.n_tiles) ti_next = __ldg(B.tile_info + t + n_warps);
-        const uint32_t r = ti.w & 0xffffffu, run_off = ti.x, run_len = ti.y, k = ti.z, flags = ti.w >> 24;
-        const bool client = (flags & B2_RUN_CLIENT) != 0, dump = (flags & B2_RUN_RPC_DUMP) != 0;
-        const uint32_t t0 = k << C.tile_shift, tile_end = t0 + C.tile_bytes, t1 = min(tile_end, run_len);
-        const uint32_t lo16 = run_off + t0;                                  // (run offsets and tile sizes are multiples of 16)
-        const uint32_t win = min(C.op_window, (run_len - t0 + 15u) & ~15u);  // the batch buffer is padded past its end
-        // ---- the tile's bytes, once
-        if (lane == 0) { bulk_wait_read<0>(); mbar_arrive_expect_tx(&S.mbar, win); bulk_g2s(S.buf, B.bytes + lo16, win, &S.mbar); }
-        __syncwarp();
-        mbar_wait(&S.mbar, phase & 1u); phase++;
-        // ---- speculative entry (k_tile_search's rule) and the frame chain from it (walk_tile_spec's rules), out of shared memory
-        const uint32_t entry = k == 0 ? 0u : onepass_search(S.buf, t0, t1, run_len, C, lane);
-        uint32_t count = 0, exit_pos = 0, kind = kStop; int last = 0;
-        if (lane == 0 && entry != kNone) {
-            const uint8_t* run_s = S.buf - t0;                              // run_s + pos is the image of run byte pos, for pos inside the window
-            const uint32_t pmask = run_mask(C.proto_mask, flags);
-            uint32_t pos = entry; int pf = -1; kind = kRanOff;
-            while (pos < tile_end) {
-                Step sp; bool fast = false;
-                if (run_len - pos >= 12) {
-                    const uint8_t* h = run_s + pos;
-                    const uint32_t h0 = load_le32(h), body = load_be32(h + 4), meta = load_be32(h + 8);
-                    const int idx = h0 == kMagicPRPC ? 1 : h0 == kMagicSTRM ? 2 : 0;
-                    if (idx && ((pmask >> idx) & 1u) && pf != 12 && (uint64_t)body <= C.max_body_size && (uint64_t)(run_len - pos) >= 12ull + body && meta <= body) {
-                        sp.err = B2_PARSE_OK; sp.index = idx; sp.pf = idx; sp.frame_pos = pos; sp.new_pos = pos + 12 + body; sp.body = body; sp.meta = meta; sp.popped = false;
-                        fast = true;
-                    }
-                }
-                if (!fast) sp = cut_input_message(run_s, run_len, pos, pf, C.max_body_size, client, pmask);
-                if (count == 0 && (sp.popped || (sp.index != 12 && nshead_claims(run_s, run_len, pos, C.max_body_size, pmask)))) { kind = kAmbig; break; }
-                if (sp.err != B2_PARSE_OK) { kind = kStop; break; }
-                if (count < 32) S.foff[count] = (run_off + sp.frame_pos) | ((uint32_t)(sp.index != 1) << 31);
-                count++; last = sp.index; pf = sp.index; pos = sp.new_pos;
-            }
-            exit_pos = pos;
-        }
-        count = __shfl_sync(0xffffffffu, count, 0); exit_pos = __shfl_sync(0xffffffffu, exit_pos, 0);
-        // every frame that starts here must lie inside the window (it is decoded and answered in place)
-        const bool served = count <= min(32u, K) && (count == 0 || exit_pos - t0 <= win);
-        if (lane == 0) {
-            TileRec rec; rec.entry = entry; rec.exit = exit_pos; rec.count = count; rec.kind = (uint8_t)kind; rec.last_proto = (int8_t)last; rec.live = 0; rec.pf_in = -1;
-            if (entry == kNone) { rec.exit = 0; rec.count = 0; rec.kind = kStop; rec.last_proto = 0; }
-            B.tiles[t] = rec;
-            B.spec_count[t] = served ? count : kNone;
-        }
-        __syncwarp();
-        if (!served || count == 0) continue;
-        // ---- decode, echo, pack: k_fused's in-place round over the same image
-        const uint32_t cnt = count;
-        const uint32_t sub_lo = run_off + entry, sub_hi = run_off + exit_pos;
-        uint32_t fo_raw = 0;
-        if (lane < cnt) fo_raw = S.foff[lane];
-        const uint32_t i = t * K + lane;
-        const uint32_t fo = fo_raw & 0x7fffffffu;
-        DecodeOut o; o.fast = false; o.slow = false; o.prefix = 0; o.rs = 0;
-        bool in_place = false;
-        if (lane < cnt && i < B.max_msgs) {
-            uint8_t* f = S.buf + (fo - lo16);
-            in_place = !client && !dump && !(fo_raw >> 31) && fused_fast_echo(B, ms, C.n_methods, i, fo, r, f, lo16 + win - fo, nullptr, o);
-            if (!in_place) decode_one<true>(B, C, i, fo_raw, f, B.heads + (size_t)i * kHeadBytes, 0xffffffffu, r, &o);
-        }
-        if (in_place) o.prefix = 0;
-        const uint32_t slow_mask = __ballot_sync(0xffffffffu, o.slow);
-        if (slow_mask) {
-            uint32_t sbase = 0;
-            if (lane == 0) sbase = atomicAdd(B.totals + 3, (uint32_t)__popc(slow_mask));
-            sbase = __shfl_sync(0xffffffffu, sbase, 0);
-            if (o.slow) B.slow_idx[sbase + __popc(slow_mask & ((1u << lane) - 1u))] = i;
-        }
-        if (o.fast && o.prefix) { uint8_t* dst = S.buf + (o.rs - lo16); const uint8_t* src = B.heads + (size_t)i * kHeadBytes; for (uint32_t q = 0; q < o.prefix; q++) dst[q] = src[q]; }
-        fence_proxy_async();
-        __syncwarp();
-        fused_store(B.resp, S.buf, lo16, sub_lo, sub_hi, lane);
-        if (lane == 0) bulk_commit();
-        __syncwarp();
-    }
-    if (lane == 0) bulk_wait<0>();
-}
-
-// --- k_compact: staged descriptors (tile t, message j -> t * spec_k + j) to their final, run-ordered places; four threads per descriptor
-__global__ void __launch_bounds__(256) k_compact(BatchPtrs Bs, b2_msg_desc* out, uint32_t out_cap, DevConfig C) {
-    if (Bs.totals[2] & 7u) return;
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x, K = C.spec_k;
-    const uint32_t t = g / (K * 4), rem = g % (K * 4), j = rem >> 2, q = rem & 3u;
-    if (t >= Bs.n_tiles) return;
-    const TileRec rec = Bs.tiles[t];
-    if (!rec.live || j >= rec.count) return;
-    const uint32_t r = __ldg(Bs.tile_info + t).w & 0xffffffu;
-    const uint32_t dst = Bs.run_status[r].first_msg + Bs.tile_base[t] + j;
-    if (dst >= out_cap) return;
-    reinterpret_cast<uint4*>(out + dst)[q] = reinterpret_cast<const uint4*>(Bs.msgs + (size_t)t * K + j)[q];
-}
-
 // --- k_pack_requests: the client mirror -------------------------------------------------------------
 // PackRpcRequest + SerializeRpcRequest (baidu_rpc_protocol.cpp:1015-1133) and PackStreamMessage
 // (streaming_rpc_protocol.cpp:42-58): one warp per frame.  The meta length does not depend on the body, so the
@@ -2699,7 +2514,7 @@ __global__ void __launch_bounds__(256) k_pack_responses(const uint8_t* bytes, co
 template <bool kLite>
 __global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs B, DevConfig C) {
     const uint32_t lane = threadIdx.x & 31;
-    if (B.totals[2] & 7u) return;                      // (4: k_resolve turned k_onepass's speculative work down — the batch is re-run staged)
+    if (B.totals[2] & 3u) return;
     finalize_runs(B, C);                               // (was a separate launch)
     const uint32_t n_verify = C.verify_done ? 0u : B.totals[7];
     if (B.totals[3] == 0 && n_verify == 0) return;

@@ -362,9 +362,8 @@ int  b2_batch_launch(b2_ctx* ctx);
 int  b2_batch_wait(b2_ctx* ctx);
 int  b2_elapsed_ms(b2_ctx* a, b2_ctx* b, float* ms);
 
-/* What the last upload / launch decided: out[0] tile bytes, [1] tiles, [2] frame offsets kept per tile, [3] which pipeline served the
- * batch: 2 = k_onepass (search + walk + decode + pack from one load per tile), 1 = the fused decode+pack kernel behind the staged front
- * kernels (also what serves a batch whose one-pass speculation k_resolve turned down), 0 = the slot-scan pipeline. */
+/* What the last upload / launch decided: out[0] tile bytes, [1] tiles, [2] frame offsets kept per tile, [3] 1 = the fused
+ * decode+pack kernel served the batch (0 = the slot-scan pipeline). */
 int  b2_batch_info(b2_ctx* ctx, uint32_t out[4]);
 
 /* PCI bus id ("0000:1b:00.0") of a device, for a host side that wants to run its polling threads and first-touch its pinned blocks on

@@ -10,6 +10,6 @@ ncu --set full --clock-control none --import-source on -k regex:"k_tile_search|k
     python tools/prof_pass.py 1 > gpurun_out/r2_prof_pipeline.log 2>&1
 ncu --set full --clock-control none -k regex:"k_tile_walk_pull|k_decode|k_pack_tma|k_scan_blocks|k_frame_table|k_emit_iov" -s 12 -c 6 -o gpurun_out/r2_prof_pull \
     python tools/prof_pass.py 1 1024 0 iovec > gpurun_out/r2_prof_pull.log 2>&1
-ncu --set full --clock-control none -k regex:"k_crc_verify" -s 2 -c 1 -o gpurun_out/r2_prof_crc \
+ncu --set full --clock-control none -k regex:"k_crc_verify" -s 1 -c 1 -o gpurun_out/r2_prof_crc \
     python tools/prof_pass.py 1 1024 1 > gpurun_out/r2_prof_crc.log 2>&1
 python __graft_entry__.py smoke > gpurun_out/r2_smoke.txt 2>&1
