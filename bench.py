@@ -126,7 +126,7 @@ def ncu_traffic(kernel, args):
 def build_batch(run_mib, rank, pinned=True, payload=PAYLOAD, checksum=0, kind=0):
     from brpc_b200 import press
     from brpc_b200.abi import PinnedBuffer
-    run_bytes = (run_mib << 20) - 16 * 7          # not a multiple of the frame: every run ends mid-frame
+    run_bytes = int(run_mib * (1 << 20)) - 16 * 7          # not a multiple of the frame: every run ends mid-frame
     stride = (run_bytes + 15) // 16 * 16
     nbytes = N_SOCKETS * stride
     buf = PinnedBuffer(nbytes) if pinned else None
@@ -493,7 +493,7 @@ def socket_ids_of(rank, world):
 
 def fill_batch_plain(data, run_mib, rank, world, payload=PAYLOAD, checksum=0, kind=0):
     lib, Spec = load_press()
-    run_bytes = (run_mib << 20) - 16 * 7
+    run_bytes = int(run_mib * (1 << 20)) - 16 * 7
     stride = (run_bytes + 15) // 16 * 16
     sp = Spec(b"example.EchoService", b"Echo", payload, 0, kind, checksum, 20260921)
     ids = socket_ids_of(rank, world)
@@ -512,7 +512,8 @@ def main():
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--run-mib", type=int, default=4, help="MiB pending per connection per batch")
+    ap.add_argument("--run-mib", type=float, default=4, help="MiB pending per connection per batch (a fraction for many small connections)")
+    ap.add_argument("--sockets", type=int, default=64, help="connections per GPU in one batch (the rpc_press sweep of BASELINE configs[2] uses 1024)")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--payload", type=int, default=1024, help="EchoRequest.message bytes (rpc_press sweep: 64..65536)")
@@ -525,6 +526,10 @@ def main():
                     help="echo = the headline metric; stream_snappy = BASELINE configs[4] (256 KiB snappy streaming frames), grpc_h2 = configs[3]")
     ap.add_argument("--frames-per-stream", type=int, default=8)
     args = ap.parse_args()
+    global N_SOCKETS
+    N_SOCKETS = max(1, args.sockets)
+    if args.run_mib == int(args.run_mib):
+        args.run_mib = int(args.run_mib)
     if args.workload == "stream_snappy":
         return stream_snappy_main(args)
     if args.workload == "grpc_h2":
@@ -534,8 +539,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     hbm_peak, peak_src = read_peaks()
     ncores = os.cpu_count() or 1
-    workload = ("multi_threaded_echo_c++ baidu_std %d B payload: %d connections/GPU x %d MiB pending, "
-                "runs cut mid-frame; batch %d MiB > L2 (no flush needed)" % (args.payload, N_SOCKETS, args.run_mib, N_SOCKETS * args.run_mib))
+    workload = ("multi_threaded_echo_c++ baidu_std %d B payload: %d connections/GPU x %s MiB pending, runs cut mid-frame; batch %d MiB > L2 (no flush needed)"
+                % (args.payload, N_SOCKETS, args.run_mib, int(N_SOCKETS * args.run_mib)))
     config = {"workload": workload, "payload_bytes": args.payload, "request_checksum": args.checksum, "connections_per_gpu": N_SOCKETS,
               "run_mib": args.run_mib, "l2": "inputs larger than L2", "pipeline_depth": args.pipeline,
               "sharding": "gpu = (socket_id & 0xffffffff) %% %d (shard.owner_of)" % max(1, world),
@@ -544,7 +549,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        nb = N_SOCKETS * (((args.run_mib << 20) - 112 + 15) // 16 * 16)
+        nb = N_SOCKETS * ((int(args.run_mib * (1 << 20)) - 112 + 15) // 16 * 16)
         data = np.zeros(nb, np.uint8)
         runs, n_full, nbytes = fill_batch_plain(data, args.run_mib, 0, 1, payload=args.payload, checksum=args.checksum, kind=args.payload_kind)
         t0 = time.perf_counter()
@@ -577,7 +582,7 @@ def main():
     torch.cuda.set_device(dev)
     numa_cpus = pin_to_gpu_numa(dev)        # pinned buffers are allocated (first touched) on the GPU's own NUMA node
 
-    nb = N_SOCKETS * (((args.run_mib << 20) - 112 + 15) // 16 * 16)
+    nb = N_SOCKETS * ((int(args.run_mib * (1 << 20)) - 112 + 15) // 16 * 16)
     buf = PinnedBuffer(nb); data = buf.array
     runs, n_full, nbytes = fill_batch_plain(data, args.run_mib, rank, world, payload=args.payload, checksum=args.checksum, kind=args.payload_kind)
     from brpc_b200 import shard
@@ -810,7 +815,7 @@ def main():
                 try:
                     for cx in ctxs:
                         cx.close()
-                    out = subprocess.run([tb, "bench", str(args.run_mib), "40", "1", "2", "8", "2"], capture_output=True, text=True, timeout=120)
+                    out = subprocess.run([tb, "bench", str(int(args.run_mib)), "40", "1", "2", "8", "2"], capture_output=True, text=True, timeout=120)
                     line["e2e_messenger"] = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else {"error": (out.stderr or out.stdout)[-300:]}
                 except Exception as e:      # noqa: BLE001
                     line["e2e_messenger"] = {"error": repr(e)}

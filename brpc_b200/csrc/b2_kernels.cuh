@@ -1903,6 +1903,10 @@ __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t 
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
+// L2 prefetch of a byte range (16-byte aligned address and size): the DRAM reads start now, the later bulk load finds the lines in L2
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
@@ -2149,6 +2153,9 @@ __device__ __forceinline__ void fused_store(uint8_t* resp, const uint8_t* img, u
 #ifndef B2_FUSED_REGS
 #define B2_FUSED_REGS 128
 #endif
+#ifndef B2_FUSED_PREFETCH
+#define B2_FUSED_PREFETCH 1
+#endif
 static_assert(B2_FUSED_REGS * B2_FUSED_WARPS * 32 <= 65536, "k_fused: registers x threads must fit the SM's register file");
 __global__ void __maxnreg__(B2_FUSED_REGS) k_fused(BatchPtrs B, DevConfig C) {
     extern __shared__ __align__(128) uint8_t fused_raw[];
@@ -2179,6 +2186,7 @@ __global__ void __maxnreg__(B2_FUSED_REGS) k_fused(BatchPtrs B, DevConfig C) {
         TileRec rec; *reinterpret_cast<uint4*>(&rec) = rec_cur;
         const uint32_t count = rec.count;
         if (!rec.live || count == 0) continue;
+        const uint4 ti_nx = ti;                                      // (the NEXT tile's run record, loaded above)
         const uint4 ti = ti_cur;
         const uint32_t r = ti.w & 0xffffffu, run_off = ti.x, run_len = ti.y;
         const bool client = ((ti.w >> 24) & B2_RUN_CLIENT) != 0, dump = ((ti.w >> 24) & B2_RUN_RPC_DUMP) != 0;
@@ -2215,6 +2223,17 @@ __global__ void __maxnreg__(B2_FUSED_REGS) k_fused(BatchPtrs B, DevConfig C) {
             if (fits) {
                 // ---- the whole round in one buffer: load, decode in place, patch, store
                 if (lane == 0) { bulk_wait_read<0>(); mbar_arrive_expect_tx(&S.mbar, span); bulk_g2s(S.buf, B.bytes + lo16, span, &S.mbar); }
+#if B2_FUSED_PREFETCH
+                // while this tile is on its way: ask for the NEXT tile's bytes (its record arrived meanwhile) to be brought into L2, so that a
+                // warp has two tiles' worth of DRAM reads in flight with one staging buffer
+                if (lane == 0 && done == 0 && tn < B.n_tiles) {
+                    TileRec nx; *reinterpret_cast<uint4*>(&nx) = rec_raw;
+                    if (nx.live && nx.count) {
+                        const uint32_t plo = (ti_nx.x + nx.entry) & ~15u, phi = (ti_nx.x + nx.exit + 15u) & ~15u;
+                        if (phi > plo) bulk_prefetch_l2(B.bytes + plo, min(phi - plo, 2u * kFusedBuf));
+                    }
+                }
+#endif
                 __syncwarp();
                 mbar_wait(&S.mbar, phase & 1u); phase++;
                 bool in_place = false;

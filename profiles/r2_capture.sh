@@ -13,3 +13,8 @@ ncu --set full --clock-control none -k regex:"k_tile_walk_pull|k_decode|k_pack_t
 ncu --set full --clock-control none -k regex:"k_crc_verify" -s 1 -c 1 -o gpurun_out/r2_prof_crc \
     python tools/prof_pass.py 1 1024 1 > gpurun_out/r2_prof_crc.log 2>&1
 python __graft_entry__.py smoke > gpurun_out/r2_smoke.txt 2>&1
+# memcheck over the paths added this round (gzip / zlib inflate, host-produced replies, the iovec list, the latency path)
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest -m gpu -q -x \
+    tests/test_gpu_replies.py "tests/test_gpu_gzip.py::test_gzip_requests_on_the_latency_path_and_with_snappy_replies" \
+    "tests/test_gpu_gzip.py::test_bodies_beyond_the_device_limit_go_to_the_host" tests/test_gpu_ring.py > gpurun_out/r2_sanitizer.txt 2>&1
+tail -5 gpurun_out/r2_sanitizer.txt
