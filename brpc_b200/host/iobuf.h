@@ -83,7 +83,10 @@ public:
             Block* b = nullptr;
             if (!_refs.empty()) {
                 BlockRef& r = _refs.back();
-                if (!r.block->user_deleter && !r.block->full() && r.offset + r.length == r.block->size) b = r.block;
+                // only a block nobody else references is extended in place: a buffer that shares it (a message cut off a read buffer and handed
+                // to another thread, a copy) may be appended to as well, and two writers behind the same `size` would collide.  The producer of
+                // the block — IOPortal, the only writer of its read blocks — keeps filling it (butil's TLS-block rule, iobuf.cpp:245-330)
+                if (!r.block->user_deleter && !r.block->full() && r.offset + r.length == r.block->size && r.block->nshared.load(std::memory_order_acquire) == 1) b = r.block;
             }
             if (!b) {
                 b = create_block();
