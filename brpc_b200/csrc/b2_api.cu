@@ -2,6 +2,7 @@
 // Host code is plain C++ + the CUDA runtime; nothing here computes on the CPU:
 // without a CUDA device every entry point fails with B2_E_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdio.h>
 #include <time.h>
 #include <stdlib.h>
@@ -851,6 +852,18 @@ extern "C" int b2_counters_read(b2_ctx* c, int64_t out[B2_N_COUNTERS]) {
     return B2_OK;
 }
 extern "C" void* b2_counters_device_ptr(b2_ctx* c) { return c ? (void*)c->d_counters : nullptr; }
+// ncclAllReduce(sendbuff, recvbuff, count, ncclInt64 = 4, ncclSum = 0, comm, stream) — nccl.h; looked up in the process, not linked
+extern "C" int b2_counters_allreduce(b2_ctx* c, void* nccl_comm) {
+    if (!c || !nccl_comm) { set_err("null argument"); return B2_E_INVAL; }
+    typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    static allreduce_fn fn = reinterpret_cast<allreduce_fn>(dlsym(RTLD_DEFAULT, "ncclAllReduce"));
+    if (!fn) { set_err("ncclAllReduce is not loaded in this process"); return B2_E_INVAL; }
+    CU(cudaSetDevice(c->opt.device));
+    const int rc = fn(c->d_counters, c->d_counters, B2_N_COUNTERS, 4 /*ncclInt64*/, 0 /*ncclSum*/, nccl_comm, c->stream);
+    if (rc != 0) { char code[16]; snprintf(code, sizeof code, "%d", rc); set_err("ncclAllReduce failed: ncclResult_t %s", code); return B2_E_CUDA; }
+    CU(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
 
 // device pointers of the resident batch, for harnesses that time or inspect kernels directly
 extern "C" void* b2_debug_resp_device_ptr(b2_ctx* c) { return c ? (void*)c->d_resp : nullptr; }

@@ -589,6 +589,11 @@ int  b2_h2_pack_responses(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const
 int  b2_counters_read(b2_ctx* ctx, int64_t out[B2_N_COUNTERS]);
 /* device pointer of the int64[8] (for ncclAllReduce / torch.distributed) */
 void* b2_counters_device_ptr(b2_ctx* ctx);
+/* bvar's cross-shard sum (an Adder combined over agents, src/bvar/reducer.h:227-233,335) across GPUs: ncclAllReduce(sum, int64 x 8) of the
+ * counters IN PLACE on `nccl_comm` (an ncclComm_t of the caller: one rank per GPU) and the ctx's stream; the call returns when the sum is
+ * there.  The library does not link NCCL: the entry point is looked up in the running process (torch / the transport loaded it), and the
+ * call fails with B2_E_INVAL when it is not there.  Every rank of the communicator must call it. */
+int  b2_counters_allreduce(b2_ctx* ctx, void* nccl_comm);
 
 #ifdef __cplusplus
 }
