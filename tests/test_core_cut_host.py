@@ -1,0 +1,120 @@
+"""CPU: the PRODUCT's CutInputMessage chain — brpc_b200/csrc/b2_core.cuh, the source the kernels compile, built for the host
+(tests/cpp/core_host.cc, a test harness) — against the oracle's restatement of input_messenger.cpp:84-179,206-322 on every run of mixed
+five-protocol traffic: server and client sockets, every preferred index, handler masks, corruptions, truncation at random points, and
+rpc_dump files.  The GPU tests compare the kernels with the oracle; this one runs the kernels' cut rules themselves where no GPU is."""
+import ctypes as C
+import os
+import random
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import _oracle as O
+from _traffic import SEED, echo_frame, mixed_frames, rnd62
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+ALL = (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4) | (1 << 12)
+
+
+@pytest.fixture(scope="module")
+def core():
+    so = os.path.join(HERE, "cpp", "libcore_host.so")
+    src = os.path.join(HERE, "cpp", "core_host.cc")
+    hdr = os.path.join(ROOT, "brpc_b200", "csrc", "b2_core.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-o", so, src])
+    lib = C.CDLL(so)
+    lib.core_cut_run.restype = C.c_uint32
+    lib.core_cut_run.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+    return lib
+
+
+def hulu(meta, payload):
+    return b"HULU" + struct.pack("<II", len(meta) + len(payload), len(meta)) + meta + payload
+
+
+def sofa(meta, payload):
+    return b"SOFA" + struct.pack("<IQQ", len(meta), len(payload), len(meta) + len(payload)) + meta + payload
+
+
+def nshead(body, log_id=7):
+    return struct.pack("<HHI16sIII", 1, 2, log_id, b"b2-test", 0xfb709394, 0, len(body)) + body
+
+
+def five_protocol_stream(rng, n):
+    out = []
+    for i in range(n):
+        c = rng.random()
+        body = rnd62(rng, rng.choice([0, 1, 20, 100, 1000]))
+        meta = rnd62(rng, rng.choice([0, 5, 40]))
+        if c < 0.22: out.append(hulu(meta, body))
+        elif c < 0.40: out.append(sofa(meta, body))
+        elif c < 0.58: out.append(nshead(body, log_id=i))
+        elif c < 0.84: out.append(echo_frame(rng, i, body))
+        elif c < 0.88: out.append(b"HULU" + struct.pack("<II", 10, 50) + bytes(10))           # meta_size > body_size: popped, TRY_OTHERS
+        elif c < 0.92: out.append(O.pack_stream_frame(rng.randrange(1 << 30), -1, 3, None, body))
+        elif c < 0.95: out.append(sofa(meta, body)[:16] + struct.pack("<Q", 12345) + meta + body)   # msg_size mismatch
+        elif c < 0.97: out.append(rnd62(rng, rng.randrange(1, 40)))                             # garbage: the connection dies here
+        else: out.append(b"PRP" + rnd62(rng, 3))                                              # a magic prefix that goes wrong
+    return out
+
+
+def compare(core, chunks, mask, preferred=-1, flags=0, max_body=0):
+    from brpc_b200.messenger import make_runs
+    data, runs = make_runs(chunks)
+    runs["preferred_proto"] = preferred; runs["flags"] = flags
+    cfg = O.make_config(protocols=mask, max_body_size=max_body)
+    rs, msgs, resp = O.process_batch(cfg, data, runs)
+    buf = bytes(data)
+    out = (C.c_uint32 * 3)(); offs = (C.c_uint32 * 4096)()
+    n_total = 0
+    for r in range(len(runs)):
+        off, ln = int(runs["offset"][r]), int(runs["length"][r])
+        n = core.core_cut_run(buf[off:off + ln], ln, preferred, max_body or (64 << 20), 1 if flags & 1 else 0, mask, flags, out, offs, 4096)
+        got = (n, out[0], out[1], C.c_int32(out[2]).value)
+        want = (int(rs["n_msgs"][r]), int(rs["consumed"][r]), int(rs["parse_error"][r]), int(rs["preferred_proto"][r]))
+        assert got == want, ("run", r, got, want, mask, preferred, flags)
+        f0 = int(rs["first_msg"][r])
+        for k in range(min(n, 4096)):
+            assert (offs[k] & 0x7fffffff) + off == int(msgs["frame_off"][f0 + k]), (r, k)
+            if not flags & 4:                                                     # (a dump record's `protocol` is the sample's, not the handler's)
+                assert (offs[k] >> 31) == (0 if int(msgs["protocol"][f0 + k]) == 1 else 1), (r, k, int(msgs["protocol"][f0 + k]))
+        n_total += n
+    return n_total
+
+
+def test_cut_chain_on_baidu_std_and_streaming_traffic(core):
+    rng = random.Random(SEED + 901)
+    total = 0
+    for trial in range(6):
+        streams = [b"".join(mixed_frames(rng, rng.randrange(1, 60), big=trial == 0)) for _ in range(40)]
+        chunks = [s[:rng.randrange(len(s) + 1)] if rng.random() < 0.5 else s for s in streams]
+        for pref in (-1, 1, 2):
+            total += compare(core, chunks, (1 << 1) | (1 << 2), preferred=pref)
+        total += compare(core, chunks, (1 << 1) | (1 << 2), preferred=-1, flags=1)              # client sockets: the baidu_std <-> streaming fallback
+        total += compare(core, chunks, (1 << 1) | (1 << 2), preferred=1, max_body=3000)         # TOO_BIG_DATA
+    assert total > 5000
+
+
+def test_cut_chain_on_five_protocols(core):
+    rng = random.Random(SEED + 902)
+    total = 0
+    for trial in range(8):
+        streams = [b"".join(five_protocol_stream(rng, rng.randrange(1, 50))) for _ in range(40)]
+        chunks = [s[:rng.randrange(len(s) + 1)] if rng.random() < 0.5 else s for s in streams]
+        for mask in (ALL, (1 << 1) | (1 << 3), (1 << 1) | (1 << 2) | (1 << 12), (1 << 4) | (1 << 12), 1 << 12):
+            for pref in (-1, 1, 3, 4, 12):
+                total += compare(core, chunks, mask, preferred=pref)
+    assert total > 10000
+
+
+def test_cut_chain_on_rpc_dump_files(core):
+    import json
+    vec = json.load(open(os.path.join(HERE, "golden", "dump_vectors.json")))
+    files = [bytes.fromhex(v["file_hex"]) for v in vec["files"]]
+    rng = random.Random(SEED + 903)
+    chunks = files + [f[:rng.randrange(len(f) + 1)] for f in files] + [f[:10] + b"\xff" + f[11:] for f in files if len(f) > 20]
+    assert compare(core, chunks, (1 << 1) | (1 << 2), preferred=-1, flags=4) > 0
