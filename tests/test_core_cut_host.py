@@ -118,3 +118,48 @@ def test_cut_chain_on_rpc_dump_files(core):
     rng = random.Random(SEED + 903)
     chunks = files + [f[:rng.randrange(len(f) + 1)] for f in files] + [f[:10] + b"\xff" + f[11:] for f in files if len(f) > 20]
     assert compare(core, chunks, (1 << 1) | (1 << 2), preferred=-1, flags=4) > 0
+
+
+def test_product_decoders_against_the_oracle_on_golden_and_fuzz_vectors(core):
+    """decode_rpc_meta / decode_stream_meta / decode_echo_request of b2_core.cuh (host build) field by field against the oracle, which the
+    python-protobuf vectors pin (tests/test_oracle_golden.py): 3 000+ valid, mutated and truncated metas."""
+    import json
+    core.core_decode_rpc_meta.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_void_p]
+    core.core_decode_stream_meta.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p]
+    core.core_decode_echo_request.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    gold = lambda n: json.load(open(os.path.join(HERE, "golden", n)))
+    metas = [bytes.fromhex(r["hex"]) for r in gold("rpc_meta_vectors.json")["rpc_meta"]] + [bytes.fromhex(r["hex"]) for r in gold("pb_fuzz_vectors.json")["rpc_meta"]]
+    rng = random.Random(SEED + 904)
+    metas += [m[:rng.randrange(len(m) + 1)] for m in metas[:600]]
+    out = (C.c_longlong * 14)()
+    n_ok = 0
+    for b in metas:
+        ok_o, m = O.parse_rpc_meta(b)
+        ok_p = core.core_decode_rpc_meta(b, len(b), 0, out)
+        assert bool(ok_p) == ok_o, b.hex()
+        if not ok_o:
+            continue
+        n_ok += 1
+        assert out[0] == m.has and out[1] == m.correlation_id and out[3] == m.compress_type and out[4] == m.attachment_size, b.hex()
+        assert out[5] == m.checksum_type and out[6] == m.content_type and out[13] == m.error_code, b.hex()
+        if m.has & (1 << 12): assert out[2] == m.log_id
+        if m.has_service_name: assert (out[7], out[8]) == (m.service_name.off, m.service_name.len)
+        if m.has_method_name: assert (out[9], out[10]) == (m.method_name.off, m.method_name.len)
+        if m.has & (1 << 11): assert (out[11], out[12]) == (m.checksum_value.off, m.checksum_value.len)
+    assert n_ok > 1000
+    frames = [bytes.fromhex(r["hex"]) for r in gold("pb_fuzz_vectors.json")["stream_frame_meta"]]
+    frames += [f[:rng.randrange(len(f) + 1)] for f in frames[:300]]
+    so = (C.c_longlong * 5)()
+    for b in frames:
+        ok_o, m = O.parse_stream_meta(b)
+        assert bool(core.core_decode_stream_meta(b, len(b), so)) == ok_o, b.hex()
+        if ok_o:
+            assert (so[0], so[1], so[4]) == (m.has, m.stream_id, m.frame_type) and so[2] == m.source_stream_id and so[3] == m.consumed_size, b.hex()
+    off = C.c_uint32(); ln = C.c_uint32()
+    bodies = [b"", b"\x0a\x00", b"\x0a\x03abc", b"\x0a\x03ab", b"\x12\x01x\x0a\x02hi", b"\x0a\x01a\x0a\x02bc", b"\x08\x01", b"\x0a\x80\x01" + b"x" * 128, b"\x0a\xff\xff\xff\xff\x0f",
+              b"\x0b\x0c", b"\x0a\x02hi\x00"] + [bytes(rng.getrandbits(8) for _ in range(rng.randrange(0, 12))) for _ in range(2000)]
+    for b in bodies:
+        ok_o, (o_off, o_len) = O.parse_echo_request(b)
+        assert bool(core.core_decode_echo_request(b, len(b), C.byref(off), C.byref(ln))) == ok_o, b.hex()
+        if ok_o:
+            assert (off.value, ln.value) == (o_off, o_len), b.hex()
