@@ -163,3 +163,39 @@ def test_product_decoders_against_the_oracle_on_golden_and_fuzz_vectors(core):
         assert bool(core.core_decode_echo_request(b, len(b), C.byref(off), C.byref(ln))) == ok_o, b.hex()
         if ok_o:
             assert (off.value, ln.value) == (o_off, o_len), b.hex()
+
+
+def test_cut_chain_and_decoders_on_arbitrary_bytes(core):
+    """hypothesis: ANY byte string as a run / as a meta — seeded with the magics and header shapes so that the interesting branches are
+    reached — gives the same verdicts from the product's rules and the oracle's."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    core.core_decode_rpc_meta.argtypes = [C.c_char_p, C.c_uint32, C.c_int, C.c_void_p]
+    magic = st.sampled_from([b"PRPC", b"STRM", b"HULU", b"SOFA", b"PRP", b"ST", b"\xfb\x70\x93\x94", b"", b"P", b"HUL"])
+    u32 = st.integers(0, 2 ** 32 - 1)
+    small = st.integers(0, 80)
+    def frame_like(m, a, b, tail):
+        return m + struct.pack(">II", a, b) + tail
+    piece = st.one_of(st.binary(max_size=48),
+                      st.builds(frame_like, magic, small, small, st.binary(max_size=96)),
+                      st.builds(frame_like, magic, u32, u32, st.binary(max_size=16)),
+                      st.builds(lambda m, a, b, t: m + struct.pack("<II", a, b) + t, magic, small, small, st.binary(max_size=96)),
+                      st.builds(lambda body: struct.pack("<HHI16sIII", 1, 2, 3, b"x", 0xfb709394, 0, len(body)) + body, st.binary(max_size=40)))
+    runs = st.lists(piece, min_size=0, max_size=6).map(b"".join)
+
+    @settings(max_examples=400, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(runs, st.sampled_from([-1, 1, 2, 3, 4, 12]), st.sampled_from([ALL, (1 << 1) | (1 << 2), (1 << 1) | (1 << 12), 1 << 3]), st.sampled_from([0, 1]), st.sampled_from([0, 50]))
+    def cut(run, pref, mask, flags, max_body):
+        compare(core, [run], mask, preferred=pref, flags=flags, max_body=max_body)
+    cut()
+
+    out = (C.c_longlong * 14)()
+
+    @settings(max_examples=600, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.lists(st.one_of(st.binary(max_size=12), st.sampled_from([b"\x0a", b"\x12", b"\x18", b"\x20", b"\x28", b"\x32", b"\x3a", b"\x42", b"\x4a", b"\x50", b"\x58", b"\x62",
+                                                                          b"\x0a\x02\x0a\x00", b"\x12\x02\x08\x00", b"\xff\xff\xff\xff\x0f", b"\x80"])), max_size=12).map(b"".join))
+    def meta(b):
+        ok_o, m = O.parse_rpc_meta(b)
+        assert bool(core.core_decode_rpc_meta(b, len(b), 0, out)) == ok_o, b.hex()
+        if ok_o:
+            assert out[0] == m.has and out[1] == m.correlation_id and out[3] == m.compress_type and out[13] == m.error_code, b.hex()
+    meta()
