@@ -88,3 +88,56 @@ def test_device_h2_source_many_seeds(h2lib):
         m, c, e = run_scenario(mk, make_runs, n_conns=24, n_calls=10, violations=0.3, seed=seed, step_choices=[2, 17, 300, 2500, 12000])
         total += m
     assert total > 1500
+
+
+def _records(buf):
+    out = []; p = 0
+    while p < len(buf):
+        nl = buf[p] | (buf[p + 1] << 8); vl = buf[p + 2] | (buf[p + 3] << 8)
+        out.append((bytes(buf[p + 4:p + 4 + nl]), bytes(buf[p + 4 + nl:p + 4 + nl + vl]))); p += 4 + nl + vl
+    return out
+
+
+def test_device_hpack_source_on_rfc_vectors_and_against_the_oracle(h2lib):
+    """hpack_decode_block of b2_h2.cuh (host build): the RFC 7541 Appendix C vectors the reference asserts (test/brpc_hpack_unittest.cpp), then
+    blocks made of valid pieces, mutations and truncations on a long-lived table — status and headers equal the oracle's, block after block."""
+    import json
+    import random
+    import _oracle as O
+    h2lib.h2h_hpack_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    h2lib.h2h_hpack_reset.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    ctx = HostH2Context(h2lib, 0x5a, max_conns=4, pending=1, stream_bytes=256)
+    out = C.create_string_buffer(1 << 16); ol = C.c_uint32(); nh = C.c_uint32()
+
+    def dev(b, cap=1 << 16):
+        st = h2lib.h2h_hpack_decode(ctx.h, 0, b, len(b), out, cap, C.byref(ol), C.byref(nh))
+        return st, _records(out.raw[:ol.value])
+    vec = json.load(open(os.path.join(HERE, "golden", "hpack_vectors.json")))
+    n = 0
+    for t in vec["unittest"]:
+        h2lib.h2h_hpack_reset(ctx.h, 0, t["max_table_size"])
+        for s in t["steps"]:
+            st, hdrs = dev(bytes.fromhex(s["bytes_hex"]))
+            assert st == 0 and hdrs == [(a.lower().encode(), b.encode()) for a, b in s["headers"]], t["test"]
+            n += len(hdrs)
+    assert n >= 50
+    rng = random.Random(4242)
+    pieces = [bytes.fromhex(s["bytes_hex"]) for t in vec["unittest"] for s in t["steps"]] + [bytes.fromhex(s["hex"]) for s in vec["seed_corpus"]]
+    h2lib.h2h_hpack_reset(ctx.h, 0, 4096); orc = O.HPack(4096)
+    agree = 0
+    for k in range(6000):
+        b = bytearray(rng.choice(pieces))
+        c = rng.random()
+        if c < 0.25 and b: del b[rng.randrange(len(b)):]
+        elif c < 0.5 and b: b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+        elif c < 0.6: b += rng.choice(pieces)
+        elif c < 0.65: b = bytearray(bytes(rng.getrandbits(8) for _ in range(rng.randrange(1, 20))))
+        want = orc.decode_block(bytes(b)); got = dev(bytes(b))
+        assert got[0] == want[0], (k, bytes(b).hex(), got[0], want[0])
+        if want[0] == 0:
+            assert got[1] == want[1], (k, bytes(b).hex())
+            agree += 1
+        else:                                   # a failed block leaves the connection dead in both: start both tables afresh
+            h2lib.h2h_hpack_reset(ctx.h, 0, 4096); orc = O.HPack(4096)
+    assert agree > 1500
+    ctx.close()
