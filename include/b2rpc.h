@@ -16,9 +16,12 @@
  * StreamFrameMeta of each message, runs the registered device handler (echo)
  * and packs the response frames (SendRpcResponse,
  * src/brpc/policy/baidu_rpc_protocol.cpp:273-460).
- * Further down: leaf codecs (CRC32C, snappy), the client mirror (b2_pack_requests), and the h2/gRPC server path
- * (b2_h2_process_batch = ParseH2Message, b2_h2_pack_responses = H2UnsentResponse + PackH2Message) whose per-connection
- * state lives on the device between calls.
+ * Further down: how bytes cross PCIe (b2_set_modes: kernels pull the pinned read blocks in place, replies by reference or as the
+ * writev gather list), the latency path (b2_ring_*: a persistent kernel behind a pinned submit ring), the handler set of the messenger
+ * (b2_set_protocols: hulu_pbrpc / sofa_pbrpc / nshead framing; rpc_dump files as a source), leaf codecs with the reference's signatures
+ * (CRC32C, snappy), the client mirror (b2_pack_requests), replies the host produced (b2_pack_responses = SendRpcResponse), and the
+ * h2/gRPC server path (b2_h2_process_batch = ParseH2Message, b2_h2_pack_responses = H2UnsentResponse + PackH2Message) whose
+ * per-connection state lives on the device between calls.
  */
 #ifndef B2RPC_H_
 #define B2RPC_H_
