@@ -42,7 +42,9 @@ public:
         explicit Conn(uint64_t id) : sock(id), base(nullptr), cap(0), fill(0), group(0), fd(-1) {}
     };
     // replies of one connection, in order, as an iovec list (2 entries per by-reference reply): the writev that KeepWrite would issue.
-    // Default sink: IOBuf references + Socket::Write.
+    // Default sink: IOBuf references + Socket::Write.  A sink must be DONE with the list when it returns — the entries point into the batch's
+    // pinned reply block and the connection's read region, both reused by the next round: what a writev could not take (EAGAIN) has to be
+    // copied or written before returning.  With B2_RESP_IOVEC the list is the device's own (entries of length 0 for unanswered messages).
     typedef std::function<void(Conn*, const struct iovec*, size_t)> ReplySink;
     typedef void (*Process)(InputMessageBase* msg);
 
