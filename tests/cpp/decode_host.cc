@@ -1,0 +1,75 @@
+// Test harness (not product): the per-message device functions of brpc_b200/csrc/b2_kernels.cuh — decode_one (k_decode / k_small's decoder) and
+// fused_fast_echo (k_fused's exact-shape decoder) — called from the CPU suite on single messages, through the generated host-compilable copy of
+// the kernels file (tests/cpp/gen_kernels_host.py).  One lane, one message: what a lane of the kernels does.
+#include "kernels_host_prelude.h"
+#include "kernels_host.cuh"
+#include <string>
+#include <vector>
+using namespace b2;
+// the kernels' dynamic shared-memory arrays (declared `extern` in the generated copy): never touched here, the linker just wants them
+namespace b2 { __attribute__((aligned(128))) uint8_t fused_raw[16], pack_smem_raw[16], small_raw[16]; __attribute__((aligned(16))) uint8_t s_rings[16]; uint32_t sm[4]; }
+
+extern "C" {
+struct kh_out {
+    b2_msg_desc d; MsgAux a; PackJob job; uint32_t slot; uint32_t ref[4]; uint8_t head[kHeadBytes];
+    uint32_t fast_ok, fast_prefix, fast_rs;          // fused_fast_echo: accepted?, prefix length, reply start (batch offset)
+    b2_msg_desc fast_d;
+};
+struct kh_ctx { DevMethod methods[4]; uint32_t n_methods; DevConfig C; };
+kh_ctx* kh_create(uint64_t max_body, uint32_t proto_mask, uint32_t by_ref, uint32_t stream_handler, const char* identity) {
+    kh_ctx* k = new kh_ctx; memset(k, 0, sizeof *k);
+    k->C.max_body_size = max_body ? max_body : (64ull << 20); k->C.proto_mask = proto_mask; k->C.by_ref = by_ref; k->C.stream_handler = stream_handler;
+    k->C.tile_bytes = 8192; k->C.tile_shift = 13; k->C.spec_k = 16; k->C.pull_vecs = 8;
+    if (identity) { k->C.identity_len = (uint32_t)strlen(identity); memcpy(k->C.identity, identity, k->C.identity_len); }
+    return k;
+}
+void kh_destroy(kh_ctx* k) { delete k; }
+// what b2_register_method writes into the device table
+void kh_add_method(kh_ctx* k, const char* service_full, const char* service_short, const char* method, const char* request_type, int handler, int echo_att, int r_cks, int r_cmp) {
+    DevMethod& m = k->methods[k->n_methods++];
+    const std::string full = std::string(service_full) + "." + method;
+    m.full_method_len = (uint32_t)full.size(); memcpy(m.full_method, full.data(), full.size());
+    m.service_short_len = (uint32_t)strlen(service_short); memcpy(m.service_short, service_short, m.service_short_len);
+    m.service_full_len = (uint32_t)strlen(service_full); memcpy(m.service_full, service_full, m.service_full_len);
+    m.request_type_len = (uint32_t)strlen(request_type); memcpy(m.request_type, request_type, m.request_type_len);
+    m.handler = handler; m.echo_attachment = echo_att; m.response_checksum_type = r_cks; m.response_compress_type = r_cmp;
+    k->C.n_methods = k->n_methods;
+}
+// one message: bytes = the whole batch buffer (padded by the caller), fo_raw = its frame offset (| bit 31 when not baidu_std), run = its run
+void kh_decode(kh_ctx* k, const uint8_t* bytes, uint32_t fo_raw, const b2_run* run, kh_out* out) {
+    memset(out, 0, sizeof *out);
+    uint32_t frame_run = 0, totals[16] = { 0 }; uint32_t ref4[4] = { 0, 0, 0, 0 };
+    BatchPtrs B; memset(&B, 0, sizeof B);
+    B.bytes = bytes; B.runs = run; B.n_runs = 1; B.frame_run = &frame_run; B.msgs = &out->d; B.aux = &out->a; B.jobs = &out->job; B.slot = &out->slot;
+    B.refs = reinterpret_cast<uint4*>(ref4); B.heads = out->head; B.methods = k->methods; B.totals = totals; B.max_msgs = 1; B.max_resp = 0xfffffff0u;
+    const uint32_t fo = fo_raw & 0x7fffffffu;
+    // (srow: the frame's first bytes as staged by decode_round — here simply the frame itself, all of it "staged")
+    decode_one<false>(B, k->C, 0, fo_raw, bytes + fo, out->head, 0xffffffffu);
+    memcpy(out->ref, ref4, 16);
+    // the exact-shape decoder of k_fused on a private copy of the frame (it writes the reply prefix in place)
+    const uint32_t body = load_be32(bytes + fo + 4);
+    if (!(fo_raw >> 31) && !(run->flags & (B2_RUN_CLIENT | B2_RUN_RPC_DUMP)) && load_le32(bytes + fo) == kMagicPRPC && body < (64u << 20)) {
+        std::vector<uint8_t> img(bytes + fo, bytes + fo + 12 + body + 16);
+        b2_msg_desc fd; memset(&fd, 0, sizeof fd);
+        BatchPtrs F = B; F.msgs = &fd;
+        DecodeOut o; o.fast = false; o.slow = false; o.prefix = 0; o.rs = 0;
+        if (fused_fast_echo(F, k->methods, k->n_methods, 0, fo, 0, img.data(), 12 + body, nullptr, o)) {
+            out->fast_ok = 1; out->fast_prefix = o.prefix; out->fast_rs = o.rs; out->fast_d = fd;
+            // hand the patched prefix back through `head` is not possible (in place): the caller asks for it separately
+        }
+    }
+}
+// the reply fused_fast_echo builds in place, for a message it accepts: returns its length (0 = declined), bytes to `reply`
+uint32_t kh_fast_reply(kh_ctx* k, const uint8_t* bytes, uint32_t fo, uint8_t* reply, uint32_t cap) {
+    const uint32_t body = load_be32(bytes + fo + 4);
+    if (load_le32(bytes + fo) != kMagicPRPC || body >= (64u << 20)) return 0;
+    std::vector<uint8_t> img(bytes + fo, bytes + fo + 12 + body + 16);
+    b2_msg_desc fd; BatchPtrs F; memset(&F, 0, sizeof F); F.msgs = &fd; F.max_msgs = 1;
+    DecodeOut o; o.fast = false; o.slow = false; o.prefix = 0; o.rs = 0;
+    if (!fused_fast_echo(F, k->methods, k->n_methods, 0, fo, 0, img.data(), 12 + body, nullptr, o)) return 0;
+    if (fd.resp_len > cap) return 0;
+    memcpy(reply, img.data() + (fd.resp_off - fo), fd.resp_len);
+    return fd.resp_len;
+}
+}
+extern "C" uint32_t kh_sizeof_out(void) { return (uint32_t)sizeof(kh_out); }

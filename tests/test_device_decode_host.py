@@ -1,0 +1,147 @@
+"""CPU: the per-message device functions of the hot path — decode_one (what a lane of k_decode / k_small / k_ring runs) and fused_fast_echo
+(what a lane of k_fused runs for the exact PackRpcRequest shape) — from a host-compilable copy of brpc_b200/csrc/b2_kernels.cuh
+(tests/cpp/gen_kernels_host.py: inline PTX dropped, a warp of one lane), message by message against the oracle: descriptor fields, error
+classes, reply lengths, the reply prefix of the bandwidth path, and the whole in-place reply of the fused path."""
+import ctypes as C
+import os
+import random
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+import _oracle as O  # noqa: E402
+from _traffic import SEED, echo_frame, mixed_frames, rnd62, split_runs  # noqa: E402
+from brpc_b200.abi import ECHO_METHOD, MSG_DT, RUN_DT  # noqa: E402
+from brpc_b200.messenger import make_runs  # noqa: E402
+
+AUX_DT = np.dtype([(n, "<u4") for n in ("msg_off", "msg_len", "att_len", "att_off", "cks_off", "cks_len", "svc_off", "svc_len", "mth_off", "mth_len", "pad", "err_kind")])
+JOB_DT = np.dtype([("src_off", "<u4"), ("bulk_len", "<u4"), ("head_len", "<u2"), ("pad", "u1"), ("fast", "u1"), ("slot_len", "<u4")])
+OUT_DT = np.dtype([("d", MSG_DT), ("a", AUX_DT), ("job", JOB_DT), ("slot", "<u4"), ("ref", "<u4", 4), ("head", "u1", 96),
+                   ("fast_ok", "<u4"), ("fast_prefix", "<u4"), ("fast_rs", "<u4"), ("fast_d", MSG_DT)])
+DESC_FIELDS = ["frame_off", "body_size", "meta_size", "correlation_id", "log_id", "attachment_size", "compress_type", "checksum_type", "has_bits", "protocol",
+               "content_type", "method_idx"]
+
+
+@pytest.fixture(scope="module")
+def kh():
+    cpp = os.path.join(HERE, "cpp")
+    so = os.path.join(cpp, "libdecode_host.so")
+    deps = [os.path.join(cpp, f) for f in ("gen_kernels_host.py", "kernels_host_prelude.h", "h2_host_prelude.h", "decode_host.cc")] + \
+           [os.path.join(ROOT, "brpc_b200", "csrc", f) for f in ("b2_kernels.cuh", "b2_core.cuh", "b2_inflate.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call([sys.executable, os.path.join(cpp, "gen_kernels_host.py")])
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-w", "-I", os.path.join(cpp, "stub"), "-I", os.path.join(ROOT, "include"),
+                               "-o", so, os.path.join(cpp, "decode_host.cc")])
+    lib = C.CDLL(so)
+    lib.kh_create.restype = C.c_void_p
+    lib.kh_create.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_char_p]
+    lib.kh_destroy.argtypes = [C.c_void_p]
+    lib.kh_add_method.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.kh_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    lib.kh_fast_reply.restype = C.c_uint32
+    lib.kh_fast_reply.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    assert lib.kh_sizeof_out() == OUT_DT.itemsize, (lib.kh_sizeof_out(), OUT_DT.itemsize)
+    return lib
+
+
+def make(kh, methods, identity=None, by_ref=0, mask=(1 << 1) | (1 << 2)):
+    k = kh.kh_create(0, mask, by_ref, 0, identity)
+    for m in methods:
+        kh.kh_add_method(k, m["service_full_name"], m["service_name"], m["method_name"], m["request_type_name"], m["handler"], m["echo_attachment"],
+                         m["response_checksum_type"], m["response_compress_type"])
+    return k
+
+
+def compare(kh, k, cfg, chunks, flags=0):
+    data, runs = make_runs(chunks)
+    runs["flags"] = flags
+    rs, msgs, resp = O.process_batch(cfg, data, runs)
+    buf = np.concatenate([np.asarray(data, np.uint8), np.zeros(4096, np.uint8)])
+    out = np.zeros(1, OUT_DT); reply = np.zeros(1 << 20, np.uint8)
+    stats = {"n": 0, "fast": 0, "fused": 0, "err": 0}
+    for i in range(len(msgs)):
+        m = msgs[i]
+        run = runs[int(m["run_idx"]):int(m["run_idx"]) + 1].copy()
+        fo = int(m["frame_off"])
+        status = int(m["status"])
+        if status in (9,):                       # framed-only protocols: decode_one is not what handles their payload
+            continue
+        fo_raw = fo | ((0 if int(m["protocol"]) == 1 or flags & 4 else 1) << 31)
+        kh.kh_decode(k, buf.ctypes.data, fo_raw, run.ctypes.data, out.ctypes.data)
+        d = out["d"][0]; a = out["a"][0]; job = out["job"][0]
+        tag = (i, status, int(d["status"]))
+        for f in DESC_FIELDS:
+            if f == "method_idx" and status in (3, 4, 5):
+                continue
+            assert d[f] == m[f], (tag, f, d[f], m[f])
+        dstatus = int(d["status"])
+        if dstatus == 0 and (int(d["checksum_type"]) == 1 or int(d["compress_type"]) != 0):
+            assert status in (0, 1), tag                                     # the pack stage verifies / decompresses: it may still fail there
+            if status == 1:
+                assert int(m["error_code"]) == 1003, tag
+        elif dstatus == 7 and status in (7, 8):
+            pass                                                             # client side: the pack stage verifies / decompresses as well
+        else:
+            assert dstatus == status and int(d["error_code"]) == int(m["error_code"]), (tag, int(d["error_code"]), int(m["error_code"]))
+        want = bytes(resp[int(m["resp_off"]):int(m["resp_off"]) + int(m["resp_len"])])
+        if dstatus == 1:                                                     # error reply: its exact length is known at decode time
+            assert int(d["resp_len"]) == len(want), tag
+            stats["err"] += 1
+        if int(job["fast"]) == 1 and status == 0:                            # the bandwidth path: the pre-built prefix in front of the payload
+            prefix = len(want) - int(a["msg_len"]) - int(a["att_len"])
+            head = bytes(out["head"][0][int(a["pad"]):int(a["pad"]) + prefix])
+            assert int(d["resp_len"]) == len(want) and head == want[:prefix], tag
+            assert want[prefix:] == bytes(buf[fo + int(a["msg_off"]):fo + int(a["msg_off"]) + int(a["msg_len"]) + int(a["att_len"])]), tag
+            stats["fast"] += 1
+        if out["fast_ok"][0]:                                                # k_fused's exact-shape decoder took it: whole reply, in place
+            assert status == 0 and int(job["fast"]) == 1, tag
+            n = kh.kh_fast_reply(k, buf.ctypes.data, fo, reply.ctypes.data, reply.nbytes)
+            assert n == len(want) and bytes(reply[:n]) == want, tag
+            fd = out["fast_d"][0]
+            for f in DESC_FIELDS:
+                assert fd[f] == m[f], (tag, "fused", f)
+            assert int(fd["status"]) == 0 and int(fd["resp_len"]) == len(want)
+            stats["fused"] += 1
+        stats["n"] += 1
+    return stats
+
+
+def test_decode_one_and_fused_fast_echo_on_mixed_traffic(kh):
+    rng = random.Random(SEED + 951)
+    total = {"n": 0, "fast": 0, "fused": 0, "err": 0}
+    for identity in (None, b"10.1.2.3:8000"):
+        for rck in (0, 1):
+            ms = [dict(ECHO_METHOD, response_checksum_type=rck, echo_attachment=rng.choice([0, 1]))]
+            k = make(kh, ms, identity=identity)
+            cfg = O.make_config(methods=ms, server_identity=identity)
+            for trial in range(3):
+                streams = [mixed_frames(rng, rng.randrange(20, 120), big=trial == 0) for _ in range(12)]
+                st = compare(kh, k, cfg, split_runs(rng, streams))
+                for key in total: total[key] += st[key]
+            kh.kh_destroy(k)
+    assert total["n"] > 4000 and total["fast"] > 800 and total["err"] > 150, total
+    # plain pipelined echoes: the shape k_fused answers itself
+    k = make(kh, [dict(ECHO_METHOD)]); cfg = O.make_config()
+    streams = [[echo_frame(rng, s * 1000 + i, rnd62(rng, rng.choice([0, 1, 16, 127, 128, 1024, 20000]))) for i in range(60)] for s in range(10)]
+    st = compare(kh, k, cfg, split_runs(rng, streams))
+    assert st["fused"] > 300 and st["fused"] <= st["fast"], st        # (it declines what does not fit in place: tiny payloads)
+    kh.kh_destroy(k)
+
+
+def test_decode_one_on_client_sockets_and_dump_files(kh):
+    rng = random.Random(SEED + 952)
+    k = make(kh, [dict(ECHO_METHOD)]); cfg = O.make_config()
+    # server replies (the oracle's own, which python-protobuf pins) fed back as client-side input
+    streams = [mixed_frames(rng, 80) for _ in range(8)]
+    data, runs = make_runs(split_runs(rng, streams, cut_tail=False))
+    rs, msgs, resp = O.process_batch(cfg, data, runs)
+    replies = [bytes(resp[int(m["resp_off"]):int(m["resp_off"]) + int(m["resp_len"])]) for m in msgs if int(m["resp_len"]) and int(m["status"]) in (0, 1)]
+    chunks = [b"".join(replies[i::6]) for i in range(6)]
+    st = compare(kh, k, cfg, chunks, flags=1)
+    assert st["n"] > 300
+    kh.kh_destroy(k)
