@@ -73,3 +73,20 @@ uint32_t kh_fast_reply(kh_ctx* k, const uint8_t* bytes, uint32_t fo, uint8_t* re
 }
 }
 extern "C" uint32_t kh_sizeof_out(void) { return (uint32_t)sizeof(kh_out); }
+// the error reply lane 0 of the pack stage writes for a message decode_one answered with an error: returns its length
+extern "C" uint32_t kh_error_reply(kh_ctx* k, const uint8_t* bytes, const kh_out* o, uint8_t* reply) {
+    return pack_error_reply(reply, k->C, k->methods, o->d, o->a, bytes + (o->d.frame_off & 0x7fffffffu));
+}
+// k_tile_walk's speculative walk (register fast path, header prefetch) and the plain restatement it must equal, from the same entry:
+// out = {exit, count, kind, last_proto} x 2, offs = the offsets each of them emitted
+struct EmitVec { uint32_t* out; uint32_t cap; uint32_t* n; void operator()(uint32_t i, const Step& s) const { if (i < cap) out[i] = s.frame_pos | ((uint32_t)(s.index != 1) << 31); *n = i + 1; } };
+extern "C" void kh_walks(const uint8_t* run, uint32_t len, uint32_t entry, uint32_t tile_end, uint64_t max_body, int client, uint32_t mask,
+                         uint32_t* out, uint32_t* offs_spec, uint32_t* offs_plain, uint32_t cap) {
+    TileRec a, b; memset(&a, 0, sizeof a); memset(&b, 0, sizeof b);
+    uint32_t na = 0, nb = 0;
+    EmitVec ea = { offs_spec, cap, &na }, eb = { offs_plain, cap, &nb };
+    walk_tile_spec(run, len, entry, tile_end, max_body, client != 0, a, ea, mask);
+    walk_tile<true>(run, len, entry, -1, tile_end, max_body, client != 0, b, eb, mask);
+    out[0] = a.exit; out[1] = a.count; out[2] = a.kind; out[3] = (uint32_t)(int)a.last_proto;
+    out[4] = b.exit; out[5] = b.count; out[6] = b.kind; out[7] = (uint32_t)(int)b.last_proto;
+}

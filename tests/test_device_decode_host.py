@@ -45,6 +45,9 @@ def kh():
     lib.kh_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     lib.kh_fast_reply.restype = C.c_uint32
     lib.kh_fast_reply.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+    lib.kh_error_reply.restype = C.c_uint32
+    lib.kh_error_reply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.kh_walks.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
     assert lib.kh_sizeof_out() == OUT_DT.itemsize, (lib.kh_sizeof_out(), OUT_DT.itemsize)
     return lib
 
@@ -89,8 +92,10 @@ def compare(kh, k, cfg, chunks, flags=0):
         else:
             assert dstatus == status and int(d["error_code"]) == int(m["error_code"]), (tag, int(d["error_code"]), int(m["error_code"]))
         want = bytes(resp[int(m["resp_off"]):int(m["resp_off"]) + int(m["resp_len"])])
-        if dstatus == 1:                                                     # error reply: its exact length is known at decode time
-            assert int(d["resp_len"]) == len(want), tag
+        if dstatus == 1:                                                     # error reply: its exact length is known at decode time,
+            assert int(d["resp_len"]) == len(want), tag                       # and lane 0 of the pack stage writes it: pack_error_reply
+            n = kh.kh_error_reply(k, buf.ctypes.data, out.ctypes.data, reply.ctypes.data)
+            assert n == len(want) and bytes(reply[:n]) == want, tag
             stats["err"] += 1
         if int(job["fast"]) == 1 and status == 0:                            # the bandwidth path: the pre-built prefix in front of the payload
             prefix = len(want) - int(a["msg_len"]) - int(a["att_len"])
@@ -145,3 +150,30 @@ def test_decode_one_on_client_sockets_and_dump_files(kh):
     st = compare(kh, k, cfg, chunks, flags=1)
     assert st["n"] > 300
     kh.kh_destroy(k)
+
+
+def test_speculative_walk_equals_the_plain_walk_from_any_entry(kh):
+    """walk_tile_spec (k_tile_walk: steps decided from registers, next header prefetched) against walk_tile<true> (the CutInputMessage
+    restatement step by step) from true frame starts, from positions inside payloads, on five-protocol traffic with garbage, for several tile ends."""
+    import struct
+    rng = random.Random(SEED + 953)
+    from test_core_cut_host import five_protocol_stream, ALL
+    out = (C.c_uint32 * 8)(); oa = (C.c_uint32 * 256)(); ob = (C.c_uint32 * 256)()
+    checked = 0
+    for trial in range(60):
+        frames = five_protocol_stream(rng, rng.randrange(5, 60)) if trial % 2 else mixed_frames(rng, rng.randrange(5, 60))
+        run = b"".join(frames)
+        run = run[:rng.randrange(len(run) // 2, len(run) + 1)]
+        padded = run + bytes(64)
+        starts = [0]
+        for f in frames: starts.append(starts[-1] + len(f))
+        entries = [s_ for s_ in starts if s_ < len(run)] + [rng.randrange(len(run)) for _ in range(20)]
+        for mask in (ALL, (1 << 1) | (1 << 2)):
+            for entry in entries:
+                tile_end = min(len(run) + 100, entry + rng.choice([1, 100, 2000, 8192, 1 << 20]))
+                kh.kh_walks(padded, len(run), entry, tile_end, 64 << 20, 0, mask, out, oa, ob, 256)
+                assert tuple(out[0:4]) == tuple(out[4:8]), (trial, entry, tile_end, mask, tuple(out))
+                n = min(out[1], 256)
+                assert list(oa[:n]) == list(ob[:n]), (trial, entry)
+                checked += 1
+    assert checked > 2000
