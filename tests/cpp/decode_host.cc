@@ -90,3 +90,37 @@ extern "C" void kh_walks(const uint8_t* run, uint32_t len, uint32_t entry, uint3
     out[0] = a.exit; out[1] = a.count; out[2] = a.kind; out[3] = (uint32_t)(int)a.last_proto;
     out[4] = b.exit; out[5] = b.count; out[6] = b.kind; out[7] = (uint32_t)(int)b.last_proto;
 }
+
+// ---- the front of the staged pipeline on the host: k_tile_walk (thread per tile) -> k_resolve (a block of ONE thread per run: its block-wide
+// steps degenerate correctly, the cross-run prefix is done here instead of by its last-CTA epilogue) -> k_frame_table.  The speculative entries
+// are GIVEN (k_tile_search is warp-cooperative and not what is under test): k_resolve must produce the sequential cut whatever they are.
+extern "C" int kh_front(const uint8_t* bytes, const b2_run* runs, uint32_t n_runs, uint32_t tile_shift, uint32_t proto_mask, uint64_t max_body,
+                        const uint32_t* entries /* per tile, run-relative, kNone = none */, uint32_t n_tiles_expected,
+                        b2_run_status* rs_out, uint32_t* frame_off, uint32_t* frame_run, uint32_t cap, uint32_t* n_msgs_out, uint32_t* n_rewalked) {
+    const uint32_t tile = 1u << tile_shift;
+    std::vector<uint32_t> rtb(n_runs + 1, 0);
+    for (uint32_t r = 0; r < n_runs; r++) rtb[r + 1] = rtb[r] + (uint32_t)(((uint64_t)runs[r].length + tile - 1) >> tile_shift);
+    const uint32_t nt = rtb[n_runs];
+    if (nt != n_tiles_expected) return -1;
+    std::vector<uint4> ti(nt ? nt : 1);
+    for (uint32_t r = 0; r < n_runs; r++) for (uint32_t t = rtb[r]; t < rtb[r + 1]; t++) ti[t] = make_uint4(runs[r].offset, runs[r].length, t - rtb[r], r | (runs[r].flags << 24));
+    std::vector<TileRec> tiles(nt ? nt : 1); std::vector<uint32_t> tile_base(nt + 1, 0), scratch(3 * (size_t)nt + 3, 0), spec((size_t)kSpecK * nt + 1, 0), totals(16, 0);
+    for (uint32_t t = 0; t < nt; t++) { memset(&tiles[t], 0, sizeof(TileRec)); tiles[t].entry = entries[t]; }
+    BatchPtrs B; memset(&B, 0, sizeof B);
+    B.bytes = bytes; B.runs = runs; B.run_tile_base = rtb.data(); B.tile_info = ti.data(); B.tiles = tiles.data(); B.tile_base = tile_base.data();
+    B.tile_scratch = scratch.data(); B.tile_spec = spec.data(); B.run_status = rs_out; B.frame_off = frame_off; B.frame_run = frame_run; B.totals = totals.data();
+    B.n_runs = n_runs; B.n_tiles = nt; B.max_msgs = cap; B.max_resp = 0xfffffff0u;
+    DevConfig C; memset(&C, 0, sizeof C);
+    C.max_body_size = max_body ? max_body : (64ull << 20); C.tile_bytes = tile; C.tile_shift = tile_shift; C.spec_k = kSpecK; C.proto_mask = proto_mask;
+    blockDim.x = 1; threadIdx.x = 0; gridDim.x = 0x7fffffffu;                   // (the last-CTA epilogues never fire: the prefix over runs is done below)
+    for (uint32_t t = 0; t < nt; t++) { blockIdx.x = t; k_tile_walk(B, C); }
+    for (uint32_t r = 0; r < n_runs; r++) { blockIdx.x = r; k_resolve(B, C, 1u); }
+    uint32_t total = 0, rew = 0;
+    for (uint32_t r = 0; r < n_runs; r++) { rs_out[r].first_msg = total; total += rs_out[r].n_msgs; }
+    for (uint32_t t = 0; t < nt; t++) rew += (tiles[t].kind & kKindRewalked) ? 1u : 0u;
+    totals[0] = total;
+    *n_msgs_out = total; *n_rewalked = rew;
+    if (total > cap) return -2;
+    for (uint32_t g = 0; g < nt * kSpecK; g++) { blockIdx.x = g; k_frame_table(B, C); }
+    return 0;
+}

@@ -177,3 +177,62 @@ def test_speculative_walk_equals_the_plain_walk_from_any_entry(kh):
                 assert list(oa[:n]) == list(ob[:n]), (trial, entry)
                 checked += 1
     assert checked > 2000
+
+
+def test_the_exactness_gate_with_adversarial_speculation(kh):
+    """"k_tile_search / k_tile_walk only propose; k_resolve verifies the chain from the run start, so the result is by construction
+    the sequential one."  Here the proposals are hostile — true frame starts, random positions (inside payloads, inside headers), frame
+    look-alikes carried in payloads, none at all — on five-protocol traffic with garbage and truncation, for several tile sizes: k_tile_walk ->
+    k_resolve -> k_frame_table (the kernels' own code, host build) must give the oracle's runs and frame table every time."""
+    import struct
+    from test_core_cut_host import five_protocol_stream, ALL
+    kh.kh_front.restype = C.c_int
+    kh.kh_front.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    from brpc_b200.abi import RUN_STATUS_DT
+    rng = random.Random(SEED + 954)
+    fake = echo_frame(rng, 5, b"x" * 30)
+    n_cases = 0; n_rew = 0
+    for trial in range(40):
+        kind = trial % 4
+        if kind == 0: streams = [b"".join(mixed_frames(rng, rng.randrange(5, 80), big=rng.random() < 0.3)) for _ in range(10)]
+        elif kind == 1: streams = [b"".join(five_protocol_stream(rng, rng.randrange(5, 80))) for _ in range(10)]
+        elif kind == 2: streams = [b"".join(echo_frame(rng, i, (fake * 40)[:rng.choice([100, 1024, 5000])]) for i in range(rng.randrange(5, 60))) for _ in range(10)]
+        else: streams = [b"".join(echo_frame(rng, i, rnd62(rng, rng.choice([0, 10, 1024, 30000]))) for i in range(rng.randrange(1, 40))) for _ in range(10)]
+        chunks = [s[:rng.randrange(len(s) + 1)] if rng.random() < 0.5 else s for s in streams]
+        mask = ALL if kind == 1 else (1 << 1) | (1 << 2)
+        data, runs = make_runs(chunks)
+        runs["preferred_proto"] = rng.choice([-1, 1, 2])
+        cfg = O.make_config(protocols=mask)
+        rs, msgs, resp = O.process_batch(cfg, data, runs)
+        buf = np.concatenate([np.asarray(data, np.uint8), np.zeros(4096, np.uint8)])
+        for shift in (9, 11, 13):
+            tile = 1 << shift
+            nt = int(sum((int(l) + tile - 1) >> shift for l in runs["length"]))
+            true_starts = set((int(m["run_idx"]), int(m["frame_off"]) - int(runs["offset"][int(m["run_idx"])])) for m in msgs)
+            for mode in range(4):
+                entries = np.full(max(nt, 1), 0xffffffff, np.uint32)
+                t = 0
+                for r in range(len(runs)):
+                    ln = int(runs["length"][r])
+                    for k in range((ln + tile - 1) >> shift):
+                        lo, hi = k * tile, min((k + 1) * tile, ln)
+                        firsts = sorted(p for (rr, p) in true_starts if rr == r and lo <= p < hi)
+                        if k == 0:
+                            e = 0
+                        elif mode == 0: e = firsts[0] if firsts else 0xffffffff                 # what a perfect search proposes
+                        elif mode == 1: e = rng.randrange(lo, hi)                                  # anywhere
+                        elif mode == 2: e = 0xffffffff if rng.random() < 0.5 else (firsts[-1] if firsts else rng.randrange(lo, hi))   # nothing, or a LATER true start
+                        else: e = rng.choice([lo, hi - 1, (firsts[0] + 1) if firsts and firsts[0] + 1 < hi else lo])
+                        entries[t] = e; t += 1
+                rs_d = np.zeros(len(runs), RUN_STATUS_DT); fo = np.zeros(len(msgs) + 64, np.uint32); fr = np.zeros(len(msgs) + 64, np.uint32)
+                nm = C.c_uint32(); rew = C.c_uint32()
+                rc = kh.kh_front(buf.ctypes.data, runs.ctypes.data, len(runs), shift, mask, 0, entries.ctypes.data, nt, rs_d.ctypes.data, fo.ctypes.data, fr.ctypes.data,
+                                 len(fo), C.byref(nm), C.byref(rew))
+                assert rc == 0 and nm.value == len(msgs), (trial, shift, mode, rc, nm.value, len(msgs))
+                for f in ("consumed", "parse_error", "n_msgs", "first_msg", "preferred_proto"):
+                    assert np.array_equal(rs_d[f], rs[f]), (trial, shift, mode, f)
+                assert np.array_equal(fo[:nm.value] & 0x7fffffff, msgs["frame_off"]) and np.array_equal(fr[:nm.value], msgs["run_idx"]), (trial, shift, mode)
+                assert np.array_equal(fo[:nm.value] >> 31, (msgs["protocol"] != 1).astype(np.uint32)), (trial, shift, mode)
+                n_cases += 1; n_rew += rew.value
+    assert n_cases == 40 * 3 * 4 and n_rew > 1000
