@@ -281,7 +281,8 @@ __device__ __forceinline__ void walk_tile_spec(const uint8_t* run, uint32_t len,
         if (len - pos >= 12) {
             const HdrWords h = pre_pos == pos ? pre : load_hdr_words(run + pos);
             const uint32_t guess = pos + prev_len;
-            if (prev_len && guess < tile_end && len - guess >= 12) { pre = load_hdr_words(run + guess); pre_pos = guess; }   // in flight while h is used
+            // (guess <= len - 12, written so that a guess past the run's end — the last tile's end lies beyond it — cannot wrap around)
+            if (prev_len && guess < tile_end && (uint64_t)guess + 12 <= len) { pre = load_hdr_words(run + guess); pre_pos = guess; }   // in flight while h is used
             else pre_pos = kNone;
             const uint32_t sh = 8u * (pos & 3u);                      // run offsets are 16-byte aligned: alignment of run + pos is pos & 3
             const uint32_t h0 = sh ? __funnelshift_r(h.w0, h.w1, sh) : h.w0, h1 = sh ? __funnelshift_r(h.w1, h.w2, sh) : h.w1,
