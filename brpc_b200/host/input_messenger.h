@@ -105,7 +105,9 @@ public:
     // writev (IOBuf::cut_multiple_into_file_descriptor).  In brpc KeepWrite runs in a new bthread; here it runs on the executor
     // set with SetKeepWriteExecutor (default: the writer's own thread, polling the fd while it would block).
     // A socket without an fd (tests, or a transport that ships _write_buf itself) just queues into _write_buf.
-    struct WriteRequest { IOBuf data; WriteRequest* next; };
+    // (`next` is written by the pusher after its exchange and read by the writer that waits for it to leave UNCONNECTED: an atomic here,
+    //  where butil gets away with a plain pointer on the platforms it supports)
+    struct WriteRequest { IOBuf data; std::atomic<WriteRequest*> next; };
     void set_fd(int fd) { _fd = fd; }
     int fd() const { return _fd; }
     typedef std::function<void(std::function<void()>)> KeepWriteExecutor;
