@@ -64,7 +64,7 @@ def compare(kh, k, cfg, chunks, flags=0):
     data, runs = make_runs(chunks)
     runs["flags"] = flags
     rs, msgs, resp = O.process_batch(cfg, data, runs)
-    buf = np.concatenate([np.asarray(data, np.uint8), np.zeros(4096, np.uint8)])
+    buf = np.concatenate([np.asarray(data, np.uint8), np.zeros(1024, np.uint8)])
     out = np.zeros(1, OUT_DT); reply = np.zeros(1 << 20, np.uint8)
     stats = {"n": 0, "fast": 0, "fused": 0, "err": 0}
     for i in range(len(msgs)):
@@ -205,7 +205,7 @@ def test_the_exactness_gate_with_adversarial_speculation(kh):
         runs["preferred_proto"] = rng.choice([-1, 1, 2])
         cfg = O.make_config(protocols=mask)
         rs, msgs, resp = O.process_batch(cfg, data, runs)
-        buf = np.concatenate([np.asarray(data, np.uint8), np.zeros(4096, np.uint8)])
+        buf = np.concatenate([np.asarray(data, np.uint8), np.zeros(1024, np.uint8)])
         for shift in (9, 11, 13):
             tile = 1 << shift
             nt = int(sum((int(l) + tile - 1) >> shift for l in runs["length"]))
