@@ -819,8 +819,8 @@ def main():
                     line["e2e_messenger"] = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else {"error": (out.stderr or out.stdout)[-300:]}
                 except Exception as e:      # noqa: BLE001
                     line["e2e_messenger"] = {"error": repr(e)}
-        if not args.no_cpu_baseline:
-            # bounded sample: the first 8 connections of the same batch, 1 thread, ~10 s
+        if not args.no_cpu_baseline and not use_dist:
+            # (rank 0 at N = 1 only) bounded sample: the first 8 connections of the same batch, 1 thread, ~10 s
             sub = runs[:8].copy()
             q1, m1, p1 = cpu_arm(data, sub, 1, min_seconds=8.0)
             line["cpu_baseline"] = {"value": q1, "unit": "msgs/s", "cores": 1, "kind": "port",

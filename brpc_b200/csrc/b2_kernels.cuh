@@ -923,7 +923,9 @@ __device__ __forceinline__ bool decode_one_impl(const BatchPtrs& B, const DevCon
                 B.msgs[i] = d; B.aux[i] = a;
                 const uint32_t csl = d.status == B2_MSG_RESPONSE_UNZ ? ((resp_len + 15u) & ~15u) : 0u;
                 if (kFused) {
-                    out->fast = false; out->prefix = 0; out->rs = 0; out->slow = resp_len > 0;
+                    // (an EMPTY message under a CRC32C checksum still has its checksum to verify: pack_one does, so it must see the message)
+                    out->fast = false; out->prefix = 0; out->rs = 0;
+                    out->slow = resp_len > 0 || (d.status == B2_MSG_RESPONSE && d.error_code == 0 && d.checksum_type == B2_CHECKSUM_TYPE_CRC32C);
                     B.slot[i] = csl ? fused_overflow_slot(B, C, csl) : 0u;
                     return false;
                 }
@@ -1688,7 +1690,11 @@ __device__ __forceinline__ void pack_one(const BatchPtrs& B, const DevConfig& C,
     const uint32_t bi = i / (kScanBlock * kScanItems);
     const uint32_t slot_off = C.fused ? B.slot[i] : B.slot[i] + B.scan_tmp[bi];
     const b2_msg_desc d = B.msgs[i];
-    if (d.resp_len == 0) { if (lane == 0 && d.status != B2_MSG_RESPONSE) B.msgs[i].resp_off = slot_off; return; }
+    __syncwarp();                                                   // (lane 0 stores resp_off / resp_len / status into msgs[i] further down: every lane has its copy first)
+    // nothing to produce — except for a client-side response that parsed to an empty message and carries a CRC32C checksum: Crc32cVerify comes
+    // before the parse in DeserializeRpcMessage, a wrong checksum fails the call whatever the message holds
+    const bool empty_to_verify = d.status == B2_MSG_RESPONSE && d.error_code == 0 && d.checksum_type == B2_CHECKSUM_TYPE_CRC32C;
+    if (d.resp_len == 0 && !empty_to_verify) { if (lane == 0 && d.status != B2_MSG_RESPONSE) B.msgs[i].resp_off = slot_off; return; }
     const MsgAux a = B.aux[i];
     const uint8_t* frame = B.bytes + d.frame_off;
     if (d.status == B2_MSG_REPLAY) {
@@ -2569,7 +2575,9 @@ __global__ void __launch_bounds__(256, B2_SLOW_MIN_BLOCKS) k_pack_slow(BatchPtrs
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n_slow) break;
         const uint32_t i = B.slow_idx[k];
-        if (C.fused && B.msgs[i].status == kDeferred) {              // parked by k_fused: the out-of-line decode (sizing pass included), then the pack
+        const bool deferred = C.fused && B.msgs[i].status == kDeferred;
+        __syncwarp();                                               // (every lane has read the status before lane 0 rewrites the descriptor)
+        if (deferred) {                                             // parked by k_fused: the out-of-line decode (sizing pass included), then the pack
             if (lane == 0) {
                 const uint32_t fo_raw = B.msgs[i].frame_off; DecodeOut o;
                 decode_one_gz<true>(B, C, i, fo_raw, B.bytes + (fo_raw & 0x7fffffffu), B.heads + (size_t)i * kHeadBytes, 0xffffffffu, B.msgs[i].run_idx, &o);

@@ -119,6 +119,31 @@ def test_k_small_bench_shape_codecs_and_client_side(sh):
     sh.sh_destroy(k)
 
 
+def empty_reply_frames():
+    """client-side replies whose EchoResponse is EMPTY (body b"" or 0a 00) under a CRC32C checksum, right and wrong: Crc32cVerify comes before
+    the parse (DeserializeRpcMessage), so a wrong checksum fails the call although there is nothing to hand over"""
+    from _traffic import raw_response_frame
+    out = []
+    for body in (b"", b"\x0a\x00", b"\x10\x05"):                 # nothing / an empty string / one unknown field (`message` is a required field: only the second parses)
+        good = O.lib.orc_crc32c_mask(O.crc32c(body)).to_bytes(4, "big")
+        bad = bytes([good[0] ^ 0x40]) + good[1:]
+        for cks in (good, bad, b"", good + b"\x00"):
+            out.append(raw_response_frame(body, 77 + len(out), checksum_type=1, checksum_value=cks))
+        out.append(raw_response_frame(body, 99, checksum_type=1, checksum_value=bad, attachment=b"tail"))
+    return out
+
+
+def test_k_small_verifies_the_checksum_of_empty_replies(sh):
+    k = make(sh, [dict(ECHO_METHOD)]); cfg = O.make_config()
+    fr = empty_reply_frames()
+    flg, dev, (data, runs) = k_small(sh, k, [b"".join(fr[i::2]) for i in range(2)], flags=1)
+    assert flg == 0
+    orc = O.process_batch(cfg, data, runs)
+    assert_same(dev, orc, "empty replies")
+    assert int((dev[1]["error_code"] == 1003).sum()) == 14 and int((dev[1]["error_code"] == 0).sum()) == 1     # only {0a 00} with the right checksum succeeds
+    sh.sh_destroy(k)
+
+
 def test_k_small_capacity_flags(sh):
     """more messages / reply bytes than the compact block holds: the kernel must flag it (the library then takes the tile pipeline), not overrun"""
     rng = random.Random(SEED + 983)

@@ -13,5 +13,5 @@ def test_fuzz_few_seconds(monkeypatch):
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import fuzz_parity
     monkeypatch.setenv("B2_SMALL", "on")
-    batches, seeds, msgs = fuzz_parity.run(budget=8.0, base_seed=123000)
+    batches, seeds, msgs = fuzz_parity.run(budget=float(os.environ.get("B2_FUZZ_SECONDS", "8")), base_seed=123000)     # (longer on the CPU emulator)
     assert batches >= 5 and msgs > 5000
