@@ -8,8 +8,10 @@
 //     exactly the launch's size (so an overrun is an ASan report); static __shared__ variables are function-local statics
 //   cudaMalloc / cudaHostAlloc = malloc (filled with B2_EMUL_FILL, default 0xa5: device memory comes as it is), copies are memcpy,
 //     streams are synchronous — except a launch on a stream created for a persistent kernel (be_launch_async), which runs on its own thread
-//   cp.async / cp.async.bulk (TMA) copies happen at issue time, mbarrier waits return at once: the DATA FLOW of the kernels is what is
-//     checked here, not the ordering of the asynchronous proxies
+//   cp.async / cp.async.bulk (TMA) copies happen at issue time — or, with B2_EMUL_ASYNC=late, at the latest moment the program's own waits
+//     allow (see "asynchronous copies" below): a missing wait shows as wrong bytes.  fence.proxy.async is not modelled
+//   A thread that returns from the kernel leaves the barriers (what the hardware does); B2_EMUL_WARN=1 reports a full-mask collective
+//     executed after lanes of the warp returned, B2_EMUL_TRACE=1 prints every launch
 #pragma once
 #include <execinfo.h>
 #include <pthread.h>
@@ -142,6 +144,7 @@ static inline unsigned long long clock64() { return be_now_ns(); }
 static inline void __nanosleep(unsigned ns) { timespec ts = { 0, (long)ns }; nanosleep(&ts, nullptr); }
 using std::min; using std::max;
 
+static inline void be_thread_exit();
 static void be_run_block(be_block_state& st, unsigned n, unsigned bidx, unsigned grid, void (*fn)(void*), void* arg) {
     st.block.init(n);
     const unsigned nw = (n + 31) / 32;
@@ -151,6 +154,7 @@ static void be_run_block(be_block_state& st, unsigned n, unsigned bidx, unsigned
     auto body = [](void* p) -> void* {
         Arg* a = (Arg*)p; be_cur = a->st; threadIdx.x = a->tid; blockDim.x = a->n; blockIdx.x = a->bidx; gridDim.x = a->grid;
         a->fn(a->arg);
+        be_thread_exit();
         a->st->warps[a->tid >> 5].bar.drop(); a->st->block.drop();      // an exited thread no longer takes part in barriers
         return nullptr;
     };
@@ -162,6 +166,63 @@ static void be_run_block(be_block_state& st, unsigned n, unsigned bidx, unsigned
         for (unsigned t = 0; t < n; t++) pthread_join(th[t], nullptr);
         pthread_attr_destroy(&at);
     }
+}
+
+// ------------------------------------------------------------------------------------------ asynchronous copies
+// B2_EMUL_ASYNC=issue (default): cp.async / cp.async.bulk copies happen when they are issued.
+// B2_EMUL_ASYNC=late: they happen at the LATEST moment the program allows — a bulk load lands when somebody waits on its mbarrier (the
+// destination holds 0xEE until then), a bulk store reads its shared-memory source when the issuing thread's wait_group(.read) retires its
+// group (or the thread exits), a 16-byte cp.async lands at cp.async.wait_group.  A kernel that reads a staging buffer before the wait, or
+// refills it before the store that reads it has drained, produces wrong bytes in this mode.
+#include <map>
+struct be_copy { void* dst; const void* src; uint32_t n; };
+static inline bool be_late() { static const bool v = [] { const char* e = getenv("B2_EMUL_ASYNC"); return e && !strcmp(e, "late"); }(); return v; }
+static std::mutex g_be_mbar_mu;
+static std::map<const void*, std::vector<be_copy>> g_be_mbar;                 // loads in flight, by the mbarrier that will announce them
+static thread_local std::vector<std::vector<be_copy>> be_store_groups;        // this thread's committed bulk-store groups, oldest first
+static thread_local std::vector<be_copy> be_store_open, be_cp16_pending;
+static inline void be_align16(const void* a, const void* b, uint32_t n, const char* what) {
+    if (((uintptr_t)a | (uintptr_t)b | n) & 15u) { fprintf(stderr, "cuda_emul: %s: misaligned %s (%p, %p, %u)\n", be_cur ? be_cur->kernel : "?", what, a, b, n); abort(); }
+}
+static inline void be_bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, const void* bar) {
+    be_align16(sdst, gsrc, bytes, "bulk load");
+    if (!be_late()) { memcpy(sdst, gsrc, bytes); return; }
+    memset(sdst, 0xEE, bytes);
+    std::lock_guard<std::mutex> l(g_be_mbar_mu); g_be_mbar[bar].push_back({ sdst, gsrc, bytes });
+}
+static inline void be_mbar_wait(const void* bar) {
+    if (!be_late()) return;
+    std::lock_guard<std::mutex> l(g_be_mbar_mu);
+    auto it = g_be_mbar.find(bar);
+    if (it == g_be_mbar.end()) return;
+    for (const be_copy& c : it->second) memcpy(c.dst, c.src, c.n);
+    g_be_mbar.erase(it);
+}
+static inline void be_bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    be_align16(gdst, ssrc, bytes, "bulk store");
+    if (!be_late()) { memcpy(gdst, ssrc, bytes); return; }
+    be_store_open.push_back({ gdst, ssrc, bytes });
+}
+static inline void be_bulk_commit() { if (be_late()) { be_store_groups.push_back(std::move(be_store_open)); be_store_open.clear(); } }
+static inline void be_bulk_retire(size_t keep) {
+    while (be_store_groups.size() > keep) {
+        for (const be_copy& c : be_store_groups.front()) memcpy(c.dst, c.src, c.n);
+        be_store_groups.erase(be_store_groups.begin());
+    }
+}
+static inline void be_cp16(void* sdst, const void* gsrc) {
+    if (!be_late()) { memcpy(sdst, gsrc, 16); return; }
+    memset(sdst, 0xEE, 16); be_cp16_pending.push_back({ sdst, gsrc, 16 });
+}
+static inline void be_cp16_wait() { for (const be_copy& c : be_cp16_pending) memcpy(c.dst, c.src, c.n); be_cp16_pending.clear(); }
+static inline void be_thread_exit() {          // a thread that leaves the kernel has nothing in flight any more
+    be_cp16_wait();
+    if (!be_store_open.empty()) be_bulk_commit();
+    be_bulk_retire(0);
+}
+static inline void be_prefetch(const void* gsrc, uint32_t bytes) {       // an L2 prefetch reads: a range beyond the buffer is an ASan report
+    be_align16(gsrc, gsrc, bytes, "prefetch");
+    const volatile uint8_t* p = (const volatile uint8_t*)gsrc; uint8_t a = 0; for (uint32_t i = 0; i < bytes; i++) a ^= p[i]; (void)a;
 }
 
 // ------------------------------------------------------------------------------------------ the runtime
@@ -180,7 +241,7 @@ typedef be_event* cudaEvent_t;
 
 static std::mutex g_be_mu;
 static std::set<std::pair<uintptr_t, size_t>> g_be_host;            // cudaHostAlloc'ed ranges (what cudaPointerGetAttributes reports as pinned + mapped)
-static inline int be_fill() { static int v = -1; if (v < 0) { const char* e = getenv("B2_EMUL_FILL"); v = e ? (int)strtol(e, nullptr, 0) & 0xff : 0xa5; } return v; }
+static inline int be_fill() { static const int v = [] { const char* e = getenv("B2_EMUL_FILL"); return e ? (int)strtol(e, nullptr, 0) & 0xff : 0xa5; }(); return v; }
 static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : e == cudaErrorNotReady ? "not ready" : "emulated CUDA error"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }

@@ -31,9 +31,12 @@ def device_source(name):
     src = open(os.path.join(CSRC, name)).read()
     if name == "b2_kernels.cuh":
         n0 = src.count('asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"')
-        src = src.replace('asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");', 'memcpy((void*)dst, (const void*)(src), 16);')
-        assert src.count("memcpy((void*)dst, (const void*)(src), 16);") == n0 == 2
+        src = src.replace('asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");', 'be_cp16((void*)dst, (const void*)(src));')
+        assert src.count("be_cp16((void*)dst, (const void*)(src));") == n0 == 2
         src = src.replace("const uint32_t dst = (uint32_t)__cvta_generic_to_shared(", "const size_t dst = (size_t)__cvta_generic_to_shared(")
+        n1 = src.count('asm volatile("cp.async.wait_group 0;" ::: "memory");')
+        src = src.replace('asm volatile("cp.async.wait_group 0;" ::: "memory");', "be_cp16_wait();")
+        assert n1 == 2
         # the snappy decoder's window in shared memory: a 32-bit shared address on the device, a pointer here
         src = replace_function(src, r"^__device__ __forceinline__ uint32_t ring_ld\(", "__device__ __forceinline__ uint32_t ring_ld(const uint8_t* ring_s, uint32_t p) { return ring_s[p & (kSnapRing - 1)]; }")
         src = replace_function(src, r"^__device__ __forceinline__ void ring_st\(", "__device__ __forceinline__ void ring_st(uint8_t* ring_s, uint32_t p, uint32_t v) { ring_s[p & (kSnapRing - 1)] = (uint8_t)v; }")
@@ -43,19 +46,13 @@ def device_source(name):
         # TMA + mbarrier: the copy happens when it is issued, the wait finds it done
         src = replace_function(src, r"^__device__ __forceinline__ void mbar_init\(", "__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t) { *bar = 0; }")
         src = replace_function(src, r"^__device__ __forceinline__ void mbar_arrive_expect_tx\(", "__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long*, uint32_t) {}")
-        src = replace_function(src, r"^__device__ __forceinline__ void mbar_wait\(", "__device__ __forceinline__ void mbar_wait(unsigned long long*, uint32_t) {}")
-        src = replace_function(src, r"^__device__ __forceinline__ void bulk_g2s\(",
-                               "__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long*) {\n"
-                               "    if (((uintptr_t)sdst | (uintptr_t)gsrc | bytes) & 15u) { fprintf(stderr, \"cuda_emul: misaligned bulk load\\n\"); abort(); }\n"
-                               "    memcpy(sdst, gsrc, bytes);\n}")
-        src = replace_function(src, r"^__device__ __forceinline__ void bulk_s2g\(",
-                               "__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {\n"
-                               "    if (((uintptr_t)gdst | (uintptr_t)ssrc | bytes) & 15u) { fprintf(stderr, \"cuda_emul: misaligned bulk store\\n\"); abort(); }\n"
-                               "    memcpy(gdst, ssrc, bytes);\n}")
-        src = replace_function(src, r"^__device__ __forceinline__ void bulk_prefetch_l2\(",
-                               "__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {\n"
-                               "    if (((uintptr_t)gsrc | bytes) & 15u) { fprintf(stderr, \"cuda_emul: misaligned prefetch\\n\"); abort(); }\n"
-                               "    const volatile uint8_t* p = (const volatile uint8_t*)gsrc; uint8_t a = 0; for (uint32_t i = 0; i < bytes; i++) a ^= p[i]; (void)a;\n}")
+        src = replace_function(src, r"^__device__ __forceinline__ void mbar_wait\(", "__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t) { be_mbar_wait(bar); }")
+        src = replace_function(src, r"^__device__ __forceinline__ void bulk_g2s\(", "__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar) { be_bulk_g2s(sdst, gsrc, bytes, bar); }")
+        src = replace_function(src, r"^__device__ __forceinline__ void bulk_s2g\(", "__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) { be_bulk_s2g(gdst, ssrc, bytes); }")
+        src = replace_function(src, r"^__device__ __forceinline__ void bulk_prefetch_l2\(", "__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) { be_prefetch(gsrc, bytes); }")
+        src = replace_function(src, r"^__device__ __forceinline__ void bulk_commit\(", "__device__ __forceinline__ void bulk_commit() { be_bulk_commit(); }")
+        src = replace_function(src, r"^template <int N> __device__ __forceinline__ void bulk_wait_read\(", "template <int N> __device__ __forceinline__ void bulk_wait_read() { be_bulk_retire(N); }")
+        src = replace_function(src, r"^template <int N> __device__ __forceinline__ void bulk_wait\(", "template <int N> __device__ __forceinline__ void bulk_wait() { be_bulk_retire(N); }")
         # the ring's doorbell words in mapped host memory, the device clock
         src = replace_function(src, r"^__device__ __forceinline__ uint32_t ld_sys_u32\(", "__device__ __forceinline__ uint32_t ld_sys_u32(const volatile uint32_t* p) { return __atomic_load_n((const uint32_t*)p, __ATOMIC_ACQUIRE); }")
         src = replace_function(src, r"^__device__ __forceinline__ void st_sys_u32\(", "__device__ __forceinline__ void st_sys_u32(volatile uint32_t* p, uint32_t v) { __atomic_store_n((uint32_t*)p, v, __ATOMIC_RELEASE); }")

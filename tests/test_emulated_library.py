@@ -3,7 +3,8 @@ CUDA execution model (tests/cpp/cuda_emul.h: blocks of host threads, warp collec
 done at issue time; tests/cpp/gen_emul_lib.py rewrites the launches and the inline PTX, nothing else), then GPU test files run against it
 UNCHANGED through the C ABI (tests/emul_runner.py points this one process's ctypes loader at the emulated build; the package itself cannot
 load it and has no CPU fallback).  What this checks: the data flow of the kernels and the host-side orchestration of every ABI call, bit for
-bit against the oracle, on a machine without a GPU.  What it cannot check: the ordering of the asynchronous proxies, and speed.
+bit against the oracle, on a machine without a GPU — with B2_EMUL_ASYNC=late also that every staging buffer is waited for before it is read
+or refilled (the asynchronous copies then land at the latest moment the kernel's own waits allow).  What it cannot check: speed.
 Default: a subset sized for the CPU suite; B2_LONG_TESTS=1 runs every GPU test file (about 25 minutes on 8 cores; results of the full run,
 also under AddressSanitizer, are in profiles/r2_emulator.md)."""
 import os
@@ -31,8 +32,8 @@ def build(out=None, extra=()):
     return so
 
 
-def run_files(files, timeout):
-    env = dict(os.environ, B2_EMUL_LIB=build(), B2_FUZZ_SECONDS="150")
+def run_files(files, timeout, **more):
+    env = dict(os.environ, B2_EMUL_LIB=build(), B2_FUZZ_SECONDS="150", **more)
     p = subprocess.run([sys.executable, os.path.join(HERE, "emul_runner.py"), *[os.path.join(HERE, f) for f in files], "-m", "gpu", "-q", "-x",
                         "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
     tail = (p.stdout + p.stderr)[-3000:]
@@ -43,6 +44,11 @@ def run_files(files, timeout):
 def test_gpu_test_files_pass_on_the_emulated_library():
     tail = run_files(QUICK, 900)
     assert " passed" in tail and "failed" not in tail and "skipped" not in tail
+
+
+def test_asynchronous_copies_landing_as_late_as_the_waits_allow():
+    tail = run_files(["test_gpu_zz_empty_reply_checksum.py", "test_gpu_dump.py"], 900, B2_EMUL_ASYNC="late")
+    assert " passed" in tail and "failed" not in tail
 
 
 def test_smoke_on_the_emulated_library():
