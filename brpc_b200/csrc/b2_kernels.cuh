@@ -444,9 +444,15 @@ __global__ void __launch_bounds__(256) k_resolve(BatchPtrs B, DevConfig C, uint3
     uint32_t* cp = link + nt;                                     // [nt] count << 2 | last_proto
     uint32_t* live = cp + nt;                                     // [nt]
     __shared__ uint32_t s_final_pos, s_warp_sum[8], s_warp_pf[8], s_carry_sum, s_carry_pf;
+    // The speculation rests on the cut at a position not depending on the preferred index (only the ORDER of the handlers does, and the tiles
+    // where bytes get popped on the way are re-walked).  On a CLIENT-side socket with more than baidu_std / streaming_rpc enabled that does
+    // not hold: the channel's protocol is fixed, a frame of another handler is an error there (input_messenger.cpp:122-138), so what a
+    // tile holds depends on the message before it.  Such runs take the exact chain: every tile re-walked in order with the true index.
+    const uint32_t rmask = run_mask(C.proto_mask, run.flags);
+    const bool pf_decides = (run.flags & B2_RUN_CLIENT) && !(rmask & kProtoMaskDump) && (rmask & ~((1u << B2_PROTOCOL_BAIDU_STD) | (1u << B2_PROTOCOL_STREAMING_RPC))) != 0;
     for (uint32_t k = threadIdx.x; k < nt; k += blockDim.x) {
         const TileRec t = tiles[k];
-        link[k] = (k == 0 && t.entry != 0) ? kLinkRewalk : make_link(t, tiles, nt, C.tile_shift);
+        link[k] = ((k == 0 && t.entry != 0) || pf_decides) ? kLinkRewalk : make_link(t, tiles, nt, C.tile_shift);
         cp[k] = (t.count << 4) | ((uint32_t)t.last_proto & 15u);     // (protocol indices go up to 12: nshead)
         live[k] = 0;
     }

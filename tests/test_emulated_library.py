@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 CPP = os.path.join(HERE, "cpp")
 LONG = os.environ.get("B2_LONG_TESTS") == "1"
 
-QUICK = ["test_gpu_zz_empty_reply_checksum.py", "test_gpu_h2.py", "test_gpu_crc32c.py", "test_gpu_dump.py"]
+QUICK = ["test_gpu_zz_late_fixes.py", "test_gpu_h2.py", "test_gpu_crc32c.py", "test_gpu_dump.py"]
 
 
 def build(out=None, extra=()):
@@ -47,7 +47,7 @@ def test_gpu_test_files_pass_on_the_emulated_library():
 
 
 def test_asynchronous_copies_landing_as_late_as_the_waits_allow():
-    tail = run_files(["test_gpu_zz_empty_reply_checksum.py", "test_gpu_dump.py"], 900, B2_EMUL_ASYNC="late")
+    tail = run_files(["test_gpu_zz_late_fixes.py", "test_gpu_dump.py"], 900, B2_EMUL_ASYNC="late")
     assert " passed" in tail and "failed" not in tail
 
 
@@ -63,3 +63,48 @@ def test_every_gpu_test_file_on_the_emulated_library():
     files = sorted(f for f in os.listdir(HERE) if f.startswith("test_gpu_") and f.endswith(".py"))
     for f in files:
         run_files([f], 3000)
+
+
+FAKE_NCCL = r"""
+#include <stddef.h>
+#include <stdint.h>
+// a stand-in for ncclAllReduce as two ranks holding the same counters would see it: checks what b2_counters_allreduce passes, doubles in place
+extern "C" int b2_fake_nccl_calls = 0;
+extern "C" int ncclAllReduce(const void* send, void* recv, size_t count, int dtype, int op, void* comm, void* stream) {
+    if (send != recv || dtype != 4 /*ncclInt64*/ || op != 0 /*ncclSum*/ || comm != (void*)0x1234 || !stream) return 5;   /* ncclInvalidArgument */
+    int64_t* p = (int64_t*)recv;
+    for (size_t i = 0; i < count; i++) p[i] *= 2;
+    b2_fake_nccl_calls++;
+    return 0;
+}
+"""
+
+
+def test_counters_allreduce_through_a_stand_in_nccl(tmp_path):
+    """b2_counters_allreduce (bvar Adder semantics across GPUs: one in-place ncclAllReduce of the device-resident counters) had no GPU run this
+    round: here the emulated library calls a stand-in ncclAllReduce that checks the arguments and plays a second rank with equal counters."""
+    src = tmp_path / "fake_nccl.cc"; so = tmp_path / "libfake_nccl.so"
+    src.write_text(FAKE_NCCL)
+    subprocess.check_call(["g++", "-O1", "-fPIC", "-shared", "-o", str(so), str(src)])
+    code = r'''
+import ctypes, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+fake = ctypes.CDLL(%r, mode=ctypes.RTLD_GLOBAL)
+import emul_runner; ctypes.CDLL = emul_runner.EmulCDLL
+import numpy as np, brpc_b200
+from brpc_b200 import abi, press
+ctx = brpc_b200.Context(device=0, max_batch_bytes=8 << 20, max_msgs=1 << 14, max_runs=64)
+data = np.zeros(8 * (64 << 10), dtype=np.uint8)
+runs, n_full = press.fill_batch(press.spec(payload_bytes=1024, payload_kind=1), data, 8, (64 << 10) - 77)
+ctx.process_batch(data, runs)
+before = list(ctx.counters())
+abi.lib.b2_counters_allreduce.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+assert abi.lib.b2_counters_allreduce(ctx._h, ctypes.c_void_p(0x1234)) == 0, abi.lib.b2_last_error()
+after = list(ctx.counters())
+assert before[1] == n_full and after == [2 * v for v in before], (before, after)
+assert ctypes.c_int.in_dll(fake, "b2_fake_nccl_calls").value == 1
+assert abi.lib.b2_counters_allreduce(ctx._h, None) != 0
+print("allreduce ok", before[:3], after[:3])
+''' % (ROOT, HERE, str(so))
+    p = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, B2_EMUL_LIB=build()), capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "allreduce ok" in p.stdout, (p.stdout + p.stderr)[-2000:]

@@ -1,0 +1,54 @@
+"""One-off fuzz run on the CPU (not part of the test suite): mixed / corrupted / truncated traffic of all five framings, codecs, attachments,
+limits, both sides — the generator of tools/fuzz_small_host.py — through the C ABI of the EMULATED library (tests/cpp/libb2rpc_emul.so, see
+tests/test_emulated_library.py), over random tile sizes, the one-launch path on / off, k_fused on / off, against the oracle bit for bit.
+Usage: python tools/fuzz_emul.py [seconds] [base seed]"""
+import ctypes, os, random, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "tools"))
+import emul_runner
+ctypes.CDLL = emul_runner.EmulCDLL
+import numpy as np
+import brpc_b200
+import _oracle as O
+from _compare import assert_same
+from brpc_b200.abi import ECHO_METHOD
+import fuzz_small_host as F
+
+
+def run(budget, base_seed):
+    t0 = time.time(); seed = 0; total = 0; batches = 0
+    while time.time() - t0 < budget:
+        seed += 1
+        rng = random.Random(base_seed + seed)
+        mask = rng.choice([F.ALL, (1 << 1) | (1 << 2), (1 << 1) | (1 << 3), (1 << 3) | (1 << 4) | (1 << 12)])
+        m = dict(ECHO_METHOD, response_checksum_type=rng.choice([0, 0, 1]), response_compress_type=rng.choice([0, 0, 1]), echo_attachment=rng.choice([0, 1]))
+        identity = rng.choice([None, b"10.1.2.3:8000"]); sth = rng.choice([0, 1]); max_body = rng.choice([0, 0, 600, 3000])
+        tile = rng.choice([0, 512, 1024, 4096, 16384])
+        os.environ["B2_SMALL"] = rng.choice(["on", "off", "off"]); os.environ["B2_FUSED"] = rng.choice(["on", "on", "off"])
+        ctx = brpc_b200.Context(device=0, max_batch_bytes=8 << 20, max_msgs=1 << 16, max_runs=1024, tile_bytes=tile, server_identity=identity,
+                                methods=[m], stream_handler=sth, max_body_size=max_body)
+        ctx.set_protocols(mask)
+        cfg = O.make_config(methods=[m], server_identity=identity, protocols=mask, max_body_size=max_body, stream_handler=sth)
+        client = rng.random() < 0.25
+        chunks = []
+        for s in range(rng.randrange(1, 90)):
+            b = bytearray(b"".join(F.one_frame(rng, j, client) for j in range(rng.randrange(1, 25))))
+            if rng.random() < 0.3 and len(b) > 20:
+                for _ in range(rng.randrange(1, 4)): b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+            if rng.random() < 0.1: b = b[rng.randrange(0, 13):]
+            if rng.random() < 0.4: b = b[:rng.randrange(len(b) + 1)]
+            chunks.append(bytes(b))
+        data, runs = brpc_b200.make_runs(chunks)
+        runs["preferred_proto"] = np.array([rng.choice([-1, -1, 1, 2, 3, 4, 12]) for _ in chunks], dtype=np.int32)
+        runs["flags"] = 1 if client else 0
+        for rep in range(2):                                   # (the second pass runs with the adapted tile size and, maybe, the other pipeline)
+            dev = ctx.process_batch(data, runs)
+            assert_same(dev, O.process_batch(cfg, data, runs), "fuzz seed %d tile %d small %s fused %s pass %d" % (base_seed + seed, tile, os.environ["B2_SMALL"], os.environ["B2_FUSED"], rep))
+        total += len(dev[1]); batches += 1
+        ctx.close()
+    return batches, seed, total
+
+
+if __name__ == "__main__":
+    b, sd, m = run(float(sys.argv[1]) if len(sys.argv) > 1 else 60.0, int(sys.argv[2]) if len(sys.argv) > 2 else 9000000)
+    print("fuzz ok: %d batches (%d seeds), %d messages, emulated library == oracle everywhere" % (b, sd, m))
