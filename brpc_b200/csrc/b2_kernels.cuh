@@ -938,6 +938,7 @@ __device__ __forceinline__ bool decode_one_impl(const BatchPtrs& B, const DevCon
                 B.slot[i] = csl;
                 PackJob cj; cj.src_off = 0; cj.bulk_len = 0; cj.head_len = 0; cj.pad = 0; cj.fast = 0; cj.slot_len = 0;
                 B.jobs[i] = cj;
+                if (C.by_ref) B.refs[i] = make_uint4(0, 0, 0, 0);            // (nothing is by reference on the client side; the entry is part of the output)
                 return false;
             }
             if ((m.has & B2_HAS_ATTACHMENT_SIZE) && (int64_t)req_size < att) {

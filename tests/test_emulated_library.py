@@ -32,10 +32,10 @@ def build(out=None, extra=()):
     return so
 
 
-def run_files(files, timeout, **more):
+def run_files(files, timeout, select=None, **more):
     env = dict(os.environ, B2_EMUL_LIB=build(), B2_FUZZ_SECONDS="150", **more)
     p = subprocess.run([sys.executable, os.path.join(HERE, "emul_runner.py"), *[os.path.join(HERE, f) for f in files], "-m", "gpu", "-q", "-x",
-                        "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+                        "-p", "no:cacheprovider", *(["-k", select] if select else [])], cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
     tail = (p.stdout + p.stderr)[-3000:]
     assert p.returncode == 0, tail
     return tail
@@ -47,7 +47,7 @@ def test_gpu_test_files_pass_on_the_emulated_library():
 
 
 def test_asynchronous_copies_landing_as_late_as_the_waits_allow():
-    tail = run_files(["test_gpu_zz_late_fixes.py", "test_gpu_dump.py"], 900, B2_EMUL_ASYNC="late")
+    tail = run_files(["test_gpu_zz_late_fixes.py", "test_gpu_dump.py"], 900, select="off-on or dump", B2_EMUL_ASYNC="late")      # (k_fused, k_pack_tma, k_pack_slow)
     assert " passed" in tail and "failed" not in tail
 
 

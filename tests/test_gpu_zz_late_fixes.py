@@ -103,3 +103,33 @@ def test_client_channel_protocol_is_fixed_also_across_tiles(small, fused, tile):
     n = dev[0]["n_msgs"]
     if small == "off":                                                  # (whole runs: what each channel accepted before the foreign frame)
         assert list(n) == [24, 24, 25, 3, 7, 24, 24, 24]
+
+
+def test_by_reference_entries_of_client_side_messages_are_written():
+    """B2_RESP_BY_REF: refs[i] is part of the output for EVERY message; the client-side branch of the decoder left it as the memory came
+    (tools/fuzz_emul.py on the emulated library, whose cudaMalloc memory arrives filled with 0xa5)."""
+    import random
+    import brpc_b200
+    from brpc_b200.abi import PinnedBuffer
+    rng = random.Random(20260923)
+    m = dict(brpc_b200.abi.ECHO_METHOD, response_compress_type=1)
+    d0, r0 = brpc_b200.make_runs([b"".join(echo_frame(rng, 100 * s + j, rnd62(rng, rng.choice([0, 40, 1024]))) for j in range(30)) for s in range(6)])
+    o = O.process_batch(O.make_config(methods=[m]), d0, r0)
+    replies = [bytes(o[2][int(x["resp_off"]):int(x["resp_off"]) + int(x["resp_len"])]) for x in o[1]]           # snappy-compressed EchoResponses
+    data, runs = brpc_b200.make_runs([b"".join(replies[30 * s:30 * s + 30]) for s in range(6)])
+    runs["flags"] = 1
+    pin = PinnedBuffer(len(data)); pin.array[:] = data
+    for small in ("on", "off"):
+        os.environ["B2_SMALL"] = small
+        try:
+            ctx = brpc_b200.Context(device=0, max_batch_bytes=16 << 20, max_msgs=1 << 16, max_runs=256)
+        finally:
+            os.environ.pop("B2_SMALL")
+        for im in (0, 1):
+            ctx.set_modes(im, 1)
+            rs, msgs, resp, info = ctx.process_batch_ptr(pin.ptr, len(data), runs)
+            assert len(msgs) == 180 and set(msgs["status"].tolist()) <= {7, 8} and int((msgs["status"] == 8).sum()) > 100
+            refs = info["refs"]
+            assert refs is not None and not refs["src_len"].any() and not refs["prefix_len"].any() and not refs["src_off"].any()
+        ctx.close()
+    pin.free()

@@ -13,10 +13,41 @@ import _oracle as O
 from _compare import assert_same
 from brpc_b200.abi import ECHO_METHOD
 import fuzz_small_host as F
+from _compare import MSG_FIELDS, RUN_FIELDS
+from test_gpu_modes import replies
+from brpc_b200.abi import PinnedBuffer
+
+MODES = [(1, 0), (0, 1), (1, 1), (0, 2), (1, 2)]
 
 
-def run(budget, base_seed):
-    t0 = time.time(); seed = 0; total = 0; batches = 0
+def check_modes(ctx, data, runs, orc, rng, what):
+    """B2_INPUT_PULL / B2_RESP_BY_REF / B2_RESP_IOVEC give what the copy path gives (tests/test_gpu_modes.py's comparison, on this traffic)"""
+    o_rs, o_msgs, o_resp = orc
+    pin = PinnedBuffer(max(len(data), 16)); pin.array[:len(data)] = data
+    want = replies(data, o_msgs, o_resp, None)
+    for im, rm in rng.sample(MODES, 2):
+        ctx.set_modes(im, rm)
+        rs, msgs, resp, info = ctx.process_batch_ptr(pin.ptr, len(data), runs)
+        tag = "%s input=%d resp=%d" % (what, im, rm)
+        for f in RUN_FIELDS:
+            assert np.array_equal(rs[f], o_rs[f]), tag + " run." + f
+        assert len(msgs) == len(o_msgs), tag
+        for f in MSG_FIELDS:
+            assert np.array_equal(msgs[f], o_msgs[f]), tag + " msgs." + f
+        if rm == 2 and len(msgs):
+            iov = info["iov"]; answered = (msgs["status"] == 0) | (msgs["status"] == 1)
+            for k in range(len(msgs)):
+                g = b"".join(ctypes.string_at(int(iov["base"][j]), int(iov["len"][j])) for j in (2 * k, 2 * k + 1) if iov["len"][j])
+                assert g == (want[k] if answered[k] else b""), "%s iovec reply %d differs (status %d)" % (tag, k, msgs["status"][k])
+            continue
+        got = replies(pin.array, msgs, resp, info["refs"])
+        for k, (g, w) in enumerate(zip(got, want)):
+            assert g == w, "%s reply %d differs (status %d)" % (tag, k, msgs["status"][k])
+    ctx.set_modes(0, 0); pin.free()
+
+
+def run(budget, base_seed, first=0):
+    t0 = time.time(); seed = first; total = 0; batches = 0
     while time.time() - t0 < budget:
         seed += 1
         rng = random.Random(base_seed + seed)
@@ -44,11 +75,14 @@ def run(budget, base_seed):
         for rep in range(2):                                   # (the second pass runs with the adapted tile size and, maybe, the other pipeline)
             dev = ctx.process_batch(data, runs)
             assert_same(dev, O.process_batch(cfg, data, runs), "fuzz seed %d tile %d small %s fused %s pass %d" % (base_seed + seed, tile, os.environ["B2_SMALL"], os.environ["B2_FUSED"], rep))
+        if seed % 3 == 0:
+            print("modes at seed", base_seed + seed, flush=True) if os.environ.get("B2_FUZZ_VERBOSE") else None
+            check_modes(ctx, data, runs, O.process_batch(cfg, data, runs), rng, "fuzz seed %d modes" % (base_seed + seed))
         total += len(dev[1]); batches += 1
         ctx.close()
     return batches, seed, total
 
 
 if __name__ == "__main__":
-    b, sd, m = run(float(sys.argv[1]) if len(sys.argv) > 1 else 60.0, int(sys.argv[2]) if len(sys.argv) > 2 else 9000000)
+    b, sd, m = run(float(sys.argv[1]) if len(sys.argv) > 1 else 60.0, int(sys.argv[2]) if len(sys.argv) > 2 else 9000000, int(sys.argv[3]) if len(sys.argv) > 3 else 0)
     print("fuzz ok: %d batches (%d seeds), %d messages, emulated library == oracle everywhere" % (b, sd, m))
