@@ -18,6 +18,21 @@ from test_gpu_modes import replies
 from brpc_b200.abi import PinnedBuffer
 
 MODES = [(1, 0), (0, 1), (1, 1), (0, 2), (1, 2)]
+from _traffic import mixed_frames, echo_frame, rnd62
+
+
+def frame(rng, j, client, sth):
+    """fuzz_small_host's frames plus: every branch of ProcessRpcRequest (mixed_frames), frames larger than k_fused's staging buffer,
+    streaming DATA frames whose payload is a (sometimes damaged) snappy stream when the stream handler decompresses"""
+    c = rng.random()
+    if c < 0.25:
+        return b"".join(mixed_frames(rng, 1, big=rng.random() < 0.15))
+    if c < 0.32 and sth:
+        f = echo_frame(rng, j, rnd62(rng, rng.choice([0, 30, 900, 5000])), compress_type=1)
+        z = bytearray(f[12 + int.from_bytes(f[8:12], "big"):])                       # a snappy stream
+        if rng.random() < 0.3 and z: z[rng.randrange(len(z))] ^= 1 << rng.randrange(8)
+        return O.pack_stream_frame(rng.randrange(1 << 40), rng.choice([-1, 77]), 3, rng.choice([None, True, False]), bytes(z))
+    return F.one_frame(rng, j, client)
 
 
 def check_modes(ctx, data, runs, orc, rng, what):
@@ -56,14 +71,15 @@ def run(budget, base_seed, first=0):
         identity = rng.choice([None, b"10.1.2.3:8000"]); sth = rng.choice([0, 1]); max_body = rng.choice([0, 0, 600, 3000])
         tile = rng.choice([0, 512, 1024, 4096, 16384])
         os.environ["B2_SMALL"] = rng.choice(["on", "off", "off"]); os.environ["B2_FUSED"] = rng.choice(["on", "on", "off"])
+        ms = [m] + ([dict(ECHO_METHOD, method_name=b"Echo2", handler=0)] if rng.random() < 0.5 else [])          # (Echo2: a host-handled method)
         ctx = brpc_b200.Context(device=0, max_batch_bytes=8 << 20, max_msgs=1 << 16, max_runs=1024, tile_bytes=tile, server_identity=identity,
-                                methods=[m], stream_handler=sth, max_body_size=max_body)
+                                methods=ms, stream_handler=sth, max_body_size=max_body)
         ctx.set_protocols(mask)
-        cfg = O.make_config(methods=[m], server_identity=identity, protocols=mask, max_body_size=max_body, stream_handler=sth)
+        cfg = O.make_config(methods=ms, server_identity=identity, protocols=mask, max_body_size=max_body, stream_handler=sth)
         client = rng.random() < 0.25
         chunks = []
         for s in range(rng.randrange(1, 90)):
-            b = bytearray(b"".join(F.one_frame(rng, j, client) for j in range(rng.randrange(1, 25))))
+            b = bytearray(b"".join(frame(rng, j, client, sth) for j in range(rng.randrange(1, 25))))
             if rng.random() < 0.3 and len(b) > 20:
                 for _ in range(rng.randrange(1, 4)): b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
             if rng.random() < 0.1: b = b[rng.randrange(0, 13):]
