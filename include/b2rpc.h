@@ -584,6 +584,49 @@ typedef struct b2_h2_response {
 int  b2_h2_pack_responses(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_h2_response* resps, uint32_t n,
                           void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens);
 
+/* b2_h2_pack_requests — the CLIENT side of the same connection state: H2UnsentRequest::New (src/brpc/policy/http2_rpc_protocol.cpp:
+ * 1382-1453: the header list) + H2UnsentRequest::AppendAndDestroySelf (:1496-1592) + PackH2Message (:1310-1380), what PackH2Request
+ * (:1784-1800) queues for a call on an "h2" / "h2:grpc" channel.  Per request, in the reference's order:
+ *   - the first request of a connection (b2_h2_conn_reset, nothing packed yet) is preceded by the 24-byte client preface and
+ *     SerializeH2SettingsFrameAndWU of the default client settings (:253-265, flags :34-43: ENABLE_PUSH 0, INITIAL_WINDOW_SIZE 256 KiB,
+ *     connection WINDOW_UPDATE 1 MiB - 65535) — written even when the request itself is then refused, as `out` has them there;
+ *   - AllocateClientStreamId (http2_rpc_protocol.h:399-412): 1, 3, 5, ...; past 0x7fffffff -> B2_H2_REQ_RUNOUT (EH2RUNOUTSTREAMS);
+ *   - a non-empty body is charged to the flow-control windows (H2StreamContext::ConsumeWindowSize :1199-1219): the peer's initial stream
+ *     window, then MinusWindowSize on the connection window; not enough -> B2_H2_REQ_ELIMIT, the stream id stays consumed;
+ *   - HPacker::Encode (details/hpack.cpp:696-726) against the connection's encoder table of ":method" (POST, or GET with
+ *     B2_H2_REQ_GET), ":scheme" (http / https), ":path", ":authority", "content-type" when non-empty, "accept: * / *" and
+ *     "user-agent: brpc/1.0 curl/7.0" when the flags say the call set neither (need_accept / need_user_agent), then the call's own
+ *     headers in the order the caller lists them (the reference iterates its HttpHeader map: for gRPC "te: trailers",
+ *     "grpc-accept-encoding", "grpc-timeout" of policy/http_rpc_protocol.cpp:660-704); never-indexed when the peer announced
+ *     header_table_size 0;
+ *   - HEADERS (+CONTINUATION) and the body as DATA frames split at the peer's max_frame_size, END_STREAM on the last frame, the
+ *     deferred connection WINDOW_UPDATE; B2_H2_REQ_GRPC prepends AddGrpcPrefix's 5 bytes (policy/http_rpc_protocol.cpp:254-262).
+ * `extra` headers: records {u16 name_len, u16 value_len (little endian), name, value} back to back at extra_off, extra_len bytes.
+ * The pending-stream count against max_concurrent_streams (:1529) and GOAWAY (TryToInsertStream :425-436) belong to the
+ * caller's correlation map, not to this call.  The peer's settings / WINDOW_UPDATEs reach the state through
+ * b2_h2_process_batch runs of that connection.  Requests of one connection must be adjacent and in write order. */
+#define B2_H2_REQ_GRPC       1u
+#define B2_H2_REQ_GET        2u     /* :method GET instead of POST */
+#define B2_H2_REQ_HTTPS      4u     /* :scheme https */
+#define B2_H2_REQ_ACCEPT     8u     /* need_accept: append accept: * / * */
+#define B2_H2_REQ_USER_AGENT 16u    /* need_user_agent: append user-agent: brpc/1.0 curl/7.0 */
+#define B2_H2_REQ_OK     0
+#define B2_H2_REQ_ELIMIT 1          /* brpc ELIMIT: remote_window_left is not enough */
+#define B2_H2_REQ_RUNOUT 2          /* brpc EH2RUNOUTSTREAMS */
+typedef struct b2_h2_request {
+    uint32_t conn, flags;
+    uint32_t path_off, path_len;                     /* inside bytes: URI::GenerateH2Path's result */
+    uint32_t authority_off, authority_len;
+    uint32_t content_type_off, content_type_len;     /* length 0 = no content-type header */
+    uint32_t body_off, body_len;                     /* the attachment; for gRPC the serialized message */
+    uint32_t extra_off, extra_len;
+} b2_h2_request;                                     /* 48 bytes */
+typedef struct b2_h2_request_result { int32_t status; uint32_t stream_id, out_off, out_len; } b2_h2_request_result;   /* 16 bytes */
+int  b2_h2_pack_requests(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_h2_request* reqs, uint32_t n,
+                         void* out, uint32_t out_cap, b2_h2_request_result* results);
+/* the reference's own unit-test hook (:348-352: its tests start 10 000 ids before the end of the id space): the next client stream id */
+int  b2_h2_conn_set_next_stream_id(b2_ctx* ctx, uint32_t conn, uint32_t next_id);
+
 /* ---- counters (bvar::Adder-like): per-GPU totals accumulated by
  * the kernels: [0] in_bytes [1] in_msgs [2] out_bytes [3] out_msgs [4] errors
  * [5] batches [6..7] reserved.  The cross-GPU reduce is an NCCL all-reduce on

@@ -25,6 +25,7 @@ struct orc_h2_conn {
     uint32_t r_header_table_size, r_enable_push, r_max_concurrent_streams, r_stream_window_size, r_max_frame_size, r_max_header_list_size;
     uint32_t l_stream_window_size, l_max_frame_size;
     int64_t remote_window_left, deferred_window_update;
+    int64_t last_sent_stream_id; int preface_sent;     /* client side: H2Context::_last_sent_stream_id (:331), ctx == NULL in AppendAndDestroySelf */
     h2_stream* streams; uint32_t n_pending, cap;      /* _pending_streams */
     orc_hpack* hp;
     /* HPacker::_encode_table: newest first */
@@ -32,7 +33,7 @@ struct orc_h2_conn {
 };
 orc_h2_conn* orc_h2_conn_new(void) {                 /* H2Context::H2Context (:323-353) + Init (:363-371), server side */
     orc_h2_conn* c = (orc_h2_conn*)calloc(1, sizeof *c);
-    c->last_received_stream_id = -1;
+    c->last_received_stream_id = -1; c->last_sent_stream_id = 1;
     c->r_header_table_size = 4096; c->r_enable_push = 0; c->r_max_concurrent_streams = 0xffffffffu;
     c->r_stream_window_size = (uint32_t)MAX_WINDOW; c->r_max_frame_size = 16384; c->r_max_header_list_size = 0xffffffffu;
     c->l_stream_window_size = 256 * 1024; c->l_max_frame_size = 16384;
@@ -494,4 +495,70 @@ uint32_t orc_h2_pack_response(orc_h2_conn* c, const b2_h2_response* R, const uin
     if (c->deferred_window_update > 0) { const int64_t cw = c->deferred_window_update; c->deferred_window_update = 0; put_head(o, 4, 8, 0, 0); put32(o + 9, (uint32_t)cw); o += 13; }
     free(frag); free(trailer); free(data);
     return (uint32_t)(o - out);
+}
+
+/* ---- client side: H2UnsentRequest::New (:1382-1453) + AppendAndDestroySelf (:1496-1592) + PackH2Message (:1310-1380) ------------ */
+void orc_h2_conn_set_next_stream_id(orc_h2_conn* c, uint32_t id) { c->last_sent_stream_id = id; }
+static uint8_t* encode_n(orc_h2_conn* c, uint8_t* p, const uint8_t* n, uint32_t nl, const uint8_t* v, uint32_t vl, int never_index) {
+    char name[512]; if (nl >= sizeof name) nl = sizeof name - 1;
+    memcpy(name, n, nl); name[nl] = 0;                                  /* (header names hold no NUL) */
+    return encode(c, p, name, v, vl, never_index);
+}
+int32_t orc_h2_pack_request(orc_h2_conn* c, const b2_h2_request* R, const uint8_t* bytes, uint8_t* out, uint32_t* out_len, uint32_t* stream_id) {
+    uint8_t* o = out;
+    *stream_id = 0;
+    if (!c->preface_sent) {                                             /* ctx == NULL: preface + SerializeH2SettingsFrameAndWU(_unack_local_settings) (:1508-1526) */
+        c->preface_sent = 1;
+        memcpy(o, "PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n", 24); o += 24;
+        put_head(o, 12, 4, 0, 0);
+        o[9] = 0; o[10] = 2; put32(o + 11, 0);                          /* ENABLE_PUSH = 0 (H2Settings(): enable_push false, http2.cpp:26-34) */
+        o[15] = 0; o[16] = 4; put32(o + 17, 256 * 1024);                /* FLAGS_h2_client_stream_window_size */
+        put_head(o + 21, 4, 8, 0, 0); put32(o + 30, 1024 * 1024 - 65535);   /* FLAGS_h2_client_connection_window_size - 65535 */
+        o += 34;
+    }
+    *out_len = (uint32_t)(o - out);
+    if (c->last_sent_stream_id > 0x7FFFFFFFll) return B2_H2_REQ_RUNOUT; /* AllocateClientStreamId, http2_rpc_protocol.h:399-412 */
+    const uint32_t id = (uint32_t)c->last_sent_stream_id; c->last_sent_stream_id += 2;
+    *stream_id = id;
+    const int grpc = R->flags & B2_H2_REQ_GRPC;
+    const uint32_t data_size = R->body_len + (grpc ? 5u : 0u);
+    if (data_size) {                                                    /* ConsumeWindowSize (:1199-1219); Init (:1176-1181): the stream starts with the peer's initial window */
+        if ((int64_t)c->r_stream_window_size < (int64_t)data_size) return B2_H2_REQ_ELIMIT;
+        if (c->remote_window_left < (int64_t)data_size) return B2_H2_REQ_ELIMIT;
+        c->remote_window_left -= (int64_t)data_size;
+    }
+    const int never = c->r_header_table_size == 0;
+    uint8_t* frag = (uint8_t*)malloc(8192); uint8_t* f = frag;
+    f = encode(c, f, ":method", (const uint8_t*)((R->flags & B2_H2_REQ_GET) ? "GET" : "POST"), (R->flags & B2_H2_REQ_GET) ? 3 : 4, never);
+    f = encode(c, f, ":scheme", (const uint8_t*)((R->flags & B2_H2_REQ_HTTPS) ? "https" : "http"), (R->flags & B2_H2_REQ_HTTPS) ? 5 : 4, never);
+    f = encode(c, f, ":path", bytes + R->path_off, R->path_len, never);
+    f = encode(c, f, ":authority", bytes + R->authority_off, R->authority_len, never);
+    if (R->content_type_len) f = encode(c, f, "content-type", bytes + R->content_type_off, R->content_type_len, never);
+    if (R->flags & B2_H2_REQ_ACCEPT) f = encode(c, f, "accept", (const uint8_t*)"*/*", 3, never);
+    if (R->flags & B2_H2_REQ_USER_AGENT) f = encode(c, f, "user-agent", (const uint8_t*)"brpc/1.0 curl/7.0", 17, never);
+    for (uint32_t at = 0; at + 4 <= R->extra_len;) {
+        const uint8_t* e = bytes + R->extra_off + at;
+        const uint32_t nl = e[0] | ((uint32_t)e[1] << 8), vl = e[2] | ((uint32_t)e[3] << 8);
+        if (at + 4 + nl + vl > R->extra_len) break;
+        f = encode_n(c, f, e + 4, nl, e + 4 + nl, vl, never);
+        at += 4 + nl + vl;
+    }
+    const uint32_t fl = (uint32_t)(f - frag), mfs = c->r_max_frame_size;
+    const uint8_t hflags = data_size == 0 ? 0x1 : 0;                    /* PackH2Message with empty trailers */
+    if (fl <= mfs) { put_head(o, fl, 1, hflags | 0x4, id); o += 9; memcpy(o, frag, fl); o += fl; }
+    else {
+        put_head(o, mfs, 1, hflags, id); o += 9; memcpy(o, frag, mfs); o += mfs;
+        for (uint32_t at = mfs; at < fl;) { const uint32_t nn = fl - at < mfs ? fl - at : mfs; put_head(o, nn, 9, at + nn == fl ? 0x4 : 0, id); o += 9; memcpy(o, frag + at, nn); o += nn; at += nn; }
+    }
+    uint8_t pre[5] = {0, 0, 0, 0, 0}; put32(pre + 1, R->body_len);
+    for (uint32_t at = 0; at < data_size;) {
+        const uint32_t nn = data_size - at < mfs ? data_size - at : mfs;
+        put_head(o, nn, 0, at + nn == data_size ? 0x1 : 0, id); o += 9;
+        for (uint32_t k = 0; k < nn; k++) { const uint32_t q = at + k; o[k] = grpc ? (q < 5 ? pre[q] : bytes[R->body_off + q - 5]) : bytes[R->body_off + q]; }
+        o += nn; at += nn;
+    }
+    if (c->deferred_window_update > 0) { const int64_t cw = c->deferred_window_update; c->deferred_window_update = 0; put_head(o, 4, 8, 0, 0); put32(o + 9, (uint32_t)cw); o += 13; }
+    free(frag);
+    *out_len = (uint32_t)(o - out);
+    return B2_H2_REQ_OK;
 }

@@ -244,12 +244,33 @@ H2_RESPONSE_DT = np.dtype([("conn", "<u4"), ("stream_id", "<u4"), ("status_code"
                            ("grpc_message_off", "<u4"), ("grpc_message_len", "<u4"), ("reserved", "<u4")])
 lib.orc_h2_pack_response.restype = C.c_uint32
 lib.orc_h2_pack_response.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]
+H2_REQUEST_DT = np.dtype([("conn", "<u4"), ("flags", "<u4"), ("path_off", "<u4"), ("path_len", "<u4"), ("authority_off", "<u4"),
+                          ("authority_len", "<u4"), ("content_type_off", "<u4"), ("content_type_len", "<u4"), ("body_off", "<u4"),
+                          ("body_len", "<u4"), ("extra_off", "<u4"), ("extra_len", "<u4")])          # == b2_h2_request, 48 bytes
+lib.orc_h2_pack_request.restype = C.c_int32
+lib.orc_h2_pack_request.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+lib.orc_h2_conn_set_next_stream_id.argtypes = [C.c_void_p, C.c_uint32]
 lib.orc_h2_conn_new.restype = C.c_void_p
 lib.orc_h2_conn_free.argtypes = [C.c_void_p]
 lib.orc_h2_consume.restype = C.c_uint32
 lib.orc_h2_consume.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
                                C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
                                C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+
+
+def h2_extra_records(extra):
+    return b"".join(len(n).to_bytes(2, "little") + len(v).to_bytes(2, "little") + bytes(n) + bytes(v) for n, v in extra)
+
+
+def h2_request_blob(calls):
+    """calls: (conn, flags, path, authority, content_type, body, extra headers) -> (blob bytes, H2_REQUEST_DT array)."""
+    parts = []; r = np.zeros(len(calls), H2_REQUEST_DT); at = 0
+    for i, (conn, flags, path, authority, ct, body, extra) in enumerate(calls):
+        ex = h2_extra_records(extra); offs = []
+        for piece in (path, authority, ct, body, ex):
+            offs.append(at); parts.append(bytes(piece)); at += len(piece)
+        r[i] = (conn, flags, offs[0], len(path), offs[1], len(authority), offs[2], len(ct), offs[3], len(body), offs[4], len(ex))
+    return b"".join(parts) + b"\0", r
 
 
 class H2Conn:
@@ -275,6 +296,16 @@ class H2Conn:
         out = np.zeros(len(body) * 2 + 4096, np.uint8)
         n = lib.orc_h2_pack_response(self._h, r.ctypes.data, blob, out.ctypes.data)
         return out[:n].tobytes()
+
+    def pack_request(self, path, authority, body=b"", content_type=b"application/grpc", flags=1 | 8 | 16, extra=()):
+        """Client side (H2UnsentRequest).  Returns (status, stream_id, bytes)."""
+        blob, r = h2_request_blob([(0, flags, path, authority, content_type, body, extra)])
+        out = np.zeros(len(body) * 2 + 8192, np.uint8); ol, sid = C.c_uint32(), C.c_uint32()
+        st = lib.orc_h2_pack_request(self._h, r.ctypes.data, blob, out.ctypes.data, C.byref(ol), C.byref(sid))
+        return st, sid.value, out[:ol.value].tobytes()
+
+    def set_next_stream_id(self, sid):
+        lib.orc_h2_conn_set_next_stream_id(self._h, sid)
 
     def __del__(self):
         if self._h:
