@@ -1235,6 +1235,69 @@ extern "C" int b2_h2_pack_responses(b2_ctx* c, const void* bytes, uint32_t nbyte
     return B2_OK;
 }
 
+// client side of h2: see include/b2rpc.h
+extern "C" int b2_h2_pack_requests(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_h2_request* reqs, uint32_t n,
+                                   void* out, uint32_t out_cap, b2_h2_request_result* results) {
+    if (!c || !bytes || !reqs || !out || !results) { set_err("null argument"); return B2_E_INVAL; }
+    static_assert(sizeof(b2_h2_request) == 48 && sizeof(b2_h2_request_result) == 16, "h2 request ABI layout");
+    if (nbytes > c->opt.max_resp_bytes || n > c->opt.max_msgs || out_cap > c->opt.max_resp_bytes) { set_err("exceeds ctx capacity"); return B2_E_CAPACITY; }
+    if (n == 0) return B2_OK;
+    std::vector<uint32_t> first;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const b2_h2_request& r = reqs[i];
+        if (r.conn >= c->h2_max_conns || (uint64_t)r.path_off + r.path_len > nbytes || (uint64_t)r.authority_off + r.authority_len > nbytes ||
+            (uint64_t)r.content_type_off + r.content_type_len > nbytes || (uint64_t)r.body_off + r.body_len > nbytes ||
+            (uint64_t)r.extra_off + r.extra_len > nbytes) { set_err("bad request descriptor"); return B2_E_INVAL; }
+        // the encoded header block must fit the kernel's shared-memory fragment: every header costs at most its bytes + 2 x 3 length bytes + 1
+        uint64_t hdr = 4 * 16 + 64 + (uint64_t)r.path_len + r.authority_len + r.content_type_len + 16 + 32, n_extra = 0;
+        for (uint32_t at = 0; at + 4 <= r.extra_len;) {
+            const uint8_t* e = static_cast<const uint8_t*>(bytes) + r.extra_off + at;
+            const uint32_t nl = e[0] | ((uint32_t)e[1] << 8), vl = e[2] | ((uint32_t)e[3] << 8);
+            if (at + 4 + nl + vl > r.extra_len) { set_err("truncated extra header record"); return B2_E_INVAL; }
+            if (nl + vl > kH2ReqFragCap / 2) { set_err("header too long"); return B2_E_INVAL; }
+            hdr += nl + vl + 8; n_extra++; at += 4 + nl + vl;
+        }
+        if (hdr > kH2ReqFragCap || r.path_len + 16 > kH2ReqFragCap / 2 || r.authority_len + 16 > kH2ReqFragCap / 2 || r.content_type_len + 16 > kH2ReqFragCap / 2) { set_err("header block too long"); return B2_E_INVAL; }
+        if (i == 0 || r.conn != reqs[i - 1].conn) first.push_back(i);
+        const uint64_t data = (uint64_t)r.body_len + 5;
+        const uint64_t need = 58 + hdr + 9 + data + 9 * (data / 16384 + 4) + 13 + 16;
+        results[i].status = 0; results[i].stream_id = 0; results[i].out_off = (uint32_t)total; results[i].out_len = 0;
+        total = (total + need + 15) & ~15ull;
+        if (total > out_cap) { set_err("out_cap too small"); return B2_E_CAPACITY; }
+    }
+    const uint32_t n_groups = (uint32_t)first.size();
+    first.push_back(n);
+    for (uint32_t g = 0; g < n_groups; g++)
+        for (uint32_t g2 = g + 1; g2 < n_groups; g2++) if (reqs[first[g]].conn == reqs[first[g2]].conn) { set_err("requests of one connection must be adjacent"); return B2_E_INVAL; }
+    int rc = h2_ensure(c); if (rc != B2_OK) return rc;
+    CU(cudaSetDevice(c->opt.device));
+    b2_h2_request* d_reqs = reinterpret_cast<b2_h2_request*>(c->d_msgs);          // 48 B <= 64 B per entry
+    b2_h2_request_result* d_res = reinterpret_cast<b2_h2_request_result*>(c->d_aux);
+    static_assert(sizeof(MsgAux) >= sizeof(b2_h2_request_result), "results live in the aux array");
+    uint32_t* d_first = c->d_frame_off;
+    uint8_t* d_in = c->d_unz + c->opt.max_resp_bytes;             // second half of the scratch (as b2_h2_pack_responses)
+    CU(cudaMemcpyAsync(d_in, bytes, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_reqs, reqs, sizeof(b2_h2_request) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_res, results, sizeof(b2_h2_request_result) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_first, first.data(), 4 * first.size(), cudaMemcpyHostToDevice, c->stream));
+    k_h2_pack_req<<<(n_groups + kH2PackWarps - 1) / kH2PackWarps, kH2PackWarps * 32, 0, c->stream>>>(d_in, d_reqs, d_first, n_groups, c->d_h2, c->d_resp, d_res);
+    CU(cudaMemcpyAsync(results, d_res, sizeof(b2_h2_request_result) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out, c->d_resp, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->uploaded = false; c->executed = false;
+    return B2_OK;
+}
+extern "C" int b2_h2_conn_set_next_stream_id(b2_ctx* c, uint32_t conn, uint32_t next_id) {
+    if (!c) { set_err("null argument"); return B2_E_INVAL; }
+    int rc = h2_ensure(c); if (rc != B2_OK) return rc;
+    if (conn >= c->h2_max_conns) { set_err("conn out of range"); return B2_E_INVAL; }
+    CU(cudaSetDevice(c->opt.device));
+    k_h2_set_next_stream_id<<<1, 1, 0, c->stream>>>(c->d_h2, conn, next_id);
+    CU(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
 extern "C" int b2_pack_requests(b2_ctx* c, const void* bytes, uint32_t nbytes, const b2_request* reqs, uint32_t n,
                                 void* out, uint32_t out_cap, uint32_t* out_offs, uint32_t* out_lens) {
     if (!c || (!bytes && nbytes) || !reqs || !out || !out_offs || !out_lens) { set_err("null argument"); return B2_E_INVAL; }

@@ -279,6 +279,7 @@ struct H2Conn {
     uint32_t r_header_table_size, r_enable_push, r_max_concurrent_streams, r_stream_window_size, r_max_frame_size, r_max_header_list_size;
     uint32_t l_stream_window_size, l_max_frame_size;
     long long remote_window_left, deferred_window_update;
+    long long last_sent_stream_id; uint32_t preface_sent, pad0;  // client side: H2Context::_last_sent_stream_id (:331); the preface goes out with the first request
     HpackState enc;                                              // HPacker::_encode_table (responses)
 };
 // Pending streams live outside H2Conn so that their number and size are run-time choices (b2_h2_configure): connection i
@@ -294,6 +295,7 @@ __device__ __forceinline__ void h2_conn_init(H2Conn& c, H2Stream* S, uint32_t P)
     c.r_stream_window_size = (uint32_t)kH2MaxWindow; c.r_max_frame_size = 16384; c.r_max_header_list_size = 0xffffffffu;
     c.l_stream_window_size = 256 * 1024; c.l_max_frame_size = 16384;     // H2Settings() defaults, http2.cpp:26-34
     c.remote_window_left = kH2MaxWindow; c.deferred_window_update = 0;
+    c.last_sent_stream_id = 1; c.preface_sent = 0; c.pad0 = 0;
     for (uint32_t i = 0; i < P; i++) S[i].id = -1;
     c.enc.max_size = 4096; c.enc.size = 0; c.enc.count = 0; c.enc.head = 0; c.enc.byte_head = 0;   // _hpacker.Init(header_table_size), :367
 }
@@ -861,5 +863,105 @@ __global__ void __launch_bounds__(kH2PackWarps * 32) k_h2_pack(const uint8_t* by
         __syncwarp();                                                // the shared buffers are reused by the next response
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Client side: H2UnsentRequest::New (:1382-1453, the header list) + AppendAndDestroySelf (:1496-1592) + PackH2Message (:1310-1380).
+// The same split as k_h2_pack: one warp per connection, lane 0 runs the serial part (stream id, windows, HPACK encode against the
+// connection's table) into shared memory, the warp writes the frames.
+constexpr uint32_t kH2ReqFragCap = 2048;
+__global__ void __launch_bounds__(kH2PackWarps * 32) k_h2_pack_req(const uint8_t* bytes, const b2_h2_request* reqs, const uint32_t* group_first, uint32_t n_groups,
+                                                                   H2Conn* conns, uint8_t* out, b2_h2_request_result* results) {
+    __shared__ __align__(16) uint8_t s_buf[kH2PackWarps][2][kH2ReqFragCap];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t g = blockIdx.x * kH2PackWarps + w;
+    if (g >= n_groups) return;
+    uint8_t* frag = s_buf[w][0]; uint8_t* tmp = s_buf[w][1];
+    for (uint32_t i = group_first[g]; i < group_first[g + 1]; i++) {
+        const b2_h2_request R = reqs[i];
+        uint8_t* o0 = out + results[i].out_off; uint8_t* o = o0;
+        const bool grpc = R.flags & B2_H2_REQ_GRPC;
+        const uint32_t data_size = R.body_len + (grpc ? 5u : 0u);
+        uint32_t st = B2_H2_REQ_OK, sid = 0, fl = 0, mfs = 0, cw = 0, pre = 0;
+        if (lane == 0) {
+            H2Conn& c = conns[R.conn];
+            if (!c.preface_sent) { c.preface_sent = 1; pre = 1; }
+            if (c.last_sent_stream_id > 0x7FFFFFFFll) st = B2_H2_REQ_RUNOUT;                      // AllocateClientStreamId
+            else {
+                sid = (uint32_t)c.last_sent_stream_id; c.last_sent_stream_id += 2;
+                // ConsumeWindowSize (:1199-1219) on a stream that starts with the peer's initial window (Init :1176-1181)
+                if (data_size && ((long long)c.r_stream_window_size < (long long)data_size || c.remote_window_left < (long long)data_size)) st = B2_H2_REQ_ELIMIT;
+                else {
+                    c.remote_window_left -= (long long)data_size;
+                    const bool never = c.r_header_table_size == 0;
+                    uint8_t* f = frag;
+                    f = (R.flags & B2_H2_REQ_GET) ? hp_encode(c.enc, f, (const uint8_t*)":method", 7, (const uint8_t*)"GET", 3, never, tmp)
+                                                  : hp_encode(c.enc, f, (const uint8_t*)":method", 7, (const uint8_t*)"POST", 4, never, tmp);
+                    f = (R.flags & B2_H2_REQ_HTTPS) ? hp_encode(c.enc, f, (const uint8_t*)":scheme", 7, (const uint8_t*)"https", 5, never, tmp)
+                                                    : hp_encode(c.enc, f, (const uint8_t*)":scheme", 7, (const uint8_t*)"http", 4, never, tmp);
+                    f = hp_encode(c.enc, f, (const uint8_t*)":path", 5, bytes + R.path_off, R.path_len, never, tmp);
+                    f = hp_encode(c.enc, f, (const uint8_t*)":authority", 10, bytes + R.authority_off, R.authority_len, never, tmp);
+                    if (R.content_type_len) f = hp_encode(c.enc, f, (const uint8_t*)"content-type", 12, bytes + R.content_type_off, R.content_type_len, never, tmp);
+                    if (R.flags & B2_H2_REQ_ACCEPT) f = hp_encode(c.enc, f, (const uint8_t*)"accept", 6, (const uint8_t*)"*/*", 3, never, tmp);
+                    if (R.flags & B2_H2_REQ_USER_AGENT) f = hp_encode(c.enc, f, (const uint8_t*)"user-agent", 10, (const uint8_t*)"brpc/1.0 curl/7.0", 17, never, tmp);
+                    for (uint32_t at = 0; at + 4 <= R.extra_len;) {
+                        const uint8_t* e = bytes + R.extra_off + at;
+                        const uint32_t nl = e[0] | ((uint32_t)e[1] << 8), vl = e[2] | ((uint32_t)e[3] << 8);
+                        if (at + 4 + nl + vl > R.extra_len) break;
+                        f = hp_encode(c.enc, f, e + 4, nl, e + 4 + nl, vl, never, tmp);
+                        at += 4 + nl + vl;
+                    }
+                    fl = (uint32_t)(f - frag); mfs = c.r_max_frame_size;
+                    if (c.deferred_window_update > 0) { cw = (uint32_t)c.deferred_window_update; c.deferred_window_update = 0; }
+                }
+            }
+        }
+        st = __shfl_sync(0xffffffffu, st, 0); sid = __shfl_sync(0xffffffffu, sid, 0); fl = __shfl_sync(0xffffffffu, fl, 0);
+        mfs = __shfl_sync(0xffffffffu, mfs, 0); cw = __shfl_sync(0xffffffffu, cw, 0); pre = __shfl_sync(0xffffffffu, pre, 0);
+        __syncwarp();
+        if (pre) {                                                   // preface + SerializeH2SettingsFrameAndWU(default client settings) (:1508-1526)
+            if (lane < 24) o[lane] = (uint8_t)"PRI * HTTP/2.0\r\n\r\nSM\r\n\r\n"[lane];
+            if (lane == 0) {
+                uint8_t* p = o + 24;
+                h2_put_head(p, 12, 4, 0, 0);
+                p[9] = 0; p[10] = 2; put_be32(p + 11, 0);
+                p[15] = 0; p[16] = 4; put_be32(p + 17, 256u * 1024u);
+                h2_put_head(p + 21, 4, 8, 0, 0); put_be32(p + 30, 1024u * 1024u - 65535u);
+            }
+            o += 58;
+        }
+        if (st != B2_H2_REQ_OK) {
+            if (lane == 0) { results[i].status = (int32_t)st; results[i].stream_id = sid; results[i].out_len = (uint32_t)(o - o0); }
+            __syncwarp();
+            continue;
+        }
+        const uint8_t hflags = data_size == 0 ? 0x1 : 0;
+        if (fl <= mfs) {
+            if (lane == 0) h2_put_head(o, fl, 1, hflags | 0x4, sid);
+            for (uint32_t k = lane; k < fl; k += 32) o[9 + k] = frag[k];
+            o += 9 + fl;
+        } else {                                                     // (kH2ReqFragCap < 16384 <= max_frame_size: kept for the shape)
+            if (lane == 0) {
+                uint8_t* q = o;
+                h2_put_head(q, mfs, 1, hflags, sid); q += 9; for (uint32_t k = 0; k < mfs; k++) *q++ = frag[k];
+                for (uint32_t at = mfs; at < fl;) { const uint32_t nn = min(fl - at, mfs); h2_put_head(q, nn, 9, at + nn == fl ? 0x4 : 0, sid); q += 9; for (uint32_t k = 0; k < nn; k++) *q++ = frag[at + k]; at += nn; }
+            }
+            o += fl + 9 * ((fl + mfs - 1) / mfs);
+        }
+        const uint8_t* body = bytes + R.body_off;
+        for (uint32_t at = 0; at < data_size;) {
+            const uint32_t nn = min(data_size - at, mfs);
+            if (lane == 0) h2_put_head(o, nn, 0, at + nn == data_size ? 0x1 : 0, sid);
+            o += 9;
+            uint32_t k = 0;
+            if (grpc && at < 5) { k = min(nn, 5u - at); if (lane < k) { const uint32_t q = at + lane; o[lane] = q == 0 ? 0 : (uint8_t)(R.body_len >> (8 * (4 - q))); } }   // AddGrpcPrefix
+            warp_copy(o + k, body + (at + k - (grpc ? 5u : 0u)), nn - k, lane);
+            o += nn; at += nn;
+        }
+        if (cw) { if (lane == 0) { h2_put_head(o, 4, 8, 0, 0); put_be32(o + 9, cw); } o += 13; }
+        if (lane == 0) { results[i].status = B2_H2_REQ_OK; results[i].stream_id = sid; results[i].out_len = (uint32_t)(o - o0); }
+        __syncwarp();                                                // the shared buffers are reused by the next request
+    }
+}
+__global__ void k_h2_set_next_stream_id(H2Conn* conns, uint32_t conn, uint32_t next_id) { conns[conn].last_sent_stream_id = next_id; }
 #endif
 }  // namespace b2
