@@ -1288,6 +1288,21 @@ extern "C" int b2_h2_pack_requests(b2_ctx* c, const void* bytes, uint32_t nbytes
     c->uploaded = false; c->executed = false;
     return B2_OK;
 }
+extern "C" int b2_h2_conn_peer_update(b2_ctx* c, uint32_t conn, const b2_h2_peer_update* u) {
+    if (!c || !u) { set_err("null argument"); return B2_E_INVAL; }
+    static_assert(sizeof(b2_h2_peer_update) == 24, "peer update ABI layout");
+    if ((u->set & B2_H2_PEER_MAX_FRAME_SIZE) && (u->max_frame_size < 16384u || u->max_frame_size > 16777215u)) { set_err("max_frame_size out of range"); return B2_E_INVAL; }   // ParseH2Settings :166-211
+    if ((u->set & B2_H2_PEER_STREAM_WINDOW) && u->stream_window_size > 0x7fffffffu) { set_err("stream_window_size out of range"); return B2_E_INVAL; }
+    int rc = h2_ensure(c); if (rc != B2_OK) return rc;
+    if (conn >= c->h2_max_conns) { set_err("conn out of range"); return B2_E_INVAL; }
+    CU(cudaSetDevice(c->opt.device));
+    int* d_rc = reinterpret_cast<int*>(c->d_slot); int h_rc = 0;
+    k_h2_peer_update<<<1, 1, 0, c->stream>>>(c->d_h2, conn, *u, d_rc);
+    CU(cudaMemcpyAsync(&h_rc, d_rc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (h_rc != 0) { set_err("connection window would pass 2^31 - 1 (FLOW_CONTROL_ERROR)"); return B2_E_INVAL; }
+    return B2_OK;
+}
 extern "C" int b2_h2_conn_set_next_stream_id(b2_ctx* c, uint32_t conn, uint32_t next_id) {
     if (!c) { set_err("null argument"); return B2_E_INVAL; }
     int rc = h2_ensure(c); if (rc != B2_OK) return rc;

@@ -962,6 +962,18 @@ __global__ void __launch_bounds__(kH2PackWarps * 32) k_h2_pack_req(const uint8_t
         __syncwarp();                                                // the shared buffers are reused by the next request
     }
 }
+// b2_h2_conn_peer_update: OnSettings' effect on _remote_settings (:848-915) and OnWindowUpdate on stream 0 (:1006-1041), mirrored by the host
+__global__ void k_h2_peer_update(H2Conn* conns, uint32_t conn, b2_h2_peer_update u, int* rc) {
+    H2Conn& c = conns[conn];
+    *rc = 0;
+    if (u.set & B2_H2_PEER_HEADER_TABLE_SIZE) c.r_header_table_size = u.header_table_size;
+    if (u.set & B2_H2_PEER_MAX_FRAME_SIZE) c.r_max_frame_size = u.max_frame_size;
+    if (u.set & B2_H2_PEER_STREAM_WINDOW) c.r_stream_window_size = u.stream_window_size;
+    if (u.set & B2_H2_PEER_CONN_WINDOW_ADD) {
+        if (u.conn_window_add < 0) c.remote_window_left += u.conn_window_add;
+        else if (!h2_add_window(c.remote_window_left, u.conn_window_add)) *rc = -1;
+    }
+}
 __global__ void k_h2_set_next_stream_id(H2Conn* conns, uint32_t conn, uint32_t next_id) { conns[conn].last_sent_stream_id = next_id; }
 #endif
 }  // namespace b2

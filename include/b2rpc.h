@@ -603,8 +603,10 @@ int  b2_h2_pack_responses(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const
  *     deferred connection WINDOW_UPDATE; B2_H2_REQ_GRPC prepends AddGrpcPrefix's 5 bytes (policy/http_rpc_protocol.cpp:254-262).
  * `extra` headers: records {u16 name_len, u16 value_len (little endian), name, value} back to back at extra_off, extra_len bytes.
  * The pending-stream count against max_concurrent_streams (:1529) and GOAWAY (TryToInsertStream :425-436) belong to the
- * caller's correlation map, not to this call.  The peer's settings / WINDOW_UPDATEs reach the state through
- * b2_h2_process_batch runs of that connection.  Requests of one connection must be adjacent and in write order. */
+ * caller's correlation map, not to this call.  NOT built: the receiving half of a client connection (ParseH2Message on a socket
+ * created by connect -> H2StreamContext::OnEndStream :823-846 -> ProcessHttpResponse) — the host's H2Context keeps parsing the
+ * server's frames and mirrors what they change into the device's connection with b2_h2_conn_peer_update.  Requests of one
+ * connection must be adjacent and in write order. */
 #define B2_H2_REQ_GRPC       1u
 #define B2_H2_REQ_GET        2u     /* :method GET instead of POST */
 #define B2_H2_REQ_HTTPS      4u     /* :scheme https */
@@ -624,6 +626,19 @@ typedef struct b2_h2_request {
 typedef struct b2_h2_request_result { int32_t status; uint32_t stream_id, out_off, out_len; } b2_h2_request_result;   /* 16 bytes */
 int  b2_h2_pack_requests(b2_ctx* ctx, const void* bytes, uint32_t nbytes, const b2_h2_request* reqs, uint32_t n,
                          void* out, uint32_t out_cap, b2_h2_request_result* results);
+/* What the peer's frames change in the state b2_h2_pack_requests / b2_h2_pack_responses read, for a connection whose frames the HOST
+ * parses: H2Context::OnSettings (:848-915: _remote_settings; the first SETTINGS also takes MAX_WINDOW_SIZE - 65535 off the connection
+ * window — pass it as a negative conn_window_add) and OnWindowUpdate on stream 0 (:1006-1041: AddWindowSize, B2_E_INVAL when the
+ * window would pass 2^31 - 1 — FLOW_CONTROL_ERROR there).  Fields are applied when their bit is set in `set`. */
+#define B2_H2_PEER_HEADER_TABLE_SIZE 1u
+#define B2_H2_PEER_MAX_FRAME_SIZE    2u
+#define B2_H2_PEER_STREAM_WINDOW     4u
+#define B2_H2_PEER_CONN_WINDOW_ADD   8u
+typedef struct b2_h2_peer_update {
+    uint32_t set, header_table_size, max_frame_size, stream_window_size;
+    int64_t  conn_window_add;
+} b2_h2_peer_update;                                 /* 24 bytes */
+int  b2_h2_conn_peer_update(b2_ctx* ctx, uint32_t conn, const b2_h2_peer_update* u);
 /* the reference's own unit-test hook (:348-352: its tests start 10 000 ids before the end of the id space): the next client stream id */
 int  b2_h2_conn_set_next_stream_id(b2_ctx* ctx, uint32_t conn, uint32_t next_id);
 

@@ -159,6 +159,7 @@ uint32_t orc_h2_pack_response(orc_h2_conn* c, const b2_h2_response* r, const uin
 /* client side: H2UnsentRequest::New + AppendAndDestroySelf (http2_rpc_protocol.cpp:1382-1592); returns B2_H2_REQ_* */
 int32_t orc_h2_pack_request(orc_h2_conn* c, const b2_h2_request* r, const uint8_t* bytes, uint8_t* out, uint32_t* out_len, uint32_t* stream_id);
 void orc_h2_conn_set_next_stream_id(orc_h2_conn* c, uint32_t id);
+int orc_h2_conn_peer_update(orc_h2_conn* c, const b2_h2_peer_update* u);
 uint32_t orc_h2_scan(const uint8_t* in, uint32_t n, uint32_t max_frame_size, orc_h2_frame* frames, uint32_t cap,
                      uint32_t* consumed, uint32_t* err);
 /* SendRpcResponse (baidu_rpc_protocol.cpp:273-460) for a reply the host produced: the checker of b2_pack_responses.

@@ -562,3 +562,15 @@ int32_t orc_h2_pack_request(orc_h2_conn* c, const b2_h2_request* R, const uint8_
     *out_len = (uint32_t)(o - out);
     return B2_H2_REQ_OK;
 }
+
+/* the peer's SETTINGS / connection WINDOW_UPDATE as the host's parser mirrors them (OnSettings :848-915, OnWindowUpdate :1006-1041) */
+int orc_h2_conn_peer_update(orc_h2_conn* c, const b2_h2_peer_update* u) {
+    if (u->set & B2_H2_PEER_HEADER_TABLE_SIZE) c->r_header_table_size = u->header_table_size;
+    if (u->set & B2_H2_PEER_MAX_FRAME_SIZE) { if (u->max_frame_size < 16384u || u->max_frame_size > 16777215u) return -1; c->r_max_frame_size = u->max_frame_size; }
+    if (u->set & B2_H2_PEER_STREAM_WINDOW) { if (u->stream_window_size > (uint32_t)MAX_WINDOW) return -1; c->r_stream_window_size = u->stream_window_size; }
+    if (u->set & B2_H2_PEER_CONN_WINDOW_ADD) {
+        if (u->conn_window_add < 0) c->remote_window_left += u->conn_window_add;        /* the first SETTINGS: a plain subtraction (:884) */
+        else if (!add_window(&c->remote_window_left, u->conn_window_add)) return -1;
+    }
+    return 0;
+}

@@ -250,6 +250,8 @@ H2_REQUEST_DT = np.dtype([("conn", "<u4"), ("flags", "<u4"), ("path_off", "<u4")
 lib.orc_h2_pack_request.restype = C.c_int32
 lib.orc_h2_pack_request.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
 lib.orc_h2_conn_set_next_stream_id.argtypes = [C.c_void_p, C.c_uint32]
+lib.orc_h2_conn_peer_update.argtypes = [C.c_void_p, C.c_void_p]
+H2_PEER_UPDATE_DT = np.dtype([("set", "<u4"), ("header_table_size", "<u4"), ("max_frame_size", "<u4"), ("stream_window_size", "<u4"), ("conn_window_add", "<i8")])
 lib.orc_h2_conn_new.restype = C.c_void_p
 lib.orc_h2_conn_free.argtypes = [C.c_void_p]
 lib.orc_h2_consume.restype = C.c_uint32
@@ -303,6 +305,12 @@ class H2Conn:
         out = np.zeros(len(body) * 2 + 8192, np.uint8); ol, sid = C.c_uint32(), C.c_uint32()
         st = lib.orc_h2_pack_request(self._h, r.ctypes.data, blob, out.ctypes.data, C.byref(ol), C.byref(sid))
         return st, sid.value, out[:ol.value].tobytes()
+
+    def peer_update(self, header_table_size=None, max_frame_size=None, stream_window_size=None, conn_window_add=None):
+        u = np.zeros(1, H2_PEER_UPDATE_DT)
+        vals = (header_table_size, max_frame_size, stream_window_size, conn_window_add)
+        u[0] = (sum(1 << i for i, v in enumerate(vals) if v is not None), *(0 if v is None else v for v in vals))
+        return lib.orc_h2_conn_peer_update(self._h, u.ctypes.data)
 
     def set_next_stream_id(self, sid):
         lib.orc_h2_conn_set_next_stream_id(self._h, sid)

@@ -1,8 +1,8 @@
 """GPU: the client side of h2 (b2_h2_pack_requests = H2UnsentRequest::New + AppendAndDestroySelf + PackH2Message) against the oracle
 (pinned by a real grpcio server, tests/test_oracle_h2_client_grpcio.py): preface + settings with the first request, stream ids, HPACK
 encoder state across batches (names and whole headers indexed as they repeat, eviction with long values), DATA split at the peer's
-max_frame_size after the peer's SETTINGS went through b2_h2_process_batch, never-indexed headers for header_table_size 0, flow
-control (ELIMIT), id exhaustion (EH2RUNOUTSTREAMS)."""
+max_frame_size after b2_h2_conn_peer_update, never-indexed headers for header_table_size 0, flow control (ELIMIT), id exhaustion
+(EH2RUNOUTSTREAMS)."""
 import random
 
 import numpy as np
@@ -56,33 +56,40 @@ def test_h2_client_requests_packed_on_the_device():
 
 
 def test_h2_client_requests_follow_the_peers_settings_and_windows():
-    """The peer's SETTINGS / WINDOW_UPDATE reach the connection through b2_h2_process_batch; what the client packs afterwards follows
-    them: max_frame_size 20000, header_table_size 0 (never indexed), a small stream window (ELIMIT)."""
+    """The host parses the server's frames (the receiving half of a client connection is not on the device) and mirrors SETTINGS /
+    WINDOW_UPDATE with b2_h2_conn_peer_update; what the client packs afterwards follows them: max_frame_size 20000, header_table_size 0
+    (never indexed), a small stream window and a drained connection window (ELIMIT), updates between batches."""
     import brpc_b200
-    import _h2traffic as T
     from brpc_b200.abi import H2_REQUEST_DT
     rng = random.Random(SEED + 1)
     ctx = _ctx()
-    peers = [((5, 20000),), ((1, 0),), ((4, 1000),), ((5, 70000), (4, 1 << 20))]
+    first = -(0x7fffffff - 65535)                                  # OnSettings, first SETTINGS frame (:884)
+    peers = [dict(max_frame_size=20000, conn_window_add=first), dict(header_table_size=0, conn_window_add=first),
+             dict(stream_window_size=1000, conn_window_add=first), dict(max_frame_size=70000, stream_window_size=1 << 20, conn_window_add=first), {}]
     orc = [O.H2Conn() for _ in peers]
-    streams = [T.PREFACE + T.settings(p) for p in peers]          # (fed as a server-side connection: the state both sides share)
-    for i in range(len(peers)):
+    for i, p in enumerate(peers):
         ctx.h2_conn_reset(i)
-    data, runs = brpc_b200.make_runs(streams)
-    rs, msgs, out = ctx.h2_process_batch(data, runs)
-    for i, s in enumerate(streams):
-        e, cons, *_ = orc[i].consume(s)
-        assert e == int(rs[i]["parse_error"]) and cons == len(s)
-    n_elimit = 0
-    for rnd in range(4):
+        if p:
+            ctx.h2_conn_peer_update(i, **p); assert orc[i].peer_update(**p) == 0
+    n_elimit = 0; n_ok = 0
+    for rnd in range(6):
         calls = [_call(rng, i) for i in range(len(peers)) for _ in range(5)]
         blob, reqs = O.h2_request_blob(calls)
         res, got = ctx.h2_pack_requests(np.frombuffer(blob, np.uint8), reqs.astype(H2_REQUEST_DT))
         for k, c in enumerate(calls):
             st, sid, want = orc[c[0]].pack_request(c[2], c[3], c[5], content_type=c[4], flags=c[1], extra=c[6])
             assert (int(res[k]["status"]), int(res[k]["stream_id"]), got[k]) == (st, sid, want), (rnd, k)
-            n_elimit += st == 1
-    assert n_elimit > 0
+            n_elimit += st == 1; n_ok += st == 0
+        if rnd == 2:                                               # the peer opens its windows / changes its mind between batches
+            for i in (0, 2, 3):
+                u = dict(conn_window_add=rng.randrange(1, 1 << 20), stream_window_size=65535 + 1000 * i, header_table_size=256 * i)
+                ctx.h2_conn_peer_update(i, **u); assert orc[i].peer_update(**u) == 0
+    assert n_elimit > 10 and n_ok > 60
+    # AddWindowSize past 2^31 - 1 is FLOW_CONTROL_ERROR in OnWindowUpdate; out-of-range settings are what ParseH2Settings refuses
+    for bad in (dict(conn_window_add=0x7fffffff), dict(max_frame_size=16383), dict(max_frame_size=1 << 24), dict(stream_window_size=1 << 31)):
+        with pytest.raises(brpc_b200.B2Error):
+            ctx.h2_conn_peer_update(4, **bad)
+        assert orc[4].peer_update(**bad) == -1
 
 
 def test_h2_client_stream_ids_run_out():

@@ -38,8 +38,27 @@ def _server():
 
 class FrameReader:
     """Splits the server's bytes into h2 frames; answers SETTINGS / PING like a client must so that the server keeps going."""
-    def __init__(self, sock):
-        self.s = sock; self.buf = b""; self.hp = O.HpackDecoder() if hasattr(O, "HpackDecoder") else None
+    def __init__(self, sock, conn=None):
+        self.s = sock; self.buf = b""; self.conn = conn; self.first = True; self.mirrored = []
+
+    def mirror(self, ftype, flags, sid, payload):
+        """What the host's H2Context would hand to b2_h2_conn_peer_update: the server's SETTINGS and connection WINDOW_UPDATEs."""
+        if self.conn is None:
+            return
+        if ftype == 4 and not (flags & 1):
+            u = {}
+            for k in range(0, len(payload), 6):
+                ident, v = int.from_bytes(payload[k:k + 2], "big"), int.from_bytes(payload[k + 2:k + 6], "big")
+                name = {1: "header_table_size", 4: "stream_window_size", 5: "max_frame_size"}.get(ident)
+                if name:
+                    u[name] = v
+            if self.first:
+                u["conn_window_add"] = -(0x7fffffff - 65535); self.first = False
+            if u:
+                assert self.conn.peer_update(**u) == 0; self.mirrored.append(u)
+        elif ftype == 8 and sid == 0:
+            u = dict(conn_window_add=int.from_bytes(payload, "big") & 0x7fffffff)
+            assert self.conn.peer_update(**u) == 0; self.mirrored.append(u)
 
     def frames(self, until):
         while not until():
@@ -53,6 +72,7 @@ class FrameReader:
                     self.s.sendall(b"\0\0\0\x04\x01\0\0\0\0")              # SETTINGS ack
                 if f[0] == 6 and not (f[1] & 1):
                     self.s.sendall(b"\0\0\x08\x06\x01\0\0\0\0" + f[3])       # PING ack
+                self.mirror(*f)
                 yield f
                 if until():
                     return
@@ -62,9 +82,9 @@ class FrameReader:
             self.buf += d
 
 
-def _run_calls(conn, sock, calls, window_updates=True):
+def _run_calls(conn, sock, calls, window_updates=True, rd=None):
     """Sends every call through the oracle's client side, collects {stream: [DATA bytes, ended]} from the server."""
-    rd = FrameReader(sock)
+    rd = rd or FrameReader(sock)
     got = {}; bad = []; sent = []
 
     def done():
@@ -137,3 +157,26 @@ def test_oracle_client_stream_ids_run_out_and_windows():
             break
         n_ok += 1
     assert n_ok == 2047                                                          # floor((2^31 - 1) / 2^20)
+
+
+def test_oracle_client_follows_the_servers_settings():
+    """The same, with the server's SETTINGS and connection WINDOW_UPDATEs mirrored into the oracle's connection (what a host-side parser
+    hands to b2_h2_conn_peer_update): bodies beyond the server's initial 65535-byte windows wait for nothing here because C-core opens
+    its windows at once; a body larger than the stream window is refused with ELIMIT instead of being sent."""
+    srv, port, h = _server()
+    try:
+        conn = O.H2Conn()
+        with socket.create_connection(("127.0.0.1", port)) as s:
+            s.settimeout(20)
+            rd = FrameReader(s, conn)
+            sent, got = _run_calls(conn, s, [(b"/example.EchoService/Echo", b"first", GRPC_EXTRA)], rd=rd)
+            assert rd.mirrored and "conn_window_add" in rd.mirrored[0]           # the server's SETTINGS came with the first reply
+            bodies = [bytes([65 + i % 26]) * n for i, n in enumerate([10, 30000, 16384, 100, 50000, 0, 7])]
+            s2, g2 = _run_calls(conn, s, [(b"/example.EchoService/Echo", b, GRPC_EXTRA) for b in bodies], rd=rd)
+            for sid, body in zip(s2, bodies):
+                assert g2[sid] == [b"\0" + len(body).to_bytes(4, "big") + body, True]
+            assert conn.peer_update(stream_window_size=1000) == 0                 # (as if the server had shrunk its stream windows)
+            st, sid, b = conn.pack_request(b"/example.EchoService/Echo", b"127.0.0.1:1", bytes(2000), extra=GRPC_EXTRA)
+            assert st == 1 and b == b""                                          # refused with ELIMIT instead of being sent
+    finally:
+        srv.stop(0)
