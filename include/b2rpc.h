@@ -21,7 +21,8 @@
  * (b2_set_protocols: hulu_pbrpc / sofa_pbrpc / nshead framing; rpc_dump files as a source), leaf codecs with the reference's signatures
  * (CRC32C, snappy), the client mirror (b2_pack_requests), replies the host produced (b2_pack_responses = SendRpcResponse), and the
  * h2/gRPC server path (b2_h2_process_batch = ParseH2Message, b2_h2_pack_responses = H2UnsentResponse + PackH2Message) whose
- * per-connection state lives on the device between calls.
+ * per-connection state lives on the device between calls, and the sending half of h2 client connections (b2_h2_pack_requests =
+ * H2UnsentRequest::New + AppendAndDestroySelf; b2_h2_conn_peer_update mirrors the peer's SETTINGS / WINDOW_UPDATE).
  */
 #ifndef B2RPC_H_
 #define B2RPC_H_
